@@ -1,0 +1,22 @@
+"""esr_nerf_b200 — B200-native (sm_100a) render hot path of ESR-NeRF behind the reference's own
+render-function signatures.  See DESIGN.md / INTEGRATION.md.
+
+Public surface (mirrors the reference names):
+    VoxurfF                               <- app.fine.model.VoxurfF
+    render_utils.render_utils_cuda.*      <- app/utils/base/cuda/render_utils.cpp (live entries)
+    render_utils.total_variation_cuda.*   <- app/utils/base/cuda/total_variation.cpp
+    render_utils.segment_coo              <- torch_scatter.segment_coo(reduce="sum")
+    render_utils.Alphas2Weights           <- app/utils/base/module.py:117-143
+"""
+from . import _lib  # noqa: F401
+from ._lib import EsrError, build  # noqa: F401
+
+
+def __getattr__(name):  # lazy: importing the package must work on a box without a GPU
+    if name == "VoxurfF":
+        from .voxurff import VoxurfF
+        return VoxurfF
+    if name in ("render_utils", "fused", "modules", "synthetic", "voxurff"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

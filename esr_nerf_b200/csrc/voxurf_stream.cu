@@ -1,0 +1,311 @@
+// voxurf_stream.cu — ray-ordered stages of the fused render path: march (AABB + MaskCache + SDF tap),
+// NeuS alpha + transmittance scan + the two threshold compactions, and their backward.
+// One warp owns one ray slot: candidate steps / stream samples are processed 32 at a time so every
+// global access of a warp is a contiguous run; compaction is ballot + popc, no atomics, and the
+// stream order equals the reference's (ray-major, step-minor) order.
+#include "common.cuh"
+
+using namespace esr;
+
+static inline unsigned ray_blocks(int64_t n_rays) {
+  const int64_t want = (n_rays + 7) / 8;  // 8 warps per block, one warp per ray
+  const int64_t cap = (int64_t)num_sms() * 64;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage A/B: march
+// ---------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+    k_march(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+            const float *__restrict__ rays_d, const int32_t *__restrict__ ray_order, int64_t n_rays,
+            const float *__restrict__ mask_density, const float *__restrict__ sdf_grid,
+            int32_t *__restrict__ n_steps, int32_t *__restrict__ cnt_inbox, int32_t *__restrict__ cnt_mask,
+            const int32_t *__restrict__ off_mask, int32_t *__restrict__ s_ray, int32_t *__restrict__ s_step,
+            float *__restrict__ s_sdf) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = lane_id();
+  const unsigned lt = lanemask_lt();
+  for (int64_t slot = warp; slot < n_rays; slot += nwarps) {
+    const int r = ray_order ? ray_order[slot] : (int)slot;
+    const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
+    const int base = FILL ? off_mask[slot] : 0;
+    int c_in = 0, c_mask = 0;
+    for (int k0 = 0; k0 < s.n; k0 += 32) {
+      const int k = k0 + (int)lane;
+      float px, py, pz;
+      ray_point(s, sc.stepdist, k, px, py, pz);
+      const bool inb = (k < s.n) && !out_bbox(sc.xyz_min, sc.xyz_max, px, py, pz);
+      const bool keep = inb && mask_keep(sc, mask_density, px, py, pz);
+      const unsigned bal = __ballot_sync(FULL, keep);
+      if (FILL) {
+        if (keep) {
+          const int pos = base + c_mask + __popc(bal & lt);
+          s_ray[pos] = r;
+          s_step[pos] = k;
+          s_sdf[pos] = tap1_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz);
+        }
+      } else {
+        c_in += __popc(__ballot_sync(FULL, inb));
+      }
+      c_mask += __popc(bal);
+    }
+    if (!FILL && lane == 0) {
+      n_steps[slot] = s.n;
+      cnt_inbox[slot] = c_in;
+      cnt_mask[slot] = c_mask;
+    }
+  }
+}
+
+static int check_scene(const esr_scene_t *sc) {
+  ESR_CHECK_ARG(sc != nullptr);
+  ESR_CHECK_ARG(sc->gx > 0 && sc->gy > 0 && sc->gz > 0 && sc->mx > 0 && sc->my > 0 && sc->mz > 0);
+  ESR_CHECK_ARG(sc->stepdist > 0.f && sc->voxel_size > 0.f);
+  return ESR_OK;
+}
+
+extern "C" int esr_march_count(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                               const int32_t *ray_order, int64_t n_rays, const float *mask_density, int32_t *n_steps,
+                               int32_t *cnt_inbox, int32_t *cnt_mask, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
+  if (n_rays == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && mask_density && n_steps && cnt_inbox && cnt_mask);
+  k_march<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
+                                                                       mask_density, nullptr, n_steps, cnt_inbox,
+                                                                       cnt_mask, nullptr, nullptr, nullptr, nullptr);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                              const int32_t *ray_order, int64_t n_rays, const float *mask_density,
+                              const float *sdf_grid, const int32_t *off_mask, int32_t *s_ray, int32_t *s_step,
+                              float *s_sdf, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
+  if (n_rays == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && mask_density && sdf_grid && off_mask && s_ray && s_step && s_sdf);
+  k_march<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
+                                                                      mask_density, sdf_grid, nullptr, nullptr,
+                                                                      nullptr, off_mask, s_ray, s_step, s_sdf);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage C/D: NeuS alpha -> alpha filter -> exact sequential transmittance -> weight filter
+// ---------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+    k_alpha_scan(const __grid_constant__ esr_scene_t sc, const int32_t *__restrict__ ray_order, int64_t n_rays,
+                 const int32_t *__restrict__ off_mask, const int32_t *__restrict__ s_step,
+                 const float *__restrict__ s_sdf, const int32_t *__restrict__ off_shade,
+                 int32_t *__restrict__ cnt_shade, float *__restrict__ alphainv_last, float *__restrict__ s_alpha,
+                 float *__restrict__ s_T, int32_t *__restrict__ h_ray, int32_t *__restrict__ h_step,
+                 int32_t *__restrict__ h_m1, float *__restrict__ h_w, float *__restrict__ h_sdf) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = lane_id();
+  const unsigned lt = lanemask_lt();
+  for (int64_t slot = warp; slot < n_rays; slot += nwarps) {
+    const int r = ray_order ? ray_order[slot] : (int)slot;
+    const int s = off_mask[slot], e = off_mask[slot + 1];
+    const int out_base = FILL ? off_shade[slot] : 0;
+    float Tc = 1.f;
+    bool done = false;
+    int n_shade = 0;
+    for (int base = s; base < e; base += 32) {
+      const int i = base + (int)lane;
+      const bool valid = i < e;
+      float a = 0.f, sd = 0.f;
+      if (valid) {
+        sd = __ldg(s_sdf + i);
+        const bool has_prev = i > s, has_next = i + 1 < e;
+        const float sp = has_prev ? __ldg(s_sdf + i - 1) : 0.f;
+        const float sn = has_next ? __ldg(s_sdf + i + 1) : 0.f;
+        float pc, nc;
+        a = neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+      }
+      const bool f0 = valid && (a > sc.fast_thres);  // voxurff.py:201
+      float myT = -1.f, myW = 0.f;
+      unsigned m = __ballot_sync(FULL, f0);
+      // kernel.cu:591-601 replayed in order over the surviving samples (uniform across the warp)
+      while (m && !done) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const float aj = __shfl_sync(FULL, a, j);
+        if ((int)lane == j) {
+          myT = Tc;
+          myW = __fmul_rn(Tc, aj);
+        }
+        Tc = (float)((1. - (double)aj) * (double)Tc);
+        if ((double)Tc < 1e-3) done = true;
+      }
+      const bool f1 = (myT >= 0.f) && (myW > sc.fast_thres);  // voxurff.py:209
+      const unsigned b1 = __ballot_sync(FULL, f1);
+      if (FILL) {
+        if (valid) {
+          s_alpha[i] = a;
+          s_T[i] = myT;
+        }
+        if (f1) {
+          const int pos = out_base + n_shade + __popc(b1 & lt);
+          h_ray[pos] = r;
+          h_step[pos] = __ldg(s_step + i);
+          h_m1[pos] = i;
+          h_w[pos] = myW;
+          h_sdf[pos] = sd;
+        }
+      }
+      n_shade += __popc(b1);
+    }
+    if (!FILL && lane == 0) {
+      cnt_shade[slot] = n_shade;
+      alphainv_last[r] = Tc;
+    }
+  }
+}
+
+extern "C" int esr_alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
+                                    const int32_t *off_mask, const float *s_sdf, int32_t *cnt_shade,
+                                    float *alphainv_last, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
+  if (n_rays == 0) return ESR_OK;
+  ESR_CHECK_ARG(off_mask && cnt_shade && alphainv_last);
+  k_alpha_scan<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(
+      *sc, ray_order, n_rays, off_mask, nullptr, s_sdf, nullptr, cnt_shade, alphainv_last, nullptr, nullptr, nullptr,
+      nullptr, nullptr, nullptr, nullptr);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_alpha_scan_fill(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
+                                   const int32_t *off_mask, const int32_t *s_step, const float *s_sdf,
+                                   const int32_t *off_shade, float *s_alpha, float *s_T, int32_t *h_ray,
+                                   int32_t *h_step, int32_t *h_m1, float *h_w, float *h_sdf, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
+  if (n_rays == 0) return ESR_OK;
+  ESR_CHECK_ARG(off_mask && s_step && off_shade && s_alpha && s_T && h_ray && h_step && h_m1 && h_w && h_sdf);
+  k_alpha_scan<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(
+      *sc, ray_order, n_rays, off_mask, s_step, s_sdf, off_shade, nullptr, nullptr, s_alpha, s_T, h_ray, h_step, h_m1,
+      h_w, h_sdf);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage C': backward.  (1) per ray, chunks in reverse: Alphas2Weights backward as a warp suffix scan,
+// then d(alpha)/d(prev_est, next_est); (2) per M1 sample: fold neighbour terms and scatter into the
+// dense SDF gradient volume with the forward trilinear weights.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_alpha_scan_bwd(const __grid_constant__ esr_scene_t sc, const int32_t *__restrict__ ray_order, int64_t n_rays,
+                     const int32_t *__restrict__ off_mask, const float *__restrict__ s_sdf,
+                     const float *__restrict__ s_alpha, const float *__restrict__ s_T,
+                     const float *__restrict__ alphainv_last, const float *__restrict__ g_w_m1,
+                     const float *__restrict__ g_last, float *__restrict__ dprev, float *__restrict__ dnext) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = lane_id();
+  for (int64_t slot = warp; slot < n_rays; slot += nwarps) {
+    const int r = ray_order ? ray_order[slot] : (int)slot;
+    const int s = off_mask[slot], e = off_mask[slot + 1];
+    float carry = g_last ? g_last[r] * alphainv_last[r] : 0.f;
+    for (int hi = e; hi > s; hi -= 32) {
+      const int i = hi - 1 - (int)lane;
+      const bool valid = i >= s;
+      float a = 0.f, Ti = -1.f, gw = 0.f;
+      if (valid) {
+        a = s_alpha[i];
+        Ti = s_T[i];
+        gw = g_w_m1[i];
+      }
+      const bool proc = valid && Ti >= 0.f;
+      const float x = proc ? gw * (Ti * a) : 0.f;
+      float inc = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(FULL, inc, o);
+        if (lane >= (unsigned)o) inc += u;
+      }
+      const float back_cum = carry + (inc - x);
+      carry += __shfl_sync(FULL, inc, 31);
+      if (!valid) continue;
+      float dp = 0.f, dn = 0.f;
+      if (proc) {
+        const float ga = (float)((double)(gw * Ti) - (double)back_cum / ((double)(1.f - a) + 1e-10));
+        if (ga != 0.f) {
+          const float sd = s_sdf[i];
+          const bool has_prev = i > s, has_next = i + 1 < e;
+          const float sp = has_prev ? s_sdf[i - 1] : 0.f;
+          const float sn = has_next ? s_sdf[i + 1] : 0.f;
+          float pc, nc;
+          neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+          const float q = pc - nc;
+          const float num = fmaxf(q, 0.f) + 1e-5f, den = pc + 1e-5f;
+          const float rr = num / den;
+          if (rr >= 0.f && rr <= 1.f) {  // clamp passes gradient on the closed interval
+            const float inv = 1.f / den;
+            const float relu_g = q > 0.f ? 1.f : 0.f;
+            const float d_pc = ga * (relu_g * inv - num * inv * inv);
+            const float d_nc = ga * (-relu_g * inv);
+            dp = d_pc * pc * (1.f - pc) * sc.s_val;
+            dn = d_nc * nc * (1.f - nc) * sc.s_val;
+          }
+        }
+      }
+      dprev[i] = dp;
+      dnext[i] = dn;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_sdf_scatter(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                  const float *__restrict__ rays_d, const int32_t *__restrict__ s_ray,
+                  const int32_t *__restrict__ s_step, const float *__restrict__ dprev,
+                  const float *__restrict__ dnext, int64_t m1, float *__restrict__ grad_sdf) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m1) return;
+  const int r = s_ray[i];
+  const bool has_prev = i > 0 && s_ray[i - 1] == r;
+  const bool has_next = i + 1 < m1 && s_ray[i + 1] == r;
+  float g = (has_prev ? 0.5f : 1.f) * dprev[i] + (has_next ? 0.5f : 1.f) * dnext[i];
+  if (has_prev) g += 0.5f * dnext[i - 1];
+  if (has_next) g += 0.5f * dprev[i + 1];
+  if (g == 0.f) return;
+  const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
+  float px, py, pz;
+  ray_point(s, sc.stepdist, s_step[i], px, py, pz);
+  const Cell c = make_cell(world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx),
+                           world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy),
+                           world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz));
+  scatter1(grad_sdf, sc.gx, sc.gy, sc.gz, c, g);
+}
+
+extern "C" int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                  const int32_t *ray_order, int64_t n_rays, const int32_t *off_mask,
+                                  const int32_t *s_ray, const int32_t *s_step, const float *s_sdf,
+                                  const float *s_alpha, const float *s_T, const float *alphainv_last,
+                                  const float *g_w_m1, const float *g_last, float *tmp_dprev, float *tmp_dnext,
+                                  int64_t m1, float *grad_sdf_grid, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && m1 >= 0 && m1 < (1ll << 31));
+  if (n_rays == 0 || m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && off_mask && s_ray && s_step && s_sdf && s_alpha && s_T && alphainv_last &&
+                g_w_m1 && tmp_dprev && tmp_dnext && grad_sdf_grid);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_alpha_scan_bwd<<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, s_alpha, s_T,
+                                                       alphainv_last, g_w_m1, g_last, tmp_dprev, tmp_dnext);
+  ESR_LAUNCH_OK();
+  k_sdf_scatter<<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,
+                                               grad_sdf_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}

@@ -1,0 +1,338 @@
+"""torch.autograd bindings of the fused pipeline stages in libesr_b200.so (include/esr_b200.h §2).
+
+PyTorch is plumbing here: it owns device memory and streams and carries the (tiny) [N,3] outputs into
+the caller's loss; every per-sample computation is a hand-written kernel behind the C ABI.
+
+Stage map (reference lines in parentheses):
+  march()            A/B  sample_pts_on_rays + AABB filter + MaskCache + SDF tap   (voxurff.py:186-193)
+  AlphaScan          C/D  NeuS alpha, alpha filter, Alphas2Weights, weight filter  (voxurff.py:195-213)
+  Shade              E+F  feature encode + off/emo radiance MLPs                   (voxurff.py:215-254)
+  Tonemap            G+F  tone-map encode + tonemapper MLP                         (voxurff.py:256, 783-788)
+  Composite          H    weighted per-ray sums                                    (voxurff.py:258-272)
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MlpDesc, Scene, check, ptr, stream_ptr
+
+FEAT_DIM = 96
+FEAT_GRAD_DIM = 56
+TFEAT_DIM = 48
+TFEAT_GRAD_DIM = 40
+
+RADIANCE_DESC = dict(k0=96, width=192, n_hidden=3, n_out=3, act=1)   # pbr/module.py:6-21 (softplus)
+TONEMAP_DESC = dict(k0=48, width=192, n_hidden=1, n_out=3, act=2)    # pbr/module.py:24-39 (sigmoid)
+
+
+def make_scene(xyz_min, xyz_max, grid_size, mask_xyz_min, mask_xyz_max, mask_size, near, far, stepdist,
+               voxel_size, act_shift, mask_thres, fast_thres, s_val) -> Scene:
+    sc = Scene()
+    for i in range(3):
+        sc.xyz_min[i] = float(xyz_min[i])
+        sc.xyz_max[i] = float(xyz_max[i])
+        sc.mask_xyz_min[i] = float(mask_xyz_min[i])
+        sc.mask_xyz_max[i] = float(mask_xyz_max[i])
+    sc.gx, sc.gy, sc.gz = (int(v) for v in grid_size)
+    sc.mx, sc.my, sc.mz = (int(v) for v in mask_size)
+    sc.near, sc.far = float(near), float(far)
+    sc.stepdist, sc.voxel_size = float(stepdist), float(voxel_size)
+    sc.act_shift, sc.mask_thres, sc.fast_thres, sc.s_val = float(act_shift), float(mask_thres), float(fast_thres), float(s_val)
+    return sc
+
+
+def _i32(n, dev):
+    return torch.empty(int(n), dtype=torch.int32, device=dev)
+
+
+def _f32(*shape, dev):
+    return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+
+def exclusive_scan(counts: torch.Tensor) -> torch.Tensor:
+    """int32 [n] -> int32 [n+1] exclusive offsets, last = total."""
+    L = _lib.lib()
+    n = counts.shape[0]
+    out = _i32(n + 1, counts.device)
+    scratch = torch.empty(L.esr_scan_scratch_bytes(n), dtype=torch.uint8, device=counts.device)
+    check(L.esr_exclusive_scan_i32(ptr(counts), ptr(out), n, ptr(scratch), stream_ptr()))
+    return out
+
+
+@dataclass
+class Streams:
+    """Packed sample streams of one render call (all int32 / float32, ray-slot order)."""
+    n_rays: int
+    ray_order: Optional[torch.Tensor]
+    n_steps: torch.Tensor       # [N] candidate steps per slot (== reference N_steps)
+    cnt_inbox: torch.Tensor     # [N] in-AABB candidates per slot
+    off_mask: torch.Tensor      # [N+1] exclusive offsets of the M1 (post-MaskCache) stream
+    m1: int
+    s_ray: torch.Tensor         # [M1]
+    s_step: torch.Tensor        # [M1]
+    s_sdf: torch.Tensor         # [M1]
+    # filled by AlphaScan
+    off_shade: Optional[torch.Tensor] = None   # [N+1]
+    m3: int = 0
+    m3_on: int = 0
+    s_alpha: Optional[torch.Tensor] = None
+    s_T: Optional[torch.Tensor] = None
+    h_ray: Optional[torch.Tensor] = None
+    h_step: Optional[torch.Tensor] = None
+    h_m1: Optional[torch.Tensor] = None
+    h_sdf: Optional[torch.Tensor] = None
+
+
+def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid) -> Streams:
+    """Stages A/B.  One host read (M1) sizes the stream buffers — the reference syncs at the same
+    point (render_utils_kernel.cu:212) and four more times before shading."""
+    L = _lib.lib()
+    dev = rays_o.device
+    n = rays_o.shape[0]
+    n_steps, cnt_in, cnt_mask = _i32(n, dev), _i32(n, dev), _i32(n, dev)
+    st = stream_ptr()
+    scp = ctypes.byref(sc)
+    check(L.esr_march_count(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(n_steps),
+                            ptr(cnt_in), ptr(cnt_mask), st))
+    off_mask = exclusive_scan(cnt_mask)
+    m1 = int(off_mask[n].item())
+    s_ray, s_step, s_sdf = _i32(m1, dev), _i32(m1, dev), _f32(m1, dev=dev)
+    check(L.esr_march_fill(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(sdf_grid),
+                           ptr(off_mask), ptr(s_ray), ptr(s_step), ptr(s_sdf), st))
+    return Streams(n, ray_order, n_steps, cnt_in, off_mask, m1, s_ray, s_step, s_sdf)
+
+
+class AlphaScan(torch.autograd.Function):
+    """(h_w [M3], alphainv_last [N]) = f(sdf_grid); fills the M3 stream fields of `streams`."""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, sc: Scene, rays_o, rays_d, streams: Streams, n_on):
+        L = _lib.lib()
+        dev = rays_o.device
+        n, st, scp = streams.n_rays, stream_ptr(), ctypes.byref(sc)
+        cnt_shade = _i32(n, dev)
+        last = _f32(n, dev=dev)
+        check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
+                                     ptr(cnt_shade), ptr(last), st))
+        off_shade = exclusive_scan(cnt_shade)
+        if n_on is None:
+            m3 = int(off_shade[n].item())
+            m3_on = m3
+        else:
+            m3, m3_on = torch.stack([off_shade[n], off_shade[n_on]]).tolist()
+        streams.off_shade, streams.m3, streams.m3_on = off_shade, m3, m3_on
+        streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
+        streams.h_ray, streams.h_step, streams.h_m1 = _i32(m3, dev), _i32(m3, dev), _i32(m3, dev)
+        streams.h_sdf = _f32(m3, dev=dev)
+        h_w = _f32(m3, dev=dev)
+        check(L.esr_alpha_scan_fill(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_step),
+                                    ptr(streams.s_sdf), ptr(off_shade), ptr(streams.s_alpha), ptr(streams.s_T),
+                                    ptr(streams.h_ray), ptr(streams.h_step), ptr(streams.h_m1), ptr(h_w),
+                                    ptr(streams.h_sdf), st))
+        ctx.sc, ctx.streams = sc, streams
+        ctx.save_for_backward(rays_o, rays_d, last, sdf_grid)
+        ctx.mark_non_differentiable()
+        return h_w, last
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_hw, g_last):
+        rays_o, rays_d, last, sdf_grid = ctx.saved_tensors
+        s: Streams = ctx.streams
+        dev = rays_o.device
+        grad_sdf = torch.zeros_like(sdf_grid)
+        if s.m1 == 0:
+            return grad_sdf, None, None, None, None, None
+        g_w_m1 = torch.zeros(s.m1, dtype=torch.float32, device=dev)
+        if s.m3:
+            g_w_m1.index_copy_(0, s.h_m1.long(), g_hw.contiguous())
+        tmp_p, tmp_n = _f32(s.m1, dev=dev), _f32(s.m1, dev=dev)
+        check(_lib.lib().esr_alpha_scan_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.ray_order), s.n_rays,
+                                            ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(s.s_alpha),
+                                            ptr(s.s_T), ptr(last), ptr(g_w_m1), ptr(g_last.contiguous()), ptr(tmp_p),
+                                            ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
+        return grad_sdf, None, None, None, None, None
+
+
+def _desc(d: dict) -> MlpDesc:
+    return MlpDesc(d["k0"], d["width"], d["n_hidden"], d["n_out"], d["act"])
+
+
+def mlp_pack(desc: dict, flat: torch.Tensor) -> torch.Tensor:
+    L = _lib.lib()
+    d = _desc(desc)
+    assert flat.numel() == L.esr_mlp_param_count(ctypes.byref(d)), (flat.numel(), L.esr_mlp_param_count(ctypes.byref(d)))
+    image = torch.empty(L.esr_mlp_image_bytes(ctypes.byref(d)), dtype=torch.uint8, device=flat.device)
+    check(L.esr_mlp_pack(ctypes.byref(d), ptr(flat.detach().contiguous()), ptr(image), stream_ptr()))
+    return image
+
+
+def encode_features(sc: Scene, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s: Streams, bf16: bool):
+    x = torch.empty(s.m3, FEAT_DIM, dtype=torch.bfloat16 if bf16 else torch.float32, device=rays_o.device)
+    check(_lib.lib().esr_encode_fwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(viewdirs), ptr(sdf_grid),
+                                    ptr(off_grid), ptr(emo_grid), 6, ptr(s.h_ray), ptr(s.h_step), ptr(s.h_sdf), s.m3,
+                                    ptr(x), int(bf16), stream_ptr()))
+    return x
+
+
+def encode_backward(sc: Scene, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s: Streams, d_feat):
+    g_sdf = torch.zeros_like(sdf_grid)
+    g_off = torch.zeros_like(off_grid)
+    g_emo = torch.zeros_like(emo_grid)
+    check(_lib.lib().esr_encode_bwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(sdf_grid), 6, ptr(s.h_ray),
+                                    ptr(s.h_step), s.m3, ptr(d_feat), ptr(g_sdf), ptr(g_off), ptr(g_emo),
+                                    stream_ptr()))
+    return g_sdf, g_off, g_emo
+
+
+def _check_cl(grid: torch.Tensor, name: str):
+    if not grid.is_contiguous(memory_format=torch.channels_last_3d):
+        raise _lib.EsrError(f"{name} must be in channels_last_3d memory format (DenseGrid.ensure_layout)")
+
+
+class Encode(torch.autograd.Function):
+    """fp32 feature rows [M3,96] (strict / validation path; the bf16 product path is `Shade`)."""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, off_grid, emo_grid, sc, rays_o, rays_d, viewdirs, streams):
+        _check_cl(off_grid, "off_color.grid")
+        _check_cl(emo_grid, "emo_color.grid")
+        ctx.sc, ctx.streams = sc, streams
+        ctx.save_for_backward(rays_o, rays_d, sdf_grid, off_grid, emo_grid)
+        return encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, streams, bf16=False)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_x):
+        rays_o, rays_d, sdf_grid, off_grid, emo_grid = ctx.saved_tensors
+        d_feat = d_x[:, :FEAT_GRAD_DIM].contiguous()
+        g = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, ctx.streams, d_feat)
+        return (*g, None, None, None, None, None)
+
+
+def _mlp_forward(desc, image, x, rb, re, m_total, train):
+    L = _lib.lib()
+    d = _desc(desc)
+    dev = x.device
+    y = torch.zeros(m_total, desc["n_out"], dtype=torch.float32, device=dev)
+    hidden = (torch.empty(desc["n_hidden"], m_total, desc["width"], dtype=torch.bfloat16, device=dev)
+              if train else None)
+    check(L.esr_mlp_fwd(ctypes.byref(d), ptr(image), ptr(x), rb, re, m_total, ptr(y), ptr(hidden), stream_ptr()))
+    return y, hidden
+
+
+def _mlp_backward(desc, image, x, y, d_y, rb, re, m_total, hidden, d_x, dx_cols, accumulate, scratch=None):
+    L = _lib.lib()
+    d = _desc(desc)
+    dev = x.device
+    if scratch is None:
+        scratch = torch.empty(desc["n_hidden"], m_total, desc["width"], dtype=torch.bfloat16, device=dev)
+    d_z_out = torch.empty(m_total, 8, dtype=torch.float32, device=dev)
+    grad_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=dev)
+    check(L.esr_mlp_bwd(ctypes.byref(d), ptr(image), ptr(x), ptr(y), ptr(d_y), rb, re, m_total, ptr(hidden),
+                        ptr(scratch), ptr(d_z_out), ptr(d_x), dx_cols, int(accumulate), ptr(grad_flat), stream_ptr()))
+    return grad_flat, scratch
+
+
+class Shade(torch.autograd.Function):
+    """Encode + the two radiance MLPs on tensor cores (bf16 in, fp32 accumulate).
+
+    Returns (lin_off [M3,3], lin_emo [M3,3]); lin_emo rows >= m3_on are zero (with the on-first ray
+    order only emission-on rays occupy rows [0,m3_on)).  `off_grad_rows` / `emo_grad_rows` tell the
+    backward which row range can carry a non-zero cotangent (voxurff.py:243-254: emission-on rays see the
+    off net only through a stop-gradient)."""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, off_grid, emo_grid, flat_off, flat_emo, sc, rays_o, rays_d, viewdirs, streams,
+                off_grad_rows, emo_grad_rows):
+        _check_cl(off_grid, "off_color.grid")
+        _check_cl(emo_grid, "emo_color.grid")
+        s: Streams = streams
+        train = any(ctx.needs_input_grad[:5])
+        x = encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s, bf16=True)
+        img_off, img_emo = mlp_pack(RADIANCE_DESC, flat_off), mlp_pack(RADIANCE_DESC, flat_emo)
+        lin_off, hid_off = _mlp_forward(RADIANCE_DESC, img_off, x, 0, s.m3, s.m3, train)
+        lin_emo, hid_emo = _mlp_forward(RADIANCE_DESC, img_emo, x, 0, s.m3_on, s.m3, train)
+        ctx.sc, ctx.streams = sc, s
+        ctx.rows = (off_grad_rows, emo_grad_rows)
+        ctx.hidden = (hid_off, hid_emo)
+        ctx.save_for_backward(rays_o, rays_d, sdf_grid, off_grid, emo_grid, x, img_off, img_emo, lin_off, lin_emo)
+        return lin_off, lin_emo
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_off, d_emo):
+        rays_o, rays_d, sdf_grid, off_grid, emo_grid, x, img_off, img_emo, lin_off, lin_emo = ctx.saved_tensors
+        s: Streams = ctx.streams
+        hid_off, hid_emo = ctx.hidden
+        (ob, oe), (eb, ee) = ctx.rows
+        d_x = torch.zeros(s.m3, FEAT_GRAD_DIM, dtype=torch.float32, device=x.device)
+        g_off_flat, scratch = _mlp_backward(RADIANCE_DESC, img_off, x, lin_off, d_off.contiguous(), ob, oe, s.m3,
+                                            hid_off, d_x, FEAT_GRAD_DIM, 1)
+        g_emo_flat, _ = _mlp_backward(RADIANCE_DESC, img_emo, x, lin_emo, d_emo.contiguous(), eb, ee, s.m3, hid_emo,
+                                      d_x, FEAT_GRAD_DIM, 1, scratch)
+        ctx.hidden = None
+        g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x)
+        return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None
+
+
+class Tonemap(torch.autograd.Function):
+    """rgb = sigmoid(tonemapper([lin, sin(lin 2^f), cos(lin 2^f)]))  (voxurff.py:783-788) on tensor cores."""
+
+    @staticmethod
+    def forward(ctx, lin, flat_tone):
+        L = _lib.lib()
+        m = lin.shape[0]
+        lin = lin.contiguous()
+        xt = torch.empty(m, TFEAT_DIM, dtype=torch.bfloat16, device=lin.device)
+        lin_copy = torch.empty_like(lin)
+        check(L.esr_tonemap_encode_fwd(ptr(lin), None, None, None, m, ptr(lin_copy), ptr(xt), 1, stream_ptr()))
+        img = mlp_pack(TONEMAP_DESC, flat_tone)
+        rgb, hid = _mlp_forward(TONEMAP_DESC, img, xt, 0, m, m, any(ctx.needs_input_grad))
+        ctx.hidden = hid
+        ctx.save_for_backward(lin, xt, img, rgb)
+        return rgb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_rgb):
+        lin, xt, img, rgb = ctx.saved_tensors
+        m = lin.shape[0]
+        d_xt = torch.empty(m, TFEAT_GRAD_DIM, dtype=torch.float32, device=lin.device)
+        g_flat, _ = _mlp_backward(TONEMAP_DESC, img, xt, rgb, d_rgb.contiguous(), 0, m, m, ctx.hidden, d_xt,
+                                  TFEAT_GRAD_DIM, 0)
+        ctx.hidden = None
+        d_lin = torch.empty_like(lin)
+        check(_lib.lib().esr_tonemap_encode_bwd(ptr(lin), ptr(d_xt), None, m, ptr(d_lin), stream_ptr()))
+        return d_lin, g_flat
+
+
+class Composite(torch.autograd.Function):
+    """(sum_ray w*a, sum_ray w*b): warp-per-ray segmented sums replacing segment_coo (voxurff.py:259-272)."""
+
+    @staticmethod
+    def forward(ctx, h_w, a, b, streams):
+        s: Streams = streams
+        dev = h_w.device
+        a, b = a.contiguous(), b.contiguous()
+        out_a, out_b = _f32(s.n_rays, 3, dev=dev), _f32(s.n_rays, 3, dev=dev)
+        check(_lib.lib().esr_composite_fwd(ptr(s.ray_order), s.n_rays, ptr(s.off_shade), ptr(h_w), ptr(a), ptr(b),
+                                           ptr(out_a), ptr(out_b), stream_ptr()))
+        ctx.streams = s
+        ctx.save_for_backward(h_w, a, b)
+        return out_a, out_b
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, c_a, c_b):
+        h_w, a, b = ctx.saved_tensors
+        s: Streams = ctx.streams
+        d_a, d_b, g_w = torch.empty_like(a), torch.empty_like(b), torch.empty_like(h_w)
+        check(_lib.lib().esr_composite_bwd(ptr(s.h_ray), None, ptr(h_w), ptr(a), ptr(b), ptr(c_a.contiguous()),
+                                           ptr(c_b.contiguous()), s.m3, ptr(d_a), ptr(d_b), ptr(g_w), stream_ptr()))
+        return g_w, d_a, d_b, None

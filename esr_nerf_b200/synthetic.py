@@ -1,0 +1,77 @@
+"""Deterministic synthetic scenes and rays for parity tests and bench.py.
+
+No dataset travels with the repo, so every measurement uses: cubic AABB +-1.05; sdf.grid = |p| - 0.6 +
+0.01 N(0,1); colour grids 0.1 N(0,1); MaskCache density +10 (dense) or +10 inside the shell
+||p|-0.6| < 0.1 and -10 elsewhere (sparse); rays from camera centres on the r=4 sphere towards targets in
+the r=0.9 ball with un-normalised directions (|d| ~ U(1,1.2)); em_modes ~ Bernoulli(0.5).
+All tensors are generated on the CPU with fixed seeds and moved by the caller.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+FINE_MODEL_CFG = dict(  # cfg/app/fine.yaml:13-30
+    mask_ks=3, maskcache_thres=1e-3, fastcolor_thres=1e-4, stepsize=0.5, color_dim=6, rgbnet_width=192,
+    rgbnet_depth=4, tonemap_width=192, tonemap_depth=2, posbase_pe=5, viewbase_pe=1, colorbase_pe=5,
+    grad_feat=[0.5, 1.0, 1.5, 2.0], neus_alpha="interp")
+
+
+def fine_cfg(device="cuda:0", **overrides):
+    model = dict(FINE_MODEL_CFG)
+    model.update(overrides)
+    return SimpleNamespace(system=SimpleNamespace(device=device),
+                           app=SimpleNamespace(model=SimpleNamespace(**model)))
+
+
+def make_rays(n: int, seed: int = 1234, em_p: float = 0.5) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    origin = F.normalize(torch.randn(n, 3, generator=g), dim=-1) * 4.0
+    target = F.normalize(torch.randn(n, 3, generator=g), dim=-1) * 0.9 * torch.rand(n, 1, generator=g) ** (1 / 3)
+    dirs = F.normalize(target - origin, dim=-1)
+    rays_d = dirs * (1.0 + 0.2 * torch.rand(n, 1, generator=g))
+    em_modes = (torch.rand(n, generator=g) < em_p).long()
+    return dict(rays_o=origin.contiguous(), rays_d=rays_d.contiguous(), viewdirs=F.normalize(rays_d, dim=-1),
+                em_modes=em_modes, rgbs=torch.rand(n, 3, generator=g))
+
+
+def mask_density(res: int, sparse: bool) -> torch.Tensor:
+    """[1,1,res,res,res] alphamask-stage density on the AABB lattice."""
+    if not sparse:
+        return torch.full([1, 1, res, res, res], 10.0)
+    ax = torch.linspace(-1.05, 1.05, res)
+    gx, gy, gz = torch.meshgrid(ax, ax, ax, indexing="ij")
+    r = (gx ** 2 + gy ** 2 + gz ** 2).sqrt()
+    return torch.where((r - 0.6).abs() < 0.1, 10.0, -10.0)[None, None].contiguous()
+
+
+def sphere_sdf(world_size, radius: float = 0.6, noise: float = 0.01, seed: int = 1) -> torch.Tensor:
+    ax = [torch.linspace(-1.05, 1.05, int(w)) for w in world_size]
+    gx, gy, gz = torch.meshgrid(*ax, indexing="ij")
+    sdf = (gx ** 2 + gy ** 2 + gz ** 2).sqrt() - radius
+    g = torch.Generator().manual_seed(seed)
+    return (sdf + noise * torch.randn(sdf.shape, generator=g))[None, None].contiguous()
+
+
+def color_grid(world_size, channels: int, seed: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return 0.1 * torch.randn([1, channels, *[int(w) for w in world_size]], generator=g)
+
+
+def fill_fine_model(model, sdf_noise: float = 0.01) -> None:
+    """Overwrite the grids of a (reference or esr_nerf_b200) VoxurfF in place with the synthetic scene."""
+    ws = [int(w) for w in model.world_size]
+    dev = model.sdf.grid.device
+    with torch.no_grad():
+        model.sdf.grid.copy_(sphere_sdf(ws, noise=sdf_noise).to(dev))
+        model.off_color.grid.copy_(color_grid(ws, 6, 2).to(dev))
+        model.emo_color.grid.copy_(color_grid(ws, 6, 3).to(dev))
+
+
+BBOX_MIN = torch.tensor([-1.05, -1.05, -1.05])
+BBOX_MAX = torch.tensor([1.05, 1.05, 1.05])
+NEAR, FAR = 2.0, 6.0          # data/esr_nerf/esrnerf.py:77-79
+MASK_ALPHA_INIT = 1e-6        # cfg/app/alphamask.yaml:17

@@ -1,0 +1,228 @@
+"""Drop-in for the reference's fine-stage render model ``app.fine.model.VoxurfF``
+(app/fine/model/voxurff.py): same constructor arguments, same ``state_dict`` keys/shapes, same
+``forward(**batch) -> Dict[str, Tensor]`` contract with ``.train()/.eval()`` rebinding ``forward``
+(voxurff.py:170-175) — but the per-sample work runs in the fused sm_100a kernels of libesr_b200.so.
+
+    renderer = VoxurfF(cfg, near, far, xyz_min, xyz_max, mask_xyz_min, mask_xyz_max,
+                       mask_alpha_init, mask_density, s_val, num_voxels)
+    results = renderer(s_val=s_val, **batch)          # fine.py:352
+
+``mlp_mode``: "bf16" (default, tensor cores; 1e-2 parity class) or "torch_fp32" (library fp32 GEMMs
+for the three MLPs, everything else unchanged; 1e-4 parity class, used by the strict tests).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import fused
+from .modules import (DenseGrid, GradientConv, MaskCache, RadianceNet, TonemapNet, cfg_get, flat_mlp_params,
+                      radiance_in_cols, tonemap_in_cols, voxel_geometry)
+
+
+class VoxurfF(nn.Module):
+    def __init__(self, cfg, near: float, far: float, xyz_min: torch.Tensor, xyz_max: torch.Tensor,
+                 mask_xyz_min: torch.Tensor, mask_xyz_max: torch.Tensor, mask_alpha_init: float,
+                 mask_density: torch.Tensor, s_val: float, num_voxles: int):
+        super().__init__()
+        self.cfg = cfg
+        self.device = cfg_get(cfg, "system.device")
+        m = "app.model."
+        # dynamic variables (voxurff.py:48-58)
+        self.near, self.far = near, far
+        self.xyz_min = xyz_min.to(self.device).float()
+        self.xyz_max = xyz_max.to(self.device).float()
+        self.mask_xyz_min = mask_xyz_min.to(self.device).float()
+        self.mask_xyz_max = mask_xyz_max.to(self.device).float()
+        self.mask_alpha_init = mask_alpha_init
+        self.mask_density = mask_density.to(self.device).float()
+        self.s_val = s_val
+        # static variables (voxurff.py:60-77)
+        self.mask_ks = cfg_get(cfg, m + "mask_ks")
+        self.maskcache_thres = cfg_get(cfg, m + "maskcache_thres")
+        self.fastcolor_thres = cfg_get(cfg, m + "fastcolor_thres")
+        self.stepsize = cfg_get(cfg, m + "stepsize")
+        self.color_dim = cfg_get(cfg, m + "color_dim")
+        self.rgbnet_width = cfg_get(cfg, m + "rgbnet_width")
+        self.rgbnet_depth = cfg_get(cfg, m + "rgbnet_depth")
+        self.tonemap_width = cfg_get(cfg, m + "tonemap_width")
+        self.tonemap_depth = cfg_get(cfg, m + "tonemap_depth")
+        self.posbase_pe = cfg_get(cfg, m + "posbase_pe")
+        self.viewbase_pe = cfg_get(cfg, m + "viewbase_pe")
+        self.colorbase_pe = cfg_get(cfg, m + "colorbase_pe")
+        self.grad_feat = [float(v) for v in cfg_get(cfg, m + "grad_feat")]
+        self.neus_alpha = cfg_get(cfg, m + "neus_alpha")
+        self._check_supported()
+
+        self.set_grid_resolution(num_voxles)
+        ws = self.world_size
+
+        self.sdf = DenseGrid(1, ws, self.xyz_min, self.xyz_max)
+        # unit-sphere initialisation on the [-1,1] lattice (voxurff.py:88-97)
+        ax = [torch.linspace(-1.0, 1.0, int(w), dtype=torch.float64) for w in ws]
+        gx, gy, gz = torch.meshgrid(*ax, indexing="ij")
+        self.sdf.grid.data = ((gx ** 2 + gy ** 2 + gz ** 2) ** 0.5 - 1).float()[None, None]
+        self.sdf_random_init = True
+        self.tv_smooth_conv = GradientConv()
+        self.mask_cache = MaskCache(self.mask_xyz_min, self.mask_xyz_max, self.mask_density, self.mask_alpha_init,
+                                    self.maskcache_thres, self.mask_ks)
+
+        self.off_color = DenseGrid(self.color_dim, ws, self.xyz_min, self.xyz_max)
+        dim0 = (3 + 3 * self.posbase_pe * 2) + (3 * self.viewbase_pe * 3) + self.color_dim
+        dim0 += len(self.grad_feat) * 3 + len(self.grad_feat) * 6 + 1
+        self.off_rgbnet = RadianceNet(dim0, self.rgbnet_width, self.rgbnet_depth)
+        self.emo_color = DenseGrid(self.color_dim, ws, self.xyz_min, self.xyz_max)
+        self.emo_rgbnet = RadianceNet(dim0, self.rgbnet_width, self.rgbnet_depth)
+        self.tonemapper = TonemapNet(3 + 3 * self.colorbase_pe * 2, self.tonemap_width, self.tonemap_depth)
+        self.to(self.device)
+        self.set_nonempty_mask()
+
+        self.normal_flipper = torch.tensor([1.0, -1.0, -1.0], device=self.device)
+        # execution options of the B200 path
+        self.mlp_mode = "bf16"
+        self.on_first_order = True   # process emission-on rays first so the emo net runs on a row prefix
+        self.keep_streams = False    # tests: keep the packed streams of the last call in self.last_streams
+        self.last_streams = None
+        self.train()
+
+    # ------------------------------------------------------------------------------------------
+    def _check_supported(self):
+        ok = (self.color_dim == 6 and self.rgbnet_width == 192 and self.rgbnet_depth == 4 and
+              self.tonemap_width == 192 and self.tonemap_depth == 2 and self.posbase_pe == 5 and
+              self.viewbase_pe == 1 and self.colorbase_pe == 5 and self.grad_feat == [0.5, 1.0, 1.5, 2.0] and
+              self.neus_alpha == "interp")
+        if not ok:
+            raise NotImplementedError(
+                "libesr_b200 instantiates the shipped fine-stage shape only (cfg/app/fine.yaml:13-30): color_dim 6, "
+                "rgbnet 192x4, tonemap 192x2, PE 5/1/5, grad_feat [.5,1,1.5,2], neus_alpha interp")
+
+    def train(self, mode=True):
+        self.forward = self.forward_training if mode else self.forward_evaluate
+        return super().train(mode)
+
+    def set_grid_resolution(self, num_voxels: int):
+        """voxurff.py:539-545"""
+        self.num_voxels = num_voxels
+        self.voxel_size, self.world_size = voxel_geometry(self.xyz_min, self.xyz_max, num_voxels)
+
+    @torch.no_grad()
+    def scale_volume_grid(self, num_voxels):
+        """voxurff.py:547-566"""
+        self.set_grid_resolution(num_voxels)
+        self.sdf.scale_volume_grid(self.world_size)
+        self.off_color.scale_volume_grid(self.world_size)
+        self.emo_color.scale_volume_grid(self.world_size)
+        self.set_nonempty_mask()
+
+    @torch.no_grad()
+    def set_nonempty_mask(self):
+        """voxurff.py:568-598"""
+        ax = [torch.linspace(float(self.xyz_min[i]), float(self.xyz_max[i]), self.sdf.grid.shape[2 + i],
+                             device=self.sdf.grid.device) for i in range(3)]
+        xyz = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1)
+        self.nonempty_mask = self.mask_cache(xyz)[None, None].contiguous()
+        self.sdf.grid[~self.nonempty_mask] = 1
+
+    def sdf_total_variation_add_grad(self, weight: float, dense_mode: bool):
+        """voxurff.py:619-621"""
+        w = weight * self.world_size.max() / 128
+        self.sdf.total_variation_add_grad(w, w, w, dense_mode)
+
+    # ------------------------------------------------------------------------------------------
+    def _scene(self, s_val: float, near=None):
+        g = self.sdf.grid.shape
+        md = self.mask_cache.density.shape
+        return fused.make_scene(self.xyz_min.tolist(), self.xyz_max.tolist(), g[2:], self.mask_xyz_min.tolist(),
+                                self.mask_xyz_max.tolist(), md[2:], self.near if near is None else near, 1e9,
+                                float(self.stepsize * self.voxel_size), float(self.voxel_size),
+                                self.mask_cache.act_shift, self.maskcache_thres, self.fastcolor_thres, s_val)
+
+    def _flat(self, which: str):
+        dev = self.sdf.grid.device
+        if which == "tone":
+            return flat_mlp_params(self.tonemapper.layers(), tonemap_in_cols(dev), 48)
+        net = self.off_rgbnet if which == "off" else self.emo_rgbnet
+        return flat_mlp_params(net.layers(), radiance_in_cols(which, dev), 96)
+
+    def _streams(self, sc, rays_o, rays_d, em_modes):
+        n = rays_o.shape[0]
+        order, n_on = None, None
+        if self.on_first_order and em_modes is not None and em_modes.dim() == 1:
+            on = em_modes == 1
+            order = torch.argsort((~on).to(torch.uint8), stable=True).to(torch.int32)
+            n_on = on.sum()
+        for g in (self.sdf, self.off_color, self.emo_color):
+            g.ensure_layout()
+        streams = fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach())
+        return streams, n_on
+
+    def forward_training(self, **kwargs) -> Dict[str, torch.Tensor]:
+        """voxurff.py:177-278"""
+        rays_o = kwargs["rays_o"].contiguous().float()
+        rays_d = kwargs["rays_d"].contiguous().float()
+        viewdirs = kwargs["viewdirs"].contiguous().float()
+        em_modes = kwargs["em_modes"].contiguous()
+        self.s_val = kwargs["s_val"]
+        N = rays_o.shape[0]
+        with torch.cuda.device(rays_o.device):
+            sc = self._scene(float(self.s_val))
+            streams, n_on = self._streams(sc, rays_o, rays_d, em_modes)
+            h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, streams, n_on)
+            s = streams
+            on = (em_modes[s.h_ray.long()] == 1) if s.m3 else torch.zeros(0, dtype=torch.bool, device=rays_o.device)
+            if self.mlp_mode == "bf16":
+                ordered = n_on is not None
+                off_rows = (s.m3_on, s.m3) if ordered else (0, s.m3)
+                emo_rows = (0, s.m3_on) if ordered else (0, s.m3)
+                lin_off, lin_emo = fused.Shade.apply(self.sdf.grid, self.off_color.grid, self.emo_color.grid,
+                                                     self._flat("off"), self._flat("emo"), sc, rays_o, rays_d,
+                                                     viewdirs, s, off_rows, emo_rows)
+                # voxurff.py:243-254: on-rays emo + stop-gradient(off); off-rays off
+                lin = torch.where(on[:, None], lin_emo + lin_off.detach(), lin_off)
+                rgb = fused.Tonemap.apply(lin, self._flat("tone"))
+            elif self.mlp_mode == "torch_fp32":
+                x = fused.Encode.apply(self.sdf.grid, self.off_color.grid, self.emo_color.grid, sc, rays_o, rays_d,
+                                       viewdirs, s)
+                dev = x.device
+                lin_off = self.off_rgbnet(x[:, self._ref_cols("off", dev)])
+                lin_emo = self.emo_rgbnet(x[:, self._ref_cols("emo", dev)])
+                lin = torch.where(on[:, None], lin_emo + lin_off.detach(), lin_off)
+                rgb = self.apply_tonemapper(lin)
+            else:
+                raise ValueError(f"unknown mlp_mode {self.mlp_mode!r}")
+            rgb_marched, lin_marched = fused.Composite.apply(h_w, rgb, lin, s)
+        if self.keep_streams:
+            self.last_streams = dict(streams=s, h_w=h_w.detach(), lin=lin.detach(), rgb=rgb.detach())
+        return {
+            "etc/alphainv_cum": last,
+            "etc/white_bg": last[..., None],
+            "srgb/rgb": rgb_marched,
+            "lin/rgb": lin_marched,
+        }
+
+    def forward_evaluate(self, **kwargs):
+        raise NotImplementedError("forward_evaluate lands with the inference row of SURVEY.md §8 (config 4)")
+
+    # ------------------------------------------------------------------------------------------
+    _ref_cols_cache = None
+
+    def _ref_cols(self, which: str, dev):
+        """reference 85-column input order expressed as indices into the internal 96-column row"""
+        inv = torch.empty(85, dtype=torch.long)
+        cols = radiance_in_cols(which, "cpu")
+        for c_int, c_ref in enumerate(cols.tolist()):
+            if c_ref >= 0:
+                inv[c_ref] = c_int
+        return inv.to(dev)
+
+    def apply_tonemapper(self, lin_rgb):
+        """voxurff.py:783-788 (fp32 library path)"""
+        freq = torch.tensor([2.0 ** i for i in range(self.colorbase_pe)], device=lin_rgb.device)
+        emb = (lin_rgb.unsqueeze(-1) * freq).flatten(-2)
+        return self.tonemapper(torch.cat([lin_rgb, emb.sin(), emb.cos()], dim=-1))
+
+
+_ = F

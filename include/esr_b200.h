@@ -1,0 +1,251 @@
+/*
+ * esr_b200.h — C ABI of libesr_b200.so: the B200 (sm_100a) render hot path of ESR-NeRF.
+ *
+ * Drop-in boundary.  Every entry point takes raw DEVICE pointers, sizes,
+ * scalars and a cudaStream_t (as void*); the caller owns all memory; nothing here
+ * allocates persistent device memory.  Return value: 0 = ok, <0 = error
+ * (ESR_ERR_*), message via esr_last_error().  Thread-safe per (device, stream).
+ * All citations are relative to the reference tree (ecrireme/ESR-NeRF).
+ *
+ * Section 1 replaces, one for one, what the reference's pybind module
+ * `render_utils_cuda` exports for this path (app/utils/base/cuda/render_utils.cpp:170-184,
+ * live entries only) and the torch_scatter.segment_coo call the render functions use.
+ * Section 2 is the fused pipeline that the drop-in render modules
+ * (esr_nerf_b200.VoxurfF ...) run instead of the reference's ~200 ATen launches.
+ */
+#ifndef ESR_B200_H
+#define ESR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESR_OK 0
+#define ESR_ERR_BAD_ARG (-1)
+#define ESR_ERR_CUDA (-2)
+#define ESR_ERR_CAPACITY (-3)
+
+typedef void *esr_stream_t; /* cudaStream_t */
+
+const char *esr_last_error(void);
+int esr_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t esr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Native-op replacements (reference-shaped: int64 indices, bool masks)
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * sample_pts_on_rays — render_utils.cpp:74-85, render_utils_kernel.cu:196-242.
+ * Two-call protocol replacing the reference's `.item<int>()` host sync (kernel.cu:212):
+ *   _count writes N_steps[n], its inclusive cumsum N_cum[n] (both int64), t_min/t_max[n]
+ *          and *total (int64, device) = sum(N_steps);
+ *   _fill  writes ray_pts[total,3], mask_outbbox[total] (uint8 0/1), ray_id[total],
+ *          step_id[total] (int64).  `total` is the value read back by the caller.
+ * scratch: >= esr_scan_scratch_bytes(n_rays) bytes.
+ */
+int esr_sample_pts_on_rays_count(const float *rays_o, const float *rays_d, const float xyz_min[3],
+                                 const float xyz_max[3], float near, float far, float stepdist,
+                                 int64_t n_rays, int64_t *N_steps, int64_t *N_cum, float *t_min,
+                                 float *t_max, int64_t *total, void *scratch, esr_stream_t stream);
+int esr_sample_pts_on_rays_fill(const float *rays_o, const float *rays_d, const float xyz_min[3],
+                                const float xyz_max[3], float near, float far, float stepdist,
+                                int64_t n_rays, const int64_t *N_cum, int64_t total, float *ray_pts,
+                                uint8_t *mask_outbbox, int64_t *ray_id, int64_t *step_id,
+                                esr_stream_t stream);
+int64_t esr_scan_scratch_bytes(int64_t n);
+
+/*
+ * alpha2weight / alpha2weight_backward — render_utils.cpp:142-167, kernel.cu:576-707.
+ * Same outputs as the reference (weight zero-filled / T one-filled past the early stop,
+ * i_end truncated at the stop index).  ray_id must be sorted (as the reference assumes).
+ */
+int esr_alpha2weight_fwd(const float *alpha, const int64_t *ray_id, int64_t n_pts, int64_t n_rays,
+                         float *weight, float *T, float *alphainv_last, int64_t *i_start,
+                         int64_t *i_end, esr_stream_t stream);
+int esr_alpha2weight_bwd(const float *alpha, const float *weight, const float *T,
+                         const float *alphainv_last, const int64_t *i_start, const int64_t *i_end,
+                         int64_t n_pts, int64_t n_rays, const float *grad_weights,
+                         const float *grad_last, float *grad_alpha, esr_stream_t stream);
+
+/*
+ * segment_coo(src, index, out=zeros[n_out,C], reduce="sum") — third-party torch_scatter as used
+ * at e.g. app/fine/model/voxurff.py:260-272.  index sorted; out is fully written (no pre-zero).
+ * Backward = gather: grad_src[i,:] = grad_out[index[i],:].
+ */
+int esr_segment_sum_fwd(const float *src, const int64_t *index, int64_t n_pts, int channels,
+                        int64_t n_out, float *out, esr_stream_t stream);
+int esr_segment_sum_bwd(const float *grad_out, const int64_t *index, int64_t n_pts, int channels,
+                        float *grad_src, esr_stream_t stream);
+
+/*
+ * total_variation_add_grad (dense / sparse) — total_variation_kernel.cu:14-35,68-98, incl. the
+ * reference's axis-weight quirk (wz applied on the k and i axes, wx unused).
+ */
+int esr_tv_add_grad(const float *param, float *grad, float wx, float wy, float wz, int64_t sz_i,
+                    int64_t sz_j, int64_t sz_k, int64_t n_total, int dense_mode, esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Fused pipeline (int32 packed streams; one warp per ray for ray-ordered stages)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct esr_scene {
+  float xyz_min[3], xyz_max[3];           /* bbox of the sdf / colour grids (voxurff.py:51-52) */
+  int32_t gx, gy, gz;                     /* grid dims X,Y,Z (world_size, voxurff.py:543) */
+  float mask_xyz_min[3], mask_xyz_max[3]; /* MaskCache bbox (module.py:89-90) */
+  int32_t mx, my, mz;                     /* MaskCache (max-pooled) density dims */
+  float near, far;                        /* far is 1e9 in the wrappers (voxurff.py:633) */
+  float stepdist;                         /* stepsize * voxel_size (voxurff.py:636) */
+  float voxel_size;
+  float act_shift;                        /* log(1/(1-alpha_init)-1), module.py:101 */
+  float mask_thres;                       /* maskcache_thres, 1e-3 */
+  float fast_thres;                       /* fastcolor_thres, 1e-4 */
+  float s_val;                            /* NeuS inverse std */
+} esr_scene_t;
+
+/* exclusive scan of int32 counts: out[i] = sum_{j<i} in[j]; out[n] = total (out has n+1 slots) */
+int esr_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, void *scratch,
+                           esr_stream_t stream);
+
+/*
+ * Stage A/B — march: AABB slab test + per-ray sample count (kernel.cu:12-79), candidate points
+ * (kernel.cu:167-194), AABB filter (voxurff.py:649-652), MaskCache test (module.py:104-114) and the
+ * trilinear SDF tap (voxurff.py:671) in one warp-per-ray pass.  ray_order (nullable) lets the caller
+ * process rays in a permuted order: slot w handles ray ray_order[w]; streams are in slot order.
+ *   count: n_steps[slot], cnt_inbox[slot], cnt_mask[slot]                     (int32)
+ *   fill : s_ray[M1] (original ray index), s_step[M1], s_sdf[M1] at off_mask[slot] + rank
+ */
+int esr_march_count(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                    const int32_t *ray_order, int64_t n_rays, const float *mask_density,
+                    int32_t *n_steps, int32_t *cnt_inbox, int32_t *cnt_mask, esr_stream_t stream);
+int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                   const int32_t *ray_order, int64_t n_rays, const float *mask_density,
+                   const float *sdf_grid, const int32_t *off_mask, int32_t *s_ray, int32_t *s_step,
+                   float *s_sdf, esr_stream_t stream);
+
+/*
+ * Stage C/D — NeuS 'interp' alpha (functions.py:72-105), alpha>thr filter (voxurff.py:201),
+ * transmittance scan with the reference's sequential float/double recurrence and early stop
+ * (kernel.cu:591-603), weight>thr filter (voxurff.py:209).  Warp per ray slot over its M1 segment.
+ *   count: cnt_shade[slot]; alphainv_last[ray]
+ *   fill : h_ray/h_step/h_m1[M3] (int32), h_w/h_sdf[M3]; s_alpha[M1], s_T[M1]
+ *          (s_T = T of the sample, or -1 when the sample is not part of the scan)
+ */
+int esr_alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
+                         const int32_t *off_mask, const float *s_sdf, int32_t *cnt_shade,
+                         float *alphainv_last, esr_stream_t stream);
+int esr_alpha_scan_fill(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
+                        const int32_t *off_mask, const int32_t *s_step, const float *s_sdf,
+                        const int32_t *off_shade, float *s_alpha, float *s_T, int32_t *h_ray,
+                        int32_t *h_step, int32_t *h_m1, float *h_w, float *h_sdf,
+                        esr_stream_t stream);
+
+/*
+ * Stage C' — backward of Alphas2Weights (kernel.cu:653-707) and of the NeuS alpha, then trilinear
+ * scatter of dL/dsdf into the dense SDF gradient volume.
+ *   g_w_m1[M1]: dL/dweight scattered to the M1 stream (zero where not shaded)
+ *   g_last[n_rays]: dL/dalphainv_last
+ */
+int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                       const int32_t *ray_order, int64_t n_rays, const int32_t *off_mask,
+                       const int32_t *s_ray, const int32_t *s_step, const float *s_sdf,
+                       const float *s_alpha, const float *s_T, const float *alphainv_last,
+                       const float *g_w_m1, const float *g_last, float *tmp_dprev, float *tmp_dnext,
+                       int64_t m1, float *grad_sdf_grid, esr_stream_t stream);
+
+/*
+ * Stage E — per shaded sample feature encode (voxurff.py:219-241): 24 multi-scale SDF taps +
+ * 12 normal components (voxurff.py:678-721), colour-grid taps (module.py:24-35), positional /
+ * view encodings.  Internal column order of the 96-wide row (bf16 or f32):
+ *   [off_color 6 | emo_color 6 | sdf 1 | feat 24 | normal 12 | xyz 3 | sin 15 | cos 15 |
+ *    view 3 | sin view 3 | cos view 3 | zero pad 5]
+ * Colour grids are CHANNELS-LAST in memory ([X][Y][Z][C], torch.channels_last_3d of [1,C,X,Y,Z]).
+ * out_is_bf16: 1 -> __nv_bfloat16 rows, 0 -> float rows.
+ */
+#define ESR_FEAT_DIM 96
+#define ESR_FEAT_GRAD_DIM 56 /* columns [0,49) carry gradient; padded to 56 */
+int esr_encode_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                   const float *viewdirs, const float *sdf_grid, const float *off_color_grid,
+                   const float *emo_color_grid, int color_dim, const int32_t *h_ray,
+                   const int32_t *h_step, const float *h_sdf, int64_t m3, void *feat,
+                   int out_is_bf16, esr_stream_t stream);
+/* d_feat: [m3, ESR_FEAT_GRAD_DIM] f32.  Scatter-adds into the three dense gradient volumes. */
+int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                   const float *sdf_grid, int color_dim, const int32_t *h_ray, const int32_t *h_step,
+                   int64_t m3, const float *d_feat, float *grad_sdf_grid, float *grad_off_grid,
+                   float *grad_emo_grid, esr_stream_t stream);
+
+/*
+ * Stage G — combine radiances + tone-map encoding (voxurff.py:243-256, 783-788):
+ *   lin = lin_off (+ lin_emo on emission-on rays); tfeat = [lin, sin(lin*2^f), cos(lin*2^f)] padded
+ *   to 48 columns (bf16 or f32).
+ */
+#define ESR_TFEAT_DIM 48
+#define ESR_TFEAT_GRAD_DIM 40 /* 33 used */
+int esr_tonemap_encode_fwd(const float *lin_off, const float *lin_emo, const int32_t *h_ray,
+                           const int64_t *em_modes, int64_t m3, float *lin, void *tfeat,
+                           int out_is_bf16, esr_stream_t stream);
+/* d_lin = d_lin_direct + dPE(d_tfeat) */
+int esr_tonemap_encode_bwd(const float *lin, const float *d_tfeat, const float *d_lin_direct,
+                           int64_t m3, float *d_lin, esr_stream_t stream);
+
+/*
+ * Stage H — compositing (replaces segment_coo x k, voxurff.py:259-272): warp per ray slot.
+ *   out_a[ray,3] = sum w*a, out_b[ray,3] = sum w*b (b nullable).
+ * Backward (sample parallel): d_a = w*c_a[ray], d_b = w*c_b[ray],
+ *   g_w[h_m1 ? h_m1[j] : j] = a.c_a[ray] + b.c_b[ray]   (h_m1 nullable: gradient stays in M3 order).
+ */
+int esr_composite_fwd(const int32_t *ray_order, int64_t n_rays, const int32_t *off_shade,
+                      const float *h_w, const float *a, const float *b, float *out_a, float *out_b,
+                      esr_stream_t stream);
+int esr_composite_bwd(const int32_t *h_ray, const int32_t *h_m1, const float *h_w, const float *a,
+                      const float *b, const float *c_a, const float *c_b, int64_t m3, float *d_a,
+                      float *d_b, float *g_w_m1, esr_stream_t stream);
+
+/*
+ * Stage F — small MLPs on tensor cores (pbr/module.py:6-39; the only dense contraction on the path).
+ * Packed parameter image (built by esr_mlp_pack): bf16 weights [out][in_padded] per layer followed by
+ * f32 biases; see esr_mlp_desc_t.  Hidden activation ReLU; output activation softplus (1) or
+ * sigmoid (2).
+ */
+typedef struct esr_mlp_desc {
+  int32_t k0;      /* padded input width: multiple of 16 (96 radiance, 48 tonemap) */
+  int32_t width;   /* hidden width: 192 */
+  int32_t n_hidden;/* hidden layers: 3 (radiance nets), 1 (tonemapper) */
+  int32_t n_out;   /* real outputs (<= 8) */
+  int32_t act;     /* 1 softplus, 2 sigmoid */
+} esr_mlp_desc_t;
+
+int64_t esr_mlp_param_count(const esr_mlp_desc_t *d); /* f32 elements of the flat master copy */
+int64_t esr_mlp_image_bytes(const esr_mlp_desc_t *d);
+/*
+ * flat f32 master copy layout: for each layer l: W_l [out_l][in_l_padded] then b_l [out_l]
+ * (output layer padded to 8 rows).  esr_mlp_pack converts it to the bf16 kernel image (+ transposed
+ * copies for the data-gradient pass).
+ */
+int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image, esr_stream_t stream);
+/*
+ * Forward over rows [row_begin,row_end) of x (bf16 [*,k0]).  y: f32 [*,n_out] (activated).
+ * hidden (nullable): bf16 [n_hidden][m_total][width] post-ReLU activations saved for backward.
+ */
+int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t row_begin,
+                int64_t row_end, int64_t m_total, float *y, void *hidden, esr_stream_t stream);
+/*
+ * Backward over rows [row_begin,row_end): d_y is dL/dy (post-activation), y the saved outputs.
+ *   d_x (nullable): f32 [*, dx_cols] gets dL/dx for the first dx_cols input columns
+ *                   (accumulate != 0 adds to existing values).
+ *   d_z: bf16 scratch [n_hidden][m_total][width] + f32 [m_total][8] for the output layer
+ *   grad_flat: f32 flat gradient (same layout as flat_params), ACCUMULATED into (atomics).
+ */
+int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const float *y,
+                const float *d_y, int64_t row_begin, int64_t row_end, int64_t m_total,
+                const void *hidden, void *d_z, float *d_z_out, float *d_x, int dx_cols,
+                int accumulate, float *grad_flat, esr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESR_B200_H */

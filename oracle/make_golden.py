@@ -1,0 +1,126 @@
+"""ORACLE — generates the committed golden vectors in tests/golden/ by running the reference's OWN
+render model (app/fine/model/voxurff.py, imported through oracle/ref_harness.py) on the CPU.
+
+    python -m oracle.make_golden            # needs /root/reference; run in the build container only
+
+Each fixture holds the synthetic inputs' seeds, the reference outputs, the intermediate sample streams
+(post-MaskCache and shaded), and digests of every parameter gradient under fixed random cotangents.
+Grids are regenerated from seeds by esr_nerf_b200.synthetic (deterministic CPU torch), MLP weights are
+stored once in tests/golden/fine_weights.npz.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from esr_nerf_b200 import synthetic as S  # noqa: E402
+from oracle import ref_harness as H  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (num_voxels, mask_res, sparse, n_rays, s_val, ray_seed)
+    "fine_sparse_s20": (40 ** 3, 20, True, 128, 20.0, 1234),
+    "fine_dense_s220": (40 ** 3, 20, False, 128, 220.0, 4321),
+    "fine_sparse_s60_big": (64 ** 3, 32, True, 192, 60.0, 99),
+}
+GRAD_PROBES = 4096
+
+
+def build_reference_model(num_voxels, mask_res, sparse, s_val, weights=None):
+    _, _, VoxurfF, _ = H.reference_classes()
+    cfg = H.fine_cfg()
+    torch.manual_seed(0)
+    m = VoxurfF(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(mask_res, sparse), s_val, num_voxels)
+    if weights is not None:
+        m.load_state_dict({**m.state_dict(), **weights})
+    S.fill_fine_model(m)
+    m.train()
+    return m
+
+
+def mlp_weight_keys(sd):
+    return [k for k in sd if ("rgbnet" in k or "tonemapper" in k)]
+
+
+def cotangents(n, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {"srgb/rgb": torch.randn(n, 3, generator=g), "lin/rgb": torch.randn(n, 3, generator=g),
+            "etc/alphainv_cum": torch.randn(n, generator=g), "etc/white_bg": torch.randn(n, 1, generator=g)}
+
+
+def grad_digest(name, g: torch.Tensor):
+    """sum, abs-sum and GRAD_PROBES seeded probe values of a gradient tensor (logical [1,C,X,Y,Z] / [O,I] order)."""
+    flat = g.detach().contiguous().reshape(-1).double()
+    # (hash() is salted per process -> derive the seed from the name bytes instead)
+    gen = torch.Generator().manual_seed(int.from_bytes(name.encode(), "little") % (2 ** 31))
+    nz = torch.nonzero(flat).reshape(-1)
+    k = min(GRAD_PROBES // 2, nz.numel())
+    pick_nz = nz[torch.randperm(nz.numel(), generator=gen)[:k]] if k else nz[:0]
+    pick_any = torch.randint(0, flat.numel(), (GRAD_PROBES - k,), generator=gen)
+    idx = torch.cat([pick_nz, pick_any])
+    return {f"grad/{name}/sum": flat.sum().item(), f"grad/{name}/abs_sum": flat.abs().sum().item(),
+            f"grad/{name}/idx": idx.numpy().astype(np.int64), f"grad/{name}/val": flat[idx].float().numpy()}
+
+
+def run_case(name, spec, weights):
+    num_voxels, mask_res, sparse, n, s_val, seed = spec
+    m = build_reference_model(num_voxels, mask_res, sparse, s_val, weights)
+    rays = S.make_rays(n, seed)
+    # instrument the stream: re-run the same calls the reference forward makes (voxurff.py:186-213)
+    with torch.no_grad():
+        ray_pts, ray_id, step_id = m.sample_ray(rays_o=rays["rays_o"], rays_d=rays["rays_d"])
+        m0 = ray_pts.shape[0]
+        keep = m.mask_cache(ray_pts)
+        ray_pts, ray_id, step_id = ray_pts[keep], ray_id[keep], step_id[keep]
+        sdf, _ = m.sample_sdf_grad(ray_pts)
+        alpha = m.neus_alpha_from_sdf_scatter(rays["viewdirs"], ray_id, None, sdf, None, s_val)
+        k0 = alpha > m.fastcolor_thres
+        w, T, last, _, _ = H.alpha2weight(alpha[k0], ray_id[k0], n)
+        k1 = w > m.fastcolor_thres
+        m3_ray, m3_step, m3_w = ray_id[k0][k1], step_id[k0][k1], w[k1]
+    out = m(s_val=s_val, rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+            em_modes=rays["em_modes"], rgbs=rays["rgbs"])
+    cot = cotangents(n)
+    loss = sum((out[k] * cot[k]).sum() for k in cot)
+    loss.backward()
+    fx = dict(num_voxels=num_voxels, mask_res=mask_res, sparse=int(sparse), n_rays=n, s_val=s_val, ray_seed=seed,
+              m0=m0, m1_ray=ray_id.numpy().astype(np.int32), m1_step=step_id.numpy().astype(np.int32),
+              m1_sdf=sdf.numpy(), m1_alpha=alpha.numpy(), m3_ray=m3_ray.numpy().astype(np.int32),
+              m3_step=m3_step.numpy().astype(np.int32), m3_weights=m3_w.numpy(), loss=loss.item())
+    for k, v in out.items():
+        fx["out/" + k] = v.detach().numpy()
+    for pname, p in m.named_parameters():
+        if p.grad is not None:
+            fx.update(grad_digest(pname, p.grad))
+    np.savez_compressed(os.path.join(GOLDEN, f"voxurff_{name}.npz"), **fx)
+    print(f"{name}: m0={m0} m1={ray_id.numel()} m3={m3_ray.numel()} loss={loss.item():.6f}")
+
+
+def main():
+    if not H.reference_available():
+        raise SystemExit("reference tree not available; golden vectors can only be generated in the build container")
+    os.makedirs(GOLDEN, exist_ok=True)
+    wpath = os.path.join(GOLDEN, "fine_weights.npz")
+    m = build_reference_model(40 ** 3, 20, True, 20.0)
+    sd = m.state_dict()
+    weights = {k: sd[k].clone() for k in mlp_weight_keys(sd)}
+    # give the biases / last layers non-trivial values so every gradient path is exercised
+    g = torch.Generator().manual_seed(11)
+    for k in weights:
+        if k.endswith("bias"):
+            weights[k] = weights[k] + 0.05 * torch.randn(weights[k].shape, generator=g)
+    np.savez_compressed(wpath, **{k: v.numpy() for k, v in weights.items()})
+    for name, spec in CASES.items():
+        run_case(name, spec, weights)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Shared helpers of the parity tests (golden fixtures, oracle scene dicts, comparisons)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from esr_nerf_b200 import synthetic as S
+from esr_nerf_b200.modules import voxel_geometry
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["fine_sparse_s20", "fine_dense_s220", "fine_sparse_s60_big"]
+
+
+def load_case(name):
+    fx = dict(np.load(os.path.join(GOLDEN, f"voxurff_{name}.npz")))
+    w = dict(np.load(os.path.join(GOLDEN, "fine_weights.npz")))
+    return fx, {k: torch.from_numpy(v) for k, v in w.items()}
+
+
+def cotangents(n, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {"srgb/rgb": torch.randn(n, 3, generator=g), "lin/rgb": torch.randn(n, 3, generator=g),
+            "etc/alphainv_cum": torch.randn(n, generator=g), "etc/white_bg": torch.randn(n, 1, generator=g)}
+
+
+def oracle_scene(num_voxels, mask_res, sparse):
+    """scene dict consumed by oracle/voxurf_port.py, built with the reference's float32 formulas"""
+    from oracle import voxurf_port as P
+
+    voxel_size, world_size = voxel_geometry(S.BBOX_MIN, S.BBOX_MAX, num_voxels)
+    stepdist = 0.5 * voxel_size
+    return dict(xyz_min=S.BBOX_MIN, xyz_max=S.BBOX_MAX, mask_xyz_min=S.BBOX_MIN, mask_xyz_max=S.BBOX_MAX,
+                mask_density_pooled=P.pooled_mask_density(S.mask_density(mask_res, sparse)),
+                act_shift=float(np.log(1 / (1 - S.MASK_ALPHA_INIT) - 1)), mask_thres=1e-3, fast_thres=1e-4,
+                near=S.NEAR, far=S.FAR, stepdist=float(stepdist), voxel_size=float(voxel_size),
+                world_size=[int(w) for w in world_size], grad_feat=[0.5, 1.0, 1.5, 2.0])
+
+
+def oracle_params(scene, weights, requires_grad=True):
+    """grids from the synthetic generator + golden MLP weights, as the dict the port consumes"""
+    from oracle import voxurf_port as P
+
+    ws = scene["world_size"]
+    sd = dict(weights)
+    sd["sdf.grid"] = S.sphere_sdf(ws)
+    sd["off_color.grid"] = S.color_grid(ws, 6, 2)
+    sd["emo_color.grid"] = S.color_grid(ws, 6, 3)
+    leaves = {k: v.clone().float().requires_grad_(requires_grad) for k, v in sd.items()}
+    return P.params_from_state_dict(leaves), leaves
+
+
+def build_product_model(fx, weights, device="cuda:0"):
+    from esr_nerf_b200.voxurff import VoxurfF
+
+    cfg = S.fine_cfg(device=device)
+    m = VoxurfF(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(int(fx["mask_res"]), bool(fx["sparse"])), float(fx["s_val"]), int(fx["num_voxels"]))
+    m.load_state_dict({**m.state_dict(), **weights})
+    S.fill_fine_model(m)
+    return m
+
+
+def digest_check(fx, name, grad: torch.Tensor, rtol, atol_frac=0.1):
+    """compare a gradient tensor (logical layout) with a golden digest; returns max scaled error"""
+    flat = grad.detach().contiguous().reshape(-1).double().cpu()
+    idx = torch.from_numpy(fx[f"grad/{name}/idx"])
+    val = torch.from_numpy(fx[f"grad/{name}/val"]).double()
+    scale = val.abs().max().clamp_min(1e-12)
+    err = ((flat[idx] - val).abs() / (rtol * val.abs() + atol_frac * rtol * scale)).max().item()
+    s_err = abs(flat.abs().sum().item() - float(fx[f"grad/{name}/abs_sum"])) / max(float(fx[f"grad/{name}/abs_sum"]), 1e-12)
+    return err, s_err
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()

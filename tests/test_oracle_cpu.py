@@ -1,0 +1,251 @@
+"""CPU suite (-m "not gpu"): pins the oracle (C restatement + torch port) against the golden vectors the
+reference's own code produced, and — when /root/reference is present — against the reference itself;
+checks host logic and that the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import esr_testlib as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------
+# C restatement: reference semantics and edge cases (render_utils_kernel.cu)
+# ---------------------------------------------------------------------------------------------
+def test_c_oracle_sample_pts_edge_cases():
+    from oracle import ref_harness as H
+
+    mn, mx = torch.tensor([-1.0, -1.0, -1.0]), torch.tensor([1.0, 1.0, 1.0])
+    o = torch.tensor([[0.0, 0.0, -3.0], [5.0, 5.0, 5.0], [0.0, 0.0, -3.0]])
+    d = torch.tensor([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 0.0, 2.0]])  # hit (zero comps), miss, hit |d|=2
+    pts, mask, rid, sid, n, tmin, tmax = H.sample_pts_on_rays(o, d, mn, mx, 0.5, 1e9, 0.25)
+    assert n.tolist()[1] == 1                      # a missing ray still gets one (out-of-box) sample (kernel.cu:52-53)
+    assert n[0] == n[2]                            # count depends on the metric length, not on |d|
+    assert torch.equal(rid, torch.repeat_interleave(torch.arange(3), n))
+    assert sid[0] == 0 and (sid[1:][rid[1:] != rid[:-1]] == 0).all()
+    assert mask[rid == 1].all()
+    assert tmin[0] == 2.0 and tmax[0] == 4.0
+    # empty input
+    e = H.sample_pts_on_rays(o[:0], d[:0], mn, mx, 0.5, 1e9, 0.25)
+    assert e[0].shape == (0, 3) and e[4].numel() == 0
+
+
+def test_c_oracle_alpha2weight_semantics():
+    from oracle import ref_harness as H
+
+    alpha = torch.tensor([0.5, 0.5, 0.999, 0.9, 0.3, 0.2, 0.1])
+    ray_id = torch.tensor([0, 0, 0, 0, 2, 2, 2])
+    w, T, last, i_s, i_e = H.alpha2weight(alpha, ray_id, 4)
+    # ray 0 stops after its third sample (T = .25 * .001 < 1e-3): the 4th keeps weight 0 / T 1 (kernel.cu:597-603)
+    assert w[3] == 0 and T[3] == 1 and i_e[0] == 3
+    assert torch.allclose(w[:3], torch.tensor([0.5, 0.25, 0.25 * 0.999]))
+    assert last[1] == 1 and i_s[1] == 0 and i_e[1] == 0 and last[3] == 1      # rays without samples
+    assert torch.allclose(last[2], torch.tensor(0.7 * 0.8 * 0.9))
+    gw = torch.randn(7)
+    gl = torch.randn(4)
+    g = H.alpha2weight_backward(alpha, w, T, last, i_s, i_e, 4, gw, gl)
+    assert g[3] == 0
+    # autograd check of the recurrence on ray 2
+    a = alpha[4:].clone().double().requires_grad_(True)
+    Tt = torch.cumprod(torch.cat([torch.ones(1, dtype=torch.double), 1 - a]), 0)
+    loss = (Tt[:-1] * a * gw[4:].double()).sum() + Tt[-1] * gl[2].double()
+    loss.backward()
+    assert torch.allclose(g[4:].double(), a.grad, rtol=1e-5, atol=1e-6)
+    # empty stream
+    w0, T0, last0, _, _ = H.alpha2weight(alpha[:0], ray_id[:0], 3)
+    assert w0.numel() == 0 and (last0 == 1).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# torch port vs golden vectors (made by the reference's own code) and vs the reference itself
+# ---------------------------------------------------------------------------------------------
+def _run_port(fx, weights):
+    from esr_nerf_b200 import synthetic as S
+    from oracle import voxurf_port as P
+
+    scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    params, leaves = C.oracle_params(scene, weights)
+    rays = S.make_rays(int(fx["n_rays"]), int(fx["ray_seed"]))
+    out, inter = P.voxurff_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                            rays["em_modes"], float(fx["s_val"]))
+    cot = C.cotangents(int(fx["n_rays"]))
+    loss = sum((out[k] * cot[k]).sum() for k in cot)
+    loss.backward()
+    return out, inter, leaves, loss
+
+
+@pytest.mark.parametrize("case", C.CASES)
+def test_port_matches_golden(case):
+    fx, weights = C.load_case(case)
+    out, inter, leaves, loss = _run_port(fx, weights)
+    assert inter["m0"] == int(fx["m0"])
+    for k in ("m1_ray", "m1_step", "m3_ray", "m3_step"):
+        assert np.array_equal(inter[k].numpy().astype(np.int32), fx[k]), k          # integer streams: bit-exact
+    assert np.array_equal(inter["m3_weights"].detach().numpy(), fx["m3_weights"])   # same C scan -> same bits
+    for k in ("etc/alphainv_cum", "etc/white_bg", "srgb/rgb", "lin/rgb"):
+        assert C.rel_err(out[k], torch.from_numpy(fx["out/" + k])) < 1e-5, k
+    for name, leaf in leaves.items():
+        if f"grad/{name}/idx" in fx and leaf.grad is not None:
+            err, s_err = C.digest_check(fx, name, leaf.grad, rtol=1e-4)
+            assert err < 1.0 and s_err < 1e-4, (name, err, s_err)
+
+
+@pytest.mark.parametrize("case", C.CASES[:1])
+def test_port_matches_reference(case):
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box): golden vectors stand in")
+    from esr_nerf_b200 import synthetic as S
+    from oracle.make_golden import build_reference_model
+
+    fx, weights = C.load_case(case)
+    ref = build_reference_model(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]), float(fx["s_val"]),
+                                weights)
+    rays = S.make_rays(int(fx["n_rays"]), 777)   # rays the fixtures have never seen
+    ref_out = ref(s_val=float(fx["s_val"]), **rays)
+    from oracle import voxurf_port as P
+
+    scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    assert scene["world_size"] == [int(w) for w in ref.world_size]
+    assert abs(scene["stepdist"] - float(ref.stepsize * ref.voxel_size)) == 0
+    params, leaves = C.oracle_params(scene, weights)
+    out, _ = P.voxurff_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                        rays["em_modes"], float(fx["s_val"]))
+    cot = C.cotangents(int(fx["n_rays"]))
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    ref_grads = dict(ref.named_parameters())
+    for name, leaf in leaves.items():
+        if name in ref_grads and ref_grads[name].grad is not None:
+            assert C.rel_err(leaf.grad, ref_grads[name].grad) < 1e-5, name
+
+
+def test_eval_port_matches_reference():
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import voxurf_port as P
+    from oracle.make_golden import build_reference_model
+
+    fx, weights = C.load_case("fine_sparse_s20")
+    ref = build_reference_model(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]), 20.0, weights)
+    ref.eval()
+    rays = S.make_rays(64, 5)
+    pos_rt = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(3)))[0]
+    scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    params, _ = C.oracle_params(scene, weights, requires_grad=False)
+    for em in (0, 1):
+        with torch.no_grad():
+            r = ref(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+                    em_modes=torch.tensor(em), pos_rt=pos_rt)
+            o, _ = P.voxurff_forward_evaluate(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                              torch.tensor(em), pos_rt, 20.0)
+        assert set(r) == set(o)
+        for k in r:
+            assert C.rel_err(o[k], r[k]) < 1e-5, k
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI + host logic
+# ---------------------------------------------------------------------------------------------
+def test_cabi_exports_every_declared_symbol():
+    from esr_nerf_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "esr_b200.h")).read()
+    declared = set(re.findall(r"\b(esr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = ctypes.CDLL(_lib.build())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.lib().esr_version() >= 100
+    assert ctypes.sizeof(_lib.Scene) == 4 * 26
+
+
+def test_state_dict_contract_and_layout():
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.voxurff import VoxurfF
+
+    m = VoxurfF(S.fine_cfg("cpu"), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(12, True), 20.0, 24 ** 3)
+    keys = list(m.state_dict())
+    expect = ["sdf.grid", "tv_smooth_conv.m.weight", "tv_smooth_conv.m.bias", "off_color.grid"]
+    expect += [f"off_rgbnet.linear.{i}.{p}" for i in ("0", "2.0", "3.0", "4") for p in ("weight", "bias")]
+    expect += ["emo_color.grid"]
+    expect += [f"emo_rgbnet.linear.{i}.{p}" for i in ("0", "2.0", "3.0", "4") for p in ("weight", "bias")]
+    expect += [f"tonemapper.srgb.{i}.{p}" for i in ("0", "2") for p in ("weight", "bias")]
+    assert keys == expect
+    assert m.off_rgbnet.linear[0].weight.shape == (192, 85) and m.tonemapper.srgb[0].weight.shape == (192, 33)
+    assert tuple(m.off_color.grid.shape) == (1, 6, 24, 24, 24)
+    assert m.off_color.grid.is_contiguous(memory_format=torch.channels_last_3d)
+    # a reference-layout checkpoint loads and is re-laid-out channels-last without changing values
+    sd = {k: v.clone().contiguous() for k, v in m.state_dict().items()}
+    sd["off_color.grid"] = torch.randn(1, 6, 24, 24, 24)
+    m.load_state_dict(sd)
+    assert torch.equal(m.off_color.grid.data, sd["off_color.grid"])
+    assert m.off_color.grid.is_contiguous(memory_format=torch.channels_last_3d)
+    from oracle import ref_harness as H
+    if H.reference_available():
+        from oracle.make_golden import build_reference_model
+        ref = build_reference_model(24 ** 3, 12, True, 20.0)
+        assert list(ref.state_dict()) == keys
+        assert [tuple(v.shape) for v in ref.state_dict().values()] == [tuple(v.shape) for v in m.state_dict().values()]
+
+
+def test_flat_param_packing_roundtrip():
+    """internal 96-column order <-> reference 85-column order (voxurff.py:228-254)"""
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.modules import radiance_in_cols
+    from esr_nerf_b200.voxurff import VoxurfF
+
+    m = VoxurfF(S.fine_cfg("cpu"), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(12, True), 20.0, 24 ** 3)
+    for which, net in (("off", m.off_rgbnet), ("emo", m.emo_rgbnet)):
+        flat = m._flat(which)
+        assert flat.numel() == 192 * 96 + 192 + 2 * (192 * 192 + 192) + 8 * 192 + 8
+        w0 = flat[: 192 * 96].reshape(192, 96)
+        x_ref = torch.randn(5, 85)
+        cols = radiance_in_cols(which, "cpu")
+        x_int = torch.zeros(5, 96)
+        for c_int, c_ref in enumerate(cols.tolist()):
+            if c_ref >= 0:
+                x_int[:, c_int] = x_ref[:, c_ref]
+        assert torch.allclose(x_int @ w0.T, x_ref @ net.linear[0].weight.T, atol=1e-5)
+        assert torch.equal(x_int[:, m._ref_cols(which, "cpu")], x_ref)
+        # gradient of the flat image flows back to the nn.Linear parameters
+        flat.sum().backward()
+        assert net.linear[0].weight.grad is not None and net.linear[4].bias.grad is not None
+    other = 6 if True else 0
+    assert (m._flat("off")[: 192 * 96].reshape(192, 96)[:, 6:12] == 0).all()
+    assert (m._flat("emo")[: 192 * 96].reshape(192, 96)[:, 0:6] == 0).all()
+    assert other == 6
+
+
+def test_product_has_no_cpu_path():
+    from esr_nerf_b200 import EsrError
+    from esr_nerf_b200.render_utils import alpha2weight
+
+    with pytest.raises(RuntimeError):
+        alpha2weight(torch.rand(4), torch.zeros(4, dtype=torch.long), 1)
+    from esr_nerf_b200._lib import ptr
+    with pytest.raises(EsrError):
+        ptr(torch.zeros(3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "esr_nerf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "oracle/" not in src, f
