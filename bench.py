@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — train rays/s (fwd+bwd) of the fine-stage render step on B200 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference render path on host CPU cores
+
+Workload: VoxurfF, 256^3 grids, sparse 100^3 MaskCache, 2^16 rays per GPU per
+step, synthetic scene and rays (esr_nerf_b200/synthetic.py), random-init MLPs.  One step =
+renderer(**batch) + fixed scalar loss + backward to every parameter .grad (+ one NCCL allreduce of the
+gradients when N > 1).  Optimizer / TV / logging excluded.
+
+One JSON line on rank 0; keys per the driver contract (+ roofline, cpu_baseline, e2e, clocks, gpu_launches).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "train rays/sec (fwd+bwd)"
+UNIT = "rays/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+# algorithmic FLOPs per shaded sample, forward: radiance net 85->192->192->192->3, tonemapper 33->192->3
+FLOP_RADIANCE = 181_248
+FLOP_TONEMAP = 13_824
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=1 << 16, help="rays per GPU per step")
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--mask-res", type=int, default=100)
+    ap.add_argument("--dense", action="store_true", help="dense MaskCache instead of the sparse shell")
+    ap.add_argument("--s-val", type=float, default=20.0)
+    ap.add_argument("--mlp-mode", default="bf16", choices=["bf16", "torch_fp32"])
+    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            d = json.load(open(path))
+            out = dict(FALLBACK_PEAKS)
+            for k in out:
+                if k in d and d[k]:
+                    out[k] = float(d[k])
+            return out, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+def workload_name(a):
+    return (f"giftbox_w-like fine stage (VoxurfF {a.grid}^3, {'dense' if a.dense else 'sparse'} {a.mask_res}^3 MaskCache, "
+            f"s_val {a.s_val:g}), {a.rays} rays/GPU/step, synthetic scene")
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port (the reference's Python cannot be imported on the GPU box)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_setup(a):
+    import esr_testlib as C
+    from esr_nerf_b200 import synthetic as S
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    scene = C.oracle_scene(a.grid ** 3, a.mask_res, not a.dense)
+    torch.manual_seed(0)
+    weights = random_mlp_weights()
+    params, leaves = C.oracle_params(scene, weights)
+    rays = S.make_rays(a.cpu_rays, 1234)
+    return scene, params, leaves, rays
+
+
+def random_mlp_weights():
+    """PyTorch-default-initialised MLP weights under the reference's state_dict keys (seed 0)."""
+    from esr_nerf_b200.modules import RadianceNet, TonemapNet
+
+    torch.manual_seed(0)
+    nets = {"off_rgbnet": RadianceNet(85, 192, 4), "emo_rgbnet": RadianceNet(85, 192, 4), "tonemapper": TonemapNet(33, 192, 2)}
+    sd = {}
+    for name, net in nets.items():
+        for k, v in net.state_dict().items():
+            sd[f"{name}.{k}"] = v.detach().clone()
+    return sd
+
+
+def loss_fn(out, rgbs):
+    """fixed scalar loss: sRGB MSE + linear MSE + a transmittance term (shape of fine.py:355-382)"""
+    l = ((out["srgb/rgb"] + out["etc/white_bg"] - rgbs) ** 2).mean()
+    l = l + 0.1 * ((out["lin/rgb"] - rgbs) ** 2).mean()
+    l = l + 0.01 * (out["etc/alphainv_cum"] ** 2).mean()
+    return l
+
+
+def cpu_port_step(a, scene, params, leaves, rays):
+    from oracle import voxurf_port as P
+
+    for leaf in leaves.values():
+        leaf.grad = None
+    out, inter = P.voxurff_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                            rays["em_modes"], a.s_val)
+    loss_fn(out, rays["rgbs"]).backward()
+    return inter
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    scene, params, leaves, rays = cpu_port_setup(a)
+    for _ in range(max(a.warmup, 0) and 1):  # one warm-up pass is enough for a CPU port (page-in, thread pool)
+        cpu_port_step(a, scene, params, leaves, rays)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_port_step(a, scene, params, leaves, rays)
+    dt = time.perf_counter() - t0
+    v = a.cpu_rays * a.steps / dt
+    sample = f"{a.cpu_rays} rays/step of the same workload (oracle port of the reference render path, torch CPU, fp32)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def stage_report(L):
+    need = L.esr_stage_timing_report(None, 0)
+    buf = ctypes.create_string_buffer(int(need) + 16)
+    L.esr_stage_timing_report(buf, len(buf))
+    stages = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        stages[name] = (int(cnt), float(ms))
+    return stages
+
+
+def algorithmic_work(stage, c):
+    """(bound, algorithmic bytes or FLOPs of ALL launches of `stage` in one step) — DESIGN.md §4.
+    c: per-step counts N, M0, M1, M3, M3_on (rows the emission net runs on)."""
+    N, M0, M1, M3, M3on = c["N"], c["M0"], c["M1"], c["M3"], c["M3_on"]
+    Mcand = c["Mraw"]
+    taps_fwd = (768 + 192) * M3 + 192 * M3on            # 24 SDF taps + off colour (+ emo colour on its rows)
+    t = {
+        "k_march_count": ("hbm", 24 * N + 32 * M0 + 12 * N),
+        "k_march_fill": ("hbm", 24 * N + 32 * M0 + 32 * M1 + 12 * M1),
+        "k_alpha_scan_count": ("hbm", 4 * M1 + 8 * N),
+        "k_alpha_scan_fill": ("hbm", 8 * M1 + 8 * M1 + 20 * M3),
+        "k_encode_fwd": ("hbm", 8 * M3 + taps_fwd + 192 * M3),
+        "k_encode_bwd": ("hbm", 8 * M3 + 2 * taps_fwd + 224 * M3),
+        "k_alpha_scan_bwd": ("hbm", 16 * M1 + 8 * M1),
+        "k_sdf_scatter": ("hbm", 16 * M1 + 64 * M1),
+        "k_composite_fwd": ("hbm", 28 * M3 + 24 * N),
+        "k_composite_bwd": ("hbm", 32 * M3 + 28 * M3),
+        "k_mlp_fwd_radiance": ("tensor", FLOP_RADIANCE * (M3 + M3on)),
+        "k_mlp_dgrad_radiance": ("tensor", FLOP_RADIANCE * (M3 + M3on)),
+        "k_mlp_wgrad": ("tensor", (FLOP_RADIANCE - 2 * 192 * 3) * (M3 + M3on) + 2 * 33 * 192 * M3),
+        "k_mlp_fwd_tonemap": ("tensor", FLOP_TONEMAP * M3),
+        "k_mlp_dgrad_tonemap": ("tensor", FLOP_TONEMAP * M3),
+    }
+    _ = Mcand
+    return t.get(stage)
+
+
+def run_b200(a, rank, world, local_rank):
+    from esr_nerf_b200 import _lib
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.voxurff import VoxurfF
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    model = VoxurfF(S.fine_cfg(device=str(dev)), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX,
+                    S.MASK_ALPHA_INIT, S.mask_density(a.mask_res, not a.dense), a.s_val, a.grid ** 3)
+    model.load_state_dict({**model.state_dict(), **random_mlp_weights()})
+    S.fill_fine_model(model)
+    model.mlp_mode = a.mlp_mode
+    model.keep_streams = True
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    host = S.make_rays(a.rays, 1234 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    batch = {k: v.to(dev) for k, v in host.items()}
+
+    def step(b):
+        for p in params:
+            p.grad = None
+        out = model(s_val=a.s_val, **b)
+        loss = loss_fn(out, b["rgbs"])
+        loss.backward()
+        if dist is not None:  # rays sharded, gradients summed once per step (north_star)
+            for p in params:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+        return out, loss
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step(batch)
+    sync_all()
+    st = model.last_streams["streams"]
+    counts = {"N": a.rays, "Mraw": int(st.n_steps.sum()), "M0": int(st.cnt_inbox.sum()), "M1": st.m1, "M3": st.m3,
+              "M3_on": st.m3_on}
+
+    # ---- device-resident timed region (value) with per-kernel events (roofline) ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    L.esr_stage_timing(1)
+    launches0 = L.esr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(a.steps):
+        step(batch)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = L.esr_launch_count() - launches0
+    stages = stage_report(L)
+    L.esr_stage_timing(0)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- end-to-end region: pinned host rays -> H2D, step, D2H of the rendered outputs ----
+    e2e = None
+    if not a.no_e2e:
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = 0
+        sync_all()
+        e0.record()
+        for _ in range(a.steps):
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            out, loss = step(b)
+            res = [out["srgb/rgb"].detach().cpu(), out["lin/rgb"].detach().cpu(), out["etc/alphainv_cum"].detach().cpu(),
+                   loss.detach().cpu()]
+            d2h = sum(r.numel() * r.element_size() for r in res)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": a.rays * world * a.steps / (float(t.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    stage_rows = []
+    for name, (cnt, tot) in stages.items():
+        w = algorithmic_work(name, counts)
+        row = {"kernel": name, "launches_per_step": cnt / a.steps, "ms_per_step": tot / a.steps}
+        if w is not None:
+            bound, work = w
+            per_s = work / (tot / a.steps * 1e-3) if tot > 0 else 0.0
+            if bound == "hbm":
+                row.update(bound="hbm", achieved=per_s / 1e9, unit="GB/s", frac=per_s / 1e9 / pk["hbm_gbs"])
+            else:
+                row.update(bound="tensor", achieved=per_s / 1e12, unit="TFLOP/s",
+                           frac=per_s / 1e12 / pk["bf16_tflops_sustained"])
+        stage_rows.append(row)
+    stage_rows.sort(key=lambda r: -r["ms_per_step"])
+    top = next((r for r in stage_rows if "bound" in r), None)
+    roofline = None
+    if top is not None:
+        roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
+                    "peak": pk["hbm_gbs"] if top["bound"] == "hbm" else pk["bf16_tflops_sustained"],
+                    "unit": top["unit"], "frac": top["frac"], "traffic": None, "peak_source": pk_src,
+                    "avg_launch_ms": top["ms_per_step"] / max(top["launches_per_step"], 1e-9),
+                    "share_of_kernel_time": top["ms_per_step"] / max(sum(r["ms_per_step"] for r in stage_rows), 1e-9)}
+
+    cpu_baseline = None
+    if world == 1 and not a.no_cpu_baseline:
+        scene, cparams, leaves, crays = cpu_port_setup(a)
+        cpu_port_step(a, scene, cparams, leaves, crays)
+        reps = 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cpu_port_step(a, scene, cparams, leaves, crays)
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {"value": a.cpu_rays / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"{a.cpu_rays} rays/step of the same workload, oracle port (torch CPU fp32), "
+                                  f"1 warm-up + {reps} timed steps"}
+
+    total_rays = a.rays * world * a.steps
+    line = {
+        "metric": METRIC, "value": total_rays / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (grids, scan, compositing) + bf16 tensor-core MLPs, f32 accumulate"
+        if a.mlp_mode == "bf16" else "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "parallelism": f"dp{world} (rays sharded, gradient allreduce)",
+                   "l2": "working set (0.83 GB of grids + grads) exceeds the 126 MB L2; no flush between steps",
+                   "counts_per_gpu_step": counts,
+                   "samples_per_s": {"candidate_M0": counts["M0"] * world * a.steps / (ms * 1e-3),
+                                     "shaded_M3": counts["M3"] * world * a.steps / (ms * 1e-3)}},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "kernels": stage_rows[:12],
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_b200(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,8 @@ PROTOTYPES = {
     "esr_last_error": (ctypes.c_char_p, []),
     "esr_version": (I32, []),
     "esr_launch_count": (I64, []),
+    "esr_stage_timing": (I32, [I32]),
+    "esr_stage_timing_report": (I64, [ctypes.c_char_p, I64]),
     "esr_scan_scratch_bytes": (I64, [I64]),
     "esr_sample_pts_on_rays_count": (I32, [P, P, F3P, F3P, F32, F32, F32, I64, P, P, P, P, P, P, P]),
     "esr_sample_pts_on_rays_fill": (I32, [P, P, F3P, F3P, F32, F32, F32, I64, P, I64, P, P, P, P, P]),

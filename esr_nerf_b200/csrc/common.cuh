@@ -15,6 +15,14 @@ namespace esr {
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 
+// Per-kernel device timing for bench.py's roofline block: when enabled through esr_stage_timing(1) every
+// launch site brackets its kernel with a pair of CUDA events on the launching stream (ESR_STAGE before the
+// launch, ESR_LAUNCH_OK after it); esr_stage_timing_report sums the elapsed times per stage name.
+// Disabled (the default) it costs one branch per launch.
+void stage_begin(const char *name, cudaStream_t st);
+void stage_end();
+#define ESR_STAGE(name, stream) esr::stage_begin(name, (cudaStream_t)(stream))
+
 #define ESR_CHECK_ARG(cond)                                                  \
   do {                                                                       \
     if (!(cond)) {                                                           \
@@ -36,6 +44,7 @@ void count_launch(int n = 1);
 // check the launch that was just issued (sticky-free peek) and count it
 #define ESR_LAUNCH_OK()                  \
   do {                                   \
+    esr::stage_end();                    \
     esr::count_launch();                 \
     ESR_CHECK_CUDA(cudaGetLastError());  \
   } while (0)

@@ -374,6 +374,7 @@ extern "C" int esr_encode_fwd(const esr_scene_t *sc, const float *rays_o, const 
   ESR_CHECK_ARG(rays_o && rays_d && viewdirs && sdf_grid && off_color_grid && emo_color_grid && h_ray && h_step &&
                 h_sdf && feat);
   cudaStream_t st = (cudaStream_t)stream;
+  ESR_STAGE("k_encode_fwd", st);
   if (out_is_bf16)
     k_encode_fwd<__nv_bfloat16><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,
                                                                emo_color_grid, h_ray, h_step, h_sdf, m3,
@@ -394,6 +395,7 @@ extern "C" int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const 
   ESR_CHECK_ARG(m3 >= 0);
   if (m3 == 0) return ESR_OK;
   ESR_CHECK_ARG(rays_o && rays_d && sdf_grid && h_ray && h_step && d_feat && grad_sdf_grid);
+  ESR_STAGE("k_encode_bwd", (cudaStream_t)stream);
   k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
                                                                 d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid);
   ESR_LAUNCH_OK();
@@ -407,6 +409,7 @@ extern "C" int esr_tonemap_encode_fwd(const float *lin_off, const float *lin_emo
   if (m3 == 0) return ESR_OK;
   ESR_CHECK_ARG(lin_off && lin && tfeat && (!lin_emo || (h_ray && em_modes)));
   cudaStream_t st = (cudaStream_t)stream;
+  ESR_STAGE("k_tonemap_encode_fwd", st);
   if (out_is_bf16)
     k_tonemap_encode_fwd<__nv_bfloat16>
         <<<cdiv(m3, 256), 256, 0, st>>>(lin_off, lin_emo, h_ray, em_modes, m3, lin, (__nv_bfloat16 *)tfeat);
@@ -422,6 +425,7 @@ extern "C" int esr_tonemap_encode_bwd(const float *lin, const float *d_tfeat, co
   ESR_CHECK_ARG(m3 >= 0);
   if (m3 == 0) return ESR_OK;
   ESR_CHECK_ARG(lin && d_tfeat && d_lin);
+  ESR_STAGE("k_tonemap_encode_bwd", (cudaStream_t)stream);
   k_tonemap_encode_bwd<<<cdiv(m3, 256), 256, 0, (cudaStream_t)stream>>>(lin, d_tfeat, d_lin_direct, m3, d_lin);
   ESR_LAUNCH_OK();
   return ESR_OK;
@@ -433,6 +437,7 @@ extern "C" int esr_composite_fwd(const int32_t *ray_order, int64_t n_rays, const
   if (n_rays == 0) return ESR_OK;
   ESR_CHECK_ARG(off_shade && out_a && (!b || out_b));
   const int64_t want = (n_rays + 7) / 8, cap = (int64_t)num_sms() * 32;
+  ESR_STAGE("k_composite_fwd", (cudaStream_t)stream);
   k_composite_fwd<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(ray_order, n_rays, off_shade,
                                                                                          h_w, a, b, out_a, out_b);
   ESR_LAUNCH_OK();
@@ -445,6 +450,7 @@ extern "C" int esr_composite_bwd(const int32_t *h_ray, const int32_t *h_m1, cons
   ESR_CHECK_ARG(m3 >= 0);
   if (m3 == 0) return ESR_OK;
   ESR_CHECK_ARG(h_ray && h_w && a && c_a && d_a && g_w_m1 && (!b || (c_b && d_b)));
+  ESR_STAGE("k_composite_bwd", (cudaStream_t)stream);
   k_composite_bwd<<<cdiv(m3, 256), 256, 0, (cudaStream_t)stream>>>(h_ray, h_m1, h_w, a, b, c_a, c_b, m3, d_a, d_b,
                                                                    g_w_m1);
   ESR_LAUNCH_OK();

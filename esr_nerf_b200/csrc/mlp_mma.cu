@@ -592,6 +592,7 @@ static int run_fwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
   auto kern = k_mlp_fwd<K0, W, NH>;
   constexpr int bytes = FwdSmem<K0, W, NH>::bytes;
   if (int e = set_smem(kern, bytes)) return e;
+  ESR_STAGE(K0 == 96 ? "k_mlp_fwd_radiance" : "k_mlp_fwd_tonemap", st);
   kern<<<persistent_grid(re - rb), MLP_THREADS, bytes, st>>>(L, (const uint8_t *)image, (const __nv_bfloat16 *)x, rb,
                                                              re, mt, y, (__nv_bfloat16 *)hidden, d->n_out, d->act);
   ESR_LAUNCH_OK();
@@ -605,6 +606,7 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
   auto kern = k_mlp_dgrad<K0, W, NH, DXP>;
   constexpr int bytes = BwdSmem<K0, W, NH, DXP>::bytes;
   if (int e = set_smem(kern, bytes)) return e;
+  ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_radiance" : "k_mlp_dgrad_tonemap", st);
   kern<<<persistent_grid(re - rb), MLP_THREADS, bytes, st>>>(L, (const uint8_t *)image, y, d_y, rb, re, mt,
                                                              (const __nv_bfloat16 *)hidden, (__nv_bfloat16 *)d_z,
                                                              d_z_out, d_x, dx_cols, accumulate, d->n_out, d->act);
@@ -617,6 +619,7 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
   // layer 0: In = x
   constexpr int wg_bytes0 = 2 * WG_KSTEP * ((W + 8) + (K0 + 8)) * 2, wg_bytes = 2 * WG_KSTEP * 2 * (W + 8) * 2;
   if (int e = set_smem(k_mlp_wgrad<W, K0>, wg_bytes0)) return e;
+  ESR_STAGE("k_mlp_wgrad", st);
   k_mlp_wgrad<W, K0><<<grid, MLP_THREADS, wg_bytes0, st>>>(Z, (const __nv_bfloat16 *)x, rb, re,
                                                            grad_flat + L.flat_w(0), grad_flat + L.flat_b(0));
   ESR_LAUNCH_OK();
@@ -624,11 +627,13 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
     if (int e = set_smem(k_mlp_wgrad<W, W>, wg_bytes)) return e;
   }
   for (int l = 1; l < NH; ++l) {
+    ESR_STAGE("k_mlp_wgrad", st);
     k_mlp_wgrad<W, W><<<grid, MLP_THREADS, wg_bytes, st>>>(Z + (int64_t)l * mt * W, H + (int64_t)(l - 1) * mt * W, rb,
                                                            re, grad_flat + L.flat_w(l), grad_flat + L.flat_b(l));
     ESR_LAUNCH_OK();
   }
   const unsigned grid_o = (unsigned)max((int64_t)1, min((int64_t)num_sms() * 4, (rows + 63) / 64));
+  ESR_STAGE("k_mlp_wgrad_out", st);
   k_mlp_wgrad_out<W><<<grid_o, W, 0, st>>>(d_z_out, H + (int64_t)(NH - 1) * mt * W, rb, re, d->n_out,
                                            grad_flat + L.flat_w(NH), grad_flat + L.flat_b(NH));
   ESR_LAUNCH_OK();
@@ -652,6 +657,7 @@ extern "C" int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, v
   ESR_CHECK_ARG(flat_params && image);
   const MlpLayout L = layout_of(d);
   const int64_t n = max(max(L.img_fwd_elems(), L.imgT_elems()), L.n_bias());
+  ESR_STAGE("k_mlp_pack", (cudaStream_t)stream);
   k_mlp_pack<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(L, flat_params, (uint8_t *)image);
   ESR_LAUNCH_OK();
   return ESR_OK;

@@ -3,8 +3,13 @@
 // alpha2weight_backward; torch_scatter.segment_coo(sum); total_variation_add_grad.
 // int64 indices / bool masks at this boundary, exactly like the reference.
 #include <stdarg.h>
+#include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -19,7 +24,88 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct TimingRec {
+  const char *name;
+  cudaEvent_t a, b;
+};
+static std::atomic<bool> g_timing{false};
+static std::mutex g_timing_mu;
+static std::vector<TimingRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t get_event() {
+  cudaEvent_t e;
+  if (!g_event_pool.empty()) {
+    e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEventCreate(&e);
+  return e;
+}
+
+static thread_local int g_pending = -1;
+static thread_local cudaStream_t g_pending_stream = nullptr;
+
+void stage_begin(const char *name, cudaStream_t st) {
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  TimingRec r{name, get_event(), get_event()};
+  cudaEventRecord(r.a, st);
+  g_pending = (int)g_recs.size();
+  g_pending_stream = st;
+  g_recs.push_back(r);
+}
+void stage_end() {
+  if (g_pending < 0) return;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  if (g_pending < (int)g_recs.size()) cudaEventRecord(g_recs[g_pending].b, g_pending_stream);
+  g_pending = -1;
+}
 }  // namespace esr
+
+extern "C" int esr_stage_timing(int enable) {
+  std::lock_guard<std::mutex> lk(esr::g_timing_mu);
+  for (auto &r : esr::g_recs) {
+    esr::g_event_pool.push_back(r.a);
+    esr::g_event_pool.push_back(r.b);
+  }
+  esr::g_recs.clear();
+  esr::g_timing.store(enable != 0);
+  return ESR_OK;
+}
+
+extern "C" int64_t esr_stage_timing_report(char *buf, int64_t buf_bytes) {
+  std::lock_guard<std::mutex> lk(esr::g_timing_mu);
+  std::map<std::string, std::pair<long long, double>> acc;
+  std::vector<std::string> order;
+  for (auto &r : esr::g_recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    auto it = acc.find(r.name);
+    if (it == acc.end()) {
+      order.push_back(r.name);
+      acc[r.name] = {1, (double)ms};
+    } else {
+      it->second.first += 1;
+      it->second.second += ms;
+    }
+  }
+  std::string out;
+  char line[256];
+  for (auto &n : order) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", n.c_str(), acc[n].first, acc[n].second);
+    out += line;
+  }
+  if (buf && buf_bytes > 0) {
+    const int64_t k = (int64_t)out.size() < buf_bytes - 1 ? (int64_t)out.size() : buf_bytes - 1;
+    memcpy(buf, out.data(), (size_t)k);
+    buf[k] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
 
 using namespace esr;
 
@@ -86,6 +172,7 @@ extern "C" int esr_sample_pts_on_rays_count(const float *rays_o, const float *ra
   ESR_CHECK_ARG(rays_o && rays_d && xyz_min && xyz_max && N_steps && N_cum && t_min && t_max);
   Box box;
   for (int i = 0; i < 3; ++i) box.mn[i] = xyz_min[i], box.mx[i] = xyz_max[i];
+  ESR_STAGE("k_ray_counts", st);
   k_ray_counts<<<cdiv(n_rays, 256), 256, 0, st>>>(rays_o, rays_d, box, near, far, stepdist, n_rays, N_steps, t_min,
                                                   t_max);
   ESR_LAUNCH_OK();
@@ -103,6 +190,7 @@ extern "C" int esr_sample_pts_on_rays_fill(const float *rays_o, const float *ray
   Box box;
   for (int i = 0; i < 3; ++i) box.mn[i] = xyz_min[i], box.mx[i] = xyz_max[i];
   const int64_t blocks = min((int64_t)cdiv(n_rays, 8), (int64_t)num_sms() * 16);
+  ESR_STAGE("k_ray_fill", (cudaStream_t)stream);
   k_ray_fill<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, box, near, far, stepdist, n_rays,
                                                                  N_cum, ray_pts, mask_outbbox, ray_id, step_id);
   ESR_LAUNCH_OK();
@@ -224,10 +312,12 @@ extern "C" int esr_alpha2weight_fwd(const float *alpha, const int64_t *ray_id, i
   ESR_CHECK_CUDA(cudaMemsetAsync(i_end, 0, sizeof(int64_t) * n_rays, st));
   if (n_pts > 0) {
     ESR_CHECK_ARG(alpha && ray_id && weight && T);
+    ESR_STAGE("k_segments", st);
     k_segments<<<cdiv(n_pts, 256), 256, 0, st>>>(ray_id, n_pts, i_start, i_end);
     ESR_LAUNCH_OK();
   }
   const int64_t blocks = min((int64_t)cdiv(n_rays, 8), (int64_t)num_sms() * 16);
+  ESR_STAGE("k_alpha2weight", st);
   k_alpha2weight<<<(unsigned)blocks, 256, 0, st>>>(alpha, n_rays, weight, T, alphainv_last, i_start, i_end);
   ESR_LAUNCH_OK();
   return ESR_OK;
@@ -244,6 +334,7 @@ extern "C" int esr_alpha2weight_bwd(const float *alpha, const float *weight, con
   ESR_CHECK_CUDA(cudaMemsetAsync(grad_alpha, 0, sizeof(float) * n_pts, st));
   if (n_rays == 0) return ESR_OK;
   const int64_t blocks = min((int64_t)cdiv(n_rays, 8), (int64_t)num_sms() * 16);
+  ESR_STAGE("k_alpha2weight_bwd", st);
   k_alpha2weight_bwd<<<(unsigned)blocks, 256, 0, st>>>(alpha, weight, T, alphainv_last, i_start, i_end, n_rays,
                                                        grad_weights, grad_last, grad_alpha);
   ESR_LAUNCH_OK();
@@ -293,6 +384,7 @@ extern "C" int esr_segment_sum_fwd(const float *src, const int64_t *index, int64
   ESR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_out * channels, st));
   if (n_pts == 0) return ESR_OK;
   ESR_CHECK_ARG(src && index);
+  ESR_STAGE("k_segment_sum", st);
   k_segment_sum<<<cdiv(n_pts, 256), 256, 0, st>>>(src, index, n_pts, channels, out);
   ESR_LAUNCH_OK();
   return ESR_OK;
@@ -304,6 +396,7 @@ extern "C" int esr_segment_sum_bwd(const float *grad_out, const int64_t *index, 
   if (n_pts == 0) return ESR_OK;
   ESR_CHECK_ARG(grad_out && index && grad_src);
   const int64_t n = n_pts * channels;
+  ESR_STAGE("k_segment_gather", (cudaStream_t)stream);
   k_segment_gather<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, index, n, channels, grad_src);
   ESR_LAUNCH_OK();
   return ESR_OK;
@@ -342,6 +435,7 @@ extern "C" int esr_tv_add_grad(const float *param, float *grad, float wx, float 
   if (n_total == 0) return ESR_OK;
   wy /= 6;
   wz /= 6;
+  ESR_STAGE("k_tv_add_grad", stream);
   if (dense_mode)
     k_tv_add_grad<true><<<cdiv(n_total, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, wy, wz, sz_i, sz_j, sz_k,
                                                                               n_total);

@@ -108,10 +108,13 @@ int device_scan(const Tin *in, T *out, int64_t n, T *total_out, void *scratch, c
   }
   const int nblocks = (int)cdiv(n, SCAN_TILE);
   T *tot = EXCLUSIVE ? out + n : (total_out ? total_out : sums + nblocks);
+  ESR_STAGE("scan_block_sums", st);
   scan_block_sums<Tin, T><<<nblocks, SCAN_THREADS, 0, st>>>(in, n, sums);
   ESR_LAUNCH_OK();
+  ESR_STAGE("scan_of_sums", st);
   scan_of_sums<T><<<1, SCAN_THREADS, 0, st>>>(sums, nblocks, tot);
   ESR_LAUNCH_OK();
+  ESR_STAGE("scan_apply", st);
   scan_apply<Tin, T, EXCLUSIVE><<<nblocks, SCAN_THREADS, 0, st>>>(in, n, sums, out);
   ESR_LAUNCH_OK();
   if (EXCLUSIVE && total_out) ESR_CHECK_CUDA(cudaMemcpyAsync(total_out, tot, sizeof(T), cudaMemcpyDeviceToDevice, st));

@@ -74,6 +74,7 @@ extern "C" int esr_march_count(const esr_scene_t *sc, const float *rays_o, const
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
   ESR_CHECK_ARG(rays_o && rays_d && mask_density && n_steps && cnt_inbox && cnt_mask);
+  ESR_STAGE("k_march_count", (cudaStream_t)stream);
   k_march<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
                                                                        mask_density, nullptr, n_steps, cnt_inbox,
                                                                        cnt_mask, nullptr, nullptr, nullptr, nullptr);
@@ -88,7 +89,9 @@ extern "C" int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const 
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
-  ESR_CHECK_ARG(rays_o && rays_d && mask_density && sdf_grid && off_mask && s_ray && s_step && s_sdf);
+  // s_* may be NULL when the stream is empty (M1 == 0): they are only written for surviving samples
+  ESR_CHECK_ARG(rays_o && rays_d && mask_density && sdf_grid && off_mask);
+  ESR_STAGE("k_march_fill", (cudaStream_t)stream);
   k_march<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
                                                                       mask_density, sdf_grid, nullptr, nullptr,
                                                                       nullptr, off_mask, s_ray, s_step, s_sdf);
@@ -177,6 +180,7 @@ extern "C" int esr_alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_or
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
   ESR_CHECK_ARG(off_mask && cnt_shade && alphainv_last);
+  ESR_STAGE("k_alpha_scan_count", (cudaStream_t)stream);
   k_alpha_scan<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(
       *sc, ray_order, n_rays, off_mask, nullptr, s_sdf, nullptr, cnt_shade, alphainv_last, nullptr, nullptr, nullptr,
       nullptr, nullptr, nullptr, nullptr);
@@ -191,7 +195,9 @@ extern "C" int esr_alpha_scan_fill(const esr_scene_t *sc, const int32_t *ray_ord
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
-  ESR_CHECK_ARG(off_mask && s_step && off_shade && s_alpha && s_T && h_ray && h_step && h_m1 && h_w && h_sdf);
+  // stream pointers may be NULL when the corresponding stream is empty (M1 == 0 / M3 == 0)
+  ESR_CHECK_ARG(off_mask && off_shade);
+  ESR_STAGE("k_alpha_scan_fill", (cudaStream_t)stream);
   k_alpha_scan<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(
       *sc, ray_order, n_rays, off_mask, s_step, s_sdf, off_shade, nullptr, nullptr, s_alpha, s_T, h_ray, h_step, h_m1,
       h_w, h_sdf);
@@ -301,9 +307,11 @@ extern "C" int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, co
   ESR_CHECK_ARG(rays_o && rays_d && off_mask && s_ray && s_step && s_sdf && s_alpha && s_T && alphainv_last &&
                 g_w_m1 && tmp_dprev && tmp_dnext && grad_sdf_grid);
   cudaStream_t st = (cudaStream_t)stream;
+  ESR_STAGE("k_alpha_scan_bwd", st);
   k_alpha_scan_bwd<<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, s_alpha, s_T,
                                                        alphainv_last, g_w_m1, g_last, tmp_dprev, tmp_dnext);
   ESR_LAUNCH_OK();
+  ESR_STAGE("k_sdf_scatter", st);
   k_sdf_scatter<<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,
                                                grad_sdf_grid);
   ESR_LAUNCH_OK();

@@ -33,6 +33,14 @@ const char *esr_last_error(void);
 int esr_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t esr_launch_count(void);
+/*
+ * Per-kernel device timing (measurement only; bench.py's roofline block).  esr_stage_timing(1) clears the
+ * records and makes every launch site bracket its kernel with CUDA events on the launching stream;
+ * esr_stage_timing_report synchronises those events and writes one line per stage, "name launches total_ms\n",
+ * into buf (NUL-terminated, truncated to buf_bytes) and returns the number of bytes the full report needs.
+ */
+int esr_stage_timing(int enable);
+int64_t esr_stage_timing_report(char *buf, int64_t buf_bytes);
 
 /* ------------------------------------------------------------------------------------------
  * 1. Native-op replacements (reference-shaped: int64 indices, bool masks)

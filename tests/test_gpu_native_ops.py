@@ -1,0 +1,160 @@
+"""GPU parity (-m gpu) of the reference-shaped native ops served through the C ABI
+(include/esr_b200.h section 1) against the C oracle (oracle/render_utils_ref.c, a restatement of
+app/utils/base/cuda/render_utils_kernel.cu).  Integer / index / mask outputs are compared bit-exactly;
+fp32 outputs bit-exactly where the op order is the reference's, else within the tolerance written
+beside the assert."""
+import numpy as np
+import pytest
+import torch
+
+import esr_testlib as C
+from esr_nerf_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from esr_nerf_b200 import render_utils as R
+    from oracle import ref_harness as H
+    return R, H
+
+
+def _rays(n, seed, miss_frac=0.1, zero_comp=True):
+    r = S.make_rays(n, seed)
+    o, d = r["rays_o"].clone(), r["rays_d"].clone()
+    g = torch.Generator().manual_seed(seed + 1)
+    k = int(n * miss_frac)
+    if k:  # rays that miss the box entirely
+        d[:k] = -d[:k]
+    if zero_comp and n >= 8:  # exact-zero direction components hit the 1e-6 substitution (kernel.cu:23-25)
+        d[k:k + 3, 0] = 0.0
+        d[k + 3:k + 5, 1] = 0.0
+        o[k + 5] = torch.tensor([0.0, 0.0, -3.0])
+        d[k + 5] = torch.tensor([0.0, 0.0, 1.1])
+    _ = g
+    return o.contiguous(), d.contiguous()
+
+
+@pytest.mark.parametrize("n,stepdist,near", [(257, 0.021, 2.0), (2000, 0.0041, 2.0), (64, 0.05, 1e-5), (1, 0.01, 2.0)])
+def test_sample_pts_on_rays_bit_exact(n, stepdist, near):
+    R, H = _ops()
+    o, d = _rays(n, 10 + n)
+    mn, mx = S.BBOX_MIN, S.BBOX_MAX
+    ref = H.sample_pts_on_rays(o, d, mn, mx, near, 1e9, stepdist)
+    got = R.render_utils_cuda.sample_pts_on_rays(o.to(DEV), d.to(DEV), mn.to(DEV), mx.to(DEV), near, 1e9, stepdist)
+    names = ["ray_pts", "mask_outbbox", "ray_id", "step_id", "N_steps", "t_min", "t_max"]
+    assert got[1].dtype == torch.bool and got[2].dtype == torch.int64 and got[4].dtype == torch.int64
+    for name, a, b in zip(names, got, ref):
+        assert a.shape == b.shape, name
+        assert torch.equal(a.cpu(), b), name          # bit-exact, floats included (same op order and FMA shape)
+    # sortedness / packing invariants the reference's callers rely on
+    rid = got[2].cpu()
+    assert (rid[1:] >= rid[:-1]).all()
+    assert torch.equal(torch.bincount(rid, minlength=n), got[4].cpu())
+
+
+def test_sample_pts_on_rays_empty_and_errors():
+    R, _ = _ops()
+    mn, mx = S.BBOX_MIN.to(DEV), S.BBOX_MAX.to(DEV)
+    e = R.render_utils_cuda.sample_pts_on_rays(torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, device=DEV), mn, mx,
+                                                2.0, 1e9, 0.01)
+    assert e[0].shape == (0, 3) and e[2].numel() == 0 and e[4].numel() == 0
+    with pytest.raises(RuntimeError):   # render_utils.cpp:46-48 CHECK_INPUT semantics
+        R.render_utils_cuda.sample_pts_on_rays(torch.zeros(4, 3), torch.zeros(4, 3, device=DEV), mn, mx, 2.0, 1e9, 0.01)
+    with pytest.raises(RuntimeError):
+        R.render_utils_cuda.sample_pts_on_rays(torch.zeros(3, 4, device=DEV).t(), torch.zeros(4, 3, device=DEV), mn,
+                                                mx, 2.0, 1e9, 0.01)
+
+
+def _alpha_stream(n_rays, seed, max_len=300, opaque_frac=0.3, empty_frac=0.2):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(0, max_len, (n_rays,), generator=g)
+    lens[torch.rand(n_rays, generator=g) < empty_frac] = 0
+    if n_rays > 3:
+        lens[1] = 1           # single-sample ray
+        lens[2] = 33          # one past a warp chunk
+        lens[3] = 32
+    ray_id = torch.repeat_interleave(torch.arange(n_rays), lens)
+    m = ray_id.numel()
+    alpha = torch.rand(m, generator=g) * 0.05
+    opaque = torch.rand(n_rays, generator=g) < opaque_frac
+    alpha = torch.where(opaque[ray_id] & (torch.rand(m, generator=g) < 0.2), torch.rand(m, generator=g), alpha)
+    return alpha.contiguous(), ray_id.contiguous()
+
+
+@pytest.mark.parametrize("n_rays,seed", [(5, 0), (300, 1), (4096, 2)])
+def test_alpha2weight_fwd_bit_exact_bwd_close(n_rays, seed):
+    R, H = _ops()
+    alpha, ray_id = _alpha_stream(n_rays, seed)
+    w, T, last, i_s, i_e = H.alpha2weight(alpha, ray_id, n_rays)
+    gw, gT, glast, gi_s, gi_e = R.render_utils_cuda.alpha2weight(alpha.to(DEV), ray_id.to(DEV), n_rays)
+    # early-stop index, weights, T and alphainv_last: bit-exact (sequential float/double recurrence, kernel.cu:591-603)
+    assert torch.equal(gi_e.cpu(), i_e) and torch.equal(gi_s.cpu(), i_s)
+    assert torch.equal(gw.cpu(), w) and torch.equal(gT.cpu(), T) and torch.equal(glast.cpu(), last)
+    g = torch.Generator().manual_seed(seed + 100)
+    grad_w, grad_last = torch.randn(alpha.shape, generator=g), torch.randn(n_rays, generator=g)
+    ref = H.alpha2weight_backward(alpha, w, T, last, i_s, i_e, n_rays, grad_w, grad_last)
+    got = R.render_utils_cuda.alpha2weight_backward(gw.new_tensor(alpha), gw, gT, glast, gi_s, gi_e, n_rays,
+                                                    grad_w.to(DEV), grad_last.to(DEV))
+    # the suffix sum is a warp scan here (re-associated): 1e-5 relative to the largest gradient of the stream
+    assert C.rel_err(got, ref) < 1e-5
+    assert torch.equal(got.cpu() == 0, ref == 0) or (got.cpu()[ref == 0].abs().max() == 0)
+
+
+def test_alphas2weights_autograd_and_empty():
+    R, H = _ops()
+    alpha, ray_id = _alpha_stream(64, 9)
+    a = alpha.to(DEV).requires_grad_(True)
+    w, last = R.Alphas2Weights.apply(a, ray_id.to(DEV), 64)
+    (w.sum() * 0.5 + last.sum()).backward()
+    wr, Tr, lr, i_s, i_e = H.alpha2weight(alpha, ray_id, 64)
+    ref = H.alpha2weight_backward(alpha, wr, Tr, lr, i_s, i_e, 64, torch.full_like(alpha, 0.5), torch.ones(64))
+    assert C.rel_err(a.grad, ref) < 1e-5
+    w0, T0, l0, s0, e0 = R.render_utils_cuda.alpha2weight(torch.zeros(0, device=DEV), torch.zeros(0, dtype=torch.long, device=DEV), 7)
+    assert w0.numel() == 0 and (l0 == 1).all() and (s0 == 0).all() and (e0 == 0).all()
+
+
+@pytest.mark.parametrize("channels", [1, 3, 5])
+def test_segment_coo_sum(channels):
+    R, _ = _ops()
+    alpha, ray_id = _alpha_stream(500, 3)
+    g = torch.Generator().manual_seed(4)
+    src = torch.randn(ray_id.numel(), channels, generator=g)
+    ref = torch.zeros(500, channels, dtype=torch.float64).index_add_(0, ray_id, src.double())
+    s = src.to(DEV).requires_grad_(True)
+    out = R.segment_coo(src=s, index=ray_id.to(DEV), out=torch.zeros(500, channels, device=DEV), reduce="sum")
+    # torch_scatter's summation order is unspecified (third-party, un-pinned): fp32 sum tolerance 1e-5 of max
+    assert C.rel_err(out, ref) < 1e-5
+    cot = torch.randn(500, channels, generator=g)
+    (out * cot.to(DEV)).sum().backward()
+    assert torch.equal(s.grad.cpu(), cot[ray_id])          # backward is a pure gather
+
+
+def test_total_variation_add_grad():
+    R, H = _ops()
+    g = torch.Generator().manual_seed(5)
+    p = torch.randn(1, 1, 9, 11, 13, generator=g) * 2
+    grad = torch.randn(p.shape, generator=g)
+    ref = grad.clone()
+    H.total_variation_add_grad(p, ref, 0.3, 0.3, 0.3, True)
+    got = grad.to(DEV)
+    R.total_variation_cuda.total_variation_add_grad(p.to(DEV), got, 0.3, 0.3, 0.3, True)
+    assert C.rel_err(got, ref) < 1e-6
+    # sparse mode only touches voxels that already carry gradient (total_variation_kernel.cu:20)
+    sp = grad.clone()
+    sp[0, 0, :4] = 0
+    got = sp.to(DEV)
+    R.total_variation_cuda.total_variation_add_grad(p.to(DEV), got, 0.3, 0.3, 0.3, False)
+    assert (got[0, 0, :4] == 0).all() and C.rel_err(got[0, 0, 4:], ref[0, 0, 4:]) < 1e-6
+
+
+def test_exclusive_scan_large():
+    from esr_nerf_b200 import fused
+    g = torch.Generator().manual_seed(6)
+    for n in (1, 4095, 4096, 4097, 1 << 20):
+        c = torch.randint(0, 900, (n,), generator=g, dtype=torch.int32)
+        out = fused.exclusive_scan(c.to(DEV)).cpu()
+        ref = torch.cat([torch.zeros(1, dtype=torch.int64), c.long().cumsum(0)])
+        assert torch.equal(out.long(), ref), n
+    _ = np
