@@ -98,12 +98,57 @@ def sdf_feature_taps(scene: Dict, sdf_grid: torch.Tensor, xyz: torch.Tensor, dis
     return feat.reshape(M, 6 * K), grad.reshape(M, 3 * K), normal.reshape(M, 3 * K)
 
 
+def _bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+class _RoundBf16(torch.autograd.Function):
+    """value and cotangent both rounded to bf16 (the storage points of the tensor-core MLP kernels)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundBf16Bwd(torch.autograd.Function):
+    """identity forward, bf16-rounded cotangent"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+MLP_PRECISION = "fp32"   # "bf16": emulate the rounding points of the bf16 tensor-core kernels (fp32 accumulate)
+
+
 def mlp(x, layers, out_act):
-    """pbr/module.py:6-39: Linear/ReLU stack; layers = [(W,b), ...]."""
+    """pbr/module.py:6-39: Linear/ReLU stack; layers = [(W,b), ...].
+
+    With MLP_PRECISION == "bf16" the same stack is evaluated with inputs, weights, hidden activations and
+    their cotangents rounded to bf16 where esr_mlp_fwd / esr_mlp_bwd store them (fp32 accumulation, fp32
+    bias / output) — the numeric contract of the product's bf16 mode, used to separate kernel bugs from
+    the inherent bf16 error."""
+    if MLP_PRECISION == "fp32":
+        for i, (w, b) in enumerate(layers):
+            x = F.linear(x, w, b)
+            if i + 1 < len(layers):
+                x = F.relu(x)
+        return out_act(x)
+    x = _RoundBf16.apply(x)
     for i, (w, b) in enumerate(layers):
-        x = F.linear(x, w, b)
+        x = F.linear(x, _RoundBf16.apply(w), b)
         if i + 1 < len(layers):
-            x = F.relu(x)
+            x = _RoundBf16.apply(F.relu(x))
+        else:
+            x = _RoundBf16Bwd.apply(x)
     return out_act(x)
 
 

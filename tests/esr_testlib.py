@@ -76,3 +76,31 @@ def digest_check(fx, name, grad: torch.Tensor, rtol, atol_frac=0.1):
 def rel_err(a: torch.Tensor, b: torch.Tensor):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def grad_err(g: torch.Tensor, r: torch.Tensor):
+    """(max-abs error / max|ref|, relative L2 error) of a gradient tensor"""
+    g, r = g.detach().double().cpu(), r.detach().double().cpu()
+    d = g - r
+    return (d.abs().max() / r.abs().max().clamp_min(1e-30)).item(), (d.norm() / r.norm().clamp_min(1e-30)).item()
+
+
+def grad_close(g: torch.Tensor, r: torch.Tensor, tol: float, outlier_frac: float = 0.01, l2_factor: float = 30.0):
+    """Gradient comparison that tolerates isolated ReLU-boundary flips.
+
+    The MLP gradients are discontinuous where a hidden pre-activation crosses zero; two fp32 evaluations
+    with different summation orders (cuBLAS vs MKL, the reference's own GPU and CPU runs included) flip a
+    handful of the ~10^7 ReLU masks of a batch, and each flip perturbs one row of one weight gradient (and
+    the 48 grid cells its sample touches) by O(1) of a single sample's contribution.  So: pass if
+    max-abs error <= tol * max|ref|; otherwise require that the entries beyond that bound are a small
+    fraction (< outlier_frac, or <= 3 entries) of the non-zero entries AND the relative L2 error stays below l2_factor*tol."""
+    g, r = g.detach().double().cpu(), r.detach().double().cpu()
+    d = (g - r).abs()
+    bound = tol * r.abs().max().clamp_min(1e-30)
+    if (d <= bound).all():
+        return True, "max-rel ok"
+    nz = max(int((r != 0).sum()), 1)
+    n_out = int((d > bound).sum())
+    l2 = float((g - r).norm() / r.norm().clamp_min(1e-30))
+    ok = n_out <= max(3, outlier_frac * nz) and l2 < l2_factor * tol      # 3: a flipped unit in a 192-entry bias
+    return ok, f"max-rel {float(d.max() / r.abs().max()):.2e} outliers {n_out}/{nz} rel-L2 {l2:.2e}"
