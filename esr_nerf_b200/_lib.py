@@ -17,8 +17,8 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
-SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_mma.cu"]
-HEADERS = ["common.cuh", "scan.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
+SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_mma.cu", "mlp_tc.cu"]
+HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

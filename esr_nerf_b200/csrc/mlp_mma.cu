@@ -8,44 +8,14 @@
 //   dgrad   : d_y -> d_z of every layer (bf16, for wgrad) -> d_x (f32, first dx_cols columns)
 //   wgrad   : dW_l += dZ_l^T . In_l as a split-K (over samples) GEMM with ldmatrix.trans operands,
 //             fp32 partials reduced into the flat gradient with RED.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "mlp_layout.cuh"
 
 using namespace esr;
 
 namespace {
-
-// ------------------------------------------------------------------------------------------------
-// parameter image layout
-// ------------------------------------------------------------------------------------------------
-struct MlpLayout {
-  int k0, W, NH, n_out;
-  // flat f32 master copy
-  __host__ __device__ int64_t flat_w(int l) const {  // offset of W_l
-    if (l == 0) return 0;
-    int64_t o = (int64_t)W * k0 + W;
-    o += (int64_t)(l - 1) * ((int64_t)W * W + W);
-    return o;
-  }
-  __host__ __device__ int64_t flat_b(int l) const { return flat_w(l) + (l == 0 ? (int64_t)W * k0 : (l < NH ? (int64_t)W * W : (int64_t)8 * W)); }
-  __host__ __device__ int64_t flat_count() const { return flat_b(NH) + 8; }
-  // bf16 image, element offsets (bf16 units) of the forward weights
-  __host__ __device__ int64_t img_w(int l) const {
-    if (l == 0) return 0;
-    return (int64_t)W * k0 + (int64_t)(l - 1) * W * W;
-  }
-  __host__ __device__ int64_t img_fwd_elems() const { return img_w(NH) + (int64_t)8 * W; }
-  __host__ __device__ int64_t img_bias_bytes_off() const { return img_fwd_elems() * 2; }
-  __host__ __device__ int64_t n_bias() const { return (int64_t)NH * W + 8; }
-  __host__ __device__ int64_t img_bwd_bytes_off() const { return img_bias_bytes_off() + n_bias() * 4; }
-  // transposed copies (bf16 units relative to img_bwd): woT [W][16], whT[l-1] [W][W] (l=1..NH-1), w0T [k0][W]
-  __host__ __device__ int64_t imgT_wo() const { return 0; }
-  __host__ __device__ int64_t imgT_wh(int l) const { return (int64_t)W * 16 + (int64_t)(l - 1) * W * W; }
-  __host__ __device__ int64_t imgT_w0() const { return (int64_t)W * 16 + (int64_t)(NH - 1) * W * W; }
-  __host__ __device__ int64_t imgT_elems() const { return imgT_w0() + (int64_t)k0 * W; }
-  __host__ __device__ int64_t img_bytes() const { return img_bwd_bytes_off() + imgT_elems() * 2; }
-};
-
-static MlpLayout layout_of(const esr_mlp_desc_t *d) { return MlpLayout{d->k0, d->width, d->n_hidden, d->n_out}; }
 
 __global__ void k_mlp_pack(MlpLayout L, const float *__restrict__ flat, uint8_t *__restrict__ image) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -544,34 +514,71 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
   }
 }
 
-// output layer (n_out <= 8 rows): dWo[o][i] += sum_m dz_out[m][o] * H[m][i]; dbo[o] += sum_m dz_out[m][o]
+// output layer (n_out <= 3 real rows of 8): dWo[o][i] += sum_m dz_out[m][o] * H[m][i]; dbo[o] += sum_m dz_out[m][o].
+// Skinny (3 x W) and bound by streaming H once: a warp owns a contiguous slab of rows, each lane 6 of the W=192
+// columns (three bf16x2 words), rows unrolled x4 so 12 loads per lane are in flight; 18 accumulators per lane.
 template <int W>
-__global__ void __launch_bounds__(W)
+__global__ void __launch_bounds__(256)
     k_mlp_wgrad_out(const float *__restrict__ dz_out /* [m][8] */, const __nv_bfloat16 *__restrict__ h,
                     int64_t row_begin, int64_t row_end, int n_out, float *__restrict__ gW /* [8][W] */,
                     float *__restrict__ gb /* [8] */) {
+  static_assert(W == 192, "lane mapping assumes 192 = 32 lanes x 3 bf16x2 words");
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = lane_id();
   const int64_t n_rows = row_end - row_begin;
-  const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
-  const int64_t m0 = row_begin + (int64_t)blockIdx.x * per, m1 = min(row_end, m0 + per);
-  const int i = threadIdx.x;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int64_t m = m0; m < m1; ++m) {
-    const float hv = __bfloat162float(h[m * W + i]);
-    const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dz_out + m * 8));
-    const float4 d1 = __ldg(reinterpret_cast<const float4 *>(dz_out + m * 8 + 4));
-    const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+  const int64_t per = (n_rows + nwarps - 1) / nwarps;
+  const int64_t m0 = row_begin + warp * per, m1 = min(row_end, m0 + per);
+  float acc[3][6], bs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      acc[o] = fmaf(d[o], hv, acc[o]);
-      bs[o] += d[o];
+  for (int o = 0; o < 3; ++o)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[o][j] = 0.f;
+  const uint32_t *hw = reinterpret_cast<const uint32_t *>(h);  // bf16x2 words, W/2 per row
+  constexpr int UN = 4;
+  for (int64_t m = m0; m < m1; m += UN) {
+    uint32_t v[UN][3];
+    float d[UN][3];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const bool ok = m + u < m1;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[u][j] = ok ? __ldg(hw + (m + u) * (W / 2) + 32 * j + lane) : 0u;
+#pragma unroll
+      for (int o = 0; o < 3; ++o) d[u][o] = ok ? __ldg(dz_out + (m + u) * 8 + o) : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        bs[o] += d[u][o];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          acc[o][2 * j] = fmaf(d[u][o], bf16_lo(v[u][j]), acc[o][2 * j]);
+          acc[o][2 * j + 1] = fmaf(d[u][o], bf16_hi(v[u][j]), acc[o][2 * j + 1]);
+        }
+      }
   }
   if (m0 < m1) {
-    for (int o = 0; o < n_out; ++o) {
-      red_add(gW + (int64_t)o * W + i, acc[o]);
-      if (i == 0) red_add(gb + o, bs[o]);
+    for (int o = 0; o < n_out && o < 3; ++o) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) red_add2(gW + (int64_t)o * W + 2 * (32 * j + lane), acc[o][2 * j], acc[o][2 * j + 1]);
+      if (lane == 0) red_add(gb + o, bs[o]);
     }
   }
+}
+
+// image = [mma.sync image | pad to 128 | tcgen05 image]
+static int64_t tc_image_off(const esr_mlp_desc_t *d) { return (layout_of(d).img_bytes() + 127) / 128 * 128; }
+
+// ESR_MLP_PATH=mma selects the legacy mma.sync forward / data-gradient kernels (A/B measurements); default tcgen05
+static bool use_tc(const esr_mlp_desc_t *d) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = getenv("ESR_MLP_PATH");
+    mode = (e && e[0] == 'm') ? 0 : 1;
+  }
+  return mode == 1 && tc_supported(d);
 }
 
 template <typename K>
@@ -603,14 +610,20 @@ template <int K0, int W, int NH, int DXP>
 static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *image, const void *x, const float *y,
                    const float *d_y, int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z,
                    float *d_z_out, float *d_x, int dx_cols, int accumulate, float *grad_flat, cudaStream_t st) {
-  auto kern = k_mlp_dgrad<K0, W, NH, DXP>;
-  constexpr int bytes = BwdSmem<K0, W, NH, DXP>::bytes;
-  if (int e = set_smem(kern, bytes)) return e;
-  ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_radiance" : "k_mlp_dgrad_tonemap", st);
-  kern<<<persistent_grid(re - rb), MLP_THREADS, bytes, st>>>(L, (const uint8_t *)image, y, d_y, rb, re, mt,
-                                                             (const __nv_bfloat16 *)hidden, (__nv_bfloat16 *)d_z,
-                                                             d_z_out, d_x, dx_cols, accumulate, d->n_out, d->act);
-  ESR_LAUNCH_OK();
+  if (use_tc(d)) {
+    if (int e = tc_dgrad(d, (const uint8_t *)image + tc_image_off(d), y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x,
+                         dx_cols, accumulate, st))
+      return e;
+  } else {
+    auto kern = k_mlp_dgrad<K0, W, NH, DXP>;
+    constexpr int bytes = BwdSmem<K0, W, NH, DXP>::bytes;
+    if (int e = set_smem(kern, bytes)) return e;
+    ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_radiance" : "k_mlp_dgrad_tonemap", st);
+    kern<<<persistent_grid(re - rb), MLP_THREADS, bytes, st>>>(L, (const uint8_t *)image, y, d_y, rb, re, mt,
+                                                               (const __nv_bfloat16 *)hidden, (__nv_bfloat16 *)d_z,
+                                                               d_z_out, d_x, dx_cols, accumulate, d->n_out, d->act);
+    ESR_LAUNCH_OK();
+  }
   if (!grad_flat) return ESR_OK;
   const __nv_bfloat16 *H = (const __nv_bfloat16 *)hidden;
   const __nv_bfloat16 *Z = (const __nv_bfloat16 *)d_z;
@@ -632,9 +645,9 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
                                                            re, grad_flat + L.flat_w(l), grad_flat + L.flat_b(l));
     ESR_LAUNCH_OK();
   }
-  const unsigned grid_o = (unsigned)max((int64_t)1, min((int64_t)num_sms() * 4, (rows + 63) / 64));
+  const unsigned grid_o = (unsigned)max((int64_t)1, min((int64_t)num_sms() * 4, (rows + 255) / 256));
   ESR_STAGE("k_mlp_wgrad_out", st);
-  k_mlp_wgrad_out<W><<<grid_o, W, 0, st>>>(d_z_out, H + (int64_t)(NH - 1) * mt * W, rb, re, d->n_out,
+  k_mlp_wgrad_out<W><<<grid_o, 256, 0, st>>>(d_z_out, H + (int64_t)(NH - 1) * mt * W, rb, re, d->n_out,
                                            grad_flat + L.flat_w(NH), grad_flat + L.flat_b(NH));
   ESR_LAUNCH_OK();
   return ESR_OK;
@@ -643,15 +656,14 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
 static int check_desc(const esr_mlp_desc_t *d) {
   ESR_CHECK_ARG(d != nullptr);
   ESR_CHECK_ARG(d->k0 % 16 == 0 && d->k0 > 0 && d->width % 64 == 0 && d->n_hidden >= 1);
-  ESR_CHECK_ARG(d->n_out >= 1 && d->n_out <= 8 && (d->act == 1 || d->act == 2));
+  ESR_CHECK_ARG(d->n_out >= 1 && d->n_out <= 3 && (d->act == 1 || d->act == 2));
   return ESR_OK;
 }
 
 }  // namespace
 
+extern "C" int64_t esr_mlp_image_bytes(const esr_mlp_desc_t *d) { return d ? tc_image_off(d) + tc_image_bytes(d) : 0; }
 extern "C" int64_t esr_mlp_param_count(const esr_mlp_desc_t *d) { return d ? layout_of(d).flat_count() : 0; }
-extern "C" int64_t esr_mlp_image_bytes(const esr_mlp_desc_t *d) { return d ? layout_of(d).img_bytes() : 0; }
-
 extern "C" int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image, esr_stream_t stream) {
   if (int e = check_desc(d)) return e;
   ESR_CHECK_ARG(flat_params && image);
@@ -660,7 +672,7 @@ extern "C" int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, v
   ESR_STAGE("k_mlp_pack", (cudaStream_t)stream);
   k_mlp_pack<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(L, flat_params, (uint8_t *)image);
   ESR_LAUNCH_OK();
-  return ESR_OK;
+  return tc_pack(d, flat_params, (uint8_t *)image + tc_image_off(d), (cudaStream_t)stream);
 }
 
 // instantiated shapes: radiance nets 96->192x3->3 (pbr/module.py:6-21 with dim0 85), tone mapper 48->192->3
@@ -674,6 +686,8 @@ extern "C" int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const voi
   ESR_CHECK_ARG(image && x && y);
   const MlpLayout L = layout_of(d);
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(d))
+    return tc_fwd(d, (const uint8_t *)image + tc_image_off(d), x, row_begin, row_end, m_total, y, hidden, st);
 #define FWD_CALL(...) run_fwd<__VA_ARGS__>(L, d, image, x, row_begin, row_end, m_total, y, hidden, st)
   if (d->k0 == 96 && d->width == 192 && d->n_hidden == 3) return FWD_CALL(96, 192, 3, 56);
   if (d->k0 == 48 && d->width == 192 && d->n_hidden == 1) return FWD_CALL(48, 192, 1, 40);

@@ -1,0 +1,622 @@
+// mlp_tc.cu — the radiance / tone-map MLPs (pbr/module.py:6-39) as fused layer chains on the 5th-gen tensor
+// cores: tcgen05.mma issued by one thread per CTA, accumulators in TMEM, every weight matrix of the net
+// resident in shared memory for the life of the (persistent) CTA, hidden activations never leaving the SM
+// between layers: the epilogue warps read the fp32 accumulator tile out of TMEM (tcgen05.ld), apply
+// bias + ReLU (forward) or the ReLU mask (data gradient), pack to bf16 and write the result back INTO TMEM
+// (tcgen05.st) where the next layer's MMA consumes it as its A operand (the .ts form: A from tensor memory,
+// B from shared memory).  Only the first layer's A tile (the encoded feature rows / the output cotangent)
+// comes from shared memory.
+//
+//   forward : x[128,K0] -> (192 x NH, ReLU) -> n_out, softplus|sigmoid;  saves H_l (bf16) for backward
+//   dgrad   : d_y -> dZ_out -> (W^T chain, ReLU masks from H_l) -> d_x;   saves dZ_l (bf16) for wgrad
+//
+// Tile = 128 rows (UMMA M = 128, cta_group::1): TMEM lane = row, TMEM column = feature.
+// Operand layout in shared memory: K-major, no swizzle, "chunk-major": element (r, k) of an [R x K] matrix
+// lives at byte  (k/8) * (R*16) + r*16 + (k%8)*2  — i.e. 8x8 core matrices of 128 contiguous bytes, the two
+// K-halves of one MMA (K = 16) R*16 bytes apart (descriptor LBO), consecutive 8-row groups 128 bytes apart
+// (descriptor SBO).  The global weight image built by tc_pack has exactly this byte order, so staging is a
+// straight copy, and an epilogue thread (= one row) writing one 16-byte chunk per k-chunk is conflict-free.
+#include "mlp_layout.cuh"
+
+using namespace esr;
+
+namespace {
+
+constexpr int TC_W = 192;         // hidden width
+constexpr int TC_TM = 128;        // rows per tile
+constexpr int TC_THREADS = 160;   // warps 0-3: epilogue (TMEM lanes 32w..32w+31), warp 4: MMA issuer
+constexpr int TC_NOUT_PAD = 16;   // output layer rows padded to the minimum UMMA N for M = 128
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+ESR_D uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+ESR_D void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+ESR_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+ESR_D void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// generic-proxy writes to shared memory (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma)
+ESR_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+ESR_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+ESR_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+ESR_D void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+ESR_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100)
+ESR_D uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor: D f32, A/B bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
+}
+
+ESR_D void mma_ss(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+ESR_D void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+ESR_D void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TC_R4(r, i) "%" #r "0" #i
+// tcgen05.ld 32x32b.x16 / .x32: thread t of warp w receives columns [c, c+N) of TMEM lane 32*(w%4)+t
+ESR_D void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+ESR_D void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+ESR_D void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+ESR_D void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+ESR_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+ESR_D void cp_async16_zfill(uint32_t dst, const void *src, bool pred) {
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+ESR_D void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+ESR_D uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&v);
+}
+ESR_D float lo16(uint32_t v) { return __uint_as_float(v << 16); }
+ESR_D float hi16(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// ------------------------------------------------------------------------------------------------
+// image layout (bytes).  Every matrix is bf16 chunk-major [K/8][R][8].
+// ------------------------------------------------------------------------------------------------
+struct TcLayout {
+  int k0, NH, dxn;
+  __host__ __device__ int64_t mat_bytes(int rows, int k) const { return (int64_t)rows * k * 2; }
+  // forward section: W0 [W x k0], W_1..W_{NH-1} [W x W], Wo [16 x W], bias f32 [NH*W + 16]
+  __host__ __device__ int64_t f_w0() const { return 0; }
+  __host__ __device__ int64_t f_wh(int l) const { return mat_bytes(TC_W, k0) + (int64_t)(l - 1) * mat_bytes(TC_W, TC_W); }
+  __host__ __device__ int64_t f_wo() const { return f_wh(NH); }
+  __host__ __device__ int64_t f_bias() const { return f_wo() + mat_bytes(TC_NOUT_PAD, TC_W); }
+  __host__ __device__ int64_t f_bytes() const { return f_bias() + (int64_t)(NH * TC_W + TC_NOUT_PAD) * 4; }
+  // dgrad section (transposes): WoT [W x 16], W_{l}T [W x W] for l = NH-1 .. 1 (stored in index order l-1), W0T [dxn x W]
+  __host__ __device__ int64_t b_wo() const { return 0; }
+  __host__ __device__ int64_t b_wh(int l) const { return mat_bytes(TC_W, TC_NOUT_PAD) + (int64_t)(l - 1) * mat_bytes(TC_W, TC_W); }
+  __host__ __device__ int64_t b_w0() const { return b_wh(NH); }
+  __host__ __device__ int64_t b_bytes() const { return b_w0() + mat_bytes(dxn, TC_W); }
+  __host__ __device__ int64_t bwd_off() const { return (f_bytes() + 127) / 128 * 128; }
+  __host__ __device__ int64_t total() const { return bwd_off() + (b_bytes() + 127) / 128 * 128; }
+};
+
+static TcLayout tc_layout(const esr_mlp_desc_t *d) { return TcLayout{d->k0, d->n_hidden, d->k0 == 96 ? 64 : 48}; }
+
+ESR_HD int64_t chunk_index(int rows, int r, int k) { return ((int64_t)(k >> 3) * rows + r) * 8 + (k & 7); }
+
+__global__ void k_tc_pack(TcLayout T, MlpLayout L, const float *__restrict__ flat, uint8_t *__restrict__ image) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = TC_W, NH = T.NH;
+  __nv_bfloat16 *f = reinterpret_cast<__nv_bfloat16 *>(image);
+  __nv_bfloat16 *b = reinterpret_cast<__nv_bfloat16 *>(image + T.bwd_off());
+  // one thread per (layer-matrix element) of the padded logical matrices; enumerate W0, Wh.., Wo in turn
+  int64_t e = i;
+  // W0 [W x k0]
+  if (e < (int64_t)W * T.k0) {
+    const int o = (int)(e / T.k0), in = (int)(e % T.k0);
+    const float v = flat[L.flat_w(0) + e];
+    f[T.f_w0() / 2 + chunk_index(W, o, in)] = __float2bfloat16(v);
+    if (in < T.dxn) b[T.b_w0() / 2 + chunk_index(T.dxn, in, o)] = __float2bfloat16(v);
+    return;
+  }
+  e -= (int64_t)W * T.k0;
+  for (int l = 1; l < NH; ++l) {
+    if (e < (int64_t)W * W) {
+      const int o = (int)(e / W), in = (int)(e % W);
+      const float v = flat[L.flat_w(l) + e];
+      f[T.f_wh(l) / 2 + chunk_index(W, o, in)] = __float2bfloat16(v);
+      b[T.b_wh(l) / 2 + chunk_index(W, in, o)] = __float2bfloat16(v);
+      return;
+    }
+    e -= (int64_t)W * W;
+  }
+  // Wo [16 x W] (flat copy holds 8 rows; rows >= 8 are zero)
+  if (e < (int64_t)TC_NOUT_PAD * W) {
+    const int o = (int)(e / W), in = (int)(e % W);
+    const float v = o < 8 ? flat[L.flat_w(NH) + (int64_t)o * W + in] : 0.f;
+    f[T.f_wo() / 2 + chunk_index(TC_NOUT_PAD, o, in)] = __float2bfloat16(v);
+    b[T.b_wo() / 2 + chunk_index(W, in, o)] = __float2bfloat16(v);
+    return;
+  }
+  e -= (int64_t)TC_NOUT_PAD * W;
+  // biases
+  if (e < (int64_t)NH * W + TC_NOUT_PAD) {
+    float *bias = reinterpret_cast<float *>(image + T.f_bias());
+    float v;
+    if (e < (int64_t)NH * W) {
+      const int l = (int)(e / W);
+      v = flat[L.flat_b(l) + (e - (int64_t)l * W)];
+    } else {
+      const int o = (int)(e - (int64_t)NH * W);
+      v = o < 8 ? flat[L.flat_b(NH) + o] : 0.f;
+    }
+    bias[e] = v;
+  }
+}
+
+// cooperative straight copy global -> shared (16-byte words)
+ESR_D void stage_bytes(uint8_t *dst, const uint8_t *__restrict__ src, int64_t bytes) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+  for (int64_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+ESR_D float act_fwd(float z, int act) {
+  if (act == 1) return z > 20.f ? z : log1pf(expf(z));  // softplus(beta=1, threshold=20)
+  if (act == 2) return 1.f / (1.f + expf(-z));
+  return z;
+}
+
+// TMEM column map (512 columns allocated): accumulator D [0,192), bf16 A operand [192,288), small accumulator [288, 352)
+constexpr uint32_t TM_D = 0, TM_A = 192, TM_S = 288, TM_COLS = 512;
+
+// ------------------------------------------------------------------------------------------------
+// forward chain
+// ------------------------------------------------------------------------------------------------
+template <int K0, int NH>
+struct FwdSm {
+  static constexpr int w0 = 0;
+  static constexpr int wh = w0 + TC_W * K0 * 2;
+  static constexpr int wo = wh + (NH - 1) * TC_W * TC_W * 2;
+  static constexpr int bias = wo + TC_NOUT_PAD * TC_W * 2;
+  static constexpr int weights_bytes = bias + (NH * TC_W + TC_NOUT_PAD) * 4;   // == TcLayout::f_bytes()
+  static constexpr int x = (weights_bytes + 127) / 128 * 128;
+  static constexpr int bar = x + TC_TM * K0 * 2;
+  static constexpr int bytes = bar + 16;
+};
+
+template <int K0, int NH>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_mlp_fwd_tc(const uint8_t *__restrict__ image, const __nv_bfloat16 *__restrict__ x, int64_t row_begin,
+                 int64_t row_end, int64_t m_total, float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden, int n_out,
+                 int act) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = FwdSm<K0, NH>;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_addr(smem);
+  const uint32_t bar = sbase + S::bar;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 8);
+
+  stage_bytes(smem, image, S::weights_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
+
+  const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
+  const uint32_t lane_base = (32u * warp) << 16;  // TMEM lane field of this epilogue warp
+  const int t = threadIdx.x;                      // epilogue threads: row within the tile
+  uint32_t phase = 0;
+
+  auto load_x = [&](int64_t tile) {  // epilogue threads: one row each, K0/8 16-byte chunks
+    const int64_t row = row_begin + tile * TC_TM + t;
+    const bool ok = row < row_end;
+    const __nv_bfloat16 *src = x + (ok ? row : row_begin) * K0;
+#pragma unroll
+    for (int c = 0; c < K0 / 8; ++c) cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, src + c * 8, ok);
+  };
+
+  if (warp < 4 && blockIdx.x < n_tiles) load_x(blockIdx.x);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = row_begin + tile * TC_TM + t;
+    const bool valid = warp < 4 && row < row_end;
+    // ---- layer 0: A = x tile (shared), B = W0 ----
+    if (warp < 4) {
+      cp_async_wait_all();
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4 && lane == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < K0 / 16; ++s)
+        mma_ss(tmem + TM_D, make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
+               make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
+      mma_commit(bar);
+    }
+#pragma unroll 1
+    for (int l = 0; l < NH; ++l) {
+      if (warp < 4) {
+        mbar_wait(bar, phase);
+        tc_fence_after();
+        if (l == 0 && tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);  // x tile is free: prefetch the next one
+        // bias + ReLU -> bf16 -> TMEM A operand (+ global copy for the backward pass)
+        const float *b = sbias + l * TC_W;
+        __nv_bfloat16 *hrow = hidden ? hidden + ((int64_t)l * m_total + row) * TC_W : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < TC_W / 32; ++cc) {
+          uint32_t r[32], p[16];
+          tmem_ld32(tmem + lane_base + TM_D + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 bb = *reinterpret_cast<const float2 *>(b + cc * 32 + 2 * j);
+            p[j] = pack2(fmaxf(__uint_as_float(r[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(r[2 * j + 1]) + bb.y, 0.f));
+          }
+          tmem_st16(tmem + lane_base + TM_A + cc * 16, p);
+          if (hrow && valid) {
+            uint4 *dst = reinterpret_cast<uint4 *>(hrow + cc * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+          }
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 4 && lane == 0) {
+        tc_fence_after();
+        if (l + 1 < NH) {
+          const uint32_t wl = sbase + S::wh + l * (TC_W * TC_W * 2);
+#pragma unroll
+          for (int s = 0; s < TC_W / 16; ++s)
+            mma_ts(tmem + TM_D, tmem + TM_A + 8 * s, make_desc(wl + 2 * s * (TC_W * 16), TC_W * 16, 128),
+                   make_idesc(TC_W), s > 0);
+        } else {
+#pragma unroll
+          for (int s = 0; s < TC_W / 16; ++s)
+            mma_ts(tmem + TM_S, tmem + TM_A + 8 * s,
+                   make_desc(sbase + S::wo + 2 * s * (TC_NOUT_PAD * 16), TC_NOUT_PAD * 16, 128),
+                   make_idesc(TC_NOUT_PAD), s > 0);
+        }
+        mma_commit(bar);
+      }
+      phase ^= 1;
+    }
+    // ---- output layer epilogue ----
+    if (warp < 4) {
+      mbar_wait(bar, phase);
+      tc_fence_after();
+      uint32_t r[16];
+      tmem_ld16(tmem + lane_base + TM_S, r);
+      tmem_ld_wait();
+      if (valid) {
+        const float *bo = sbias + NH * TC_W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < n_out) y[row * n_out + c] = act_fwd(__uint_as_float(r[c]) + bo[c], act);
+      }
+    }
+    phase ^= 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// data-gradient chain
+// ------------------------------------------------------------------------------------------------
+template <int K0, int NH, int DXN>
+struct BwdSm {
+  static constexpr int wo = 0;                                        // WoT [W x 16]
+  static constexpr int wh = wo + TC_W * TC_NOUT_PAD * 2;              // W_lT, l = 1..NH-1
+  static constexpr int w0 = wh + (NH - 1) * TC_W * TC_W * 2;          // W0T [DXN x W]
+  static constexpr int weights_bytes = w0 + DXN * TC_W * 2;           // == TcLayout::b_bytes()
+  static constexpr int dz = (weights_bytes + 127) / 128 * 128;        // dZ_out tile [128 x 16] bf16
+  static constexpr int bar = dz + TC_TM * TC_NOUT_PAD * 2;
+  static constexpr int bytes = bar + 16;
+};
+
+template <int K0, int NH, int DXN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_mlp_dgrad_tc(const uint8_t *__restrict__ image_bwd, const float *__restrict__ y, const float *__restrict__ d_y,
+                   int64_t row_begin, int64_t row_end, int64_t m_total, const __nv_bfloat16 *__restrict__ hidden,
+                   __nv_bfloat16 *__restrict__ d_z, float *__restrict__ d_z_out, float *__restrict__ d_x, int dx_cols,
+                   int accumulate, int n_out, int act) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = BwdSm<K0, NH, DXN>;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_addr(smem);
+  const uint32_t bar = sbase + S::bar;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 8);
+
+  stage_bytes(smem, image_bwd, S::weights_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
+  // chunk 1 (columns 8..15) of the dZ_out tile stays zero
+  if (threadIdx.x < TC_TM) *reinterpret_cast<uint4 *>(smem + S::dz + TC_TM * 16 + threadIdx.x * 16) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
+  const uint32_t lane_base = (32u * warp) << 16;
+  const int t = threadIdx.x;
+  uint32_t phase = 0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = row_begin + tile * TC_TM + t;
+    const bool valid = warp < 4 && row < row_end;
+    // ---- dZ_out = d_y * act'(y): A tile of the first MMA ----
+    if (warp < 4) {
+      float dz[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < n_out) {
+            const float yy = y[row * n_out + c];
+            dz[c] = d_y[row * n_out + c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
+          }
+        if (d_z_out) {
+          *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], 0.f);
+          *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4 && lane == 0) {
+      tc_fence_after();
+      mma_ss(tmem + TM_D, make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
+             make_idesc(TC_W), 0);
+      mma_commit(bar);
+    }
+#pragma unroll 1
+    for (int l = NH - 1; l >= 0; --l) {
+      if (warp < 4) {
+        mbar_wait(bar, phase);
+        tc_fence_after();
+        // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy for the weight-gradient GEMM
+        const __nv_bfloat16 *hrow = hidden + ((int64_t)l * m_total + (valid ? row : row_begin)) * TC_W;
+        __nv_bfloat16 *zrow = d_z + ((int64_t)l * m_total + row) * TC_W;
+#pragma unroll 1
+        for (int cc = 0; cc < TC_W / 32; ++cc) {
+          uint32_t r[32], p[16], h[16];
+          const uint4 *hs = reinterpret_cast<const uint4 *>(hrow + cc * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v = valid ? __ldg(hs + q) : make_uint4(0, 0, 0, 0);
+            h[4 * q] = v.x, h[4 * q + 1] = v.y, h[4 * q + 2] = v.z, h[4 * q + 3] = v.w;
+          }
+          tmem_ld32(tmem + lane_base + TM_D + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            p[j] = pack2(lo16(h[j]) > 0.f ? __uint_as_float(r[2 * j]) : 0.f, hi16(h[j]) > 0.f ? __uint_as_float(r[2 * j + 1]) : 0.f);
+          tmem_st16(tmem + lane_base + TM_A + cc * 16, p);
+          if (valid) {
+            uint4 *dst = reinterpret_cast<uint4 *>(zrow + cc * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+          }
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 4 && lane == 0) {
+        tc_fence_after();
+        if (l > 0) {
+          const uint32_t wl = sbase + S::wh + (l - 1) * (TC_W * TC_W * 2);
+#pragma unroll
+          for (int s = 0; s < TC_W / 16; ++s)
+            mma_ts(tmem + TM_D, tmem + TM_A + 8 * s, make_desc(wl + 2 * s * (TC_W * 16), TC_W * 16, 128),
+                   make_idesc(TC_W), s > 0);
+        } else {
+#pragma unroll
+          for (int s = 0; s < TC_W / 16; ++s)
+            mma_ts(tmem + TM_S, tmem + TM_A + 8 * s, make_desc(sbase + S::w0 + 2 * s * (DXN * 16), DXN * 16, 128),
+                   make_idesc(DXN), s > 0);
+        }
+        mma_commit(bar);
+      }
+      phase ^= 1;
+    }
+    // ---- d_x epilogue ----
+    if (warp < 4) {
+      mbar_wait(bar, phase);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < DXN / 16; ++cc) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + TM_S + cc * 16, r);
+        tmem_ld_wait();
+        if (valid && d_x) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = cc * 16 + 4 * q;
+            if (col < dx_cols) {  // dx_cols is a multiple of 4 (56 / 40)
+              float4 *p4 = reinterpret_cast<float4 *>(d_x + row * dx_cols + col);
+              float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              if (accumulate) {
+                const float4 o = *p4;
+                v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+              }
+              *p4 = v;
+            }
+          }
+        }
+      }
+    }
+    phase ^= 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TM_COLS);
+}
+
+template <typename K>
+static int set_smem_tc(K kernel, int bytes) {
+  ESR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return ESR_OK;
+}
+
+static unsigned tc_grid(int64_t rows) {
+  const int64_t tiles = (rows + TC_TM - 1) / TC_TM;
+  const int64_t sms = num_sms();
+  return (unsigned)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
+}
+
+template <int K0, int NH>
+static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t rb, int64_t re, int64_t mt,
+                      float *y, void *hidden, cudaStream_t st) {
+  auto kern = k_mlp_fwd_tc<K0, NH>;
+  constexpr int bytes = FwdSm<K0, NH>::bytes;
+  if (int e = set_smem_tc(kern, bytes)) return e;
+  ESR_STAGE(K0 == 96 ? "k_mlp_fwd_tc_radiance" : "k_mlp_fwd_tc_tonemap", st);
+  kern<<<tc_grid(re - rb), TC_THREADS, bytes, st>>>((const uint8_t *)image, (const __nv_bfloat16 *)x, rb, re, mt, y,
+                                                    (__nv_bfloat16 *)hidden, d->n_out, d->act);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+template <int K0, int NH, int DXN>
+static int launch_dgrad(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const float *y, const float *d_y,
+                        int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z, float *d_z_out, float *d_x,
+                        int dx_cols, int accumulate, cudaStream_t st) {
+  auto kern = k_mlp_dgrad_tc<K0, NH, DXN>;
+  constexpr int bytes = BwdSm<K0, NH, DXN>::bytes;
+  if (int e = set_smem_tc(kern, bytes)) return e;
+  ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_tc_radiance" : "k_mlp_dgrad_tc_tonemap", st);
+  kern<<<tc_grid(re - rb), TC_THREADS, bytes, st>>>((const uint8_t *)image + T.bwd_off(), y, d_y, rb, re, mt,
+                                                    (const __nv_bfloat16 *)hidden, (__nv_bfloat16 *)d_z, d_z_out, d_x,
+                                                    dx_cols, accumulate, d->n_out, d->act);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+}  // namespace
+
+namespace esr {
+
+bool tc_supported(const esr_mlp_desc_t *d) {
+  return d && d->width == TC_W && ((d->k0 == 96 && d->n_hidden == 3) || (d->k0 == 48 && d->n_hidden == 1));
+}
+
+int64_t tc_image_bytes(const esr_mlp_desc_t *d) { return tc_supported(d) ? tc_layout(d).total() : 0; }
+
+int tc_pack(const esr_mlp_desc_t *d, const float *flat_params, void *tc_image, cudaStream_t st) {
+  if (!tc_supported(d)) return ESR_OK;
+  const TcLayout T = tc_layout(d);
+  const MlpLayout L = layout_of(d);
+  static_assert(FwdSm<96, 3>::weights_bytes > 0, "");
+  ESR_CHECK_CUDA(cudaMemsetAsync(tc_image, 0, (size_t)T.total(), st));
+  const int64_t n = (int64_t)TC_W * T.k0 + (int64_t)(T.NH - 1) * TC_W * TC_W + (int64_t)TC_NOUT_PAD * TC_W +
+                    (int64_t)T.NH * TC_W + TC_NOUT_PAD;
+  ESR_STAGE("k_tc_pack", st);
+  k_tc_pack<<<cdiv(n, 256), 256, 0, st>>>(T, L, flat_params, (uint8_t *)tc_image);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t row_begin, int64_t row_end,
+           int64_t m_total, float *y, void *hidden, cudaStream_t st) {
+  if (d->k0 == 96 && d->n_hidden == 3) return launch_fwd<96, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, st);
+  if (d->k0 == 48 && d->n_hidden == 1) return launch_fwd<48, 1>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, st);
+  set_error("tc_fwd: shape not instantiated");
+  return ESR_ERR_BAD_ARG;
+}
+
+int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, const float *d_y, int64_t row_begin,
+             int64_t row_end, int64_t m_total, const void *hidden, void *d_z, float *d_z_out, float *d_x, int dx_cols,
+             int accumulate, cudaStream_t st) {
+  const TcLayout T = tc_layout(d);
+  if (d->k0 == 96 && d->n_hidden == 3)
+    return launch_dgrad<96, 3, 64>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
+                                   dx_cols, accumulate, st);
+  if (d->k0 == 48 && d->n_hidden == 1)
+    return launch_dgrad<48, 1, 48>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
+                                   dx_cols, accumulate, st);
+  set_error("tc_dgrad: shape not instantiated");
+  return ESR_ERR_BAD_ARG;
+}
+
+}  // namespace esr

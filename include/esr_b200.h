@@ -223,7 +223,7 @@ typedef struct esr_mlp_desc {
   int32_t k0;      /* padded input width: multiple of 16 (96 radiance, 48 tonemap) */
   int32_t width;   /* hidden width: 192 */
   int32_t n_hidden;/* hidden layers: 3 (radiance nets), 1 (tonemapper) */
-  int32_t n_out;   /* real outputs (<= 8) */
+  int32_t n_out;   /* real outputs (<= 3; the output layer is padded to 8 rows in the flat copy) */
   int32_t act;     /* 1 softplus, 2 sigmoid */
 } esr_mlp_desc_t;
 
