@@ -19,28 +19,23 @@ struct MlpLayout {
   }
   __host__ __device__ int64_t flat_b(int l) const { return flat_w(l) + (l == 0 ? (int64_t)W * k0 : (l < NH ? (int64_t)W * W : (int64_t)8 * W)); }
   __host__ __device__ int64_t flat_count() const { return flat_b(NH) + 8; }
-  // bf16 image, element offsets (bf16 units) of the forward weights
-  __host__ __device__ int64_t img_w(int l) const {
-    if (l == 0) return 0;
-    return (int64_t)W * k0 + (int64_t)(l - 1) * W * W;
-  }
-  __host__ __device__ int64_t img_fwd_elems() const { return img_w(NH) + (int64_t)8 * W; }
-  __host__ __device__ int64_t img_bias_bytes_off() const { return img_fwd_elems() * 2; }
-  __host__ __device__ int64_t n_bias() const { return (int64_t)NH * W + 8; }
-  __host__ __device__ int64_t img_bwd_bytes_off() const { return img_bias_bytes_off() + n_bias() * 4; }
-  // transposed copies (bf16 units relative to img_bwd): woT [W][16], whT[l-1] [W][W] (l=1..NH-1), w0T [k0][W]
-  __host__ __device__ int64_t imgT_wo() const { return 0; }
-  __host__ __device__ int64_t imgT_wh(int l) const { return (int64_t)W * 16 + (int64_t)(l - 1) * W * W; }
-  __host__ __device__ int64_t imgT_w0() const { return (int64_t)W * 16 + (int64_t)(NH - 1) * W * W; }
-  __host__ __device__ int64_t imgT_elems() const { return imgT_w0() + (int64_t)k0 * W; }
-  __host__ __device__ int64_t img_bytes() const { return img_bwd_bytes_off() + imgT_elems() * 2; }
 };
 
 static inline MlpLayout layout_of(const esr_mlp_desc_t *d) { return MlpLayout{d->k0, d->width, d->n_hidden, d->n_out}; }
 
 
 // ------------------------------------------------------------------------------------------------
-// tcgen05 path (mlp_tc.cu).  The "tc image" follows the mma.sync image in the same buffer.
+// Activation buffers (hidden H_l saved by the forward chain, dZ_l saved by the data-gradient chain): per layer
+// [ceil(m/128)] tiles of [24 feature chunks][128 rows][8 bf16] — the shared-memory operand layout of the
+// tensor-core kernels, so that one thread per row moves 16-byte chunks that are contiguous across a warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int ACT_W = 192;
+ESR_HD int64_t act_rows_padded(int64_t m_total) { return (m_total + 127) / 128 * 128; }
+// index, in 16-byte units, of feature chunk c (8 features) of absolute row `row`
+ESR_HD int64_t act_chunk_index(int64_t row, int c) { return ((row >> 7) * (ACT_W / 8) + c) * 128 + (row & 127); }
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 path (mlp_tc.cu)
 // ------------------------------------------------------------------------------------------------
 int64_t tc_image_bytes(const esr_mlp_desc_t *d);
 int tc_pack(const esr_mlp_desc_t *d, const float *flat_params, void *tc_image, cudaStream_t st);

@@ -1,13 +1,12 @@
-// mlp_mma.cu — the small radiance / tone-map MLPs (pbr/module.py:6-39) on tensor cores.
+// mlp_mma.cu — C-ABI entry points of the MLP stage (esr_mlp_*) and the weight-gradient GEMMs.
 //
-// v1 tensor path: warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  The whole parameter set of
-// one net (<= 200 KB as bf16) is staged ONCE per CTA in shared memory and the CTAs are persistent over
-// 128-row tiles; activations never leave registers between layers (the m16n8 accumulator fragment of
-// layer l is re-packed in place into the m16k16 A fragment of layer l+1).
-//   forward : x[rows,k0] bf16 -> y[rows,n_out] f32 (+ optional bf16 hidden activations for training)
-//   dgrad   : d_y -> d_z of every layer (bf16, for wgrad) -> d_x (f32, first dx_cols columns)
-//   wgrad   : dW_l += dZ_l^T . In_l as a split-K (over samples) GEMM with ldmatrix.trans operands,
-//             fp32 partials reduced into the flat gradient with RED.
+//   forward / data gradient : fused tcgen05 layer chains, mlp_tc.cu
+//   weight gradient         : dW_l += dZ_l^T . In_l as a split-K (over samples) GEMM; v1 = warp-level
+//                             mma.sync.m16n8k16 with ldmatrix.trans operands, fp32 partials reduced into the flat
+//                             gradient with RED.
+// Hidden activations H_l and their cotangents dZ_l travel between the kernels in the TILED layout of
+// mlp_layout.cuh (act_chunk_index): per 128-row tile, [24 feature chunks][128 rows][8 bf16], so that one
+// epilogue thread per row writes / reads 16-byte chunks that are contiguous across the warp.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -16,45 +15,6 @@
 using namespace esr;
 
 namespace {
-
-__global__ void k_mlp_pack(MlpLayout L, const float *__restrict__ flat, uint8_t *__restrict__ image) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  __nv_bfloat16 *fw = reinterpret_cast<__nv_bfloat16 *>(image);
-  float *bias = reinterpret_cast<float *>(image + L.img_bias_bytes_off());
-  __nv_bfloat16 *bw = reinterpret_cast<__nv_bfloat16 *>(image + L.img_bwd_bytes_off());
-  const int W = L.W;
-  // forward weights + biases
-  if (i < L.img_fwd_elems()) {
-    int l = 0;
-    while (l < L.NH && i >= L.img_w(l + 1)) ++l;
-    const int64_t e = i - L.img_w(l);
-    fw[i] = __float2bfloat16(flat[L.flat_w(l) + e]);
-  }
-  if (i < L.n_bias()) {
-    const int l = (int)(i / W) < L.NH ? (int)(i / W) : L.NH;
-    const int64_t e = i - (int64_t)l * W;
-    bias[i] = flat[L.flat_b(l) + e];
-  }
-  // transposed copies
-  if (i < L.imgT_elems()) {
-    float v;
-    if (i < L.imgT_wh(1)) {  // woT [W][16]: (in i, out o) <- Wo[o][i], zero for o >= 8
-      const int in = (int)(i / 16), o = (int)(i % 16);
-      v = o < 8 ? flat[L.flat_w(L.NH) + (int64_t)o * W + in] : 0.f;
-    } else if (i < L.imgT_w0()) {  // whT[l-1] [in][out] <- W_l[out][in]
-      const int64_t e = i - L.imgT_wh(1);
-      const int l = 1 + (int)(e / ((int64_t)W * W));
-      const int64_t r = e % ((int64_t)W * W);
-      const int in = (int)(r / W), o = (int)(r % W);
-      v = flat[L.flat_w(l) + (int64_t)o * W + in];
-    } else {  // w0T [k0][W] <- W_0[out][in]
-      const int64_t e = i - L.imgT_w0();
-      const int in = (int)(e / W), o = (int)(e % W);
-      v = flat[L.flat_w(0) + (int64_t)o * L.k0 + in];
-    }
-    bw[i] = __float2bfloat16(v);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -100,41 +60,6 @@ ESR_D void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// copy a [rows][cols] bf16 matrix from global into shared with a padded row stride (cols + 8)
-ESR_D void stage_matrix(__nv_bfloat16 *dst, const __nv_bfloat16 *__restrict__ src, int rows, int cols) {
-  const int chunks = cols / 8;  // 16-byte chunks per row
-  const int stride = cols + 8;
-  for (int c = threadIdx.x; c < rows * chunks; c += blockDim.x) {
-    const int r = c / chunks, q = c - r * chunks;
-    *reinterpret_cast<uint4 *>(dst + r * stride + q * 8) = __ldg(reinterpret_cast<const uint4 *>(src + r * cols + q * 8));
-  }
-}
-
-// One dense layer for a warp's 16 rows: acc[NT][4] (+)= A[KT] . B^T, B staged as [n][k] with row stride
-// (k_cols + 8).  ldmatrix.x4 fetches the B fragments of two n-tiles per k-tile.
-template <int KT, int NT>
-ESR_D void warp_layer(const uint32_t (&a)[KT][4], uint32_t w_smem, int stride_elems, float (&acc)[NT][4]) {
-  const unsigned lane = lane_id();
-  const unsigned mi = lane >> 3, r = lane & 7;
-  const uint32_t lane_off = (uint32_t)(((8 * (mi >> 1) + r) * stride_elems + 8 * (mi & 1)) * 2);
-#pragma unroll
-  for (int kt = 0; kt < KT; ++kt) {
-#pragma unroll
-    for (int np = 0; np < NT / 2; ++np) {
-      uint32_t b0, b1, b2, b3;
-      ldsm_x4(w_smem + lane_off + (uint32_t)((16 * np * stride_elems + 16 * kt) * 2), b0, b1, b2, b3);
-      mma_bf16(acc[2 * np], a[kt], b0, b1);
-      mma_bf16(acc[2 * np + 1], a[kt], b2, b3);
-    }
-    if (NT & 1) {
-      uint32_t b0, b1;
-      const uint32_t off2 = (uint32_t)(((r)*stride_elems + 8 * (mi & 1)) * 2);  // lanes 0-15 supply addresses
-      ldsm_x2(w_smem + off2 + (uint32_t)((8 * (NT - 1) * stride_elems + 16 * kt) * 2), b0, b1);
-      mma_bf16(acc[NT - 1], a[kt], b0, b1);
-    }
-  }
-}
-
 template <int NT>
 ESR_D void zero_acc(float (&acc)[NT][4]) {
 #pragma unroll
@@ -142,251 +67,6 @@ ESR_D void zero_acc(float (&acc)[NT][4]) {
 }
 
 constexpr int MLP_THREADS = 256;
-constexpr int TILE_ROWS = 128;
-
-// ------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------
-template <int K0, int W, int NH>
-struct FwdSmem {
-  static constexpr int w0 = 0;                                    // [W][K0+8]
-  static constexpr int wh = w0 + W * (K0 + 8);                    // [NH-1][W][W+8]
-  static constexpr int wo = wh + (NH - 1) * W * (W + 8);          // [8][W+8]
-  static constexpr int bf16_elems = wo + 8 * (W + 8);
-  static constexpr int bias_off_bytes = bf16_elems * 2;           // f32 [NH*W+8]
-  static constexpr int bytes = bias_off_bytes + (NH * W + 8) * 4;
-};
-
-template <int K0, int W, int NH>
-__global__ void __launch_bounds__(MLP_THREADS, 1)
-    k_mlp_fwd(MlpLayout L, const uint8_t *__restrict__ image, const __nv_bfloat16 *__restrict__ x, int64_t row_begin,
-              int64_t row_end, int64_t m_total, float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden, int n_out,
-              int act) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  using S = FwdSmem<K0, W, NH>;
-  __nv_bfloat16 *sw = reinterpret_cast<__nv_bfloat16 *>(smem);
-  float *sbias = reinterpret_cast<float *>(smem + S::bias_off_bytes);
-  {
-    const __nv_bfloat16 *gw = reinterpret_cast<const __nv_bfloat16 *>(image);
-    stage_matrix(sw + S::w0, gw + L.img_w(0), W, K0);
-#pragma unroll
-    for (int l = 1; l < NH; ++l) stage_matrix(sw + S::wh + (l - 1) * W * (W + 8), gw + L.img_w(l), W, W);
-    stage_matrix(sw + S::wo, gw + L.img_w(NH), 8, W);
-    const float *gb = reinterpret_cast<const float *>(image + L.img_bias_bytes_off());
-    for (int i = threadIdx.x; i < NH * W + 8; i += blockDim.x) sbias[i] = gb[i];
-  }
-  __syncthreads();
-
-  constexpr int KT0 = K0 / 16, KT = W / 16, NT = W / 8;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  const unsigned g = lane >> 2, t = lane & 3;
-  const uint32_t s_base = smem_u32(sw);
-  const int64_t n_rows = row_end - row_begin;
-  const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
-
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t rA = row_begin + tile * TILE_ROWS + warp * 16 + g, rB = rA + 8;
-    const bool vA = rA < row_end, vB = rB < row_end;
-    float acc[NT][4];
-    uint32_t a[KT][4];
-    {  // layer 0: A fragments straight from global memory
-      uint32_t a0[KT0][4];
-      const uint32_t *xa = reinterpret_cast<const uint32_t *>(x + rA * K0);
-      const uint32_t *xb = reinterpret_cast<const uint32_t *>(x + rB * K0);
-#pragma unroll
-      for (int kt = 0; kt < KT0; ++kt) {
-        a0[kt][0] = vA ? __ldg(xa + 8 * kt + t) : 0u;
-        a0[kt][1] = vB ? __ldg(xb + 8 * kt + t) : 0u;
-        a0[kt][2] = vA ? __ldg(xa + 8 * kt + 4 + t) : 0u;
-        a0[kt][3] = vB ? __ldg(xb + 8 * kt + 4 + t) : 0u;
-      }
-      zero_acc(acc);
-      warp_layer<KT0, NT>(a0, s_base + S::w0 * 2, K0 + 8, acc);
-    }
-#pragma unroll
-    for (int l = 0; l < NH; ++l) {
-      // bias + ReLU, re-pack the accumulator fragment as the next layer's A fragment
-      const float *b = sbias + l * W;
-#pragma unroll
-      for (int kt = 0; kt < KT; ++kt) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = 2 * kt + h;
-          const float b0 = b[8 * j + 2 * t], b1 = b[8 * j + 2 * t + 1];
-          a[kt][2 * h] = pack_bf16(fmaxf(acc[j][0] + b0, 0.f), fmaxf(acc[j][1] + b1, 0.f));
-          a[kt][2 * h + 1] = pack_bf16(fmaxf(acc[j][2] + b0, 0.f), fmaxf(acc[j][3] + b1, 0.f));
-        }
-      }
-      if (hidden) {
-        uint32_t *ha = reinterpret_cast<uint32_t *>(hidden + ((int64_t)l * m_total + rA) * W);
-        uint32_t *hb = reinterpret_cast<uint32_t *>(hidden + ((int64_t)l * m_total + rB) * W);
-#pragma unroll
-        for (int kt = 0; kt < KT; ++kt) {
-          if (vA) ha[8 * kt + t] = a[kt][0], ha[8 * kt + 4 + t] = a[kt][2];
-          if (vB) hb[8 * kt + t] = a[kt][1], hb[8 * kt + 4 + t] = a[kt][3];
-        }
-      }
-      if (l + 1 < NH) {
-        zero_acc(acc);
-        warp_layer<KT, NT>(a, s_base + (S::wh + l * W * (W + 8)) * 2, W + 8, acc);
-      }
-    }
-    // output layer: one n-tile of 8 (n_out <= 8 real outputs)
-    float o[1][4];
-    zero_acc(o);
-    warp_layer<KT, 1>(a, s_base + S::wo * 2, W + 8, o);
-    const float *bo = sbias + NH * W;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col = 2 * t + h;
-      if (col < n_out) {
-        float zA = o[0][h] + bo[col], zB = o[0][2 + h] + bo[col];
-        if (act == 1) {  // softplus(beta=1, threshold=20)
-          zA = zA > 20.f ? zA : log1pf(expf(zA));
-          zB = zB > 20.f ? zB : log1pf(expf(zB));
-        } else if (act == 2) {
-          zA = 1.f / (1.f + expf(-zA));
-          zB = 1.f / (1.f + expf(-zB));
-        }
-        if (vA) y[rA * n_out + col] = zA;
-        if (vB) y[rB * n_out + col] = zB;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward, data gradient chain
-// ------------------------------------------------------------------------------------------------
-template <int K0, int W, int NH, int DXP /* padded dx cols, multiple of 8 */>
-struct BwdSmem {
-  static constexpr int woT = 0;                                   // [W][16+8]
-  static constexpr int whT = woT + W * 24;                        // [NH-1][W][W+8]
-  static constexpr int w0T = whT + (NH - 1) * W * (W + 8);        // [DXP][W+8]
-  static constexpr int bf16_elems = w0T + DXP * (W + 8);
-  static constexpr int bytes = bf16_elems * 2;
-};
-
-template <int K0, int W, int NH, int DXP>
-__global__ void __launch_bounds__(MLP_THREADS, 1)
-    k_mlp_dgrad(MlpLayout L, const uint8_t *__restrict__ image, const float *__restrict__ y,
-                const float *__restrict__ d_y, int64_t row_begin, int64_t row_end, int64_t m_total,
-                const __nv_bfloat16 *__restrict__ hidden, __nv_bfloat16 *__restrict__ d_z,
-                float *__restrict__ d_z_out, float *__restrict__ d_x, int dx_cols, int accumulate, int n_out,
-                int act) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  using S = BwdSmem<K0, W, NH, DXP>;
-  __nv_bfloat16 *sw = reinterpret_cast<__nv_bfloat16 *>(smem);
-  {
-    const __nv_bfloat16 *gw = reinterpret_cast<const __nv_bfloat16 *>(image + L.img_bwd_bytes_off());
-    stage_matrix(sw + S::woT, gw + L.imgT_wo(), W, 16);
-#pragma unroll
-    for (int l = 1; l < NH; ++l) stage_matrix(sw + S::whT + (l - 1) * W * (W + 8), gw + L.imgT_wh(l), W, W);
-    stage_matrix(sw + S::w0T, gw + L.imgT_w0(), DXP, W);
-  }
-  __syncthreads();
-
-  constexpr int KT = W / 16, NT = W / 8, NTX = DXP / 8;
-  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-  const unsigned g = lane >> 2, t = lane & 3;
-  const uint32_t s_base = smem_u32(sw);
-  const int64_t n_rows = row_end - row_begin;
-  const int64_t n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
-
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t rA = row_begin + tile * TILE_ROWS + warp * 16 + g, rB = rA + 8;
-    const bool vA = rA < row_end, vB = rB < row_end;
-    // d z_out = d_y * act'(y)   (softplus: 1 - exp(-y); sigmoid: y (1 - y))
-    float dzA[2] = {0.f, 0.f}, dzB[2] = {0.f, 0.f};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col = 2 * t + h;
-      if (col < n_out) {
-        if (vA) {
-          const float yy = y[rA * n_out + col];
-          dzA[h] = d_y[rA * n_out + col] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
-        }
-        if (vB) {
-          const float yy = y[rB * n_out + col];
-          dzB[h] = d_y[rB * n_out + col] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
-        }
-      }
-    }
-    if (d_z_out) {
-      if (vA) *reinterpret_cast<float2 *>(d_z_out + rA * 8 + 2 * t) = make_float2(dzA[0], dzA[1]);
-      if (vB) *reinterpret_cast<float2 *>(d_z_out + rB * 8 + 2 * t) = make_float2(dzB[0], dzB[1]);
-    }
-    float acc[NT][4];
-    uint32_t a[KT][4];
-    {
-      uint32_t ao[1][4];
-      ao[0][0] = pack_bf16(dzA[0], dzA[1]);
-      ao[0][1] = pack_bf16(dzB[0], dzB[1]);
-      ao[0][2] = 0u;
-      ao[0][3] = 0u;
-      zero_acc(acc);
-      warp_layer<1, NT>(ao, s_base + S::woT * 2, 24, acc);
-    }
-#pragma unroll
-    for (int l = NH - 1; l >= 0; --l) {
-      // ReLU mask from the saved activations of layer l; pack d z_l; save it for wgrad
-      const uint32_t *ha = reinterpret_cast<const uint32_t *>(hidden + ((int64_t)l * m_total + rA) * W);
-      const uint32_t *hb = reinterpret_cast<const uint32_t *>(hidden + ((int64_t)l * m_total + rB) * W);
-      uint32_t *za = reinterpret_cast<uint32_t *>(d_z + ((int64_t)l * m_total + rA) * W);
-      uint32_t *zb = reinterpret_cast<uint32_t *>(d_z + ((int64_t)l * m_total + rB) * W);
-#pragma unroll
-      for (int kt = 0; kt < KT; ++kt) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = 2 * kt + h;
-          const uint32_t mA = vA ? __ldg(ha + 4 * j + t) : 0u;
-          const uint32_t mB = vB ? __ldg(hb + 4 * j + t) : 0u;
-          const float x0 = bf16_lo(mA) > 0.f ? acc[j][0] : 0.f;
-          const float x1 = bf16_hi(mA) > 0.f ? acc[j][1] : 0.f;
-          const float x2 = bf16_lo(mB) > 0.f ? acc[j][2] : 0.f;
-          const float x3 = bf16_hi(mB) > 0.f ? acc[j][3] : 0.f;
-          a[kt][2 * h] = pack_bf16(x0, x1);
-          a[kt][2 * h + 1] = pack_bf16(x2, x3);
-          if (vA) za[4 * j + t] = a[kt][2 * h];
-          if (vB) zb[4 * j + t] = a[kt][2 * h + 1];
-        }
-      }
-      if (l > 0) {
-        zero_acc(acc);
-        warp_layer<KT, NT>(a, s_base + (S::whT + (l - 1) * W * (W + 8)) * 2, W + 8, acc);
-      }
-    }
-    if (d_x) {
-      float ax[NTX][4];
-      zero_acc(ax);
-      warp_layer<KT, NTX>(a, s_base + S::w0T * 2, W + 8, ax);
-#pragma unroll
-      for (int j = 0; j < NTX; ++j) {
-        const int col = 8 * j + 2 * t;
-        if (col < dx_cols) {  // dx_cols is even
-          if (vA) {
-            float2 *p = reinterpret_cast<float2 *>(d_x + rA * dx_cols + col);
-            float2 v = make_float2(ax[j][0], ax[j][1]);
-            if (accumulate) {
-              const float2 o = *p;
-              v.x += o.x, v.y += o.y;
-            }
-            *p = v;
-          }
-          if (vB) {
-            float2 *p = reinterpret_cast<float2 *>(d_x + rB * dx_cols + col);
-            float2 v = make_float2(ax[j][2], ax[j][3]);
-            if (accumulate) {
-              const float2 o = *p;
-              v.x += o.x, v.y += o.y;
-            }
-            *p = v;
-          }
-        }
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // backward, weight gradient: dW[o][i] += sum_m dZ[m][o] * In[m][i];  db[o] += sum_m dZ[m][o]
@@ -394,10 +74,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
 // ------------------------------------------------------------------------------------------------
 constexpr int WG_KSTEP = 32;  // samples per pipeline stage
 
-template <int W, int KIN>
+// dz: tiled activation layout; in: tiled (IN_TILED, a hidden layer) or row-major [m][KIN] (the MLP input x)
+template <int W, int KIN, bool IN_TILED>
 __global__ void __launch_bounds__(MLP_THREADS, 1)
     k_mlp_wgrad(const __nv_bfloat16 *__restrict__ dz, const __nv_bfloat16 *__restrict__ in, int64_t row_begin,
                 int64_t row_end, float *__restrict__ gW /* [W][KIN] */, float *__restrict__ gb /* [W] */) {
+  static_assert(W == ACT_W, "tiled activation layout is defined for the 192-wide hidden layers");
   constexpr int SZ = W + 8, SI = KIN + 8;
   constexpr int MT = W / 4 / 16;       // m-tiles (o) per warp: 192/4/16 = 3
   constexpr int NTW = KIN / 2 / 8;     // n-tiles (i) per warp
@@ -424,12 +106,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
     for (int c = threadIdx.x; c < WG_KSTEP * CZ; c += MLP_THREADS) {
       const int rr = c / CZ, q = c - rr * CZ;
       const bool ok = m0 + rr < row_end;
-      cp_async16(smem_u32(&s_dz[buf][rr * SZ + q * 8]), dz + (ok ? (m0 + rr) * W + q * 8 : 0), ok);
+      cp_async16(smem_u32(&s_dz[buf][rr * SZ + q * 8]), dz + (ok ? act_chunk_index(m0 + rr, q) * 8 : 0), ok);
     }
     for (int c = threadIdx.x; c < WG_KSTEP * CI; c += MLP_THREADS) {
       const int rr = c / CI, q = c - rr * CI;
       const bool ok = m0 + rr < row_end;
-      cp_async16(smem_u32(&s_in[buf][rr * SI + q * 8]), in + (ok ? (m0 + rr) * KIN + q * 8 : 0), ok);
+      const int64_t src = IN_TILED ? act_chunk_index(m0 + rr, q) * 8 : (m0 + rr) * KIN + q * 8;
+      cp_async16(smem_u32(&s_in[buf][rr * SI + q * 8]), in + (ok ? src : 0), ok);
     }
     cp_async_commit();
   };
@@ -515,70 +198,71 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
 }
 
 // output layer (n_out <= 3 real rows of 8): dWo[o][i] += sum_m dz_out[m][o] * H[m][i]; dbo[o] += sum_m dz_out[m][o].
-// Skinny (3 x W) and bound by streaming H once: a warp owns a contiguous slab of rows, each lane 6 of the W=192
-// columns (three bf16x2 words), rows unrolled x4 so 12 loads per lane are in flight; 18 accumulators per lane.
+// Skinny (3 x W) and bound by streaming H once.  Work item = (feature chunk c, slab of rows): a warp walks its
+// slab 32 rows at a time, lane = row, one 16-byte load of the tiled H layout per lane (512 contiguous bytes per
+// warp), 24 accumulators per lane, one shuffle reduction + RED at the end.
 template <int W>
 __global__ void __launch_bounds__(256)
-    k_mlp_wgrad_out(const float *__restrict__ dz_out /* [m][8] */, const __nv_bfloat16 *__restrict__ h,
+    k_mlp_wgrad_out(const float *__restrict__ dz_out /* [m][8] */, const __nv_bfloat16 *__restrict__ h /* tiled */,
                     int64_t row_begin, int64_t row_end, int n_out, float *__restrict__ gW /* [8][W] */,
                     float *__restrict__ gb /* [8] */) {
-  static_assert(W == 192, "lane mapping assumes 192 = 32 lanes x 3 bf16x2 words");
+  static_assert(W == ACT_W, "tiled activation layout");
+  constexpr int NC = W / 8;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nslabs = (((int64_t)gridDim.x * blockDim.x) >> 5) / NC;
   const unsigned lane = lane_id();
-  const int64_t n_rows = row_end - row_begin;
-  const int64_t per = (n_rows + nwarps - 1) / nwarps;
-  const int64_t m0 = row_begin + warp * per, m1 = min(row_end, m0 + per);
-  float acc[3][6], bs[3] = {0.f, 0.f, 0.f};
+  const int c = (int)(warp % NC);
+  const int64_t slab = warp / NC;
+  if (slab >= nslabs) return;
+  const int64_t g_begin = row_begin >> 5, g_end = (row_end + 31) >> 5;  // 32-row groups (absolute rows)
+  const int64_t per = (g_end - g_begin + nslabs - 1) / nslabs;
+  const int64_t g0 = g_begin + slab * per, g1 = min(g_end, g0 + per);
+  float acc[3][8], bs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int o = 0; o < 3; ++o)
 #pragma unroll
-    for (int j = 0; j < 6; ++j) acc[o][j] = 0.f;
-  const uint32_t *hw = reinterpret_cast<const uint32_t *>(h);  // bf16x2 words, W/2 per row
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+  const uint4 *h4 = reinterpret_cast<const uint4 *>(h);
   constexpr int UN = 4;
-  for (int64_t m = m0; m < m1; m += UN) {
-    uint32_t v[UN][3];
+  for (int64_t g = g0; g < g1; g += UN) {
+    uint4 v[UN];
     float d[UN][3];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const bool ok = m + u < m1;
+      const int64_t m = (g + u) * 32 + lane;
+      const bool ok = g + u < g1 && m >= row_begin && m < row_end;
+      v[u] = ok ? __ldg(h4 + act_chunk_index(m, c)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) v[u][j] = ok ? __ldg(hw + (m + u) * (W / 2) + 32 * j + lane) : 0u;
-#pragma unroll
-      for (int o = 0; o < 3; ++o) d[u][o] = ok ? __ldg(dz_out + (m + u) * 8 + o) : 0.f;
+      for (int o = 0; o < 3; ++o) d[u][o] = ok ? __ldg(dz_out + m * 8 + o) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < UN; ++u)
+    for (int u = 0; u < UN; ++u) {
+      const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
       for (int o = 0; o < 3; ++o) {
         bs[o] += d[u][o];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          acc[o][2 * j] = fmaf(d[u][o], bf16_lo(v[u][j]), acc[o][2 * j]);
-          acc[o][2 * j + 1] = fmaf(d[u][o], bf16_hi(v[u][j]), acc[o][2 * j + 1]);
+        for (int j = 0; j < 4; ++j) {
+          acc[o][2 * j] = fmaf(d[u][o], bf16_lo(w4[j]), acc[o][2 * j]);
+          acc[o][2 * j + 1] = fmaf(d[u][o], bf16_hi(w4[j]), acc[o][2 * j + 1]);
         }
       }
-  }
-  if (m0 < m1) {
-    for (int o = 0; o < n_out && o < 3; ++o) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) red_add2(gW + (int64_t)o * W + 2 * (32 * j + lane), acc[o][2 * j], acc[o][2 * j + 1]);
-      if (lane == 0) red_add(gb + o, bs[o]);
     }
   }
-}
-
-// image = [mma.sync image | pad to 128 | tcgen05 image]
-static int64_t tc_image_off(const esr_mlp_desc_t *d) { return (layout_of(d).img_bytes() + 127) / 128 * 128; }
-
-// ESR_MLP_PATH=mma selects the legacy mma.sync forward / data-gradient kernels (A/B measurements); default tcgen05
-static bool use_tc(const esr_mlp_desc_t *d) {
-  static int mode = -1;
-  if (mode < 0) {
-    const char *e = getenv("ESR_MLP_PATH");
-    mode = (e && e[0] == 'm') ? 0 : 1;
+  if (g0 >= g1) return;
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = warp_sum(acc[o][j]);
+    bs[o] = warp_sum(bs[o]);
   }
-  return mode == 1 && tc_supported(d);
+  if (lane == 0) {
+    for (int o = 0; o < n_out && o < 3; ++o) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) red_add2(gW + (int64_t)o * W + 8 * c + j, acc[o][j], acc[o][j + 1]);
+      if (c == 0) red_add(gb + o, bs[o]);
+    }
+  }
 }
 
 template <typename K>
@@ -587,43 +271,11 @@ static int set_smem(K kernel, int bytes) {
   return ESR_OK;
 }
 
-static unsigned persistent_grid(int64_t rows) {
-  const int64_t tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
-  const int64_t sms = num_sms();
-  return (unsigned)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
-}
-
-template <int K0, int W, int NH, int DXP>
-static int run_fwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *image, const void *x, int64_t rb,
-                   int64_t re, int64_t mt, float *y, void *hidden, cudaStream_t st) {
-  auto kern = k_mlp_fwd<K0, W, NH>;
-  constexpr int bytes = FwdSmem<K0, W, NH>::bytes;
-  if (int e = set_smem(kern, bytes)) return e;
-  ESR_STAGE(K0 == 96 ? "k_mlp_fwd_radiance" : "k_mlp_fwd_tonemap", st);
-  kern<<<persistent_grid(re - rb), MLP_THREADS, bytes, st>>>(L, (const uint8_t *)image, (const __nv_bfloat16 *)x, rb,
-                                                             re, mt, y, (__nv_bfloat16 *)hidden, d->n_out, d->act);
-  ESR_LAUNCH_OK();
-  return ESR_OK;
-}
-
 template <int K0, int W, int NH, int DXP>
 static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *image, const void *x, const float *y,
                    const float *d_y, int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z,
                    float *d_z_out, float *d_x, int dx_cols, int accumulate, float *grad_flat, cudaStream_t st) {
-  if (use_tc(d)) {
-    if (int e = tc_dgrad(d, (const uint8_t *)image + tc_image_off(d), y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x,
-                         dx_cols, accumulate, st))
-      return e;
-  } else {
-    auto kern = k_mlp_dgrad<K0, W, NH, DXP>;
-    constexpr int bytes = BwdSmem<K0, W, NH, DXP>::bytes;
-    if (int e = set_smem(kern, bytes)) return e;
-    ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_radiance" : "k_mlp_dgrad_tonemap", st);
-    kern<<<persistent_grid(re - rb), MLP_THREADS, bytes, st>>>(L, (const uint8_t *)image, y, d_y, rb, re, mt,
-                                                               (const __nv_bfloat16 *)hidden, (__nv_bfloat16 *)d_z,
-                                                               d_z_out, d_x, dx_cols, accumulate, d->n_out, d->act);
-    ESR_LAUNCH_OK();
-  }
+  if (int e = tc_dgrad(d, image, y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x, dx_cols, accumulate, st)) return e;
   if (!grad_flat) return ESR_OK;
   const __nv_bfloat16 *H = (const __nv_bfloat16 *)hidden;
   const __nv_bfloat16 *Z = (const __nv_bfloat16 *)d_z;
@@ -631,23 +283,25 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
   const unsigned grid = (unsigned)max((int64_t)1, min((int64_t)num_sms(), (rows + 255) / 256));
   // layer 0: In = x
   constexpr int wg_bytes0 = 2 * WG_KSTEP * ((W + 8) + (K0 + 8)) * 2, wg_bytes = 2 * WG_KSTEP * 2 * (W + 8) * 2;
-  if (int e = set_smem(k_mlp_wgrad<W, K0>, wg_bytes0)) return e;
+  const int64_t ls = act_rows_padded(mt) * W;  // layer stride of the tiled activation buffers
+  if (int e = set_smem(k_mlp_wgrad<W, K0, false>, wg_bytes0)) return e;
   ESR_STAGE("k_mlp_wgrad", st);
-  k_mlp_wgrad<W, K0><<<grid, MLP_THREADS, wg_bytes0, st>>>(Z, (const __nv_bfloat16 *)x, rb, re,
+  k_mlp_wgrad<W, K0, false><<<grid, MLP_THREADS, wg_bytes0, st>>>(Z, (const __nv_bfloat16 *)x, rb, re,
                                                            grad_flat + L.flat_w(0), grad_flat + L.flat_b(0));
   ESR_LAUNCH_OK();
   if (NH > 1) {
-    if (int e = set_smem(k_mlp_wgrad<W, W>, wg_bytes)) return e;
+    if (int e = set_smem(k_mlp_wgrad<W, W, true>, wg_bytes)) return e;
   }
   for (int l = 1; l < NH; ++l) {
     ESR_STAGE("k_mlp_wgrad", st);
-    k_mlp_wgrad<W, W><<<grid, MLP_THREADS, wg_bytes, st>>>(Z + (int64_t)l * mt * W, H + (int64_t)(l - 1) * mt * W, rb,
+    k_mlp_wgrad<W, W, true><<<grid, MLP_THREADS, wg_bytes, st>>>(Z + (int64_t)l * ls, H + (int64_t)(l - 1) * ls, rb,
                                                            re, grad_flat + L.flat_w(l), grad_flat + L.flat_b(l));
     ESR_LAUNCH_OK();
   }
-  const unsigned grid_o = (unsigned)max((int64_t)1, min((int64_t)num_sms() * 4, (rows + 255) / 256));
+  // 8 warps per block; warps = 24 chunks x slabs.  3 blocks = 24 warps = one slab.
+  const int64_t slabs = max((int64_t)1, min((int64_t)num_sms(), (rows + 511) / 512));
   ESR_STAGE("k_mlp_wgrad_out", st);
-  k_mlp_wgrad_out<W><<<grid_o, 256, 0, st>>>(d_z_out, H + (int64_t)(NH - 1) * mt * W, rb, re, d->n_out,
+  k_mlp_wgrad_out<W><<<(unsigned)(3 * slabs), 256, 0, st>>>(d_z_out, H + (int64_t)(NH - 1) * ls, rb, re, d->n_out,
                                            grad_flat + L.flat_w(NH), grad_flat + L.flat_b(NH));
   ESR_LAUNCH_OK();
   return ESR_OK;
@@ -655,6 +309,11 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
 
 static int check_desc(const esr_mlp_desc_t *d) {
   ESR_CHECK_ARG(d != nullptr);
+  if (!tc_supported(d)) {
+    set_error("MLP shape k0=%d width=%d hidden=%d is not instantiated (radiance 96->192x3, tone mapper 48->192x1)",
+              d->k0, d->width, d->n_hidden);
+    return ESR_ERR_BAD_ARG;
+  }
   ESR_CHECK_ARG(d->k0 % 16 == 0 && d->k0 > 0 && d->width % 64 == 0 && d->n_hidden >= 1);
   ESR_CHECK_ARG(d->n_out >= 1 && d->n_out <= 3 && (d->act == 1 || d->act == 2));
   return ESR_OK;
@@ -662,17 +321,13 @@ static int check_desc(const esr_mlp_desc_t *d) {
 
 }  // namespace
 
-extern "C" int64_t esr_mlp_image_bytes(const esr_mlp_desc_t *d) { return d ? tc_image_off(d) + tc_image_bytes(d) : 0; }
+extern "C" int64_t esr_mlp_image_bytes(const esr_mlp_desc_t *d) { return d ? tc_image_bytes(d) : 0; }
+extern "C" int64_t esr_mlp_act_rows(int64_t m_total) { return act_rows_padded(m_total); }
 extern "C" int64_t esr_mlp_param_count(const esr_mlp_desc_t *d) { return d ? layout_of(d).flat_count() : 0; }
 extern "C" int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image, esr_stream_t stream) {
   if (int e = check_desc(d)) return e;
   ESR_CHECK_ARG(flat_params && image);
-  const MlpLayout L = layout_of(d);
-  const int64_t n = max(max(L.img_fwd_elems(), L.imgT_elems()), L.n_bias());
-  ESR_STAGE("k_mlp_pack", (cudaStream_t)stream);
-  k_mlp_pack<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(L, flat_params, (uint8_t *)image);
-  ESR_LAUNCH_OK();
-  return tc_pack(d, flat_params, (uint8_t *)image + tc_image_off(d), (cudaStream_t)stream);
+  return tc_pack(d, flat_params, image, (cudaStream_t)stream);
 }
 
 // instantiated shapes: radiance nets 96->192x3->3 (pbr/module.py:6-21 with dim0 85), tone mapper 48->192->3
@@ -684,16 +339,7 @@ extern "C" int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const voi
   ESR_CHECK_ARG(row_begin >= 0 && row_end >= row_begin && row_end <= m_total);
   if (row_end == row_begin) return ESR_OK;
   ESR_CHECK_ARG(image && x && y);
-  const MlpLayout L = layout_of(d);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(d))
-    return tc_fwd(d, (const uint8_t *)image + tc_image_off(d), x, row_begin, row_end, m_total, y, hidden, st);
-#define FWD_CALL(...) run_fwd<__VA_ARGS__>(L, d, image, x, row_begin, row_end, m_total, y, hidden, st)
-  if (d->k0 == 96 && d->width == 192 && d->n_hidden == 3) return FWD_CALL(96, 192, 3, 56);
-  if (d->k0 == 48 && d->width == 192 && d->n_hidden == 1) return FWD_CALL(48, 192, 1, 40);
-#undef FWD_CALL
-  set_error("esr_mlp_fwd: MLP shape k0=%d width=%d hidden=%d is not instantiated", d->k0, d->width, d->n_hidden);
-  return ESR_ERR_BAD_ARG;
+  return tc_fwd(d, image, x, row_begin, row_end, m_total, y, hidden, (cudaStream_t)stream);
 }
 
 extern "C" int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const float *y,

@@ -24,7 +24,8 @@ namespace {
 
 constexpr int TC_W = 192;         // hidden width
 constexpr int TC_TM = 128;        // rows per tile
-constexpr int TC_THREADS = 160;   // warps 0-3: epilogue (TMEM lanes 32w..32w+31), warp 4: MMA issuer
+constexpr int TC_EPI_WARPS = 8;   // warps 0-7: epilogue (TMEM lane quadrant w % 4, column half w / 4)
+constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1);   // + warp 8: MMA issuer / TMEM owner
 constexpr int TC_NOUT_PAD = 16;   // output layer rows padded to the minimum UMMA N for M = 128
 
 // ------------------------------------------------------------------------------------------------
@@ -95,7 +96,6 @@ ESR_D void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-#define TC_R4(r, i) "%" #r "0" #i
 // tcgen05.ld 32x32b.x16 / .x32: thread t of warp w receives columns [c, c+N) of TMEM lane 32*(w%4)+t
 ESR_D void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -245,6 +245,15 @@ struct FwdSm {
   static constexpr int bytes = bar + 16;
 };
 
+// Epilogue thread geometry (8 warps): TMEM lane quadrant = warp % 4 (hardware rule for tcgen05.ld/st), column
+// half = warp / 4: thread (q, lane, half) owns row 32q + lane and feature columns [96 half, 96 half + 96).
+struct EpiThread {
+  int row_in_tile, half;
+  uint32_t lane_base;
+  __device__ EpiThread(unsigned warp, unsigned lane)
+      : row_in_tile(32 * (warp & 3) + lane), half(warp >> 2), lane_base((32u * (warp & 3)) << 16) {}
+};
+
 template <int K0, int NH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_fwd_tc(const uint8_t *__restrict__ image, const __nv_bfloat16 *__restrict__ x, int64_t row_begin,
@@ -253,6 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   extern __shared__ __align__(128) uint8_t smem[];
   using S = FwdSm<K0, NH>;
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
   const uint32_t bar = sbase + S::bar;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 8);
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
+  if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -271,31 +281,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
 
   const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
-  const uint32_t lane_base = (32u * warp) << 16;  // TMEM lane field of this epilogue warp
-  const int t = threadIdx.x;                      // epilogue threads: row within the tile
+  const EpiThread et(warp, lane);
+  const int t = et.row_in_tile;
   uint32_t phase = 0;
 
-  auto load_x = [&](int64_t tile) {  // epilogue threads: one row each, K0/8 16-byte chunks
+  auto load_x = [&](int64_t tile) {  // 2 epilogue threads per row: 16-byte chunks c = half, half + 2, ...
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool ok = row < row_end;
     const __nv_bfloat16 *src = x + (ok ? row : row_begin) * K0;
 #pragma unroll
-    for (int c = 0; c < K0 / 8; ++c) cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, src + c * 8, ok);
+    for (int c = et.half; c < K0 / 8; c += 2) cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, src + c * 8, ok);
   };
 
-  if (warp < 4 && blockIdx.x < n_tiles) load_x(blockIdx.x);
+  if (is_epi && blockIdx.x < n_tiles) load_x(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = row_begin + tile * TC_TM + t;
-    const bool valid = warp < 4 && row < row_end;
+    const bool valid = is_epi && row < row_end;
     // ---- layer 0: A = x tile (shared), B = W0 ----
-    if (warp < 4) {
+    if (is_epi) {
       cp_async_wait_all();
       fence_proxy_async();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4 && lane == 0) {
+    if (is_issuer && lane == 0) {
       tc_fence_after();
 #pragma unroll
       for (int s = 0; s < K0 / 16; ++s)
@@ -305,35 +315,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 #pragma unroll 1
     for (int l = 0; l < NH; ++l) {
-      if (warp < 4) {
+      if (is_epi) {
         mbar_wait(bar, phase);
         tc_fence_after();
         if (l == 0 && tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);  // x tile is free: prefetch the next one
-        // bias + ReLU -> bf16 -> TMEM A operand (+ global copy for the backward pass)
+        // bias + ReLU -> bf16 -> TMEM A operand (+ global copy, tiled layout, for the backward pass)
         const float *b = sbias + l * TC_W;
-        __nv_bfloat16 *hrow = hidden ? hidden + ((int64_t)l * m_total + row) * TC_W : nullptr;
-#pragma unroll 1
-        for (int cc = 0; cc < TC_W / 32; ++cc) {
+        uint4 *hl = hidden ? reinterpret_cast<uint4 *>(hidden + (int64_t)l * act_rows_padded(m_total) * TC_W) : nullptr;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const int col0 = 96 * et.half + 32 * cc;
           uint32_t r[32], p[16];
-          tmem_ld32(tmem + lane_base + TM_D + cc * 32, r);
+          tmem_ld32(tmem + et.lane_base + TM_D + col0, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float2 bb = *reinterpret_cast<const float2 *>(b + cc * 32 + 2 * j);
+            const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
             p[j] = pack2(fmaxf(__uint_as_float(r[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(r[2 * j + 1]) + bb.y, 0.f));
           }
-          tmem_st16(tmem + lane_base + TM_A + cc * 16, p);
-          if (hrow && valid) {
-            uint4 *dst = reinterpret_cast<uint4 *>(hrow + cc * 32);
+          tmem_st16(tmem + et.lane_base + TM_A + col0 / 2, p);
+          if (hl && valid) {  // the warp's 32 rows write 512 contiguous bytes per chunk
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+            for (int q = 0; q < 4; ++q)
+              hl[act_chunk_index(row, col0 / 8 + q)] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
           }
         }
         tmem_st_wait();
       }
       tc_fence_before();
       __syncthreads();
-      if (warp == 4 && lane == 0) {
+      if (is_issuer && lane == 0) {
         tc_fence_after();
         if (l + 1 < NH) {
           const uint32_t wl = sbase + S::wh + l * (TC_W * TC_W * 2);
@@ -352,25 +363,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       phase ^= 1;
     }
-    // ---- output layer epilogue ----
-    if (warp < 4) {
+    // ---- output layer epilogue (column half 0 threads) ----
+    if (is_epi) {
       mbar_wait(bar, phase);
       tc_fence_after();
-      uint32_t r[16];
-      tmem_ld16(tmem + lane_base + TM_S, r);
-      tmem_ld_wait();
-      if (valid) {
-        const float *bo = sbias + NH * TC_W;
+      if (et.half == 0) {
+        uint32_t r[16];
+        tmem_ld16(tmem + et.lane_base + TM_S, r);
+        tmem_ld_wait();
+        if (valid) {
+          const float *bo = sbias + NH * TC_W;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (c < n_out) y[row * n_out + c] = act_fwd(__uint_as_float(r[c]) + bo[c], act);
+          for (int c = 0; c < 3; ++c)
+            if (c < n_out) y[row * n_out + c] = act_fwd(__uint_as_float(r[c]) + bo[c], act);
+        }
       }
     }
     phase ^= 1;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TM_COLS);
+  if (is_issuer) tmem_dealloc(tmem, TM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,6 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   extern __shared__ __align__(128) uint8_t smem[];
   using S = BwdSm<K0, NH, DXN>;
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
   const uint32_t bar = sbase + S::bar;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 8);
@@ -405,7 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
+  if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
   // chunk 1 (columns 8..15) of the dZ_out tile stays zero
   if (threadIdx.x < TC_TM) *reinterpret_cast<uint4 *>(smem + S::dz + TC_TM * 16 + threadIdx.x * 16) = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
@@ -415,15 +429,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem = *tmem_slot;
 
   const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
-  const uint32_t lane_base = (32u * warp) << 16;
-  const int t = threadIdx.x;
+  const EpiThread et(warp, lane);
+  const int t = et.row_in_tile;
+  const int64_t layer_stride = act_rows_padded(m_total) * TC_W;
   uint32_t phase = 0;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = row_begin + tile * TC_TM + t;
-    const bool valid = warp < 4 && row < row_end;
-    // ---- dZ_out = d_y * act'(y): A tile of the first MMA ----
-    if (warp < 4) {
+    const bool valid = is_epi && row < row_end;
+    // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column half 0 threads) ----
+    if (is_epi && et.half == 0) {
       float dz[3] = {0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4 && lane == 0) {
+    if (is_issuer && lane == 0) {
       tc_fence_after();
       mma_ss(tmem + TM_D, make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
              make_idesc(TC_W), 0);
@@ -450,38 +465,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 #pragma unroll 1
     for (int l = NH - 1; l >= 0; --l) {
-      if (warp < 4) {
+      if (is_epi) {
+        // ReLU masks: this thread's 12 chunks of H_l, requested BEFORE waiting for the MMA so that the global
+        // latency overlaps the tensor work of this layer
+        const uint4 *hl = reinterpret_cast<const uint4 *>(hidden + (int64_t)l * layer_stride);
+        uint4 *zl = reinterpret_cast<uint4 *>(d_z + (int64_t)l * layer_stride);
+        uint4 h[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q)
+          h[q] = valid ? __ldg(hl + act_chunk_index(row, 12 * et.half + q)) : make_uint4(0, 0, 0, 0);
         mbar_wait(bar, phase);
         tc_fence_after();
-        // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy for the weight-gradient GEMM
-        const __nv_bfloat16 *hrow = hidden + ((int64_t)l * m_total + (valid ? row : row_begin)) * TC_W;
-        __nv_bfloat16 *zrow = d_z + ((int64_t)l * m_total + row) * TC_W;
-#pragma unroll 1
-        for (int cc = 0; cc < TC_W / 32; ++cc) {
-          uint32_t r[32], p[16], h[16];
-          const uint4 *hs = reinterpret_cast<const uint4 *>(hrow + cc * 32);
+        // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy (tiled) for the weight-gradient GEMM
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 v = valid ? __ldg(hs + q) : make_uint4(0, 0, 0, 0);
-            h[4 * q] = v.x, h[4 * q + 1] = v.y, h[4 * q + 2] = v.z, h[4 * q + 3] = v.w;
-          }
-          tmem_ld32(tmem + lane_base + TM_D + cc * 32, r);
+        for (int cc = 0; cc < 3; ++cc) {
+          const int col0 = 96 * et.half + 32 * cc;
+          uint32_t r[32], p[16];
+          tmem_ld32(tmem + et.lane_base + TM_D + col0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            p[j] = pack2(lo16(h[j]) > 0.f ? __uint_as_float(r[2 * j]) : 0.f, hi16(h[j]) > 0.f ? __uint_as_float(r[2 * j + 1]) : 0.f);
-          tmem_st16(tmem + lane_base + TM_A + cc * 16, p);
-          if (valid) {
-            uint4 *dst = reinterpret_cast<uint4 *>(zrow + cc * 32);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 hv = h[4 * cc + q];
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+            for (int j = 0; j < 4; ++j)
+              p[4 * q + j] = pack2(lo16(hw[j]) > 0.f ? __uint_as_float(r[8 * q + 2 * j]) : 0.f,
+                                   hi16(hw[j]) > 0.f ? __uint_as_float(r[8 * q + 2 * j + 1]) : 0.f);
+          }
+          tmem_st16(tmem + et.lane_base + TM_A + col0 / 2, p);
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              zl[act_chunk_index(row, col0 / 8 + q)] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
           }
         }
         tmem_st_wait();
       }
       tc_fence_before();
       __syncthreads();
-      if (warp == 4 && lane == 0) {
+      if (is_issuer && lane == 0) {
         tc_fence_after();
         if (l > 0) {
           const uint32_t wl = sbase + S::wh + (l - 1) * (TC_W * TC_W * 2);
@@ -499,14 +521,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       phase ^= 1;
     }
-    // ---- d_x epilogue ----
-    if (warp < 4) {
+    // ---- d_x epilogue: 16-column groups split between the two column halves ----
+    if (is_epi) {
       mbar_wait(bar, phase);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < DXN / 16; ++cc) {
+        if ((cc & 1) != et.half) continue;  // warp-uniform
         uint32_t r[16];
-        tmem_ld16(tmem + lane_base + TM_S + cc * 16, r);
+        tmem_ld16(tmem + et.lane_base + TM_S + cc * 16, r);
         tmem_ld_wait();
         if (valid && d_x) {
 #pragma unroll
@@ -530,7 +553,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TM_COLS);
+  if (is_issuer) tmem_dealloc(tmem, TM_COLS);
 }
 
 template <typename K>
@@ -587,7 +610,6 @@ int tc_pack(const esr_mlp_desc_t *d, const float *flat_params, void *tc_image, c
   if (!tc_supported(d)) return ESR_OK;
   const TcLayout T = tc_layout(d);
   const MlpLayout L = layout_of(d);
-  static_assert(FwdSm<96, 3>::weights_bytes > 0, "");
   ESR_CHECK_CUDA(cudaMemsetAsync(tc_image, 0, (size_t)T.total(), st));
   const int64_t n = (int64_t)TC_W * T.k0 + (int64_t)(T.NH - 1) * TC_W * TC_W + (int64_t)TC_NOUT_PAD * TC_W +
                     (int64_t)T.NH * TC_W + TC_NOUT_PAD;

@@ -220,8 +220,8 @@ def _mlp_forward(desc, image, x, rb, re, m_total, train):
     d = _desc(desc)
     dev = x.device
     y = torch.zeros(m_total, desc["n_out"], dtype=torch.float32, device=dev)
-    hidden = (torch.empty(desc["n_hidden"], m_total, desc["width"], dtype=torch.bfloat16, device=dev)
-              if train else None)
+    hidden = (torch.empty(desc["n_hidden"], L.esr_mlp_act_rows(m_total), desc["width"], dtype=torch.bfloat16,
+                          device=dev) if train else None)   # tiled layout private to the library
     check(L.esr_mlp_fwd(ctypes.byref(d), ptr(image), ptr(x), rb, re, m_total, ptr(y), ptr(hidden), stream_ptr()))
     return y, hidden
 
@@ -231,7 +231,8 @@ def _mlp_backward(desc, image, x, y, d_y, rb, re, m_total, hidden, d_x, dx_cols,
     d = _desc(desc)
     dev = x.device
     if scratch is None:
-        scratch = torch.empty(desc["n_hidden"], m_total, desc["width"], dtype=torch.bfloat16, device=dev)
+        scratch = torch.empty(desc["n_hidden"], L.esr_mlp_act_rows(m_total), desc["width"], dtype=torch.bfloat16,
+                              device=dev)
     d_z_out = torch.empty(m_total, 8, dtype=torch.float32, device=dev)
     grad_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=dev)
     check(L.esr_mlp_bwd(ctypes.byref(d), ptr(image), ptr(x), ptr(y), ptr(d_y), rb, re, m_total, ptr(hidden),

@@ -230,14 +230,20 @@ typedef struct esr_mlp_desc {
 int64_t esr_mlp_param_count(const esr_mlp_desc_t *d); /* f32 elements of the flat master copy */
 int64_t esr_mlp_image_bytes(const esr_mlp_desc_t *d);
 /*
+ * Row count (m_total rounded up to the 128-row tile) the activation buffers `hidden` and `d_z` must be sized
+ * for.  Both are bf16 [n_hidden][esr_mlp_act_rows(m_total)][width] in a TILED layout private to the library
+ * (per 128-row tile: [width/8 feature chunks][128 rows][8]); callers only allocate and pass them through.
+ */
+int64_t esr_mlp_act_rows(int64_t m_total);
+/*
  * flat f32 master copy layout: for each layer l: W_l [out_l][in_l_padded] then b_l [out_l]
- * (output layer padded to 8 rows).  esr_mlp_pack converts it to the bf16 kernel image (+ transposed
- * copies for the data-gradient pass).
+ * (output layer padded to 8 rows).  esr_mlp_pack converts it to the bf16 kernel image: every weight matrix and
+ * its transpose in the shared-memory operand layout of the tcgen05 kernels, plus the f32 biases.
  */
 int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image, esr_stream_t stream);
 /*
  * Forward over rows [row_begin,row_end) of x (bf16 [*,k0]).  y: f32 [*,n_out] (activated).
- * hidden (nullable): bf16 [n_hidden][m_total][width] post-ReLU activations saved for backward.
+ * hidden (nullable): bf16 [n_hidden][esr_mlp_act_rows(m_total)][width] post-ReLU activations saved for backward.
  */
 int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t row_begin,
                 int64_t row_end, int64_t m_total, float *y, void *hidden, esr_stream_t stream);
@@ -245,7 +251,7 @@ int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64
  * Backward over rows [row_begin,row_end): d_y is dL/dy (post-activation), y the saved outputs.
  *   d_x (nullable): f32 [*, dx_cols] gets dL/dx for the first dx_cols input columns
  *                   (accumulate != 0 adds to existing values).
- *   d_z: bf16 scratch [n_hidden][m_total][width] + f32 [m_total][8] for the output layer
+ *   d_z: bf16 scratch [n_hidden][esr_mlp_act_rows(m_total)][width]; d_z_out: f32 [m_total][8] (output layer)
  *   grad_flat: f32 flat gradient (same layout as flat_params), ACCUMULATED into (atomics).
  */
 int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const float *y,

@@ -16,6 +16,12 @@ def _bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def _untile(buf):
+    """library-private tiled activation layout [tiles][24 chunks][128 rows][8] -> row-major [rows, 192]"""
+    rows = buf.shape[0]
+    return buf.reshape(rows // 128, 24, 128, 8).permute(0, 2, 1, 3).reshape(rows, 192)
+
+
 def _flat_and_layers(desc, seed):
     g = torch.Generator().manual_seed(seed)
     k0, w, nh = desc["k0"], desc["width"], desc["n_hidden"]
@@ -79,7 +85,7 @@ def test_mlp_fwd_bwd_matches_bf16_contract(which, m, rb, re):
     if rb > 0:
         assert (y[:rb] == 0).all()                      # rows outside [rb, re) untouched
     for l, h in enumerate(hid_ref):
-        got = hidden[l, rb:re].float().cpu()
+        got = _untile(hidden[l])[rb:re].float().cpu()
         # bf16 storage: allow 1 ulp (2^-8 relative) + accumulation-order noise
         assert torch.allclose(got, h, rtol=1e-2, atol=1e-2), (l, (got - h).abs().max())
 
