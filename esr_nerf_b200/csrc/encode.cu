@@ -2,6 +2,7 @@
 // trilinear gathers + scatter-add), tone-map encode fwd/bwd, and the per-ray compositing fwd/bwd that
 // replaces torch_scatter.segment_coo.
 #include "common.cuh"
+#include "mlp_layout.cuh"
 
 using namespace esr;
 
@@ -75,21 +76,41 @@ struct RowWriter;
 template <>
 struct RowWriter<float> {
   float *row;
+  ESR_D RowWriter(float *b, int64_t r) : row(b + r * ESR_FEAT_DIM) {}
+  ESR_D void finish() {}
   template <int N>
   ESR_D void put(int col0, const float (&v)[N]) {
 #pragma unroll
     for (int i = 0; i < N; i += 2) *reinterpret_cast<float2 *>(row + col0 + i) = make_float2(v[i], v[i + 1]);
   }
 };
-template <>
-struct RowWriter<__nv_bfloat16> {
-  __nv_bfloat16 *row;
+// bf16 rows go to the MLP kernels in the TILED layout of mlp_layout.cuh ([tile][chunk][128 rows][8]): the row is
+// assembled in registers (all column indices are compile-time after unrolling) and flushed as 16-byte chunks, which
+// are contiguous across the consecutive rows of a warp.
+template <int WIDTH>
+struct TiledRowWriter {
+  uint32_t w[WIDTH / 2];
   template <int N>
   ESR_D void put(int col0, const float (&v)[N]) {
 #pragma unroll
-    for (int i = 0; i < N; i += 2)
-      *reinterpret_cast<__nv_bfloat162 *>(row + col0 + i) = __floats2bfloat162_rn(v[i], v[i + 1]);
+    for (int i = 0; i < N; i += 2) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(v[i], v[i + 1]);
+      w[(col0 + i) >> 1] = *reinterpret_cast<uint32_t *>(&p);
+    }
   }
+  ESR_D void flush(__nv_bfloat16 *base, int64_t row) {
+    uint4 *b4 = reinterpret_cast<uint4 *>(base);
+#pragma unroll
+    for (int c = 0; c < WIDTH / 8; ++c)
+      b4[tiled_chunk_index(row, c, WIDTH / 8)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  }
+};
+template <>
+struct RowWriter<__nv_bfloat16> : TiledRowWriter<ESR_FEAT_DIM> {
+  __nv_bfloat16 *base;
+  int64_t row;
+  ESR_D RowWriter(__nv_bfloat16 *b, int64_t r) : base(b), row(r) {}
+  ESR_D void finish() { flush(base, row); }
 };
 
 constexpr int COL_SDF = 12, COL_FEAT = 13, COL_NRM = 37, COL_XYZ = 49, COL_SIN = 52, COL_COS = 67, COL_VIEW = 82;
@@ -112,7 +133,7 @@ __global__ void __launch_bounds__(128)
   g.ix = world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx);
   g.iy = world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy);
   g.iz = world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz);
-  RowWriter<OutT> wr{feat + j * ESR_FEAT_DIM};
+  RowWriter<OutT> wr(feat, j);
 
   {  // colour grids (module.py:24-35), channels-last
     const Cell c = make_cell(g.ix, g.iy, g.iz);
@@ -174,6 +195,7 @@ __global__ void __launch_bounds__(128)
     for (int c = 9; c < 14; ++c) v[c] = 0.f;
     wr.put(COL_VIEW, v);
   }
+  wr.finish();
 }
 
 __global__ void __launch_bounds__(128)
@@ -270,8 +292,14 @@ __global__ void __launch_bounds__(256)
   }
 #pragma unroll
   for (int c = 33; c < 48; ++c) v[c] = 0.f;
-  RowWriter<OutT> wr{tfeat + j * ESR_TFEAT_DIM};
-  wr.put(0, v);
+  if constexpr (sizeof(OutT) == 2) {
+    TiledRowWriter<ESR_TFEAT_DIM> wr;
+    wr.put(0, v);
+    wr.flush(tfeat, j);
+  } else {
+#pragma unroll
+    for (int c = 0; c < ESR_TFEAT_DIM; ++c) tfeat[j * ESR_TFEAT_DIM + c] = v[c];
+  }
 }
 
 __global__ void __launch_bounds__(256)

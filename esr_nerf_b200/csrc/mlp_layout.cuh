@@ -29,10 +29,14 @@ static inline MlpLayout layout_of(const esr_mlp_desc_t *d) { return MlpLayout{d-
 // [ceil(m/128)] tiles of [24 feature chunks][128 rows][8 bf16] — the shared-memory operand layout of the
 // tensor-core kernels, so that one thread per row moves 16-byte chunks that are contiguous across a warp.
 // ------------------------------------------------------------------------------------------------
+// The bf16 MLP inputs (encoded feature rows x, tone-map feature rows) use the same tiling with their own width.
 constexpr int ACT_W = 192;
 ESR_HD int64_t act_rows_padded(int64_t m_total) { return (m_total + 127) / 128 * 128; }
-// index, in 16-byte units, of feature chunk c (8 features) of absolute row `row`
-ESR_HD int64_t act_chunk_index(int64_t row, int c) { return ((row >> 7) * (ACT_W / 8) + c) * 128 + (row & 127); }
+// index, in 16-byte units, of feature chunk c (8 features) of absolute row `row` in a [*, 8*chunks_per_row] matrix
+ESR_HD int64_t tiled_chunk_index(int64_t row, int c, int chunks_per_row) {
+  return ((row >> 7) * chunks_per_row + c) * 128 + (row & 127);
+}
+ESR_HD int64_t act_chunk_index(int64_t row, int c) { return tiled_chunk_index(row, c, ACT_W / 8); }
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 path (mlp_tc.cu)
@@ -45,5 +49,8 @@ int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t
 int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, const float *d_y, int64_t row_begin,
              int64_t row_end, int64_t m_total, const void *hidden, void *d_z, float *d_z_out, float *d_x,
              int dx_cols, int accumulate, cudaStream_t st);
+// hidden-layer weight / bias gradients: grad_flat (flat master layout) += dZ_l^T . In_l for l = 0 .. n_hidden-1
+int tc_wgrad(const esr_mlp_desc_t *d, const void *x, int64_t row_begin, int64_t row_end, int64_t m_total,
+             const void *hidden, const void *d_z, float *grad_flat, cudaStream_t st);
 
 }  // namespace esr

@@ -280,24 +280,8 @@ static int run_bwd(const MlpLayout &L, const esr_mlp_desc_t *d, const void *imag
   const __nv_bfloat16 *H = (const __nv_bfloat16 *)hidden;
   const __nv_bfloat16 *Z = (const __nv_bfloat16 *)d_z;
   const int64_t rows = re - rb;
-  const unsigned grid = (unsigned)max((int64_t)1, min((int64_t)num_sms(), (rows + 255) / 256));
-  // layer 0: In = x
-  constexpr int wg_bytes0 = 2 * WG_KSTEP * ((W + 8) + (K0 + 8)) * 2, wg_bytes = 2 * WG_KSTEP * 2 * (W + 8) * 2;
   const int64_t ls = act_rows_padded(mt) * W;  // layer stride of the tiled activation buffers
-  if (int e = set_smem(k_mlp_wgrad<W, K0, false>, wg_bytes0)) return e;
-  ESR_STAGE("k_mlp_wgrad", st);
-  k_mlp_wgrad<W, K0, false><<<grid, MLP_THREADS, wg_bytes0, st>>>(Z, (const __nv_bfloat16 *)x, rb, re,
-                                                           grad_flat + L.flat_w(0), grad_flat + L.flat_b(0));
-  ESR_LAUNCH_OK();
-  if (NH > 1) {
-    if (int e = set_smem(k_mlp_wgrad<W, W, true>, wg_bytes)) return e;
-  }
-  for (int l = 1; l < NH; ++l) {
-    ESR_STAGE("k_mlp_wgrad", st);
-    k_mlp_wgrad<W, W, true><<<grid, MLP_THREADS, wg_bytes, st>>>(Z + (int64_t)l * ls, H + (int64_t)(l - 1) * ls, rb,
-                                                           re, grad_flat + L.flat_w(l), grad_flat + L.flat_b(l));
-    ESR_LAUNCH_OK();
-  }
+  if (int e = tc_wgrad(d, x, rb, re, mt, hidden, d_z, grad_flat, st)) return e;
   // 8 warps per block; warps = 24 chunks x slabs.  3 blocks = 24 warps = one slab.
   const int64_t slabs = max((int64_t)1, min((int64_t)num_sms(), (rows + 511) / 512));
   ESR_STAGE("k_mlp_wgrad_out", st);

@@ -288,9 +288,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   auto load_x = [&](int64_t tile) {  // 2 epilogue threads per row: 16-byte chunks c = half, half + 2, ...
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool ok = row < row_end;
-    const __nv_bfloat16 *src = x + (ok ? row : row_begin) * K0;
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(x);  // tiled layout: a warp reads 512 contiguous bytes per chunk
 #pragma unroll
-    for (int c = et.half; c < K0 / 8; c += 2) cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, src + c * 8, ok);
+    for (int c = et.half; c < K0 / 8; c += 2)
+      cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, x4 + tiled_chunk_index(ok ? row : row_begin, c, K0 / 8), ok);
   };
 
   if (is_epi && blockIdx.x < n_tiles) load_x(blockIdx.x);
@@ -556,6 +557,183 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (is_issuer) tmem_dealloc(tmem, TM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW_l[o][i] += sum_m dZ_l[m][o] * In_l[m][i],  db_l[o] += sum_m dZ_l[m][o]
+//
+// A GEMM whose K dimension is the sample index.  Both operands are read straight out of the tiled activation
+// buffers: a [128 rows x 8c features] tile is, byte for byte, a no-swizzle MN-major UMMA operand (8 features
+// contiguous, the next 8 rows 128 B further = LBO, the next 8 features 2048 B further = SBO), so one 1-D bulk copy
+// (cp.async.bulk, completion on an mbarrier) per operand per tile feeds the tensor core with no re-layout.
+// M = 192 output features does not fit one UMMA (M <= 128): two accumulators of M = 128 over features [0,128) and
+// [64,192) (the overlap is computed twice and discarded).  A constant "ones" chunk appended to the B tile makes the
+// bias gradient column KIN of the same accumulator.  Split-K across persistent CTAs; fp32 partials leave through
+// vector RED.
+// ------------------------------------------------------------------------------------------------
+ESR_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+ESR_D void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+ESR_D void red_add4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// instruction descriptor: D f32, A/B bf16, both MN-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
+
+template <int KIN>
+struct WgSm {
+  static constexpr int a_bytes = TC_TM * TC_W * 2;                // dZ tile
+  static constexpr int b_chunks = KIN / 8 + 2;                    // In tile + 2 constant chunks ("ones" column)
+  static constexpr int b_bytes = b_chunks * TC_TM * 16;
+  static constexpr int stage = a_bytes + b_bytes;
+  static constexpr int bar = 2 * stage;                           // full[2], empty[2] (8 B each), tmem slot
+  static constexpr int bytes = bar + 48;
+  static constexpr int NB = KIN + 16;                             // UMMA N
+};
+
+template <int KIN>
+__global__ void __launch_bounds__(160, 1)
+    k_mlp_wgrad_tc(const __nv_bfloat16 *__restrict__ dz, const __nv_bfloat16 *__restrict__ in, int64_t row_begin,
+                   int64_t row_end, float *__restrict__ gW /* [192][KIN] */, float *__restrict__ gb /* [192] */) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = WgSm<KIN>;
+  const int64_t T0 = row_begin >> 7, T1 = (row_end + 127) >> 7;
+  const int64_t per = (T1 - T0 + gridDim.x - 1) / gridDim.x;
+  const int64_t ta = T0 + (int64_t)blockIdx.x * per, tb = min(T1, ta + per);
+  const int64_t n = tb - ta;
+  if (n <= 0) return;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_addr(smem);
+  const uint32_t bar_full = sbase + S::bar, bar_empty = sbase + S::bar + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
+  const bool driver = threadIdx.x == 128;  // producer + MMA issuer
+
+  // constant chunks of both stages: column KIN of the B tile is 1.0 for every row, columns KIN+1.. are zero
+  for (int i = threadIdx.x; i < 2 * 2 * TC_TM; i += blockDim.x) {
+    const int st = i / (2 * TC_TM), r = i % (2 * TC_TM);  // r < 128: chunk KIN/8, else chunk KIN/8 + 1
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < TC_TM) v.x = 0x00003f80u;  // bf16 1.0 in element 0
+    *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_bytes + (KIN / 8) * (TC_TM * 16) + r * 16) = v;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1), mbar_init(bar_full + 8, 1), mbar_init(bar_empty, 1), mbar_init(bar_empty + 8, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint4 *dz4 = reinterpret_cast<const uint4 *>(dz), *in4 = reinterpret_cast<const uint4 *>(in);
+
+  auto load_tile = [&](int64_t tile, int st) {  // driver thread
+    const uint32_t full = bar_full + 8 * st;
+    mbar_expect_tx(full, S::a_bytes + (KIN / 8) * TC_TM * 16);
+    bulk_g2s(sbase + st * S::stage, dz4 + tile * (TC_W / 8) * TC_TM, S::a_bytes, full);
+    bulk_g2s(sbase + st * S::stage + S::a_bytes, in4 + tile * (KIN / 8) * TC_TM, (KIN / 8) * TC_TM * 16, full);
+  };
+
+  if (driver) load_tile(ta, 0);
+  for (int64_t it = 0; it < n; ++it) {
+    const int st = (int)(it & 1);
+    const uint32_t k_par = (uint32_t)((it >> 1) & 1);
+    const int64_t tile = ta + it;
+    if (driver && it + 1 < n) {
+      if (it >= 1) mbar_wait(bar_empty + 8 * (st ^ 1), (uint32_t)(((it - 1) >> 1) & 1));  // MMAs of tile it-1 retired
+      load_tile(tile + 1, st ^ 1);
+    }
+    const int64_t r0 = tile * TC_TM;
+    if (r0 < row_begin || r0 + TC_TM > row_end) {
+      // boundary tile: rows outside [row_begin, row_end) hold unrelated data -> zero them in both operands
+      mbar_wait(bar_full + 8 * st, k_par);
+      if (threadIdx.x < TC_TM) {
+        const int64_t row = r0 + threadIdx.x;
+        if (row < row_begin || row >= row_end) {
+          uint8_t *a = smem + st * S::stage + threadIdx.x * 16;
+#pragma unroll 4
+          for (int c = 0; c < TC_W / 8; ++c) *reinterpret_cast<uint4 *>(a + c * (TC_TM * 16)) = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+          for (int c = 0; c < KIN / 8 + 1; ++c)   // + the "ones" chunk: the row must not count in the bias either
+            *reinterpret_cast<uint4 *>(a + S::a_bytes + c * (TC_TM * 16)) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      fence_proxy_async();
+      __syncthreads();
+    }
+    if (driver) {
+      mbar_wait(bar_full + 8 * st, k_par);
+      tc_fence_after();
+      const uint32_t a0 = sbase + st * S::stage, b0 = a0 + S::a_bytes;
+#pragma unroll
+      for (int s = 0; s < TC_TM / 16; ++s) {
+        const uint64_t bd = make_desc(b0 + s * 256, 128, TC_TM * 16);
+        mma_ss(tmem + 0, make_desc(a0 + s * 256, 128, TC_TM * 16), bd, make_idesc_mn(S::NB), (it | s) != 0);
+        mma_ss(tmem + 256, make_desc(a0 + 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16), bd, make_idesc_mn(S::NB),
+               (it | s) != 0);
+      }
+      mma_commit(bar_empty + 8 * st);
+    }
+    __syncthreads();
+    if (r0 < row_begin || r0 + TC_TM > row_end) {
+      // restore the "ones" chunk rows zeroed above once the MMAs that read them have retired (next use of the stage)
+      mbar_wait(bar_empty + 8 * st, k_par);
+      if (threadIdx.x < TC_TM)
+        *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_bytes + (KIN / 8) * (TC_TM * 16) + threadIdx.x * 16) =
+            make_uint4(0x00003f80u, 0, 0, 0);
+      fence_proxy_async();
+      __syncthreads();
+    }
+  }
+  // ---- epilogue: accumulators -> global gradient (RED) ----
+  mbar_wait(bar_empty + 8 * (int)((n - 1) & 1), (uint32_t)(((n - 1) >> 1) & 1));
+  tc_fence_after();
+  if (warp < 4) {
+    const uint32_t lane_base = (32u * warp) << 16;
+    const int ml = 32 * warp + lane;  // accumulator row
+#pragma unroll 1
+    for (int acc = 0; acc < 2; ++acc) {
+      const int o = acc == 0 ? ml : 64 + ml;
+      const bool use = acc == 0 || ml >= 64;  // accumulator 1: only features 128..191 are new
+#pragma unroll 1
+      for (int cc = 0; cc < S::NB / 16; ++cc) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + acc * 256 + cc * 16, r);
+        tmem_ld_wait();
+        if (!use) continue;
+        if (cc < KIN / 16) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            red_add4(gW + (int64_t)o * KIN + cc * 16 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        } else {
+          red_add(gb + o, __uint_as_float(r[0]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, TM_COLS);
+}
+
+template <int KIN>
+static int launch_wgrad(const __nv_bfloat16 *dz, const __nv_bfloat16 *in, int64_t rb, int64_t re, float *gW, float *gb,
+                        cudaStream_t st) {
+  auto kern = k_mlp_wgrad_tc<KIN>;
+  constexpr int bytes = WgSm<KIN>::bytes;
+  ESR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int64_t tiles = ((re + 127) >> 7) - (rb >> 7);
+  const unsigned grid = (unsigned)max((int64_t)1, min((int64_t)num_sms(), tiles));
+  ESR_STAGE("k_mlp_wgrad_tc", st);
+  kern<<<grid, 160, bytes, st>>>(dz, in, rb, re, gW, gb);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
 template <typename K>
 static int set_smem_tc(K kernel, int bytes) {
   ESR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -639,6 +817,24 @@ int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, cons
                                    dx_cols, accumulate, st);
   set_error("tc_dgrad: shape not instantiated");
   return ESR_ERR_BAD_ARG;
+}
+
+int tc_wgrad(const esr_mlp_desc_t *d, const void *x, int64_t row_begin, int64_t row_end, int64_t m_total,
+             const void *hidden, const void *d_z, float *grad_flat, cudaStream_t st) {
+  const MlpLayout L = layout_of(d);
+  const int64_t ls = act_rows_padded(m_total) * TC_W;
+  const __nv_bfloat16 *H = (const __nv_bfloat16 *)hidden, *Z = (const __nv_bfloat16 *)d_z;
+  int e;
+  if (d->k0 == 96)
+    e = launch_wgrad<96>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, grad_flat + L.flat_w(0), grad_flat + L.flat_b(0), st);
+  else
+    e = launch_wgrad<48>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, grad_flat + L.flat_w(0), grad_flat + L.flat_b(0), st);
+  if (e) return e;
+  for (int l = 1; l < d->n_hidden; ++l)
+    if ((e = launch_wgrad<192>(Z + l * ls, H + (l - 1) * ls, row_begin, row_end, grad_flat + L.flat_w(l),
+                               grad_flat + L.flat_b(l), st)))
+      return e;
+  return ESR_OK;
 }
 
 }  // namespace esr

@@ -173,7 +173,9 @@ def mlp_pack(desc: dict, flat: torch.Tensor) -> torch.Tensor:
 
 
 def encode_features(sc: Scene, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s: Streams, bf16: bool):
-    x = torch.empty(s.m3, FEAT_DIM, dtype=torch.bfloat16 if bf16 else torch.float32, device=rays_o.device)
+    # bf16 rows are written in the library's tiled layout (padded to whole 128-row tiles); f32 rows are row-major
+    rows = _lib.lib().esr_mlp_act_rows(s.m3) if bf16 else s.m3
+    x = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16 if bf16 else torch.float32, device=rays_o.device)
     check(_lib.lib().esr_encode_fwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(viewdirs), ptr(sdf_grid),
                                     ptr(off_grid), ptr(emo_grid), 6, ptr(s.h_ray), ptr(s.h_step), ptr(s.h_sdf), s.m3,
                                     ptr(x), int(bf16), stream_ptr()))
@@ -290,7 +292,7 @@ class Tonemap(torch.autograd.Function):
         L = _lib.lib()
         m = lin.shape[0]
         lin = lin.contiguous()
-        xt = torch.empty(m, TFEAT_DIM, dtype=torch.bfloat16, device=lin.device)
+        xt = torch.empty(L.esr_mlp_act_rows(m), TFEAT_DIM, dtype=torch.bfloat16, device=lin.device)  # tiled layout
         lin_copy = torch.empty_like(lin)
         check(L.esr_tonemap_encode_fwd(ptr(lin), None, None, None, m, ptr(lin_copy), ptr(xt), 1, stream_ptr()))
         img = mlp_pack(TONEMAP_DESC, flat_tone)

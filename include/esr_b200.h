@@ -171,7 +171,10 @@ int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, const float *
  *   [off_color 6 | emo_color 6 | sdf 1 | feat 24 | normal 12 | xyz 3 | sin 15 | cos 15 |
  *    view 3 | sin view 3 | cos view 3 | zero pad 5]
  * Colour grids are CHANNELS-LAST in memory ([X][Y][Z][C], torch.channels_last_3d of [1,C,X,Y,Z]).
- * out_is_bf16: 1 -> __nv_bfloat16 rows, 0 -> float rows.
+ * out_is_bf16: 0 -> float rows, row-major [m3][96];
+ *              1 -> __nv_bfloat16 rows in the library's TILED MLP-input layout (per 128-row tile:
+ *                   [12 feature chunks][128 rows][8]); `feat` must hold esr_mlp_act_rows(m3) rows.  The same holds
+ *                   for esr_tonemap_encode_fwd's tfeat (48 columns = 6 chunks).
  */
 #define ESR_FEAT_DIM 96
 #define ESR_FEAT_GRAD_DIM 56 /* columns [0,49) carry gradient; padded to 56 */
@@ -242,7 +245,8 @@ int64_t esr_mlp_act_rows(int64_t m_total);
  */
 int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image, esr_stream_t stream);
 /*
- * Forward over rows [row_begin,row_end) of x (bf16 [*,k0]).  y: f32 [*,n_out] (activated).
+ * Forward over rows [row_begin,row_end) of x (bf16, k0 columns, TILED layout as written by esr_encode_fwd /
+ * esr_tonemap_encode_fwd with out_is_bf16 = 1).  y: f32 [*,n_out] (activated).
  * hidden (nullable): bf16 [n_hidden][esr_mlp_act_rows(m_total)][width] post-ReLU activations saved for backward.
  */
 int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t row_begin,

@@ -22,6 +22,15 @@ def _untile(buf):
     return buf.reshape(rows // 128, 24, 128, 8).permute(0, 2, 1, 3).reshape(rows, 192)
 
 
+def _tile(x):
+    """row-major [m, K] -> the library's tiled input layout, rows padded to whole 128-row tiles"""
+    m, k = x.shape
+    rows = (m + 127) // 128 * 128
+    xp = torch.zeros(rows, k, dtype=x.dtype, device=x.device)
+    xp[:m] = x
+    return xp.reshape(rows // 128, 128, k // 8, 8).permute(0, 2, 1, 3).contiguous().reshape(rows, k)
+
+
 def _flat_and_layers(desc, seed):
     g = torch.Generator().manual_seed(seed)
     k0, w, nh = desc["k0"], desc["width"], desc["n_hidden"]
@@ -78,7 +87,7 @@ def test_mlp_fwd_bwd_matches_bf16_contract(which, m, rb, re):
     y_ref, hid_ref, dx_ref, ws = _reference(desc, layers, x, d_y, rb, re)
 
     image = fused.mlp_pack(desc, flat.to(DEV))
-    xd = x.to(DEV).to(torch.bfloat16).contiguous()
+    xd = _tile(x.to(DEV).to(torch.bfloat16))
     y, hidden = fused._mlp_forward(desc, image, xd, rb, re, m, True)
     torch.cuda.synchronize()
     assert torch.allclose(y[rb:re].cpu(), y_ref, rtol=2e-3, atol=2e-3), (y[rb:re].cpu() - y_ref).abs().max()
@@ -120,7 +129,7 @@ def test_mlp_accumulate_and_second_net_rows():
     x = _bf(torch.randn(m, 96, generator=g))
     d_y = torch.randn(m, 3, generator=g)
     image = fused.mlp_pack(desc, flat.to(DEV))
-    xd = x.to(DEV).to(torch.bfloat16).contiguous()
+    xd = _tile(x.to(DEV).to(torch.bfloat16))
     y, hidden = fused._mlp_forward(desc, image, xd, 0, m, m, True)
     d_x = torch.zeros(m, 56, device=DEV)
     fused._mlp_backward(desc, image, xd, y, d_y.to(DEV), m_on, m, m, hidden, d_x, 56, 1)
