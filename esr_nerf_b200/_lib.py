@@ -17,7 +17,7 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
-SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_mma.cu", "mlp_tc.cu"]
+SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -134,6 +134,7 @@ PROTOTYPES = {
     "esr_mlp_param_count": (I64, [DESC_P]),
     "esr_mlp_image_bytes": (I64, [DESC_P]),
     "esr_mlp_act_rows": (I64, [I64]),
+    "esr_mlp_hidden_bytes": (I64, [DESC_P, I64]),
     "esr_mlp_pack": (I32, [DESC_P, P, P, P]),
     "esr_mlp_fwd": (I32, [DESC_P, P, P, I64, I64, I64, P, P, P]),
     "esr_mlp_bwd": (I32, [DESC_P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, I32, P, P]),

@@ -1,5 +1,5 @@
-// mlp_layout.cuh — parameter layouts shared by the MLP kernels (mlp_mma.cu: mma.sync path and weight-gradient
-// GEMMs; mlp_tc.cu: tcgen05 forward / data-gradient chains).
+// mlp_layout.cuh — parameter and activation layouts shared by the MLP kernels (mlp_tc.cu: tcgen05 forward /
+// data-gradient chains and weight-gradient GEMMs; mlp_api.cu: C-ABI entry points).
 #pragma once
 #include "common.cuh"
 
@@ -37,6 +37,19 @@ ESR_HD int64_t tiled_chunk_index(int64_t row, int c, int chunks_per_row) {
   return ((row >> 7) * chunks_per_row + c) * 128 + (row & 127);
 }
 ESR_HD int64_t act_chunk_index(int64_t row, int c) { return tiled_chunk_index(row, c, ACT_W / 8); }
+// `hidden` buffer = [n_hidden][rows_padded][192] bf16 activations, then the ReLU masks the data-gradient chain reads
+// instead of the activations: per layer [tile][2 column halves][128 rows] x uint4 (3 words used: bit j of word w =
+// [H[row][96 half + 32 w + j] > 0]).
+ESR_HD int64_t act_hidden_bytes(int n_hidden, int64_t m_total) {
+  return (int64_t)n_hidden * act_rows_padded(m_total) * (ACT_W * 2 + 32);
+}
+ESR_HD int64_t act_mask_base_bytes(int n_hidden, int64_t m_total) {
+  return (int64_t)n_hidden * act_rows_padded(m_total) * ACT_W * 2;
+}
+// index, in 16-byte units from the mask base, of the mask words of (layer l, row, column half)
+ESR_HD int64_t act_mask_index(int l, int64_t rows_padded, int64_t row, int half) {
+  return (int64_t)l * rows_padded * 2 + ((row >> 7) * 2 + half) * 128 + (row & 127);
+}
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 path (mlp_tc.cu)

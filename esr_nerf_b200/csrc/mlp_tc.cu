@@ -323,23 +323,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // bias + ReLU -> bf16 -> TMEM A operand (+ global copy, tiled layout, for the backward pass)
         const float *b = sbias + l * TC_W;
         uint4 *hl = hidden ? reinterpret_cast<uint4 *>(hidden + (int64_t)l * act_rows_padded(m_total) * TC_W) : nullptr;
+        uint32_t mask[3];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           const int col0 = 96 * et.half + 32 * cc;
           uint32_t r[32], p[16];
           tmem_ld32(tmem + et.lane_base + TM_D + col0, r);
           tmem_ld_wait();
+          uint32_t mk = 0;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
-            p[j] = pack2(fmaxf(__uint_as_float(r[2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(r[2 * j + 1]) + bb.y, 0.f));
+            const float z0 = __uint_as_float(r[2 * j]) + bb.x, z1 = __uint_as_float(r[2 * j + 1]) + bb.y;
+            p[j] = pack2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+            // mask of the STORED activation (bf16 rounding can only flush z > 0 to +0 for subnormals; compare the
+            // rounded word so forward and backward agree): predicated OR of an immediate
+            if (p[j] & 0x0000ffffu) mk |= 1u << (2 * j);
+            if (p[j] & 0xffff0000u) mk |= 1u << (2 * j + 1);
           }
+          mask[cc] = mk;
           tmem_st16(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (hl && valid) {  // the warp's 32 rows write 512 contiguous bytes per chunk
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               hl[act_chunk_index(row, col0 / 8 + q)] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
           }
+        }
+        if (hidden && valid) {
+          uint4 *mb = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
+          mb[act_mask_index(l, act_rows_padded(m_total), row, et.half)] = make_uint4(mask[0], mask[1], mask[2], 0u);
         }
         tmem_st_wait();
       }
@@ -467,14 +479,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll 1
     for (int l = NH - 1; l >= 0; --l) {
       if (is_epi) {
-        // ReLU masks: this thread's 12 chunks of H_l, requested BEFORE waiting for the MMA so that the global
-        // latency overlaps the tensor work of this layer
-        const uint4 *hl = reinterpret_cast<const uint4 *>(hidden + (int64_t)l * layer_stride);
+        // ReLU mask bits of this thread's 96 columns of H_l (written by the forward chain), requested BEFORE waiting
+        // for the MMA so that the global latency overlaps the tensor work of this layer
+        const uint4 *mb = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(hidden) +
+                                                           act_mask_base_bytes(NH, m_total));
         uint4 *zl = reinterpret_cast<uint4 *>(d_z + (int64_t)l * layer_stride);
-        uint4 h[12];
-#pragma unroll
-        for (int q = 0; q < 12; ++q)
-          h[q] = valid ? __ldg(hl + act_chunk_index(row, 12 * et.half + q)) : make_uint4(0, 0, 0, 0);
+        const uint4 mk4 = valid ? __ldg(mb + act_mask_index(l, act_rows_padded(m_total), row, et.half)) : make_uint4(0, 0, 0, 0);
+        const uint32_t mask[3] = {mk4.x, mk4.y, mk4.z};
         mbar_wait(bar, phase);
         tc_fence_after();
         // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy (tiled) for the weight-gradient GEMM
@@ -484,15 +495,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           uint32_t r[32], p[16];
           tmem_ld32(tmem + et.lane_base + TM_D + col0, r);
           tmem_ld_wait();
+          const uint32_t mk = mask[cc];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 hv = h[4 * cc + q];
-            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              p[4 * q + j] = pack2(lo16(hw[j]) > 0.f ? __uint_as_float(r[8 * q + 2 * j]) : 0.f,
-                                   hi16(hw[j]) > 0.f ? __uint_as_float(r[8 * q + 2 * j + 1]) : 0.f);
-          }
+          for (int j = 0; j < 16; ++j)
+            p[j] = pack2((mk >> (2 * j)) & 1u ? __uint_as_float(r[2 * j]) : 0.f,
+                         (mk >> (2 * j + 1)) & 1u ? __uint_as_float(r[2 * j + 1]) : 0.f);
           tmem_st16(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (valid) {
 #pragma unroll

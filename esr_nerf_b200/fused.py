@@ -222,8 +222,9 @@ def _mlp_forward(desc, image, x, rb, re, m_total, train):
     d = _desc(desc)
     dev = x.device
     y = torch.zeros(m_total, desc["n_out"], dtype=torch.float32, device=dev)
-    hidden = (torch.empty(desc["n_hidden"], L.esr_mlp_act_rows(m_total), desc["width"], dtype=torch.bfloat16,
-                          device=dev) if train else None)   # tiled layout private to the library
+    # activations (tiled bf16) + ReLU bit masks, layout private to the library
+    hidden = (torch.empty(L.esr_mlp_hidden_bytes(ctypes.byref(d), m_total), dtype=torch.uint8, device=dev)
+              if train else None)
     check(L.esr_mlp_fwd(ctypes.byref(d), ptr(image), ptr(x), rb, re, m_total, ptr(y), ptr(hidden), stream_ptr()))
     return y, hidden
 

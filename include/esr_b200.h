@@ -238,6 +238,9 @@ int64_t esr_mlp_image_bytes(const esr_mlp_desc_t *d);
  * (per 128-row tile: [width/8 feature chunks][128 rows][8]); callers only allocate and pass them through.
  */
 int64_t esr_mlp_act_rows(int64_t m_total);
+/* bytes of the `hidden` buffer of esr_mlp_fwd / esr_mlp_bwd: the bf16 activations above followed by the ReLU bit
+ * masks (32 B per row per layer) that the data-gradient chain reads instead of the activations */
+int64_t esr_mlp_hidden_bytes(const esr_mlp_desc_t *d, int64_t m_total);
 /*
  * flat f32 master copy layout: for each layer l: W_l [out_l][in_l_padded] then b_l [out_l]
  * (output layer padded to 8 rows).  esr_mlp_pack converts it to the bf16 kernel image: every weight matrix and
@@ -247,7 +250,7 @@ int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image,
 /*
  * Forward over rows [row_begin,row_end) of x (bf16, k0 columns, TILED layout as written by esr_encode_fwd /
  * esr_tonemap_encode_fwd with out_is_bf16 = 1).  y: f32 [*,n_out] (activated).
- * hidden (nullable): bf16 [n_hidden][esr_mlp_act_rows(m_total)][width] post-ReLU activations saved for backward.
+ * hidden (nullable): esr_mlp_hidden_bytes(d, m_total) bytes; post-ReLU activations + ReLU masks saved for backward.
  */
 int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t row_begin,
                 int64_t row_end, int64_t m_total, float *y, void *hidden, esr_stream_t stream);
