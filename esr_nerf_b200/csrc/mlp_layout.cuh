@@ -38,17 +38,17 @@ ESR_HD int64_t tiled_chunk_index(int64_t row, int c, int chunks_per_row) {
 }
 ESR_HD int64_t act_chunk_index(int64_t row, int c) { return tiled_chunk_index(row, c, ACT_W / 8); }
 // `hidden` buffer = [n_hidden][rows_padded][192] bf16 activations, then the ReLU masks the data-gradient chain reads
-// instead of the activations: per layer [tile][2 column halves][128 rows] x uint4 (3 words used: bit j of word w =
-// [H[row][96 half + 32 w + j] > 0]).
+// instead of the activations: per layer [tile][4 column groups][128 rows] x uint2 (48 bits used: bit j =
+// [H[row][48 grp + j] > 0]).
 ESR_HD int64_t act_hidden_bytes(int n_hidden, int64_t m_total) {
   return (int64_t)n_hidden * act_rows_padded(m_total) * (ACT_W * 2 + 32);
 }
 ESR_HD int64_t act_mask_base_bytes(int n_hidden, int64_t m_total) {
   return (int64_t)n_hidden * act_rows_padded(m_total) * ACT_W * 2;
 }
-// index, in 16-byte units from the mask base, of the mask words of (layer l, row, column half)
-ESR_HD int64_t act_mask_index(int l, int64_t rows_padded, int64_t row, int half) {
-  return (int64_t)l * rows_padded * 2 + ((row >> 7) * 2 + half) * 128 + (row & 127);
+// index, in 8-byte units from the mask base, of the mask words of (layer l, row, column group)
+ESR_HD int64_t act_mask_index(int l, int64_t rows_padded, int64_t row, int grp) {
+  return (int64_t)l * rows_padded * 4 + ((row >> 7) * 4 + grp) * 128 + (row & 127);
 }
 
 // ------------------------------------------------------------------------------------------------

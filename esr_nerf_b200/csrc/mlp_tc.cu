@@ -24,7 +24,8 @@ namespace {
 
 constexpr int TC_W = 192;         // hidden width
 constexpr int TC_TM = 128;        // rows per tile
-constexpr int TC_EPI_WARPS = 8;   // warps 0-7: epilogue (TMEM lane quadrant w % 4, column half w / 4)
+constexpr int TC_EPI_WARPS = 16;  // epilogue warps: TMEM lane quadrant w % 4, column group w / 4 (48 columns each)
+constexpr int TC_GCOLS = TC_W / (TC_EPI_WARPS / 4);   // 48
 constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1);   // + warp 8: MMA issuer / TMEM owner
 constexpr int TC_NOUT_PAD = 16;   // output layer rows padded to the minimum UMMA N for M = 128
 
@@ -123,6 +124,11 @@ ESR_D void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+ESR_D void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 ESR_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -245,13 +251,14 @@ struct FwdSm {
   static constexpr int bytes = bar + 16;
 };
 
-// Epilogue thread geometry (8 warps): TMEM lane quadrant = warp % 4 (hardware rule for tcgen05.ld/st), column
-// half = warp / 4: thread (q, lane, half) owns row 32q + lane and feature columns [96 half, 96 half + 96).
+// Epilogue thread geometry (16 warps): TMEM lane quadrant = warp % 4 (hardware rule for tcgen05.ld/st), column
+// group = warp / 4: thread (q, lane, grp) owns row 32q + lane and feature columns [48 grp, 48 grp + 48).
+// Four warps per scheduler hide the TMEM / global latencies of one another.
 struct EpiThread {
-  int row_in_tile, half;
+  int row_in_tile, grp;
   uint32_t lane_base;
   __device__ EpiThread(unsigned warp, unsigned lane)
-      : row_in_tile(32 * (warp & 3) + lane), half(warp >> 2), lane_base((32u * (warp & 3)) << 16) {}
+      : row_in_tile(32 * (warp & 3) + lane), grp(warp >> 2), lane_base((32u * (warp & 3)) << 16) {}
 };
 
 template <int K0, int NH>
@@ -285,12 +292,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int t = et.row_in_tile;
   uint32_t phase = 0;
 
-  auto load_x = [&](int64_t tile) {  // 2 epilogue threads per row: 16-byte chunks c = half, half + 2, ...
+  auto load_x = [&](int64_t tile) {  // 4 epilogue threads per row: 16-byte chunks c = grp, grp + 4, ...
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool ok = row < row_end;
     const uint4 *x4 = reinterpret_cast<const uint4 *>(x);  // tiled layout: a warp reads 512 contiguous bytes per chunk
 #pragma unroll
-    for (int c = et.half; c < K0 / 8; c += 2)
+    for (int c = et.grp; c < K0 / 8; c += 4)
       cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, x4 + tiled_chunk_index(ok ? row : row_begin, c, K0 / 8), ok);
   };
 
@@ -323,35 +330,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // bias + ReLU -> bf16 -> TMEM A operand (+ global copy, tiled layout, for the backward pass)
         const float *b = sbias + l * TC_W;
         uint4 *hl = hidden ? reinterpret_cast<uint4 *>(hidden + (int64_t)l * act_rows_padded(m_total) * TC_W) : nullptr;
-        uint32_t mask[3];
+        uint32_t r[3][16];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + TM_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+        tmem_ld_wait();
+        uint32_t mask[2] = {0u, 0u};
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-          const int col0 = 96 * et.half + 32 * cc;
-          uint32_t r[32], p[16];
-          tmem_ld32(tmem + et.lane_base + TM_D + col0, r);
-          tmem_ld_wait();
-          uint32_t mk = 0;
+          const int col0 = TC_GCOLS * et.grp + 16 * cc;
+          uint32_t p[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
-            const float z0 = __uint_as_float(r[2 * j]) + bb.x, z1 = __uint_as_float(r[2 * j + 1]) + bb.y;
+            const float z0 = __uint_as_float(r[cc][2 * j]) + bb.x, z1 = __uint_as_float(r[cc][2 * j + 1]) + bb.y;
             p[j] = pack2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
-            // mask of the STORED activation (bf16 rounding can only flush z > 0 to +0 for subnormals; compare the
-            // rounded word so forward and backward agree): predicated OR of an immediate
-            if (p[j] & 0x0000ffffu) mk |= 1u << (2 * j);
-            if (p[j] & 0xffff0000u) mk |= 1u << (2 * j + 1);
+            // mask of the STORED activation (compare the rounded word so forward and backward agree)
+            if (p[j] & 0x0000ffffu) mask[cc >> 1] |= 1u << (16 * (cc & 1) + 2 * j);
+            if (p[j] & 0xffff0000u) mask[cc >> 1] |= 1u << (16 * (cc & 1) + 2 * j + 1);
           }
-          mask[cc] = mk;
-          tmem_st16(tmem + et.lane_base + TM_A + col0 / 2, p);
+          tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (hl && valid) {  // the warp's 32 rows write 512 contiguous bytes per chunk
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              hl[act_chunk_index(row, col0 / 8 + q)] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+            hl[act_chunk_index(row, col0 / 8)] = make_uint4(p[0], p[1], p[2], p[3]);
+            hl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(p[4], p[5], p[6], p[7]);
           }
         }
         if (hidden && valid) {
-          uint4 *mb = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
-          mb[act_mask_index(l, act_rows_padded(m_total), row, et.half)] = make_uint4(mask[0], mask[1], mask[2], 0u);
+          uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
+          mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
         }
         tmem_st_wait();
       }
@@ -376,11 +381,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       phase ^= 1;
     }
-    // ---- output layer epilogue (column half 0 threads) ----
+    // ---- output layer epilogue (column group 0 threads) ----
     if (is_epi) {
       mbar_wait(bar, phase);
       tc_fence_after();
-      if (et.half == 0) {
+      if (et.grp == 0) {
         uint32_t r[16];
         tmem_ld16(tmem + et.lane_base + TM_S, r);
         tmem_ld_wait();
@@ -445,20 +450,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const EpiThread et(warp, lane);
   const int t = et.row_in_tile;
   const int64_t layer_stride = act_rows_padded(m_total) * TC_W;
+  const uint2 *mask_base = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(hidden) +
+                                                             act_mask_base_bytes(NH, m_total));
   uint32_t phase = 0;
+
+  // Per-tile global inputs (output cotangent, ReLU masks of every layer) are requested one tile ahead so their
+  // latency hides behind the current tile's chain.
+  float pf_y[3], pf_dy[3];
+  uint2 pf_mask[NH];
+  auto prefetch = [&](int64_t tile) {
+    const int64_t row = row_begin + tile * TC_TM + t;
+    const bool ok = is_epi && tile < n_tiles && row < row_end;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const bool okc = ok && et.grp == 0 && c < n_out;
+      pf_y[c] = okc ? __ldg(y + row * n_out + c) : 0.f;
+      pf_dy[c] = okc ? __ldg(d_y + row * n_out + c) : 0.f;
+    }
+#pragma unroll
+    for (int l = 0; l < NH; ++l)
+      pf_mask[l] = ok ? __ldg(mask_base + act_mask_index(l, act_rows_padded(m_total), row, et.grp)) : make_uint2(0, 0);
+  };
+  prefetch(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool valid = is_epi && row < row_end;
-    // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column half 0 threads) ----
-    if (is_epi && et.half == 0) {
+    uint2 cur_mask[NH];
+#pragma unroll
+    for (int l = 0; l < NH; ++l) cur_mask[l] = pf_mask[l];
+    // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column group 0 threads) ----
+    if (is_epi && et.grp == 0) {
       float dz[3] = {0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           if (c < n_out) {
-            const float yy = y[row * n_out + c];
-            dz[c] = d_y[row * n_out + c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
+            const float yy = pf_y[c];
+            dz[c] = pf_dy[c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
           }
         if (d_z_out) {
           *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], 0.f);
@@ -468,6 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
       fence_proxy_async();
     }
+    prefetch(tile + gridDim.x);
     tc_fence_before();
     __syncthreads();
     if (is_issuer && lane == 0) {
@@ -479,32 +509,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll 1
     for (int l = NH - 1; l >= 0; --l) {
       if (is_epi) {
-        // ReLU mask bits of this thread's 96 columns of H_l (written by the forward chain), requested BEFORE waiting
-        // for the MMA so that the global latency overlaps the tensor work of this layer
-        const uint4 *mb = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(hidden) +
-                                                           act_mask_base_bytes(NH, m_total));
+        // ReLU mask bits of this thread's 48 columns of H_l (written by the forward chain, prefetched above)
         uint4 *zl = reinterpret_cast<uint4 *>(d_z + (int64_t)l * layer_stride);
-        const uint4 mk4 = valid ? __ldg(mb + act_mask_index(l, act_rows_padded(m_total), row, et.half)) : make_uint4(0, 0, 0, 0);
-        const uint32_t mask[3] = {mk4.x, mk4.y, mk4.z};
+        uint2 mk2 = cur_mask[0];
+#pragma unroll
+        for (int q = 1; q < NH; ++q)
+          if (q == l) mk2 = cur_mask[q];
+        const uint32_t mask[2] = {mk2.x, mk2.y};
         mbar_wait(bar, phase);
         tc_fence_after();
         // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy (tiled) for the weight-gradient GEMM
+        uint32_t r[3][16];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + TM_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+        tmem_ld_wait();
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-          const int col0 = 96 * et.half + 32 * cc;
-          uint32_t r[32], p[16];
-          tmem_ld32(tmem + et.lane_base + TM_D + col0, r);
-          tmem_ld_wait();
-          const uint32_t mk = mask[cc];
+          const int col0 = TC_GCOLS * et.grp + 16 * cc;
+          const uint32_t mk = mask[cc >> 1] >> (16 * (cc & 1));
+          uint32_t p[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            p[j] = pack2((mk >> (2 * j)) & 1u ? __uint_as_float(r[2 * j]) : 0.f,
-                         (mk >> (2 * j + 1)) & 1u ? __uint_as_float(r[2 * j + 1]) : 0.f);
-          tmem_st16(tmem + et.lane_base + TM_A + col0 / 2, p);
+          for (int j = 0; j < 8; ++j)
+            p[j] = pack2((mk >> (2 * j)) & 1u ? __uint_as_float(r[cc][2 * j]) : 0.f,
+                         (mk >> (2 * j + 1)) & 1u ? __uint_as_float(r[cc][2 * j + 1]) : 0.f);
+          tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              zl[act_chunk_index(row, col0 / 8 + q)] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+            zl[act_chunk_index(row, col0 / 8)] = make_uint4(p[0], p[1], p[2], p[3]);
+            zl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(p[4], p[5], p[6], p[7]);
           }
         }
         tmem_st_wait();
@@ -529,13 +560,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       phase ^= 1;
     }
-    // ---- d_x epilogue: 16-column groups split between the two column halves ----
+    // ---- d_x epilogue: one 16-column group per epilogue column group ----
     if (is_epi) {
       mbar_wait(bar, phase);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < DXN / 16; ++cc) {
-        if ((cc & 1) != et.half) continue;  // warp-uniform
+        if (cc != et.grp) continue;  // warp-uniform
         uint32_t r[16];
         tmem_ld16(tmem + et.lane_base + TM_S + cc * 16, r);
         tmem_ld_wait();

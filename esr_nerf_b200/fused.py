@@ -275,11 +275,15 @@ class Shade(torch.autograd.Function):
         s: Streams = ctx.streams
         hid_off, hid_emo = ctx.hidden
         (ob, oe), (eb, ee) = ctx.rows
-        d_x = torch.zeros(s.m3, FEAT_GRAD_DIM, dtype=torch.float32, device=x.device)
+        # with the emission-on rays first the two nets back-propagate through disjoint row ranges that together
+        # cover every row: each d_x row is written exactly once (no zero-fill, no read-modify-write)
+        disjoint = (eb, ee, oe) == (0, ob, s.m3)
+        d_x = (torch.empty if disjoint else torch.zeros)(s.m3, FEAT_GRAD_DIM, dtype=torch.float32, device=x.device)
+        acc = 0 if disjoint else 1
         g_off_flat, scratch = _mlp_backward(RADIANCE_DESC, img_off, x, lin_off, d_off.contiguous(), ob, oe, s.m3,
-                                            hid_off, d_x, FEAT_GRAD_DIM, 1)
+                                            hid_off, d_x, FEAT_GRAD_DIM, acc)
         g_emo_flat, _ = _mlp_backward(RADIANCE_DESC, img_emo, x, lin_emo, d_emo.contiguous(), eb, ee, s.m3, hid_emo,
-                                      d_x, FEAT_GRAD_DIM, 1, scratch)
+                                      d_x, FEAT_GRAD_DIM, acc, scratch)
         ctx.hidden = None
         g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x)
         return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None
