@@ -43,6 +43,11 @@ ESR_HD int64_t act_chunk_index(int64_t row, int c) { return tiled_chunk_index(ro
 ESR_HD int64_t act_hidden_bytes(int n_hidden, int64_t m_total) {
   return (int64_t)n_hidden * act_rows_padded(m_total) * (ACT_W * 2 + 32);
 }
+// `d_z` scratch = [n_hidden][rows_padded][192] bf16 hidden-layer cotangents, then the output-layer cotangent as
+// [rows_padded][16] bf16 (tiled with 2 chunks per row)
+ESR_HD int64_t act_dz_bytes(int n_hidden, int64_t m_total) {
+  return act_rows_padded(m_total) * ((int64_t)n_hidden * ACT_W * 2 + 32);
+}
 ESR_HD int64_t act_mask_base_bytes(int n_hidden, int64_t m_total) {
   return (int64_t)n_hidden * act_rows_padded(m_total) * ACT_W * 2;
 }

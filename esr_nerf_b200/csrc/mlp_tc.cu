@@ -494,7 +494,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
+      const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
+      if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
+        uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
+        zo[tiled_chunk_index(row, 0, 2)] = dz16;
+        zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
       fence_proxy_async();
     }
     prefetch(tile + gridDim.x);
@@ -621,23 +627,30 @@ ESR_D void red_add4(float *addr, float a, float b, float c, float d) {
 // instruction descriptor: D f32, A/B bf16, both MN-major, M = 128
 __host__ __device__ constexpr uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
 
-template <int KIN>
+// ACH = feature chunks (8 features each) of the A operand per row: 24 for a hidden layer's dZ_l (two accumulators,
+// see above), 2 for the output layer's dZ_out (16 columns, 3 real: one accumulator over a 128-feature A tile whose
+// chunks 2..15 are constant zero).
+template <int KIN, int ACH>
 struct WgSm {
-  static constexpr int a_bytes = TC_TM * TC_W * 2;                // dZ tile
+  static constexpr int a_chunks = ACH == 24 ? 24 : 16;
+  static constexpr int a_bytes = a_chunks * TC_TM * 16;
+  static constexpr int a_load = ACH * TC_TM * 16;
   static constexpr int b_chunks = KIN / 8 + 2;                    // In tile + 2 constant chunks ("ones" column)
   static constexpr int b_bytes = b_chunks * TC_TM * 16;
+  static constexpr int b_load = (KIN / 8) * TC_TM * 16;
   static constexpr int stage = a_bytes + b_bytes;
   static constexpr int bar = 2 * stage;                           // full[2], empty[2] (8 B each), tmem slot
   static constexpr int bytes = bar + 48;
   static constexpr int NB = KIN + 16;                             // UMMA N
 };
 
-template <int KIN>
+template <int KIN, int ACH>
 __global__ void __launch_bounds__(160, 1)
     k_mlp_wgrad_tc(const __nv_bfloat16 *__restrict__ dz, const __nv_bfloat16 *__restrict__ in, int64_t row_begin,
-                   int64_t row_end, float *__restrict__ gW /* [192][KIN] */, float *__restrict__ gb /* [192] */) {
+                   int64_t row_end, int out_rows, float *__restrict__ gW /* [out_rows][KIN] */,
+                   float *__restrict__ gb /* [out_rows] */) {
   extern __shared__ __align__(128) uint8_t smem[];
-  using S = WgSm<KIN>;
+  using S = WgSm<KIN, ACH>;
   const int64_t T0 = row_begin >> 7, T1 = (row_end + 127) >> 7;
   const int64_t per = (T1 - T0 + gridDim.x - 1) / gridDim.x;
   const int64_t ta = T0 + (int64_t)blockIdx.x * per, tb = min(T1, ta + per);
@@ -649,12 +662,17 @@ __global__ void __launch_bounds__(160, 1)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
   const bool driver = threadIdx.x == 128;  // producer + MMA issuer
 
-  // constant chunks of both stages: column KIN of the B tile is 1.0 for every row, columns KIN+1.. are zero
+  // constant chunks of both stages: column KIN of the B tile is 1.0 for every row, columns KIN+1.. are zero;
+  // A chunks that are never loaded are zero
   for (int i = threadIdx.x; i < 2 * 2 * TC_TM; i += blockDim.x) {
     const int st = i / (2 * TC_TM), r = i % (2 * TC_TM);  // r < 128: chunk KIN/8, else chunk KIN/8 + 1
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < TC_TM) v.x = 0x00003f80u;  // bf16 1.0 in element 0
     *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_bytes + (KIN / 8) * (TC_TM * 16) + r * 16) = v;
+  }
+  for (int i = threadIdx.x; i < 2 * (S::a_chunks - ACH) * TC_TM; i += blockDim.x) {
+    const int st = i / ((S::a_chunks - ACH) * TC_TM), r = i % ((S::a_chunks - ACH) * TC_TM);
+    *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_load + r * 16) = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
     mbar_init(bar_full, 1), mbar_init(bar_full + 8, 1), mbar_init(bar_empty, 1), mbar_init(bar_empty + 8, 1);
@@ -670,9 +688,9 @@ __global__ void __launch_bounds__(160, 1)
 
   auto load_tile = [&](int64_t tile, int st) {  // driver thread
     const uint32_t full = bar_full + 8 * st;
-    mbar_expect_tx(full, S::a_bytes + (KIN / 8) * TC_TM * 16);
-    bulk_g2s(sbase + st * S::stage, dz4 + tile * (TC_W / 8) * TC_TM, S::a_bytes, full);
-    bulk_g2s(sbase + st * S::stage + S::a_bytes, in4 + tile * (KIN / 8) * TC_TM, (KIN / 8) * TC_TM * 16, full);
+    mbar_expect_tx(full, S::a_load + S::b_load);
+    bulk_g2s(sbase + st * S::stage, dz4 + tile * ACH * TC_TM, S::a_load, full);
+    bulk_g2s(sbase + st * S::stage + S::a_bytes, in4 + tile * (KIN / 8) * TC_TM, S::b_load, full);
   };
 
   if (driver) load_tile(ta, 0);
@@ -685,7 +703,8 @@ __global__ void __launch_bounds__(160, 1)
       load_tile(tile + 1, st ^ 1);
     }
     const int64_t r0 = tile * TC_TM;
-    if (r0 < row_begin || r0 + TC_TM > row_end) {
+    const bool boundary = r0 < row_begin || r0 + TC_TM > row_end;
+    if (boundary) {
       // boundary tile: rows outside [row_begin, row_end) hold unrelated data -> zero them in both operands
       mbar_wait(bar_full + 8 * st, k_par);
       if (threadIdx.x < TC_TM) {
@@ -693,7 +712,7 @@ __global__ void __launch_bounds__(160, 1)
         if (row < row_begin || row >= row_end) {
           uint8_t *a = smem + st * S::stage + threadIdx.x * 16;
 #pragma unroll 4
-          for (int c = 0; c < TC_W / 8; ++c) *reinterpret_cast<uint4 *>(a + c * (TC_TM * 16)) = make_uint4(0, 0, 0, 0);
+          for (int c = 0; c < ACH; ++c) *reinterpret_cast<uint4 *>(a + c * (TC_TM * 16)) = make_uint4(0, 0, 0, 0);
 #pragma unroll 4
           for (int c = 0; c < KIN / 8 + 1; ++c)   // + the "ones" chunk: the row must not count in the bias either
             *reinterpret_cast<uint4 *>(a + S::a_bytes + c * (TC_TM * 16)) = make_uint4(0, 0, 0, 0);
@@ -710,13 +729,14 @@ __global__ void __launch_bounds__(160, 1)
       for (int s = 0; s < TC_TM / 16; ++s) {
         const uint64_t bd = make_desc(b0 + s * 256, 128, TC_TM * 16);
         mma_ss(tmem + 0, make_desc(a0 + s * 256, 128, TC_TM * 16), bd, make_idesc_mn(S::NB), (it | s) != 0);
-        mma_ss(tmem + 256, make_desc(a0 + 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16), bd, make_idesc_mn(S::NB),
-               (it | s) != 0);
+        if (ACH == 24)
+          mma_ss(tmem + 256, make_desc(a0 + 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16), bd, make_idesc_mn(S::NB),
+                 (it | s) != 0);
       }
       mma_commit(bar_empty + 8 * st);
     }
     __syncthreads();
-    if (r0 < row_begin || r0 + TC_TM > row_end) {
+    if (boundary) {
       // restore the "ones" chunk rows zeroed above once the MMAs that read them have retired (next use of the stage)
       mbar_wait(bar_empty + 8 * st, k_par);
       if (threadIdx.x < TC_TM)
@@ -733,22 +753,23 @@ __global__ void __launch_bounds__(160, 1)
     const uint32_t lane_base = (32u * warp) << 16;
     const int ml = 32 * warp + lane;  // accumulator row
 #pragma unroll 1
-    for (int acc = 0; acc < 2; ++acc) {
+    for (int acc = 0; acc < (ACH == 24 ? 2 : 1); ++acc) {
       const int o = acc == 0 ? ml : 64 + ml;
-      const bool use = acc == 0 || ml >= 64;  // accumulator 1: only features 128..191 are new
+      const bool use = (acc == 0 || ml >= 64) && o < out_rows;  // accumulator 1: only features 128..191 are new
 #pragma unroll 1
       for (int cc = 0; cc < S::NB / 16; ++cc) {
         uint32_t r[16];
         tmem_ld16(tmem + lane_base + acc * 256 + cc * 16, r);
         tmem_ld_wait();
-        if (!use) continue;
-        if (cc < KIN / 16) {
+        if (use) {
+          if (cc < KIN / 16) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            red_add4(gW + (int64_t)o * KIN + cc * 16 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                     __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-        } else {
-          red_add(gb + o, __uint_as_float(r[0]));
+            for (int q = 0; q < 4; ++q)
+              red_add4(gW + (int64_t)o * KIN + cc * 16 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          } else {
+            red_add(gb + o, __uint_as_float(r[0]));
+          }
         }
       }
     }
@@ -758,16 +779,16 @@ __global__ void __launch_bounds__(160, 1)
   if (warp == 4) tmem_dealloc(tmem, TM_COLS);
 }
 
-template <int KIN>
-static int launch_wgrad(const __nv_bfloat16 *dz, const __nv_bfloat16 *in, int64_t rb, int64_t re, float *gW, float *gb,
-                        cudaStream_t st) {
-  auto kern = k_mlp_wgrad_tc<KIN>;
-  constexpr int bytes = WgSm<KIN>::bytes;
+template <int KIN, int ACH>
+static int launch_wgrad(const __nv_bfloat16 *dz, const __nv_bfloat16 *in, int64_t rb, int64_t re, int out_rows, float *gW,
+                        float *gb, cudaStream_t st) {
+  auto kern = k_mlp_wgrad_tc<KIN, ACH>;
+  constexpr int bytes = WgSm<KIN, ACH>::bytes;
   ESR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   const int64_t tiles = ((re + 127) >> 7) - (rb >> 7);
   const unsigned grid = (unsigned)max((int64_t)1, min((int64_t)num_sms(), tiles));
-  ESR_STAGE("k_mlp_wgrad_tc", st);
-  kern<<<grid, 160, bytes, st>>>(dz, in, rb, re, gW, gb);
+  ESR_STAGE(ACH == 24 ? "k_mlp_wgrad_tc" : "k_mlp_wgrad_tc_out", st);
+  kern<<<grid, 160, bytes, st>>>(dz, in, rb, re, out_rows, gW, gb);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -861,18 +882,23 @@ int tc_wgrad(const esr_mlp_desc_t *d, const void *x, int64_t row_begin, int64_t 
              const void *hidden, const void *d_z, float *grad_flat, cudaStream_t st) {
   const MlpLayout L = layout_of(d);
   const int64_t ls = act_rows_padded(m_total) * TC_W;
+  const int NH = d->n_hidden;
   const __nv_bfloat16 *H = (const __nv_bfloat16 *)hidden, *Z = (const __nv_bfloat16 *)d_z;
   int e;
   if (d->k0 == 96)
-    e = launch_wgrad<96>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, grad_flat + L.flat_w(0), grad_flat + L.flat_b(0), st);
+    e = launch_wgrad<96, 24>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, TC_W, grad_flat + L.flat_w(0),
+                             grad_flat + L.flat_b(0), st);
   else
-    e = launch_wgrad<48>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, grad_flat + L.flat_w(0), grad_flat + L.flat_b(0), st);
+    e = launch_wgrad<48, 24>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, TC_W, grad_flat + L.flat_w(0),
+                             grad_flat + L.flat_b(0), st);
   if (e) return e;
-  for (int l = 1; l < d->n_hidden; ++l)
-    if ((e = launch_wgrad<192>(Z + l * ls, H + (l - 1) * ls, row_begin, row_end, grad_flat + L.flat_w(l),
-                               grad_flat + L.flat_b(l), st)))
+  for (int l = 1; l < NH; ++l)
+    if ((e = launch_wgrad<192, 24>(Z + l * ls, H + (l - 1) * ls, row_begin, row_end, TC_W, grad_flat + L.flat_w(l),
+                                   grad_flat + L.flat_b(l), st)))
       return e;
-  return ESR_OK;
+  // output layer: A = dZ_out (tiled, 2 chunks per row, stored after the hidden-layer dZ), In = H_{NH-1}
+  return launch_wgrad<192, 2>(Z + NH * ls, H + (NH - 1) * ls, row_begin, row_end, d->n_out, grad_flat + L.flat_w(NH),
+                              grad_flat + L.flat_b(NH), st);
 }
 
 }  // namespace esr

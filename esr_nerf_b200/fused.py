@@ -234,9 +234,8 @@ def _mlp_backward(desc, image, x, y, d_y, rb, re, m_total, hidden, d_x, dx_cols,
     d = _desc(desc)
     dev = x.device
     if scratch is None:
-        scratch = torch.empty(desc["n_hidden"], L.esr_mlp_act_rows(m_total), desc["width"], dtype=torch.bfloat16,
-                              device=dev)
-    d_z_out = torch.empty(m_total, 8, dtype=torch.float32, device=dev)
+        scratch = torch.empty(L.esr_mlp_dz_bytes(ctypes.byref(d), m_total), dtype=torch.uint8, device=dev)
+    d_z_out = None
     grad_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=dev)
     check(L.esr_mlp_bwd(ctypes.byref(d), ptr(image), ptr(x), ptr(y), ptr(d_y), rb, re, m_total, ptr(hidden),
                         ptr(scratch), ptr(d_z_out), ptr(d_x), dx_cols, int(accumulate), ptr(grad_flat), stream_ptr()))

@@ -241,6 +241,8 @@ int64_t esr_mlp_act_rows(int64_t m_total);
 /* bytes of the `hidden` buffer of esr_mlp_fwd / esr_mlp_bwd: the bf16 activations above followed by the ReLU bit
  * masks (32 B per row per layer) that the data-gradient chain reads instead of the activations */
 int64_t esr_mlp_hidden_bytes(const esr_mlp_desc_t *d, int64_t m_total);
+/* bytes of the `d_z` scratch of esr_mlp_bwd (bf16 cotangents of every layer's pre-activation, tiled) */
+int64_t esr_mlp_dz_bytes(const esr_mlp_desc_t *d, int64_t m_total);
 /*
  * flat f32 master copy layout: for each layer l: W_l [out_l][in_l_padded] then b_l [out_l]
  * (output layer padded to 8 rows).  esr_mlp_pack converts it to the bf16 kernel image: every weight matrix and
@@ -258,7 +260,8 @@ int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64
  * Backward over rows [row_begin,row_end): d_y is dL/dy (post-activation), y the saved outputs.
  *   d_x (nullable): f32 [*, dx_cols] gets dL/dx for the first dx_cols input columns
  *                   (accumulate != 0 adds to existing values).
- *   d_z: bf16 scratch [n_hidden][esr_mlp_act_rows(m_total)][width]; d_z_out: f32 [m_total][8] (output layer)
+ *   d_z: scratch of esr_mlp_dz_bytes(d, m_total) bytes; d_z_out (nullable): f32 [m_total][8], receives the output
+ *        layer's pre-activation cotangent (diagnostic)
  *   grad_flat: f32 flat gradient (same layout as flat_params), ACCUMULATED into (atomics).
  */
 int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const float *y,
