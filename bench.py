@@ -225,11 +225,14 @@ def algorithmic_work(stage, c):
         "k_sdf_scatter": ("hbm", 16 * M1 + 64 * M1),
         "k_composite_fwd": ("hbm", 28 * M3 + 24 * N),
         "k_composite_bwd": ("hbm", 32 * M3 + 28 * M3),
-        "k_mlp_fwd_radiance": ("tensor", FLOP_RADIANCE * (M3 + M3on)),
-        "k_mlp_dgrad_radiance": ("tensor", FLOP_RADIANCE * (M3 + M3on)),
-        "k_mlp_wgrad": ("tensor", (FLOP_RADIANCE - 2 * 192 * 3) * (M3 + M3on) + 2 * 33 * 192 * M3),
-        "k_mlp_fwd_tonemap": ("tensor", FLOP_TONEMAP * M3),
-        "k_mlp_dgrad_tonemap": ("tensor", FLOP_TONEMAP * M3),
+        # forward: off net on every shaded row, emo net on the emission-on rows; backward: each row through ONE net
+        # (emission-on rows reach the off net through a stop-gradient, voxurff.py:243-254)
+        "k_mlp_fwd_tc_radiance": ("tensor", FLOP_RADIANCE * (M3 + M3on)),
+        "k_mlp_dgrad_tc_radiance": ("tensor", FLOP_RADIANCE * M3),
+        "k_mlp_wgrad_tc": ("tensor", (FLOP_RADIANCE - 2 * 192 * 3) * M3 + 2 * 33 * 192 * M3),
+        "k_mlp_wgrad_tc_out": ("tensor", 2 * 192 * 3 * 2 * M3),
+        "k_mlp_fwd_tc_tonemap": ("tensor", FLOP_TONEMAP * M3),
+        "k_mlp_dgrad_tc_tonemap": ("tensor", FLOP_TONEMAP * M3),
     }
     _ = Mcand
     return t.get(stage)
@@ -238,6 +241,7 @@ def algorithmic_work(stage, c):
 def run_b200(a, rank, world, local_rank):
     from esr_nerf_b200 import _lib
     from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.dist import allreduce_gradients
     from esr_nerf_b200.voxurff import VoxurfF
 
     if not torch.cuda.is_available():
@@ -270,9 +274,7 @@ def run_b200(a, rank, world, local_rank):
         loss = loss_fn(out, b["rgbs"])
         loss.backward()
         if dist is not None:  # rays sharded, gradients summed once per step (north_star)
-            for p in params:
-                if p.grad is not None:
-                    dist.all_reduce(p.grad)
+            allreduce_gradients(params)
         return out, loss
 
     def sync_all():

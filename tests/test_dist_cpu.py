@@ -1,0 +1,73 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: ray sharding + one gradient all-reduce per step must
+reproduce the single-process gradient of a sum-over-rays loss."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from esr_nerf_b200 import dist as D
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    frozen = torch.nn.Parameter(torch.ones(3), requires_grad=False)
+    g = torch.Generator().manual_seed(1)
+    n = 101                                                   # not divisible by the world size
+    batch = {"rays_o": torch.randn(n, 3, generator=g), "rays_d": torch.randn(n, 3, generator=g),
+             "rgbs": torch.rand(n, 3, generator=g), "s_val": 20.0}
+    local = D.shard_batch(batch, rank, world)
+    assert local["s_val"] == 20.0
+    pred = net(torch.cat([local["rays_o"], local["rays_d"]], -1))
+    loss = ((pred - local["rgbs"]) ** 2).sum() / n           # sum over local rays / GLOBAL ray count
+    loss.backward()
+    nbytes = D.allreduce_gradients(list(net.parameters()) + [frozen])
+    assert nbytes == sum(p.numel() * 4 for p in net.parameters())
+    if rank == 0:
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+        ref.load_state_dict(net.state_dict())
+        rl = ((ref(torch.cat([batch["rays_o"], batch["rays_d"]], -1)) - batch["rgbs"]) ** 2).sum() / n
+        rl.backward()
+        err = max((a.grad - b.grad).abs().max().item() for a, b in zip(net.parameters(), ref.parameters()))
+        out.put(err)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_slices_cover_batch():
+    from esr_nerf_b200.dist import shard_slice
+
+    for n in (0, 1, 7, 64, 101):
+        for world in (1, 2, 3, 8):
+            idx = []
+            for r in range(world):
+                sl = shard_slice(n, r, world)
+                idx += list(range(n))[sl]
+            assert idx == list(range(n)), (n, world)
+    assert shard_slice(65536, 7, 8) == slice(57344, 65536)    # last global ray on the last rank
+
+
+def test_two_rank_gradient_allreduce_matches_single_process():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) < 1e-6
