@@ -127,6 +127,7 @@ PROTOTYPES = {
     "esr_alpha_scan_bwd": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, I64, P, P]),
     "esr_encode_fwd": (I32, [SCENE_P, P, P, P, P, P, P, I32, P, P, P, I64, P, I32, P]),
     "esr_encode_bwd": (I32, [SCENE_P, P, P, P, I32, P, P, I64, P, P, P, P, P]),
+    "esr_sdf_fd_gradient": (I32, [SCENE_P, P, P, P, P, P, I64, P, P]),
     "esr_tonemap_encode_fwd": (I32, [P, P, P, P, I64, P, P, I32, P]),
     "esr_tonemap_encode_bwd": (I32, [P, P, P, I64, P, P]),
     "esr_composite_fwd": (I32, [P, I64, P, P, P, P, P, P, P]),

@@ -374,6 +374,42 @@ __global__ void __launch_bounds__(ENC_THREADS)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// sample_sdf_grad (voxurff.py:670-676): finite-difference SDF gradient from the 6 axis taps at 1 voxel, in
+// world units and (x, y, z) order — the inference path turns it into the normal map (voxurff.py:421-430).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_sdf_fd_gradient(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                      const float *__restrict__ rays_d, const float *__restrict__ sdf_grid,
+                      const int32_t *__restrict__ h_ray, const int32_t *__restrict__ h_step, int64_t m3,
+                      float *__restrict__ grad_out) {
+  __shared__ float s_lines[N_LINES * ENC_THREADS];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m3) return;
+  const int r = h_ray[j];
+  const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
+  float px, py, pz;
+  ray_point(s, sc.stepdist, h_step[j], px, py, pz);
+  const SdfFrame fr = make_frame(sc, world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx),
+                                 world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy),
+                                 world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz));
+  load_lines(fr, sdf_grid, s_lines);
+  float g[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // a = 0: z, 1: y, 2: x
+    const TapRef lo = tap_ref(fr, a, -1.f), hi = tap_ref(fr, a, 1.f);
+    const float fl = __fmaf_rn(s_lines[(lo.slot + 1) * ENC_THREADS + threadIdx.x], lo.wh,
+                               __fmul_rn(s_lines[lo.slot * ENC_THREADS + threadIdx.x], lo.wl));
+    const float fh = __fmaf_rn(s_lines[(hi.slot + 1) * ENC_THREADS + threadIdx.x], hi.wh,
+                               __fmul_rn(s_lines[hi.slot * ENC_THREADS + threadIdx.x], hi.wl));
+    g[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fh, fl), __fsub_rn(hi.coord, lo.coord)), sc.voxel_size);
+  }
+  grad_out[3 * j] = g[2];
+  grad_out[3 * j + 1] = g[1];
+  grad_out[3 * j + 2] = g[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // tone-map encode (voxurff.py:243-256, 783-788)
 // ---------------------------------------------------------------------------------------------
@@ -535,6 +571,20 @@ extern "C" int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const 
   ESR_STAGE("k_encode_bwd", (cudaStream_t)stream);
   k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
                                                                 d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_sdf_fd_gradient(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                   const float *sdf_grid, const int32_t *h_ray, const int32_t *h_step, int64_t m3,
+                                   float *grad_out, esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(m3 >= 0);
+  if (m3 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && sdf_grid && h_ray && h_step && grad_out);
+  ESR_STAGE("k_sdf_fd_gradient", stream);
+  k_sdf_fd_gradient<<<cdiv(m3, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray,
+                                                                                     h_step, m3, grad_out);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

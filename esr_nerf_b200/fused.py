@@ -192,6 +192,40 @@ def encode_backward(sc: Scene, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s: 
     return g_sdf, g_off, g_emo
 
 
+def sdf_fd_gradient(sc: Scene, rays_o, rays_d, sdf_grid, s: Streams) -> torch.Tensor:
+    """sample_sdf_grad (voxurff.py:670-676) at the shaded samples -> [M3,3] world-space gradient (x, y, z)."""
+    g = torch.empty(s.m3, 3, dtype=torch.float32, device=rays_o.device)
+    check(_lib.lib().esr_sdf_fd_gradient(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(sdf_grid), ptr(s.h_ray),
+                                         ptr(s.h_step), s.m3, ptr(g), stream_ptr()))
+    return g
+
+
+def mlp_infer(desc, flat, x, rb, re, m_total):
+    """forward only (no activations saved)"""
+    y, _ = _mlp_forward(desc, mlp_pack(desc, flat), x, rb, re, m_total, False)
+    return y
+
+
+def tonemap_infer(lin, flat_tone):
+    """rgb = sigmoid(tonemapper(PE(lin))) without autograd state (voxurff.py:783-788)"""
+    L = _lib.lib()
+    m = lin.shape[0]
+    lin = lin.contiguous()
+    xt = torch.empty(L.esr_mlp_act_rows(m), TFEAT_DIM, dtype=torch.bfloat16, device=lin.device)
+    lin_copy = torch.empty_like(lin)
+    check(L.esr_tonemap_encode_fwd(ptr(lin), None, None, None, m, ptr(lin_copy), ptr(xt), 1, stream_ptr()))
+    return mlp_infer(TONEMAP_DESC, flat_tone, xt, 0, m, m)
+
+
+def composite_infer(h_w, a, b, s: Streams):
+    dev = h_w.device
+    a, b = a.contiguous(), b.contiguous()
+    out_a, out_b = _f32(s.n_rays, 3, dev=dev), _f32(s.n_rays, 3, dev=dev)
+    check(_lib.lib().esr_composite_fwd(ptr(s.ray_order), s.n_rays, ptr(s.off_shade), ptr(h_w), ptr(a), ptr(b),
+                                       ptr(out_a), ptr(out_b), stream_ptr()))
+    return out_a, out_b
+
+
 def _check_cl(grid: torch.Tensor, name: str):
     if not grid.is_contiguous(memory_format=torch.channels_last_3d):
         raise _lib.EsrError(f"{name} must be in channels_last_3d memory format (DenseGrid.ensure_layout)")

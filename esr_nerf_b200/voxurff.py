@@ -203,8 +203,65 @@ class VoxurfF(nn.Module):
             "lin/rgb": lin_marched,
         }
 
-    def forward_evaluate(self, **kwargs):
-        raise NotImplementedError("forward_evaluate lands with the inference row of SURVEY.md §8 (config 4)")
+    @torch.no_grad()
+    def forward_evaluate(self, **kwargs) -> Dict[str, torch.Tensor]:
+        """voxurff.py:280-461 — inference: the three radiances (off, emo, on = off + emo) in linear and tone-mapped
+        space, normal / depth / disparity maps; `em_modes` (0-dim) selects which one is aliased to srgb/rgb."""
+        rays_o = kwargs["rays_o"].contiguous().float()
+        rays_d = kwargs["rays_d"].contiguous().float()
+        viewdirs = kwargs["viewdirs"].contiguous().float()
+        em_modes = kwargs["em_modes"]
+        pos_rt = kwargs["pos_rt"].to(rays_o.device).float()
+        N = rays_o.shape[0]
+        dev = rays_o.device
+        with torch.cuda.device(dev):
+            sc = self._scene(float(self.s_val))
+            streams, _ = self._streams(sc, rays_o, rays_d, None)
+            h_w, last = fused.AlphaScan.apply(self.sdf.grid.detach(), sc, rays_o, rays_d, streams, None)
+            s = streams
+            if s.m3 <= 1 and s.m1 and int((s.s_alpha > self.fastcolor_thres).sum()) == 1:
+                # voxurff.py:306-331 (SURVEY.md Q7): exactly one sample passes the alpha filter -> .squeeze() makes
+                # 0-dim tensors and the reference returns empty images
+                z3 = torch.zeros_like(rays_o)
+                depth = z3[..., 0]
+                return {"etc/depth": depth, "etc/disp": 1 / (depth + self.far), "etc/normal": z3,
+                        "etc/white_bg": torch.ones_like(z3[..., :1]), "srgb/off_rgb": z3, "lin/off_rgb": z3,
+                        "srgb/on_rgb": z3, "lin/on_rgb": z3, "srgb/emo_rgb": z3, "lin/emo_rgb": z3, "srgb/rgb": z3,
+                        "lin/rgb": z3}
+            sdf_g, off_g, emo_g = self.sdf.grid.detach(), self.off_color.grid.detach(), self.emo_color.grid.detach()
+            if self.mlp_mode == "bf16":
+                x = fused.encode_features(sc, rays_o, rays_d, viewdirs, sdf_g, off_g, emo_g, s, bf16=True)
+                lin_off = fused.mlp_infer(fused.RADIANCE_DESC, self._flat("off").detach(), x, 0, s.m3, s.m3)
+                lin_emo = fused.mlp_infer(fused.RADIANCE_DESC, self._flat("emo").detach(), x, 0, s.m3, s.m3)
+                lin_on = lin_off + lin_emo
+                srgb = fused.tonemap_infer(torch.cat([lin_off, lin_on, lin_emo], 0), self._flat("tone").detach())
+            elif self.mlp_mode == "torch_fp32":
+                x = fused.encode_features(sc, rays_o, rays_d, viewdirs, sdf_g, off_g, emo_g, s, bf16=False)
+                lin_off = self.off_rgbnet(x[:, self._ref_cols("off", dev)])
+                lin_emo = self.emo_rgbnet(x[:, self._ref_cols("emo", dev)])
+                lin_on = lin_off + lin_emo
+                srgb = self.apply_tonemapper(torch.cat([lin_off, lin_on, lin_emo], 0))
+            else:
+                raise ValueError(f"unknown mlp_mode {self.mlp_mode!r}")
+            off_rgb, on_rgb, emo_rgb = srgb[: s.m3], srgb[s.m3: 2 * s.m3], srgb[2 * s.m3:]
+            grad = fused.sdf_fd_gradient(sc, rays_o, rays_d, sdf_g, s)
+            normal = (F.normalize(grad, dim=-1) @ pos_rt * self.normal_flipper.to(dev) + 1.0) / 2.0
+            dist = float(self.stepsize * self.voxel_size)
+            dvec = torch.zeros(s.m3, 3, device=dev)
+            dvec[:, 0] = s.h_step.float() * dist
+            off_m, lin_off_m = fused.composite_infer(h_w, off_rgb, lin_off, s)
+            on_m, lin_on_m = fused.composite_infer(h_w, on_rgb, lin_on, s)
+            emo_m, lin_emo_m = fused.composite_infer(h_w, emo_rgb, lin_emo, s)
+            normal_m, depth3 = fused.composite_infer(h_w, normal, dvec, s)
+        depth = depth3[:, 0].contiguous()
+        disp = 1 / (depth + last * self.far)
+        em = int(em_modes) if not torch.is_tensor(em_modes) else int(em_modes.item())
+        rgb_m, lin_rgb_m = (off_m, lin_off_m) if em == 0 else (on_m, lin_on_m)
+        if self.keep_streams:
+            self.last_streams = dict(streams=s, h_w=h_w)
+        return {"etc/depth": depth, "etc/disp": disp, "etc/normal": normal_m, "etc/white_bg": last.unsqueeze(-1),
+                "srgb/off_rgb": off_m, "lin/off_rgb": lin_off_m, "srgb/on_rgb": on_m, "lin/on_rgb": lin_on_m,
+                "srgb/emo_rgb": emo_m, "lin/emo_rgb": lin_emo_m, "srgb/rgb": rgb_m, "lin/rgb": lin_rgb_m}
 
     # ------------------------------------------------------------------------------------------
     _ref_cols_cache = None

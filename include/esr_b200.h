@@ -190,6 +190,15 @@ int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays
                    float *grad_emo_grid, esr_stream_t stream);
 
 /*
+ * sample_sdf_grad (voxurff.py:670-676) over the shaded stream: finite-difference SDF gradient from the six axis
+ * taps at 1 voxel, world units, (x, y, z) order.  grad_out: f32 [m3,3].  Used by the inference path for the normal
+ * map (voxurff.py:421-430).
+ */
+int esr_sdf_fd_gradient(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *sdf_grid,
+                        const int32_t *h_ray, const int32_t *h_step, int64_t m3, float *grad_out,
+                        esr_stream_t stream);
+
+/*
  * Stage G — combine radiances + tone-map encoding (voxurff.py:243-256, 783-788):
  *   lin = lin_off (+ lin_emo on emission-on rays); tfeat = [lin, sin(lin*2^f), cos(lin*2^f)] padded
  *   to 48 columns (bf16 or f32).

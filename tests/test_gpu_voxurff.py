@@ -221,3 +221,46 @@ def test_full_size_properties():
         assert C.rel_err(o1[k], o0[k]) < 1e-5, k                                 # ray order does not change rays
     for k in g0:
         assert C.rel_err(g1[k], g0[k]) < 2e-3, k                                 # atomics / split-K order only
+
+
+@pytest.mark.parametrize("mode", ["torch_fp32", "bf16"])
+@pytest.mark.parametrize("em", [0, 1])
+def test_forward_evaluate_vs_oracle_port(mode, em):
+    """Inference path (voxurff.py:280-461, BASELINE config 4 shape of outputs): all 12 maps vs the oracle port
+    (itself pinned against the reference's forward_evaluate in tests/test_oracle_cpu.py)."""
+    from oracle import voxurf_port as P
+
+    fx, weights = C.load_case("fine_sparse_s60_big")
+    n = 1500
+    rays = S.make_rays(n, 77)
+    pos_rt = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(3)))[0]
+    scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), True)
+    params, _ = C.oracle_params(scene, weights, requires_grad=False)
+    with torch.no_grad():
+        ref, inter = P.voxurff_forward_evaluate(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                                torch.tensor(em), pos_rt, float(fx["s_val"]))
+    m = C.build_product_model(fx, weights, DEV)
+    m.mlp_mode, m.keep_streams = mode, True
+    m.eval()
+    out = m(rays_o=rays["rays_o"].to(DEV), rays_d=rays["rays_d"].to(DEV), viewdirs=rays["viewdirs"].to(DEV),
+            em_modes=torch.tensor(em), pos_rt=pos_rt.to(DEV))
+    assert set(out) == set(ref)
+    st = m.last_streams["streams"]
+    assert torch.equal(st.h_ray.long().cpu(), inter["m3_ray"]) and torch.equal(st.h_step.long().cpu(), inter["m3_step"])
+    tol = TOL[mode]
+    for k in ref:
+        assert out[k].shape == ref[k].shape, k
+        assert C.rel_err(out[k], ref[k]) < tol, (k, C.rel_err(out[k], ref[k]))
+    m.train()
+    assert m.forward == m.forward_training
+
+
+def test_forward_evaluate_empty_image():
+    fx, weights = C.load_case("fine_sparse_s20")
+    m = C.build_product_model(fx, weights, DEV)
+    m.eval()
+    rays = S.make_rays(33, 5)
+    out = m(rays_o=rays["rays_o"].to(DEV), rays_d=(-rays["rays_d"]).to(DEV), viewdirs=(-rays["viewdirs"]).to(DEV),
+            em_modes=torch.tensor(1), pos_rt=torch.eye(3, device=DEV))
+    assert (out["srgb/rgb"] == 0).all() and (out["etc/white_bg"] == 1).all() and (out["etc/depth"] == 0).all()
+    assert torch.allclose(out["etc/disp"], torch.full((33,), 1 / S.FAR, device=DEV))
