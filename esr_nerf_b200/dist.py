@@ -39,3 +39,59 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int
         dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
         nbytes += p.grad.numel() * p.grad.element_size()
     return nbytes
+
+
+class GridGradCompactor:
+    """All-reduce only the grid-gradient voxels that CAN be non-zero.
+
+    The dense grid gradients are 64 MB (sdf) + 2 x 384 MB (colour) at 256^3 — a 0.83 GB all-reduce per step, most of
+    it zeros: samples only exist where MaskCache keeps them (module.py:104-114), trilinear taps reach one voxel
+    further and the multi-scale SDF taps two more (voxurff.py:678-721).  The set `nonempty_mask` dilated by
+    `dilate` voxels is static between grid rescales (voxurff.py:547-598), so each step gathers those voxels of the
+    three gradient volumes into one [K, 13] buffer, all-reduces it, and scatters it back.  `verify=True` checks that
+    nothing outside the set carried gradient (used by the tests)."""
+
+    def __init__(self, model, dilate: int = 5):
+        import torch.nn.functional as F
+
+        self.model = model
+        m = model.nonempty_mask.float()
+        k = 2 * dilate + 1
+        self.mask = F.max_pool3d(m, kernel_size=k, stride=1, padding=dilate) > 0
+        self.idx = torch.nonzero(self.mask.reshape(-1)).reshape(-1)
+        self.shape = tuple(model.sdf.grid.shape[2:])
+        self.grids = [model.sdf.grid, model.off_color.grid, model.emo_color.grid]
+
+    @property
+    def fraction(self) -> float:
+        return self.idx.numel() / self.mask.numel()
+
+    @staticmethod
+    def _rows(g: torch.Tensor) -> torch.Tensor:
+        """[1,C,X,Y,Z] gradient (contiguous for C == 1, channels_last_3d otherwise) -> [XYZ, C] view in memory order"""
+        v = g.permute(0, 2, 3, 4, 1)
+        assert v.is_contiguous(), "grid gradient is not in the parameter's memory layout"
+        return v.reshape(-1, g.shape[1])
+
+    def allreduce(self, group=None, verify: bool = False) -> int:
+        import torch.distributed as dist
+
+        rows = []
+        for p in self.grids:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            rows.append(self._rows(p.grad))
+        if verify:
+            for r in rows:
+                total, inside = r.abs().sum(), r[self.idx].abs().sum()
+                assert float(total - inside) == 0.0, "gradient outside the dilated occupancy set"
+        buf = torch.cat([r[self.idx] for r in rows], dim=1)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        c0 = 0
+        for r in rows:
+            r.index_copy_(0, self.idx, buf[:, c0:c0 + r.shape[1]])
+            c0 += r.shape[1]
+        nbytes = buf.numel() * buf.element_size()
+        grid_ids = {id(p) for p in self.grids}
+        others = [p for p in self.model.parameters() if id(p) not in grid_ids]
+        return nbytes + allreduce_gradients(others, group)
