@@ -353,6 +353,47 @@ class Tonemap(torch.autograd.Function):
         return d_lin, g_flat
 
 
+class CombineTonemap(torch.autograd.Function):
+    """(rgb, lin) from the two radiances: lin = lin_off (+ lin_emo on emission-on rays, which see the off net
+    through a stop-gradient, voxurff.py:243-254); rgb = sigmoid(tonemapper(PE(lin))) (voxurff.py:783-788).
+    One encode kernel + the tensor-core MLP; replaces torch.where / add / copies around `Tonemap`."""
+
+    @staticmethod
+    def forward(ctx, lin_off, lin_emo, flat_tone, h_ray, em_modes, ordered):
+        L = _lib.lib()
+        m = lin_off.shape[0]
+        lin_off, lin_emo = lin_off.contiguous(), lin_emo.contiguous()
+        xt = torch.empty(L.esr_mlp_act_rows(m), TFEAT_DIM, dtype=torch.bfloat16, device=lin_off.device)  # tiled layout
+        lin = torch.empty_like(lin_off)
+        check(L.esr_tonemap_encode_fwd(ptr(lin_off), ptr(lin_emo), ptr(h_ray), ptr(em_modes), m, ptr(lin), ptr(xt), 1,
+                                       stream_ptr()))
+        img = mlp_pack(TONEMAP_DESC, flat_tone)
+        rgb, hid = _mlp_forward(TONEMAP_DESC, img, xt, 0, m, m, any(ctx.needs_input_grad[:3]))
+        ctx.hidden, ctx.ordered = hid, ordered
+        ctx.save_for_backward(lin, xt, img, rgb, h_ray, em_modes)
+        return rgb, lin
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_rgb, d_lin_direct):
+        lin, xt, img, rgb, h_ray, em_modes = ctx.saved_tensors
+        m = lin.shape[0]
+        d_xt = torch.empty(m, TFEAT_GRAD_DIM, dtype=torch.float32, device=lin.device)
+        g_flat, _ = _mlp_backward(TONEMAP_DESC, img, xt, rgb, d_rgb.contiguous(), 0, m, m, ctx.hidden, d_xt,
+                                  TFEAT_GRAD_DIM, 0)
+        ctx.hidden = None
+        d_lin = torch.empty_like(lin)
+        check(_lib.lib().esr_tonemap_encode_bwd(ptr(lin), ptr(d_xt), ptr(d_lin_direct.contiguous()), m, ptr(d_lin),
+                                                stream_ptr()))
+        if ctx.ordered:
+            # emission-on rows are a prefix and each net back-propagates through its own row range only (Shade.backward):
+            # both can read the same cotangent
+            return d_lin, d_lin, g_flat, None, None, None
+        on = (em_modes[h_ray.long()] == 1)[:, None]
+        zero = torch.zeros_like(d_lin)
+        return torch.where(on, zero, d_lin), torch.where(on, d_lin, zero), g_flat, None, None, None
+
+
 class Composite(torch.autograd.Function):
     """(sum_ray w*a, sum_ray w*b): warp-per-ray segmented sums replacing segment_coo (voxurff.py:259-272)."""
 

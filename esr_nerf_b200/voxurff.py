@@ -164,7 +164,7 @@ class VoxurfF(nn.Module):
         rays_o = kwargs["rays_o"].contiguous().float()
         rays_d = kwargs["rays_d"].contiguous().float()
         viewdirs = kwargs["viewdirs"].contiguous().float()
-        em_modes = kwargs["em_modes"].contiguous()
+        em_modes = kwargs["em_modes"].long().contiguous()
         self.s_val = kwargs["s_val"]
         N = rays_o.shape[0]
         with torch.cuda.device(rays_o.device):
@@ -172,7 +172,6 @@ class VoxurfF(nn.Module):
             streams, n_on = self._streams(sc, rays_o, rays_d, em_modes)
             h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, streams, n_on)
             s = streams
-            on = (em_modes[s.h_ray.long()] == 1) if s.m3 else torch.zeros(0, dtype=torch.bool, device=rays_o.device)
             if self.mlp_mode == "bf16":
                 ordered = n_on is not None
                 off_rows = (s.m3_on, s.m3) if ordered else (0, s.m3)
@@ -181,12 +180,12 @@ class VoxurfF(nn.Module):
                                                      self._flat("off"), self._flat("emo"), sc, rays_o, rays_d,
                                                      viewdirs, s, off_rows, emo_rows)
                 # voxurff.py:243-254: on-rays emo + stop-gradient(off); off-rays off
-                lin = torch.where(on[:, None], lin_emo + lin_off.detach(), lin_off)
-                rgb = fused.Tonemap.apply(lin, self._flat("tone"))
+                rgb, lin = fused.CombineTonemap.apply(lin_off, lin_emo, self._flat("tone"), s.h_ray, em_modes, ordered)
             elif self.mlp_mode == "torch_fp32":
                 x = fused.Encode.apply(self.sdf.grid, self.off_color.grid, self.emo_color.grid, sc, rays_o, rays_d,
                                        viewdirs, s)
                 dev = x.device
+                on = (em_modes[s.h_ray.long()] == 1) if s.m3 else torch.zeros(0, dtype=torch.bool, device=dev)
                 lin_off = self.off_rgbnet(x[:, self._ref_cols("off", dev)])
                 lin_emo = self.emo_rgbnet(x[:, self._ref_cols("emo", dev)])
                 lin = torch.where(on[:, None], lin_emo + lin_off.detach(), lin_off)
