@@ -170,22 +170,84 @@ class GradientConv(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # flat parameter images for the tensor-core MLP kernels
 # ------------------------------------------------------------------------------------------------
-def flat_mlp_params(layers: Sequence[nn.Linear], in_cols: torch.Tensor, k0: int) -> torch.Tensor:
-    """Assemble the f32 master copy esr_mlp_pack consumes (include/esr_b200.h): per layer W then b;
-    layer 0 columns are gathered into the kernel's internal column order (``in_cols[c]`` = reference
-    input column feeding internal column c, or -1 for a zero column); the output layer is padded to 8
-    rows.  Built with differentiable torch ops so autograd routes the flat gradient back to the
-    nn.Linear parameters."""
-    first, last = layers[0], layers[-1]
-    w0 = torch.cat([first.weight, first.weight.new_zeros(first.weight.shape[0], 1)], 1)
-    idx = torch.where(in_cols < 0, torch.full_like(in_cols, first.weight.shape[1]), in_cols)
-    parts = [w0[:, idx].reshape(-1), first.bias]
-    for lin in layers[1:-1]:
-        parts += [lin.weight.reshape(-1), lin.bias]
-    pad = 8 - last.weight.shape[0]
-    parts += [F.pad(last.weight, (0, 0, 0, pad)).reshape(-1), F.pad(last.bias, (0, pad))]
+class _FlatParams(torch.autograd.Function):
+    """One autograd node per net: nn.Linear parameters -> flat f32 master copy (and the flat gradient back)."""
+
+    @staticmethod
+    def forward(ctx, idx, inv, k0, *params):
+        w_first, b_first = params[0], params[1]
+        w_last, b_last = params[-2], params[-1]
+        width = w_first.shape[0]
+        total = width * k0 + width + sum(p.numel() for p in params[2:-2]) + 8 * width + 8
+        flat = torch.zeros(total, dtype=torch.float32, device=w_first.device)
+        # layer 0: reference column order -> internal column order (idx[c] = reference column of internal column c,
+        # = in_features for a zero column)
+        w0 = torch.cat([w_first.detach(), w_first.new_zeros(width, 1)], 1)
+        flat[: width * k0].view(width, k0).copy_(w0.index_select(1, idx))
+        o = width * k0
+        flat[o:o + width].copy_(b_first.detach())
+        o += width
+        for p in params[2:-2]:
+            flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
+            o += p.numel()
+        n_out = w_last.shape[0]
+        flat[o:o + n_out * width].copy_(w_last.detach().reshape(-1))
+        o += 8 * width
+        flat[o:o + n_out].copy_(b_last.detach())
+        ctx.k0, ctx.shapes = k0, [p.shape for p in params]
+        ctx.save_for_backward(inv)
+        return flat
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (inv,) = ctx.saved_tensors
+        shapes, k0 = ctx.shapes, ctx.k0
+        width = shapes[0][0]
+        grads = [g[: width * k0].view(width, k0).index_select(1, inv)]      # inv[r] = internal column of reference column r
+        o = width * k0
+        grads.append(g[o:o + width])
+        o += width
+        for shp in shapes[2:-2]:
+            n = shp.numel()
+            grads.append(g[o:o + n].view(shp))
+            o += n
+        n_out = shapes[-2][0]
+        grads.append(g[o:o + n_out * width].view(n_out, width))
+        o += 8 * width
+        grads.append(g[o:o + n_out])
+        return (None, None, None, *grads)
+
+
+_COLS_CACHE = {}
+
+
+def _col_maps(kind: str, device):
+    """cached (idx, inv) index tensors of a net's input-column permutation on `device`"""
+    key = (kind, str(device))
+    if key not in _COLS_CACHE:
+        cols = tonemap_in_cols("cpu") if kind == "tone" else radiance_in_cols(kind, "cpu")
+        n_ref = int(cols.max()) + 1
+        idx = torch.where(cols < 0, torch.full_like(cols, n_ref), cols)
+        inv = torch.empty(n_ref, dtype=torch.long)
+        for c_int, c_ref in enumerate(cols.tolist()):
+            if c_ref >= 0:
+                inv[c_ref] = c_int
+        _COLS_CACHE[key] = (idx.to(device), inv.to(device))
+    return _COLS_CACHE[key]
+
+
+def flat_mlp_params(layers: Sequence[nn.Linear], kind: str, k0: int) -> torch.Tensor:
+    """Assemble the f32 master copy esr_mlp_pack consumes (include/esr_b200.h): per layer W then b; layer 0 columns
+    are gathered into the kernel's internal column order (`kind` = "off" | "emo" | "tone" selects the permutation,
+    zero columns for padding); the output layer is padded to 8 rows.  A single autograd node routes the flat gradient
+    back to the nn.Linear parameters."""
+    params = []
+    for lin in layers:
+        params += [lin.weight, lin.bias]
+    idx, inv = _col_maps(kind, params[0].device)
     assert idx.numel() == k0
-    return torch.cat(parts)
+    return _FlatParams.apply(idx, inv, k0, *params)
 
 
 def radiance_in_cols(which: str, device) -> torch.Tensor:

@@ -141,11 +141,10 @@ class VoxurfF(nn.Module):
                                 self.mask_cache.act_shift, self.maskcache_thres, self.fastcolor_thres, s_val)
 
     def _flat(self, which: str):
-        dev = self.sdf.grid.device
         if which == "tone":
-            return flat_mlp_params(self.tonemapper.layers(), tonemap_in_cols(dev), 48)
+            return flat_mlp_params(self.tonemapper.layers(), "tone", 48)
         net = self.off_rgbnet if which == "off" else self.emo_rgbnet
-        return flat_mlp_params(net.layers(), radiance_in_cols(which, dev), 96)
+        return flat_mlp_params(net.layers(), which, 96)
 
     def _streams(self, sc, rays_o, rays_d, em_modes):
         n = rays_o.shape[0]
@@ -169,6 +168,9 @@ class VoxurfF(nn.Module):
         N = rays_o.shape[0]
         with torch.cuda.device(rays_o.device):
             sc = self._scene(float(self.s_val))
+            if self.mlp_mode == "bf16":
+                # weight prep is queued before the two stream-size host reads below so the GPU never waits for it
+                flat_off, flat_emo, flat_tone = self._flat("off"), self._flat("emo"), self._flat("tone")
             streams, n_on = self._streams(sc, rays_o, rays_d, em_modes)
             h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, streams, n_on)
             s = streams
@@ -177,10 +179,10 @@ class VoxurfF(nn.Module):
                 off_rows = (s.m3_on, s.m3) if ordered else (0, s.m3)
                 emo_rows = (0, s.m3_on) if ordered else (0, s.m3)
                 lin_off, lin_emo = fused.Shade.apply(self.sdf.grid, self.off_color.grid, self.emo_color.grid,
-                                                     self._flat("off"), self._flat("emo"), sc, rays_o, rays_d,
-                                                     viewdirs, s, off_rows, emo_rows)
+                                                     flat_off, flat_emo, sc, rays_o, rays_d, viewdirs, s, off_rows,
+                                                     emo_rows)
                 # voxurff.py:243-254: on-rays emo + stop-gradient(off); off-rays off
-                rgb, lin = fused.CombineTonemap.apply(lin_off, lin_emo, self._flat("tone"), s.h_ray, em_modes, ordered)
+                rgb, lin = fused.CombineTonemap.apply(lin_off, lin_emo, flat_tone, s.h_ray, em_modes, ordered)
             elif self.mlp_mode == "torch_fp32":
                 x = fused.Encode.apply(self.sdf.grid, self.off_color.grid, self.emo_color.grid, sc, rays_o, rays_d,
                                        viewdirs, s)
