@@ -138,7 +138,7 @@ PROTOTYPES = {
     "esr_mlp_hidden_bytes": (I64, [DESC_P, I64]),
     "esr_mlp_dz_bytes": (I64, [DESC_P, I64]),
     "esr_mlp_pack": (I32, [DESC_P, P, P, P]),
-    "esr_mlp_fwd": (I32, [DESC_P, P, P, I64, I64, I64, P, P, P]),
+    "esr_mlp_fwd": (I32, [DESC_P, P, P, I64, I64, I64, P, P, I64, P]),
     "esr_mlp_bwd": (I32, [DESC_P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, I32, P, P]),
 }
 

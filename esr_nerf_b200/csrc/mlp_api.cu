@@ -64,12 +64,13 @@ extern "C" int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, v
 // (pbr/module.py:24-39 with dim0 33)
 
 extern "C" int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t row_begin,
-                           int64_t row_end, int64_t m_total, float *y, void *hidden, esr_stream_t stream) {
+                           int64_t row_end, int64_t m_total, float *y, void *hidden, int64_t save_row_begin,
+                           esr_stream_t stream) {
   if (int e = check_desc(d)) return e;
   ESR_CHECK_ARG(row_begin >= 0 && row_end >= row_begin && row_end <= m_total);
   if (row_end == row_begin) return ESR_OK;
   ESR_CHECK_ARG(image && x && y);
-  return tc_fwd(d, image, x, row_begin, row_end, m_total, y, hidden, (cudaStream_t)stream);
+  return tc_fwd(d, image, x, row_begin, row_end, m_total, y, hidden, save_row_begin, (cudaStream_t)stream);
 }
 
 extern "C" int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const float *y,

@@ -63,7 +63,7 @@ int64_t tc_image_bytes(const esr_mlp_desc_t *d);
 int tc_pack(const esr_mlp_desc_t *d, const float *flat_params, void *tc_image, cudaStream_t st);
 bool tc_supported(const esr_mlp_desc_t *d);
 int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t row_begin, int64_t row_end,
-           int64_t m_total, float *y, void *hidden, cudaStream_t st);
+           int64_t m_total, float *y, void *hidden, int64_t save_begin, cudaStream_t st);
 int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, const float *d_y, int64_t row_begin,
              int64_t row_end, int64_t m_total, const void *hidden, void *d_z, float *d_z_out, float *d_x,
              int dx_cols, int accumulate, cudaStream_t st);

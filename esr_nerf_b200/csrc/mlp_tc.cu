@@ -264,8 +264,8 @@ struct EpiThread {
 template <int K0, int NH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_fwd_tc(const uint8_t *__restrict__ image, const __nv_bfloat16 *__restrict__ x, int64_t row_begin,
-                 int64_t row_end, int64_t m_total, float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden, int n_out,
-                 int act) {
+                 int64_t row_end, int64_t m_total, float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden,
+                 int64_t save_begin, int n_out, int act) {
   extern __shared__ __align__(128) uint8_t smem[];
   using S = FwdSm<K0, NH>;
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool valid = is_epi && row < row_end;
+    const bool save = valid && hidden && row >= save_begin;  // rows the backward pass will visit
     // ---- layer 0: A = x tile (shared), B = W0 ----
     if (is_epi) {
       cp_async_wait_all();
@@ -349,12 +350,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (p[j] & 0xffff0000u) mask[cc >> 1] |= 1u << (16 * (cc & 1) + 2 * j + 1);
           }
           tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
-          if (hl && valid) {  // the warp's 32 rows write 512 contiguous bytes per chunk
+          if (save) {  // the warp's 32 rows write 512 contiguous bytes per chunk
             hl[act_chunk_index(row, col0 / 8)] = make_uint4(p[0], p[1], p[2], p[3]);
             hl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(p[4], p[5], p[6], p[7]);
           }
         }
-        if (hidden && valid) {
+        if (save) {
           uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
           mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
         }
@@ -807,13 +808,13 @@ static unsigned tc_grid(int64_t rows) {
 
 template <int K0, int NH>
 static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t rb, int64_t re, int64_t mt,
-                      float *y, void *hidden, cudaStream_t st) {
+                      float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
   auto kern = k_mlp_fwd_tc<K0, NH>;
   constexpr int bytes = FwdSm<K0, NH>::bytes;
   if (int e = set_smem_tc(kern, bytes)) return e;
   ESR_STAGE(K0 == 96 ? "k_mlp_fwd_tc_radiance" : "k_mlp_fwd_tc_tonemap", st);
   kern<<<tc_grid(re - rb), TC_THREADS, bytes, st>>>((const uint8_t *)image, (const __nv_bfloat16 *)x, rb, re, mt, y,
-                                                    (__nv_bfloat16 *)hidden, d->n_out, d->act);
+                                                    (__nv_bfloat16 *)hidden, save_begin, d->n_out, d->act);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -857,9 +858,11 @@ int tc_pack(const esr_mlp_desc_t *d, const float *flat_params, void *tc_image, c
 }
 
 int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t row_begin, int64_t row_end,
-           int64_t m_total, float *y, void *hidden, cudaStream_t st) {
-  if (d->k0 == 96 && d->n_hidden == 3) return launch_fwd<96, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, st);
-  if (d->k0 == 48 && d->n_hidden == 1) return launch_fwd<48, 1>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, st);
+           int64_t m_total, float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
+  if (d->k0 == 96 && d->n_hidden == 3)
+    return launch_fwd<96, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
+  if (d->k0 == 48 && d->n_hidden == 1)
+    return launch_fwd<48, 1>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
   set_error("tc_fwd: shape not instantiated");
   return ESR_ERR_BAD_ARG;
 }

@@ -251,7 +251,7 @@ class Encode(torch.autograd.Function):
         return (*g, None, None, None, None, None)
 
 
-def _mlp_forward(desc, image, x, rb, re, m_total, train):
+def _mlp_forward(desc, image, x, rb, re, m_total, train, save_begin=0):
     L = _lib.lib()
     d = _desc(desc)
     dev = x.device
@@ -259,7 +259,8 @@ def _mlp_forward(desc, image, x, rb, re, m_total, train):
     # activations (tiled bf16) + ReLU bit masks, layout private to the library
     hidden = (torch.empty(L.esr_mlp_hidden_bytes(ctypes.byref(d), m_total), dtype=torch.uint8, device=dev)
               if train else None)
-    check(L.esr_mlp_fwd(ctypes.byref(d), ptr(image), ptr(x), rb, re, m_total, ptr(y), ptr(hidden), stream_ptr()))
+    check(L.esr_mlp_fwd(ctypes.byref(d), ptr(image), ptr(x), rb, re, m_total, ptr(y), ptr(hidden), int(save_begin),
+                        stream_ptr()))
     return y, hidden
 
 
@@ -293,7 +294,7 @@ class Shade(torch.autograd.Function):
         train = any(ctx.needs_input_grad[:5])
         x = encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s, bf16=True)
         img_off, img_emo = mlp_pack(RADIANCE_DESC, flat_off), mlp_pack(RADIANCE_DESC, flat_emo)
-        lin_off, hid_off = _mlp_forward(RADIANCE_DESC, img_off, x, 0, s.m3, s.m3, train)
+        lin_off, hid_off = _mlp_forward(RADIANCE_DESC, img_off, x, 0, s.m3, s.m3, train, save_begin=off_grad_rows[0])
         lin_emo, hid_emo = _mlp_forward(RADIANCE_DESC, img_emo, x, 0, s.m3_on, s.m3, train)
         ctx.sc, ctx.streams = sc, s
         ctx.rows = (off_grad_rows, emo_grad_rows)

@@ -261,10 +261,13 @@ int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image,
 /*
  * Forward over rows [row_begin,row_end) of x (bf16, k0 columns, TILED layout as written by esr_encode_fwd /
  * esr_tonemap_encode_fwd with out_is_bf16 = 1).  y: f32 [*,n_out] (activated).
- * hidden (nullable): esr_mlp_hidden_bytes(d, m_total) bytes; post-ReLU activations + ReLU masks saved for backward.
+ * hidden (nullable): esr_mlp_hidden_bytes(d, m_total) bytes; post-ReLU activations + ReLU masks saved for backward,
+ * only for rows >= save_row_begin (rows the caller will never back-propagate through — e.g. the off net on
+ * emission-on rays, which see it through a stop-gradient, voxurff.py:243-254 — need not be stored).
  */
 int esr_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t row_begin,
-                int64_t row_end, int64_t m_total, float *y, void *hidden, esr_stream_t stream);
+                int64_t row_end, int64_t m_total, float *y, void *hidden, int64_t save_row_begin,
+                esr_stream_t stream);
 /*
  * Backward over rows [row_begin,row_end): d_y is dL/dy (post-activation), y the saved outputs.
  *   d_x (nullable): f32 [*, dx_cols] gets dL/dx for the first dx_cols input columns
