@@ -198,7 +198,7 @@ struct RowWriter<__nv_bfloat16> : TiledRowWriter<ESR_FEAT_DIM> {
 constexpr int COL_SDF = 12, COL_FEAT = 13, COL_NRM = 37, COL_XYZ = 49, COL_SIN = 52, COL_COS = 67, COL_VIEW = 82;
 
 template <typename OutT>
-__global__ void __launch_bounds__(ENC_THREADS)
+__global__ void __launch_bounds__(ENC_THREADS, 8)
     k_encode_fwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
                  const float *__restrict__ rays_d, const float *__restrict__ viewdirs,
                  const float *__restrict__ sdf_grid, const float *__restrict__ off_grid,
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(ENC_THREADS)
   wr.finish();
 }
 
-__global__ void __launch_bounds__(ENC_THREADS)
+__global__ void __launch_bounds__(ENC_THREADS, 5)
     k_encode_bwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
                  const float *__restrict__ rays_d, const float *__restrict__ sdf_grid,
                  const int32_t *__restrict__ h_ray, const int32_t *__restrict__ h_step, int64_t m3,
