@@ -85,7 +85,7 @@ class Scene(ctypes.Structure):
         ("near", ctypes.c_float), ("far", ctypes.c_float),
         ("stepdist", ctypes.c_float), ("voxel_size", ctypes.c_float),
         ("act_shift", ctypes.c_float), ("mask_thres", ctypes.c_float),
-        ("fast_thres", ctypes.c_float), ("s_val", ctypes.c_float),
+        ("fast_thres", ctypes.c_float), ("s_val", ctypes.c_float), ("alpha_thres", ctypes.c_float),
     ]
 
 
@@ -125,6 +125,9 @@ PROTOTYPES = {
     "esr_alpha_scan_count": (I32, [SCENE_P, P, I64, P, P, P, P, P]),
     "esr_alpha_scan_fill": (I32, [SCENE_P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]),
     "esr_alpha_scan_bwd": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, I64, P, P]),
+    "esr_neus_alpha_bwd": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, I64, P, P]),
+    "esr_encode_coarse_fwd": (I32, [SCENE_P, P, P, P, P, P, P, P, P, I64, P, P]),
+    "esr_encode_coarse_bwd": (I32, [SCENE_P, P, P, P, P, P, I64, P, P, P, P, P]),
     "esr_encode_fwd": (I32, [SCENE_P, P, P, P, P, P, P, I32, P, P, P, I64, P, I32, P]),
     "esr_encode_bwd": (I32, [SCENE_P, P, P, P, I32, P, P, I64, P, P, P, P, P]),
     "esr_sdf_fd_gradient": (I32, [SCENE_P, P, P, P, P, P, I64, P, P]),

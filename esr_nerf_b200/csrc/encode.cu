@@ -376,6 +376,106 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
 
 
 // ---------------------------------------------------------------------------------------------
+// Coarse-stage feature encode (voxurfc.py:205-249), thread per shaded sample.
+// ---------------------------------------------------------------------------------------------
+constexpr int CF_OFF = 0, CF_EMO = 12, CF_XYZ = 24, CF_SIN = 27, CF_COS = 42, CF_VIEW = 57, CF_NRM = 66;
+
+ESR_D void coarse_sample(const esr_scene_t &sc, const float *rays_o, const float *rays_d, int r, int step, float &px,
+                         float &py, float &pz, Cell &c) {
+  const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
+  ray_point(s, sc.stepdist, step, px, py, pz);
+  c = make_cell(world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx), world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy),
+                world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz));
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_encode_coarse_fwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                        const float *__restrict__ rays_d, const float *__restrict__ viewdirs,
+                        const float *__restrict__ grad_vol, const float *__restrict__ off_grid,
+                        const float *__restrict__ emo_grid, const int32_t *__restrict__ h_ray,
+                        const int32_t *__restrict__ h_step, int64_t m3, float *__restrict__ feat) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m3) return;
+  const int r = h_ray[j];
+  float px, py, pz;
+  Cell c;
+  coarse_sample(sc, rays_o, rays_d, r, h_step[j], px, py, pz, c);
+  float *row = feat + j * ESR_COARSE_FEAT_DIM;
+  float col[12];
+  tapC<12>(off_grid, sc.gx, sc.gy, sc.gz, c, col);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) row[CF_OFF + i] = col[i];
+  tapC<12>(emo_grid, sc.gx, sc.gy, sc.gz, c, col);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) row[CF_EMO + i] = col[i];
+  const float mn[3] = {sc.xyz_min[0], sc.xyz_min[1], sc.xyz_min[2]}, mx[3] = {sc.xyz_max[0], sc.xyz_max[1], sc.xyz_max[2]};
+  const float p[3] = {px, py, pz};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float u = __fdiv_rn(__fsub_rn(p[a], mn[a]), __fsub_rn(mx[a], mn[a]));
+    row[CF_XYZ + a] = u;
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      const float x = __fmul_rn(u, (float)(1 << f));
+      row[CF_SIN + a * 5 + f] = sinf(x);
+      row[CF_COS + a * 5 + f] = cosf(x);
+    }
+    const float v = __ldg(viewdirs + 3 * (int64_t)r + a);
+    row[CF_VIEW + a] = v;
+    row[CF_VIEW + 3 + a] = sinf(v);
+    row[CF_VIEW + 6 + a] = cosf(v);
+  }
+  // normal = g / (|g| + 1e-5), g = trilinear tap of the (d/dx, d/dy, d/dz) volume (voxurfc.py:206,227)
+  const int64_t vol = (int64_t)sc.gx * sc.gy * sc.gz;
+  float g[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) g[a] = tap1(grad_vol + a * vol, sc.gx, sc.gy, sc.gz, c);
+  const float den = __fadd_rn(sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]), 1e-5f);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) row[CF_NRM + a] = __fdiv_rn(g[a], den);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) row[CF_NRM + 3 + a] = 0.f;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_encode_coarse_bwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                        const float *__restrict__ rays_d, const float *__restrict__ grad_vol,
+                        const int32_t *__restrict__ h_ray, const int32_t *__restrict__ h_step, int64_t m3,
+                        const float *__restrict__ d_feat, float *__restrict__ g_vol, float *__restrict__ g_off,
+                        float *__restrict__ g_emo) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m3) return;
+  float px, py, pz;
+  Cell c;
+  coarse_sample(sc, rays_o, rays_d, h_ray[j], h_step[j], px, py, pz, c);
+  const float *d = d_feat + j * ESR_COARSE_FEAT_DIM;
+  float dc[12];
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dc[i] = d[CF_OFF + i], any |= dc[i] != 0.f;
+  if (g_off && any) scatterC<12>(g_off, sc.gx, sc.gy, sc.gz, c, dc);
+  any = false;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dc[i] = d[CF_EMO + i], any |= dc[i] != 0.f;
+  if (g_emo && any) scatterC<12>(g_emo, sc.gx, sc.gy, sc.gz, c, dc);
+  // n = g / (|g| + eps):  dg = dn / (r + eps) - g (g . dn) / (r (r + eps)^2)
+  const int64_t vol = (int64_t)sc.gx * sc.gy * sc.gz;
+  float g[3], dn[3], dot = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    g[a] = tap1(grad_vol + a * vol, sc.gx, sc.gy, sc.gz, c);
+    dn[a] = d[CF_NRM + a];
+    dot += g[a] * dn[a];
+  }
+  const float rr = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]), den = rr + 1e-5f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float dg = dn[a] / den - (rr > 0.f ? g[a] * dot / (rr * den * den) : 0.f);
+    if (dg != 0.f) scatter1(g_vol + a * vol, sc.gx, sc.gy, sc.gz, c, dg);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // sample_sdf_grad (voxurff.py:670-676): finite-difference SDF gradient from the 6 axis taps at 1 voxel, in
 // world units and (x, y, z) order — the inference path turns it into the normal map (voxurff.py:421-430).
 // ---------------------------------------------------------------------------------------------
@@ -571,6 +671,36 @@ extern "C" int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const 
   ESR_STAGE("k_encode_bwd", (cudaStream_t)stream);
   k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
                                                                 d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_encode_coarse_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                     const float *viewdirs, const float *grad_vol, const float *off_color_grid,
+                                     const float *emo_color_grid, const int32_t *h_ray, const int32_t *h_step,
+                                     int64_t m3, float *feat, esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(m3 >= 0);
+  if (m3 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && viewdirs && grad_vol && off_color_grid && emo_color_grid && h_ray && h_step && feat);
+  ESR_STAGE("k_encode_coarse_fwd", stream);
+  k_encode_coarse_fwd<<<cdiv(m3, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(
+      *sc, rays_o, rays_d, viewdirs, grad_vol, off_color_grid, emo_color_grid, h_ray, h_step, m3, feat);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_encode_coarse_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                     const float *grad_vol, const int32_t *h_ray, const int32_t *h_step, int64_t m3,
+                                     const float *d_feat, float *g_grad_vol, float *g_off_grid, float *g_emo_grid,
+                                     esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(m3 >= 0);
+  if (m3 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && grad_vol && h_ray && h_step && d_feat && g_grad_vol);
+  ESR_STAGE("k_encode_coarse_bwd", stream);
+  k_encode_coarse_bwd<<<cdiv(m3, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(
+      *sc, rays_o, rays_d, grad_vol, h_ray, h_step, m3, d_feat, g_grad_vol, g_off_grid, g_emo_grid);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256)
         float pc, nc;
         a = neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
       }
-      const bool f0 = valid && (a > sc.fast_thres);  // voxurff.py:201
+      const bool f0 = valid && (a > sc.alpha_thres);  // voxurff.py:201 (coarse stage: no alpha filter)
       float myT = -1.f, myW = 0.f;
       unsigned m = __ballot_sync(FULL, f0);
       // kernel.cu:591-601 replayed in order over the surviving samples (uniform across the warp)
@@ -215,24 +215,25 @@ __global__ void __launch_bounds__(256)
                      const int32_t *__restrict__ off_mask, const float *__restrict__ s_sdf,
                      const float *__restrict__ s_alpha, const float *__restrict__ s_T,
                      const float *__restrict__ alphainv_last, const float *__restrict__ g_w_m1,
-                     const float *__restrict__ g_last, float *__restrict__ dprev, float *__restrict__ dnext) {
+                     const float *__restrict__ g_last, const float *__restrict__ g_alpha,
+                     float *__restrict__ dprev, float *__restrict__ dnext) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned lane = lane_id();
   for (int64_t slot = warp; slot < n_rays; slot += nwarps) {
     const int r = ray_order ? ray_order[slot] : (int)slot;
     const int s = off_mask[slot], e = off_mask[slot + 1];
-    float carry = g_last ? g_last[r] * alphainv_last[r] : 0.f;
+    float carry = (g_last && !g_alpha) ? g_last[r] * alphainv_last[r] : 0.f;
     for (int hi = e; hi > s; hi -= 32) {
       const int i = hi - 1 - (int)lane;
       const bool valid = i >= s;
       float a = 0.f, Ti = -1.f, gw = 0.f;
-      if (valid) {
+      if (valid && !g_alpha) {
         a = s_alpha[i];
         Ti = s_T[i];
         gw = g_w_m1[i];
       }
-      const bool proc = valid && Ti >= 0.f;
+      const bool proc = valid && (g_alpha || Ti >= 0.f);
       const float x = proc ? gw * (Ti * a) : 0.f;
       float inc = x;
 #pragma unroll
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(256)
       if (!valid) continue;
       float dp = 0.f, dn = 0.f;
       if (proc) {
-        const float ga = (float)((double)(gw * Ti) - (double)back_cum / ((double)(1.f - a) + 1e-10));
+        const float ga = g_alpha ? g_alpha[i]
+                                 : (float)((double)(gw * Ti) - (double)back_cum / ((double)(1.f - a) + 1e-10));
         if (ga != 0.f) {
           const float sd = s_sdf[i];
           const bool has_prev = i > s, has_next = i + 1 < e;
@@ -309,7 +311,30 @@ extern "C" int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, co
   cudaStream_t st = (cudaStream_t)stream;
   ESR_STAGE("k_alpha_scan_bwd", st);
   k_alpha_scan_bwd<<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, s_alpha, s_T,
-                                                       alphainv_last, g_w_m1, g_last, tmp_dprev, tmp_dnext);
+                                                       alphainv_last, g_w_m1, g_last, nullptr, tmp_dprev, tmp_dnext);
+  ESR_LAUNCH_OK();
+  ESR_STAGE("k_sdf_scatter", st);
+  k_sdf_scatter<<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,
+                                               grad_sdf_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+
+extern "C" int esr_neus_alpha_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                  const int32_t *ray_order, int64_t n_rays, const int32_t *off_mask,
+                                  const int32_t *s_ray, const int32_t *s_step, const float *s_sdf,
+                                  const float *g_alpha_m1, float *tmp_dprev, float *tmp_dnext, int64_t m1,
+                                  float *grad_sdf_grid, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && m1 >= 0 && m1 < (1ll << 31));
+  if (n_rays == 0 || m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && off_mask && s_ray && s_step && s_sdf && g_alpha_m1 && tmp_dprev && tmp_dnext &&
+                grad_sdf_grid);
+  cudaStream_t st = (cudaStream_t)stream;
+  ESR_STAGE("k_neus_alpha_bwd", st);
+  k_alpha_scan_bwd<<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, nullptr, nullptr, nullptr,
+                                                       nullptr, nullptr, g_alpha_m1, tmp_dprev, tmp_dnext);
   ESR_LAUNCH_OK();
   ESR_STAGE("k_sdf_scatter", st);
   k_sdf_scatter<<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,

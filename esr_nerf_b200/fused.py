@@ -31,7 +31,7 @@ TONEMAP_DESC = dict(k0=48, width=192, n_hidden=1, n_out=3, act=2)    # pbr/modul
 
 
 def make_scene(xyz_min, xyz_max, grid_size, mask_xyz_min, mask_xyz_max, mask_size, near, far, stepdist,
-               voxel_size, act_shift, mask_thres, fast_thres, s_val) -> Scene:
+               voxel_size, act_shift, mask_thres, fast_thres, s_val, alpha_thres=None) -> Scene:
     sc = Scene()
     for i in range(3):
         sc.xyz_min[i] = float(xyz_min[i])
@@ -43,6 +43,7 @@ def make_scene(xyz_min, xyz_max, grid_size, mask_xyz_min, mask_xyz_max, mask_siz
     sc.near, sc.far = float(near), float(far)
     sc.stepdist, sc.voxel_size = float(stepdist), float(voxel_size)
     sc.act_shift, sc.mask_thres, sc.fast_thres, sc.s_val = float(act_shift), float(mask_thres), float(fast_thres), float(s_val)
+    sc.alpha_thres = float(fast_thres if alpha_thres is None else alpha_thres)
     return sc
 
 
@@ -419,3 +420,86 @@ class Composite(torch.autograd.Function):
         check(_lib.lib().esr_composite_bwd(ptr(s.h_ray), None, ptr(h_w), ptr(a), ptr(b), ptr(c_a.contiguous()),
                                            ptr(c_b.contiguous()), s.m3, ptr(d_a), ptr(d_b), ptr(g_w), stream_ptr()))
         return g_w, d_a, d_b, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# coarse stage (VoxurfC, voxurfc.py:186-271)
+# ---------------------------------------------------------------------------------------------------
+COARSE_FEAT_DIM = 72
+
+
+class CoarseAlpha(torch.autograd.Function):
+    """NeuS alpha of the samples that survive the first Alphas2Weights pass (weights > thres, voxurfc.py:211-218):
+    h_alpha [M3] = f(smoothed sdf grid).  Fills the M3 stream fields of `streams`.  The reference then recomputes
+    the weights on the survivors (voxurfc.py:219) — done by the caller with the reference-shaped Alphas2Weights."""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, sc: Scene, rays_o, rays_d, streams: Streams):
+        L = _lib.lib()
+        dev = rays_o.device
+        n, st, scp = streams.n_rays, stream_ptr(), ctypes.byref(sc)
+        cnt_shade = _i32(n, dev)
+        last = _f32(n, dev=dev)
+        check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
+                                     ptr(cnt_shade), ptr(last), st))
+        off_shade = exclusive_scan(cnt_shade)
+        m3 = int(off_shade[n].item())
+        streams.off_shade, streams.m3, streams.m3_on = off_shade, m3, m3
+        streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
+        streams.h_ray, streams.h_step, streams.h_m1 = _i32(m3, dev), _i32(m3, dev), _i32(m3, dev)
+        streams.h_sdf = _f32(m3, dev=dev)
+        h_w = _f32(m3, dev=dev)
+        check(L.esr_alpha_scan_fill(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_step),
+                                    ptr(streams.s_sdf), ptr(off_shade), ptr(streams.s_alpha), ptr(streams.s_T),
+                                    ptr(streams.h_ray), ptr(streams.h_step), ptr(streams.h_m1), ptr(h_w),
+                                    ptr(streams.h_sdf), st))
+        h_alpha = streams.s_alpha[streams.h_m1.long()] if m3 else _f32(0, dev=dev)
+        ctx.sc, ctx.streams = sc, streams
+        ctx.save_for_backward(rays_o, rays_d, sdf_grid)
+        return h_alpha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_alpha):
+        rays_o, rays_d, sdf_grid = ctx.saved_tensors
+        s: Streams = ctx.streams
+        dev = rays_o.device
+        grad_sdf = torch.zeros_like(sdf_grid)
+        if s.m1 == 0 or s.m3 == 0:
+            return grad_sdf, None, None, None, None
+        g_m1 = torch.zeros(s.m1, dtype=torch.float32, device=dev)
+        g_m1.index_copy_(0, s.h_m1.long(), g_alpha.contiguous())
+        tmp_p, tmp_n = _f32(s.m1, dev=dev), _f32(s.m1, dev=dev)
+        check(_lib.lib().esr_neus_alpha_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.ray_order), s.n_rays,
+                                            ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(g_m1),
+                                            ptr(tmp_p), ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
+        return grad_sdf, None, None, None, None
+
+
+class EncodeCoarse(torch.autograd.Function):
+    """[M3,72] f32 coarse feature rows (esr_encode_coarse_fwd): colour taps, PE, normal from the gradient volume."""
+
+    @staticmethod
+    def forward(ctx, grad_vol, off_grid, emo_grid, sc, rays_o, rays_d, viewdirs, streams):
+        _check_cl(off_grid, "off_color.grid")
+        _check_cl(emo_grid, "emo_color.grid")
+        s: Streams = streams
+        grad_vol = grad_vol.contiguous()
+        x = torch.empty(s.m3, COARSE_FEAT_DIM, dtype=torch.float32, device=rays_o.device)
+        check(_lib.lib().esr_encode_coarse_fwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(viewdirs), ptr(grad_vol),
+                                               ptr(off_grid), ptr(emo_grid), ptr(s.h_ray), ptr(s.h_step), s.m3, ptr(x),
+                                               stream_ptr()))
+        ctx.sc, ctx.streams = sc, s
+        ctx.save_for_backward(rays_o, rays_d, grad_vol, off_grid, emo_grid)
+        return x
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_x):
+        rays_o, rays_d, grad_vol, off_grid, emo_grid = ctx.saved_tensors
+        s: Streams = ctx.streams
+        g_vol, g_off, g_emo = torch.zeros_like(grad_vol), torch.zeros_like(off_grid), torch.zeros_like(emo_grid)
+        check(_lib.lib().esr_encode_coarse_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(grad_vol),
+                                               ptr(s.h_ray), ptr(s.h_step), s.m3, ptr(d_x.contiguous()), ptr(g_vol),
+                                               ptr(g_off), ptr(g_emo), stream_ptr()))
+        return g_vol, g_off, g_emo, None, None, None, None, None

@@ -71,6 +71,29 @@ def fill_fine_model(model, sdf_noise: float = 0.01) -> None:
         model.emo_color.grid.copy_(color_grid(ws, 6, 3).to(dev))
 
 
+COARSE_MODEL_CFG = dict(  # cfg/app/coarse.yaml:13-31
+    mask_ks=3, maskcache_thres=1e-3, fastcolor_thres=1e-4, stepsize=0.5, num_voxels=96 ** 3, color_dim=12,
+    rgbnet_width=128, rgbnet_depth=3, posbase_pe=5, viewbase_pe=1, smooth_ksize=5, smooth_sigma=0.8,
+    neus_alpha="interp")
+
+
+def coarse_cfg(device="cuda:0", **overrides):
+    model = dict(COARSE_MODEL_CFG)
+    model.update(overrides)
+    return SimpleNamespace(system=SimpleNamespace(device=device),
+                           app=SimpleNamespace(model=SimpleNamespace(**model)))
+
+
+def fill_coarse_model(model, sdf_noise: float = 0.01) -> None:
+    """Overwrite the grids of a (reference or esr_nerf_b200) VoxurfC in place with the synthetic scene."""
+    ws = [int(w) for w in model.world_size]
+    dev = model.sdf.grid.device
+    with torch.no_grad():
+        model.sdf.grid.copy_(sphere_sdf(ws, noise=sdf_noise).to(dev))
+        model.off_color.grid.copy_(color_grid(ws, 12, 2).to(dev))
+        model.emo_color.grid.copy_(color_grid(ws, 12, 3).to(dev))
+
+
 BBOX_MIN = torch.tensor([-1.05, -1.05, -1.05])
 BBOX_MAX = torch.tensor([1.05, 1.05, 1.05])
 NEAR, FAR = 2.0, 6.0          # data/esr_nerf/esrnerf.py:77-79

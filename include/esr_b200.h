@@ -110,8 +110,10 @@ typedef struct esr_scene {
   float voxel_size;
   float act_shift;                        /* log(1/(1-alpha_init)-1), module.py:101 */
   float mask_thres;                       /* maskcache_thres, 1e-3 */
-  float fast_thres;                       /* fastcolor_thres, 1e-4 */
+  float fast_thres;                       /* fastcolor_thres, 1e-4: weight filter (voxurff.py:209, voxurfc.py:214) */
   float s_val;                            /* NeuS inverse std */
+  float alpha_thres;                      /* alpha filter before the scan: fastcolor_thres in the fine stage
+                                             (voxurff.py:201); negative (= no filter) in the coarse stage */
 } esr_scene_t;
 
 /* exclusive scan of int32 counts: out[i] = sum_{j<i} in[j]; out[n] = total (out has n+1 slots) */
@@ -163,6 +165,15 @@ int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, const float *
                        const float *s_alpha, const float *s_T, const float *alphainv_last,
                        const float *g_w_m1, const float *g_last, float *tmp_dprev, float *tmp_dnext,
                        int64_t m1, float *grad_sdf_grid, esr_stream_t stream);
+/*
+ * Same backward with dL/dalpha given directly on the M1 stream (g_alpha_m1) instead of going through the
+ * Alphas2Weights recurrence: the coarse stage recomputes the weights on the shaded samples with the reference-shaped
+ * esr_alpha2weight_* ops (voxurfc.py:211-219), so only the NeuS alpha -> sdf part is needed here.
+ */
+int esr_neus_alpha_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                       int64_t n_rays, const int32_t *off_mask, const int32_t *s_ray, const int32_t *s_step,
+                       const float *s_sdf, const float *g_alpha_m1, float *tmp_dprev, float *tmp_dnext, int64_t m1,
+                       float *grad_sdf_grid, esr_stream_t stream);
 
 /*
  * Stage E — per shaded sample feature encode (voxurff.py:219-241): 24 multi-scale SDF taps +
@@ -188,6 +199,22 @@ int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays
                    const float *sdf_grid, int color_dim, const int32_t *h_ray, const int32_t *h_step,
                    int64_t m3, const float *d_feat, float *grad_sdf_grid, float *grad_off_grid,
                    float *grad_emo_grid, esr_stream_t stream);
+
+/*
+ * Coarse-stage feature encode (voxurfc.py:205-249): trilinear tap of the dense central-difference gradient volume
+ * `grad_vol` ([1,3,X,Y,Z], channels-first, voxurfc.py:597-616) -> normal = g / (|g| + 1e-5); 12-channel colour-grid
+ * taps (channels-last); positional / view encodings.  Row (f32, row-major, 72 columns):
+ *   [off_color 12 | emo_color 12 | xyz 3 | sin 15 | cos 15 | view 3 | sin view 3 | cos view 3 | normal 3 | pad 3]
+ * Backward: d_feat [m3,72] -> scatter-add into the two colour-grid gradients and the gradient-volume gradient.
+ */
+#define ESR_COARSE_FEAT_DIM 72
+int esr_encode_coarse_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                          const float *grad_vol, const float *off_color_grid, const float *emo_color_grid,
+                          const int32_t *h_ray, const int32_t *h_step, int64_t m3, float *feat,
+                          esr_stream_t stream);
+int esr_encode_coarse_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *grad_vol,
+                          const int32_t *h_ray, const int32_t *h_step, int64_t m3, const float *d_feat,
+                          float *g_grad_vol, float *g_off_grid, float *g_emo_grid, esr_stream_t stream);
 
 /*
  * sample_sdf_grad (voxurff.py:670-676) over the shaded stream: finite-difference SDF gradient from the six axis

@@ -104,6 +104,68 @@ def run_case(name, spec, weights):
     print(f"{name}: m0={m0} m1={ray_id.numel()} m3={m3_ray.numel()} loss={loss.item():.6f}")
 
 
+COARSE_CASES = {
+    # name: (num_voxels, mask_res, sparse, n_rays, s_val, ray_seed)   — BASELINE config 1 shape, shrunk
+    "coarse_sparse_s5": (32 ** 3, 16, True, 128, 5.0, 1234),
+    "coarse_dense_s25": (40 ** 3, 20, False, 160, 25.0, 555),
+}
+
+
+def coarse_cfg(num_voxels):
+    return H.DictConfig(dict(system=dict(device="cpu"), app=dict(model=dict(S.COARSE_MODEL_CFG, num_voxels=num_voxels))))
+
+
+def build_reference_coarse(num_voxels, mask_res, sparse, s_val, weights=None):
+    _, VoxurfC, _, _ = H.reference_classes()
+    torch.manual_seed(0)
+    m = VoxurfC(coarse_cfg(num_voxels), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(mask_res, sparse), s_val)
+    if weights is not None:
+        m.load_state_dict({**m.state_dict(), **weights})
+    S.fill_coarse_model(m)
+    m.train()
+    return m
+
+
+def coarse_cotangents(n, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {"srgb/rgb": torch.randn(n, 3, generator=g), "etc/alphainv_cum": torch.randn(n, generator=g),
+            "etc/white_bg": torch.randn(n, 1, generator=g)}
+
+
+def run_coarse_case(name, spec, weights):
+    num_voxels, mask_res, sparse, n, s_val, seed = spec
+    m = build_reference_coarse(num_voxels, mask_res, sparse, s_val, weights)
+    rays = S.make_rays(n, seed)
+    out = m(s_val=s_val, rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+            em_modes=rays["em_modes"], rgbs=rays["rgbs"])
+    cot = coarse_cotangents(n)
+    loss = sum((out[k] * cot[k]).sum() for k in cot)
+    loss.backward()
+    fx = dict(num_voxels=num_voxels, mask_res=mask_res, sparse=int(sparse), n_rays=n, s_val=s_val, ray_seed=seed,
+              loss=loss.item())
+    for k, v in out.items():
+        fx["out/" + k] = v.detach().numpy()
+    for pname, p in m.named_parameters():
+        if p.grad is not None:
+            fx.update(grad_digest(pname, p.grad))
+    np.savez_compressed(os.path.join(GOLDEN, f"voxurfc_{name}.npz"), **fx)
+    print(f"{name}: loss={loss.item():.6f}")
+
+
+def main_coarse():
+    m = build_reference_coarse(32 ** 3, 16, True, 5.0)
+    sd = m.state_dict()
+    weights = {k: sd[k].clone() for k in sd if "rgbnet" in k}
+    g = torch.Generator().manual_seed(12)
+    for k in weights:  # the reference zero-initialises the last bias; give every bias a non-trivial value
+        if k.endswith("bias"):
+            weights[k] = weights[k] + 0.05 * torch.randn(weights[k].shape, generator=g)
+    np.savez_compressed(os.path.join(GOLDEN, "coarse_weights.npz"), **{k: v.numpy() for k, v in weights.items()})
+    for name, spec in COARSE_CASES.items():
+        run_coarse_case(name, spec, weights)
+
+
 def main():
     if not H.reference_available():
         raise SystemExit("reference tree not available; golden vectors can only be generated in the build container")
@@ -118,8 +180,10 @@ def main():
         if k.endswith("bias"):
             weights[k] = weights[k] + 0.05 * torch.randn(weights[k].shape, generator=g)
     np.savez_compressed(wpath, **{k: v.numpy() for k, v in weights.items()})
-    for name, spec in CASES.items():
-        run_case(name, spec, weights)
+    if "--coarse-only" not in sys.argv:
+        for name, spec in CASES.items():
+            run_case(name, spec, weights)
+    main_coarse()
 
 
 if __name__ == "__main__":

@@ -104,3 +104,52 @@ def grad_close(g: torch.Tensor, r: torch.Tensor, tol: float, outlier_frac: float
     l2 = float((g - r).norm() / r.norm().clamp_min(1e-30))
     ok = n_out <= max(3, outlier_frac * nz) and l2 < l2_factor * tol      # 3: a flipped unit in a 192-entry bias
     return ok, f"max-rel {float(d.max() / r.abs().max()):.2e} outliers {n_out}/{nz} rel-L2 {l2:.2e}"
+
+
+# ---------------------------------------------------------------------------------------------------
+# coarse stage (VoxurfC)
+# ---------------------------------------------------------------------------------------------------
+COARSE_CASES = ["coarse_sparse_s5", "coarse_dense_s25"]
+
+
+def load_coarse_case(name):
+    fx = dict(np.load(os.path.join(GOLDEN, f"voxurfc_{name}.npz")))
+    w = dict(np.load(os.path.join(GOLDEN, "coarse_weights.npz")))
+    return fx, {k: torch.from_numpy(v) for k, v in w.items()}
+
+
+def coarse_cotangents(n, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {"srgb/rgb": torch.randn(n, 3, generator=g), "etc/alphainv_cum": torch.randn(n, generator=g),
+            "etc/white_bg": torch.randn(n, 1, generator=g)}
+
+
+def coarse_oracle_scene(num_voxels, mask_res, sparse):
+    from oracle import voxurfc_port as PC
+
+    scene = oracle_scene(num_voxels, mask_res, sparse)
+    scene["smooth_kernel"] = PC.gaussian_kernel(5, 0.8)
+    return scene
+
+
+def coarse_oracle_params(scene, weights, requires_grad=True):
+    from oracle import voxurfc_port as PC
+
+    ws = scene["world_size"]
+    sd = dict(weights)
+    sd["sdf.grid"] = S.sphere_sdf(ws)
+    sd["off_color.grid"] = S.color_grid(ws, 12, 2)
+    sd["emo_color.grid"] = S.color_grid(ws, 12, 3)
+    leaves = {k: v.clone().float().requires_grad_(requires_grad) for k, v in sd.items()}
+    return PC.params_from_state_dict(leaves), leaves
+
+
+def build_product_coarse(fx, weights, device="cuda:0"):
+    from esr_nerf_b200.voxurfc import VoxurfC
+
+    cfg = S.coarse_cfg(device=device, num_voxels=int(fx["num_voxels"]))
+    m = VoxurfC(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(int(fx["mask_res"]), bool(fx["sparse"])), float(fx["s_val"]))
+    m.load_state_dict({**m.state_dict(), **weights})
+    S.fill_coarse_model(m)
+    return m
