@@ -4,6 +4,7 @@ render-function signatures.  See DESIGN.md / INTEGRATION.md.
 Public surface (mirrors the reference names):
     VoxurfF                               <- app.fine.model.VoxurfF
     VoxurfC                               <- app.coarse.model.VoxurfC
+    DVGO                                  <- app.coarse.model.DVGO
     render_utils.render_utils_cuda.*      <- app/utils/base/cuda/render_utils.cpp (live entries)
     render_utils.total_variation_cuda.*   <- app/utils/base/cuda/total_variation.cpp
     render_utils.segment_coo              <- torch_scatter.segment_coo(reduce="sum")
@@ -17,10 +18,13 @@ def __getattr__(name):  # lazy: importing the package must work on a box without
     if name == "VoxurfF":
         from .voxurff import VoxurfF
         return VoxurfF
+    if name == "DVGO":
+        from .dvgo import DVGO
+        return DVGO
     if name == "VoxurfC":
         from .voxurfc import VoxurfC
         return VoxurfC
-    if name in ("render_utils", "fused", "modules", "synthetic", "voxurff", "voxurfc", "dist"):
+    if name in ("render_utils", "fused", "modules", "synthetic", "voxurff", "voxurfc", "dvgo", "dist"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -17,7 +17,7 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
-SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu"]
+SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -89,6 +89,14 @@ class Scene(ctypes.Structure):
     ]
 
 
+class DvgoScene(ctypes.Structure):
+    """esr_dvgo_scene_t"""
+    _fields_ = [("xyz_min", ctypes.c_float * 3), ("xyz_max", ctypes.c_float * 3),
+                ("gx", ctypes.c_int32), ("gy", ctypes.c_int32), ("gz", ctypes.c_int32),
+                ("near", ctypes.c_float), ("far", ctypes.c_float), ("stepdist", ctypes.c_float),
+                ("interval", ctypes.c_float), ("act_shift", ctypes.c_float)]
+
+
 class MlpDesc(ctypes.Structure):
     """esr_mlp_desc_t"""
     _fields_ = [("k0", ctypes.c_int32), ("width", ctypes.c_int32), ("n_hidden", ctypes.c_int32),
@@ -103,6 +111,7 @@ F3 = ctypes.c_float * 3
 F3P = ctypes.POINTER(ctypes.c_float)
 SCENE_P = ctypes.POINTER(Scene)
 DESC_P = ctypes.POINTER(MlpDesc)
+DVGO_P = ctypes.POINTER(DvgoScene)
 
 # every symbol declared in include/esr_b200.h: name -> (restype, argtypes)
 PROTOTYPES = {
@@ -135,6 +144,9 @@ PROTOTYPES = {
     "esr_tonemap_encode_bwd": (I32, [P, P, P, I64, P, P]),
     "esr_composite_fwd": (I32, [P, I64, P, P, P, P, P, P, P]),
     "esr_composite_bwd": (I32, [P, P, P, P, P, P, P, I64, P, P, P, P]),
+    "esr_dvgo_fwd": (I32, [DVGO_P, P, P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P]),
+    "esr_dvgo_eval": (I32, [DVGO_P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P, P, P]),
+    "esr_dvgo_bwd": (I32, [DVGO_P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "esr_mlp_param_count": (I64, [DESC_P]),
     "esr_mlp_image_bytes": (I64, [DESC_P]),
     "esr_mlp_act_rows": (I64, [I64]),

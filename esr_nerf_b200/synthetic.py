@@ -94,6 +94,25 @@ def fill_coarse_model(model, sdf_noise: float = 0.01) -> None:
         model.emo_color.grid.copy_(color_grid(ws, 12, 3).to(dev))
 
 
+def dvgo_cfg(device="cuda:0", num_voxels=1024000):
+    """cfg/app/alphamask.yaml:13-17"""
+    return SimpleNamespace(system=SimpleNamespace(device=device),
+                           app=SimpleNamespace(model=SimpleNamespace(num_voxels=num_voxels, stepsize=0.5, alpha_init=1e-6)))
+
+
+def fill_dvgo_model(model) -> None:
+    """Synthetic alphamask-stage scene: density high inside the r = 0.6 ball (smooth falloff), random colour grids."""
+    ws = [int(w) for w in model.density.shape[2:]]
+    ax = [torch.linspace(-1.05, 1.05, w) for w in ws]
+    gx, gy, gz = torch.meshgrid(*ax, indexing="ij")
+    r = (gx ** 2 + gy ** 2 + gz ** 2).sqrt()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        model.density.copy_(((0.6 - r) * 40 + 12 + 0.5 * torch.randn(r.shape, generator=g))[None, None].to(model.density.device))
+        model.off_color.copy_(torch.randn([1, 3, *ws], generator=g).to(model.density.device))
+        model.emo_color.copy_(torch.randn([1, 3, *ws], generator=g).to(model.density.device))
+
+
 BBOX_MIN = torch.tensor([-1.05, -1.05, -1.05])
 BBOX_MAX = torch.tensor([1.05, 1.05, 1.05])
 NEAR, FAR = 2.0, 6.0          # data/esr_nerf/esrnerf.py:77-79

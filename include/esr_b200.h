@@ -308,6 +308,43 @@ int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const
                 const void *hidden, void *d_z, float *d_z_out, float *d_x, int dx_cols,
                 int accumulate, float *grad_flat, esr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 3. Alphamask stage (DVGO, app/coarse/model/dvgo.py:140-288): dense [N x S] sampling, density / colour grids only
+ * ---------------------------------------------------------------------------------------- */
+typedef struct esr_dvgo_scene {
+  float xyz_min[3], xyz_max[3]; /* dvgo.py:27-28 */
+  int32_t gx, gy, gz;           /* world_size */
+  float near, far;              /* t clamp of the slab test (dvgo.py:152-158) */
+  float stepdist;               /* stepsize * voxel_size (dvgo.py:167) */
+  float interval;               /* stepsize (dvgo.py:184) */
+  float act_shift;              /* log(1/(1-alpha_init)-1) (dvgo.py:37) */
+} esr_dvgo_scene_t;
+
+/*
+ * DVGO.forward_training (dvgo.py:174-214).  jitter: f32 [n_rays] per-ray sample offset in [0,1) (the reference's
+ * torch.rand_like draw, dvgo.py:163; nullable = 0).  Grids: density [1,1,X,Y,Z], colours [1,3,X,Y,Z], channels-first.
+ * Outputs (all f32): alphainv_cum [N,S+1], weights [N,S], raw_rgb [N,S,3], rgb [N,3]; alpha [N,S], raw_off / raw_emo
+ * [N,S,3] (per-grid sigmoid colours) are saved for backward.
+ */
+int esr_dvgo_fwd(const esr_dvgo_scene_t *sc, const float *rays_o, const float *rays_d, const float *jitter,
+                 const int64_t *em_modes, const float *density, const float *off_color, const float *emo_color,
+                 int64_t n_rays, int n_samples, float *alpha, float *raw_off, float *raw_emo, float *alphainv_cum,
+                 float *weights, float *raw_rgb, float *rgb, esr_stream_t stream);
+/* DVGO.forward_evaluate (dvgo.py:216-263): off / emo / on = off + emo colour maps and depth = sum w |o - p| */
+int esr_dvgo_eval(const esr_dvgo_scene_t *sc, const float *rays_o, const float *rays_d, const float *density,
+                  const float *off_color, const float *emo_color, int64_t n_rays, int n_samples, float *alpha,
+                  float *raw_off, float *raw_emo, float *alphainv_cum, float *weights, float *off_rgb, float *emo_rgb,
+                  float *on_rgb, float *depth, esr_stream_t stream);
+/*
+ * Backward of esr_dvgo_fwd: cotangents of (alphainv_cum, weights, raw_rgb, rgb) -> scatter-add into the three grid
+ * gradients.  d_alpha [N,S] and d_raw [N,S,3] are scratch.
+ */
+int esr_dvgo_bwd(const esr_dvgo_scene_t *sc, const float *rays_o, const float *rays_d, const float *jitter,
+                 const int64_t *em_modes, const float *density, int64_t n_rays, int n_samples, const float *alpha,
+                 const float *raw_off, const float *raw_emo, const float *alphainv_cum, const float *raw_rgb,
+                 const float *g_cum, const float *g_weights, const float *g_raw_rgb, const float *g_rgb, float *d_alpha,
+                 float *d_raw, float *grad_density, float *grad_off_color, float *grad_emo_color, esr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

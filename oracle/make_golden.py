@@ -166,6 +166,53 @@ def main_coarse():
         run_coarse_case(name, spec, weights)
 
 
+DVGO_CASES = {"dvgo_24": (24 ** 3, 96, 77), "dvgo_40": (40 ** 3, 64, 78)}   # name: (num_voxels, n_rays, seed)
+
+
+def dvgo_cotangents(n, S, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {"etc/alphainv_cum": torch.randn(n, S + 1, generator=g), "etc/weights": torch.randn(n, S, generator=g),
+            "etc/white_bg": torch.randn(n, 1, generator=g), "srgb/raw_rgb": 0.1 * torch.randn(n, S, 3, generator=g),
+            "srgb/rgb": torch.randn(n, 3, generator=g)}
+
+
+def build_reference_dvgo(num_voxels):
+    DVGO, _, _, _ = H.reference_classes()
+    cfg = H.DictConfig(dict(system=dict(device="cpu"), app=dict(model=dict(num_voxels=num_voxels, stepsize=0.5,
+                                                                            alpha_init=S.MASK_ALPHA_INIT))))
+    m = DVGO(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX)
+    S.fill_dvgo_model(m)
+    m.train()
+    return m
+
+
+def main_dvgo():
+    for name, (num_voxels, n, seed) in DVGO_CASES.items():
+        m = build_reference_dvgo(num_voxels)
+        rays = S.make_rays(n, seed)
+        torch.manual_seed(seed)                      # the reference draws the sampler jitter with torch.rand_like
+        out = m(rays_o=rays["rays_o"], rays_d=rays["rays_d"], em_modes=rays["em_modes"])
+        torch.manual_seed(seed)
+        jitter = torch.rand(n, 1)                    # same stream, stored with the fixture
+        cot = dvgo_cotangents(n, m.N_samples)
+        loss = sum((out[k] * cot[k]).sum() for k in cot)
+        loss.backward()
+        fx = dict(num_voxels=num_voxels, n_rays=n, ray_seed=seed, n_samples=m.N_samples, jitter=jitter.numpy(),
+                  loss=loss.item())
+        for k, v in out.items():
+            fx["out/" + k] = v.detach().numpy()
+        for pname, p in m.named_parameters():
+            fx.update(grad_digest(pname, p.grad))
+        m.eval()
+        with torch.no_grad():
+            for em in (0, 1):
+                ev = m(rays_o=rays["rays_o"], rays_d=rays["rays_d"], em_modes=torch.tensor(em))
+                for k, v in ev.items():
+                    fx[f"eval{em}/" + k] = v.numpy()
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **fx)
+        print(f"{name}: S={m.N_samples} loss={loss.item():.6f}")
+
+
 def main():
     if not H.reference_available():
         raise SystemExit("reference tree not available; golden vectors can only be generated in the build container")
@@ -180,10 +227,13 @@ def main():
         if k.endswith("bias"):
             weights[k] = weights[k] + 0.05 * torch.randn(weights[k].shape, generator=g)
     np.savez_compressed(wpath, **{k: v.numpy() for k, v in weights.items()})
+    if "--dvgo-only" in sys.argv:
+        return main_dvgo()
     if "--coarse-only" not in sys.argv:
         for name, spec in CASES.items():
             run_case(name, spec, weights)
     main_coarse()
+    main_dvgo()
 
 
 if __name__ == "__main__":

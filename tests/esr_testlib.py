@@ -153,3 +153,37 @@ def build_product_coarse(fx, weights, device="cuda:0"):
     m.load_state_dict({**m.state_dict(), **weights})
     S.fill_coarse_model(m)
     return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# alphamask stage (DVGO)
+# ---------------------------------------------------------------------------------------------------
+DVGO_CASES = ["dvgo_24", "dvgo_40"]
+
+
+def load_dvgo_case(name):
+    return dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+
+
+def dvgo_cotangents(n, S_, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {"etc/alphainv_cum": torch.randn(n, S_ + 1, generator=g), "etc/weights": torch.randn(n, S_, generator=g),
+            "etc/white_bg": torch.randn(n, 1, generator=g), "srgb/raw_rgb": 0.1 * torch.randn(n, S_, 3, generator=g),
+            "srgb/rgb": torch.randn(n, 3, generator=g)}
+
+
+def build_product_dvgo(num_voxels, device="cuda:0"):
+    from esr_nerf_b200.dvgo import DVGO
+
+    m = DVGO(S.dvgo_cfg(device, num_voxels), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX).to(device)
+    S.fill_dvgo_model(m)
+    return m
+
+
+def dvgo_oracle(num_voxels):
+    """(scene, params-with-grad) for oracle/dvgo_port.py on the synthetic alphamask scene"""
+    m = build_product_dvgo(num_voxels, "cpu")
+    scene = dict(xyz_min=S.BBOX_MIN, xyz_max=S.BBOX_MAX, near=S.NEAR, far=S.FAR, n_samples=m.N_samples, stepsize=0.5,
+                 voxel_size=m.voxel_size, act_shift=float(m.act_shift))
+    params = {k: getattr(m, k).detach().clone().requires_grad_(True) for k in ("density", "off_color", "emo_color")}
+    return scene, params
