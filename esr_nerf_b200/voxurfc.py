@@ -150,8 +150,49 @@ class VoxurfC(nn.Module):
             self.last_streams = dict(streams=s, h_w=weights.detach(), rgb=rgb.detach())
         return {"etc/alphainv_cum": last, "etc/white_bg": 1 - wsum[:, :1], "srgb/rgb": rgb_marched}
 
-    def forward_evaluate(self, **kwargs):
-        raise NotImplementedError("VoxurfC.forward_evaluate (voxurfc.py:273-424) is not built yet (SURVEY.md §8a row 8)")
+    @torch.no_grad()
+    def forward_evaluate(self, **kwargs) -> Dict[str, torch.Tensor]:
+        """voxurfc.py:273-424"""
+        rays_o = kwargs["rays_o"].contiguous().float()
+        rays_d = kwargs["rays_d"].contiguous().float()
+        viewdirs = kwargs["viewdirs"].contiguous().float()
+        em_modes = kwargs["em_modes"]
+        N = rays_o.shape[0]
+        dev = rays_o.device
+        pos_rt = kwargs["pos_rt"].to(dev).float()
+        with torch.cuda.device(dev):
+            sc = self._scene(float(self.s_val))
+            for g in (self.sdf, self.off_color, self.emo_color):
+                g.ensure_layout()
+            sdf_grid = self.smooth_conv(self.sdf.grid).contiguous()
+            self.gradient = self.neus_sdf_gradient()
+            s = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, sdf_grid)
+            h_alpha = fused.CoarseAlpha.apply(sdf_grid, sc, rays_o, rays_d, s)
+            if s.m3 <= 1:                                                              # voxurfc.py:322-335
+                z3 = torch.zeros_like(rays_o)
+                return {"etc/depth": z3[..., 0], "etc/disp": 1 / (z3[..., 0] + self.far), "etc/normal": z3,
+                        "etc/white_bg": torch.ones_like(z3[..., :1]), "srgb/off_rgb": z3, "srgb/emo_rgb": z3,
+                        "srgb/on_rgb": z3, "srgb/rgb": z3}
+            ray_id = s.h_ray.long()
+            weights, _ = Alphas2Weights.apply(h_alpha, ray_id, N)
+            x = fused.EncodeCoarse.apply(self.gradient, self.off_color.grid, self.emo_color.grid, sc, rays_o, rays_d,
+                                         viewdirs, s)
+            feat = x[:, 24:69]
+            off = torch.sigmoid(self.off_rgbnet(torch.cat([x[:, 0:12], feat], -1)))
+            emo = torch.sigmoid(self.emo_rgbnet(torch.cat([x[:, 12:24], feat], -1)))
+            normal = ((x[:, 66:69] @ pos_rt) * torch.tensor([1.0, -1.0, -1.0], device=dev) + 1.0) / 2.0
+            dvec = torch.ones(s.m3, 3, device=dev)
+            dvec[:, 0] = s.h_step.float() * float(self.stepsize * self.voxel_size)
+            off_m, emo_m = fused.composite_infer(weights, off, emo, s)
+            on_m, nrm_m = fused.composite_infer(weights, off + emo, normal, s)
+            dw, _ = fused.composite_infer(weights, dvec, dvec, s)                      # (depth, sum w, sum w)
+        depth, bg = dw[:, 0].contiguous(), 1 - dw[:, 1:2]
+        disp = 1 / (depth + bg[..., -1] * self.far)
+        em = int(em_modes) if not torch.is_tensor(em_modes) else int(em_modes.item())
+        if self.keep_streams:
+            self.last_streams = dict(streams=s, h_w=weights)
+        return {"etc/depth": depth, "etc/disp": disp, "etc/normal": nrm_m, "etc/white_bg": bg, "srgb/off_rgb": off_m,
+                "srgb/emo_rgb": emo_m, "srgb/on_rgb": on_m, "srgb/rgb": off_m if em == 0 else on_m}
 
 
 _ = F

@@ -86,6 +86,52 @@ def voxurfc_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     return out, inter
 
 
+def voxurfc_forward_evaluate(scene: Dict, params: Dict, rays_o, rays_d, viewdirs, em_modes, pos_rt, s_val: float):
+    """voxurfc.py:273-424"""
+    from . import ref_harness as H
+
+    N = rays_o.shape[0]
+    ray_pts, ray_id, step_id, _ = P._march(scene, rays_o, rays_d)
+    keep = P.mask_cache(scene, ray_pts)
+    ray_pts, ray_id, step_id = ray_pts[keep], ray_id[keep], step_id[keep]
+    sdf_grid = smooth_conv(params["sdf"], scene["smooth_kernel"])
+    sdf = P.grid_sample_world(sdf_grid, ray_pts, scene["xyz_min"], scene["xyz_max"])[:, 0]
+    gradient = P.grid_sample_world(neus_sdf_gradient(params["sdf"], scene["voxel_size"]), ray_pts, scene["xyz_min"],
+                                   scene["xyz_max"])
+    alpha = P.neus_alpha_interp(ray_id, sdf, s_val)
+    weights = H.alpha2weight(alpha, ray_id, N)[0]
+    k1 = weights > scene["fast_thres"]
+    ray_pts, ray_id, step_id, alpha, gradient = ray_pts[k1], ray_id[k1], step_id[k1], alpha[k1], gradient[k1]
+    if int(k1.sum()) <= 1:                                                              # voxurfc.py:322-335
+        z3 = torch.zeros_like(rays_o)
+        return {"etc/depth": z3[..., 0], "etc/disp": 1 / (z3[..., 0] + scene["far"]), "etc/normal": z3,
+                "etc/white_bg": torch.ones_like(z3[..., :1]), "srgb/off_rgb": z3, "srgb/emo_rgb": z3, "srgb/on_rgb": z3,
+                "srgb/rgb": z3}, dict(m3_ray=ray_id, m3_step=step_id)
+    weights = H.alpha2weight(alpha, ray_id, N)[0]
+    u = (ray_pts - scene["xyz_min"]) / (scene["xyz_max"] - scene["xyz_min"])
+    freq = torch.tensor([2.0 ** i for i in range(5)])
+    emb = (u.unsqueeze(-1) * freq).flatten(-2)
+    vemb = (viewdirs.unsqueeze(-1) * torch.tensor([1.0])).flatten(-2)
+    normal = gradient / (gradient.norm(dim=-1, keepdim=True) + 1e-5)
+    rgb_feat = torch.cat([u, emb.sin(), emb.cos(), vemb[ray_id], vemb.sin()[ray_id], vemb.cos()[ray_id], normal], -1)
+    off_c = P.grid_sample_world(params["off_color"], ray_pts, scene["xyz_min"], scene["xyz_max"])
+    emo_c = P.grid_sample_world(params["emo_color"], ray_pts, scene["xyz_min"], scene["xyz_max"])
+    off = torch.sigmoid(P.mlp(torch.cat([off_c, rgb_feat], -1), params["off_rgbnet"], lambda t: t))
+    emo = torch.sigmoid(P.mlp(torch.cat([emo_c, rgb_feat], -1), params["emo_rgbnet"], lambda t: t))
+    w_ = weights[:, None]
+
+    def comp(x):
+        return torch.zeros(N, x.shape[1]).index_add(0, ray_id, w_ * x)
+
+    nrm = ((normal @ pos_rt) * torch.tensor([1.0, -1.0, -1.0]) + 1.0) / 2.0
+    depth = torch.zeros(N).index_add(0, ray_id, weights * step_id * scene["stepdist"])
+    bg = 1 - comp(torch.ones_like(w_))
+    out = {"etc/depth": depth, "etc/disp": 1 / (depth + bg[..., -1] * scene["far"]), "etc/normal": comp(nrm),
+           "etc/white_bg": bg, "srgb/off_rgb": comp(off), "srgb/emo_rgb": comp(emo), "srgb/on_rgb": comp(off + emo)}
+    out["srgb/rgb"] = out["srgb/off_rgb"] if int(em_modes) == 0 else out["srgb/on_rgb"]
+    return out, dict(m3_ray=ray_id, m3_step=step_id, m3_weights=weights)
+
+
 def params_from_state_dict(sd: Dict[str, torch.Tensor]) -> Dict:
     def net(prefix):
         return [(sd[f"{prefix}.{i}.weight"].float(), sd[f"{prefix}.{i}.bias"].float()) for i in ("0", "2.0", "3")]

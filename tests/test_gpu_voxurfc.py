@@ -82,3 +82,29 @@ def test_coarse_all_rays_miss():
     rays["rays_d"], rays["viewdirs"] = -rays["rays_d"], -rays["viewdirs"]
     out = m(s_val=5.0, **{k: v.to(DEV) for k, v in rays.items()})
     assert (out["etc/alphainv_cum"] == 1).all() and (out["srgb/rgb"] == 0).all() and (out["etc/white_bg"] == 1).all()
+
+
+@pytest.mark.parametrize("em", [0, 1])
+def test_coarse_forward_evaluate_vs_oracle_port(em):
+    """voxurfc.py:273-424: 8 inference maps vs the oracle port (pinned against the reference on the CPU)."""
+    from oracle import voxurfc_port as PC
+
+    fx, weights = C.load_coarse_case("coarse_dense_s25")
+    rays = S.make_rays(700, 77)
+    pos_rt = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(3)))[0]
+    scene = C.coarse_oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    params, _ = C.coarse_oracle_params(scene, weights, requires_grad=False)
+    with torch.no_grad():
+        ref, inter = PC.voxurfc_forward_evaluate(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                                 torch.tensor(em), pos_rt, float(fx["s_val"]))
+    m = C.build_product_coarse(fx, weights, DEV)
+    m.keep_streams = True
+    m.eval()
+    out = m(rays_o=rays["rays_o"].to(DEV), rays_d=rays["rays_d"].to(DEV), viewdirs=rays["viewdirs"].to(DEV),
+            em_modes=torch.tensor(em), pos_rt=pos_rt.to(DEV))
+    assert set(out) == set(ref)
+    st = m.last_streams["streams"]
+    assert torch.equal(st.h_ray.long().cpu(), inter["m3_ray"]) and torch.equal(st.h_step.long().cpu(), inter["m3_step"])
+    for k in ref:
+        assert out[k].shape == ref[k].shape, k
+        assert C.rel_err(out[k], ref[k]) < 1e-4, (k, C.rel_err(out[k], ref[k]))

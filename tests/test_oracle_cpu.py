@@ -213,6 +213,33 @@ def test_coarse_port_matches_reference():
             assert C.rel_err(leaf.grad, ref_grads[name].grad) < 1e-5, name
 
 
+def test_coarse_eval_port_matches_reference():
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import voxurfc_port as PC
+    from oracle.make_golden import build_reference_coarse
+
+    fx, weights = C.load_coarse_case("coarse_sparse_s5")
+    ref = build_reference_coarse(int(fx["num_voxels"]), int(fx["mask_res"]), True, 5.0, weights)
+    ref.eval()
+    rays = S.make_rays(64, 5)
+    pos_rt = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(3)))[0]
+    scene = C.coarse_oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), True)
+    params, _ = C.coarse_oracle_params(scene, weights, requires_grad=False)
+    for em in (0, 1):
+        with torch.no_grad():
+            r = ref(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"], em_modes=torch.tensor(em),
+                    pos_rt=pos_rt)
+            o, _ = PC.voxurfc_forward_evaluate(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                               torch.tensor(em), pos_rt, 5.0)
+        assert set(r) == set(o)
+        for k in r:
+            assert C.rel_err(o[k], r[k]) < 1e-5, k
+
+
 # ---------------------------------------------------------------------------------------------
 # alphamask stage (DVGO): port vs golden vectors and vs the reference itself
 # ---------------------------------------------------------------------------------------------
