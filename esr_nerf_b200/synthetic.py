@@ -71,6 +71,33 @@ def fill_fine_model(model, sdf_noise: float = 0.01) -> None:
         model.emo_color.grid.copy_(color_grid(ws, 6, 3).to(dev))
 
 
+LTS_MODEL_CFG = dict(  # cfg/app/lts.yaml:13-44 (pdra.yaml shares the model block)
+    FINE_MODEL_CFG, brdfnet_width=128, brdfnet_depth=4, env_sg=48, env_activation="softplus", ray_sampling="random",
+    num_2ndrays=256, num_ltspts=100, lts_near=1e-5)
+
+
+def lts_cfg(device="cuda:0", **overrides):
+    model = dict(LTS_MODEL_CFG)
+    model.update(overrides)
+    return SimpleNamespace(system=SimpleNamespace(device=device),
+                           app=SimpleNamespace(model=SimpleNamespace(**model)))
+
+
+def fill_esrnerf_model(model, sdf_noise: float = 0.01) -> None:
+    """Overwrite the grids of a (reference or esr_nerf_b200) ESRNeRF in place with the synthetic scene."""
+    fill_fine_model(model, sdf_noise)
+    ws = [int(w) for w in model.world_size]
+    with torch.no_grad():
+        model.brdf.grid.copy_(color_grid(ws, 6, 4).to(model.brdf.grid.device))
+
+
+def uncert_masks(n: int) -> torch.Tensor:
+    """PDRA batch shape (utils2/utils.py:297-302): the first half of the batch is 'uncertain'"""
+    m = torch.zeros(n, dtype=torch.bool)
+    m[: n // 2] = True
+    return m
+
+
 COARSE_MODEL_CFG = dict(  # cfg/app/coarse.yaml:13-31
     mask_ks=3, maskcache_thres=1e-3, fastcolor_thres=1e-4, stepsize=0.5, num_voxels=96 ** 3, color_dim=12,
     rgbnet_width=128, rgbnet_depth=3, posbase_pe=5, viewbase_pe=1, smooth_ksize=5, smooth_sigma=0.8,

@@ -213,7 +213,100 @@ def main_dvgo():
         print(f"{name}: S={m.N_samples} loss={loss.item():.6f}")
 
 
+# ---------------------------------------------------------------------------------------------------
+# LTS / PDRA stage (ESRNeRF.forward_training, esrnerf.py:681-851)
+# ---------------------------------------------------------------------------------------------------
+ESRNERF_CASES = {
+    # name: (num_voxels, mask_res, sparse, n_rays, s_val, ray_seed, num_2ndrays, num_ltspts, pdra_mode, draw_seed)
+    "lts_sparse_s220": (40 ** 3, 20, True, 128, 220.0, 1234, 16, 12, False, 41),
+    "pdra_sparse_s60": (48 ** 3, 24, True, 160, 60.0, 77, 8, 20, True, 42),
+}
+NORMAL_EPS, EMIT_EPS = 0.01, 0.02
+
+
+def lts_cfg(**over):
+    return H.DictConfig(dict(system=dict(device="cpu"), app=dict(model=dict(S.LTS_MODEL_CFG, **over))))
+
+
+def build_reference_esrnerf(num_voxels, mask_res, sparse, s_val, weights=None, **cfg_over):
+    _, _, _, ESRNeRF = H.reference_classes()
+    torch.manual_seed(0)
+    m = ESRNeRF(lts_cfg(**cfg_over), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(mask_res, sparse), s_val, num_voxels)
+    if weights is not None:
+        m.load_state_dict({**m.state_dict(), **weights})
+    S.fill_esrnerf_model(m)
+    m.train()
+    return m
+
+
+class patched_draws:
+    """Serve the reference's four random draws (np.random.choice, torch.randn, torch.randn_like x2) from a
+    device-independent seeded stream (oracle.esrnerf_port.FixedDraws) while the reference forward runs."""
+
+    def __init__(self, draws):
+        self.d = draws
+
+    def __enter__(self):
+        self.saved = (np.random.choice, torch.randn, torch.randn_like)
+        d = self.d
+        np.random.choice = lambda n, k, replace=False: d.choice(int(n), int(k)).numpy()
+        torch.randn = lambda *shape, device=None, **kw: d.randn(*shape)
+        torch.randn_like = lambda t, **kw: d.randn(*t.shape)
+        return self
+
+    def __exit__(self, *exc):
+        np.random.choice, torch.randn, torch.randn_like = self.saved
+
+
+def esrnerf_cotangents(out, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {k: torch.randn(out[k].shape, generator=g) for k in sorted(out)}
+
+
+def run_esrnerf_case(name, spec, weights):
+    from oracle import esrnerf_port as E
+
+    num_voxels, mask_res, sparse, n, s_val, seed, n2, npts, pdra, dseed = spec
+    m = build_reference_esrnerf(num_voxels, mask_res, sparse, s_val, weights, num_2ndrays=n2, num_ltspts=npts)
+    m.pdra_mode = pdra
+    rays = S.make_rays(n, seed)
+    with patched_draws(E.FixedDraws(dseed)):
+        out = m(s_val=s_val, rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+                em_modes=rays["em_modes"], uncert_masks=S.uncert_masks(n), normal_eps=NORMAL_EPS, emit_eps=EMIT_EPS)
+    cot = esrnerf_cotangents(out)
+    loss = sum((out[k] * cot[k]).sum() for k in cot)
+    loss.backward()
+    fx = dict(num_voxels=num_voxels, mask_res=mask_res, sparse=int(sparse), n_rays=n, s_val=s_val, ray_seed=seed,
+              num_2ndrays=n2, num_ltspts=npts, pdra_mode=int(pdra), draw_seed=dseed, normal_eps=NORMAL_EPS,
+              emit_eps=EMIT_EPS, loss=loss.item())
+    for k, v in out.items():
+        fx["out/" + k] = v.detach().numpy()
+    for pname, p in m.named_parameters():
+        if p.grad is not None:
+            fx.update(grad_digest(pname, p.grad))
+    np.savez_compressed(os.path.join(GOLDEN, f"esrnerf_{name}.npz"), **fx)
+    print(f"{name}: m3={out['etc/emit'].shape[0]} loss={loss.item():.6f}")
+
+
+def main_esrnerf():
+    fine = dict(np.load(os.path.join(GOLDEN, "fine_weights.npz")))
+    m = build_reference_esrnerf(40 ** 3, 20, True, 220.0)
+    sd = m.state_dict()
+    weights = {k: sd[k].clone() for k in sd if ("emitnet" in k or "brdfnet" in k or "envmap" in k)}
+    g = torch.Generator().manual_seed(13)
+    for k in weights:  # the reference zero-initialises the last biases; give every bias a non-trivial value
+        if k.endswith("bias"):
+            weights[k] = weights[k] + 0.05 * torch.randn(weights[k].shape, generator=g)
+    np.savez_compressed(os.path.join(GOLDEN, "lts_weights.npz"), **{k: v.numpy() for k, v in weights.items()})
+    weights.update({k: torch.from_numpy(v) for k, v in fine.items()})
+    for name, spec in ESRNERF_CASES.items():
+        run_esrnerf_case(name, spec, weights)
+
+
 def main():
+    if "--esrnerf-only" in sys.argv:
+        return main_esrnerf()
     if not H.reference_available():
         raise SystemExit("reference tree not available; golden vectors can only be generated in the build container")
     os.makedirs(GOLDEN, exist_ok=True)
@@ -234,6 +327,7 @@ def main():
             run_case(name, spec, weights)
     main_coarse()
     main_dvgo()
+    main_esrnerf()
 
 
 if __name__ == "__main__":

@@ -76,8 +76,9 @@ class _A2W(torch.autograd.Function):
         return H.alpha2weight_backward(alpha, w, T, last, i_s, i_e, ctx.n, gw.contiguous(), gl.contiguous()), None, None
 
 
-def sdf_feature_taps(scene: Dict, sdf_grid: torch.Tensor, xyz: torch.Tensor, displace):
-    """voxurff.py:678-721: 6 axis taps (z-,z+,y-,y+,x-,x+) x K displacements, FD gradient, normals."""
+def sdf_feature_taps(scene: Dict, sdf_grid: torch.Tensor, xyz: torch.Tensor, displace, fd_eps: float = 0.0):
+    """voxurff.py:678-721: 6 axis taps (z-,z+,y-,y+,x-,x+) x K displacements, FD gradient, normals.
+    fd_eps = 1e-12 gives the ESRNeRF variant (esrnerf.py:1560)."""
     M = xyz.shape[0]
     K = len(displace)
     size_zyx = torch.tensor([sdf_grid.shape[4], sdf_grid.shape[3], sdf_grid.shape[2]], dtype=torch.float32)
@@ -93,6 +94,8 @@ def sdf_feature_taps(scene: Dict, sdf_grid: torch.Tensor, xyz: torch.Tensor, dis
     feat = feat.reshape(M, 6, K)
     taps = taps.reshape(M, 6, K, 3)
     diff = (taps[:, 1::2] - taps[:, 0::2]).max(dim=-1).values  # [M,3,K]
+    if fd_eps:
+        diff = diff + fd_eps
     grad = (feat[:, 1::2] - feat[:, 0::2]) / diff / scene["voxel_size"]
     normal = F.normalize(grad, dim=1)
     return feat.reshape(M, 6 * K), grad.reshape(M, 3 * K), normal.reshape(M, 3 * K)

@@ -187,3 +187,66 @@ def dvgo_oracle(num_voxels):
                  voxel_size=m.voxel_size, act_shift=float(m.act_shift))
     params = {k: getattr(m, k).detach().clone().requires_grad_(True) for k in ("density", "off_color", "emo_color")}
     return scene, params
+
+
+# ---------------------------------------------------------------------------------------------------
+# LTS / PDRA stage (ESRNeRF)
+# ---------------------------------------------------------------------------------------------------
+ESRNERF_CASES = ["lts_sparse_s220", "pdra_sparse_s60"]
+
+
+def load_esrnerf_case(name):
+    fx = dict(np.load(os.path.join(GOLDEN, f"esrnerf_{name}.npz")))
+    w = dict(np.load(os.path.join(GOLDEN, "fine_weights.npz")))
+    w.update(np.load(os.path.join(GOLDEN, "lts_weights.npz")))
+    return fx, {k: torch.from_numpy(v) for k, v in w.items()}
+
+
+def esrnerf_oracle_scene(fx):
+    scene = oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    scene.update(num_2ndrays=int(fx["num_2ndrays"]), num_ltspts=int(fx["num_ltspts"]), lts_near=1e-5)
+    return scene
+
+
+def esrnerf_oracle_params(scene, weights, requires_grad=True):
+    from oracle import esrnerf_port as E
+
+    ws = scene["world_size"]
+    sd = dict(weights)
+    sd["sdf.grid"] = S.sphere_sdf(ws)
+    sd["off_color.grid"] = S.color_grid(ws, 6, 2)
+    sd["emo_color.grid"] = S.color_grid(ws, 6, 3)
+    sd["brdf.grid"] = S.color_grid(ws, 6, 4)
+    leaves = {k: v.clone().float().requires_grad_(requires_grad) for k, v in sd.items()}
+    return E.params_from_state_dict(leaves), leaves
+
+
+def esrnerf_cotangents(out, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {k: torch.randn(out[k].shape, generator=g) for k in sorted(out)}
+
+
+def run_esrnerf_port(fx, weights, draws=None):
+    from oracle import esrnerf_port as E
+
+    scene = esrnerf_oracle_scene(fx)
+    params, leaves = esrnerf_oracle_params(scene, weights)
+    n = int(fx["n_rays"])
+    rays = S.make_rays(n, int(fx["ray_seed"]))
+    out, inter = E.esrnerf_forward_training(
+        scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"], rays["em_modes"], S.uncert_masks(n),
+        float(fx["s_val"]), float(fx["normal_eps"]), float(fx["emit_eps"]), bool(fx["pdra_mode"]),
+        draws or E.FixedDraws(int(fx["draw_seed"])))
+    return out, inter, leaves, rays
+
+
+def build_product_esrnerf(fx, weights, device="cuda:0"):
+    from esr_nerf_b200.esrnerf import ESRNeRF
+
+    cfg = S.lts_cfg(device=device, num_2ndrays=int(fx["num_2ndrays"]), num_ltspts=int(fx["num_ltspts"]))
+    m = ESRNeRF(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                S.mask_density(int(fx["mask_res"]), bool(fx["sparse"])), float(fx["s_val"]), int(fx["num_voxels"]))
+    m.load_state_dict({**m.state_dict(), **weights})
+    S.fill_esrnerf_model(m)
+    m.pdra_mode = bool(fx["pdra_mode"])
+    return m

@@ -1,0 +1,69 @@
+"""CPU suite for the LTS / PDRA stage oracle: oracle/esrnerf_port.py (the travelling restatement of
+ESRNeRF.forward_training, esrnerf.py:487-851) against the golden vectors made by the reference's own class, and —
+when /root/reference is present — against the reference class itself with the reference's own RNG calls."""
+import numpy as np
+import pytest
+import torch
+
+import esr_testlib as C
+
+
+@pytest.mark.parametrize("case", C.ESRNERF_CASES)
+def test_esrnerf_port_matches_golden(case):
+    fx, weights = C.load_esrnerf_case(case)
+    out, inter, leaves, _ = C.run_esrnerf_port(fx, weights)
+    assert set(out) == {k[4:] for k in fx if k.startswith("out/")}
+    for k in out:
+        assert tuple(out[k].shape) == fx["out/" + k].shape, k            # same shaded-sample count: streams match
+        assert C.rel_err(out[k], torch.from_numpy(fx["out/" + k])) < 1e-5, k
+    cot = C.esrnerf_cotangents(out)
+    loss = sum((out[k] * cot[k]).sum() for k in cot)
+    loss.backward()
+    assert abs(loss.item() - float(fx["loss"])) < 1e-4 * max(1.0, abs(float(fx["loss"])))
+    checked = 0
+    for name, leaf in leaves.items():
+        if f"grad/{name}/idx" in fx:
+            assert leaf.grad is not None, name
+            err, s_err = C.digest_check(fx, name, leaf.grad, rtol=1e-4)
+            assert err < 1.0 and s_err < 1e-4, (name, err, s_err)
+            checked += 1
+    assert checked >= 40        # 5 grids/nets x layers + envmap: every parameter of the stage receives a gradient
+
+
+def test_esrnerf_port_matches_reference():
+    """same weights, rays and RNG state: the port draws with the reference's own calls (np.random.choice,
+    torch.randn) in the reference's order, so outputs agree to rounding"""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box): golden vectors stand in")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import esrnerf_port as E
+    from oracle.make_golden import build_reference_esrnerf
+
+    fx, weights = C.load_esrnerf_case("pdra_sparse_s60")
+    n, s_val = 96, 35.0
+    ref = build_reference_esrnerf(int(fx["num_voxels"]), int(fx["mask_res"]), True, s_val, weights, num_2ndrays=8,
+                                  num_ltspts=16)
+    ref.pdra_mode = True
+    rays = S.make_rays(n, 4242)          # rays the fixtures have never seen
+    um = S.uncert_masks(n)
+    np.random.seed(5)
+    torch.manual_seed(11)
+    ref_out = ref(s_val=s_val, rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+                  em_modes=rays["em_modes"], uncert_masks=um, normal_eps=0.01, emit_eps=0.03)
+    scene = C.esrnerf_oracle_scene(dict(fx, num_2ndrays=8, num_ltspts=16))
+    params, leaves = C.esrnerf_oracle_params(scene, weights)
+    np.random.seed(5)
+    torch.manual_seed(11)
+    out, _ = E.esrnerf_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                        rays["em_modes"], um, s_val, 0.01, 0.03, True, E.Draws())
+    cot = C.esrnerf_cotangents(out)
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    assert set(out) == set(ref_out)
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    for name, p in ref.named_parameters():
+        if p.grad is not None:
+            assert C.rel_err(leaves[name].grad, p.grad) < 1e-5, name
