@@ -2,6 +2,7 @@
 render-function signatures.  See DESIGN.md / INTEGRATION.md.
 
 Public surface (mirrors the reference names):
+    ESRNeRF                               <- app.fine.model.ESRNeRF   (LTS / PDRA stages; forward_training)
     VoxurfF                               <- app.fine.model.VoxurfF
     VoxurfC                               <- app.coarse.model.VoxurfC
     DVGO                                  <- app.coarse.model.DVGO
@@ -18,13 +19,16 @@ def __getattr__(name):  # lazy: importing the package must work on a box without
     if name == "VoxurfF":
         from .voxurff import VoxurfF
         return VoxurfF
+    if name == "ESRNeRF":
+        from .esrnerf import ESRNeRF
+        return ESRNeRF
     if name == "DVGO":
         from .dvgo import DVGO
         return DVGO
     if name == "VoxurfC":
         from .voxurfc import VoxurfC
         return VoxurfC
-    if name in ("render_utils", "fused", "modules", "synthetic", "voxurff", "voxurfc", "dvgo", "dist"):
+    if name in ("render_utils", "fused", "modules", "synthetic", "voxurff", "voxurfc", "dvgo", "dist", "esrnerf", "pbr"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -17,7 +17,7 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
-SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu"]
+SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -86,6 +86,7 @@ class Scene(ctypes.Structure):
         ("stepdist", ctypes.c_float), ("voxel_size", ctypes.c_float),
         ("act_shift", ctypes.c_float), ("mask_thres", ctypes.c_float),
         ("fast_thres", ctypes.c_float), ("s_val", ctypes.c_float), ("alpha_thres", ctypes.c_float),
+        ("fd_eps", ctypes.c_float), ("sdf_tap_manual", ctypes.c_int32),
     ]
 
 
@@ -139,6 +140,11 @@ PROTOTYPES = {
     "esr_encode_coarse_bwd": (I32, [SCENE_P, P, P, P, P, P, I64, P, P, P, P, P]),
     "esr_encode_fwd": (I32, [SCENE_P, P, P, P, P, P, P, I32, P, P, P, I64, P, I32, P]),
     "esr_encode_bwd": (I32, [SCENE_P, P, P, P, I32, P, P, I64, P, P, P, P, P]),
+    "esr_encode_pbr_fwd": (I32, [SCENE_P, P, P, P, P, P, P, P, I32, P, P, P, P, I64, P, P, I32, P]),
+    "esr_encode_pbr_bwd": (I32, [SCENE_P, P, P, P, I32, P, P, P, I64, P, P, P, P, P, P, P]),
+    "esr_sample_points": (I32, [SCENE_P, P, P, P, P, I64, P, P]),
+    "esr_sdf_expgrad_fwd": (I32, [SCENE_P, P, P, I64, I32, P, P, P]),
+    "esr_sdf_expgrad_bwd": (I32, [SCENE_P, P, I64, P, P, P, P]),
     "esr_sdf_fd_gradient": (I32, [SCENE_P, P, P, P, P, P, I64, P, P]),
     "esr_tonemap_encode_fwd": (I32, [P, P, P, P, I64, P, P, I32, P]),
     "esr_tonemap_encode_bwd": (I32, [P, P, P, I64, P, P]),

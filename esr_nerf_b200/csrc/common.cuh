@@ -203,6 +203,27 @@ ESR_D float tap1_world(const float *__restrict__ g, int X, int Y, int Z, const f
   return tap1(g, X, Y, Z, c);
 }
 
+// differentiable_grid_sample arithmetic (functions.py:142-309, reached through esrnerf.py:1572-1596): the same 8
+// weights, corner indices CLAMPED to the grid instead of zero padding, and value * weight products summed with
+// separately rounded torch ops (no FMA), in the order tnw .. bse.
+ESR_D int clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+ESR_D float tap1_manual(const float *__restrict__ g, int X, int Y, int Z, const Cell &c) {
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int x = clampi(c.x0 + (k >> 2), X - 1), y = clampi(c.y0 + ((k >> 1) & 1), Y - 1), z = clampi(c.z0 + (k & 1), Z - 1);
+    const float term = __fmul_rn(__ldg(g + ((int64_t)x * Y + y) * Z + z), c.w[k]);
+    acc = k == 0 ? term : __fadd_rn(acc, term);
+  }
+  return acc;
+}
+ESR_D float tap1_manual_world(const float *__restrict__ g, int X, int Y, int Z, const float *mn, const float *mx,
+                              float px, float py, float pz) {
+  const Cell c = make_cell(world_to_index(px, mn[0], mx[0], X), world_to_index(py, mn[1], mx[1], Y),
+                           world_to_index(pz, mn[2], mx[2], Z));
+  return tap1_manual(g, X, Y, Z, c);
+}
+
 // scatter-add v * w[k] into a scalar-channel gradient volume
 ESR_D void scatter1(float *__restrict__ g, int X, int Y, int Z, const Cell &c, float v) {
 #pragma unroll

@@ -165,6 +165,14 @@ struct RowWriter<float> {
 #pragma unroll
     for (int i = 0; i < N; i += 2) *reinterpret_cast<float2 *>(row + col0 + i) = make_float2(v[i], v[i + 1]);
   }
+  // second copy of the finished row with colour slot 0 replaced
+  ESR_D void second(float *b, int64_t r, const float (&col)[6]) {
+    float *dst = b + r * ESR_FEAT_DIM;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i] = col[i];
+#pragma unroll
+    for (int i = 6; i < ESR_FEAT_DIM; i += 2) *reinterpret_cast<float2 *>(dst + i) = *reinterpret_cast<const float2 *>(row + i);
+  }
 };
 // bf16 rows go to the MLP kernels in the TILED layout of mlp_layout.cuh ([tile][chunk][128 rows][8]): the row is
 // assembled in registers (all column indices are compile-time after unrolling) and flushed as 16-byte chunks, which
@@ -193,7 +201,27 @@ struct RowWriter<__nv_bfloat16> : TiledRowWriter<ESR_FEAT_DIM> {
   int64_t row;
   ESR_D RowWriter(__nv_bfloat16 *b, int64_t r) : base(b), row(r) {}
   ESR_D void finish() { flush(base, row); }
+  ESR_D void second(__nv_bfloat16 *b, int64_t r, const float (&col)[6]) {
+    put(0, col);
+    flush(b, r);
+  }
 };
+
+// world position + ray index of stream sample j: recomputed from (ray, step) exactly as the march kernel does, or
+// read from an explicit point list (LTS points, jittered points: esrnerf.py:795-830); with explicit points h_ray is
+// optional (row j looks up view direction j)
+ESR_D int sample_pos(const esr_scene_t &sc, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                     const float *__restrict__ pts, const int32_t *__restrict__ h_ray,
+                     const int32_t *__restrict__ h_step, int64_t j, float &px, float &py, float &pz) {
+  const int r = h_ray ? h_ray[j] : (int)j;
+  if (pts) {
+    px = __ldg(pts + 3 * j), py = __ldg(pts + 3 * j + 1), pz = __ldg(pts + 3 * j + 2);
+  } else {
+    const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
+    ray_point(s, sc.stepdist, h_step[j], px, py, pz);
+  }
+  return r;
+}
 
 constexpr int COL_SDF = 12, COL_FEAT = 13, COL_NRM = 37, COL_XYZ = 49, COL_SIN = 52, COL_COS = 67, COL_VIEW = 82;
 
@@ -204,14 +232,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
                  const float *__restrict__ sdf_grid, const float *__restrict__ off_grid,
                  const float *__restrict__ emo_grid, const int32_t *__restrict__ h_ray,
                  const int32_t *__restrict__ h_step, const float *__restrict__ h_sdf, int64_t m3,
-                 OutT *__restrict__ feat) {
+                 OutT *__restrict__ feat, const float *__restrict__ pts, const float *__restrict__ third_grid,
+                 OutT *__restrict__ feat2) {
   __shared__ float s_lines[N_LINES * ENC_THREADS];
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m3) return;
-  const int r = h_ray[j];
-  const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
   float px, py, pz;
-  ray_point(s, sc.stepdist, h_step[j], px, py, pz);
+  const int r = sample_pos(sc, rays_o, rays_d, pts, h_ray, h_step, j, px, py, pz);
   TapGeom g;
   g.ix = world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx);
   g.iy = world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy);
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
       float gr[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const float diff = __fsub_rn(coord[(2 * a + 1) * 4 + k], coord[(2 * a) * 4 + k]);
+        const float diff = __fadd_rn(__fsub_rn(coord[(2 * a + 1) * 4 + k], coord[(2 * a) * 4 + k]), sc.fd_eps);
         const float fd = __fsub_rn(v[1 + (2 * a + 1) * 4 + k], v[1 + (2 * a) * 4 + k]);
         gr[a] = __fdiv_rn(__fdiv_rn(fd, diff), sc.voxel_size);
       }
@@ -283,6 +310,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
     wr.put(COL_VIEW, v);
   }
   wr.finish();
+  if (third_grid) {  // same row with colour slot 0 taken from a third grid (BRDF grid, esrnerf.py:761-763)
+    const Cell c = make_cell(g.ix, g.iy, g.iz);
+    float col[6];
+    tapC<6>(third_grid, sc.gx, sc.gy, sc.gz, c, col);
+    wr.second(feat2, j, col);
+  }
 }
 
 __global__ void __launch_bounds__(ENC_THREADS, 5)
@@ -290,14 +323,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
                  const float *__restrict__ rays_d, const float *__restrict__ sdf_grid,
                  const int32_t *__restrict__ h_ray, const int32_t *__restrict__ h_step, int64_t m3,
                  const float *__restrict__ d_feat, float *__restrict__ g_sdf, float *__restrict__ g_off,
-                 float *__restrict__ g_emo) {
+                 float *__restrict__ g_emo, const float *__restrict__ pts, const float *__restrict__ d_third,
+                 float *__restrict__ g_third) {
   __shared__ float s_lines[N_LINES * ENC_THREADS], s_dl[N_LINES * ENC_THREADS];
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m3) return;
-  const int r = h_ray[j];
-  const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
   float px, py, pz;
-  ray_point(s, sc.stepdist, h_step[j], px, py, pz);
+  sample_pos(sc, rays_o, rays_d, pts, h_ray, h_step, j, px, py, pz);
   TapGeom g;
   g.ix = world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx);
   g.iy = world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy);
@@ -318,6 +350,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
     if (g_off && any_off) scatterC<6>(g_off, sc.gx, sc.gy, sc.gz, c, dv);
     if (g_emo && any_emo) scatterC<6>(g_emo, sc.gx, sc.gy, sc.gz, c, dv + 6);
     if (dv[COL_SDF] != 0.f) scatter1(g_sdf, sc.gx, sc.gy, sc.gz, c, dv[COL_SDF]);
+    if (g_third) {  // cotangent of the third (BRDF) grid's colour slot: [m3,6] f32
+      float d3[6];
+#pragma unroll
+      for (int i = 0; i < 6; i += 2) {
+        const float2 q = __ldg(reinterpret_cast<const float2 *>(d_third + j * 6 + i));
+        d3[i] = q.x, d3[i + 1] = q.y;
+      }
+      scatterC<6>(g_third, sc.gx, sc.gy, sc.gz, c, d3);
+    }
   }
   const float disp[4] = {0.5f, 1.0f, 1.5f, 2.0f};
   const SdfFrame fr = make_frame(sc, g.ix, g.iy, g.iz);
@@ -337,7 +378,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
     float gr[3], scale[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const float diff = tr[2 * a + 1].coord - tr[2 * a].coord;
+      const float diff = tr[2 * a + 1].coord - tr[2 * a].coord + sc.fd_eps;
       scale[a] = 1.f / diff / sc.voxel_size;
       gr[a] = (f[2 * a + 1] - f[2 * a]) * scale[a];
     }
@@ -636,43 +677,86 @@ static int check_scene2(const esr_scene_t *sc) {
   return ESR_OK;
 }
 
-extern "C" int esr_encode_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
-                              const float *sdf_grid, const float *off_color_grid, const float *emo_color_grid,
-                              int color_dim, const int32_t *h_ray, const int32_t *h_step, const float *h_sdf,
-                              int64_t m3, void *feat, int out_is_bf16, esr_stream_t stream) {
+static int encode_fwd_impl(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                           const float *sdf_grid, const float *off_color_grid, const float *emo_color_grid,
+                           const float *third_grid, int color_dim, const float *pts, const int32_t *h_ray,
+                           const int32_t *h_step, const float *h_sdf, int64_t m3, void *feat, void *feat2,
+                           int out_is_bf16, esr_stream_t stream) {
   if (int e = check_scene2(sc)) return e;
   ESR_CHECK_ARG(color_dim == 6);  // cfg/app/fine.yaml:20; other widths are not instantiated
   ESR_CHECK_ARG(m3 >= 0);
   if (m3 == 0) return ESR_OK;
-  ESR_CHECK_ARG(rays_o && rays_d && viewdirs && sdf_grid && off_color_grid && emo_color_grid && h_ray && h_step &&
-                h_sdf && feat);
+  ESR_CHECK_ARG(viewdirs && sdf_grid && off_color_grid && emo_color_grid && h_sdf && feat);
+  ESR_CHECK_ARG(pts || (rays_o && rays_d && h_ray && h_step));
+  ESR_CHECK_ARG(!third_grid == !feat2);
   cudaStream_t st = (cudaStream_t)stream;
   ESR_STAGE("k_encode_fwd", st);
   if (out_is_bf16)
     k_encode_fwd<__nv_bfloat16><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,
                                                                emo_color_grid, h_ray, h_step, h_sdf, m3,
-                                                               (__nv_bfloat16 *)feat);
+                                                               (__nv_bfloat16 *)feat, pts, third_grid,
+                                                               (__nv_bfloat16 *)feat2);
   else
     k_encode_fwd<float><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,
-                                                       emo_color_grid, h_ray, h_step, h_sdf, m3, (float *)feat);
+                                                       emo_color_grid, h_ray, h_step, h_sdf, m3, (float *)feat, pts,
+                                                       third_grid, (float *)feat2);
   ESR_LAUNCH_OK();
   return ESR_OK;
+}
+
+static int encode_bwd_impl(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *sdf_grid,
+                           int color_dim, const float *pts, const int32_t *h_ray, const int32_t *h_step, int64_t m3,
+                           const float *d_feat, const float *d_third, float *grad_sdf_grid, float *grad_off_grid,
+                           float *grad_emo_grid, float *grad_third_grid, esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(color_dim == 6);
+  ESR_CHECK_ARG(m3 >= 0);
+  if (m3 == 0) return ESR_OK;
+  ESR_CHECK_ARG(sdf_grid && d_feat && grad_sdf_grid);
+  ESR_CHECK_ARG(pts || (rays_o && rays_d && h_ray && h_step));
+  ESR_CHECK_ARG(!d_third == !grad_third_grid);
+  ESR_STAGE("k_encode_bwd", (cudaStream_t)stream);
+  k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
+                                                                d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
+                                                                pts, d_third, grad_third_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_encode_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                              const float *sdf_grid, const float *off_color_grid, const float *emo_color_grid,
+                              int color_dim, const int32_t *h_ray, const int32_t *h_step, const float *h_sdf,
+                              int64_t m3, void *feat, int out_is_bf16, esr_stream_t stream) {
+  ESR_CHECK_ARG(m3 == 0 || (rays_o && rays_d && h_ray && h_step));
+  return encode_fwd_impl(sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid, emo_color_grid, nullptr, color_dim,
+                         nullptr, h_ray, h_step, h_sdf, m3, feat, nullptr, out_is_bf16, stream);
 }
 
 extern "C" int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *sdf_grid,
                               int color_dim, const int32_t *h_ray, const int32_t *h_step, int64_t m3,
                               const float *d_feat, float *grad_sdf_grid, float *grad_off_grid, float *grad_emo_grid,
                               esr_stream_t stream) {
-  if (int e = check_scene2(sc)) return e;
-  ESR_CHECK_ARG(color_dim == 6);
-  ESR_CHECK_ARG(m3 >= 0);
-  if (m3 == 0) return ESR_OK;
-  ESR_CHECK_ARG(rays_o && rays_d && sdf_grid && h_ray && h_step && d_feat && grad_sdf_grid);
-  ESR_STAGE("k_encode_bwd", (cudaStream_t)stream);
-  k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
-                                                                d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid);
-  ESR_LAUNCH_OK();
-  return ESR_OK;
+  ESR_CHECK_ARG(m3 == 0 || (rays_o && rays_d && h_ray && h_step));
+  return encode_bwd_impl(sc, rays_o, rays_d, sdf_grid, color_dim, nullptr, h_ray, h_step, m3, d_feat, nullptr,
+                         grad_sdf_grid, grad_off_grid, grad_emo_grid, nullptr, stream);
+}
+
+extern "C" int esr_encode_pbr_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                  const float *viewdirs, const float *sdf_grid, const float *off_color_grid,
+                                  const float *emo_color_grid, const float *brdf_grid, int color_dim, const float *pts,
+                                  const int32_t *h_ray, const int32_t *h_step, const float *h_sdf, int64_t m3,
+                                  void *feat, void *feat_brdf, int out_is_bf16, esr_stream_t stream) {
+  return encode_fwd_impl(sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid, emo_color_grid, brdf_grid, color_dim,
+                         pts, h_ray, h_step, h_sdf, m3, feat, feat_brdf, out_is_bf16, stream);
+}
+
+extern "C" int esr_encode_pbr_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                  const float *sdf_grid, int color_dim, const float *pts, const int32_t *h_ray,
+                                  const int32_t *h_step, int64_t m3, const float *d_feat, const float *d_brdf_color,
+                                  float *grad_sdf_grid, float *grad_off_grid, float *grad_emo_grid,
+                                  float *grad_brdf_grid, esr_stream_t stream) {
+  return encode_bwd_impl(sc, rays_o, rays_d, sdf_grid, color_dim, pts, h_ray, h_step, m3, d_feat, d_brdf_color,
+                         grad_sdf_grid, grad_off_grid, grad_emo_grid, grad_brdf_grid, stream);
 }
 
 extern "C" int esr_encode_coarse_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,

@@ -39,7 +39,7 @@ static int check_desc(const esr_mlp_desc_t *d) {
     return ESR_ERR_BAD_ARG;
   }
   ESR_CHECK_ARG(d->k0 % 16 == 0 && d->k0 > 0 && d->width % 64 == 0 && d->n_hidden >= 1);
-  ESR_CHECK_ARG(d->n_out >= 1 && d->n_out <= 3 && (d->act == 1 || d->act == 2));
+  ESR_CHECK_ARG(d->n_out >= 1 && d->n_out <= 8 && (d->act == 1 || d->act == 2));
   return ESR_OK;
 }
 

@@ -261,7 +261,8 @@ struct EpiThread {
       : row_in_tile(32 * (warp & 3) + lane), grp(warp >> 2), lane_base((32u * (warp & 3)) << 16) {}
 };
 
-template <int K0, int NH>
+// NO = compile-time bound on the real output columns (3: radiance / tone-map / emission nets, 8: the 5-output BRDF net)
+template <int K0, int NH, int NO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_fwd_tc(const uint8_t *__restrict__ image, const __nv_bfloat16 *__restrict__ x, int64_t row_begin,
                  int64_t row_end, int64_t m_total, float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden,
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (valid) {
           const float *bo = sbias + NH * TC_W;
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < NO; ++c)
             if (c < n_out) y[row * n_out + c] = act_fwd(__uint_as_float(r[c]) + bo[c], act);
         }
       }
@@ -419,7 +420,7 @@ struct BwdSm {
   static constexpr int bytes = bar + 16;
 };
 
-template <int K0, int NH, int DXN>
+template <int K0, int NH, int DXN, int NO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_dgrad_tc(const uint8_t *__restrict__ image_bwd, const float *__restrict__ y, const float *__restrict__ d_y,
                    int64_t row_begin, int64_t row_end, int64_t m_total, const __nv_bfloat16 *__restrict__ hidden,
@@ -457,13 +458,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   // Per-tile global inputs (output cotangent, ReLU masks of every layer) are requested one tile ahead so their
   // latency hides behind the current tile's chain.
-  float pf_y[3], pf_dy[3];
+  float pf_y[NO], pf_dy[NO];
   uint2 pf_mask[NH];
   auto prefetch = [&](int64_t tile) {
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool ok = is_epi && tile < n_tiles && row < row_end;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < NO; ++c) {
       const bool okc = ok && et.grp == 0 && c < n_out;
       pf_y[c] = okc ? __ldg(y + row * n_out + c) : 0.f;
       pf_dy[c] = okc ? __ldg(d_y + row * n_out + c) : 0.f;
@@ -482,20 +483,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int l = 0; l < NH; ++l) cur_mask[l] = pf_mask[l];
     // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column group 0 threads) ----
     if (is_epi && et.grp == 0) {
-      float dz[3] = {0.f, 0.f, 0.f};
+      float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < NO; ++c)
           if (c < n_out) {
             const float yy = pf_y[c];
             dz[c] = pf_dy[c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
           }
         if (d_z_out) {
-          *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], 0.f);
-          *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+          *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
         }
       }
-      const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
+      const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
       if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
         uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
         zo[tiled_chunk_index(row, 0, 2)] = dz16;
@@ -806,10 +807,10 @@ static unsigned tc_grid(int64_t rows) {
   return (unsigned)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
 }
 
-template <int K0, int NH>
+template <int K0, int NH, int NO>
 static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t rb, int64_t re, int64_t mt,
                       float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
-  auto kern = k_mlp_fwd_tc<K0, NH>;
+  auto kern = k_mlp_fwd_tc<K0, NH, NO>;
   constexpr int bytes = FwdSm<K0, NH>::bytes;
   if (int e = set_smem_tc(kern, bytes)) return e;
   ESR_STAGE(K0 == 96 ? "k_mlp_fwd_tc_radiance" : "k_mlp_fwd_tc_tonemap", st);
@@ -819,11 +820,11 @@ static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x,
   return ESR_OK;
 }
 
-template <int K0, int NH, int DXN>
+template <int K0, int NH, int DXN, int NO>
 static int launch_dgrad(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const float *y, const float *d_y,
                         int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z, float *d_z_out, float *d_x,
                         int dx_cols, int accumulate, cudaStream_t st) {
-  auto kern = k_mlp_dgrad_tc<K0, NH, DXN>;
+  auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO>;
   constexpr int bytes = BwdSm<K0, NH, DXN>::bytes;
   if (int e = set_smem_tc(kern, bytes)) return e;
   ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_tc_radiance" : "k_mlp_dgrad_tc_tonemap", st);
@@ -859,10 +860,12 @@ int tc_pack(const esr_mlp_desc_t *d, const float *flat_params, void *tc_image, c
 
 int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t row_begin, int64_t row_end,
            int64_t m_total, float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
+  if (d->k0 == 96 && d->n_hidden == 3 && d->n_out <= 3)
+    return launch_fwd<96, 3, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
   if (d->k0 == 96 && d->n_hidden == 3)
-    return launch_fwd<96, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
+    return launch_fwd<96, 3, 8>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
   if (d->k0 == 48 && d->n_hidden == 1)
-    return launch_fwd<48, 1>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
+    return launch_fwd<48, 1, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
   set_error("tc_fwd: shape not instantiated");
   return ESR_ERR_BAD_ARG;
 }
@@ -871,12 +874,15 @@ int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, cons
              int64_t row_end, int64_t m_total, const void *hidden, void *d_z, float *d_z_out, float *d_x, int dx_cols,
              int accumulate, cudaStream_t st) {
   const TcLayout T = tc_layout(d);
+  if (d->k0 == 96 && d->n_hidden == 3 && d->n_out <= 3)
+    return launch_dgrad<96, 3, 64, 3>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
+                                      dx_cols, accumulate, st);
   if (d->k0 == 96 && d->n_hidden == 3)
-    return launch_dgrad<96, 3, 64>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
-                                   dx_cols, accumulate, st);
+    return launch_dgrad<96, 3, 64, 8>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
+                                      dx_cols, accumulate, st);
   if (d->k0 == 48 && d->n_hidden == 1)
-    return launch_dgrad<48, 1, 48>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
-                                   dx_cols, accumulate, st);
+    return launch_dgrad<48, 1, 48, 3>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
+                                      dx_cols, accumulate, st);
   set_error("tc_dgrad: shape not instantiated");
   return ESR_ERR_BAD_ARG;
 }

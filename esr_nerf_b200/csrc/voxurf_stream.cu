@@ -45,7 +45,9 @@ __global__ void __launch_bounds__(256)
           const int pos = base + c_mask + __popc(bal & lt);
           s_ray[pos] = r;
           s_step[pos] = k;
-          s_sdf[pos] = tap1_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz);
+          s_sdf[pos] = sc.sdf_tap_manual
+                           ? tap1_manual_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz)
+                           : tap1_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz);
         }
       } else {
         c_in += __popc(__ballot_sync(FULL, inb));

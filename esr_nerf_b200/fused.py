@@ -31,7 +31,8 @@ TONEMAP_DESC = dict(k0=48, width=192, n_hidden=1, n_out=3, act=2)    # pbr/modul
 
 
 def make_scene(xyz_min, xyz_max, grid_size, mask_xyz_min, mask_xyz_max, mask_size, near, far, stepdist,
-               voxel_size, act_shift, mask_thres, fast_thres, s_val, alpha_thres=None) -> Scene:
+               voxel_size, act_shift, mask_thres, fast_thres, s_val, alpha_thres=None, fd_eps=0.0,
+               sdf_tap_manual=False) -> Scene:
     sc = Scene()
     for i in range(3):
         sc.xyz_min[i] = float(xyz_min[i])
@@ -44,6 +45,8 @@ def make_scene(xyz_min, xyz_max, grid_size, mask_xyz_min, mask_xyz_max, mask_siz
     sc.stepdist, sc.voxel_size = float(stepdist), float(voxel_size)
     sc.act_shift, sc.mask_thres, sc.fast_thres, sc.s_val = float(act_shift), float(mask_thres), float(fast_thres), float(s_val)
     sc.alpha_thres = float(fast_thres if alpha_thres is None else alpha_thres)
+    sc.fd_eps = float(fd_eps)
+    sc.sdf_tap_manual = int(bool(sdf_tap_manual))
     return sc
 
 
@@ -95,6 +98,9 @@ def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid) -> Strea
     L = _lib.lib()
     dev = rays_o.device
     n = rays_o.shape[0]
+    if n == 0:  # no rays (e.g. an LTS segment without points): empty streams, no launch
+        z = torch.zeros(1, dtype=torch.int32, device=dev)
+        return Streams(0, ray_order, _i32(0, dev), _i32(0, dev), z, 0, _i32(0, dev), _i32(0, dev), _f32(0, dev=dev))
     n_steps, cnt_in, cnt_mask = _i32(n, dev), _i32(n, dev), _i32(n, dev)
     st = stream_ptr()
     scp = ctypes.byref(sc)
@@ -120,7 +126,7 @@ class AlphaScan(torch.autograd.Function):
         last = _f32(n, dev=dev)
         check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
                                      ptr(cnt_shade), ptr(last), st))
-        off_shade = exclusive_scan(cnt_shade)
+        off_shade = exclusive_scan(cnt_shade) if n else torch.zeros(1, dtype=torch.int32, device=dev)
         if n_on is None:
             m3 = int(off_shade[n].item())
             m3_on = m3
@@ -361,7 +367,7 @@ class CombineTonemap(torch.autograd.Function):
     One encode kernel + the tensor-core MLP; replaces torch.where / add / copies around `Tonemap`."""
 
     @staticmethod
-    def forward(ctx, lin_off, lin_emo, flat_tone, h_ray, em_modes, ordered):
+    def forward(ctx, lin_off, lin_emo, flat_tone, h_ray, em_modes, ordered, off_sees_on=False):
         L = _lib.lib()
         m = lin_off.shape[0]
         lin_off, lin_emo = lin_off.contiguous(), lin_emo.contiguous()
@@ -371,7 +377,9 @@ class CombineTonemap(torch.autograd.Function):
                                        stream_ptr()))
         img = mlp_pack(TONEMAP_DESC, flat_tone)
         rgb, hid = _mlp_forward(TONEMAP_DESC, img, xt, 0, m, m, any(ctx.needs_input_grad[:3]))
-        ctx.hidden, ctx.ordered = hid, ordered
+        # off_sees_on: the off net receives the cotangent of emission-on rows too (ESRNeRF adds the two radiances
+        # without a stop-gradient, esrnerf.py:751-757; VoxurfF detaches, voxurff.py:243-254)
+        ctx.hidden, ctx.ordered, ctx.off_sees_on = hid, ordered, off_sees_on
         ctx.save_for_backward(lin, xt, img, rgb, h_ray, em_modes)
         return rgb, lin
 
@@ -390,10 +398,11 @@ class CombineTonemap(torch.autograd.Function):
         if ctx.ordered:
             # emission-on rows are a prefix and each net back-propagates through its own row range only (Shade.backward):
             # both can read the same cotangent
-            return d_lin, d_lin, g_flat, None, None, None
+            return d_lin, d_lin, g_flat, None, None, None, None
         on = (em_modes[h_ray.long()] == 1)[:, None]
         zero = torch.zeros_like(d_lin)
-        return torch.where(on, zero, d_lin), torch.where(on, d_lin, zero), g_flat, None, None, None
+        d_off = d_lin if ctx.off_sees_on else torch.where(on, zero, d_lin)
+        return d_off, torch.where(on, d_lin, zero), g_flat, None, None, None, None
 
 
 class Composite(torch.autograd.Function):
@@ -403,22 +412,27 @@ class Composite(torch.autograd.Function):
     def forward(ctx, h_w, a, b, streams):
         s: Streams = streams
         dev = h_w.device
-        a, b = a.contiguous(), b.contiguous()
-        out_a, out_b = _f32(s.n_rays, 3, dev=dev), _f32(s.n_rays, 3, dev=dev)
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        out_a = _f32(s.n_rays, 3, dev=dev)
+        out_b = _f32(s.n_rays, 3, dev=dev) if b is not None else None
         check(_lib.lib().esr_composite_fwd(ptr(s.ray_order), s.n_rays, ptr(s.off_shade), ptr(h_w), ptr(a), ptr(b),
                                            ptr(out_a), ptr(out_b), stream_ptr()))
-        ctx.streams = s
-        ctx.save_for_backward(h_w, a, b)
-        return out_a, out_b
+        ctx.streams, ctx.has_b = s, b is not None
+        ctx.save_for_backward(h_w, a, *([b] if b is not None else []))
+        return (out_a, out_b) if b is not None else (out_a, out_a.new_zeros(0))
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, c_a, c_b):
-        h_w, a, b = ctx.saved_tensors
+        h_w, a = ctx.saved_tensors[:2]
+        b = ctx.saved_tensors[2] if ctx.has_b else None
         s: Streams = ctx.streams
-        d_a, d_b, g_w = torch.empty_like(a), torch.empty_like(b), torch.empty_like(h_w)
+        d_a, g_w = torch.empty_like(a), torch.empty_like(h_w)
+        d_b = torch.empty_like(b) if b is not None else None
         check(_lib.lib().esr_composite_bwd(ptr(s.h_ray), None, ptr(h_w), ptr(a), ptr(b), ptr(c_a.contiguous()),
-                                           ptr(c_b.contiguous()), s.m3, ptr(d_a), ptr(d_b), ptr(g_w), stream_ptr()))
+                                           ptr(c_b.contiguous()) if b is not None else None, s.m3, ptr(d_a), ptr(d_b),
+                                           ptr(g_w), stream_ptr()))
         return g_w, d_a, d_b, None
 
 
@@ -503,3 +517,150 @@ class EncodeCoarse(torch.autograd.Function):
                                                ptr(s.h_ray), ptr(s.h_step), s.m3, ptr(d_x.contiguous()), ptr(g_vol),
                                                ptr(g_off), ptr(g_emo), stream_ptr()))
         return g_vol, g_off, g_emo, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# LTS / PDRA stage (ESRNeRF, esrnerf.py:487-851)
+# ---------------------------------------------------------------------------------------------------
+EMIT_DESC = dict(k0=96, width=192, n_hidden=3, n_out=3, act=1)   # EmissionNet 76->128x3->3 softplus, zero-padded to 192
+BRDF_DESC = dict(k0=96, width=192, n_hidden=3, n_out=5, act=2)   # BRDFNet 76->128x3->5 sigmoid, zero-padded to 192
+
+
+def sample_points(sc: Scene, rays_o, rays_d, h_ray, h_step) -> torch.Tensor:
+    """ray_pts of the reference for stream samples -> [m,3] (bit-identical to kernel.cu:167-194)"""
+    m = h_ray.shape[0]
+    pts = _f32(m, 3, dev=rays_o.device)
+    check(_lib.lib().esr_sample_points(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(h_ray), ptr(h_step), m, ptr(pts),
+                                       stream_ptr()))
+    return pts
+
+
+def sdf_tap_points(sc: Scene, sdf_grid, pts) -> torch.Tensor:
+    """F.grid_sample arithmetic at explicit points (sample_sdf_grad's value, esrnerf.py:819), no autograd: the
+    gradient of this value is scattered by the encode backward through the row's sdf column."""
+    m = pts.shape[0]
+    out = _f32(m, dev=pts.device)
+    check(_lib.lib().esr_sdf_expgrad_fwd(ctypes.byref(sc), ptr(pts), ptr(sdf_grid), m, 0, ptr(out), None, stream_ptr()))
+    return out
+
+
+class SdfExpGrad(torch.autograd.Function):
+    """sample_sdf_expgrad (esrnerf.py:1572-1596): analytic d sdf / d xyz [m,3] at explicit points, differentiable
+    w.r.t. the grid (the reference's create_graph=True path)."""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, sc, pts):
+        m = pts.shape[0]
+        pts = pts.contiguous()
+        grad = _f32(m, 3, dev=pts.device)
+        check(_lib.lib().esr_sdf_expgrad_fwd(ctypes.byref(sc), ptr(pts), ptr(sdf_grid), m, 1, None, ptr(grad),
+                                             stream_ptr()))
+        ctx.sc = sc
+        ctx.save_for_backward(pts, sdf_grid)
+        return grad
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_grad):
+        pts, sdf_grid = ctx.saved_tensors
+        g = torch.zeros_like(sdf_grid)
+        check(_lib.lib().esr_sdf_expgrad_bwd(ctypes.byref(ctx.sc), ptr(pts), pts.shape[0], None,
+                                             ptr(g_grad.contiguous()), ptr(g), stream_ptr()))
+        return g, None, None
+
+
+@dataclass
+class SamplePos:
+    """where the rows of one encode call sit: stream samples (rays_o/rays_d/h_ray/h_step) or explicit points (pts;
+    h_ray optional: row j then reads view direction j)"""
+    m: int
+    viewdirs: torch.Tensor
+    h_sdf: torch.Tensor
+    rays_o: Optional[torch.Tensor] = None
+    rays_d: Optional[torch.Tensor] = None
+    h_ray: Optional[torch.Tensor] = None
+    h_step: Optional[torch.Tensor] = None
+    pts: Optional[torch.Tensor] = None
+
+
+class ShadePBR(torch.autograd.Function):
+    """Encode + any subset of the four nets of the LTS / PDRA stage on tensor cores:
+        lin_off = softplus(off_rgbnet([off_color | feat]))          esrnerf.py:755-757
+        lin_emo = softplus(emo_rgbnet([emo_color | feat]))          esrnerf.py:752-754 (caller masks by em_modes)
+        emit    = softplus(emitnet([emo_color | brdf_feat]))        esrnerf.py:765
+        brdf    = sigmoid(brdfnet([brdf_grid | brdf_feat])) [m,5]   esrnerf.py:761-764
+    `use` = (off, emo, emit, brdf) booleans; unused outputs are empty tensors.  The 76->128 nets run in the 96->192
+    kernels with zero-padded weights (view columns and hidden units 128..191 have zero weights)."""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, off_grid, emo_grid, brdf_grid, flat_off, flat_emo, flat_emit, flat_brdf, sc, pos, use):
+        _check_cl(off_grid, "off_color.grid")
+        _check_cl(emo_grid, "emo_color.grid")
+        p: SamplePos = pos
+        L = _lib.lib()
+        dev = sdf_grid.device
+        m = p.m
+        train = any(ctx.needs_input_grad[:8])
+        rows = L.esr_mlp_act_rows(m)
+        x = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16, device=dev)
+        x2 = None
+        if use[3]:
+            _check_cl(brdf_grid, "brdf.grid")
+            x2 = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16, device=dev)
+        check(L.esr_encode_pbr_fwd(ctypes.byref(sc), ptr(p.rays_o), ptr(p.rays_d), ptr(p.viewdirs), ptr(sdf_grid),
+                                   ptr(off_grid), ptr(emo_grid), ptr(brdf_grid) if use[3] else None, 6, ptr(p.pts),
+                                   ptr(p.h_ray), ptr(p.h_step), ptr(p.h_sdf), m, ptr(x), ptr(x2), 1, stream_ptr()))
+        descs = (RADIANCE_DESC, RADIANCE_DESC, EMIT_DESC, BRDF_DESC)
+        flats = (flat_off, flat_emo, flat_emit, flat_brdf)
+        outs, imgs, hids = [], [], []
+        for k in range(4):
+            if not use[k]:
+                outs.append(torch.zeros(0, descs[k]["n_out"], device=dev))
+                imgs.append(None)
+                hids.append(None)
+                continue
+            img = mlp_pack(descs[k], flats[k])
+            y, hid = _mlp_forward(descs[k], img, x2 if k == 3 else x, 0, m, m, train)
+            outs.append(y)
+            imgs.append(img)
+            hids.append(hid)
+        ctx.sc, ctx.pos, ctx.use, ctx.hids = sc, p, use, hids
+        ctx.n_saved = [t is not None for t in imgs]
+        ctx.save_for_backward(sdf_grid, off_grid, emo_grid, brdf_grid if use[3] else sdf_grid.new_zeros(0), x,
+                              x2 if x2 is not None else x.new_zeros(0), *[t for t in imgs if t is not None], *outs)
+        return tuple(outs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_off, d_emo, d_emit, d_brdf):
+        saved = ctx.saved_tensors
+        sdf_grid, off_grid, emo_grid, brdf_grid, x, x2 = saved[:6]
+        n_img = sum(ctx.n_saved)
+        img_list = list(saved[6:6 + n_img])
+        outs = saved[6 + n_img:]
+        p: SamplePos = ctx.pos
+        use, m = ctx.use, p.m
+        dev = x.device
+        descs = (RADIANCE_DESC, RADIANCE_DESC, EMIT_DESC, BRDF_DESC)
+        d_ys = (d_off, d_emo, d_emit, d_brdf)
+        imgs = [img_list.pop(0) if has else None for has in ctx.n_saved]
+        d_x = torch.zeros(m, FEAT_GRAD_DIM, dtype=torch.float32, device=dev)
+        g_flat = [None, None, None, None]
+        d_brdf_c, scratch = None, None
+        for k in (3, 0, 1, 2):   # the BRDF net first: its colour-slot cotangent is split off before the others accumulate
+            if not use[k]:
+                continue
+            g_flat[k], scratch = _mlp_backward(descs[k], imgs[k], x2 if k == 3 else x, outs[k], d_ys[k].contiguous(), 0,
+                                               m, m, ctx.hids[k], d_x, FEAT_GRAD_DIM, 1, scratch)
+            if k == 3:
+                d_brdf_c = d_x[:, :6].contiguous()
+                d_x[:, :6] = 0
+        ctx.hids = None
+        g_sdf = torch.zeros_like(sdf_grid)
+        g_off = torch.zeros_like(off_grid) if use[0] else None
+        g_emo = torch.zeros_like(emo_grid) if (use[1] or use[2]) else None
+        g_brdf = torch.zeros_like(brdf_grid) if use[3] else None
+        check(_lib.lib().esr_encode_pbr_bwd(ctypes.byref(ctx.sc), ptr(p.rays_o), ptr(p.rays_d), ptr(sdf_grid), 6,
+                                            ptr(p.pts), ptr(p.h_ray), ptr(p.h_step), m, ptr(d_x), ptr(d_brdf_c),
+                                            ptr(g_sdf), ptr(g_off), ptr(g_emo), ptr(g_brdf), stream_ptr()))
+        return (g_sdf, g_off, g_emo, g_brdf, *g_flat, None, None, None)

@@ -146,6 +146,61 @@ class TonemapNet(nn.Module):
         return torch.sigmoid(self.srgb(x))
 
 
+class EmissionNet(nn.Module):
+    """pbr/module.py:68-83: dim0 -> width x (depth-1) -> 3, softplus; parameters live under ``brdfnet.*`` (sic)."""
+
+    def __init__(self, inputdim: int, width: int, depth: int):
+        super().__init__()
+        self.brdfnet = _mlp_stack(inputdim, width, depth, 3)
+        nn.init.constant_(self.brdfnet[-1].bias, 0)
+
+    def layers(self):
+        return _linears(self.brdfnet)
+
+    def forward(self, x):
+        return F.softplus(self.brdfnet(x))
+
+
+class BRDFNet(nn.Module):
+    """pbr/module.py:42-65 as ESRNeRF constructs it (esrnerf.py:186): the `mode` argument is the
+    DenseGrid, so the 5-output branch is taken: sigmoid, split [3 base colour, 1 roughness, 1 metallic]."""
+
+    def __init__(self, inputdim: int, width: int, depth: int, mode=None):
+        super().__init__()
+        self.brdfnet = _mlp_stack(inputdim, width, depth, 5)
+        nn.init.constant_(self.brdfnet[-1].bias, 0)
+
+    def layers(self):
+        return _linears(self.brdfnet)
+
+    def forward(self, x):
+        return torch.sigmoid(self.brdfnet(x)).split([3, 1, 1], -1)
+
+
+class SphericalGaussian(nn.Module):
+    """pbr/module.py:86-143: 48-lobe spherical-Gaussian environment map, softplus activation (cfg/app/lts.yaml:29-30).
+    The initial energy normalisation follows pbr/module.py:104-127."""
+
+    def __init__(self, num_sg: int = 48, activation: str = "softplus"):
+        super().__init__()
+        if activation != "softplus":
+            raise NotImplementedError("only the shipped env_activation 'softplus' is provided (cfg/app/lts.yaml:30)")
+        mus = torch.randn(num_sg, 3)
+        lambdas = 10.0 + torch.abs(torch.randn(num_sg, 1) * 20.0)
+        lobes = torch.randn(num_sg, 3)
+        lam = torch.abs(lambdas)
+        energy = F.softplus(mus) * 2.0 * torch.pi / lam * (1.0 - torch.exp(-2.0 * lam))
+        normalized_mu = F.softplus(mus) / torch.sum(energy, dim=0, keepdim=True) * 2.0 * torch.pi * 0.8
+        self.mus = nn.Parameter(torch.log(torch.exp(normalized_mu) - 1.0))
+        self.lambdas = nn.Parameter(lambdas)
+        self.lobes = nn.Parameter(lobes)
+
+    def forward(self, dirs):
+        lobes = F.normalize(self.lobes, dim=-1)
+        lambdas = torch.abs(self.lambdas)
+        return F.softplus((self.mus * torch.exp(lambdas * ((dirs.unsqueeze(-2) * lobes).sum(-1, keepdim=True) - 1.0))).sum(-2))
+
+
 class GradientConv(nn.Module):
     """module.py:180-211 — fixed 3x3x3 smoothing kernel used by the TV regulariser; kept so the
     state_dict carries ``tv_smooth_conv.m.{weight,bias}`` like the reference's."""
@@ -250,6 +305,48 @@ def flat_mlp_params(layers: Sequence[nn.Linear], kind: str, k0: int) -> torch.Te
     return _FlatParams.apply(idx, inv, k0, *params)
 
 
+def pbr_in_cols(which: str, device) -> torch.Tensor:
+    """Internal 96-column feature row -> reference 76-column input of the emission / BRDF nets
+    [color 0-5 | xyz 6-8 | sin 9-23 | cos 24-38 | sdf 39 | feat 40-63 | normal 64-75] (esrnerf.py:761-765).
+    "emit" reads the emo_color slot (columns 6-11), "brdf" slot 0 of the BRDF copy of the row; the view columns are
+    not inputs of these nets (zero weights)."""
+    cols = [-1] * 96
+    if which == "brdf":
+        cols[0:6] = range(0, 6)
+    else:
+        cols[6:12] = range(0, 6)
+    cols[12] = 39
+    cols[13:37] = range(40, 64)
+    cols[37:49] = range(64, 76)
+    cols[49:52] = range(6, 9)
+    cols[52:67] = range(9, 24)
+    cols[67:82] = range(24, 39)
+    return torch.tensor(cols, dtype=torch.long, device=device)
+
+
+def flat_mlp_params_padded(layers: Sequence[nn.Linear], kind: str, k0: int = 96, width: int = 192) -> torch.Tensor:
+    """Flat f32 master copy (layout of flat_mlp_params) of a NARROWER net zero-padded to the instantiated kernel shape
+    (emitnet / brdfnet 76->128x3->{3,5} run as 96->192x3): padded hidden units have zero weights and biases, so they
+    stay at relu(0) = 0 and contribute nothing forward or backward.  Built from differentiable torch ops: autograd
+    routes the flat gradient back to the nn.Linear parameters."""
+    cols = pbr_in_cols(kind, layers[0].weight.device)
+    n_ref = layers[0].in_features
+    idx = torch.where(cols < 0, torch.full_like(cols, n_ref), cols)
+    parts = []
+    for i, lin in enumerate(layers):
+        w, b = lin.weight, lin.bias
+        last = i + 1 == len(layers)
+        if i == 0:
+            w = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).index_select(1, idx)      # [out, k0] internal order
+        else:
+            w = F.pad(w, (0, width - w.shape[1]))
+        rows = 8 if last else width
+        w = F.pad(w, (0, 0, 0, rows - w.shape[0]))
+        b = F.pad(b, (0, rows - b.shape[0]))
+        parts += [w.reshape(-1), b]
+    return torch.cat(parts)
+
+
 def radiance_in_cols(which: str, device) -> torch.Tensor:
     """Internal 96-column feature row (include/esr_b200.h, Stage E) -> reference 85-column input
     [color 0-5 | xyz 6-8 | sin 9-23 | cos 24-38 | view 39-47 | sdf 48 | feat 49-72 | normal 73-84]
@@ -275,7 +372,9 @@ def tonemap_in_cols(device) -> torch.Tensor:
 
 
 def voxel_geometry(xyz_min: torch.Tensor, xyz_max: torch.Tensor, num_voxels: int):
-    """voxurff.py:539-545 (set_grid_resolution), evaluated with the same float32 torch ops."""
+    """voxurff.py:539-545 (set_grid_resolution), evaluated with the same float32 torch ops on the same device as the
+    reference does (xyz_min / xyz_max live on cfg.system.device there too).  The CUDA and CPU cube roots differ by an
+    ulp, so sample positions differ from a CPU oracle's by <= 1 ulp; the integer streams do not."""
     voxel_size = ((xyz_max - xyz_min).prod() / num_voxels).pow(1 / 3)
     world_size = ((xyz_max - xyz_min) / voxel_size).long()
     return voxel_size, world_size

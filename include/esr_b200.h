@@ -114,6 +114,12 @@ typedef struct esr_scene {
   float s_val;                            /* NeuS inverse std */
   float alpha_thres;                      /* alpha filter before the scan: fastcolor_thres in the fine stage
                                              (voxurff.py:201); negative (= no filter) in the coarse stage */
+  float fd_eps;                           /* added to the finite-difference denominator of the 24-tap SDF feature:
+                                             0 (voxurff.py:711) or 1e-12 (esrnerf.py:1560) */
+  int32_t sdf_tap_manual;                 /* SDF tap of the march stage: 0 = F.grid_sample arithmetic (voxurff.py:671),
+                                             1 = differentiable_grid_sample arithmetic (esrnerf.py:1572-1596 over
+                                             functions.py:142-309: clamped corner indices, products and sums rounded
+                                             separately) */
 } esr_scene_t;
 
 /* exclusive scan of int32 counts: out[i] = sum_{j<i} in[j]; out[n] = total (out has n+1 slots) */
@@ -201,6 +207,42 @@ int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays
                    float *grad_emo_grid, esr_stream_t stream);
 
 /*
+ * LTS / PDRA stage variants (ESRNeRF, esrnerf.py:729-765, 795-830): the same row at EXPLICIT world points `pts`
+ * ([m3,3] f32, nullable: NULL = positions from (h_ray, h_step) as above; with points h_ray / h_step may be NULL and
+ * row j reads view direction j), and optionally a second copy of the row, `feat_brdf`, whose colour slot 0 holds the
+ * taps of a third grid (`brdf_grid`, the BRDFNet input of esrnerf.py:761-763; both NULL = off).  sc->fd_eps selects the
+ * finite-difference denominator.  Backward: d_brdf_color [m3,6] f32 is the cotangent of that slot.
+ */
+int esr_encode_pbr_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                       const float *sdf_grid, const float *off_color_grid, const float *emo_color_grid,
+                       const float *brdf_grid, int color_dim, const float *pts, const int32_t *h_ray,
+                       const int32_t *h_step, const float *h_sdf, int64_t m3, void *feat, void *feat_brdf,
+                       int out_is_bf16, esr_stream_t stream);
+int esr_encode_pbr_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *sdf_grid,
+                       int color_dim, const float *pts, const int32_t *h_ray, const int32_t *h_step, int64_t m3,
+                       const float *d_feat, const float *d_brdf_color, float *grad_sdf_grid, float *grad_off_grid,
+                       float *grad_emo_grid, float *grad_brdf_grid, esr_stream_t stream);
+
+/*
+ * World positions of stream samples — the reference's ray_pts (kernel.cu:167-194) after its compactions: the origins
+ * of the LTS secondary rays (esrnerf.py:576-581) and the points the eps jitters are added to (esrnerf.py:808-813).
+ * pts: f32 [m,3], bit-identical to the reference's values.
+ */
+int esr_sample_points(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *h_ray,
+                      const int32_t *h_step, int64_t m, float *pts, esr_stream_t stream);
+/*
+ * sample_sdf_expgrad (esrnerf.py:1572-1596): SDF value by differentiable_grid_sample (functions.py:142-309) and its
+ * analytic gradient d sdf / d xyz (world units, (x,y,z) order) at explicit points.  manual = 0 evaluates the value
+ * with F.grid_sample arithmetic instead (sample_sdf_grad at the jittered points, esrnerf.py:819; no gradient output).
+ * out_sdf [m] / out_grad [m,3] nullable.  Backward: both outputs are linear in the grid; g_sdf / g_grad (nullable)
+ * are scatter-added into grad_sdf_grid (the create_graph=True path of the reference, needed by the normal losses).
+ */
+int esr_sdf_expgrad_fwd(const esr_scene_t *sc, const float *pts, const float *sdf_grid, int64_t m, int manual,
+                        float *out_sdf, float *out_grad, esr_stream_t stream);
+int esr_sdf_expgrad_bwd(const esr_scene_t *sc, const float *pts, int64_t m, const float *g_sdf, const float *g_grad,
+                        float *grad_sdf_grid, esr_stream_t stream);
+
+/*
  * Coarse-stage feature encode (voxurfc.py:205-249): trilinear tap of the dense central-difference gradient volume
  * `grad_vol` ([1,3,X,Y,Z], channels-first, voxurfc.py:597-616) -> normal = g / (|g| + 1e-5); 12-channel colour-grid
  * taps (channels-last); positional / view encodings.  Row (f32, row-major, 72 columns):
@@ -262,7 +304,7 @@ typedef struct esr_mlp_desc {
   int32_t k0;      /* padded input width: multiple of 16 (96 radiance, 48 tonemap) */
   int32_t width;   /* hidden width: 192 */
   int32_t n_hidden;/* hidden layers: 3 (radiance nets), 1 (tonemapper) */
-  int32_t n_out;   /* real outputs (<= 3; the output layer is padded to 8 rows in the flat copy) */
+  int32_t n_out;   /* real outputs (<= 8: 3 radiance / tone-map / emission, 5 BRDF; padded to 8 rows in the flat copy) */
   int32_t act;     /* 1 softplus, 2 sigmoid */
 } esr_mlp_desc_t;
 
