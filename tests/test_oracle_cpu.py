@@ -303,7 +303,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert _lib.lib().esr_version() >= 100
-    assert ctypes.sizeof(_lib.Scene) == 4 * 27
+    assert ctypes.sizeof(_lib.Scene) == 4 * 29      # esr_scene_t: 27 fine-stage fields + fd_eps + sdf_tap_manual
 
 
 def test_state_dict_contract_and_layout():
