@@ -68,9 +68,6 @@ class ESRNeRF(VoxurfF):
         self.forward = self.forward_training if mode else self.forward_evaluate
         return torch.nn.Module.train(self, mode)
 
-    def forward_evaluate(self, **kwargs):
-        raise NotImplementedError("ESRNeRF.forward_evaluate (esrnerf.py:853-1297) is not built yet; no fallback")
-
     @torch.no_grad()
     def scale_volume_grid(self, num_voxels):
         super().scale_volume_grid(num_voxels)
@@ -105,6 +102,18 @@ class ESRNeRF(VoxurfF):
         return fused.ShadePBR.apply(*grids, *fl, sc, pos, use)
 
     # ------------------------------------------------------------------------------------------
+    def _secondary(self, flats, rays_o2, d_flat):
+        """The render chain over the LTS secondary rays (esrnerf.py:576-652 / 895-981): march from `lts_near`, scan,
+        both radiance nets on every shaded sample, composite -> (sum w*off, sum w*emo, T_last) per secondary ray."""
+        sc2 = self._pbr_scene(self.lts_near, False)
+        st2 = fused.march(sc2, rays_o2, d_flat, None, self.mask_cache.density, self.sdf.grid.detach())
+        sdf_g = self.sdf.grid if torch.is_grad_enabled() else self.sdf.grid.detach()
+        hw2, last2 = fused.AlphaScan.apply(sdf_g, sc2, rays_o2, d_flat, st2, None)
+        pos2 = fused.SamplePos(st2.m3, d_flat, st2.h_sdf, rays_o2, d_flat, st2.h_ray, st2.h_step)
+        lo, le, _, _ = self._shade(sc2, pos2, (True, True, False, False), flats)
+        off_m, emo_m = fused.Composite.apply(hw2, lo, le, st2)
+        return off_m, emo_m, last2, st2, hw2
+
     def _light_transport_segment(self, flats, pts, viewdirs, normal, sdf, base, rough, metal, emission, umask):
         """esrnerf.py:487-679"""
         dev = pts.device
@@ -126,13 +135,7 @@ class ESRNeRF(VoxurfF):
         R = pbr.disney_reflection(ex(base, 3).repeat(2, 1), ex(rough, 1).repeat(2, 1), ex(metal, 1).repeat(2, 1),
                                   ex(normal, 3).repeat(2, 1), d_flat.repeat(2, 1), wout)
         # incoming radiance: the secondary rays go through the whole render chain (esrnerf.py:576-652)
-        rays_o2 = ex(pts, 3).contiguous()
-        sc2 = self._pbr_scene(self.lts_near, False)
-        st2 = fused.march(sc2, rays_o2, d_flat, None, self.mask_cache.density, self.sdf.grid.detach())
-        hw2, last2 = fused.AlphaScan.apply(self.sdf.grid, sc2, rays_o2, d_flat, st2, None)
-        pos2 = fused.SamplePos(st2.m3, d_flat, st2.h_sdf, rays_o2, d_flat, st2.h_ray, st2.h_step)
-        lo, le, _, _ = self._shade(sc2, pos2, (True, True, False, False), flats)
-        off_m, emo_m = fused.Composite.apply(hw2, lo, le, st2)
+        off_m, emo_m, last2, st2, hw2 = self._secondary(flats, ex(pts, 3).contiguous(), d_flat)
         env = self.envmap(d_flat) * last2.unsqueeze(-1)
         off_hat = ((off_m + env).repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
         reflect = (emo_m.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
@@ -206,3 +209,142 @@ class ESRNeRF(VoxurfF):
             "etc/brdf": brdf,
             "etc/brdf_eps": brdf_e,
         }
+
+    # ------------------------------------------------------------------------------------------
+    # inference entry points
+    # ------------------------------------------------------------------------------------------
+    def _eval_stream(self, rays_o, rays_d, manual: bool):
+        """shared head of forward_evaluate / eval_emit / eval_esp: packed shaded stream without autograd state.
+        Returns (scene, streams, h_w, last, degenerate) — `degenerate` flags the reference's `.squeeze()` quirk
+        (SURVEY.md Q7): exactly one sample passing the alpha filter makes 0-dim tensors there and zero images."""
+        sc = self._pbr_scene(self.near, manual)
+        for g in (self.sdf, self.off_color, self.emo_color, self.brdf):
+            g.ensure_layout()
+        s = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, self.sdf.grid.detach())
+        h_w, last = fused.AlphaScan.apply(self.sdf.grid.detach(), sc, rays_o, rays_d, s, None)
+        degenerate = s.m3 <= 1 and s.m1 > 0 and int((s.s_alpha > self.fastcolor_thres).sum()) == 1
+        return sc, s, h_w, last, degenerate
+
+    @staticmethod
+    def _rays(kwargs):
+        return (kwargs["rays_o"].contiguous().float(), kwargs["rays_d"].contiguous().float(),
+                kwargs["viewdirs"].contiguous().float())
+
+    @torch.no_grad()
+    def eval_esp(self, **kwargs) -> torch.Tensor:
+        """esrnerf.py:1360-1407: expected surface point sum_ray w * ray_pts -> [N,3]"""
+        rays_o, rays_d, _ = self._rays(kwargs)
+        with torch.cuda.device(rays_o.device):
+            sc, s, h_w, _, degenerate = self._eval_stream(rays_o, rays_d, False)
+            if degenerate:
+                return torch.zeros_like(rays_o)
+            pts = fused.sample_points(sc, rays_o, rays_d, s.h_ray, s.h_step)
+            return fused.composite_infer(h_w, pts, pts, s)[0]
+
+    @torch.no_grad()
+    def eval_emit(self, **kwargs) -> torch.Tensor:
+        """esrnerf.py:1299-1358: composite of the emission net -> [N,3]"""
+        rays_o, rays_d, viewdirs = self._rays(kwargs)
+        with torch.cuda.device(rays_o.device):
+            sc, s, h_w, _, degenerate = self._eval_stream(rays_o, rays_d, False)
+            if degenerate:
+                return torch.zeros_like(rays_o)
+            pos = fused.SamplePos(s.m3, viewdirs, s.h_sdf, rays_o, rays_d, s.h_ray, s.h_step)
+            flats = [f.detach() for f in self._flats()]
+            _, _, emit, _ = self._shade(sc, pos, (False, False, True, False), flats)
+            return fused.composite_infer(h_w, emit, emit, s)[0]
+
+    def _lts_eval(self, flats, pts, viewdirs, normal, base, rough, metal, emit):
+        """esrnerf.py:854-1001 (one chunk of shaded samples): environment / emission light decomposed into direct
+        and indirect parts by Monte-Carlo integration over `num_2ndrays` hemisphere directions per sample."""
+        dev = pts.device
+        n2, P = self.num_2ndrays, pts.shape[0]
+        dirs = pbr.diffuse_scattering(normal, self._randn(P, n2, 3, dev=dev))
+
+        def ex(t, c):
+            return t.view(-1, 1, c).expand(P, n2, c).flatten(0, 1)
+
+        d_flat = dirs.flatten(0, 1).contiguous()
+        R = pbr.disney_reflection(ex(base, 3), ex(rough, 1), ex(metal, 1), ex(normal, 3), d_flat, -ex(viewdirs, 3))
+        off_m, emo_m, last2, _, _ = self._secondary(flats, ex(pts, 3).contiguous(), d_flat)
+        env = self.envmap(d_flat) * last2.unsqueeze(-1)
+        out = {"lin/env_dir": (env * R).view(-1, n2, 3).mean(-2), "lin/env_indir": (off_m * R).view(-1, n2, 3).mean(-2)}
+        out["lin/env_effects"] = out["lin/env_dir"] + out["lin/env_indir"]
+        out["lin/emit_(in)dir"] = (emo_m * R).view(-1, n2, 3).mean(-2)
+        out["lin/emit_effects"] = emit + out["lin/emit_(in)dir"]
+        return out
+
+    PBR_KEYS = ("lin/env_dir", "lin/env_indir", "lin/env_effects", "lin/emit_(in)dir", "lin/emit_effects")
+
+    @torch.no_grad()
+    def forward_evaluate(self, **kwargs) -> Dict[str, torch.Tensor]:
+        """esrnerf.py:853-1297 — inference: the 12 VoxurfF maps + emission / BRDF maps and, with `render_pbr`, the
+        light-transport decomposition of every shaded sample (in chunks of `chunk_sz` samples)."""
+        rays_o, rays_d, viewdirs = self._rays(kwargs)
+        em_modes = kwargs["em_modes"]
+        render_pbr, chunk_sz = kwargs["render_pbr"], kwargs["chunk_sz"]
+        dev = rays_o.device
+        pos_rt = kwargs["pos_rt"].to(dev).float()
+        if getattr(self, "emit_color", self.emo_color) is not self.emo_color:
+            raise NotImplementedError("a separate emit_color grid exists only after train(finetune=True) (esrnerf.py:218-239)")
+        with torch.cuda.device(dev):
+            sc, s, h_w, last, degenerate = self._eval_stream(rays_o, rays_d, True)
+            if degenerate:
+                z3 = torch.zeros_like(rays_o)
+                depth = z3[..., 0]
+                out = {"etc/depth": depth, "etc/disp": 1 / (depth + self.far), "etc/normal": z3,
+                       "etc/white_bg": torch.ones_like(z3[..., :1])}
+                for k in ("srgb/off_rgb", "lin/off_rgb", "srgb/on_rgb", "lin/on_rgb", "srgb/emo_rgb", "lin/emo_rgb",
+                          "srgb/rgb", "lin/rgb", "lin/emit", "lin/basecolor"):
+                    out[k] = z3
+                out["lin/roughness"] = out["lin/metallic"] = depth
+                if render_pbr:
+                    out.update({k: z3 for k in self.PBR_KEYS})
+                return out
+            m3 = s.m3
+            flats = [f.detach() for f in self._flats()]
+            pos = fused.SamplePos(m3, viewdirs, s.h_sdf, rays_o, rays_d, s.h_ray, s.h_step)
+            lin_off, lin_emo, emit, brdf = self._shade(sc, pos, (True, True, True, True), flats)
+            lin_on = lin_off + lin_emo
+            srgb = fused.tonemap_infer(torch.cat([lin_off, lin_on, lin_emo], 0), self._flat("tone").detach())
+            off_rgb, on_rgb, emo_rgb = srgb[:m3], srgb[m3: 2 * m3], srgb[2 * m3:]
+            grad = fused.sdf_fd_gradient(sc, rays_o, rays_d, self.sdf.grid.detach(), s)
+            normal = (F.normalize(grad, dim=-1) @ pos_rt * self.normal_flipper.to(dev) + 1.0) / 2.0
+            aux = torch.zeros(m3, 3, device=dev)          # (step * dist, roughness, metallic) share one composite
+            aux[:, 0] = s.h_step.float() * float(self.stepsize * self.voxel_size)
+            aux[:, 1:] = brdf[:, 3:5]
+            base = brdf[:, :3].contiguous()
+            off_m, lin_off_m = fused.composite_infer(h_w, off_rgb, lin_off, s)
+            on_m, lin_on_m = fused.composite_infer(h_w, on_rgb, lin_on, s)
+            emo_m, lin_emo_m = fused.composite_infer(h_w, emo_rgb, lin_emo, s)
+            normal_m, aux_m = fused.composite_infer(h_w, normal, aux, s)
+            emit_m, base_m = fused.composite_infer(h_w, emit, base, s)
+            lts = {}
+            if render_pbr and m3:
+                pts = fused.sample_points(sc, rays_o, rays_d, s.h_ray, s.h_step)
+                exp_grad = fused.SdfExpGrad.apply(self.sdf.grid.detach(), sc, pts)
+                nrm = F.normalize(exp_grad, dim=-1)
+                vdir = viewdirs[s.h_ray.long()]
+                parts = {k: [] for k in self.PBR_KEYS}
+                for idx in torch.arange(m3, device=dev).split(int(chunk_sz)):
+                    ret = self._lts_eval(flats, pts[idx], vdir[idx], nrm[idx], base[idx], brdf[idx, 3:4], brdf[idx, 4:5],
+                                         emit[idx])
+                    for k in self.PBR_KEYS:
+                        parts[k].append(ret[k])
+                cat = [torch.cat(parts[k], 0) for k in self.PBR_KEYS]
+                m01 = fused.composite_infer(h_w, cat[0], cat[1], s)
+                m23 = fused.composite_infer(h_w, cat[2], cat[3], s)
+                m4 = fused.composite_infer(h_w, cat[4], cat[4], s)
+                lts = dict(zip(self.PBR_KEYS, (*m01, *m23, m4[0])))
+            elif render_pbr:
+                lts = {k: torch.zeros_like(rays_o) for k in self.PBR_KEYS}
+        depth = aux_m[:, 0].contiguous()
+        em = int(em_modes) if not torch.is_tensor(em_modes) else int(em_modes.item())
+        rgb_m, lin_rgb_m = (off_m, lin_off_m) if em == 0 else (on_m, lin_on_m)
+        if self.keep_streams:
+            self.last_streams = dict(streams=s, h_w=h_w)
+        return {"etc/depth": depth, "etc/disp": 1 / (depth + last * self.far), "etc/normal": normal_m,
+                "etc/white_bg": last.unsqueeze(-1), "srgb/off_rgb": off_m, "lin/off_rgb": lin_off_m, "srgb/on_rgb": on_m,
+                "lin/on_rgb": lin_on_m, "srgb/emo_rgb": emo_m, "lin/emo_rgb": lin_emo_m, "srgb/rgb": rgb_m,
+                "lin/rgb": lin_rgb_m, "lin/emit": emit_m, "lin/basecolor": base_m,
+                "lin/roughness": aux_m[:, 1].contiguous(), "lin/metallic": aux_m[:, 2].contiguous(), **lts}

@@ -307,6 +307,121 @@ def esrnerf_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     return out, inter
 
 
+def _primary_eval_stream(scene, params, rays_o, rays_d, s_val, manual: bool):
+    """shared head of forward_evaluate / eval_emit / eval_esp (esrnerf.py:1012-1089, 1306-1339, 1367-1400)"""
+    N = rays_o.shape[0]
+    ray_pts, ray_id, step_id, _ = _march_near(scene, rays_o, rays_d, scene["near"])
+    keep = P.mask_cache(scene, ray_pts)
+    ray_pts, ray_id, step_id = ray_pts[keep], ray_id[keep], step_id[keep]
+    exp_grad = None
+    if manual:
+        sdf, exp_grad = sdf_expgrad(params["sdf"], ray_pts, scene["xyz_min"], scene["xyz_max"], False)
+    else:
+        sdf = _sample(params["sdf"], scene, ray_pts)[:, 0]
+    alpha = P.neus_alpha_interp(ray_id, sdf, s_val)
+    k0 = alpha > scene["fast_thres"]
+    weights, T, last, _, _ = P.H.alpha2weight(alpha[k0], ray_id[k0], N)
+    k1 = weights > scene["fast_thres"]
+
+    def pick(t):
+        return t[k0][k1]
+
+    return dict(N=N, pts=pick(ray_pts), ray=pick(ray_id), step=pick(step_id), sdf=pick(sdf), w=weights[k1], last=last,
+                exp_grad=None if exp_grad is None else pick(exp_grad))
+
+
+@torch.no_grad()
+def esrnerf_eval_esp(scene, params, rays_o, rays_d, viewdirs, s_val):
+    """esrnerf.py:1360-1407: expected surface point = sum_ray w * ray_pts"""
+    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False)
+    return torch.zeros(st["N"], 3).index_add(0, st["ray"], st["w"][:, None] * st["pts"]), st
+
+
+@torch.no_grad()
+def esrnerf_eval_emit(scene, params, rays_o, rays_d, viewdirs, s_val):
+    """esrnerf.py:1299-1358: composite of the emission net (emit_color aliases emo_color outside finetune, Q13)"""
+    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False)
+    pts = st["pts"]
+    feat, _, fnormal = _taps(scene, params, pts)
+    brdf_feat = torch.cat([_pos_emb(scene, pts), st["sdf"][:, None], feat, fnormal], -1)
+    emit = P.mlp(torch.cat([_sample(params["emo_color"], scene, pts), brdf_feat], -1), params["emitnet"], F.softplus)
+    return torch.zeros(st["N"], 3).index_add(0, st["ray"], st["w"][:, None] * emit), st
+
+
+def _lts_eval(scene, params, pts, viewdirs, normal, base, rough, metal, emit, s_val, dir_noise):
+    """esrnerf.py:854-1001 (one chunk)"""
+    n2, Pn = scene["num_2ndrays"], pts.shape[0]
+    dirs = diffuse_scattering(normal, dir_noise)
+
+    def ex(t, c):
+        return t.view(-1, 1, c).expand(Pn, n2, c).flatten(0, 1)
+
+    d_flat = dirs.flatten(0, 1)
+    R = disney_reflection(ex(base, 3), ex(rough, 1), ex(metal, 1), ex(normal, 3), d_flat, -ex(viewdirs, 3))
+    off_m, emo_m, last, _ = _secondary(scene, params, ex(pts, 3), d_flat, s_val)
+    env = sg_envmap(params, d_flat) * last.unsqueeze(-1)
+    out = {"lin/env_dir": (env * R).view(-1, n2, 3).mean(-2), "lin/env_indir": (off_m * R).view(-1, n2, 3).mean(-2)}
+    out["lin/env_effects"] = out["lin/env_dir"] + out["lin/env_indir"]
+    out["lin/emit_(in)dir"] = (emo_m * R).view(-1, n2, 3).mean(-2)
+    out["lin/emit_effects"] = emit + out["lin/emit_(in)dir"]
+    return out
+
+
+@torch.no_grad()
+def esrnerf_forward_evaluate(scene, params, rays_o, rays_d, viewdirs, em_modes, pos_rt, s_val, render_pbr: bool,
+                             chunk_sz: int, draws=None):
+    """esrnerf.py:853-1297 (general branch; the degenerate `alpha.dim() != 1` branch is not restated)."""
+    draws = draws or Draws()
+    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, True)
+    N, pts, ray_id, step_id, sdf, weights, last = (st[k] for k in ("N", "pts", "ray", "step", "sdf", "w", "last"))
+    _, g, _ = P.sdf_feature_taps(scene, params["sdf"], pts, [1.0], fd_eps=1e-12)      # esrnerf.py:1598-1605
+    grad = torch.stack([g[:, 2], g[:, 1], g[:, 0]], -1)
+    feat, _, fnormal = _taps(scene, params, pts)
+    xyz_emb = _pos_emb(scene, pts)
+    v = viewdirs[ray_id]
+    rgb_feat = torch.cat([xyz_emb, v, v.sin(), v.cos(), sdf[:, None], feat, fnormal], -1)
+    emo_c = _sample(params["emo_color"], scene, pts)
+    lin_off = P.mlp(torch.cat([_sample(params["off_color"], scene, pts), rgb_feat], -1), params["off_rgbnet"], F.softplus)
+    lin_emo = P.mlp(torch.cat([emo_c, rgb_feat], -1), params["emo_rgbnet"], F.softplus)
+    lin_on = lin_off + lin_emo
+    brdf_feat = torch.cat([xyz_emb, sdf[:, None], feat, fnormal], -1)
+    base, rough, metal = _brdf_split(P.mlp(torch.cat([_sample(params["brdf"], scene, pts), brdf_feat], -1),
+                                           params["brdfnet"], torch.sigmoid))
+    emit = P.mlp(torch.cat([emo_c, brdf_feat], -1), params["emitnet"], F.softplus)
+    w_ = weights[:, None]
+
+    def comp(x):
+        return torch.zeros(N, x.shape[1]).index_add(0, ray_id, w_ * x)
+
+    normal = F.normalize(grad, dim=-1) @ pos_rt
+    normal = (normal * torch.tensor([1.0, -1.0, -1.0]) + 1.0) / 2.0
+    depth = torch.zeros(N).index_add(0, ray_id, weights * step_id * scene["stepdist"])
+    out = {
+        "etc/depth": depth, "etc/disp": 1 / (depth + last * scene["far"]), "etc/normal": comp(normal),
+        "etc/white_bg": last.unsqueeze(-1),
+        "srgb/off_rgb": comp(P.tonemap(params, lin_off)), "lin/off_rgb": comp(lin_off),
+        "srgb/on_rgb": comp(P.tonemap(params, lin_on)), "lin/on_rgb": comp(lin_on),
+        "srgb/emo_rgb": comp(P.tonemap(params, lin_emo)), "lin/emo_rgb": comp(lin_emo),
+        "lin/emit": comp(emit), "lin/basecolor": comp(base), "lin/roughness": comp(rough)[:, 0],
+        "lin/metallic": comp(metal)[:, 0],
+    }
+    sel = "off" if int(em_modes) == 0 else "on"
+    out["srgb/rgb"], out["lin/rgb"] = out[f"srgb/{sel}_rgb"], out[f"lin/{sel}_rgb"]
+    if render_pbr:
+        vdir = viewdirs[ray_id]
+        nrm = F.normalize(st["exp_grad"], dim=-1)
+        parts = {}
+        for idx in torch.arange(pts.shape[0]).split(chunk_sz):
+            noise = draws.randn(idx.shape[0], scene["num_2ndrays"], 3)
+            ret = _lts_eval(scene, params, pts[idx], vdir[idx], nrm[idx], base[idx], rough[idx], metal[idx], emit[idx],
+                            s_val, noise)
+            for k, val in ret.items():
+                parts.setdefault(k, []).append(val)
+        for k, val in parts.items():
+            out[k] = comp(torch.cat(val, 0))
+    return out, dict(m3_ray=ray_id, m3_step=step_id, m3_weights=weights)
+
+
 def params_from_state_dict(sd: Dict[str, torch.Tensor]) -> Dict:
     """state_dict keys of the reference ESRNeRF -> the dict the port consumes."""
     p = P.params_from_state_dict(sd)

@@ -222,6 +222,7 @@ ESRNERF_CASES = {
     "pdra_sparse_s60": (48 ** 3, 24, True, 160, 60.0, 77, 8, 20, True, 42),
 }
 NORMAL_EPS, EMIT_EPS = 0.01, 0.02
+EVAL_CHUNK = 300          # LTS points per chunk in forward_evaluate(render_pbr=True): several chunks per case
 
 
 def lts_cfg(**over):
@@ -285,6 +286,21 @@ def run_esrnerf_case(name, spec, weights):
     for pname, p in m.named_parameters():
         if p.grad is not None:
             fx.update(grad_digest(pname, p.grad))
+    # inference entry points (esrnerf.py:853-1407): forward_evaluate with the PBR decomposition, eval_emit, eval_esp
+    m.eval()
+    pos_rt = torch.linalg.qr(E._randn(3, 3, generator=torch.Generator().manual_seed(3)))[0].contiguous()
+    fx["pos_rt"] = pos_rt.numpy()
+    fx["eval_chunk"] = EVAL_CHUNK
+    with torch.no_grad():
+        for em in (0, 1):
+            with patched_draws(E.FixedDraws(dseed + 100)):
+                ev = m(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"], em_modes=torch.tensor(em),
+                       pos_rt=pos_rt, render_pbr=True, chunk_sz=EVAL_CHUNK)
+            for k, v in ev.items():
+                fx[f"eval{em}/" + k] = v.numpy()
+        kw = dict(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"])
+        fx["eval_emit"] = m.eval_emit(**kw).numpy()
+        fx["eval_esp"] = m.eval_esp(**kw).numpy()
     np.savez_compressed(os.path.join(GOLDEN, f"esrnerf_{name}.npz"), **fx)
     print(f"{name}: m3={out['etc/emit'].shape[0]} loss={loss.item():.6f}")
 

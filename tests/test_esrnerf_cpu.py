@@ -67,3 +67,27 @@ def test_esrnerf_port_matches_reference():
     for name, p in ref.named_parameters():
         if p.grad is not None:
             assert C.rel_err(leaves[name].grad, p.grad) < 1e-5, name
+
+
+@pytest.mark.parametrize("case", C.ESRNERF_CASES)
+def test_esrnerf_eval_ports_match_golden(case):
+    """forward_evaluate (with the PBR decomposition, several LTS chunks), eval_emit, eval_esp: port vs the outputs of
+    the reference's own methods stored in the fixture"""
+    from esr_nerf_b200 import synthetic as S
+    from oracle import esrnerf_port as E
+
+    fx, weights = C.load_esrnerf_case(case)
+    scene = C.esrnerf_oracle_scene(fx)
+    params, _ = C.esrnerf_oracle_params(scene, weights, requires_grad=False)
+    rays = S.make_rays(int(fx["n_rays"]), int(fx["ray_seed"]))
+    args = (scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"])
+    s_val = float(fx["s_val"])
+    for em in (0, 1):
+        out, _ = E.esrnerf_forward_evaluate(*args, torch.tensor(em), torch.from_numpy(fx["pos_rt"]), s_val, True,
+                                            int(fx["eval_chunk"]), E.FixedDraws(int(fx["draw_seed"]) + 100))
+        keys = {k.split("/", 1)[1] for k in fx if k.startswith(f"eval{em}/")}
+        assert set(out) == keys and len(keys) == 21
+        for k in out:
+            assert C.rel_err(out[k], torch.from_numpy(fx[f"eval{em}/{k}"])) < 1e-5, (em, k)
+    assert C.rel_err(E.esrnerf_eval_emit(*args, s_val)[0], torch.from_numpy(fx["eval_emit"])) < 1e-5
+    assert C.rel_err(E.esrnerf_eval_esp(*args, s_val)[0], torch.from_numpy(fx["eval_esp"])) < 1e-5

@@ -123,3 +123,52 @@ def test_esrnerf_port_as_live_oracle_on_new_rays():
     for k in sorted(out):
         assert tuple(out[k].shape) == tuple(ref[k].shape), k
         assert C.rel_err(out[k], ref[k]) < (1e-4 if k in FP32_KEYS else 1e-2), k
+
+
+@pytest.mark.parametrize("case", C.ESRNERF_CASES)
+def test_esrnerf_inference_entry_points_vs_golden(case):
+    """forward_evaluate (21 maps incl. the PBR decomposition over several LTS chunks), eval_emit, eval_esp against the
+    outputs of the reference's own methods (fixture) — same random draws through FixedDraws."""
+    from oracle import esrnerf_port as E
+
+    fx, weights = C.load_esrnerf_case(case)
+    m = C.build_product_esrnerf(fx, weights, DEV)
+    m.eval()
+    m.keep_streams = True
+    n = int(fx["n_rays"])
+    rays = {k: v.to(DEV) for k, v in S.make_rays(n, int(fx["ray_seed"])).items()}
+    kw = dict(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"])
+    for em in (0, 1):
+        m.draws = E.FixedDraws(int(fx["draw_seed"]) + 100)
+        out = m(em_modes=torch.tensor(em), pos_rt=torch.from_numpy(fx["pos_rt"]), render_pbr=True,
+                chunk_sz=int(fx["eval_chunk"]), **kw)
+        keys = {k.split("/", 1)[1] for k in fx if k.startswith(f"eval{em}/")}
+        assert set(out) == keys
+        for k in sorted(out):
+            ref = torch.from_numpy(fx[f"eval{em}/{k}"])
+            assert tuple(out[k].shape) == tuple(ref.shape), k
+            tol = 1e-4 if k in ("etc/depth", "etc/disp", "etc/normal", "etc/white_bg") else 1e-2
+            assert C.rel_err(out[k], ref) < tol, (em, k, C.rel_err(out[k], ref))
+    out = m(em_modes=1, pos_rt=torch.from_numpy(fx["pos_rt"]), render_pbr=False, chunk_sz=64, **kw)   # pdra.py:656-657
+    assert len(out) == 16 and C.rel_err(out["lin/emit"], torch.from_numpy(fx["eval1/lin/emit"])) < 1e-2
+    assert C.rel_err(m.eval_emit(**kw), torch.from_numpy(fx["eval_emit"])) < 1e-2
+    assert C.rel_err(m.eval_esp(**kw), torch.from_numpy(fx["eval_esp"])) < 1e-4
+
+
+def test_esrnerf_edge_cases():
+    """all rays miss the box (empty streams through every stage, incl. an empty light-transport segment)"""
+    fx, weights = C.load_esrnerf_case("lts_sparse_s220")
+    m = C.build_product_esrnerf(fx, weights, DEV)
+    n = 24
+    rays = S.make_rays(n, 5)
+    rays["rays_d"], rays["viewdirs"] = -rays["rays_d"], -rays["viewdirs"]
+    batch = {k: v.to(DEV) for k, v in rays.items() if k != "rgbs"}
+    out = m(s_val=220.0, uncert_masks=S.uncert_masks(n).to(DEV), normal_eps=0.01, emit_eps=0.01, **batch)
+    assert (out["etc/alphainv_cum"] == 1).all() and (out["srgb/rgb"] == 0).all()
+    assert out["etc/normal"].shape == (0, 3) and out["lin/pbr/off_hat"].shape == (0, 3)
+    sum(v.sum() for v in out.values()).backward()
+    m.eval()
+    ev = m(em_modes=torch.tensor(0), pos_rt=torch.eye(3), render_pbr=True, chunk_sz=16,
+           **{k: batch[k] for k in ("rays_o", "rays_d", "viewdirs")})
+    assert (ev["etc/white_bg"] == 1).all() and (ev["lin/env_effects"] == 0).all()
+    assert (m.eval_emit(**batch) == 0).all() and (m.eval_esp(**batch) == 0).all()
