@@ -63,9 +63,21 @@ class ESRNeRF(VoxurfF):
     # ------------------------------------------------------------------------------------------
     def train(self, mode=True, finetune=False):
         """esrnerf.py:218-239"""
-        if mode and finetune:
-            raise NotImplementedError("ESRNeRF.forward_finetune (esrnerf.py:241-484) is not built yet")
-        self.forward = self.forward_training if mode else self.forward_evaluate
+        if mode and not finetune:
+            self.forward = self.forward_training
+            if hasattr(self, "emit_color"):
+                del self.emit_color
+        elif mode:
+            # scene-editing finetune (pdra.py:1079-1088): the emission net keeps reading a frozen copy of emo_color
+            self.forward = self.forward_finetune
+            self.emit_color = DenseGrid(self.color_dim, self.world_size, self.xyz_min, self.xyz_max).to(self.device)
+            self.emit_color.load_state_dict(self.emo_color.state_dict())
+            for p in self.emit_color.parameters():
+                p.requires_grad_(False)
+        else:
+            self.forward = self.forward_evaluate
+            if hasattr(self, "emo_color") and not hasattr(self, "emit_color"):
+                self.emit_color = self.emo_color
         return torch.nn.Module.train(self, mode)
 
     @torch.no_grad()
@@ -96,13 +108,14 @@ class ESRNeRF(VoxurfF):
             return self.draws.randn(*shape).to(dev)
         return torch.randn(*shape, device=dev)
 
-    def _shade(self, sc, pos, use, flats):
-        grids = (self.sdf.grid, self.off_color.grid, self.emo_color.grid, self.brdf.grid if use[3] else None)
+    def _shade(self, sc, pos, use, flats, emo_grid=None, sdf_grid=None):
+        grids = (self.sdf.grid if sdf_grid is None else sdf_grid, self.off_color.grid,
+                 self.emo_color.grid if emo_grid is None else emo_grid, self.brdf.grid if use[3] else None)
         fl = [f if u else None for f, u in zip(flats, use)]
         return fused.ShadePBR.apply(*grids, *fl, sc, pos, use)
 
     # ------------------------------------------------------------------------------------------
-    def _secondary(self, flats, rays_o2, d_flat):
+    def _secondary(self, flats, rays_o2, d_flat, use=(True, True, False, False)):
         """The render chain over the LTS secondary rays (esrnerf.py:576-652 / 895-981): march from `lts_near`, scan,
         both radiance nets on every shaded sample, composite -> (sum w*off, sum w*emo, T_last) per secondary ray."""
         sc2 = self._pbr_scene(self.lts_near, False)
@@ -110,8 +123,11 @@ class ESRNeRF(VoxurfF):
         sdf_g = self.sdf.grid if torch.is_grad_enabled() else self.sdf.grid.detach()
         hw2, last2 = fused.AlphaScan.apply(sdf_g, sc2, rays_o2, d_flat, st2, None)
         pos2 = fused.SamplePos(st2.m3, d_flat, st2.h_sdf, rays_o2, d_flat, st2.h_ray, st2.h_step)
-        lo, le, _, _ = self._shade(sc2, pos2, (True, True, False, False), flats)
-        off_m, emo_m = fused.Composite.apply(hw2, lo, le, st2)
+        lo, le, _, _ = self._shade(sc2, pos2, use, flats)
+        if use[0]:
+            off_m, emo_m = fused.Composite.apply(hw2, lo, le, st2)
+        else:
+            off_m, emo_m = None, fused.Composite.apply(hw2, le, None, st2)[0]
         return off_m, emo_m, last2, st2, hw2
 
     def _light_transport_segment(self, flats, pts, viewdirs, normal, sdf, base, rough, metal, emission, umask):
@@ -210,6 +226,54 @@ class ESRNeRF(VoxurfF):
             "etc/brdf_eps": brdf_e,
         }
 
+    @torch.no_grad()
+    def forward_finetune(self, **kwargs) -> Dict[str, torch.Tensor]:
+        """esrnerf.py:241-484 — scene-editing finetune target.  Everything runs without autograd except
+        emo_rgbnet(emo_color(x)) at the LTS points: 'lin/pbr/emo' carries gradient to emo_rgbnet /
+        emo_color only, 'lin/pbr/emo_hat' = edited emission + reflected emission is a constant target."""
+        rays_o, rays_d, viewdirs = self._rays(kwargs)
+        em_modes, em_int, em_col = kwargs["em_modes"], kwargs["em_intensities"], kwargs["em_colors"]
+        dev = rays_o.device
+        n2 = self.num_2ndrays
+        with torch.cuda.device(dev):
+            sc, s, _, _, _ = self._eval_stream(rays_o, rays_d, False)
+            idx = self._choice(s.m3, min(self.num_ltspts, s.m3), dev)
+            P = idx.shape[0]
+            if P == 0:
+                z = torch.zeros(0, 3, device=dev)
+                return {"lin/pbr/emo": z, "lin/pbr/emo_hat": z}
+            ray = s.h_ray.long()[idx]
+            pts = fused.sample_points(sc, rays_o, rays_d, s.h_ray[idx].contiguous(), s.h_step[idx].contiguous())
+            vdir = viewdirs[ray]
+            sc_pts = self._pbr_scene(self.near, False)
+            sdf, exp_grad = fused.sdf_expgrad_points(sc_pts, self.sdf.grid.detach(), pts)
+            normal = F.normalize(exp_grad, dim=-1)
+            dirs = pbr.diffuse_scattering(normal, self._randn(P, n2 + 1, 3, dev=dev))
+            v_rand = -dirs[:, -1]
+            dirs = dirs[:, :-1]
+            flats_ng = [f.detach() for f in self._flats()]
+            pos2 = fused.SamplePos(2 * P, torch.cat([vdir, v_rand], 0).contiguous(), sdf.repeat(2).contiguous(),
+                                   pts=pts.repeat(2, 1).contiguous())
+            with torch.enable_grad():   # the features are constants here: only emo_rgbnet / emo_color receive gradient
+                flat_emo = self._flat("emo")
+                _, emo, _, _ = self._shade(sc_pts, pos2, (False, True, False, False), [None, flat_emo, None, None],
+                                           sdf_grid=self.sdf.grid.detach())
+            pos1 = fused.SamplePos(P, vdir.contiguous(), sdf, pts=pts)
+            _, _, emit, brdf = self._shade(sc_pts, pos1, (False, False, True, True), flats_ng,
+                                           emo_grid=self.emit_color.grid.detach())
+
+            def ex(t, c):
+                return t.view(-1, 1, c).expand(P, n2, c).flatten(0, 1)
+
+            d_flat = dirs.flatten(0, 1).contiguous()
+            R = pbr.disney_reflection(ex(brdf[:, :3], 3).repeat(2, 1), ex(brdf[:, 3:4], 1).repeat(2, 1),
+                                      ex(brdf[:, 4:5], 1).repeat(2, 1), ex(normal, 3).repeat(2, 1), d_flat.repeat(2, 1),
+                                      torch.cat([-ex(vdir, 3), -ex(v_rand, 3)], 0))
+            _, emo_m, _, _, _ = self._secondary(flats_ng, ex(pts, 3).contiguous(), d_flat, (False, True, False, False))
+            emit = pbr.edit_emission(emit, em_modes[ray], em_int[ray], em_col[ray])
+            reflect = (emo_m.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
+        return {"lin/pbr/emo": emo, "lin/pbr/emo_hat": emit.repeat(2, 1) + reflect}
+
     # ------------------------------------------------------------------------------------------
     # inference entry points
     # ------------------------------------------------------------------------------------------
@@ -285,8 +349,7 @@ class ESRNeRF(VoxurfF):
         render_pbr, chunk_sz = kwargs["render_pbr"], kwargs["chunk_sz"]
         dev = rays_o.device
         pos_rt = kwargs["pos_rt"].to(dev).float()
-        if getattr(self, "emit_color", self.emo_color) is not self.emo_color:
-            raise NotImplementedError("a separate emit_color grid exists only after train(finetune=True) (esrnerf.py:218-239)")
+        assert getattr(self, "emit_color", self.emo_color) is self.emo_color      # eval aliases it (esrnerf.py:236-238)
         with torch.cuda.device(dev):
             sc, s, h_w, last, degenerate = self._eval_stream(rays_o, rays_d, True)
             if degenerate:

@@ -544,6 +544,16 @@ def sdf_tap_points(sc: Scene, sdf_grid, pts) -> torch.Tensor:
     return out
 
 
+def sdf_expgrad_points(sc: Scene, sdf_grid, pts):
+    """sample_sdf_expgrad (esrnerf.py:1572-1596) without autograd state -> (sdf [m], d sdf / d xyz [m,3])"""
+    m = pts.shape[0]
+    pts = pts.contiguous()
+    sdf, grad = _f32(m, dev=pts.device), _f32(m, 3, dev=pts.device)
+    check(_lib.lib().esr_sdf_expgrad_fwd(ctypes.byref(sc), ptr(pts), ptr(sdf_grid), m, 1, ptr(sdf), ptr(grad),
+                                         stream_ptr()))
+    return sdf, grad
+
+
 class SdfExpGrad(torch.autograd.Function):
     """sample_sdf_expgrad (esrnerf.py:1572-1596): analytic d sdf / d xyz [m,3] at explicit points, differentiable
     w.r.t. the grid (the reference's create_graph=True path)."""

@@ -35,3 +35,43 @@ def disney_reflection(albedo, roughness, metallic, normal, win, wout):
     k = ((1 + roughness) ** 2) / 8
     vis = (0.5 / (ion * (1 - k) + k).clamp(min=eps)) * (0.5 / (oon * (1 - k) + k).clamp(min=eps))
     return (fd + ndf * fresnel * vis) * ion * math.pi * 2
+
+
+def rgb_to_hsv(rgb: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """pbr/functions.py:214-236"""
+    mx, arg = rgb.max(-1)
+    delta = mx - rgb.min(-1).values
+    sat = delta / (mx + eps)
+    delta = torch.where(delta == 0, torch.ones_like(delta), delta)
+    rc, gc, bc = torch.unbind(mx.unsqueeze(-1) - rgb, dim=-1)
+    hue = torch.stack((bc - gc, (rc - bc) + 2.0 * delta, (gc - rc) + 4.0 * delta), dim=-1) / delta.unsqueeze(-1)
+    hue = torch.gather(hue, -1, arg.unsqueeze(-1)).squeeze(-1)
+    return torch.stack(((hue / 6.0) % 1.0, sat, mx), dim=-1)
+
+
+def hsv_to_rgb(hsv: torch.Tensor) -> torch.Tensor:
+    """pbr/functions.py:239-255"""
+    hue, sat, val = hsv[..., 0], hsv[..., 1], hsv[..., 2]
+    sector = torch.floor(hue * 6) % 6
+    frac = ((hue * 6) % 6) - sector
+    p = val * (1.0 - sat)
+    q = val * (1.0 - frac * sat)
+    t = val * (1.0 - (1.0 - frac) * sat)
+    sector = sector.long()
+    table = torch.stack((val, q, p, p, t, val, t, val, val, q, p, p, p, p, t, val, val, q), dim=-1)
+    return torch.gather(table, -1, torch.stack([sector, sector + 6, sector + 12], dim=-1))
+
+
+@torch.no_grad()
+def edit_emission(emit, em_modes, em_intensities, em_colors):
+    """esrnerf.py:407-417: per-point emission edits of the finetune stage (LightDict, utils2/utils.py: 0 off, 1 on,
+    2 intensity change, 3 colour change, 4 both): zero / scale / replace hue and saturation."""
+    emit = emit.clone()
+    i_mask = (em_modes == 2) | (em_modes == 4)
+    c_mask = (em_modes == 3) | (em_modes == 4)
+    emit[em_modes == 0] = 0
+    emit[i_mask] = emit[i_mask] * em_intensities[i_mask][..., None]
+    hsv = rgb_to_hsv(emit[c_mask])
+    hsv[..., :-1] = em_colors[c_mask]
+    emit[c_mask] = hsv_to_rgb(hsv)
+    return emit

@@ -98,6 +98,22 @@ def uncert_masks(n: int) -> torch.Tensor:
     return m
 
 
+def finetune_inputs(n: int, seed: int = 21) -> Dict[str, torch.Tensor]:
+    """per-ray emission edits of the PDRA finetune stage (pdra.py:1048-1100): mode in LightDict 0..4, intensity scale,
+    (hue, saturation) replacement"""
+    g = torch.Generator().manual_seed(seed)
+    return dict(em_modes=torch.randint(0, 5, (n,), generator=g), em_intensities=torch.rand(n, generator=g) * 2,
+                em_colors=torch.rand(n, 2, generator=g))
+
+
+def perturb_emit_color(model, seed: int = 9) -> None:
+    """make the frozen emit_color copy differ from emo_color so tests can tell the two grids apart"""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        noise = 0.05 * torch.randn(model.emit_color.grid.shape, generator=g)
+        model.emit_color.grid.add_(noise.to(model.emit_color.grid.device))
+
+
 COARSE_MODEL_CFG = dict(  # cfg/app/coarse.yaml:13-31
     mask_ks=3, maskcache_thres=1e-3, fastcolor_thres=1e-4, stepsize=0.5, num_voxels=96 ** 3, color_dim=12,
     rgbnet_width=128, rgbnet_depth=3, posbase_pe=5, viewbase_pe=1, smooth_ksize=5, smooth_sigma=0.8,

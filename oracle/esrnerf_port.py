@@ -422,6 +422,90 @@ def esrnerf_forward_evaluate(scene, params, rays_o, rays_d, viewdirs, em_modes, 
     return out, dict(m3_ray=ray_id, m3_step=step_id, m3_weights=weights)
 
 
+def rgb_to_hsv(rgb: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """pbr/functions.py:214-236"""
+    mx, arg = rgb.max(-1)
+    mn = rgb.min(-1).values
+    delta = mx - mn
+    sat = delta / (mx + eps)
+    delta = torch.where(delta == 0, torch.ones_like(delta), delta)
+    rc, gc, bc = torch.unbind(mx.unsqueeze(-1) - rgb, dim=-1)
+    h = torch.stack((bc - gc, (rc - bc) + 2.0 * delta, (gc - rc) + 4.0 * delta), dim=-1) / delta.unsqueeze(-1)
+    h = torch.gather(h, -1, arg.unsqueeze(-1)).squeeze(-1)
+    return torch.stack(((h / 6.0) % 1.0, sat, mx), dim=-1)
+
+
+def hsv_to_rgb(hsv: torch.Tensor) -> torch.Tensor:
+    """pbr/functions.py:239-255"""
+    h, sat, v = hsv[..., 0], hsv[..., 1], hsv[..., 2]
+    hi = torch.floor(h * 6) % 6
+    f = ((h * 6) % 6) - hi
+    p = v * (1.0 - sat)
+    q = v * (1.0 - f * sat)
+    t = v * (1.0 - (1.0 - f) * sat)
+    hi = hi.long()
+    table = torch.stack((v, q, p, p, t, v, t, v, v, q, p, p, p, p, t, v, v, q), dim=-1)
+    return torch.gather(table, -1, torch.stack([hi, hi + 6, hi + 12], dim=-1))
+
+
+def edit_emission(emit, em_modes, em_intensities, em_colors):
+    """esrnerf.py:407-417: emission-source editing modes (utils2 LightDict: 0 off, 1 on, 2 intensity, 3 colour, 4 both)"""
+    emit = emit.clone()
+    i_mask = (em_modes == 2) | (em_modes == 4)
+    c_mask = (em_modes == 3) | (em_modes == 4)
+    emit[em_modes == 0] = 0
+    emit[i_mask] = emit[i_mask] * em_intensities[i_mask][..., None]
+    hsv = rgb_to_hsv(emit[c_mask])
+    hsv[..., :-1] = em_colors[c_mask]
+    emit[c_mask] = hsv_to_rgb(hsv)
+    return emit
+
+
+def esrnerf_forward_finetune(scene, params, rays_o, rays_d, viewdirs, em_modes, em_intensities, em_colors, s_val,
+                             draws=None):
+    """esrnerf.py:241-484 — `@torch.no_grad` with autograd enabled only around emo_rgbnet(emo_color(x)) at the LTS
+    points (Q14): 'lin/pbr/emo' carries gradient to emo_rgbnet / emo_color, 'lin/pbr/emo_hat' is a constant target.
+    params["emit_color"] is the frozen copy of emo_color made by train(finetune=True) (esrnerf.py:224-235)."""
+    draws = draws or Draws()
+    n2 = scene["num_2ndrays"]
+    with torch.no_grad():
+        st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False)
+        m3 = st["pts"].shape[0]
+        idx = draws.choice(m3, min(scene["num_ltspts"], m3))
+        pts, ray = st["pts"][idx], st["ray"][idx]
+        vdir, modes, inten, cols = viewdirs[ray], em_modes[ray], em_intensities[ray], em_colors[ray]
+        Pn = pts.shape[0]
+        sdf, exp_grad = sdf_expgrad(params["sdf"], pts, scene["xyz_min"], scene["xyz_max"], True)
+        sdf, normal = sdf.detach(), F.normalize(exp_grad.detach(), dim=-1)
+        dirs = diffuse_scattering(normal, draws.randn(Pn, n2 + 1, 3))
+        v_rand = -dirs[:, -1]
+        dirs = dirs[:, :-1]
+        feat, _, fnormal = _taps(scene, params, pts)
+        xyz_emb = _pos_emb(scene, pts)
+        v2 = torch.cat([vdir, v_rand], 0)
+        rgb_feat = torch.cat([xyz_emb.repeat(2, 1), v2, v2.sin(), v2.cos(), sdf[:, None].repeat(2, 1), feat.repeat(2, 1),
+                              fnormal.repeat(2, 1)], -1)
+        with torch.enable_grad():
+            emo = P.mlp(torch.cat([_sample(params["emo_color"], scene, pts).repeat(2, 1), rgb_feat], -1),
+                        params["emo_rgbnet"], F.softplus)
+        brdf_feat = torch.cat([xyz_emb, sdf[:, None], feat, fnormal], -1)
+        base, rough, metal = _brdf_split(P.mlp(torch.cat([_sample(params["brdf"], scene, pts), brdf_feat], -1),
+                                               params["brdfnet"], torch.sigmoid))
+        emit = P.mlp(torch.cat([_sample(params["emit_color"], scene, pts), brdf_feat], -1), params["emitnet"], F.softplus)
+
+        def ex(t, c):
+            return t.view(-1, 1, c).expand(Pn, n2, c).flatten(0, 1)
+
+        d_flat = dirs.flatten(0, 1)
+        R = disney_reflection(ex(base, 3).repeat(2, 1), ex(rough, 1).repeat(2, 1), ex(metal, 1).repeat(2, 1),
+                              ex(normal, 3).repeat(2, 1), d_flat.repeat(2, 1), torch.cat([-ex(vdir, 3), -ex(v_rand, 3)], 0))
+        _, emo_m, _, _ = _secondary(scene, params, ex(pts, 3), d_flat, s_val)
+        emit = edit_emission(emit, modes, inten, cols)
+        reflect = (emo_m.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
+        emo_hat = emit.repeat(2, 1) + reflect
+    return {"lin/pbr/emo": emo, "lin/pbr/emo_hat": emo_hat}
+
+
 def params_from_state_dict(sd: Dict[str, torch.Tensor]) -> Dict:
     """state_dict keys of the reference ESRNeRF -> the dict the port consumes."""
     p = P.params_from_state_dict(sd)
@@ -430,6 +514,8 @@ def params_from_state_dict(sd: Dict[str, torch.Tensor]) -> Dict:
         return [(sd[f"{prefix}.{i}.weight"].float(), sd[f"{prefix}.{i}.bias"].float()) for i in idx]
 
     p["brdf"] = sd["brdf.grid"].float().contiguous()
+    if "emit_color.grid" in sd:
+        p["emit_color"] = sd["emit_color.grid"].float().contiguous()
     p["emitnet"] = net("emitnet.brdfnet", ["0", "2.0", "3.0", "4"])
     p["brdfnet"] = net("brdfnet.brdfnet", ["0", "2.0", "3.0", "4"])
     for k in ("envmap.mus", "envmap.lambdas", "envmap.lobes"):

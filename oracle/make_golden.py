@@ -301,6 +301,20 @@ def run_esrnerf_case(name, spec, weights):
         kw = dict(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"])
         fx["eval_emit"] = m.eval_emit(**kw).numpy()
         fx["eval_esp"] = m.eval_esp(**kw).numpy()
+    # scene-editing finetune target (esrnerf.py:241-484)
+    m.train(finetune=True)
+    m.zero_grad(set_to_none=True)
+    S.perturb_emit_color(m)
+    ft_in = S.finetune_inputs(n)
+    with patched_draws(E.FixedDraws(dseed + 200)):
+        ft = m(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"], **ft_in)
+    ft_cot = E._randn(ft["lin/pbr/emo"].shape, generator=torch.Generator().manual_seed(8))
+    (ft["lin/pbr/emo"] * ft_cot).sum().backward()
+    for k, v in ft.items():
+        fx["ft/" + k] = v.detach().numpy()
+    for pname, p in m.named_parameters():
+        if p.grad is not None:
+            fx.update({"ft" + k: v for k, v in grad_digest(pname, p.grad).items()})
     np.savez_compressed(os.path.join(GOLDEN, f"esrnerf_{name}.npz"), **fx)
     print(f"{name}: m3={out['etc/emit'].shape[0]} loss={loss.item():.6f}")
 

@@ -91,3 +91,38 @@ def test_esrnerf_eval_ports_match_golden(case):
             assert C.rel_err(out[k], torch.from_numpy(fx[f"eval{em}/{k}"])) < 1e-5, (em, k)
     assert C.rel_err(E.esrnerf_eval_emit(*args, s_val)[0], torch.from_numpy(fx["eval_emit"])) < 1e-5
     assert C.rel_err(E.esrnerf_eval_esp(*args, s_val)[0], torch.from_numpy(fx["eval_esp"])) < 1e-5
+
+
+def _finetune_port(fx, weights):
+    from esr_nerf_b200 import synthetic as S
+    from oracle import esrnerf_port as E
+
+    scene = C.esrnerf_oracle_scene(fx)
+    params, leaves = C.esrnerf_oracle_params(scene, weights)
+    g = torch.Generator().manual_seed(9)               # synthetic.perturb_emit_color
+    params["emit_color"] = (leaves["emo_color.grid"].detach() + 0.05 * torch.randn(leaves["emo_color.grid"].shape, generator=g))
+    n = int(fx["n_rays"])
+    rays = S.make_rays(n, int(fx["ray_seed"]))
+    ft_in = S.finetune_inputs(n)
+    out = E.esrnerf_forward_finetune(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"], ft_in["em_modes"],
+                                     ft_in["em_intensities"], ft_in["em_colors"], float(fx["s_val"]),
+                                     E.FixedDraws(int(fx["draw_seed"]) + 200))
+    return out, leaves
+
+
+@pytest.mark.parametrize("case", C.ESRNERF_CASES)
+def test_esrnerf_finetune_port_matches_golden(case):
+    """forward_finetune (esrnerf.py:241-484): outputs and the only live gradient path (emo_rgbnet / emo_color, Q14)"""
+    fx, weights = C.load_esrnerf_case(case)
+    out, leaves = _finetune_port(fx, weights)
+    for k in out:
+        assert C.rel_err(out[k], torch.from_numpy(fx["ft/" + k])) < 1e-5, k
+    assert out["lin/pbr/emo"].requires_grad and not out["lin/pbr/emo_hat"].requires_grad
+    cot = torch.randn(out["lin/pbr/emo"].shape, generator=torch.Generator().manual_seed(8))
+    (out["lin/pbr/emo"] * cot).sum().backward()
+    with_grad = {k for k, l in leaves.items() if l.grad is not None}
+    assert with_grad == {k[7:].rsplit("/", 1)[0] for k in fx if k.startswith("ftgrad/")}
+    ft = {k[2:]: v for k, v in fx.items() if k.startswith("ftgrad/")}
+    for name in with_grad:
+        err, s_err = C.digest_check(ft, name, leaves[name].grad, rtol=1e-4)
+        assert err < 1.0 and s_err < 1e-4, (name, err, s_err)

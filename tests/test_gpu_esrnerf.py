@@ -172,3 +172,37 @@ def test_esrnerf_edge_cases():
            **{k: batch[k] for k in ("rays_o", "rays_d", "viewdirs")})
     assert (ev["etc/white_bg"] == 1).all() and (ev["lin/env_effects"] == 0).all()
     assert (m.eval_emit(**batch) == 0).all() and (m.eval_esp(**batch) == 0).all()
+
+
+@pytest.mark.parametrize("case", C.ESRNERF_CASES)
+def test_esrnerf_finetune_vs_golden(case):
+    """forward_finetune (esrnerf.py:241-484) with a frozen emit_color copy that differs from emo_color: outputs, which
+    parameters receive gradient (emo_rgbnet / emo_color only) and their values"""
+    from oracle import esrnerf_port as E
+
+    fx, weights = C.load_esrnerf_case(case)
+    m = C.build_product_esrnerf(fx, weights, DEV)
+    m.train(finetune=True)
+    assert "emit_color.grid" in m.state_dict() and not m.emit_color.grid.requires_grad
+    S.perturb_emit_color(m)
+    m.draws = E.FixedDraws(int(fx["draw_seed"]) + 200)
+    n = int(fx["n_rays"])
+    rays = {k: v.to(DEV) for k, v in S.make_rays(n, int(fx["ray_seed"])).items()}
+    ft_in = {k: v.to(DEV) for k, v in S.finetune_inputs(n).items()}
+    out = m(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"], **ft_in)
+    assert set(out) == {"lin/pbr/emo", "lin/pbr/emo_hat"}
+    for k in out:
+        assert C.rel_err(out[k], torch.from_numpy(fx["ft/" + k])) < 1e-2, (k, C.rel_err(out[k], torch.from_numpy(fx["ft/" + k])))
+    assert out["lin/pbr/emo"].requires_grad and not out["lin/pbr/emo_hat"].requires_grad
+    cot = torch.randn(out["lin/pbr/emo"].shape, generator=torch.Generator().manual_seed(8))
+    (out["lin/pbr/emo"] * cot.to(DEV)).sum().backward()
+    got = {name for name, p in m.named_parameters() if p.grad is not None and bool((p.grad != 0).any())}
+    want = {k[7:].rsplit("/", 1)[0] for k in fx if k.startswith("ftgrad/")}
+    assert got == want, got ^ want
+    for name in want:
+        p = dict(m.named_parameters())[name]
+        flat = p.grad.contiguous().reshape(-1).cpu()
+        _, l2 = C.grad_err(flat[torch.from_numpy(fx[f"ftgrad/{name}/idx"])], torch.from_numpy(fx[f"ftgrad/{name}/val"]))
+        assert l2 < 0.1, (name, l2)                      # bf16 tensor-core nets: inherent bound (module docstring)
+    m.train()
+    assert "emit_color.grid" not in m.state_dict()
