@@ -44,7 +44,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=1 << 16, help="rays per GPU per step")
+    ap.add_argument("--stage", default="fine", choices=["fine", "lts", "eval"],
+                    help="fine: BASELINE configs[1] (default, the bench line); lts: configs[2] shape (ESRNeRF LTS+PDRA "
+                         "train step); eval: configs[3] shape (VoxurfF full-image inference, no backward)")
+    ap.add_argument("--rays", type=int, default=None, help="rays per GPU per step (default: 2^16 fine, 2^15 lts, "
+                                                          "1600x1200/N eval)")
+    ap.add_argument("--ltspts", type=int, default=None, help="lts: LTS points per GPU per step (default rays*100/8192)")
+    ap.add_argument("--secondary", type=int, default=256, help="lts: secondary rays per LTS point (cfg/app/lts.yaml:41)")
+    ap.add_argument("--lts-sampler", default="device", choices=["device", "numpy"],
+                    help="lts: draw the LTS points with torch.randperm on the GPU (default) or np.random.choice on the "
+                         "host as the reference does (esrnerf.py:792: O(M3) host work, ~5 ms at this size)")
+    ap.add_argument("--eval-chunk", type=int, default=1 << 18, help="eval: rays per forward_evaluate call")
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--mask-res", type=int, default=100)
     ap.add_argument("--dense", action="store_true", help="dense MaskCache instead of the sparse shell")
@@ -55,7 +65,14 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dense-allreduce", action="store_true",
                     help="N>1: all-reduce the dense grid gradients instead of the occupancy-compacted voxel set")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.rays is None:
+        a.rays = {"fine": 1 << 16, "lts": 1 << 15, "eval": 1600 * 1200 // max(a.gpus, 1)}[a.stage]
+    if a.ltspts is None:
+        a.ltspts = max(1, a.rays * 100 // 8192)
+    if a.stage != "fine" and a.s_val == 20.0:
+        a.s_val = 220.0          # lts.yaml:52 / a converged fine-stage model
+    return a
 
 
 def peaks():
@@ -74,6 +91,14 @@ def peaks():
 
 
 def workload_name(a):
+    if a.stage == "lts":
+        return (f"giftbox_w-like LTS+PDRA stage (ESRNeRF {a.grid}^3, {'dense' if a.dense else 'sparse'} {a.mask_res}^3 "
+                f"MaskCache, s_val {a.s_val:g}, pdra_mode), {a.rays} rays + {a.ltspts} LTS points x {a.secondary} "
+                f"secondary rays /GPU/step, LTS points drawn on the {a.lts_sampler}, synthetic scene")
+    if a.stage == "eval":
+        return (f"DTU-like full-image inference (VoxurfF.forward_evaluate {a.grid}^3, {'dense' if a.dense else 'sparse'} "
+                f"{a.mask_res}^3 MaskCache, s_val {a.s_val:g}), {a.rays} rays/GPU/image in chunks of {a.eval_chunk}, 12 maps, "
+                f"no backward, synthetic scene")
     return (f"giftbox_w-like fine stage (VoxurfF {a.grid}^3, {'dense' if a.dense else 'sparse'} {a.mask_res}^3 MaskCache, "
             f"s_val {a.s_val:g}), {a.rays} rays/GPU/step, synthetic scene")
 
@@ -237,14 +262,63 @@ def algorithmic_work(stage, c):
         "k_mlp_dgrad_tc_tonemap": ("tensor", FLOP_TONEMAP * M3),
     }
     _ = Mcand
+    if "encode_rows" in c:   # lts stage: rows summed over primary / LTS-point / secondary / eps passes (fused.STATS)
+        E, Rf, Rb = c["encode_rows"], c["mlp_fwd_rows"], c["mlp_bwd_rows"]
+        t.update({
+            "k_encode_fwd": ("hbm", (8 + 768 + 384 + 192) * E),
+            "k_encode_bwd": ("hbm", (8 + 2 * (768 + 384) + 224) * c["encode_bwd_rows"]),
+            "k_mlp_fwd_tc_radiance": ("tensor", FLOP_RADIANCE * Rf),
+            "k_mlp_dgrad_tc_radiance": ("tensor", FLOP_RADIANCE * Rb),
+            "k_mlp_wgrad_tc": ("tensor", FLOP_RADIANCE * Rb + 2 * 33 * 192 * M3),
+        })
     return t.get(stage)
 
 
-def run_b200(a, rank, world, local_rank):
-    from esr_nerf_b200 import _lib
+def lts_loss_fn(out, rgbs):
+    """fixed scalar loss with the shape of lts.py:340-420 / pdra.py:390-470: photometric terms + LTS consistency (MSE,
+    both sides carry gradient) + normal / emission / BRDF smoothness (L1 against the eps-jittered evaluations) +
+    certain-ray emission penalty"""
+    l = loss_fn(out, rgbs)
+    l = l + ((out["lin/pbr/off"] - out["lin/pbr/off_hat"]) ** 2).mean() + ((out["lin/pbr/emo"] - out["lin/pbr/emo_hat"]) ** 2).mean()
+    l = l + 0.1 * (out["etc/normal"] - out["etc/normal_eps"]).abs().mean()
+    l = l + 0.1 * (out["etc/emit"] - out["etc/emit_eps"]).abs().mean() + 0.1 * (out["etc/brdf"] - out["etc/brdf_eps"]).abs().mean()
+    return l + (out["etc/emit_cert"] ** 2).mean()
+
+
+def build_stage(a, dev, rank):
+    """(model, host batch (pinned), forward kwargs, loss fn or None) for --stage"""
     from esr_nerf_b200 import synthetic as S
-    from esr_nerf_b200.dist import GridGradCompactor, allreduce_gradients
+
+    dens = S.mask_density(a.mask_res, not a.dense)
+    geo = (S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT, dens, a.s_val, a.grid ** 3)
+    host = S.make_rays(a.rays, 1234 + rank)
+    if a.stage == "lts":
+        from esr_nerf_b200.esrnerf import ESRNeRF
+
+        torch.manual_seed(0)
+        model = ESRNeRF(S.lts_cfg(device=str(dev), num_2ndrays=a.secondary, num_ltspts=a.ltspts), *geo)
+        model.load_state_dict({**model.state_dict(), **random_mlp_weights()})
+        S.fill_esrnerf_model(model)
+        model.pdra_mode = True
+        model.lts_sampler = a.lts_sampler
+        host["uncert_masks"] = S.uncert_masks(a.rays)
+        return model, host, dict(s_val=a.s_val, normal_eps=0.01, emit_eps=0.01), lts_loss_fn
     from esr_nerf_b200.voxurff import VoxurfF
+
+    model = VoxurfF(S.fine_cfg(device=str(dev)), *geo)
+    model.load_state_dict({**model.state_dict(), **random_mlp_weights()})
+    S.fill_fine_model(model)
+    model.mlp_mode = a.mlp_mode
+    if a.stage == "eval":
+        model.eval()
+        host["em_modes"] = torch.zeros_like(host["em_modes"])      # DTU: all emission-off (data/dtu.py:180-183)
+        return model, host, dict(pos_rt=torch.eye(3)), None
+    return model, host, dict(s_val=a.s_val), loss_fn
+
+
+def run_b200(a, rank, world, local_rank):
+    from esr_nerf_b200 import _lib, fused
+    from esr_nerf_b200.dist import GridGradCompactor, allreduce_gradients
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 render path has no CPU fallback")
@@ -257,29 +331,38 @@ def run_b200(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    model = VoxurfF(S.fine_cfg(device=str(dev)), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX,
-                    S.MASK_ALPHA_INIT, S.mask_density(a.mask_res, not a.dense), a.s_val, a.grid ** 3)
-    model.load_state_dict({**model.state_dict(), **random_mlp_weights()})
-    S.fill_fine_model(model)
-    model.mlp_mode = a.mlp_mode
+    model, host, fwd_kw, stage_loss = build_stage(a, dev, rank)
     model.keep_streams = True
     params = [p for p in model.parameters() if p.requires_grad]
-    compactor = GridGradCompactor(model) if (world > 1 and not a.dense_allreduce) else None
+    compactor = GridGradCompactor(model) if (world > 1 and not a.dense_allreduce and a.stage == "fine") else None
     reduced = [0]
 
-    host = S.make_rays(a.rays, 1234 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     batch = {k: v.to(dev) for k, v in host.items()}
 
-    def step(b):
+    def train_step(b):
         for p in params:
             p.grad = None
-        out = model(s_val=a.s_val, **b)
-        loss = loss_fn(out, b["rgbs"])
+        fused.reset_stats()
+        out = model(**fwd_kw, **{k: v for k, v in b.items() if k != "rgbs" or a.stage == "fine"})
+        loss = stage_loss(out, b["rgbs"])
         loss.backward()
         if dist is not None:  # rays sharded, gradients summed once per step (north_star)
             reduced[0] = compactor.allreduce() if compactor is not None else allreduce_gradients(params)
         return out, loss
+
+    def eval_step(b):
+        """one full image: contiguous ray chunks through forward_evaluate, all 12 maps kept (BASELINE configs[3])"""
+        outs = []
+        n = b["rays_o"].shape[0]
+        for lo in range(0, n, a.eval_chunk):
+            sl = slice(lo, min(lo + a.eval_chunk, n))
+            outs.append(model(rays_o=b["rays_o"][sl], rays_d=b["rays_d"][sl], viewdirs=b["viewdirs"][sl],
+                              em_modes=torch.tensor(0), **fwd_kw))
+        out = {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+        return out, out["etc/depth"].mean()
+
+    step = eval_step if a.stage == "eval" else train_step
 
     def sync_all():
         if dist is not None:
@@ -290,8 +373,18 @@ def run_b200(a, rank, world, local_rank):
         step(batch)
     sync_all()
     st = model.last_streams["streams"]
-    counts = {"N": a.rays, "Mraw": int(st.n_steps.sum()), "M0": int(st.cnt_inbox.sum()), "M1": st.m1, "M3": st.m3,
+    counts = {"N": st.n_rays, "Mraw": int(st.n_steps.sum()), "M0": int(st.cnt_inbox.sum()), "M1": st.m1, "M3": st.m3,
               "M3_on": st.m3_on}
+    if a.stage == "eval":   # the last chunk only is kept in last_streams: scale to the image
+        f = a.rays / max(st.n_rays, 1)
+        counts = {k: int(v * f) for k, v in counts.items()}
+        counts["M3_on"] = counts["M3"]
+    if a.stage == "lts":
+        st2 = model.last_streams["lts"]["streams"]
+        counts.update(secondary_rays=st2.n_rays, M0_secondary=int(st2.cnt_inbox.sum()), M1_secondary=st2.m1,
+                      M3_secondary=st2.m3, encode_rows=fused.STATS["encode_rows"], mlp_fwd_rows=fused.STATS["mlp_fwd_rows"],
+                      mlp_bwd_rows=fused.STATS["mlp_bwd_rows"],
+                      encode_bwd_rows=fused.STATS["encode_rows"])
 
     # ---- device-resident timed region (value) with per-kernel events (roofline) ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -324,8 +417,8 @@ def run_b200(a, rank, world, local_rank):
         for _ in range(a.steps):
             b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             out, loss = step(b)
-            res = [out["srgb/rgb"].detach().cpu(), out["lin/rgb"].detach().cpu(), out["etc/alphainv_cum"].detach().cpu(),
-                   loss.detach().cpu()]
+            keys = sorted(out) if a.stage == "eval" else ["srgb/rgb", "lin/rgb", "etc/alphainv_cum"]
+            res = [out[k].detach().cpu() for k in keys] + [loss.detach().cpu()]
             d2h = sum(r.numel() * r.element_size() for r in res)
         e1.record()
         sync_all()
@@ -365,7 +458,7 @@ def run_b200(a, rank, world, local_rank):
                     "share_of_kernel_time": top["ms_per_step"] / max(sum(r["ms_per_step"] for r in stage_rows), 1e-9)}
 
     cpu_baseline = None
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and a.stage == "fine":
         scene, cparams, leaves, crays = cpu_port_setup(a)
         cpu_port_step(a, scene, cparams, leaves, crays)
         reps = 2
@@ -378,8 +471,10 @@ def run_b200(a, rank, world, local_rank):
                                   f"1 warm-up + {reps} timed steps"}
 
     total_rays = a.rays * world * a.steps
+    metric = {"fine": METRIC, "lts": "train rays/sec (fwd+bwd), LTS+PDRA stage",
+              "eval": "render rays/sec (inference, 12 maps)"}[a.stage]
     line = {
-        "metric": METRIC, "value": total_rays / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "metric": metric, "value": total_rays / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (grids, scan, compositing) + bf16 tensor-core MLPs, f32 accumulate"
         if a.mlp_mode == "bf16" else "f32",
@@ -387,6 +482,7 @@ def run_b200(a, rank, world, local_rank):
         "config": {"workload": workload_name(a),
                    "parallelism": f"dp{world} (rays sharded, one gradient allreduce per step"
                                   + (f", {reduced[0] / 1e6:.0f} MB/rank" if world > 1 else "") + ")",
+                   "stage": a.stage,
                    "l2": "working set (0.83 GB of grids + grads) exceeds the 126 MB L2; no flush between steps",
                    "counts_per_gpu_step": counts,
                    "samples_per_s": {"candidate_M0": counts["M0"] * world * a.steps / (ms * 1e-3),

@@ -420,7 +420,7 @@ struct BwdSm {
   static constexpr int bytes = bar + 16;
 };
 
-template <int K0, int NH, int DXN, int NO>
+template <int K0, int NH, int DXN, int NO, bool ACC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_dgrad_tc(const uint8_t *__restrict__ image_bwd, const float *__restrict__ y, const float *__restrict__ d_y,
                    int64_t row_begin, int64_t row_end, int64_t m_total, const __nv_bfloat16 *__restrict__ hidden,
@@ -481,6 +481,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     uint2 cur_mask[NH];
 #pragma unroll
     for (int l = 0; l < NH; ++l) cur_mask[l] = pf_mask[l];
+    // accumulate mode: the previous d_x values of this thread's 16 columns are requested now, a whole layer chain
+    // ahead of the epilogue that adds to them (a read-modify-write at the end would stall the only tile in flight)
+    float4 old_dx[ACC ? 4 : 1];
+    if (ACC && valid && d_x && et.grp < DXN / 16) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = et.grp * 16 + 4 * q;
+        old_dx[q] = col < dx_cols ? *reinterpret_cast<const float4 *>(d_x + row * dx_cols + col)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column group 0 threads) ----
     if (is_epi && et.grp == 0) {
       float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -586,8 +597,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               float4 *p4 = reinterpret_cast<float4 *>(d_x + row * dx_cols + col);
               float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
                                      __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-              if (accumulate) {
-                const float4 o = *p4;
+              if (ACC) {
+                const float4 o = old_dx[ACC ? q : 0];
                 v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
               }
               *p4 = v;
@@ -820,11 +831,11 @@ static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x,
   return ESR_OK;
 }
 
-template <int K0, int NH, int DXN, int NO>
-static int launch_dgrad(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const float *y, const float *d_y,
+template <int K0, int NH, int DXN, int NO, bool ACC>
+static int launch_dgrad_acc(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const float *y, const float *d_y,
                         int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z, float *d_z_out, float *d_x,
                         int dx_cols, int accumulate, cudaStream_t st) {
-  auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO>;
+  auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC>;
   constexpr int bytes = BwdSm<K0, NH, DXN>::bytes;
   if (int e = set_smem_tc(kern, bytes)) return e;
   ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_tc_radiance" : "k_mlp_dgrad_tc_tonemap", st);
@@ -833,6 +844,19 @@ static int launch_dgrad(const esr_mlp_desc_t *d, const TcLayout &T, const void *
                                                     dx_cols, accumulate, d->n_out, d->act);
   ESR_LAUNCH_OK();
   return ESR_OK;
+}
+
+template <int K0, int NH, int DXN, int NO>
+static int launch_dgrad(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const float *y, const float *d_y,
+                        int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z, float *d_z_out, float *d_x,
+                        int dx_cols, int accumulate, cudaStream_t st) {
+  // the accumulate variant carries the prefetched old d_x values in 16 more registers: separate instantiation so the
+  // write-only variant (the fine stage's disjoint row ranges) keeps its register budget
+  if (accumulate && d_x)
+    return launch_dgrad_acc<K0, NH, DXN, NO, true>(d, T, image, y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x, dx_cols,
+                                                   accumulate, st);
+  return launch_dgrad_acc<K0, NH, DXN, NO, false>(d, T, image, y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x, dx_cols,
+                                                  accumulate, st);
 }
 
 }  // namespace

@@ -35,6 +35,9 @@ class ESRNeRF(VoxurfF):
                  mask_density: torch.Tensor, s_val: float, num_voxles: int):
         self.pdra_mode = False
         self.draws = None
+        # "numpy": np.random.choice on the host exactly as the reference (esrnerf.py:792; O(M3) host work per step);
+        # "device": torch.randperm on the GPU — same distribution, different stream, no host round trip
+        self.lts_sampler = "numpy"
         # sdf / off / emo grids, radiance nets and tone mapper are constructed exactly as in VoxurfF
         # (esrnerf.py:101-172 == voxurff.py:79-130), in the same order (same seeded initialisation)
         super().__init__(cfg, near, far, xyz_min, xyz_max, mask_xyz_min, mask_xyz_max, mask_alpha_init, mask_density,
@@ -101,6 +104,8 @@ class ESRNeRF(VoxurfF):
     def _choice(self, n: int, k: int, dev) -> torch.Tensor:
         if self.draws is not None:
             return self.draws.choice(n, k).to(dev)
+        if self.lts_sampler == "device":
+            return torch.randperm(n, device=dev)[:k]
         return torch.from_numpy(np.random.choice(n, k, replace=False)).to(dev)
 
     def _randn(self, *shape, dev) -> torch.Tensor:

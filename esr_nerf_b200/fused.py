@@ -21,6 +21,16 @@ import torch
 from . import _lib
 from ._lib import MlpDesc, Scene, check, ptr, stream_ptr
 
+# per-step work counters for bench.py's roofline block (rows through the encode / MLP kernels, summed over every
+# pass of a step: primary rays, LTS points, secondary rays, eps branches); reset by the caller
+STATS = {"encode_rows": 0, "mlp_fwd_rows": 0, "mlp_bwd_rows": 0, "m0": 0, "m1": 0, "m3": 0}
+
+
+def reset_stats():
+    for k in STATS:
+        STATS[k] = 0
+
+
 FEAT_DIM = 96
 FEAT_GRAD_DIM = 56
 TFEAT_DIM = 48
@@ -48,6 +58,54 @@ def make_scene(xyz_min, xyz_max, grid_size, mask_xyz_min, mask_xyz_max, mask_siz
     sc.fd_eps = float(fd_eps)
     sc.sdf_tap_manual = int(bool(sdf_tap_manual))
     return sc
+
+
+class _GradSink:
+    """Dense grid gradients are accumulated in ONE buffer per parameter per backward pass.
+
+    Every stage that scatters into a grid gradient (alpha path, encode, analytic SDF gradient — up to a dozen calls in
+    an LTS step) would otherwise return its own zero-filled dense volume (64-384 MB each at 256^3) for autograd to
+    sum.  Instead a backward asks the sink for the parameter's buffer (zero-filled once, in the parameter's memory
+    format), scatters into it and returns None for that input; a callback queued on the autograd engine adds the
+    buffer into ``param.grad`` when the backward pass ends.  Only leaf parameters take this route (a non-leaf grid,
+    e.g. the coarse stage's smoothed SDF, gets an ordinary gradient tensor); ``torch.autograd.grad`` on the grids is
+    not supported by it (the reference's drivers call ``loss.backward()``, fine.py:382)."""
+
+    def __init__(self):
+        self.bufs = {}
+        self.armed = False
+
+    @staticmethod
+    def eligible(t: Optional[torch.Tensor]) -> bool:
+        return t is not None and t.is_leaf and t.requires_grad
+
+    def get(self, param: torch.Tensor) -> torch.Tensor:
+        key = id(param)
+        if key not in self.bufs:
+            self.bufs[key] = (param, torch.zeros_like(param))
+            if not self.armed:
+                torch.autograd.Variable._execution_engine.queue_callback(self.flush)
+                self.armed = True
+        return self.bufs[key][1]
+
+    def flush(self):
+        bufs, self.bufs, self.armed = self.bufs, {}, False
+        for param, buf in bufs.values():
+            if param.grad is None:
+                param.grad = buf
+            else:
+                param.grad.add_(buf)
+
+
+GRAD_SINK = _GradSink()
+
+
+def _grad_target(param: Optional[torch.Tensor], like: torch.Tensor):
+    """(buffer to scatter into, value to return to autograd) for a grid input of a backward"""
+    if _GradSink.eligible(param):
+        return GRAD_SINK.get(param), None
+    g = torch.zeros_like(like)
+    return g, g
 
 
 def _i32(n, dev):
@@ -141,7 +199,7 @@ class AlphaScan(torch.autograd.Function):
                                     ptr(streams.s_sdf), ptr(off_shade), ptr(streams.s_alpha), ptr(streams.s_T),
                                     ptr(streams.h_ray), ptr(streams.h_step), ptr(streams.h_m1), ptr(h_w),
                                     ptr(streams.h_sdf), st))
-        ctx.sc, ctx.streams = sc, streams
+        ctx.sc, ctx.streams, ctx.grid_param = sc, streams, sdf_grid
         ctx.save_for_backward(rays_o, rays_d, last, sdf_grid)
         ctx.mark_non_differentiable()
         return h_w, last
@@ -152,9 +210,9 @@ class AlphaScan(torch.autograd.Function):
         rays_o, rays_d, last, sdf_grid = ctx.saved_tensors
         s: Streams = ctx.streams
         dev = rays_o.device
-        grad_sdf = torch.zeros_like(sdf_grid)
         if s.m1 == 0:
-            return grad_sdf, None, None, None, None, None
+            return None, None, None, None, None, None
+        grad_sdf, ret_sdf = _grad_target(ctx.grid_param, sdf_grid)
         g_w_m1 = torch.zeros(s.m1, dtype=torch.float32, device=dev)
         if s.m3:
             g_w_m1.index_copy_(0, s.h_m1.long(), g_hw.contiguous())
@@ -163,7 +221,7 @@ class AlphaScan(torch.autograd.Function):
                                             ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(s.s_alpha),
                                             ptr(s.s_T), ptr(last), ptr(g_w_m1), ptr(g_last.contiguous()), ptr(tmp_p),
                                             ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
-        return grad_sdf, None, None, None, None, None
+        return ret_sdf, None, None, None, None, None
 
 
 def _desc(d: dict) -> MlpDesc:
@@ -189,14 +247,13 @@ def encode_features(sc: Scene, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo
     return x
 
 
-def encode_backward(sc: Scene, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s: Streams, d_feat):
-    g_sdf = torch.zeros_like(sdf_grid)
-    g_off = torch.zeros_like(off_grid)
-    g_emo = torch.zeros_like(emo_grid)
+def encode_backward(sc: Scene, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s: Streams, d_feat, params=(None, None, None)):
+    """params: the (sdf, off, emo) grid inputs of the calling Function — leaf parameters accumulate in GRAD_SINK"""
+    (g_sdf, r_sdf), (g_off, r_off), (g_emo, r_emo) = (_grad_target(p, g) for p, g in zip(params, (sdf_grid, off_grid, emo_grid)))
     check(_lib.lib().esr_encode_bwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(sdf_grid), 6, ptr(s.h_ray),
                                     ptr(s.h_step), s.m3, ptr(d_feat), ptr(g_sdf), ptr(g_off), ptr(g_emo),
                                     stream_ptr()))
-    return g_sdf, g_off, g_emo
+    return r_sdf, r_off, r_emo
 
 
 def sdf_fd_gradient(sc: Scene, rays_o, rays_d, sdf_grid, s: Streams) -> torch.Tensor:
@@ -245,7 +302,7 @@ class Encode(torch.autograd.Function):
     def forward(ctx, sdf_grid, off_grid, emo_grid, sc, rays_o, rays_d, viewdirs, streams):
         _check_cl(off_grid, "off_color.grid")
         _check_cl(emo_grid, "emo_color.grid")
-        ctx.sc, ctx.streams = sc, streams
+        ctx.sc, ctx.streams, ctx.grid_params = sc, streams, (sdf_grid, off_grid, emo_grid)
         ctx.save_for_backward(rays_o, rays_d, sdf_grid, off_grid, emo_grid)
         return encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, streams, bf16=False)
 
@@ -254,7 +311,7 @@ class Encode(torch.autograd.Function):
     def backward(ctx, d_x):
         rays_o, rays_d, sdf_grid, off_grid, emo_grid = ctx.saved_tensors
         d_feat = d_x[:, :FEAT_GRAD_DIM].contiguous()
-        g = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, ctx.streams, d_feat)
+        g = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, ctx.streams, d_feat, ctx.grid_params)
         return (*g, None, None, None, None, None)
 
 
@@ -303,7 +360,7 @@ class Shade(torch.autograd.Function):
         img_off, img_emo = mlp_pack(RADIANCE_DESC, flat_off), mlp_pack(RADIANCE_DESC, flat_emo)
         lin_off, hid_off = _mlp_forward(RADIANCE_DESC, img_off, x, 0, s.m3, s.m3, train, save_begin=off_grad_rows[0])
         lin_emo, hid_emo = _mlp_forward(RADIANCE_DESC, img_emo, x, 0, s.m3_on, s.m3, train)
-        ctx.sc, ctx.streams = sc, s
+        ctx.sc, ctx.streams, ctx.grid_params = sc, s, (sdf_grid, off_grid, emo_grid)
         ctx.rows = (off_grad_rows, emo_grad_rows)
         ctx.hidden = (hid_off, hid_emo)
         ctx.save_for_backward(rays_o, rays_d, sdf_grid, off_grid, emo_grid, x, img_off, img_emo, lin_off, lin_emo)
@@ -326,7 +383,8 @@ class Shade(torch.autograd.Function):
         g_emo_flat, _ = _mlp_backward(RADIANCE_DESC, img_emo, x, lin_emo, d_emo.contiguous(), eb, ee, s.m3, hid_emo,
                                       d_x, FEAT_GRAD_DIM, acc, scratch)
         ctx.hidden = None
-        g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x)
+        g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x,
+                                                ctx.grid_params)
         return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None
 
 
@@ -565,7 +623,7 @@ class SdfExpGrad(torch.autograd.Function):
         grad = _f32(m, 3, dev=pts.device)
         check(_lib.lib().esr_sdf_expgrad_fwd(ctypes.byref(sc), ptr(pts), ptr(sdf_grid), m, 1, None, ptr(grad),
                                              stream_ptr()))
-        ctx.sc = sc
+        ctx.sc, ctx.grid_param = sc, sdf_grid
         ctx.save_for_backward(pts, sdf_grid)
         return grad
 
@@ -573,10 +631,12 @@ class SdfExpGrad(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_grad):
         pts, sdf_grid = ctx.saved_tensors
-        g = torch.zeros_like(sdf_grid)
+        if pts.shape[0] == 0:
+            return None, None, None
+        g, ret = _grad_target(ctx.grid_param, sdf_grid)
         check(_lib.lib().esr_sdf_expgrad_bwd(ctypes.byref(ctx.sc), ptr(pts), pts.shape[0], None,
                                              ptr(g_grad.contiguous()), ptr(g), stream_ptr()))
-        return g, None, None
+        return ret, None, None
 
 
 @dataclass
@@ -622,6 +682,9 @@ class ShadePBR(torch.autograd.Function):
                                    ptr(p.h_ray), ptr(p.h_step), ptr(p.h_sdf), m, ptr(x), ptr(x2), 1, stream_ptr()))
         descs = (RADIANCE_DESC, RADIANCE_DESC, EMIT_DESC, BRDF_DESC)
         flats = (flat_off, flat_emo, flat_emit, flat_brdf)
+        STATS["encode_rows"] += m
+        STATS["mlp_fwd_rows"] += m * sum(use)
+        STATS["mlp_bwd_rows"] += m * sum(use) if train else 0
         outs, imgs, hids = [], [], []
         for k in range(4):
             if not use[k]:
@@ -635,6 +698,7 @@ class ShadePBR(torch.autograd.Function):
             imgs.append(img)
             hids.append(hid)
         ctx.sc, ctx.pos, ctx.use, ctx.hids = sc, p, use, hids
+        ctx.grid_params = (sdf_grid, off_grid, emo_grid, brdf_grid)
         ctx.n_saved = [t is not None for t in imgs]
         ctx.save_for_backward(sdf_grid, off_grid, emo_grid, brdf_grid if use[3] else sdf_grid.new_zeros(0), x,
                               x2 if x2 is not None else x.new_zeros(0), *[t for t in imgs if t is not None], *outs)
@@ -666,11 +730,17 @@ class ShadePBR(torch.autograd.Function):
                 d_brdf_c = d_x[:, :6].contiguous()
                 d_x[:, :6] = 0
         ctx.hids = None
-        g_sdf = torch.zeros_like(sdf_grid)
-        g_off = torch.zeros_like(off_grid) if use[0] else None
-        g_emo = torch.zeros_like(emo_grid) if (use[1] or use[2]) else None
-        g_brdf = torch.zeros_like(brdf_grid) if use[3] else None
+        if m == 0:
+            return (None, None, None, None, *g_flat, None, None, None)
+        needs = ctx.needs_input_grad
+        gp = ctx.grid_params
+        g_sdf, r_sdf = _grad_target(gp[0], sdf_grid) if needs[0] else (torch.zeros_like(sdf_grid), None)
+        g_off, r_off = _grad_target(gp[1], off_grid) if (use[0] and needs[1]) else (None, None)
+        g_emo, r_emo = _grad_target(gp[2], emo_grid) if ((use[1] or use[2]) and needs[2]) else (None, None)
+        g_brdf, r_brdf = _grad_target(gp[3], brdf_grid) if (use[3] and needs[3]) else (None, None)
+        if g_brdf is None:
+            d_brdf_c = None
         check(_lib.lib().esr_encode_pbr_bwd(ctypes.byref(ctx.sc), ptr(p.rays_o), ptr(p.rays_d), ptr(sdf_grid), 6,
                                             ptr(p.pts), ptr(p.h_ray), ptr(p.h_step), m, ptr(d_x), ptr(d_brdf_c),
                                             ptr(g_sdf), ptr(g_off), ptr(g_emo), ptr(g_brdf), stream_ptr()))
-        return (g_sdf, g_off, g_emo, g_brdf, *g_flat, None, None, None)
+        return (r_sdf, r_off, r_emo, r_brdf, *g_flat, None, None, None)
