@@ -140,8 +140,8 @@ PROTOTYPES = {
     "esr_encode_coarse_bwd": (I32, [SCENE_P, P, P, P, P, P, I64, P, P, P, P, P]),
     "esr_encode_fwd": (I32, [SCENE_P, P, P, P, P, P, P, I32, P, P, P, I64, P, I32, P]),
     "esr_encode_bwd": (I32, [SCENE_P, P, P, P, I32, P, P, I64, P, P, P, P, P]),
-    "esr_encode_pbr_fwd": (I32, [SCENE_P, P, P, P, P, P, P, P, I32, P, P, P, P, I64, P, P, I32, P]),
-    "esr_encode_pbr_bwd": (I32, [SCENE_P, P, P, P, I32, P, P, P, I64, P, P, P, P, P, P, P]),
+    "esr_encode_pbr_fwd": (I32, [SCENE_P, P, P, P, P, P, P, P, I32, P, P, P, P, I64, P, P, I32, P, P]),
+    "esr_encode_pbr_bwd": (I32, [SCENE_P, P, P, P, I32, P, P, P, I64, P, P, P, P, P, P, P, P]),
     "esr_sample_points": (I32, [SCENE_P, P, P, P, P, I64, P, P]),
     "esr_sdf_expgrad_fwd": (I32, [SCENE_P, P, P, I64, I32, P, P, P]),
     "esr_sdf_expgrad_bwd": (I32, [SCENE_P, P, I64, P, P, P, P]),

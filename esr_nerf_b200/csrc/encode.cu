@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
                  const float *__restrict__ emo_grid, const int32_t *__restrict__ h_ray,
                  const int32_t *__restrict__ h_step, const float *__restrict__ h_sdf, int64_t m3,
                  OutT *__restrict__ feat, const float *__restrict__ pts, const float *__restrict__ third_grid,
-                 OutT *__restrict__ feat2) {
+                 OutT *__restrict__ feat2, float *__restrict__ save_fd) {
   __shared__ float s_lines[N_LINES * ENC_THREADS];
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m3) return;
@@ -280,6 +280,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
       const float nrm = fmaxf(sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]), 1e-12f);
 #pragma unroll
       for (int a = 0; a < 3; ++a) v[25 + a * 4 + k] = __fdiv_rn(gr[a], nrm);
+      // the un-normalised finite-difference gradients, f32, for the backward pass (it then needs no grid reads at all)
+      if (save_fd) *reinterpret_cast<float4 *>(save_fd + j * 16 + 4 * k) = make_float4(gr[0], gr[1], gr[2], 0.f);
     }
     v[37] = __fdiv_rn(__fsub_rn(px, sc.xyz_min[0]), __fsub_rn(sc.xyz_max[0], sc.xyz_min[0]));
     v[38] = __fdiv_rn(__fsub_rn(py, sc.xyz_min[1]), __fsub_rn(sc.xyz_max[1], sc.xyz_min[1]));
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
                  const int32_t *__restrict__ h_ray, const int32_t *__restrict__ h_step, int64_t m3,
                  const float *__restrict__ d_feat, float *__restrict__ g_sdf, float *__restrict__ g_off,
                  float *__restrict__ g_emo, const float *__restrict__ pts, const float *__restrict__ d_third,
-                 float *__restrict__ g_third) {
+                 float *__restrict__ g_third, const float *__restrict__ saved_fd) {
   __shared__ float s_lines[N_LINES * ENC_THREADS], s_dl[N_LINES * ENC_THREADS];
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m3) return;
@@ -362,25 +364,34 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
   }
   const float disp[4] = {0.5f, 1.0f, 1.5f, 2.0f};
   const SdfFrame fr = make_frame(sc, g.ix, g.iy, g.iz);
-  load_lines(fr, sdf_grid, s_lines);
+  // the finite-difference gradients either come from the forward pass (saved_fd: no grid reads in this kernel) or
+  // are recomputed from the 18 line values
+  if (!saved_fd) load_lines(fr, sdf_grid, s_lines);
 #pragma unroll
   for (int i = 0; i < N_LINES; ++i) s_dl[i * ENC_THREADS + threadIdx.x] = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     TapRef tr[6];
-    float f[6];
 #pragma unroll
-    for (int t = 0; t < 6; ++t) {
-      tr[t] = tap_ref(fr, t >> 1, (t & 1) ? disp[k] : -disp[k]);
-      const float lo = s_lines[tr[t].slot * ENC_THREADS + threadIdx.x], hi = s_lines[(tr[t].slot + 1) * ENC_THREADS + threadIdx.x];
-      f[t] = __fmaf_rn(hi, tr[t].wh, __fmul_rn(lo, tr[t].wl));
-    }
+    for (int t = 0; t < 6; ++t) tr[t] = tap_ref(fr, t >> 1, (t & 1) ? disp[k] : -disp[k]);
     float gr[3], scale[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const float diff = tr[2 * a + 1].coord - tr[2 * a].coord + sc.fd_eps;
       scale[a] = 1.f / diff / sc.voxel_size;
-      gr[a] = (f[2 * a + 1] - f[2 * a]) * scale[a];
+    }
+    if (saved_fd) {
+      const float4 q = __ldg(reinterpret_cast<const float4 *>(saved_fd + j * 16 + 4 * k));
+      gr[0] = q.x, gr[1] = q.y, gr[2] = q.z;
+    } else {
+      float f[6];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        const float lo = s_lines[tr[t].slot * ENC_THREADS + threadIdx.x], hi = s_lines[(tr[t].slot + 1) * ENC_THREADS + threadIdx.x];
+        f[t] = __fmaf_rn(hi, tr[t].wh, __fmul_rn(lo, tr[t].wl));
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) gr[a] = (f[2 * a + 1] - f[2 * a]) * scale[a];
     }
     const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
     const float den = fmaxf(nrm, 1e-12f);
@@ -681,7 +692,7 @@ static int encode_fwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
                            const float *sdf_grid, const float *off_color_grid, const float *emo_color_grid,
                            const float *third_grid, int color_dim, const float *pts, const int32_t *h_ray,
                            const int32_t *h_step, const float *h_sdf, int64_t m3, void *feat, void *feat2,
-                           int out_is_bf16, esr_stream_t stream) {
+                           int out_is_bf16, float *save_fd, esr_stream_t stream) {
   if (int e = check_scene2(sc)) return e;
   ESR_CHECK_ARG(color_dim == 6);  // cfg/app/fine.yaml:20; other widths are not instantiated
   ESR_CHECK_ARG(m3 >= 0);
@@ -695,11 +706,11 @@ static int encode_fwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
     k_encode_fwd<__nv_bfloat16><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,
                                                                emo_color_grid, h_ray, h_step, h_sdf, m3,
                                                                (__nv_bfloat16 *)feat, pts, third_grid,
-                                                               (__nv_bfloat16 *)feat2);
+                                                               (__nv_bfloat16 *)feat2, save_fd);
   else
     k_encode_fwd<float><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,
                                                        emo_color_grid, h_ray, h_step, h_sdf, m3, (float *)feat, pts,
-                                                       third_grid, (float *)feat2);
+                                                       third_grid, (float *)feat2, save_fd);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -707,7 +718,7 @@ static int encode_fwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
 static int encode_bwd_impl(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *sdf_grid,
                            int color_dim, const float *pts, const int32_t *h_ray, const int32_t *h_step, int64_t m3,
                            const float *d_feat, const float *d_third, float *grad_sdf_grid, float *grad_off_grid,
-                           float *grad_emo_grid, float *grad_third_grid, esr_stream_t stream) {
+                           float *grad_emo_grid, float *grad_third_grid, const float *saved_fd, esr_stream_t stream) {
   if (int e = check_scene2(sc)) return e;
   ESR_CHECK_ARG(color_dim == 6);
   ESR_CHECK_ARG(m3 >= 0);
@@ -718,7 +729,7 @@ static int encode_bwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
   ESR_STAGE("k_encode_bwd", (cudaStream_t)stream);
   k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
                                                                 d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
-                                                                pts, d_third, grad_third_grid);
+                                                                pts, d_third, grad_third_grid, saved_fd);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -729,7 +740,7 @@ extern "C" int esr_encode_fwd(const esr_scene_t *sc, const float *rays_o, const 
                               int64_t m3, void *feat, int out_is_bf16, esr_stream_t stream) {
   ESR_CHECK_ARG(m3 == 0 || (rays_o && rays_d && h_ray && h_step));
   return encode_fwd_impl(sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid, emo_color_grid, nullptr, color_dim,
-                         nullptr, h_ray, h_step, h_sdf, m3, feat, nullptr, out_is_bf16, stream);
+                         nullptr, h_ray, h_step, h_sdf, m3, feat, nullptr, out_is_bf16, nullptr, stream);
 }
 
 extern "C" int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *sdf_grid,
@@ -738,25 +749,25 @@ extern "C" int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const 
                               esr_stream_t stream) {
   ESR_CHECK_ARG(m3 == 0 || (rays_o && rays_d && h_ray && h_step));
   return encode_bwd_impl(sc, rays_o, rays_d, sdf_grid, color_dim, nullptr, h_ray, h_step, m3, d_feat, nullptr,
-                         grad_sdf_grid, grad_off_grid, grad_emo_grid, nullptr, stream);
+                         grad_sdf_grid, grad_off_grid, grad_emo_grid, nullptr, nullptr, stream);
 }
 
 extern "C" int esr_encode_pbr_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
                                   const float *viewdirs, const float *sdf_grid, const float *off_color_grid,
                                   const float *emo_color_grid, const float *brdf_grid, int color_dim, const float *pts,
                                   const int32_t *h_ray, const int32_t *h_step, const float *h_sdf, int64_t m3,
-                                  void *feat, void *feat_brdf, int out_is_bf16, esr_stream_t stream) {
+                                  void *feat, void *feat_brdf, int out_is_bf16, float *save_fd, esr_stream_t stream) {
   return encode_fwd_impl(sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid, emo_color_grid, brdf_grid, color_dim,
-                         pts, h_ray, h_step, h_sdf, m3, feat, feat_brdf, out_is_bf16, stream);
+                         pts, h_ray, h_step, h_sdf, m3, feat, feat_brdf, out_is_bf16, save_fd, stream);
 }
 
 extern "C" int esr_encode_pbr_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
                                   const float *sdf_grid, int color_dim, const float *pts, const int32_t *h_ray,
                                   const int32_t *h_step, int64_t m3, const float *d_feat, const float *d_brdf_color,
                                   float *grad_sdf_grid, float *grad_off_grid, float *grad_emo_grid,
-                                  float *grad_brdf_grid, esr_stream_t stream) {
+                                  float *grad_brdf_grid, const float *saved_fd, esr_stream_t stream) {
   return encode_bwd_impl(sc, rays_o, rays_d, sdf_grid, color_dim, pts, h_ray, h_step, m3, d_feat, d_brdf_color,
-                         grad_sdf_grid, grad_off_grid, grad_emo_grid, grad_brdf_grid, stream);
+                         grad_sdf_grid, grad_off_grid, grad_emo_grid, grad_brdf_grid, saved_fd, stream);
 }
 
 extern "C" int esr_encode_coarse_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d,

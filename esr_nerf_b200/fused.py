@@ -237,22 +237,27 @@ def mlp_pack(desc: dict, flat: torch.Tensor) -> torch.Tensor:
     return image
 
 
-def encode_features(sc: Scene, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s: Streams, bf16: bool):
+def encode_features(sc: Scene, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s: Streams, bf16: bool,
+                    save_fd: bool = False):
+    """feature rows of the shaded stream; save_fd=True also returns the f32 [m3,16] finite-difference gradients the
+    backward then reuses instead of re-gathering the SDF taps"""
     # bf16 rows are written in the library's tiled layout (padded to whole 128-row tiles); f32 rows are row-major
     rows = _lib.lib().esr_mlp_act_rows(s.m3) if bf16 else s.m3
     x = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16 if bf16 else torch.float32, device=rays_o.device)
-    check(_lib.lib().esr_encode_fwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(viewdirs), ptr(sdf_grid),
-                                    ptr(off_grid), ptr(emo_grid), 6, ptr(s.h_ray), ptr(s.h_step), ptr(s.h_sdf), s.m3,
-                                    ptr(x), int(bf16), stream_ptr()))
-    return x
+    fd = torch.empty(s.m3, 16, dtype=torch.float32, device=rays_o.device) if save_fd else None
+    check(_lib.lib().esr_encode_pbr_fwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(viewdirs), ptr(sdf_grid),
+                                        ptr(off_grid), ptr(emo_grid), None, 6, None, ptr(s.h_ray), ptr(s.h_step),
+                                        ptr(s.h_sdf), s.m3, ptr(x), None, int(bf16), ptr(fd), stream_ptr()))
+    return (x, fd) if save_fd else x
 
 
-def encode_backward(sc: Scene, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s: Streams, d_feat, params=(None, None, None)):
+def encode_backward(sc: Scene, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s: Streams, d_feat, params=(None, None, None),
+                    saved_fd=None):
     """params: the (sdf, off, emo) grid inputs of the calling Function — leaf parameters accumulate in GRAD_SINK"""
     (g_sdf, r_sdf), (g_off, r_off), (g_emo, r_emo) = (_grad_target(p, g) for p, g in zip(params, (sdf_grid, off_grid, emo_grid)))
-    check(_lib.lib().esr_encode_bwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(sdf_grid), 6, ptr(s.h_ray),
-                                    ptr(s.h_step), s.m3, ptr(d_feat), ptr(g_sdf), ptr(g_off), ptr(g_emo),
-                                    stream_ptr()))
+    check(_lib.lib().esr_encode_pbr_bwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(sdf_grid), 6, None, ptr(s.h_ray),
+                                        ptr(s.h_step), s.m3, ptr(d_feat), None, ptr(g_sdf), ptr(g_off), ptr(g_emo),
+                                        None, ptr(saved_fd), stream_ptr()))
     return r_sdf, r_off, r_emo
 
 
@@ -356,20 +361,20 @@ class Shade(torch.autograd.Function):
         _check_cl(emo_grid, "emo_color.grid")
         s: Streams = streams
         train = any(ctx.needs_input_grad[:5])
-        x = encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s, bf16=True)
+        x, fd = encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s, bf16=True, save_fd=True)
         img_off, img_emo = mlp_pack(RADIANCE_DESC, flat_off), mlp_pack(RADIANCE_DESC, flat_emo)
         lin_off, hid_off = _mlp_forward(RADIANCE_DESC, img_off, x, 0, s.m3, s.m3, train, save_begin=off_grad_rows[0])
         lin_emo, hid_emo = _mlp_forward(RADIANCE_DESC, img_emo, x, 0, s.m3_on, s.m3, train)
         ctx.sc, ctx.streams, ctx.grid_params = sc, s, (sdf_grid, off_grid, emo_grid)
         ctx.rows = (off_grad_rows, emo_grad_rows)
         ctx.hidden = (hid_off, hid_emo)
-        ctx.save_for_backward(rays_o, rays_d, sdf_grid, off_grid, emo_grid, x, img_off, img_emo, lin_off, lin_emo)
+        ctx.save_for_backward(rays_o, rays_d, sdf_grid, off_grid, emo_grid, x, img_off, img_emo, lin_off, lin_emo, fd)
         return lin_off, lin_emo
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_off, d_emo):
-        rays_o, rays_d, sdf_grid, off_grid, emo_grid, x, img_off, img_emo, lin_off, lin_emo = ctx.saved_tensors
+        rays_o, rays_d, sdf_grid, off_grid, emo_grid, x, img_off, img_emo, lin_off, lin_emo, fd = ctx.saved_tensors
         s: Streams = ctx.streams
         hid_off, hid_emo = ctx.hidden
         (ob, oe), (eb, ee) = ctx.rows
@@ -384,7 +389,7 @@ class Shade(torch.autograd.Function):
                                       d_x, FEAT_GRAD_DIM, acc, scratch)
         ctx.hidden = None
         g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x,
-                                                ctx.grid_params)
+                                                ctx.grid_params, fd)
         return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None
 
 
@@ -677,9 +682,12 @@ class ShadePBR(torch.autograd.Function):
         if use[3]:
             _check_cl(brdf_grid, "brdf.grid")
             x2 = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16, device=dev)
+        fd = torch.empty(m, 16, dtype=torch.float32, device=dev) if train else None
         check(L.esr_encode_pbr_fwd(ctypes.byref(sc), ptr(p.rays_o), ptr(p.rays_d), ptr(p.viewdirs), ptr(sdf_grid),
                                    ptr(off_grid), ptr(emo_grid), ptr(brdf_grid) if use[3] else None, 6, ptr(p.pts),
-                                   ptr(p.h_ray), ptr(p.h_step), ptr(p.h_sdf), m, ptr(x), ptr(x2), 1, stream_ptr()))
+                                   ptr(p.h_ray), ptr(p.h_step), ptr(p.h_sdf), m, ptr(x), ptr(x2), 1, ptr(fd),
+                                   stream_ptr()))
+        ctx.fd = fd
         descs = (RADIANCE_DESC, RADIANCE_DESC, EMIT_DESC, BRDF_DESC)
         flats = (flat_off, flat_emo, flat_emit, flat_brdf)
         STATS["encode_rows"] += m
@@ -742,5 +750,6 @@ class ShadePBR(torch.autograd.Function):
             d_brdf_c = None
         check(_lib.lib().esr_encode_pbr_bwd(ctypes.byref(ctx.sc), ptr(p.rays_o), ptr(p.rays_d), ptr(sdf_grid), 6,
                                             ptr(p.pts), ptr(p.h_ray), ptr(p.h_step), m, ptr(d_x), ptr(d_brdf_c),
-                                            ptr(g_sdf), ptr(g_off), ptr(g_emo), ptr(g_brdf), stream_ptr()))
+                                            ptr(g_sdf), ptr(g_off), ptr(g_emo), ptr(g_brdf), ptr(ctx.fd), stream_ptr()))
+        ctx.fd = None
         return (r_sdf, r_off, r_emo, r_brdf, *g_flat, None, None, None)

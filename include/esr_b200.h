@@ -212,16 +212,19 @@ int esr_encode_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays
  * row j reads view direction j), and optionally a second copy of the row, `feat_brdf`, whose colour slot 0 holds the
  * taps of a third grid (`brdf_grid`, the BRDFNet input of esrnerf.py:761-763; both NULL = off).  sc->fd_eps selects the
  * finite-difference denominator.  Backward: d_brdf_color [m3,6] f32 is the cotangent of that slot.
+ * save_fd / saved_fd (nullable): f32 [m3,16] — the forward stores the four un-normalised finite-difference SDF
+ * gradients of each sample (4 x (z, y, x, pad)); a backward that receives them reads no grid values at all (it
+ * otherwise re-gathers the 72 line taps to recompute them).
  */
 int esr_encode_pbr_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
                        const float *sdf_grid, const float *off_color_grid, const float *emo_color_grid,
                        const float *brdf_grid, int color_dim, const float *pts, const int32_t *h_ray,
                        const int32_t *h_step, const float *h_sdf, int64_t m3, void *feat, void *feat_brdf,
-                       int out_is_bf16, esr_stream_t stream);
+                       int out_is_bf16, float *save_fd, esr_stream_t stream);
 int esr_encode_pbr_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *sdf_grid,
                        int color_dim, const float *pts, const int32_t *h_ray, const int32_t *h_step, int64_t m3,
                        const float *d_feat, const float *d_brdf_color, float *grad_sdf_grid, float *grad_off_grid,
-                       float *grad_emo_grid, float *grad_brdf_grid, esr_stream_t stream);
+                       float *grad_emo_grid, float *grad_brdf_grid, const float *saved_fd, esr_stream_t stream);
 
 /*
  * World positions of stream samples — the reference's ray_pts (kernel.cu:167-194) after its compactions: the origins
