@@ -38,8 +38,10 @@ ESR_HD int64_t tiled_chunk_index(int64_t row, int c, int chunks_per_row) {
 }
 ESR_HD int64_t act_chunk_index(int64_t row, int c) { return tiled_chunk_index(row, c, ACT_W / 8); }
 // `hidden` buffer = [n_hidden][rows_padded][192] bf16 activations, then the ReLU masks the data-gradient chain reads
-// instead of the activations: per layer [tile][4 column groups][128 rows] x uint2 (48 bits used: bit j =
-// [H[row][48 grp + j] > 0]).
+// instead of the activations: per layer [tile][4 column groups][128 rows] x uint2, 48 bits used.  Column
+// 48 grp + 16 c + 2 j + h (c < 3 sixteen-column chunks, j < 8 pairs, h = low / high half of the packed bf16 pair) is
+// bit 8 (c & 1) + j + 16 h of word c >> 1 — the layout that lets the forward epilogue derive both bits of a pair
+// from the packed word with three integer operations (mlp_tc.cu).
 ESR_HD int64_t act_hidden_bytes(int n_hidden, int64_t m_total) {
   return (int64_t)n_hidden * act_rows_padded(m_total) * (ACT_W * 2 + 32);
 }

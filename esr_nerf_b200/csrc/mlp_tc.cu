@@ -233,8 +233,25 @@ ESR_D float act_fwd(float z, int act) {
   return z;
 }
 
-// TMEM column map (512 columns allocated): accumulator D [0,192), bf16 A operand [192,288), small accumulator [288, 352)
-constexpr uint32_t TM_D = 0, TM_A = 192, TM_S = 288, TM_COLS = 512;
+// TMEM column map (512 columns allocated): two accumulator regions D0 [0,192) / D1 [192,384) used by alternate layers
+// (so the next layer's MMA can start while the epilogue still reads the current accumulator), bf16 A operand
+// [384,480).  The narrow last accumulator of a chain (output layer / d_x) lives in whichever D region is free.
+constexpr uint32_t TM_D0 = 0, TM_A = 384, TM_COLS = 512;
+ESR_D uint32_t tm_d(int i) { return TM_D0 + (uint32_t)(i & 1) * TC_W; }
+
+ESR_D void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Chunk pipeline.  An epilogue thread owns 48 accumulator columns = three 16-column chunks cc = 0..2; column group g
+// (= warp / 4) chunk cc is K-step s = 3 g + cc of the next layer's MMA.  As soon as every warp has written chunk cc of
+// the new A operand it arrives on bar_chunk[cc] and the issuer fires the four K-steps {cc, 3 + cc, 6 + cc, 9 + cc}:
+// two thirds of a layer's MMA time hides under the epilogue that produces its operand.
+ESR_D void chunk_ready(uint32_t bar_chunk, unsigned lane) {
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar_chunk);
+}
 
 // ------------------------------------------------------------------------------------------------
 // forward chain
@@ -247,8 +264,8 @@ struct FwdSm {
   static constexpr int bias = wo + TC_NOUT_PAD * TC_W * 2;
   static constexpr int weights_bytes = bias + (NH * TC_W + TC_NOUT_PAD) * 4;   // == TcLayout::f_bytes()
   static constexpr int x = (weights_bytes + 127) / 128 * 128;
-  static constexpr int bar = x + TC_TM * K0 * 2;
-  static constexpr int bytes = bar + 16;
+  static constexpr int bar = x + TC_TM * K0 * 2;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot
+  static constexpr int bytes = bar + 48;
 };
 
 // Epilogue thread geometry (16 warps): TMEM lane quadrant = warp % 4 (hardware rule for tcgen05.ld/st), column
@@ -272,12 +289,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
-  const uint32_t bar = sbase + S::bar;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 8);
+  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
 
   stage_bytes(smem, image, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -287,6 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
+  uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
 
   const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
   const EpiThread et(warp, lane);
@@ -319,14 +339,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
 #pragma unroll
       for (int s = 0; s < K0 / 16; ++s)
-        mma_ss(tmem + TM_D, make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
+        mma_ss(tmem + tm_d(0), make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
                make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
       mma_commit(bar);
-    }
+      // the rest of the chain: layer l + 1 (or the output layer) is fed chunk by chunk as the epilogue of layer l
+      // produces its A operand; its accumulator is the D region layer l does not use
 #pragma unroll 1
-    for (int l = 0; l < NH; ++l) {
-      if (is_epi) {
+      for (int l = 0; l < NH; ++l) {
+        const bool last = l + 1 == NH;
+        const uint32_t dst = tmem + tm_d(l + 1);
+        const uint32_t wl = last ? sbase + S::wo : sbase + S::wh + l * (TC_W * TC_W * 2);
+        const uint32_t rows16 = (last ? TC_NOUT_PAD : TC_W) * 16;
+        const uint32_t idesc = last ? make_idesc(TC_NOUT_PAD) : make_idesc(TC_W);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          mbar_wait(bar_chunk + 8 * cc, cphase);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int s = 3 * g + cc;
+            mma_ts(dst, tmem + TM_A + 8 * s, make_desc(wl + 2 * s * rows16, rows16, 128), idesc, (cc | g) != 0);
+          }
+        }
+        mma_commit(bar);
+        cphase ^= 1;
+      }
+    }
+    if (is_epi) {
+#pragma unroll 1
+      for (int l = 0; l < NH; ++l) {
         mbar_wait(bar, phase);
+        phase ^= 1;
         tc_fence_after();
         if (l == 0 && tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);  // x tile is free: prefetch the next one
         // bias + ReLU -> bf16 -> TMEM A operand (+ global copy, tiled layout, for the backward pass)
@@ -334,7 +377,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint4 *hl = hidden ? reinterpret_cast<uint4 *>(hidden + (int64_t)l * act_rows_padded(m_total) * TC_W) : nullptr;
         uint32_t r[3][16];
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + TM_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + tm_d(l) + TC_GCOLS * et.grp + 16 * cc, r[cc]);
         tmem_ld_wait();
         uint32_t mask[2] = {0u, 0u};
 #pragma unroll
@@ -346,50 +389,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
             const float z0 = __uint_as_float(r[cc][2 * j]) + bb.x, z1 = __uint_as_float(r[cc][2 * j + 1]) + bb.y;
             p[j] = pack2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
-            // mask of the STORED activation (compare the rounded word so forward and backward agree)
-            if (p[j] & 0x0000ffffu) mask[cc >> 1] |= 1u << (16 * (cc & 1) + 2 * j);
-            if (p[j] & 0xffff0000u) mask[cc >> 1] |= 1u << (16 * (cc & 1) + 2 * j + 1);
+            // mask of the STORED activation (test the rounded word so forward and backward agree), 3 integer ops per
+            // pair: a non-zero non-negative bf16 half plus 0x7fff carries into its top bit (halves are <= 0x7f80, so
+            // the low half never carries into the high one); the two top bits land on mask bits (s, 16 + s),
+            // s = 8 (cc & 1) + j  (mlp_layout.cuh)
+            const uint32_t t = p[j] + 0x7fff7fffu;
+            constexpr uint32_t one2 = 0x00010001u;
+            mask[cc >> 1] |= (t >> (15 - 8 * (cc & 1) - j)) & (one2 << (8 * (cc & 1) + j));
           }
           tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
-          if (save) {  // the warp's 32 rows write 512 contiguous bytes per chunk
+          if (save) {  // the warp's 32 rows write 512 contiguous bytes per chunk (issued under the TMEM store latency)
             hl[act_chunk_index(row, col0 / 8)] = make_uint4(p[0], p[1], p[2], p[3]);
             hl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(p[4], p[5], p[6], p[7]);
           }
+          chunk_ready(bar_chunk + 8 * cc, lane);
         }
         if (save) {
           uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
           mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
         }
-        tmem_st_wait();
       }
-      tc_fence_before();
-      __syncthreads();
-      if (is_issuer && lane == 0) {
-        tc_fence_after();
-        if (l + 1 < NH) {
-          const uint32_t wl = sbase + S::wh + l * (TC_W * TC_W * 2);
-#pragma unroll
-          for (int s = 0; s < TC_W / 16; ++s)
-            mma_ts(tmem + TM_D, tmem + TM_A + 8 * s, make_desc(wl + 2 * s * (TC_W * 16), TC_W * 16, 128),
-                   make_idesc(TC_W), s > 0);
-        } else {
-#pragma unroll
-          for (int s = 0; s < TC_W / 16; ++s)
-            mma_ts(tmem + TM_S, tmem + TM_A + 8 * s,
-                   make_desc(sbase + S::wo + 2 * s * (TC_NOUT_PAD * 16), TC_NOUT_PAD * 16, 128),
-                   make_idesc(TC_NOUT_PAD), s > 0);
-        }
-        mma_commit(bar);
-      }
-      phase ^= 1;
-    }
-    // ---- output layer epilogue (column group 0 threads) ----
-    if (is_epi) {
+      // ---- output layer epilogue (column group 0 threads) ----
       mbar_wait(bar, phase);
+      phase ^= 1;
       tc_fence_after();
       if (et.grp == 0) {
         uint32_t r[16];
-        tmem_ld16(tmem + et.lane_base + TM_S, r);
+        tmem_ld16(tmem + et.lane_base + tm_d(NH), r);
         tmem_ld_wait();
         if (valid) {
           const float *bo = sbias + NH * TC_W;
@@ -398,8 +424,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (c < n_out) y[row * n_out + c] = act_fwd(__uint_as_float(r[c]) + bo[c], act);
         }
       }
+      tc_fence_before();   // the next tile's first MMA overwrites D0 / the region read above
     }
-    phase ^= 1;
   }
   tc_fence_before();
   __syncthreads();
@@ -416,8 +442,8 @@ struct BwdSm {
   static constexpr int w0 = wh + (NH - 1) * TC_W * TC_W * 2;          // W0T [DXN x W]
   static constexpr int weights_bytes = w0 + DXN * TC_W * 2;           // == TcLayout::b_bytes()
   static constexpr int dz = (weights_bytes + 127) / 128 * 128;        // dZ_out tile [128 x 16] bf16
-  static constexpr int bar = dz + TC_TM * TC_NOUT_PAD * 2;
-  static constexpr int bytes = bar + 16;
+  static constexpr int bar = dz + TC_TM * TC_NOUT_PAD * 2;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot
+  static constexpr int bytes = bar + 48;
 };
 
 template <int K0, int NH, int DXN, int NO, bool ACC>
@@ -431,12 +457,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
-  const uint32_t bar = sbase + S::bar;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 8);
+  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
+  uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
 
   stage_bytes(smem, image_bwd, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -521,13 +550,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     if (is_issuer && lane == 0) {
       tc_fence_after();
-      mma_ss(tmem + TM_D, make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
+      mma_ss(tmem + tm_d(0), make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
              make_idesc(TC_W), 0);
       mma_commit(bar);
-    }
+      // chain step i handles layer l = NH - 1 - i: its accumulator is D region i & 1, the MMA it feeds (W_l^T, or
+      // W_0^T -> d_x for l == 0) accumulates in the other region, chunk by chunk (see chunk_ready)
 #pragma unroll 1
-    for (int l = NH - 1; l >= 0; --l) {
-      if (is_epi) {
+      for (int i = 0; i < NH; ++i) {
+        const int l = NH - 1 - i;
+        const uint32_t dst = tmem + tm_d(i + 1);
+        const uint32_t wl = l > 0 ? sbase + S::wh + (l - 1) * (TC_W * TC_W * 2) : sbase + S::w0;
+        const uint32_t rows16 = (l > 0 ? TC_W : DXN) * 16;
+        const uint32_t idesc = l > 0 ? make_idesc(TC_W) : make_idesc(DXN);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          mbar_wait(bar_chunk + 8 * cc, cphase);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int s = 3 * g + cc;
+            mma_ts(dst, tmem + TM_A + 8 * s, make_desc(wl + 2 * s * rows16, rows16, 128), idesc, (cc | g) != 0);
+          }
+        }
+        mma_commit(bar);
+        cphase ^= 1;
+      }
+    }
+    if (is_epi) {
+#pragma unroll 1
+      for (int i = 0; i < NH; ++i) {
+        const int l = NH - 1 - i;
         // ReLU mask bits of this thread's 48 columns of H_l (written by the forward chain, prefetched above)
         uint4 *zl = reinterpret_cast<uint4 *>(d_z + (int64_t)l * layer_stride);
         uint2 mk2 = cur_mask[0];
@@ -536,58 +588,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           if (q == l) mk2 = cur_mask[q];
         const uint32_t mask[2] = {mk2.x, mk2.y};
         mbar_wait(bar, phase);
+        phase ^= 1;
         tc_fence_after();
         // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy (tiled) for the weight-gradient GEMM
         uint32_t r[3][16];
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + TM_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + tm_d(i) + TC_GCOLS * et.grp + 16 * cc, r[cc]);
         tmem_ld_wait();
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           const int col0 = TC_GCOLS * et.grp + 16 * cc;
-          const uint32_t mk = mask[cc >> 1] >> (16 * (cc & 1));
+          const uint32_t mk = mask[cc >> 1] >> (8 * (cc & 1));   // pair j: bits (j, 16 + j)
           uint32_t p[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            p[j] = pack2((mk >> (2 * j)) & 1u ? __uint_as_float(r[cc][2 * j]) : 0.f,
-                         (mk >> (2 * j + 1)) & 1u ? __uint_as_float(r[cc][2 * j + 1]) : 0.f);
+          for (int j = 0; j < 8; ++j)   // 0xffff per live half: AND on the packed pair instead of two selects
+            p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & (((mk >> j) & 0x00010001u) * 0xffffu);
           tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (valid) {
             zl[act_chunk_index(row, col0 / 8)] = make_uint4(p[0], p[1], p[2], p[3]);
             zl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(p[4], p[5], p[6], p[7]);
           }
+          chunk_ready(bar_chunk + 8 * cc, lane);
         }
-        tmem_st_wait();
       }
-      tc_fence_before();
-      __syncthreads();
-      if (is_issuer && lane == 0) {
-        tc_fence_after();
-        if (l > 0) {
-          const uint32_t wl = sbase + S::wh + (l - 1) * (TC_W * TC_W * 2);
-#pragma unroll
-          for (int s = 0; s < TC_W / 16; ++s)
-            mma_ts(tmem + TM_D, tmem + TM_A + 8 * s, make_desc(wl + 2 * s * (TC_W * 16), TC_W * 16, 128),
-                   make_idesc(TC_W), s > 0);
-        } else {
-#pragma unroll
-          for (int s = 0; s < TC_W / 16; ++s)
-            mma_ts(tmem + TM_S, tmem + TM_A + 8 * s, make_desc(sbase + S::w0 + 2 * s * (DXN * 16), DXN * 16, 128),
-                   make_idesc(DXN), s > 0);
-        }
-        mma_commit(bar);
-      }
-      phase ^= 1;
-    }
-    // ---- d_x epilogue: one 16-column group per epilogue column group ----
-    if (is_epi) {
+      // ---- d_x epilogue: one 16-column group per epilogue column group ----
       mbar_wait(bar, phase);
+      phase ^= 1;
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < DXN / 16; ++cc) {
         if (cc != et.grp) continue;  // warp-uniform
         uint32_t r[16];
-        tmem_ld16(tmem + et.lane_base + TM_S + cc * 16, r);
+        tmem_ld16(tmem + et.lane_base + tm_d(NH) + cc * 16, r);
         tmem_ld_wait();
         if (valid && d_x) {
 #pragma unroll
@@ -606,8 +638,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
+      tc_fence_before();
     }
-    phase ^= 1;
   }
   tc_fence_before();
   __syncthreads();
