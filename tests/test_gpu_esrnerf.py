@@ -206,3 +206,49 @@ def test_esrnerf_finetune_vs_golden(case):
         assert l2 < 0.1, (name, l2)                      # bf16 tensor-core nets: inherent bound (module docstring)
     m.train()
     assert "emit_color.grid" not in m.state_dict()
+
+
+def test_esrnerf_full_size_properties():
+    """BASELINE config 3 per-GPU shape scaled to the reference batch (lts.yaml:58-59: 8192 rays, 100 LTS points x 256
+    secondary rays, 256^3 grids, sparse 100^3 mask, s_val 220): the oracle cannot run this in seconds, so check
+    size-independent properties — stream sortedness, transmittance identity, output shapes / finiteness, the PDRA
+    split, that every parameter receives a finite gradient and that two backward passes of the same step agree (the
+    gradient sink hands each dense grid gradient over exactly once)."""
+    from oracle import esrnerf_port as E
+
+    n = 8192
+    _, weights = C.load_esrnerf_case("lts_sparse_s220")
+    fx = dict(mask_res=100, sparse=1, s_val=220.0, num_voxels=256 ** 3, num_2ndrays=256, num_ltspts=100, pdra_mode=1)
+    m = C.build_product_esrnerf(fx, weights, DEV)
+    m.keep_streams = True
+    rays = {k: v.to(DEV) for k, v in S.make_rays(n, 1234).items() if k != "rgbs"}
+    um = S.uncert_masks(n).to(DEV)
+    grads = []
+    for rep in range(2):
+        m.zero_grad(set_to_none=True)
+        m.draws = E.FixedDraws(5)
+        out = m(s_val=220.0, uncert_masks=um, normal_eps=0.01, emit_eps=0.01, **rays)
+        cot = C.esrnerf_cotangents(out)
+        sum((out[k] * cot[k].to(DEV)).sum() for k in cot).backward()
+        grads.append({k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None})
+    st = m.last_streams["streams"]
+    m3 = st.m3
+    assert m3 > 10 * n / 2                                                   # the sphere is hit by most rays
+    same = st.h_ray[1:] == st.h_ray[:-1]
+    assert (st.h_ray[1:] >= st.h_ray[:-1]).all() and (st.h_step[1:][same] > st.h_step[:-1][same]).all()
+    wsum = torch.zeros(n, device=DEV).index_add_(0, st.h_ray.long(), m.last_streams["h_w"])
+    assert (wsum + out["etc/alphainv_cum"] <= 1 + 1e-4).all()
+    for k, v in out.items():
+        assert torch.isfinite(v).all(), k
+    assert out["etc/normal"].shape == (m3, 3) and out["etc/brdf"].shape == (m3, 5) and out["etc/emit_eps"].shape == (m3, 3)
+    assert out["lin/pbr/off_hat"].shape == (200, 3) and out["lin/pbr/emo"].shape == (200, 3)
+    assert out["etc/emit_uncert"].shape[0] == n // 2 and out["etc/emit_cert"].shape[0] == n - n // 2
+    assert (out["etc/brdf"] >= 0).all() and (out["etc/brdf"] <= 1).all() and (out["etc/emit"] >= 0).all()
+    st2 = m.last_streams["lts"]["streams"]
+    assert st2.n_rays == 100 * 256
+    names = {k for k, p in m.named_parameters() if p.requires_grad}
+    assert set(grads[0]) == names, names ^ set(grads[0])
+    for k in names:
+        assert torch.isfinite(grads[0][k]).all(), k
+        _, l2 = C.grad_err(grads[1][k], grads[0][k])
+        assert l2 < 1e-3, (k, l2)                                            # atomics reorder sums; nothing is dropped or doubled
