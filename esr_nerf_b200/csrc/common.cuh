@@ -85,6 +85,11 @@ ESR_D void red_add2(float *addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// 16-byte vector RED (sm_90+); addr must be 16-byte aligned
+ESR_D void red_add4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Geometry shared by all render kernels
 // ---------------------------------------------------------------------------------------------
@@ -226,10 +231,20 @@ ESR_D float tap1_manual_world(const float *__restrict__ g, int X, int Y, int Z, 
 
 // scatter-add v * w[k] into a scalar-channel gradient volume
 ESR_D void scatter1(float *__restrict__ g, int X, int Y, int Z, const Cell &c, float v) {
+  // the two corners of a (x, y) pair are adjacent along Z: one 8-byte RED when both are in the grid and the pair is
+  // 8-byte aligned (Z even, z0 even), two scalar REDs otherwise — the L2 pays per RED request, not per byte
+  const bool pair_ok = ((Z | c.z0) & 1) == 0 && (unsigned)c.z0 < (unsigned)(Z - 1);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int x = c.x0 + (k >> 2), y = c.y0 + ((k >> 1) & 1), z = c.z0 + (k & 1);
-    if (in_grid(x, y, z, X, Y, Z)) red_add(g + ((int64_t)x * Y + y) * Z + z, v * c.w[k]);
+  for (int k = 0; k < 8; k += 2) {
+    const int x = c.x0 + (k >> 2), y = c.y0 + ((k >> 1) & 1);
+    if ((unsigned)x >= (unsigned)X || (unsigned)y >= (unsigned)Y) continue;
+    float *p = g + ((int64_t)x * Y + y) * Z + c.z0;
+    if (pair_ok) {
+      red_add2(p, v * c.w[k], v * c.w[k + 1]);
+    } else {
+      if ((unsigned)c.z0 < (unsigned)Z) red_add(p, v * c.w[k]);
+      if ((unsigned)(c.z0 + 1) < (unsigned)Z) red_add(p + 1, v * c.w[k + 1]);
+    }
   }
 }
 

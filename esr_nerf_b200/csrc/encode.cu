@@ -146,9 +146,25 @@ ESR_D void scatterC(float *__restrict__ g, int X, int Y, int Z, const Cell &c, c
   for (int k = 0; k < 8; ++k) {
     const int x = c.x0 + (k >> 2), y = c.y0 + ((k >> 1) & 1), z = c.z0 + (k & 1);
     if (in_grid(x, y, z, X, Y, Z)) {
-      float *p = g + (((int64_t)x * Y + y) * Z + z) * C;
+      const int64_t vox = ((int64_t)x * Y + y) * Z + z;
+      float *p = g + vox * C;
+      if constexpr (C == 6) {
+        // 24 bytes per voxel: 16-byte aligned for even voxels, 8 (mod 16) for odd ones -> one v4 + one v2 RED
+        // either way (two L2 requests per corner instead of three)
+        float e[6];
 #pragma unroll
-      for (int ch = 0; ch < C / 2; ++ch) red_add2(p + 2 * ch, d[2 * ch] * c.w[k], d[2 * ch + 1] * c.w[k]);
+        for (int ch = 0; ch < 6; ++ch) e[ch] = d[ch] * c.w[k];
+        if ((vox & 1) == 0) {
+          red_add4(p, e[0], e[1], e[2], e[3]);
+          red_add2(p + 4, e[4], e[5]);
+        } else {
+          red_add2(p, e[0], e[1]);
+          red_add4(p + 2, e[2], e[3], e[4], e[5]);
+        }
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < C / 2; ++ch) red_add2(p + 2 * ch, d[2 * ch] * c.w[k], d[2 * ch + 1] * c.w[k]);
+      }
     }
   }
 }
@@ -416,13 +432,39 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
       s_dl[(tl.slot + 1) * ENC_THREADS + threadIdx.x] += d_lo * tl.wh;
     }
   }
-  // line cotangents -> the 4 corners of each line plane
+  // line cotangents -> the 4 corners of each line plane.  For the y- and x-displaced lines (a = 1, 2) the two corners
+  // that differ in z are adjacent in memory: one 8-byte RED per pair when it is aligned and inside the grid.
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int jl = 0; jl < 6; ++jl) {
       const float dl = s_dl[(a * 6 + jl) * ENC_THREADS + threadIdx.x];
-      if (dl != 0.f) for_line_corners(fr, a, fr.fb[a] - 2 + jl, [&](int64_t off, float w) { red_add(g_sdf + off, dl * w); });
+      if (dl == 0.f) continue;
+      const int p = fr.fb[a] - 2 + jl;
+      if (a == 0) {
+        for_line_corners(fr, a, p, [&](int64_t off, float w) { red_add(g_sdf + off, dl * w); });
+      } else {
+        if ((unsigned)p >= (unsigned)fr.size[a]) continue;
+        const int c = a == 2 ? 1 : 2;                      // the other non-z axis
+        const int z0 = fr.o0[0];
+        const bool pair_ok = ((fr.size[0] | z0) & 1) == 0 && (unsigned)z0 < (unsigned)(fr.size[0] - 1);
+#pragma unroll
+        for (int dc = 0; dc < 2; ++dc) {
+          const int qc = fr.o0[c] + dc;
+          if ((unsigned)qc >= (unsigned)fr.size[c]) continue;
+          const float wc = dc ? fr.wh[c] : fr.wl[c];
+          int zyx[3];
+          zyx[a] = p, zyx[c] = qc, zyx[0] = z0;
+          float *q = g_sdf + vox(fr, zyx[0], zyx[1], zyx[2]);
+          const float v0 = dl * __fmul_rn(fr.wl[0], wc), v1 = dl * __fmul_rn(fr.wh[0], wc);
+          if (pair_ok) {
+            red_add2(q, v0, v1);
+          } else {
+            if ((unsigned)z0 < (unsigned)fr.size[0]) red_add(q, v0);
+            if ((unsigned)(z0 + 1) < (unsigned)fr.size[0]) red_add(q + 1, v1);
+          }
+        }
+      }
     }
 }
 

@@ -666,9 +666,6 @@ ESR_D void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-ESR_D void red_add4(float *addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 // instruction descriptor: D f32, A/B bf16, both MN-major, M = 128
 __host__ __device__ constexpr uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
 
