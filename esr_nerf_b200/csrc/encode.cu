@@ -432,6 +432,40 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
       s_dl[(tl.slot + 1) * ENC_THREADS + threadIdx.x] += d_lo * tl.wh;
     }
   }
+  {  // z-displaced lines: the six planes fb-2 .. fb+3 of one (y, x) corner are six consecutive floats -> 8-byte REDs
+    // on the even-aligned pairs (3 or 4 requests per corner instead of 6)
+    float dlz[6];
+#pragma unroll
+    for (int jl = 0; jl < 6; ++jl) dlz[jl] = s_dl[jl * ENC_THREADS + threadIdx.x];
+    const int zb = fr.fb[0] - 2, Zs = fr.size[0];
+    const bool even_z = (Zs & 1) == 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int qy = fr.o0[1] + dy, qx = fr.o0[2] + dx;
+        if ((unsigned)qy >= (unsigned)fr.size[1] || (unsigned)qx >= (unsigned)fr.size[2]) continue;
+        const float w = __fmul_rn(dy ? fr.wh[1] : fr.wl[1], dx ? fr.wh[2] : fr.wl[2]);
+        float *q = g_sdf + vox(fr, 0, qy, qx);
+        auto one = [&](int jl) {
+          const int z = zb + jl;
+          if ((unsigned)z < (unsigned)Zs && dlz[jl] != 0.f) red_add(q + z, dlz[jl] * w);
+        };
+        auto two = [&](int jl) {   // zb + jl is even
+          const int z = zb + jl;
+          if (even_z && z >= 0 && z + 1 < Zs) {
+            if (dlz[jl] != 0.f || dlz[jl + 1] != 0.f) red_add2(q + z, dlz[jl] * w, dlz[jl + 1] * w);
+          } else {
+            one(jl), one(jl + 1);
+          }
+        };
+        if (zb & 1) {
+          one(0), two(1), two(3), one(5);
+        } else {
+          two(0), two(2), two(4);
+        }
+      }
+  }
   // line cotangents -> the 4 corners of each line plane.  For the y- and x-displaced lines (a = 1, 2) the two corners
   // that differ in z are adjacent in memory: one 8-byte RED per pair when it is aligned and inside the grid.
 #pragma unroll
@@ -442,7 +476,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
       if (dl == 0.f) continue;
       const int p = fr.fb[a] - 2 + jl;
       if (a == 0) {
-        for_line_corners(fr, a, p, [&](int64_t off, float w) { red_add(g_sdf + off, dl * w); });
+        continue;   // z-displaced lines: handled below, six z-adjacent planes per (y, x) corner at a time
       } else {
         if ((unsigned)p >= (unsigned)fr.size[a]) continue;
         const int c = a == 2 ? 1 : 2;                      // the other non-z axis
