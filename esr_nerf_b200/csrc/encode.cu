@@ -208,7 +208,8 @@ struct TiledRowWriter {
     uint4 *b4 = reinterpret_cast<uint4 *>(base);
 #pragma unroll
     for (int c = 0; c < WIDTH / 8; ++c)
-      b4[tiled_chunk_index(row, c, WIDTH / 8)] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      // streaming store: the rows are read once by the MLP kernels; keep the L2 for the grid taps
+      __stcs(b4 + tiled_chunk_index(row, c, WIDTH / 8), make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
   }
 };
 template <>
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
 #pragma unroll
       for (int a = 0; a < 3; ++a) v[25 + a * 4 + k] = __fdiv_rn(gr[a], nrm);
       // the un-normalised finite-difference gradients, f32, for the backward pass (it then needs no grid reads at all)
-      if (save_fd) *reinterpret_cast<float4 *>(save_fd + j * 16 + 4 * k) = make_float4(gr[0], gr[1], gr[2], 0.f);
+      if (save_fd) __stcs(reinterpret_cast<float4 *>(save_fd + j * 16 + 4 * k), make_float4(gr[0], gr[1], gr[2], 0.f));
     }
     v[37] = __fdiv_rn(__fsub_rn(px, sc.xyz_min[0]), __fsub_rn(sc.xyz_max[0], sc.xyz_min[0]));
     v[38] = __fdiv_rn(__fsub_rn(py, sc.xyz_min[1]), __fsub_rn(sc.xyz_max[1], sc.xyz_min[1]));

@@ -87,6 +87,43 @@ class DVGO(nn.Module):
         sc.interval, sc.act_shift = float(self.stepsize), float(self.act_shift)
         return sc
 
+    # ---- one-off initialisation helpers of the alphamask driver (alphamask.py:128-143); dense torch code, not hot ----
+    def grid_sampler(self, xyz: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+        """dvgo.py:265-277"""
+        shape = xyz.shape[:-1]
+        pts = xyz.reshape(1, 1, 1, -1, 3)
+        ind_norm = ((pts - self.xyz_min) / (self.xyz_max - self.xyz_min)).flip((-1,)) * 2 - 1
+        out = torch.nn.functional.grid_sample(grid, ind_norm, mode="bilinear", align_corners=True)
+        return out.reshape(grid.shape[1], -1).T.reshape(*shape, grid.shape[1]).squeeze(-1)
+
+    def voxel_count_views(self, rays_o: torch.Tensor, rays_d: torch.Tensor, chunk_size: int) -> torch.Tensor:
+        """dvgo.py:59-93: per voxel, the number of training views whose rays deposit more than one unit of trilinear
+        weight on it (the gradient of sum(grid_sample(ones)) w.r.t. the ones volume) -> [1,1,X,Y,Z]"""
+        rng = torch.arange(self.N_samples, device=rays_o.device)[None].float()
+        count = torch.zeros_like(self.density.detach())
+        for view in range(len(rays_o)):
+            ones = torch.ones_like(self.density).requires_grad_()
+            for ro, rd in zip(rays_o[view].split(chunk_size, dim=0), rays_d[view].split(chunk_size, dim=0)):
+                vec = torch.where(rd == 0, torch.full_like(rd, 1e-6), rd)
+                t_min = torch.minimum((self.xyz_max - ro) / vec, (self.xyz_min - ro) / vec).amax(-1)
+                t_min = t_min.clamp(min=self.near, max=self.far)
+                step = self.stepsize * self.voxel_size * rng
+                interpx = t_min[..., None] + step / rd.norm(dim=-1, keepdim=True)
+                pts = ro[..., None, :] + rd[..., None, :] * interpx[..., None]
+                self.grid_sampler(pts, ones).sum().backward()
+            with torch.no_grad():
+                count += ones.grad > 1
+        return count
+
+    @torch.no_grad()
+    def maskout_near_cam_vox(self, cam_o: torch.Tensor) -> None:
+        """dvgo.py:103-135: density = -100 for voxels closer than `near` to any camera centre"""
+        ax = [torch.linspace(float(self.xyz_min[i]), float(self.xyz_max[i]), self.density.shape[2 + i],
+                             device=self.density.device) for i in range(3)]
+        xyz = torch.stack(torch.meshgrid(*ax, indexing="ij"), -1)
+        nearest = torch.stack([(xyz.unsqueeze(-2) - co).pow(2).sum(-1).sqrt().amin(-1) for co in cam_o.split(100)]).amin(0)
+        self.density[nearest[None, None] <= self.near] = -100
+
     def activate_density(self, density, interval=1):
         return 1 - torch.exp(-torch.nn.functional.softplus(density + self.act_shift) * interval)
 

@@ -279,6 +279,15 @@ class ESRNeRF(VoxurfF):
             reflect = (emo_m.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
         return {"lin/pbr/emo": emo, "lin/pbr/emo_hat": emit.repeat(2, 1) + reflect}
 
+    @torch.no_grad()
+    def render_envmap(self, H: int, W: int) -> torch.Tensor:
+        """esrnerf.py:1668-1690: the SG environment map on an equirectangular H x W lattice -> [H,W,3]"""
+        dev = self.envmap.mus.device
+        phi, theta = torch.meshgrid(torch.linspace(0.0, np.pi, H, device=dev),
+                                    torch.linspace(1.0 * np.pi, -1.0 * np.pi, W, device=dev), indexing="ij")
+        dirs = torch.stack([torch.cos(theta) * torch.sin(phi), torch.sin(theta) * torch.sin(phi), torch.cos(phi)], -1)
+        return self.envmap(dirs.view(-1, 3)).view(H, W, 3)
+
     # ------------------------------------------------------------------------------------------
     # inference entry points
     # ------------------------------------------------------------------------------------------

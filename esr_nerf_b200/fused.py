@@ -150,6 +150,17 @@ class Streams:
     h_sdf: Optional[torch.Tensor] = None
 
 
+def march_count(sc: Scene, rays_o, rays_d, mask_density):
+    """per-ray (candidate steps, in-AABB candidates, MaskCache survivors), int32 [N] each — no stream is written"""
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    n_steps, cnt_in, cnt_mask = _i32(n, dev), _i32(n, dev), _i32(n, dev)
+    if n:
+        check(_lib.lib().esr_march_count(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), None, n, ptr(mask_density),
+                                         ptr(n_steps), ptr(cnt_in), ptr(cnt_mask), stream_ptr()))
+    return n_steps, cnt_in, cnt_mask
+
+
 def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid) -> Streams:
     """Stages A/B.  One host read (M1) sizes the stream buffers — the reference syncs at the same
     point (render_utils_kernel.cu:212) and four more times before shading."""

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import fused
-from .modules import DenseGrid, GradientConv, MaskCache, _mlp_stack, cfg_get, voxel_geometry
+from .modules import DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, _mlp_stack, cfg_get, voxel_geometry
 from .render_utils import Alphas2Weights
 
 
@@ -44,7 +44,7 @@ class Gaussian3DConv(nn.Module):
         return self.m(x)
 
 
-class VoxurfC(nn.Module):
+class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
     def __init__(self, cfg, near: float, far: float, xyz_min, xyz_max, mask_xyz_min, mask_xyz_max,
                  mask_alpha_init: float, mask_density: torch.Tensor, s_val: float):
         super().__init__()

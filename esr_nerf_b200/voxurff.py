@@ -19,11 +19,11 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import fused
-from .modules import (DenseGrid, GradientConv, MaskCache, RadianceNet, TonemapNet, cfg_get, flat_mlp_params,
+from .modules import (DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, RadianceNet, TonemapNet, cfg_get, flat_mlp_params,
                       radiance_in_cols, tonemap_in_cols, voxel_geometry)
 
 
-class VoxurfF(nn.Module):
+class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
     def __init__(self, cfg, near: float, far: float, xyz_min: torch.Tensor, xyz_max: torch.Tensor,
                  mask_xyz_min: torch.Tensor, mask_xyz_max: torch.Tensor, mask_alpha_init: float,
                  mask_density: torch.Tensor, s_val: float, num_voxles: int):

@@ -295,3 +295,24 @@ def test_grid_gradient_compaction_is_exact():
         dist.destroy_process_group()
     for p, b in zip(comp.grids, before):
         assert torch.equal(p.grad, b)
+
+
+def test_filter_training_rays_packed_branch_vs_oracle():
+    """fine.py:199-212 with a solved coarse stage (sdf_random_init = False): the ray filter is the march kernel's per-ray
+    MaskCache survivor count; against the C restatement of the sampler + the port's MaskCache, bit-exact"""
+    from oracle import ref_harness as H
+    from oracle import voxurf_port as P
+
+    fx, weights = C.load_case("fine_sparse_s20")
+    m = C.build_product_model(fx, weights, DEV)
+    m.sdf_random_init = False
+    rays = S.make_rays(3000, 77)
+    rays["rays_d"][:500] *= -1
+    got = m.filter_training_rays_in_maskcache_sampling(rays["rays_o"].to(DEV), rays["rays_d"].to(DEV), 1024)
+    scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    pts, out, rid = H.sample_pts_on_rays(rays["rays_o"], rays["rays_d"], scene["xyz_min"], scene["xyz_max"], scene["near"],
+                                         1e9, scene["stepdist"])[:3]
+    want = torch.zeros(3000, dtype=torch.bool)
+    inb = ~out
+    want[rid[inb][P.mask_cache(scene, pts[inb])]] = True
+    assert torch.equal(got.cpu(), want) and 0 < int(want.sum()) < 3000

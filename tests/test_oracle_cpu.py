@@ -384,3 +384,82 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 assert "oracle/" not in src, f
+
+
+def test_grid_regularizers_match_reference():
+    """density_total_variation / color_total_variation (fine.py:384-393, coarse.py:353-363) are dense torch ops over the
+    parameter volumes and run on the CPU too: values and SDF / colour-grid gradients against the reference's own
+    methods on identical grids."""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.voxurfc import VoxurfC
+    from esr_nerf_b200.voxurff import VoxurfF
+    from oracle.make_golden import build_reference_coarse, build_reference_model
+
+    ref = build_reference_model(24 ** 3, 12, True, 20.0)
+    mine = VoxurfF(S.fine_cfg("cpu"), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+                   S.mask_density(12, True), 20.0, 24 ** 3)
+    S.fill_fine_model(mine)
+    ref.gradient = ref.neus_sdf_gradient()
+    assert torch.equal(ref.nonempty_mask, mine.nonempty_mask)
+    a = ref.density_total_variation(sdf_tv=0.1, smooth_grad_tv=0.05)
+    b = mine.density_total_variation(sdf_tv=0.1, smooth_grad_tv=0.05)
+    assert C.rel_err(b, a) < 1e-6
+    a.backward()
+    b.backward()
+    assert C.rel_err(mine.sdf.grid.grad, ref.sdf.grid.grad) < 1e-5
+    assert mine.density_total_variation() == 0
+
+    refc = build_reference_coarse(24 ** 3, 12, True, 5.0)
+    minec = VoxurfC(S.coarse_cfg("cpu", num_voxels=24 ** 3), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX,
+                    S.MASK_ALPHA_INIT, S.mask_density(12, True), 5.0)
+    S.fill_coarse_model(minec)
+    refc.gradient = refc.neus_sdf_gradient()
+    a = refc.density_total_variation(sdf_tv=0.1, smooth_grad_tv=0.05) + refc.color_total_variation()
+    b = minec.density_total_variation(sdf_tv=0.1, smooth_grad_tv=0.05) + minec.color_total_variation()
+    assert C.rel_err(b, a) < 1e-6
+    a.backward()
+    b.backward()
+    for name in ("sdf", "off_color", "emo_color"):
+        g_ref, g = getattr(refc, name).grid.grad, getattr(minec, name).grid.grad
+        assert C.rel_err(g.contiguous(), g_ref) < 1e-5, name
+
+
+def test_init_path_helpers_match_reference():
+    """the one-off driver-facing helpers (alphamask.py:128-143, coarse.py:207-212, fine.py:199-212) are dense torch code
+    and run on the CPU: DVGO.voxel_count_views / maskout_near_cam_vox, filter_training_rays_in_maskcache_sampling
+    (dense branch), ESRNeRF.render_envmap against the reference's own methods"""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.voxurfc import VoxurfC
+    from oracle.make_golden import build_reference_coarse, build_reference_dvgo, build_reference_esrnerf
+
+    rays = S.make_rays(3 * 40, 17)
+    ro, rd = rays["rays_o"].view(3, 40, 3), rays["rays_d"].view(3, 40, 3)
+    ref = build_reference_dvgo(20 ** 3)
+    mine = C.build_product_dvgo(20 ** 3, "cpu")
+    assert torch.equal(mine.voxel_count_views(ro, rd, 16), ref.voxel_count_views(ro, rd, 16))
+    cams = torch.tensor([[0.0, 0.0, 2.5], [2.4, 0.3, 0.1]])
+    ref.maskout_near_cam_vox(cams)
+    mine.maskout_near_cam_vox(cams)
+    assert torch.equal(mine.density, ref.density) and int((ref.density == -100).sum()) > 0
+
+    refc = build_reference_coarse(24 ** 3, 12, True, 5.0)
+    minec = VoxurfC(S.coarse_cfg("cpu", num_voxels=24 ** 3), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX,
+                    S.MASK_ALPHA_INIT, S.mask_density(12, True), 5.0)
+    rays = S.make_rays(200, 18)
+    rays["rays_d"][:40] *= -1                                    # some rays miss
+    a = refc.filter_training_rays_in_maskcache_sampling(rays["rays_o"], rays["rays_d"], 64)
+    b = minec.filter_training_rays_in_maskcache_sampling(rays["rays_o"], rays["rays_d"], 64)
+    assert torch.equal(a, b) and 0 < int(a.sum()) < 200
+
+    fx, weights = C.load_esrnerf_case("lts_sparse_s220")
+    refe = build_reference_esrnerf(24 ** 3, 12, True, 220.0, weights)
+    minee = C.build_product_esrnerf(dict(fx, num_voxels=24 ** 3, mask_res=12), weights, "cpu")
+    assert C.rel_err(minee.render_envmap(8, 16), refe.render_envmap(8, 16)) < 1e-6
