@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--with-optimizer", action="store_true",
+                    help="also run the fused Adam step (esr_nerf_b200.optimizer, SURVEY.md §8f row 3) inside the timed "
+                         "step; NOT part of the metric BASELINE.json names (render step only), off by default")
     ap.add_argument("--dense-allreduce", action="store_true",
                     help="N>1: all-reduce the dense grid gradients instead of the occupancy-compacted voxel set")
     a = ap.parse_args()
@@ -336,6 +339,13 @@ def run_b200(a, rank, world, local_rank):
     params = [p for p in model.parameters() if p.requires_grad]
     compactor = GridGradCompactor(model) if (world > 1 and not a.dense_allreduce and a.stage == "fine") else None
     reduced = [0]
+    optimizer = None
+    if a.with_optimizer and a.stage != "eval":
+        from esr_nerf_b200.optimizer import create_optimizer_or_freeze_model
+
+        lrs = dict(off_color=0.1, off_rgbnet=0.003, emo_color=0.1, emo_rgbnet=0.003, sdf=0.0005, tonemapper=0.003,
+                   brdf=0.1, brdfnet=0.001, emitnet=0.001, envmap=0.001)             # cfg/app/{fine,lts}.yaml lrs
+        optimizer = create_optimizer_or_freeze_model(model, **lrs)
 
     host = {k: v.pin_memory() for k, v in host.items()}
     batch = {k: v.to(dev) for k, v in host.items()}
@@ -349,6 +359,8 @@ def run_b200(a, rank, world, local_rank):
         loss.backward()
         if dist is not None:  # rays sharded, gradients summed once per step (north_star)
             reduced[0] = compactor.allreduce() if compactor is not None else allreduce_gradients(params)
+        if optimizer is not None:
+            optimizer.step()
         return out, loss
 
     def eval_step(b):
@@ -482,7 +494,7 @@ def run_b200(a, rank, world, local_rank):
         "config": {"workload": workload_name(a),
                    "parallelism": f"dp{world} (rays sharded, one gradient allreduce per step"
                                   + (f", {reduced[0] / 1e6:.0f} MB/rank" if world > 1 else "") + ")",
-                   "stage": a.stage,
+                   "stage": a.stage, "optimizer_in_step": bool(optimizer is not None),
                    "l2": "working set (0.83 GB of grids + grads) exceeds the 126 MB L2; no flush between steps",
                    "counts_per_gpu_step": counts,
                    "samples_per_s": {"candidate_M0": counts["M0"] * world * a.steps / (ms * 1e-3),

@@ -17,7 +17,7 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
-SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu"]
+SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu", "optim.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -153,6 +153,7 @@ PROTOTYPES = {
     "esr_dvgo_fwd": (I32, [DVGO_P, P, P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P]),
     "esr_dvgo_eval": (I32, [DVGO_P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P, P, P]),
     "esr_dvgo_bwd": (I32, [DVGO_P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "esr_adam_step": (I32, [P, P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P]),
     "esr_mlp_param_count": (I64, [DESC_P]),
     "esr_mlp_image_bytes": (I64, [DESC_P]),
     "esr_mlp_act_rows": (I64, [I64]),

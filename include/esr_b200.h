@@ -354,6 +354,16 @@ int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const
                 int accumulate, float *grad_flat, esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Optimizer step: app/utils/optimizer.py:63-228 — dense Adam with an optional per-voxel learning
+ * rate volume (set_pervoxel_lr, optimizer.py:107-109), amsgrad off (never enabled by the reference).  One fused pass;
+ * `step` is the 1-based step count of this parameter (bias corrections are evaluated on the host in double like the
+ * reference's Python floats).  All tensors f32 contiguous with n elements and 16-byte aligned; per_lr nullable.
+ * ---------------------------------------------------------------------------------------- */
+int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, const float *per_lr, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                  esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * 3. Alphamask stage (DVGO, app/coarse/model/dvgo.py:140-288): dense [N x S] sampling, density / colour grids only
  * ---------------------------------------------------------------------------------------- */
 typedef struct esr_dvgo_scene {
