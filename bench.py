@@ -463,9 +463,13 @@ def run_b200(a, rank, world, local_rank):
     top = next((r for r in stage_rows if "bound" in r), None)
     roofline = None
     if top is not None:
+        traffic = None   # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this workload
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if a.stage == "fine" and a.rays == (1 << 16) and a.grid == 256 and not a.dense and os.path.isfile(tpath):
+            traffic = json.load(open(tpath))["dram_bytes_per_launch"].get(top["kernel"])
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
                     "peak": pk["hbm_gbs"] if top["bound"] == "hbm" else pk["bf16_tflops_sustained"],
-                    "unit": top["unit"], "frac": top["frac"], "traffic": None, "peak_source": pk_src,
+                    "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "peak_source": pk_src,
                     "avg_launch_ms": top["ms_per_step"] / max(top["launches_per_step"], 1e-9),
                     "share_of_kernel_time": top["ms_per_step"] / max(sum(r["ms_per_step"] for r in stage_rows), 1e-9)}
 
