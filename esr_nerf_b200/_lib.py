@@ -153,6 +153,8 @@ PROTOTYPES = {
     "esr_dvgo_fwd": (I32, [DVGO_P, P, P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P]),
     "esr_dvgo_eval": (I32, [DVGO_P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P, P, P]),
     "esr_dvgo_bwd": (I32, [DVGO_P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "esr_tonemap_mlp_fwd": (I32, [DESC_P, P, P, I64, P, P]),
+    "esr_tonemap_mlp_bwd": (I32, [DESC_P, P, P, P, P, P, I64, P, P, P]),
     "esr_adam_step": (I32, [P, P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P]),
     "esr_mlp_param_count": (I64, [DESC_P]),
     "esr_mlp_image_bytes": (I64, [DESC_P]),

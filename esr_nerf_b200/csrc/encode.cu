@@ -650,22 +650,29 @@ __global__ void __launch_bounds__(256)
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m3) return;
   const bool on = lin_emo && em_modes[h_ray[j]] == 1;
+  // internal column order (include/esr_b200.h): channel c occupies columns [16 c, 16 c + 16):
+  //   16 c + 0: lin_c, 16 c + 1 + f: sin(lin_c 2^f), 16 c + 6 + f: cos(lin_c 2^f), f < 5, 16 c + 11..15: zero
   float v[48];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float x = lin_off[3 * j + c];
     if (on) x += lin_emo[3 * j + c];
     lin[3 * j + c] = x;
-    v[c] = x;
+    v[16 * c] = x;
+  }
+  if (!tfeat) return;   // the fused tone-map kernels compute the encoding themselves: only `lin` is wanted
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float x = v[16 * c];
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
       const float y = __fmul_rn(x, (float)(1 << f));
-      v[3 + c * 5 + f] = sinf(y);
-      v[18 + c * 5 + f] = cosf(y);
+      v[16 * c + 1 + f] = sinf(y);
+      v[16 * c + 6 + f] = cosf(y);
     }
-  }
 #pragma unroll
-  for (int c = 33; c < 48; ++c) v[c] = 0.f;
+    for (int q = 11; q < 16; ++q) v[16 * c + q] = 0.f;
+  }
   if constexpr (sizeof(OutT) == 2) {
     TiledRowWriter<ESR_TFEAT_DIM> wr;
     wr.put(0, v);
@@ -685,12 +692,12 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float x = lin[3 * j + c];
-    float gacc = d[c] + (d_lin_direct ? d_lin_direct[3 * j + c] : 0.f);
+    float gacc = d[16 * c] + (d_lin_direct ? d_lin_direct[3 * j + c] : 0.f);
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
       const float sf = (float)(1 << f);
       const float y = x * sf;
-      gacc += sf * (cosf(y) * d[3 + c * 5 + f] - sinf(y) * d[18 + c * 5 + f]);
+      gacc += sf * (cosf(y) * d[16 * c + 1 + f] - sinf(y) * d[16 * c + 6 + f]);
     }
     d_lin[3 * j + c] = gacc;
   }
@@ -896,7 +903,7 @@ extern "C" int esr_tonemap_encode_fwd(const float *lin_off, const float *lin_emo
                                       esr_stream_t stream) {
   ESR_CHECK_ARG(m3 >= 0);
   if (m3 == 0) return ESR_OK;
-  ESR_CHECK_ARG(lin_off && lin && tfeat && (!lin_emo || (h_ray && em_modes)));
+  ESR_CHECK_ARG(lin_off && lin && (!lin_emo || (h_ray && em_modes)));   // tfeat nullable: combine only
   cudaStream_t st = (cudaStream_t)stream;
   ESR_STAGE("k_tonemap_encode_fwd", st);
   if (out_is_bf16)

@@ -92,10 +92,36 @@ extern "C" int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const voi
     return BWD_CALL(96, 192, 3, 56);
   }
   if (d->k0 == 48 && d->width == 192 && d->n_hidden == 1) {
-    ESR_CHECK_ARG(!d_x || dx_cols <= 40);
-    return BWD_CALL(48, 192, 1, 40);
+    ESR_CHECK_ARG(!d_x || dx_cols <= 48);
+    return BWD_CALL(48, 192, 1, 48);
   }
 #undef BWD_CALL
   set_error("esr_mlp_bwd: MLP shape k0=%d width=%d hidden=%d is not instantiated", d->k0, d->width, d->n_hidden);
   return ESR_ERR_BAD_ARG;
+}
+
+// fused tone-map net (voxurff.py:783-788 + pbr/module.py:24-39): see mlp_tc.cu
+static int check_tonemap_desc(const esr_mlp_desc_t *d) {
+  if (int e = check_desc(d)) return e;
+  ESR_CHECK_ARG(d->k0 == 48 && d->n_hidden == 1 && d->n_out <= 3);
+  return ESR_OK;
+}
+
+extern "C" int esr_tonemap_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const float *lin, int64_t m, float *rgb,
+                                   esr_stream_t stream) {
+  if (int e = check_tonemap_desc(d)) return e;
+  ESR_CHECK_ARG(m >= 0);
+  if (m == 0) return ESR_OK;
+  ESR_CHECK_ARG(image && lin && rgb);
+  return tc_tonemap_fwd(d, image, lin, m, rgb, (cudaStream_t)stream);
+}
+
+extern "C" int esr_tonemap_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const float *lin, const float *rgb,
+                                   const float *d_rgb, const float *d_lin_direct, int64_t m, float *d_lin,
+                                   float *grad_flat, esr_stream_t stream) {
+  if (int e = check_tonemap_desc(d)) return e;
+  ESR_CHECK_ARG(m >= 0);
+  if (m == 0) return ESR_OK;
+  ESR_CHECK_ARG(image && lin && rgb && d_rgb && d_lin && grad_flat);
+  return tc_tonemap_bwd(d, image, lin, rgb, d_rgb, d_lin_direct, m, d_lin, grad_flat, (cudaStream_t)stream);
 }

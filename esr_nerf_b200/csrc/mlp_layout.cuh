@@ -69,6 +69,11 @@ int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t
 int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, const float *d_y, int64_t row_begin,
              int64_t row_end, int64_t m_total, const void *hidden, void *d_z, float *d_z_out, float *d_x,
              int dx_cols, int accumulate, cudaStream_t st);
+// fused tone-map net (33 -> 192 -> 3, k0 = 48, one hidden layer): forward from the f32 linear radiance [m,3] with the
+// positional encoding computed in the kernel; backward = data gradient + all weight gradients in one kernel
+int tc_tonemap_fwd(const esr_mlp_desc_t *d, const void *tc_image, const float *lin, int64_t m, float *y, cudaStream_t st);
+int tc_tonemap_bwd(const esr_mlp_desc_t *d, const void *tc_image, const float *lin, const float *y, const float *d_y,
+                   const float *d_direct, int64_t m, float *d_lin, float *grad_flat, cudaStream_t st);
 // hidden-layer weight / bias gradients: grad_flat (flat master layout) += dZ_l^T . In_l for l = 0 .. n_hidden-1
 int tc_wgrad(const esr_mlp_desc_t *d, const void *x, int64_t row_begin, int64_t row_end, int64_t m_total,
              const void *hidden, const void *d_z, float *grad_flat, cudaStream_t st);

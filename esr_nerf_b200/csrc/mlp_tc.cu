@@ -278,8 +278,21 @@ struct EpiThread {
       : row_in_tile(32 * (warp & 3) + lane), grp(warp >> 2), lane_base((32u * (warp & 3)) << 16) {}
 };
 
+// tone-map positional encoding of one channel (voxurff.py:783-788) as the 16 bf16 columns [16 c, 16 c + 16) of the
+// internal tone-map row: lin, sin(lin 2^f) f<5, cos(lin 2^f) f<5, 5 zeros — two 16-byte chunks; s / c return the
+// f32 sines / cosines (the fused backward needs them again)
+ESR_D void tonemap_pe_channel(float x, uint4 &lo, uint4 &hi, float (&sn)[5], float (&cs)[5]) {
+#pragma unroll
+  for (int f = 0; f < 5; ++f)   // SFU sine / cosine: |error| ~ |y| 2^-23, far below the bf16 rounding that follows
+    __sincosf(__fmul_rn(x, (float)(1 << f)), &sn[f], &cs[f]);
+  lo = make_uint4(pack2(x, sn[0]), pack2(sn[1], sn[2]), pack2(sn[3], sn[4]), pack2(cs[0], cs[1]));
+  hi = make_uint4(pack2(cs[2], cs[3]), pack2(cs[4], 0.f), 0u, 0u);
+}
+
 // NO = compile-time bound on the real output columns (3: radiance / tone-map / emission nets, 8: the 5-output BRDF net)
-template <int K0, int NH, int NO>
+// XSRC = 0: x rows come tiled from global memory; 1 (K0 = 48 only): `x` is the f32 [m,3] linear radiance and the CTA
+// computes the tone-map encoding of its tile itself (no feature rows in HBM at all)
+template <int K0, int NH, int NO, int XSRC = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_fwd_tc(const uint8_t *__restrict__ image, const __nv_bfloat16 *__restrict__ x, int64_t row_begin,
                  int64_t row_end, int64_t m_total, float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden,
@@ -316,10 +329,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   auto load_x = [&](int64_t tile) {  // 4 epilogue threads per row: 16-byte chunks c = grp, grp + 4, ...
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool ok = row < row_end;
-    const uint4 *x4 = reinterpret_cast<const uint4 *>(x);  // tiled layout: a warp reads 512 contiguous bytes per chunk
+    if constexpr (XSRC == 1) {   // column group g < 3 encodes channel g of its row into chunks 2 g, 2 g + 1
+      if (et.grp < 3) {
+        const float v = ok ? __ldg(reinterpret_cast<const float *>(x) + 3 * row + et.grp) : 0.f;
+        uint4 lo, hi;
+        float sn[5], cs[5];
+        tonemap_pe_channel(v, lo, hi, sn, cs);
+        if (!ok) lo = hi = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp) * (TC_TM * 16) + t * 16) = lo;
+        *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hi;
+      }
+    } else {
+      const uint4 *x4 = reinterpret_cast<const uint4 *>(x);  // tiled layout: a warp reads 512 contiguous bytes per chunk
 #pragma unroll
-    for (int c = et.grp; c < K0 / 8; c += 4)
-      cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, x4 + tiled_chunk_index(ok ? row : row_begin, c, K0 / 8), ok);
+      for (int c = et.grp; c < K0 / 8; c += 4)
+        cp_async16_zfill(sbase + S::x + c * (TC_TM * 16) + t * 16, x4 + tiled_chunk_index(ok ? row : row_begin, c, K0 / 8), ok);
+    }
   };
 
   if (is_epi && blockIdx.x < n_tiles) load_x(blockIdx.x);
@@ -835,6 +860,271 @@ static int launch_wgrad(const __nv_bfloat16 *dz, const __nv_bfloat16 *in, int64_
   return ESR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused tone-map backward (voxurff.py:783-788 + pbr/module.py:24-39, 33 -> 192 -> 3): ONE kernel reads
+// (lin, rgb, d_rgb[, d_lin_direct]) = 36-48 B per row and writes d_lin (12 B per row) plus the weight gradients.
+// Everything the unfused path moved through HBM (encoded rows 96 B, hidden activations 384 B + masks, their
+// cotangents 384 B, the encoded-row cotangent 192 B: ~2.4 KB per row over four kernels) stays on the SM:
+//   T0  the tile's encoding X is recomputed from lin into shared memory (K-major for the forward MMA; the same bytes
+//       are an MN-major operand for the weight-gradient MMA), dZ_out = d_rgb * rgb (1 - rgb) likewise
+//   E1  H = relu(X W0^T + b0) recomputed on the tensor core -> bf16 tile Hs in shared memory + ReLU masks in registers
+//   E2  dZ0 = (dZ_out Wo) * mask -> TMEM (A operand of the d_x MMA) + bf16 tile Zs in shared memory
+//   E3  d_x = dZ0 W0: thread (row, channel) holds the 16 encoded columns of its channel and the sines / cosines it
+//       computed in T0 -> d_lin without any cross-thread traffic
+//   weight gradients accumulate in TMEM across all tiles of the CTA: dW0|db0 += Zs^T [X | 1] (two M = 128 halves,
+//   N = 64), dWo^T += Hs^T dZ_out (N = 16); db_out is a register sum.  They leave through REDs once per CTA.
+// TMEM: D [0,192)  A [192,288)  S [288,336)  dW0 halves [336,400) [400,464)  dWo^T halves [464,480) [480,496).
+// ------------------------------------------------------------------------------------------------
+struct TmBwdSm {
+  static constexpr int w0 = 0;                         // W0   K-major [6][192][8]
+  static constexpr int wot = w0 + TC_W * 48 * 2;       // Wo^T K-major [2][192][8]
+  static constexpr int w0t = wot + TC_W * 16 * 2;      // W0^T K-major [24][48][8]
+  static constexpr int bias = w0t + 48 * TC_W * 2;     // b0 f32 [192]
+  static constexpr int x = bias + TC_W * 4;            // X tile [8][128][8]: 6 feature chunks, ones chunk, zero chunk
+  static constexpr int hs = x + 8 * TC_TM * 16;        // H tile  [24][128][8]
+  static constexpr int zs = hs + 24 * TC_TM * 16;      // dZ0 tile [24][128][8]
+  static constexpr int dzo = zs + 24 * TC_TM * 16;     // dZ_out tile [2][128][8] (chunk 1 zero)
+  static constexpr int bar = dzo + 2 * TC_TM * 16;     // bar_mma, bar_w, TMEM slot
+  static constexpr int bytes = bar + 32;
+};
+constexpr uint32_t TMB_D = 0, TMB_A = 192, TMB_S = 288, TMB_G0 = 336, TMB_GO = 464;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_tonemap_bwd_fused(const uint8_t *__restrict__ image, int64_t bwd_off, int64_t bias_off, const float *__restrict__ lin,
+                        const float *__restrict__ y, const float *__restrict__ d_y, const float *__restrict__ d_direct,
+                        int64_t m, float *__restrict__ d_lin, float *__restrict__ gW0, float *__restrict__ gb0,
+                        float *__restrict__ gWo, float *__restrict__ gbo, int n_out, int act) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = TmBwdSm;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
+  const uint32_t sbase = smem_addr(smem);
+  const uint32_t bar = sbase + S::bar, bar_w = bar + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 16);
+
+  stage_bytes(smem + S::w0, image, TC_W * 48 * 2);
+  stage_bytes(smem + S::wot, image + bwd_off, TC_W * 16 * 2 + 48 * TC_W * 2);   // Wo^T and W0^T are adjacent in the image
+  stage_bytes(smem + S::bias, image + bias_off, TC_W * 4);
+  for (int i = threadIdx.x; i < TC_TM; i += blockDim.x) {   // constant zero chunks
+    *reinterpret_cast<uint4 *>(smem + S::x + 7 * (TC_TM * 16) + i * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(smem + S::dzo + TC_TM * 16 + i * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+  }
+  if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
+
+  const int64_t n_tiles = (m + TC_TM - 1) / TC_TM;
+  const EpiThread et(warp, lane);
+  const int t = et.row_in_tile;
+  uint32_t phase = 0;
+  float bo_acc[3] = {0.f, 0.f, 0.f};
+  int it = 0;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int64_t row = tile * TC_TM + t;
+    const bool valid = is_epi && row < m;
+    float xv = 0.f, sn[5], cs[5], dz[3] = {0.f, 0.f, 0.f};
+    // ---- T0: encoding + output cotangent tiles ----
+    if (is_epi) {
+      if (it > 0) mbar_wait(bar_w, (uint32_t)((it - 1) & 1));   // the weight-gradient MMAs that read the tiles have retired
+      if (et.grp < 3) {
+        xv = valid ? __ldg(lin + 3 * row + et.grp) : 0.f;
+        uint4 lo, hi;
+        tonemap_pe_channel(xv, lo, hi, sn, cs);
+        if (!valid) lo = hi = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp) * (TC_TM * 16) + t * 16) = lo;
+        *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hi;
+      } else {   // the "ones" column (bias gradient); zero for rows past the end
+        *reinterpret_cast<uint4 *>(smem + S::x + 6 * (TC_TM * 16) + t * 16) = make_uint4(valid ? 0x00003f80u : 0u, 0u, 0u, 0u);
+      }
+      if (et.grp == 0) {
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c < n_out) {
+              const float yy = __ldg(y + row * n_out + c);
+              dz[c] = __ldg(d_y + row * n_out + c) * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
+            }
+        }
+        *reinterpret_cast<uint4 *>(smem + S::dzo + t * 16) = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
+      }
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (is_issuer && lane == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+        mma_ss(tmem + TMB_D, make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
+               make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
+      mma_commit(bar);
+    }
+    // ---- E1: H = relu(Z0 + b0) -> shared tile + masks ----
+    uint32_t mask[2] = {0u, 0u};
+    if (is_epi) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      uint32_t r[3][16];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + TMB_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int col0 = TC_GCOLS * et.grp + 16 * cc;
+        uint32_t p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
+          p[j] = pack2(fmaxf(__uint_as_float(r[cc][2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(r[cc][2 * j + 1]) + bb.y, 0.f));
+          const uint32_t tt = p[j] + 0x7fff7fffu;
+          mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (0x00010001u << (8 * (cc & 1) + j));
+        }
+        *reinterpret_cast<uint4 *>(smem + S::hs + (col0 / 8) * (TC_TM * 16) + t * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4 *>(smem + S::hs + (col0 / 8 + 1) * (TC_TM * 16) + t * 16) = make_uint4(p[4], p[5], p[6], p[7]);
+      }
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (is_issuer && lane == 0) {
+      tc_fence_after();
+      mma_ss(tmem + TMB_D, make_desc(sbase + S::dzo, TC_TM * 16, 128), make_desc(sbase + S::wot, TC_W * 16, 128),
+             make_idesc(TC_W), 0);
+      mma_commit(bar);
+      // dWo^T += Hs^T dZ_out (rows are the K dimension: both tiles are MN-major operands as they lie)
+#pragma unroll
+      for (int s = 0; s < TC_TM / 16; ++s)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          mma_ss(tmem + TMB_GO + 16 * h, make_desc(sbase + S::hs + h * 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16),
+                 make_desc(sbase + S::dzo + s * 256, 128, TC_TM * 16), make_idesc_mn(16), (it | s) != 0);
+    }
+    // ---- E2: dZ0 = dH * mask -> TMEM A operand + shared tile ----
+    if (is_epi) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      uint32_t r[3][16];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + TMB_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int col0 = TC_GCOLS * et.grp + 16 * cc;
+        const uint32_t mk = mask[cc >> 1] >> (8 * (cc & 1));
+        uint32_t p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & (((mk >> j) & 0x00010001u) * 0xffffu);
+        tmem_st8(tmem + et.lane_base + TMB_A + col0 / 2, p);
+        *reinterpret_cast<uint4 *>(smem + S::zs + (col0 / 8) * (TC_TM * 16) + t * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4 *>(smem + S::zs + (col0 / 8 + 1) * (TC_TM * 16) + t * 16) = make_uint4(p[4], p[5], p[6], p[7]);
+      }
+      tmem_st_wait();
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (is_issuer && lane == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < TC_W / 16; ++s)
+        mma_ts(tmem + TMB_S, tmem + TMB_A + 8 * s, make_desc(sbase + S::w0t + 2 * s * (48 * 16), 48 * 16, 128), make_idesc(48),
+               s > 0);
+      mma_commit(bar);
+      // dW0 | db0 += Zs^T [X | 1]
+#pragma unroll
+      for (int s = 0; s < TC_TM / 16; ++s)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          mma_ss(tmem + TMB_G0 + 64 * h, make_desc(sbase + S::zs + h * 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16),
+                 make_desc(sbase + S::x + s * 256, 128, TC_TM * 16), make_idesc_mn(64), (it | s) != 0);
+      mma_commit(bar_w);
+    }
+    // ---- E3: d_lin of (row, channel) from the 16 encoded-column cotangents of the channel ----
+    if (is_epi) {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      if (et.grp < 3) {
+        uint32_t r[16];
+        tmem_ld16(tmem + et.lane_base + TMB_S + 16 * et.grp, r);
+        tmem_ld_wait();
+        if (valid) {
+          float g = __uint_as_float(r[0]) + (d_direct ? __ldg(d_direct + 3 * row + et.grp) : 0.f);
+#pragma unroll
+          for (int f = 0; f < 5; ++f)
+            g += (float)(1 << f) * (cs[f] * __uint_as_float(r[1 + f]) - sn[f] * __uint_as_float(r[6 + f]));
+          d_lin[3 * row + et.grp] = g;
+        }
+      }
+      if (et.grp == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bo_acc[c] += warp_sum(dz[c]);
+      }
+      tc_fence_before();
+    }
+  }
+  // ---- weight gradients: TMEM accumulators -> global (REDs) ----
+  if (it > 0) {
+    if (is_epi) {
+      mbar_wait(bar_w, (uint32_t)((it - 1) & 1));
+      tc_fence_after();
+    }
+    if (warp < 4) {
+      const uint32_t lane_base = (32u * warp) << 16;
+      const int ml = 32 * warp + lane;   // accumulator row = hidden feature (second half: feature 64 + row)
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int o = h == 0 ? ml : 64 + ml;
+        const bool use = h == 0 || ml >= 64;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[16];
+          tmem_ld16(tmem + lane_base + TMB_G0 + 64 * h + 16 * cc, r);
+          tmem_ld_wait();
+          if (!use) continue;
+          if (cc < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              red_add4(gW0 + (int64_t)o * 48 + cc * 16 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          } else {
+            red_add(gb0 + o, __uint_as_float(r[0]));
+          }
+        }
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + TMB_GO + 16 * h, r);
+        tmem_ld_wait();
+        if (use) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c < n_out) red_add(gWo + (int64_t)c * TC_W + o, __uint_as_float(r[c]));
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < n_out) red_add(gbo + c, bo_acc[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_issuer) tmem_dealloc(tmem, TM_COLS);
+}
+
 template <typename K>
 static int set_smem_tc(K kernel, int bytes) {
   ESR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -847,13 +1137,13 @@ static unsigned tc_grid(int64_t rows) {
   return (unsigned)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
 }
 
-template <int K0, int NH, int NO>
+template <int K0, int NH, int NO, int XSRC = 0>
 static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t rb, int64_t re, int64_t mt,
                       float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
-  auto kern = k_mlp_fwd_tc<K0, NH, NO>;
+  auto kern = k_mlp_fwd_tc<K0, NH, NO, XSRC>;
   constexpr int bytes = FwdSm<K0, NH>::bytes;
   if (int e = set_smem_tc(kern, bytes)) return e;
-  ESR_STAGE(K0 == 96 ? "k_mlp_fwd_tc_radiance" : "k_mlp_fwd_tc_tonemap", st);
+  ESR_STAGE(K0 == 96 ? "k_mlp_fwd_tc_radiance" : (XSRC ? "k_tonemap_fwd_fused" : "k_mlp_fwd_tc_tonemap"), st);
   kern<<<tc_grid(re - rb), TC_THREADS, bytes, st>>>((const uint8_t *)image, (const __nv_bfloat16 *)x, rb, re, mt, y,
                                                     (__nv_bfloat16 *)hidden, save_begin, d->n_out, d->act);
   ESR_LAUNCH_OK();
@@ -921,6 +1211,24 @@ int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t
     return launch_fwd<48, 1, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
   set_error("tc_fwd: shape not instantiated");
   return ESR_ERR_BAD_ARG;
+}
+
+int tc_tonemap_fwd(const esr_mlp_desc_t *d, const void *tc_image, const float *lin, int64_t m, float *y, cudaStream_t st) {
+  return launch_fwd<48, 1, 3, 1>(d, tc_image, lin, 0, m, m, y, nullptr, 0, st);
+}
+
+int tc_tonemap_bwd(const esr_mlp_desc_t *d, const void *tc_image, const float *lin, const float *y, const float *d_y,
+                   const float *d_direct, int64_t m, float *d_lin, float *grad_flat, cudaStream_t st) {
+  const TcLayout T = tc_layout(d);
+  const MlpLayout L = layout_of(d);
+  auto kern = k_tonemap_bwd_fused;
+  if (int e = set_smem_tc(kern, TmBwdSm::bytes)) return e;
+  ESR_STAGE("k_tonemap_bwd_fused", st);
+  kern<<<tc_grid(m), TC_THREADS, TmBwdSm::bytes, st>>>((const uint8_t *)tc_image, T.bwd_off(), T.f_bias(), lin, y, d_y, d_direct,
+                                                       m, d_lin, grad_flat + L.flat_w(0), grad_flat + L.flat_b(0),
+                                                       grad_flat + L.flat_w(1), grad_flat + L.flat_b(1), d->n_out, d->act);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
 }
 
 int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, const float *d_y, int64_t row_begin,

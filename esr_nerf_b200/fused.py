@@ -34,7 +34,7 @@ def reset_stats():
 FEAT_DIM = 96
 FEAT_GRAD_DIM = 56
 TFEAT_DIM = 48
-TFEAT_GRAD_DIM = 40
+TFEAT_GRAD_DIM = 48
 
 RADIANCE_DESC = dict(k0=96, width=192, n_hidden=3, n_out=3, act=1)   # pbr/module.py:6-21 (softplus)
 TONEMAP_DESC = dict(k0=48, width=192, n_hidden=1, n_out=3, act=2)    # pbr/module.py:24-39 (sigmoid)
@@ -286,15 +286,31 @@ def mlp_infer(desc, flat, x, rb, re, m_total):
     return y
 
 
-def tonemap_infer(lin, flat_tone):
-    """rgb = sigmoid(tonemapper(PE(lin))) without autograd state (voxurff.py:783-788)"""
+def _tonemap_fwd(lin, img):
+    """rgb = sigmoid(tonemapper(PE(lin))) by the fused kernel: the encoding never leaves the SM"""
+    m = lin.shape[0]
+    rgb = torch.empty(m, 3, dtype=torch.float32, device=lin.device)
+    d = _desc(TONEMAP_DESC)
+    check(_lib.lib().esr_tonemap_mlp_fwd(ctypes.byref(d), ptr(img), ptr(lin), m, ptr(rgb), stream_ptr()))
+    return rgb
+
+
+def _tonemap_bwd(lin, img, rgb, d_rgb, d_lin_direct):
+    """(d_lin, flat weight gradient) by the fused backward kernel (hidden activations recomputed on the SM)"""
     L = _lib.lib()
     m = lin.shape[0]
-    lin = lin.contiguous()
-    xt = torch.empty(L.esr_mlp_act_rows(m), TFEAT_DIM, dtype=torch.bfloat16, device=lin.device)
-    lin_copy = torch.empty_like(lin)
-    check(L.esr_tonemap_encode_fwd(ptr(lin), None, None, None, m, ptr(lin_copy), ptr(xt), 1, stream_ptr()))
-    return mlp_infer(TONEMAP_DESC, flat_tone, xt, 0, m, m)
+    d = _desc(TONEMAP_DESC)
+    d_lin = torch.empty_like(lin)
+    g_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=lin.device)
+    check(L.esr_tonemap_mlp_bwd(ctypes.byref(d), ptr(img), ptr(lin), ptr(rgb), ptr(d_rgb.contiguous()),
+                                ptr(d_lin_direct.contiguous()) if d_lin_direct is not None else None, m, ptr(d_lin),
+                                ptr(g_flat), stream_ptr()))
+    return d_lin, g_flat
+
+
+def tonemap_infer(lin, flat_tone):
+    """rgb = sigmoid(tonemapper(PE(lin))) without autograd state (voxurff.py:783-788)"""
+    return _tonemap_fwd(lin.contiguous(), mlp_pack(TONEMAP_DESC, flat_tone))
 
 
 def composite_infer(h_w, a, b, s: Streams):
@@ -405,34 +421,21 @@ class Shade(torch.autograd.Function):
 
 
 class Tonemap(torch.autograd.Function):
-    """rgb = sigmoid(tonemapper([lin, sin(lin 2^f), cos(lin 2^f)]))  (voxurff.py:783-788) on tensor cores."""
+    """rgb = sigmoid(tonemapper([lin, sin(lin 2^f), cos(lin 2^f)]))  (voxurff.py:783-788): fused tone-map kernels."""
 
     @staticmethod
     def forward(ctx, lin, flat_tone):
-        L = _lib.lib()
-        m = lin.shape[0]
         lin = lin.contiguous()
-        xt = torch.empty(L.esr_mlp_act_rows(m), TFEAT_DIM, dtype=torch.bfloat16, device=lin.device)  # tiled layout
-        lin_copy = torch.empty_like(lin)
-        check(L.esr_tonemap_encode_fwd(ptr(lin), None, None, None, m, ptr(lin_copy), ptr(xt), 1, stream_ptr()))
         img = mlp_pack(TONEMAP_DESC, flat_tone)
-        rgb, hid = _mlp_forward(TONEMAP_DESC, img, xt, 0, m, m, any(ctx.needs_input_grad))
-        ctx.hidden = hid
-        ctx.save_for_backward(lin, xt, img, rgb)
+        rgb = _tonemap_fwd(lin, img)
+        ctx.save_for_backward(lin, img, rgb)
         return rgb
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_rgb):
-        lin, xt, img, rgb = ctx.saved_tensors
-        m = lin.shape[0]
-        d_xt = torch.empty(m, TFEAT_GRAD_DIM, dtype=torch.float32, device=lin.device)
-        g_flat, _ = _mlp_backward(TONEMAP_DESC, img, xt, rgb, d_rgb.contiguous(), 0, m, m, ctx.hidden, d_xt,
-                                  TFEAT_GRAD_DIM, 0)
-        ctx.hidden = None
-        d_lin = torch.empty_like(lin)
-        check(_lib.lib().esr_tonemap_encode_bwd(ptr(lin), ptr(d_xt), None, m, ptr(d_lin), stream_ptr()))
-        return d_lin, g_flat
+        lin, img, rgb = ctx.saved_tensors
+        return _tonemap_bwd(lin, img, rgb, d_rgb, None)
 
 
 class CombineTonemap(torch.autograd.Function):
@@ -445,30 +448,23 @@ class CombineTonemap(torch.autograd.Function):
         L = _lib.lib()
         m = lin_off.shape[0]
         lin_off, lin_emo = lin_off.contiguous(), lin_emo.contiguous()
-        xt = torch.empty(L.esr_mlp_act_rows(m), TFEAT_DIM, dtype=torch.bfloat16, device=lin_off.device)  # tiled layout
         lin = torch.empty_like(lin_off)
-        check(L.esr_tonemap_encode_fwd(ptr(lin_off), ptr(lin_emo), ptr(h_ray), ptr(em_modes), m, ptr(lin), ptr(xt), 1,
+        # combine only (tfeat = NULL): the fused tone-map kernel encodes lin itself
+        check(L.esr_tonemap_encode_fwd(ptr(lin_off), ptr(lin_emo), ptr(h_ray), ptr(em_modes), m, ptr(lin), None, 1,
                                        stream_ptr()))
         img = mlp_pack(TONEMAP_DESC, flat_tone)
-        rgb, hid = _mlp_forward(TONEMAP_DESC, img, xt, 0, m, m, any(ctx.needs_input_grad[:3]))
+        rgb = _tonemap_fwd(lin, img)
         # off_sees_on: the off net receives the cotangent of emission-on rows too (ESRNeRF adds the two radiances
         # without a stop-gradient, esrnerf.py:751-757; VoxurfF detaches, voxurff.py:243-254)
-        ctx.hidden, ctx.ordered, ctx.off_sees_on = hid, ordered, off_sees_on
-        ctx.save_for_backward(lin, xt, img, rgb, h_ray, em_modes)
+        ctx.ordered, ctx.off_sees_on = ordered, off_sees_on
+        ctx.save_for_backward(lin, img, rgb, h_ray, em_modes)
         return rgb, lin
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_rgb, d_lin_direct):
-        lin, xt, img, rgb, h_ray, em_modes = ctx.saved_tensors
-        m = lin.shape[0]
-        d_xt = torch.empty(m, TFEAT_GRAD_DIM, dtype=torch.float32, device=lin.device)
-        g_flat, _ = _mlp_backward(TONEMAP_DESC, img, xt, rgb, d_rgb.contiguous(), 0, m, m, ctx.hidden, d_xt,
-                                  TFEAT_GRAD_DIM, 0)
-        ctx.hidden = None
-        d_lin = torch.empty_like(lin)
-        check(_lib.lib().esr_tonemap_encode_bwd(ptr(lin), ptr(d_xt), ptr(d_lin_direct.contiguous()), m, ptr(d_lin),
-                                                stream_ptr()))
+        lin, img, rgb, h_ray, em_modes = ctx.saved_tensors
+        d_lin, g_flat = _tonemap_bwd(lin, img, rgb, d_rgb, d_lin_direct)
         if ctx.ordered:
             # emission-on rows are a prefix and each net back-propagates through its own row range only (Shade.backward):
             # both can read the same cotangent

@@ -368,7 +368,16 @@ def radiance_in_cols(which: str, device) -> torch.Tensor:
 
 
 def tonemap_in_cols(device) -> torch.Tensor:
-    return torch.tensor(list(range(33)) + [-1] * 15, dtype=torch.long, device=device)
+    """Internal 48-column tone-map row -> reference 33-column input [lin 0-2 | sin 3-17 | cos 18-32]
+    (voxurff.py:783-788).  Channel c owns internal columns [16 c, 16 c + 16): lin_c, 5 sines, 5 cosines, 5 zeros — so
+    that one epilogue thread of the fused tone-map kernels holds everything of one channel."""
+    cols = [-1] * 48
+    for c in range(3):
+        cols[16 * c] = c
+        for f in range(5):
+            cols[16 * c + 1 + f] = 3 + c * 5 + f
+            cols[16 * c + 6 + f] = 18 + c * 5 + f
+    return torch.tensor(cols, dtype=torch.long, device=device)
 
 
 def total_variation(v: torch.Tensor, mask=None):

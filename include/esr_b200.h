@@ -276,7 +276,7 @@ int esr_sdf_fd_gradient(const esr_scene_t *sc, const float *rays_o, const float 
  *   to 48 columns (bf16 or f32).
  */
 #define ESR_TFEAT_DIM 48
-#define ESR_TFEAT_GRAD_DIM 40 /* 33 used */
+#define ESR_TFEAT_GRAD_DIM 48 /* channel c: columns [16 c, 16 c + 11) used */
 int esr_tonemap_encode_fwd(const float *lin_off, const float *lin_emo, const int32_t *h_ray,
                            const int64_t *em_modes, int64_t m3, float *lin, void *tfeat,
                            int out_is_bf16, esr_stream_t stream);
@@ -352,6 +352,20 @@ int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const
                 const float *d_y, int64_t row_begin, int64_t row_end, int64_t m_total,
                 const void *hidden, void *d_z, float *d_z_out, float *d_x, int dx_cols,
                 int accumulate, float *grad_flat, esr_stream_t stream);
+
+/*
+ * Fused tone-map net (apply_tonemapper, voxurff.py:783-788: PE(5) of the linear radiance -> 33 -> 192 -> 3 sigmoid,
+ * pbr/module.py:24-39).  d must be the tone-map shape (k0 48, one hidden layer).  The kernels compute the positional
+ * encoding themselves and keep every intermediate on the SM:
+ *   fwd: lin f32 [m,3] -> rgb f32 [m,3]                                   (24 B per row of HBM traffic)
+ *   bwd: (lin, rgb, d_rgb[, d_lin_direct]) -> d_lin [m,3] (= d_lin_direct + the gradient through the net) and
+ *        grad_flat += weight / bias gradients (flat master layout), the hidden activations recomputed in the kernel.
+ */
+int esr_tonemap_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const float *lin, int64_t m, float *rgb,
+                        esr_stream_t stream);
+int esr_tonemap_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const float *lin, const float *rgb,
+                        const float *d_rgb, const float *d_lin_direct, int64_t m, float *d_lin, float *grad_flat,
+                        esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer step: app/utils/optimizer.py:63-228 — dense Adam with an optional per-voxel learning
