@@ -113,6 +113,149 @@ __global__ void __launch_bounds__(256)
                           __ldg(pts + 3 * j + 2));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Light-transport accumulation (esrnerf.py:556-574, 654-677): for LTS point p with unit normal n, BRDF parameters
+// (base colour a, roughness r, metallic m) and n2 hemisphere directions w_j, the Monte-Carlo estimates
+//     off_hat[v] = mean_j (L_off_j + env_j) R(w_j, wo_v),   reflect[v] = mean_j L_emo_j R(w_j, wo_v)
+// for the two outgoing directions wo_0 = -view, wo_1 = -random view, with the Disney-style R of
+// pbr/functions.py:108-173.  One warp per point, lanes over the secondary rays, warp reduction; replaces ~60 elementwise
+// torch kernels forward (and ~120 backward) on [2 P n2, 3] tensors.
+// ---------------------------------------------------------------------------------------------
+struct Brdf {
+  float R[3];                      // reflectance (rgb)
+  float dR_da[3], dR_dm[3];        // d R_c / d a_c (diagonal), d R_c / d m
+  float dR_dr[3];                  // d R_c / d r
+};
+
+ESR_D float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+template <bool GRAD>
+ESR_D Brdf disney(const float *a, float r, float m, const float *n, const float *wi, const float *wo) {
+  constexpr float EPS = 1e-7f, PI = 3.14159265358979323846f;
+  Brdf b;
+  float h[3] = {wi[0] + wo[0], wi[1] + wo[1], wi[2] + wo[2]};
+  const float hn = fmaxf(sqrtf(dot3(h, h)), 1e-12f);   // F.normalize eps
+  h[0] /= hn, h[1] /= hn, h[2] /= hn;
+  const float noh = fmaxf(dot3(n, h), 0.f), ooh = fmaxf(dot3(wo, h), 0.f);
+  const float ion = fmaxf(dot3(wi, n), 0.f), oon = fmaxf(dot3(wo, n), 0.f);
+  const float r2 = fmaxf(r * r, EPS);
+  const float D = (1.f / (r2 * PI)) * expf((2.f / r2) * (noh - 1.f));
+  const float k = (1.f + r) * (1.f + r) / 8.f;
+  const float di = ion * (1.f - k) + k, dO = oon * (1.f - k) + k;
+  const float vi = 0.5f / fmaxf(di, EPS), vo = 0.5f / fmaxf(dO, EPS);
+  const float V = vi * vo;
+  const float q = 1.f - ooh, q5 = q * q * q * q * q;
+  const float scale = ion * PI * 2.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float F0 = 0.04f * (1.f - m) + a[c] * m;
+    const float F = F0 + (1.f - F0) * q5;
+    b.R[c] = ((1.f - m) * a[c] / PI + D * F * V) * scale;
+    if (GRAD) {
+      b.dR_da[c] = ((1.f - m) / PI + D * V * m * (1.f - q5)) * scale;
+      b.dR_dm[c] = (-a[c] / PI + D * V * (a[c] - 0.04f) * (1.f - q5)) * scale;
+      // d D / d r (through r2 = r^2 where the clamp is inactive), d V / d r (through k = (1 + r)^2 / 8)
+      const float dD = (r * r > EPS) ? D * (-2.f * (noh - 1.f) / (r2 * r2) - 1.f / r2) * 2.f * r : 0.f;
+      const float dk = (1.f + r) / 4.f;
+      const float dvi = (di > EPS) ? -0.5f * (1.f - ion) / (di * di) * dk : 0.f;
+      const float dvo = (dO > EPS) ? -0.5f * (1.f - oon) / (dO * dO) * dk : 0.f;
+      b.dR_dr[c] = F * (dD * V + D * (dvi * vo + vi * dvo)) * scale;
+    }
+  }
+  return b;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+    k_lts_accumulate(const float *__restrict__ normal, const float *__restrict__ base, const float *__restrict__ rough,
+                     const float *__restrict__ metal, const float *__restrict__ wo_a, const float *__restrict__ wo_b,
+                     const float *__restrict__ dirs, const float *__restrict__ rad_off, const float *__restrict__ rad_emo,
+                     int64_t P, int n2, float *__restrict__ off_hat, float *__restrict__ reflect,
+                     const float *__restrict__ g_off_hat, const float *__restrict__ g_reflect, float *__restrict__ g_base,
+                     float *__restrict__ g_rough, float *__restrict__ g_metal, float *__restrict__ g_rad_off,
+                     float *__restrict__ g_rad_emo) {
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = lane_id();
+  if (p >= P) return;
+  float n[3], a[3], wo[2][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    n[c] = __ldg(normal + 3 * p + c), a[c] = __ldg(base + 3 * p + c);
+    wo[0][c] = __ldg(wo_a + 3 * p + c), wo[1][c] = __ldg(wo_b + 3 * p + c);
+  }
+  const float r = __ldg(rough + p), m = __ldg(metal + p);
+  const float inv = 1.f / (float)n2;
+  float acc_off[2][3] = {}, acc_emo[2][3] = {};       // forward sums
+  float ga[3] = {}, gr = 0.f, gm = 0.f;                // backward sums over (j, v)
+  float go[2][3], ge[2][3];
+  if (BWD) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        go[v][c] = g_off_hat ? __ldg(g_off_hat + 3 * (v * P + p) + c) * inv : 0.f;
+        ge[v][c] = __ldg(g_reflect + 3 * (v * P + p) + c) * inv;
+      }
+  }
+  for (int j = (int)lane; j < n2; j += 32) {
+    const int64_t ray = p * n2 + j;
+    float wi[3], lo[3] = {0.f, 0.f, 0.f}, le[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      wi[c] = __ldg(dirs + 3 * ray + c);
+      if (rad_off) lo[c] = __ldg(rad_off + 3 * ray + c);
+      le[c] = __ldg(rad_emo + 3 * ray + c);
+    }
+    float d_lo[3] = {0.f, 0.f, 0.f}, d_le[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const Brdf b = disney<BWD>(a, r, m, n, wi, wo[v]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (!BWD) {
+          acc_off[v][c] += lo[c] * b.R[c];
+          acc_emo[v][c] += le[c] * b.R[c];
+        } else {
+          const float gR = go[v][c] * lo[c] + ge[v][c] * le[c];   // cotangent of R_c for this (ray, view)
+          ga[c] += gR * b.dR_da[c];
+          gm += gR * b.dR_dm[c];
+          gr += gR * b.dR_dr[c];
+          d_lo[c] += go[v][c] * b.R[c];
+          d_le[c] += ge[v][c] * b.R[c];
+        }
+      }
+    }
+    if (BWD) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (g_rad_off) g_rad_off[3 * ray + c] = d_lo[c];
+        g_rad_emo[3 * ray + c] = d_le[c];
+      }
+    }
+  }
+  if (!BWD) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float so = warp_sum(acc_off[v][c]), se = warp_sum(acc_emo[v][c]);
+        if (lane == 0) {
+          if (off_hat) off_hat[3 * (v * P + p) + c] = so * inv;
+          reflect[3 * (v * P + p) + c] = se * inv;
+        }
+      }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float s = warp_sum(ga[c]);
+      if (lane == 0) g_base[3 * p + c] = s;
+    }
+    gr = warp_sum(gr), gm = warp_sum(gm);
+    if (lane == 0) g_rough[p] = gr, g_metal[p] = gm;
+  }
+}
+
 int check_grid(const esr_scene_t *sc) {
   ESR_CHECK_ARG(sc != nullptr);
   ESR_CHECK_ARG(sc->gx > 1 && sc->gy > 1 && sc->gz > 1 && sc->stepdist > 0.f);
@@ -159,6 +302,39 @@ extern "C" int esr_sdf_expgrad_bwd(const esr_scene_t *sc, const float *pts, int6
   ESR_CHECK_ARG(pts && grad_sdf_grid && (g_sdf || g_grad));
   ESR_STAGE("k_sdf_expgrad_bwd", stream);
   k_sdf_expgrad_bwd<<<cdiv(m, 256), 256, 0, (cudaStream_t)stream>>>(*sc, pts, m, g_sdf, g_grad, grad_sdf_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_lts_accumulate_fwd(const float *normal, const float *base, const float *rough, const float *metal,
+                                      const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
+                                      const float *rad_emo, int64_t n_pts, int n_dirs, float *off_hat, float *reflect,
+                                      esr_stream_t stream) {
+  ESR_CHECK_ARG(n_pts >= 0 && n_dirs > 0);
+  if (n_pts == 0) return ESR_OK;
+  ESR_CHECK_ARG(normal && base && rough && metal && wo_a && wo_b && dirs && rad_emo && reflect && (!rad_off == !off_hat));
+  ESR_STAGE("k_lts_accumulate_fwd", stream);
+  k_lts_accumulate<false><<<cdiv(n_pts * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      normal, base, rough, metal, wo_a, wo_b, dirs, rad_off, rad_emo, n_pts, n_dirs, off_hat, reflect, nullptr, nullptr,
+      nullptr, nullptr, nullptr, nullptr, nullptr);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_lts_accumulate_bwd(const float *normal, const float *base, const float *rough, const float *metal,
+                                      const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
+                                      const float *rad_emo, int64_t n_pts, int n_dirs, const float *g_off_hat,
+                                      const float *g_reflect, float *g_base, float *g_rough, float *g_metal,
+                                      float *g_rad_off, float *g_rad_emo, esr_stream_t stream) {
+  ESR_CHECK_ARG(n_pts >= 0 && n_dirs > 0);
+  if (n_pts == 0) return ESR_OK;
+  ESR_CHECK_ARG(normal && base && rough && metal && wo_a && wo_b && dirs && rad_emo && g_reflect && g_base && g_rough &&
+                g_metal && g_rad_emo);
+  ESR_CHECK_ARG(!rad_off == !g_off_hat && !rad_off == !g_rad_off);
+  ESR_STAGE("k_lts_accumulate_bwd", stream);
+  k_lts_accumulate<true><<<cdiv(n_pts * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      normal, base, rough, metal, wo_a, wo_b, dirs, rad_off, rad_emo, n_pts, n_dirs, nullptr, nullptr, g_off_hat, g_reflect,
+      g_base, g_rough, g_metal, g_rad_off, g_rad_emo);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

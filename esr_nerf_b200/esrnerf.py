@@ -152,14 +152,13 @@ class ESRNeRF(VoxurfF):
             return t.view(-1, 1, c).expand(P, n2, c).flatten(0, 1)
 
         d_flat = dirs.flatten(0, 1).contiguous()
-        wout = torch.cat([-ex(viewdirs, 3), -ex(v_rand, 3)], 0)
-        R = pbr.disney_reflection(ex(base, 3).repeat(2, 1), ex(rough, 1).repeat(2, 1), ex(metal, 1).repeat(2, 1),
-                                  ex(normal, 3).repeat(2, 1), d_flat.repeat(2, 1), wout)
         # incoming radiance: the secondary rays go through the whole render chain (esrnerf.py:576-652)
         off_m, emo_m, last2, st2, hw2 = self._secondary(flats, ex(pts, 3).contiguous(), d_flat)
         env = self.envmap(d_flat) * last2.unsqueeze(-1)
-        off_hat = ((off_m + env).repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
-        reflect = (emo_m.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
+        # Disney reflectance x marched radiance, Monte-Carlo mean over the directions, both outgoing directions: one
+        # kernel (esr_lts_accumulate) instead of the reference's elementwise swarm (esrnerf.py:556-574, 654-666)
+        off_hat, reflect = fused.LtsAccumulate.apply(base, rough.reshape(-1), metal.reshape(-1), off_m + env, emo_m, normal,
+                                                     -viewdirs, -v_rand, d_flat, n2)
         if self.pdra_mode:   # esrnerf.py:668-675
             um = umask.repeat(2)[:, None]
             emo_hat = torch.where(um, emission.repeat(2, 1) + reflect.detach(), reflect)
@@ -271,12 +270,10 @@ class ESRNeRF(VoxurfF):
                 return t.view(-1, 1, c).expand(P, n2, c).flatten(0, 1)
 
             d_flat = dirs.flatten(0, 1).contiguous()
-            R = pbr.disney_reflection(ex(brdf[:, :3], 3).repeat(2, 1), ex(brdf[:, 3:4], 1).repeat(2, 1),
-                                      ex(brdf[:, 4:5], 1).repeat(2, 1), ex(normal, 3).repeat(2, 1), d_flat.repeat(2, 1),
-                                      torch.cat([-ex(vdir, 3), -ex(v_rand, 3)], 0))
             _, emo_m, _, _, _ = self._secondary(flats_ng, ex(pts, 3).contiguous(), d_flat, (False, True, False, False))
             emit = pbr.edit_emission(emit, em_modes[ray], em_int[ray], em_col[ray])
-            reflect = (emo_m.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
+            _, reflect = fused.LtsAccumulate.apply(brdf[:, :3], brdf[:, 3], brdf[:, 4], None, emo_m, normal, -vdir, -v_rand,
+                                                   d_flat, n2)
         return {"lin/pbr/emo": emo, "lin/pbr/emo_hat": emit.repeat(2, 1) + reflect}
 
     @torch.no_grad()

@@ -760,3 +760,42 @@ class ShadePBR(torch.autograd.Function):
                                             ptr(g_sdf), ptr(g_off), ptr(g_emo), ptr(g_brdf), ptr(ctx.fd), stream_ptr()))
         ctx.fd = None
         return (r_sdf, r_off, r_emo, r_brdf, *g_flat, None, None, None)
+
+
+class LtsAccumulate(torch.autograd.Function):
+    """(off_hat, reflect) [2P,3] of the light-transport segment (esrnerf.py:556-574, 654-677): Disney-style reflectance
+    of every (point, direction, outgoing direction) triple times the marched radiance of the secondary rays, averaged
+    over the directions — one kernel forward, one backward (esr_lts_accumulate_*).  rad_off may be None (finetune)."""
+
+    @staticmethod
+    def forward(ctx, base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs, n_dirs):
+        P = base.shape[0]
+        dev = base.device
+        t = [x.contiguous().float() if x is not None else None for x in (base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs)]
+        base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs = t
+        off_hat = _f32(2 * P, 3, dev=dev) if rad_off is not None else None
+        reflect = _f32(2 * P, 3, dev=dev)
+        check(_lib.lib().esr_lts_accumulate_fwd(ptr(normal), ptr(base), ptr(rough), ptr(metal), ptr(wo_a), ptr(wo_b), ptr(dirs),
+                                                ptr(rad_off), ptr(rad_emo), P, int(n_dirs), ptr(off_hat), ptr(reflect),
+                                                stream_ptr()))
+        ctx.n_dirs, ctx.has_off = int(n_dirs), rad_off is not None
+        ctx.save_for_backward(base, rough, metal, rad_emo, normal, wo_a, wo_b, dirs, *([rad_off] if rad_off is not None else []))
+        return (off_hat if off_hat is not None else reflect.new_zeros(0, 3)), reflect
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_off_hat, g_reflect):
+        base, rough, metal, rad_emo, normal, wo_a, wo_b, dirs = ctx.saved_tensors[:8]
+        rad_off = ctx.saved_tensors[8] if ctx.has_off else None
+        P = base.shape[0]
+        dev = base.device
+        g_base, g_rough, g_metal = _f32(P, 3, dev=dev), torch.empty_like(rough), torch.empty_like(metal)
+        g_rad_emo = torch.empty_like(rad_emo)
+        g_rad_off = torch.empty_like(rad_off) if rad_off is not None else None
+        if P:
+            check(_lib.lib().esr_lts_accumulate_bwd(ptr(normal), ptr(base), ptr(rough), ptr(metal), ptr(wo_a), ptr(wo_b),
+                                                    ptr(dirs), ptr(rad_off), ptr(rad_emo), P, ctx.n_dirs,
+                                                    ptr(g_off_hat.contiguous()) if rad_off is not None else None,
+                                                    ptr(g_reflect.contiguous()), ptr(g_base), ptr(g_rough), ptr(g_metal),
+                                                    ptr(g_rad_off), ptr(g_rad_emo), stream_ptr()))
+        return g_base, g_rough, g_metal, g_rad_off, g_rad_emo, None, None, None, None, None

@@ -246,6 +246,26 @@ int esr_sdf_expgrad_bwd(const esr_scene_t *sc, const float *pts, int64_t m, cons
                         float *grad_sdf_grid, esr_stream_t stream);
 
 /*
+ * Light-transport accumulation (esrnerf.py:556-574, 654-677; pbr/functions.py:108-173): for each of n_pts LTS points
+ * (unit normal, base colour [3], roughness, metallic, two outgoing directions wo_a = -view / wo_b = -random view) and
+ * its n_dirs hemisphere directions `dirs` [n_pts*n_dirs,3] with the marched radiance of the secondary rays
+ * (rad_off = sum w*off + env * T_last, nullable; rad_emo = sum w*emo), the Monte-Carlo means
+ *   off_hat [2*n_pts,3] = mean_j rad_off_j * R(w_j, wo_v),  reflect [2*n_pts,3] = mean_j rad_emo_j * R(w_j, wo_v)
+ * (rows [0,n_pts): wo_a, rows [n_pts, 2 n_pts): wo_b) with the Disney-style reflectance R.  Backward: cotangents of the
+ * two outputs -> g_base [n_pts,3], g_rough / g_metal [n_pts], g_rad_off / g_rad_emo [n_pts*n_dirs,3]; normals and
+ * directions carry no gradient (esrnerf.py:790: detached normal; pbr/functions.py:9: no_grad sampling).
+ */
+int esr_lts_accumulate_fwd(const float *normal, const float *base, const float *rough, const float *metal,
+                           const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
+                           const float *rad_emo, int64_t n_pts, int n_dirs, float *off_hat, float *reflect,
+                           esr_stream_t stream);
+int esr_lts_accumulate_bwd(const float *normal, const float *base, const float *rough, const float *metal,
+                           const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
+                           const float *rad_emo, int64_t n_pts, int n_dirs, const float *g_off_hat,
+                           const float *g_reflect, float *g_base, float *g_rough, float *g_metal, float *g_rad_off,
+                           float *g_rad_emo, esr_stream_t stream);
+
+/*
  * Coarse-stage feature encode (voxurfc.py:205-249): trilinear tap of the dense central-difference gradient volume
  * `grad_vol` ([1,3,X,Y,Z], channels-first, voxurfc.py:597-616) -> normal = g / (|g| + 1e-5); 12-channel colour-grid
  * taps (channels-last); positional / view encodings.  Row (f32, row-major, 72 columns):

@@ -252,3 +252,51 @@ def test_esrnerf_full_size_properties():
         assert torch.isfinite(grads[0][k]).all(), k
         _, l2 = C.grad_err(grads[1][k], grads[0][k])
         assert l2 < 1e-3, (k, l2)                                            # atomics reorder sums; nothing is dropped or doubled
+
+
+@pytest.mark.parametrize("with_off", [True, False])
+def test_lts_accumulate_kernel_vs_torch_disney(with_off):
+    """esr_lts_accumulate_fwd/bwd against the torch restatement of pbr/functions.py:108-173 (esr_nerf_b200.pbr, itself
+    checked against the reference through the golden LTS outputs): values and every gradient at 1e-4 (fp32)."""
+    import torch.nn.functional as F
+
+    from esr_nerf_b200 import fused, pbr
+
+    g = torch.Generator().manual_seed(0)
+    P, n2 = 37, 19
+    normal = F.normalize(torch.randn(P, 3, generator=g), dim=-1).to(DEV)
+    dirs = pbr.diffuse_scattering(normal, torch.randn(P, n2, 3, generator=g).to(DEV))
+    wo_a, wo_b = (F.normalize(torch.randn(P, 3, generator=g), dim=-1).to(DEV) for _ in range(2))
+    leaves = [torch.rand(P, 3, generator=g), torch.rand(P, 1, generator=g) * 0.9 + 0.05, torch.rand(P, 1, generator=g),
+              torch.rand(P * n2, 3, generator=g) * 2, torch.rand(P * n2, 3, generator=g)]
+    leaves[1][0] = 1e-5                                               # roughness below the r^2 clamp
+    a = [t.to(DEV).requires_grad_(True) for t in leaves]
+    b = [t.to(DEV).requires_grad_(True) for t in leaves]
+
+    def ex(t, c):
+        return t.view(-1, 1, c).expand(P, n2, c).flatten(0, 1)
+
+    base, rough, metal, lo, le = a
+    d_flat = dirs.flatten(0, 1)
+    R = pbr.disney_reflection(ex(base, 3).repeat(2, 1), ex(rough, 1).repeat(2, 1), ex(metal, 1).repeat(2, 1),
+                              ex(normal, 3).repeat(2, 1), d_flat.repeat(2, 1), torch.cat([ex(wo_a, 3), ex(wo_b, 3)], 0))
+    ref_off = (lo.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
+    ref_emo = (le.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
+    base2, rough2, metal2, lo2, le2 = b
+    off_hat, reflect = fused.LtsAccumulate.apply(base2, rough2.reshape(-1), metal2.reshape(-1), lo2 if with_off else None, le2,
+                                                 normal, wo_a, wo_b, d_flat, n2)
+    c1, c2 = torch.randn(2 * P, 3, generator=g).to(DEV), torch.randn(2 * P, 3, generator=g).to(DEV)
+    assert C.rel_err(reflect, ref_emo) < 1e-5
+    loss_ref = (ref_emo * c2).sum()
+    loss = (reflect * c2).sum()
+    if with_off:
+        assert C.rel_err(off_hat, ref_off) < 1e-5
+        loss_ref = loss_ref + (ref_off * c1).sum()
+        loss = loss + (off_hat * c1).sum()
+    loss_ref.backward()
+    loss.backward()
+    for i, (x, y) in enumerate(zip(a, b)):
+        if i == 3 and not with_off:
+            assert y.grad is None
+            continue
+        assert C.rel_err(y.grad, x.grad) < 1e-4, i
