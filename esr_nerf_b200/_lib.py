@@ -17,7 +17,7 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
-SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu", "optim.cu"]
+SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu", "optim.cu", "grad_exchange.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -132,6 +132,8 @@ PROTOTYPES = {
     "esr_exclusive_scan_i32": (I32, [P, P, I64, P, P]),
     "esr_march_count": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P]),
     "esr_march_fill": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P]),
+    "esr_march_count_bits": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, I32, P]),
+    "esr_march_fill_bits": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, I32, P]),
     "esr_alpha_scan_count": (I32, [SCENE_P, P, I64, P, P, P, P, P]),
     "esr_alpha_scan_fill": (I32, [SCENE_P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]),
     "esr_alpha_scan_bwd": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, I64, P, P]),
@@ -158,6 +160,9 @@ PROTOTYPES = {
     "esr_tonemap_mlp_fwd": (I32, [DESC_P, P, P, I64, P, P]),
     "esr_tonemap_mlp_bwd": (I32, [DESC_P, P, P, P, P, P, I64, P, P, P]),
     "esr_adam_step": (I32, [P, P, P, P, P, I64, F32, F32, F32, F32, F32, I64, P]),
+    "esr_grad_pack_floats": (I64, [P, I32, I64]),
+    "esr_grad_pack": (I32, [P, P, I32, P, I64, P, P]),
+    "esr_grad_unpack": (I32, [P, P, I32, P, I64, P, P]),
     "esr_mlp_param_count": (I64, [DESC_P]),
     "esr_mlp_image_bytes": (I64, [DESC_P]),
     "esr_mlp_act_rows": (I64, [I64]),

@@ -16,6 +16,9 @@ static inline unsigned ray_blocks(int64_t n_rays) {
 // ---------------------------------------------------------------------------------------------
 // Stage A/B: march
 // ---------------------------------------------------------------------------------------------
+// keep_bits (nullable): [n_rays][bits_stride] uint32, one ballot word per 32 candidate steps of a ray slot.  The count
+// pass writes it, the fill pass reads it instead of repeating the AABB test and the 8-tap MaskCache lookup of every
+// candidate (chunks beyond bits_stride, if any, are recomputed).
 template <bool FILL>
 __global__ void __launch_bounds__(256)
     k_march(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
@@ -23,7 +26,7 @@ __global__ void __launch_bounds__(256)
             const float *__restrict__ mask_density, const float *__restrict__ sdf_grid,
             int32_t *__restrict__ n_steps, int32_t *__restrict__ cnt_inbox, int32_t *__restrict__ cnt_mask,
             const int32_t *__restrict__ off_mask, int32_t *__restrict__ s_ray, int32_t *__restrict__ s_step,
-            float *__restrict__ s_sdf) {
+            float *__restrict__ s_sdf, uint32_t *__restrict__ keep_bits, int bits_stride) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned lane = lane_id();
@@ -32,25 +35,32 @@ __global__ void __launch_bounds__(256)
     const int r = ray_order ? ray_order[slot] : (int)slot;
     const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
     const int base = FILL ? off_mask[slot] : 0;
+    uint32_t *bits = keep_bits ? keep_bits + slot * (int64_t)bits_stride : nullptr;
     int c_in = 0, c_mask = 0;
     for (int k0 = 0; k0 < s.n; k0 += 32) {
       const int k = k0 + (int)lane;
+      const int chunk = k0 >> 5;
       float px, py, pz;
       ray_point(s, sc.stepdist, k, px, py, pz);
-      const bool inb = (k < s.n) && !out_bbox(sc.xyz_min, sc.xyz_max, px, py, pz);
-      const bool keep = inb && mask_keep(sc, mask_density, px, py, pz);
-      const unsigned bal = __ballot_sync(FULL, keep);
-      if (FILL) {
-        if (keep) {
-          const int pos = base + c_mask + __popc(bal & lt);
-          s_ray[pos] = r;
-          s_step[pos] = k;
-          s_sdf[pos] = sc.sdf_tap_manual
-                           ? tap1_manual_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz)
-                           : tap1_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz);
-        }
+      unsigned bal;
+      if (FILL && bits && chunk < bits_stride) {
+        bal = bits[chunk];                              // warp-uniform load
       } else {
-        c_in += __popc(__ballot_sync(FULL, inb));
+        const bool inb = (k < s.n) && !out_bbox(sc.xyz_min, sc.xyz_max, px, py, pz);
+        const bool keep = inb && mask_keep(sc, mask_density, px, py, pz);
+        bal = __ballot_sync(FULL, keep);
+        if (!FILL) {
+          c_in += __popc(__ballot_sync(FULL, inb));
+          if (bits && chunk < bits_stride && lane == 0) bits[chunk] = bal;
+        }
+      }
+      if (FILL && ((bal >> lane) & 1u)) {
+        const int pos = base + c_mask + __popc(bal & lt);
+        s_ray[pos] = r;
+        s_step[pos] = k;
+        s_sdf[pos] = sc.sdf_tap_manual
+                         ? tap1_manual_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz)
+                         : tap1_world(sdf_grid, sc.gx, sc.gy, sc.gz, sc.xyz_min, sc.xyz_max, px, py, pz);
       }
       c_mask += __popc(bal);
     }
@@ -69,9 +79,9 @@ static int check_scene(const esr_scene_t *sc) {
   return ESR_OK;
 }
 
-extern "C" int esr_march_count(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
-                               const int32_t *ray_order, int64_t n_rays, const float *mask_density, int32_t *n_steps,
-                               int32_t *cnt_inbox, int32_t *cnt_mask, esr_stream_t stream) {
+static int march_count_impl(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                            int64_t n_rays, const float *mask_density, int32_t *n_steps, int32_t *cnt_inbox,
+                            int32_t *cnt_mask, uint32_t *keep_bits, int bits_stride, esr_stream_t stream) {
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
@@ -79,15 +89,32 @@ extern "C" int esr_march_count(const esr_scene_t *sc, const float *rays_o, const
   ESR_STAGE("k_march_count", (cudaStream_t)stream);
   k_march<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
                                                                        mask_density, nullptr, n_steps, cnt_inbox,
-                                                                       cnt_mask, nullptr, nullptr, nullptr, nullptr);
+                                                                       cnt_mask, nullptr, nullptr, nullptr, nullptr,
+                                                                       keep_bits, bits_stride);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
 
-extern "C" int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
-                              const int32_t *ray_order, int64_t n_rays, const float *mask_density,
-                              const float *sdf_grid, const int32_t *off_mask, int32_t *s_ray, int32_t *s_step,
-                              float *s_sdf, esr_stream_t stream) {
+extern "C" int esr_march_count(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                               const int32_t *ray_order, int64_t n_rays, const float *mask_density, int32_t *n_steps,
+                               int32_t *cnt_inbox, int32_t *cnt_mask, esr_stream_t stream) {
+  return march_count_impl(sc, rays_o, rays_d, ray_order, n_rays, mask_density, n_steps, cnt_inbox, cnt_mask, nullptr, 0,
+                          stream);
+}
+
+extern "C" int esr_march_count_bits(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                    const int32_t *ray_order, int64_t n_rays, const float *mask_density,
+                                    int32_t *n_steps, int32_t *cnt_inbox, int32_t *cnt_mask, uint32_t *keep_bits,
+                                    int bits_stride, esr_stream_t stream) {
+  ESR_CHECK_ARG(!keep_bits || bits_stride > 0);
+  return march_count_impl(sc, rays_o, rays_d, ray_order, n_rays, mask_density, n_steps, cnt_inbox, cnt_mask, keep_bits,
+                          bits_stride, stream);
+}
+
+static int march_fill_impl(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                           int64_t n_rays, const float *mask_density, const float *sdf_grid, const int32_t *off_mask,
+                           int32_t *s_ray, int32_t *s_step, float *s_sdf, const uint32_t *keep_bits, int bits_stride,
+                           esr_stream_t stream) {
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
@@ -96,9 +123,27 @@ extern "C" int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const 
   ESR_STAGE("k_march_fill", (cudaStream_t)stream);
   k_march<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
                                                                       mask_density, sdf_grid, nullptr, nullptr,
-                                                                      nullptr, off_mask, s_ray, s_step, s_sdf);
+                                                                      nullptr, off_mask, s_ray, s_step, s_sdf,
+                                                                      const_cast<uint32_t *>(keep_bits), bits_stride);
   ESR_LAUNCH_OK();
   return ESR_OK;
+}
+
+extern "C" int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                              const int32_t *ray_order, int64_t n_rays, const float *mask_density,
+                              const float *sdf_grid, const int32_t *off_mask, int32_t *s_ray, int32_t *s_step,
+                              float *s_sdf, esr_stream_t stream) {
+  return march_fill_impl(sc, rays_o, rays_d, ray_order, n_rays, mask_density, sdf_grid, off_mask, s_ray, s_step, s_sdf,
+                         nullptr, 0, stream);
+}
+
+extern "C" int esr_march_fill_bits(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                   const int32_t *ray_order, int64_t n_rays, const float *mask_density,
+                                   const float *sdf_grid, const int32_t *off_mask, int32_t *s_ray, int32_t *s_step,
+                                   float *s_sdf, const uint32_t *keep_bits, int bits_stride, esr_stream_t stream) {
+  ESR_CHECK_ARG(!keep_bits || bits_stride > 0);
+  return march_fill_impl(sc, rays_o, rays_d, ray_order, n_rays, mask_density, sdf_grid, off_mask, s_ray, s_step, s_sdf,
+                         keep_bits, bits_stride, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -72,6 +72,7 @@ class GridGradCompactor:
         self.idx = torch.nonzero(self.mask.reshape(-1)).reshape(-1)
         self.shape = tuple(model.sdf.grid.shape[2:])
         self.grids = [model.sdf.grid, model.off_color.grid, model.emo_color.grid]
+        self._idx32 = None
 
     @property
     def fraction(self) -> float:
@@ -88,23 +89,67 @@ class GridGradCompactor:
         outside = ~self.mask.reshape(-1)
         return all(not bool((self._rows(p.grad)[outside] != 0).any()) for p in self.grids if p.grad is not None)
 
-    def allreduce(self, group=None, verify: bool = False) -> int:
-        import torch.distributed as dist
-
+    def _grids_rows(self):
         rows = []
         for p in self.grids:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
             rows.append(self._rows(p.grad))
+        return rows
+
+    def pack(self, rows) -> torch.Tensor:
+        """dense gradient volumes -> one packed buffer (CUDA: one launch of esr_grad_pack, planar blocks [K][C_j];
+        host tensors of the gloo tests: the same layout with torch indexing)"""
+        chans = [r.shape[1] for r in rows]
+        k = self.idx.numel()
+        if rows[0].is_cuda:
+            import ctypes
+
+            from ._lib import check, lib, ptr, stream_ptr
+
+            L = lib()
+            if self._idx32 is None:
+                assert self.mask.numel() < (1 << 31)
+                self._idx32 = self.idx.to(torch.int32)
+            c_arr = (ctypes.c_int32 * len(rows))(*chans)
+            v_arr = (ctypes.c_void_p * len(rows))(*[r.data_ptr() for r in rows])
+            n = int(L.esr_grad_pack_floats(c_arr, len(rows), k))
+            buf = torch.empty(n, dtype=torch.float32, device=rows[0].device)
+            check(L.esr_grad_pack(v_arr, c_arr, len(rows), ptr(self._idx32), k, ptr(buf), stream_ptr()))
+            return buf
+        blocks = []
+        for r in rows:
+            b = r[self.idx].reshape(-1)
+            blocks.append(b if b.numel() % 2 == 0 else torch.cat([b, b.new_zeros(1)]))
+        return torch.cat(blocks)
+
+    def unpack(self, rows, buf: torch.Tensor) -> None:
+        k = self.idx.numel()
+        if rows[0].is_cuda:
+            import ctypes
+
+            from ._lib import check, lib, ptr, stream_ptr
+
+            c_arr = (ctypes.c_int32 * len(rows))(*[r.shape[1] for r in rows])
+            v_arr = (ctypes.c_void_p * len(rows))(*[r.data_ptr() for r in rows])
+            check(lib().esr_grad_unpack(v_arr, c_arr, len(rows), ptr(self._idx32), k, ptr(buf), stream_ptr()))
+            return
+        off = 0
+        for r in rows:
+            n = k * r.shape[1]
+            r.index_copy_(0, self.idx, buf[off:off + n].view(k, r.shape[1]))
+            off += n + (n & 1)
+
+    def allreduce(self, group=None, verify: bool = False) -> int:
+        import torch.distributed as dist
+
+        rows = self._grids_rows()
         if verify:
             assert self.outside_is_zero(), "gradient outside the dilated occupancy set"
-        buf = torch.cat([r[self.idx] for r in rows], dim=1)
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-        c0 = 0
-        for r in rows:
-            r.index_copy_(0, self.idx, buf[:, c0:c0 + r.shape[1]])
-            c0 += r.shape[1]
-        nbytes = buf.numel() * buf.element_size()
         grid_ids = {id(p) for p in self.grids}
         others = [p for p in self.model.parameters() if id(p) not in grid_ids]
-        return nbytes + allreduce_gradients(others, group)
+        nbytes = allreduce_gradients(others, group)      # the small MLP bucket first: it is ready and tiny
+        buf = self.pack(rows)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        self.unpack(rows, buf)
+        return nbytes + buf.numel() * buf.element_size()

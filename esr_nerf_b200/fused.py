@@ -173,13 +173,18 @@ def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid) -> Strea
     n_steps, cnt_in, cnt_mask = _i32(n, dev), _i32(n, dev), _i32(n, dev)
     st = stream_ptr()
     scp = ctypes.byref(sc)
-    check(L.esr_march_count(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(n_steps),
-                            ptr(cnt_in), ptr(cnt_mask), st))
+    # keep-bit cache: one ballot word per 32 candidate steps, written by the count pass, read by the fill pass.
+    # A ray's chord is at most the AABB diagonal: ceil(diag / stepdist) + 1 candidate steps.
+    diag = sum((sc.xyz_max[i] - sc.xyz_min[i]) ** 2 for i in range(3)) ** 0.5
+    stride = int(diag / sc.stepdist) // 32 + 2
+    bits = _i32(n * stride, dev)
+    check(L.esr_march_count_bits(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(n_steps),
+                                 ptr(cnt_in), ptr(cnt_mask), ptr(bits), stride, st))
     off_mask = exclusive_scan(cnt_mask)
     m1 = int(off_mask[n].item())
     s_ray, s_step, s_sdf = _i32(m1, dev), _i32(m1, dev), _f32(m1, dev=dev)
-    check(L.esr_march_fill(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(sdf_grid),
-                           ptr(off_mask), ptr(s_ray), ptr(s_step), ptr(s_sdf), st))
+    check(L.esr_march_fill_bits(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(sdf_grid),
+                                ptr(off_mask), ptr(s_ray), ptr(s_step), ptr(s_sdf), ptr(bits), stride, st))
     return Streams(n, ray_order, n_steps, cnt_in, off_mask, m1, s_ray, s_step, s_sdf)
 
 

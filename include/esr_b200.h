@@ -143,6 +143,19 @@ int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const float *rays
                    float *s_sdf, esr_stream_t stream);
 
 /*
+ * Same two calls with a keep-bit cache: the count pass stores one ballot word per 32 candidate steps of each ray slot
+ * (keep_bits [n_rays][bits_stride] uint32, bits_stride >= ceil(max steps per ray / 32)), the fill pass reads the words
+ * instead of repeating the AABB test and the 8-tap MaskCache lookup of every candidate.  Results are identical.
+ */
+int esr_march_count_bits(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                         int64_t n_rays, const float *mask_density, int32_t *n_steps, int32_t *cnt_inbox,
+                         int32_t *cnt_mask, uint32_t *keep_bits, int bits_stride, esr_stream_t stream);
+int esr_march_fill_bits(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                        int64_t n_rays, const float *mask_density, const float *sdf_grid, const int32_t *off_mask,
+                        int32_t *s_ray, int32_t *s_step, float *s_sdf, const uint32_t *keep_bits, int bits_stride,
+                        esr_stream_t stream);
+
+/*
  * Stage C/D — NeuS 'interp' alpha (functions.py:72-105), alpha>thr filter (voxurff.py:201),
  * transmittance scan with the reference's sequential float/double recurrence and early stop
  * (kernel.cu:591-603), weight>thr filter (voxurff.py:209).  Warp per ray slot over its M1 segment.
@@ -396,6 +409,22 @@ int esr_tonemap_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const float 
 int esr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, const float *per_lr, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                   esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient exchange: pack / unpack either side of the one collective on the path, the gradient
+ * all-reduce of the ray-sharded step.  The reference has no distributed code (cfg/__init__.yaml:24); what is replaced
+ * is a dense all-reduce of every grid gradient (0.83-1.2 GB at 256^3).  `volumes[j]` is a dense gradient volume in its
+ * parameter's memory layout [V][channels[j]] (f32, channels innermost, 8-byte aligned), `idx[k]` (int32, sorted) the
+ * voxels that can carry gradient.  The packed buffer holds one [k][channels[j]] block per volume, each block starting
+ * on an even float offset; esr_grad_pack_floats returns its length in floats (-1 on bad arguments).  Pack copies
+ * volume -> buffer, unpack copies buffer -> volume (voxels outside idx are not touched).
+ * ---------------------------------------------------------------------------------------- */
+#define ESR_MAX_GRAD_VOLUMES 4
+int64_t esr_grad_pack_floats(const int32_t *channels, int n_volumes, int64_t k);
+int esr_grad_pack(void *const *volumes, const int32_t *channels, int n_volumes, const int32_t *idx, int64_t k,
+                  float *buf, esr_stream_t stream);
+int esr_grad_unpack(void *const *volumes, const int32_t *channels, int n_volumes, const int32_t *idx, int64_t k,
+                    const float *buf, esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 3. Alphamask stage (DVGO, app/coarse/model/dvgo.py:140-288): dense [N x S] sampling, density / colour grids only

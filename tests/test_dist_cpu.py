@@ -71,3 +71,65 @@ def test_two_rank_gradient_allreduce_matches_single_process():
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=5) < 1e-6
+
+
+class _TinyGrids(torch.nn.Module):
+    """the attributes GridGradCompactor reads from a VoxurfF: three grids in the parameters' memory layout + the mask"""
+
+    def __init__(self, r=9):
+        super().__init__()
+        mk = lambda c: torch.nn.Parameter(torch.zeros(1, c, r, r, r).contiguous(
+            memory_format=torch.channels_last_3d if c > 1 else torch.contiguous_format))
+        self.sdf, self.off_color, self.emo_color = (torch.nn.Module() for _ in range(3))
+        self.sdf.grid, self.off_color.grid, self.emo_color.grid = mk(1), mk(6), mk(6)
+        self.head = torch.nn.Linear(4, 2)
+        m = torch.zeros(1, 1, r, r, r, dtype=torch.bool)
+        m[..., 3:6, 3:6, 4] = True
+        self.nonempty_mask = m
+
+
+def _compactor_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from esr_nerf_b200.dist import GridGradCompactor
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = _TinyGrids()
+    comp = GridGradCompactor(model, dilate=1)
+    assert comp.idx.numel() % 2 == 1                          # odd voxel count: the sdf block is padded to 8 bytes
+    g = torch.Generator().manual_seed(10 + rank)
+    grads = []
+    for p in model.parameters():
+        v = torch.randn(p.shape, generator=g)
+        if p.dim() == 5:                                      # grid gradients live inside the dilated set only
+            v = (v * comp.mask).contiguous(memory_format=torch.channels_last_3d if p.shape[1] > 1
+                                           else torch.contiguous_format)
+        p.grad = v.clone()
+        grads.append(v)
+    nbytes = comp.allreduce(verify=True)
+    assert nbytes == 4 * (sum(p.numel() for p in model.head.parameters()) + 2 * ((comp.idx.numel() * 13 + 2) // 2))
+    g2 = torch.Generator().manual_seed(10 + (1 - rank))
+    err = 0.0
+    for p, mine in zip(model.parameters(), grads):
+        other = torch.randn(p.shape, generator=g2)
+        if p.dim() == 5:
+            other = other * comp.mask
+        err = max(err, (p.grad - (mine + other)).abs().max().item())
+    out.put(err)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_compacted_grid_allreduce_equals_dense_sum():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_compactor_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert max(out.get(timeout=5), out.get(timeout=5)) == 0.0

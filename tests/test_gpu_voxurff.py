@@ -281,20 +281,28 @@ def test_grid_gradient_compaction_is_exact():
     if not dist.is_initialized():
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
     try:
-        # gloo has no CUDA all_reduce for every build: run the collective on a CPU copy of the compacted buffer
-        rows = [comp._rows(p.grad) for p in comp.grids]
+        # gloo has no CUDA all_reduce for every build: run the collective on a CPU copy of the packed buffer
+        rows = comp._grids_rows()
         assert comp.outside_is_zero()                                         # nothing outside the set
-        buf = torch.cat([r[comp.idx] for r in rows], 1).cpu()
-        dist.all_reduce(buf)
-        buf = buf.to(DEV)
-        c0 = 0
-        for r in rows:
-            r.index_copy_(0, comp.idx, buf[:, c0:c0 + r.shape[1]])
-            c0 += r.shape[1]
+        buf = comp.pack(rows)                                                 # esr_grad_pack: planar [K][C_j] blocks
+        k, off = comp.idx.numel(), 0
+        for r in rows:                                                        # layout == torch indexing, bit for bit
+            n = k * r.shape[1]
+            assert torch.equal(buf[off:off + n].view(k, -1), r[comp.idx])
+            off += n + (n & 1)
+        assert off == buf.numel()
+        host = buf.cpu()
+        dist.all_reduce(host)
+        for p in comp.grids:
+            p.grad.add_(1.0)                                                  # unpack must overwrite exactly the set
+        comp.unpack(rows, host.to(DEV))
     finally:
         dist.destroy_process_group()
+    inside = comp.mask.reshape(-1)
     for p, b in zip(comp.grids, before):
-        assert torch.equal(p.grad, b)
+        got, ref = comp._rows(p.grad), comp._rows(b)
+        assert torch.equal(got[inside], ref[inside])                          # the set: restored from the buffer
+        assert torch.equal(got[~inside], ref[~inside] + 1.0)                  # everything else: not touched
 
 
 def test_filter_training_rays_packed_branch_vs_oracle():
