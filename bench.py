@@ -195,6 +195,15 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def wait_ready(self, timeout=8.0):
+        """block until nvidia-smi has printed its first sample: its start-up (NVML attach, ~1 s) must not land inside
+        the timed region, where it stalls the device for tens of milliseconds"""
+        t0 = time.time()
+        while self.p is not None and self.p.poll() is None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.05)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
@@ -247,8 +256,9 @@ def algorithmic_work(stage, c):
     t = {
         "k_march_count": ("hbm", 24 * N + 32 * M0 + 12 * N),
         "k_march_fill": ("hbm", 24 * N + 32 * M0 + 32 * M1 + 12 * M1),
-        "k_alpha_scan_count": ("hbm", 4 * M1 + 8 * N),
-        "k_alpha_scan_fill": ("hbm", 8 * M1 + 8 * M1 + 20 * M3),
+        "k_neus_alpha": ("hbm", 4 * M1 + 8 * M1),                # read sdf, write alpha + T preset
+        "k_transmittance": ("hbm", 4 * M1 + 4 * M1 + 16 * N),     # read alpha, write T; per-ray offsets / count / last
+        "k_shade_compact": ("hbm", 8 * M1 + 8 * M3 + 20 * M3),    # read alpha + T (+ step, sdf of survivors), write M3 stream
         "k_encode_fwd": ("hbm", 8 * M3 + taps_fwd + 192 * M3),
         "k_encode_bwd": ("hbm", 8 * M3 + 2 * taps_fwd + 224 * M3),
         "k_alpha_scan_bwd": ("hbm", 16 * M1 + 8 * M1),
@@ -387,6 +397,8 @@ def run_b200(a, rank, world, local_rank):
     for _ in range(max(a.warmup, 5)):
         step(batch)
     sync_all()
+    if sampler:
+        sampler.wait_ready()
     st = model.last_streams["streams"]
     counts = {"N": st.n_rays, "Mraw": int(st.n_steps.sum()), "M0": int(st.cnt_inbox.sum()), "M1": st.m1, "M3": st.m3,
               "M3_on": st.m3_on}

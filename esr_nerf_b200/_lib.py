@@ -134,7 +134,7 @@ PROTOTYPES = {
     "esr_march_fill": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P]),
     "esr_march_count_bits": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, I32, P]),
     "esr_march_fill_bits": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, I32, P]),
-    "esr_alpha_scan_count": (I32, [SCENE_P, P, I64, P, P, P, P, P]),
+    "esr_alpha_scan_count": (I32, [SCENE_P, P, I64, P, P, P, P, P, P, P]),
     "esr_alpha_scan_fill": (I32, [SCENE_P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]),
     "esr_alpha_scan_bwd": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, I64, P, P]),
     "esr_neus_alpha_bwd": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, I64, P, P]),

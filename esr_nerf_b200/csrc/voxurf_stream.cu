@@ -148,15 +148,65 @@ extern "C" int esr_march_fill_bits(const esr_scene_t *sc, const float *rays_o, c
 
 // ---------------------------------------------------------------------------------------------
 // Stage C/D: NeuS alpha -> alpha filter -> exact sequential transmittance -> weight filter
+//
+// Three kernels, each in the shape its work has:
+//   k_neus_alpha     warp per ray slot, lanes over its M1 segment (coalesced): alpha of every sample, T preset to -1
+//   k_transmittance  THREAD per ray slot: the reference's sequential float/double recurrence with early stop
+//                    (kernel.cu:591-603) is a dependent chain per ray; a warp now advances 32 different rays' chains
+//                    at once instead of replaying one chain on 32 lanes (32x fewer FP64 / conversion instructions —
+//                    the MIO-throttled part of the previous warp-per-ray version).  A lane walks consecutive
+//                    addresses, so each 128-byte line it touches serves its next 32 samples out of L1.
+//   k_shade_compact  warp per ray slot: weights, weight filter, ballot/popc compaction into the M3 stream (coalesced)
 // ---------------------------------------------------------------------------------------------
-template <bool FILL>
 __global__ void __launch_bounds__(256)
-    k_alpha_scan(const __grid_constant__ esr_scene_t sc, const int32_t *__restrict__ ray_order, int64_t n_rays,
-                 const int32_t *__restrict__ off_mask, const int32_t *__restrict__ s_step,
-                 const float *__restrict__ s_sdf, const int32_t *__restrict__ off_shade,
-                 int32_t *__restrict__ cnt_shade, float *__restrict__ alphainv_last, float *__restrict__ s_alpha,
-                 float *__restrict__ s_T, int32_t *__restrict__ h_ray, int32_t *__restrict__ h_step,
-                 int32_t *__restrict__ h_m1, float *__restrict__ h_w, float *__restrict__ h_sdf) {
+    k_neus_alpha(const __grid_constant__ esr_scene_t sc, int64_t n_rays, const int32_t *__restrict__ off_mask,
+                 const float *__restrict__ s_sdf, float *__restrict__ s_alpha, float *__restrict__ s_T) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = lane_id();
+  for (int64_t slot = warp; slot < n_rays; slot += nwarps) {
+    const int s = off_mask[slot], e = off_mask[slot + 1];
+    for (int i = s + (int)lane; i < e; i += 32) {
+      const float sd = __ldg(s_sdf + i);
+      const bool has_prev = i > s, has_next = i + 1 < e;
+      const float sp = has_prev ? __ldg(s_sdf + i - 1) : 0.f;
+      const float sn = has_next ? __ldg(s_sdf + i + 1) : 0.f;
+      float pc, nc;
+      s_alpha[i] = neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+      s_T[i] = -1.f;   // "not part of the scan" until k_transmittance visits the sample
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    k_transmittance(const __grid_constant__ esr_scene_t sc, const int32_t *__restrict__ ray_order, int64_t n_rays,
+                    const int32_t *__restrict__ off_mask, const float *__restrict__ s_alpha, float *__restrict__ s_T,
+                    int32_t *__restrict__ cnt_shade, float *__restrict__ alphainv_last) {
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_rays) return;
+  const int r = ray_order ? ray_order[slot] : (int)slot;
+  const int s = off_mask[slot], e = off_mask[slot + 1];
+  float Tc = 1.f;
+  int n_shade = 0;
+  for (int i = s; i < e; ++i) {
+    const float a = s_alpha[i];
+    if (!(a > sc.alpha_thres)) continue;            // voxurff.py:201 (coarse stage: alpha_thres = -1, no filter)
+    s_T[i] = Tc;                                    // kernel.cu:591-601 in order over the surviving samples
+    n_shade += (__fmul_rn(Tc, a) > sc.fast_thres) ? 1 : 0;   // voxurff.py:209
+    Tc = (float)((1. - (double)a) * (double)Tc);
+    if ((double)Tc < 1e-3) break;
+  }
+  cnt_shade[slot] = n_shade;
+  alphainv_last[r] = Tc;
+}
+
+__global__ void __launch_bounds__(256)
+    k_shade_compact(const __grid_constant__ esr_scene_t sc, const int32_t *__restrict__ ray_order, int64_t n_rays,
+                    const int32_t *__restrict__ off_mask, const int32_t *__restrict__ s_step,
+                    const float *__restrict__ s_sdf, const int32_t *__restrict__ off_shade,
+                    const float *__restrict__ s_alpha, const float *__restrict__ s_T, int32_t *__restrict__ h_ray,
+                    int32_t *__restrict__ h_step, int32_t *__restrict__ h_m1, float *__restrict__ h_w,
+                    float *__restrict__ h_sdf) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned lane = lane_id();
@@ -164,90 +214,61 @@ __global__ void __launch_bounds__(256)
   for (int64_t slot = warp; slot < n_rays; slot += nwarps) {
     const int r = ray_order ? ray_order[slot] : (int)slot;
     const int s = off_mask[slot], e = off_mask[slot + 1];
-    const int out_base = FILL ? off_shade[slot] : 0;
-    float Tc = 1.f;
-    bool done = false;
-    int n_shade = 0;
-    for (int base = s; base < e; base += 32) {
+    int pos0 = off_shade[slot];
+    const int pos_end = off_shade[slot + 1];
+    for (int base = s; base < e && pos0 < pos_end; base += 32) {
       const int i = base + (int)lane;
-      const bool valid = i < e;
-      float a = 0.f, sd = 0.f;
-      if (valid) {
-        sd = __ldg(s_sdf + i);
-        const bool has_prev = i > s, has_next = i + 1 < e;
-        const float sp = has_prev ? __ldg(s_sdf + i - 1) : 0.f;
-        const float sn = has_next ? __ldg(s_sdf + i + 1) : 0.f;
-        float pc, nc;
-        a = neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+      float T = -1.f, w = 0.f;
+      if (i < e) {
+        T = __ldg(s_T + i);
+        if (T >= 0.f) w = __fmul_rn(T, __ldg(s_alpha + i));
       }
-      const bool f0 = valid && (a > sc.alpha_thres);  // voxurff.py:201 (coarse stage: no alpha filter)
-      float myT = -1.f, myW = 0.f;
-      unsigned m = __ballot_sync(FULL, f0);
-      // kernel.cu:591-601 replayed in order over the surviving samples (uniform across the warp)
-      while (m && !done) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const float aj = __shfl_sync(FULL, a, j);
-        if ((int)lane == j) {
-          myT = Tc;
-          myW = __fmul_rn(Tc, aj);
-        }
-        Tc = (float)((1. - (double)aj) * (double)Tc);
-        if ((double)Tc < 1e-3) done = true;
-      }
-      const bool f1 = (myT >= 0.f) && (myW > sc.fast_thres);  // voxurff.py:209
+      const bool f1 = (T >= 0.f) && (w > sc.fast_thres);
       const unsigned b1 = __ballot_sync(FULL, f1);
-      if (FILL) {
-        if (valid) {
-          s_alpha[i] = a;
-          s_T[i] = myT;
-        }
-        if (f1) {
-          const int pos = out_base + n_shade + __popc(b1 & lt);
-          h_ray[pos] = r;
-          h_step[pos] = __ldg(s_step + i);
-          h_m1[pos] = i;
-          h_w[pos] = myW;
-          h_sdf[pos] = sd;
-        }
+      if (f1) {
+        const int pos = pos0 + __popc(b1 & lt);
+        h_ray[pos] = r;
+        h_step[pos] = __ldg(s_step + i);
+        h_m1[pos] = i;
+        h_w[pos] = w;
+        h_sdf[pos] = __ldg(s_sdf + i);
       }
-      n_shade += __popc(b1);
-    }
-    if (!FILL && lane == 0) {
-      cnt_shade[slot] = n_shade;
-      alphainv_last[r] = Tc;
+      pos0 += __popc(b1);
     }
   }
 }
 
 extern "C" int esr_alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
                                     const int32_t *off_mask, const float *s_sdf, int32_t *cnt_shade,
-                                    float *alphainv_last, esr_stream_t stream) {
+                                    float *alphainv_last, float *s_alpha, float *s_T, esr_stream_t stream) {
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
+  // s_sdf / s_alpha / s_T may be NULL only when the M1 stream is empty
   ESR_CHECK_ARG(off_mask && cnt_shade && alphainv_last);
-  ESR_STAGE("k_alpha_scan_count", (cudaStream_t)stream);
-  k_alpha_scan<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(
-      *sc, ray_order, n_rays, off_mask, nullptr, s_sdf, nullptr, cnt_shade, alphainv_last, nullptr, nullptr, nullptr,
-      nullptr, nullptr, nullptr, nullptr);
+  ESR_STAGE("k_neus_alpha", (cudaStream_t)stream);
+  k_neus_alpha<<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, n_rays, off_mask, s_sdf, s_alpha, s_T);
+  ESR_LAUNCH_OK();
+  ESR_STAGE("k_transmittance", (cudaStream_t)stream);
+  k_transmittance<<<cdiv(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(*sc, ray_order, n_rays, off_mask, s_alpha, s_T,
+                                                                      cnt_shade, alphainv_last);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
 
 extern "C" int esr_alpha_scan_fill(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
                                    const int32_t *off_mask, const int32_t *s_step, const float *s_sdf,
-                                   const int32_t *off_shade, float *s_alpha, float *s_T, int32_t *h_ray,
+                                   const int32_t *off_shade, const float *s_alpha, const float *s_T, int32_t *h_ray,
                                    int32_t *h_step, int32_t *h_m1, float *h_w, float *h_sdf, esr_stream_t stream) {
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
   // stream pointers may be NULL when the corresponding stream is empty (M1 == 0 / M3 == 0)
   ESR_CHECK_ARG(off_mask && off_shade);
-  ESR_STAGE("k_alpha_scan_fill", (cudaStream_t)stream);
-  k_alpha_scan<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(
-      *sc, ray_order, n_rays, off_mask, s_step, s_sdf, off_shade, nullptr, nullptr, s_alpha, s_T, h_ray, h_step, h_m1,
-      h_w, h_sdf);
+  ESR_STAGE("k_shade_compact", (cudaStream_t)stream);
+  k_shade_compact<<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, ray_order, n_rays, off_mask, s_step, s_sdf,
+                                                                       off_shade, s_alpha, s_T, h_ray, h_step, h_m1,
+                                                                       h_w, h_sdf);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

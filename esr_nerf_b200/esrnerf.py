@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 
 from . import fused, pbr
-from .modules import (BRDFNet, DenseGrid, EmissionNet, SphericalGaussian, cfg_get, flat_mlp_params_padded)
+from .modules import (BRDFNet, DenseGrid, EmissionNet, SphericalGaussian, cfg_get, flat_mlp_params_padded, host_geometry)
 from .voxurff import VoxurfF
 
 
@@ -91,9 +91,9 @@ class ESRNeRF(VoxurfF):
     def _pbr_scene(self, near: float, manual: bool):
         g = self.sdf.grid.shape
         md = self.mask_cache.density.shape
-        return fused.make_scene(self.xyz_min.tolist(), self.xyz_max.tolist(), g[2:], self.mask_xyz_min.tolist(),
-                                self.mask_xyz_max.tolist(), md[2:], near, 1e9, float(self.stepsize * self.voxel_size),
-                                float(self.voxel_size), self.mask_cache.act_shift, self.maskcache_thres,
+        h = host_geometry(self, self.stepsize)
+        return fused.make_scene(h["xyz_min"], h["xyz_max"], g[2:], h["mask_xyz_min"], h["mask_xyz_max"], md[2:], near,
+                                1e9, h["stepdist"], h["voxel_size"], self.mask_cache.act_shift, self.maskcache_thres,
                                 self.fastcolor_thres, float(self.s_val), fd_eps=1e-12, sdf_tap_manual=manual)
 
     def _flats(self):
@@ -385,7 +385,7 @@ class ESRNeRF(VoxurfF):
             grad = fused.sdf_fd_gradient(sc, rays_o, rays_d, self.sdf.grid.detach(), s)
             normal = (F.normalize(grad, dim=-1) @ pos_rt * self.normal_flipper.to(dev) + 1.0) / 2.0
             aux = torch.zeros(m3, 3, device=dev)          # (step * dist, roughness, metallic) share one composite
-            aux[:, 0] = s.h_step.float() * float(self.stepsize * self.voxel_size)
+            aux[:, 0] = s.h_step.float() * host_geometry(self, self.stepsize)["stepdist"]
             aux[:, 1:] = brdf[:, 3:5]
             base = brdf[:, :3].contiguous()
             off_m, lin_off_m = fused.composite_infer(h_w, off_rgb, lin_off, s)

@@ -161,15 +161,17 @@ def march_count(sc: Scene, rays_o, rays_d, mask_density):
     return n_steps, cnt_in, cnt_mask
 
 
-def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid) -> Streams:
+def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_read=None):
     """Stages A/B.  One host read (M1) sizes the stream buffers — the reference syncs at the same
-    point (render_utils_kernel.cu:212) and four more times before shading."""
+    point (render_utils_kernel.cu:212) and four more times before shading.  `also_read` (optional 0-dim integer device
+    tensor, e.g. the emission-on ray count) rides along on that read: returns (streams, int(also_read))."""
     L = _lib.lib()
     dev = rays_o.device
     n = rays_o.shape[0]
     if n == 0:  # no rays (e.g. an LTS segment without points): empty streams, no launch
         z = torch.zeros(1, dtype=torch.int32, device=dev)
-        return Streams(0, ray_order, _i32(0, dev), _i32(0, dev), z, 0, _i32(0, dev), _i32(0, dev), _f32(0, dev=dev))
+        empty = Streams(0, ray_order, _i32(0, dev), _i32(0, dev), z, 0, _i32(0, dev), _i32(0, dev), _f32(0, dev=dev))
+        return empty if also_read is None else (empty, int(also_read))
     n_steps, cnt_in, cnt_mask = _i32(n, dev), _i32(n, dev), _i32(n, dev)
     st = stream_ptr()
     scp = ctypes.byref(sc)
@@ -181,11 +183,15 @@ def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid) -> Strea
     check(L.esr_march_count_bits(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(n_steps),
                                  ptr(cnt_in), ptr(cnt_mask), ptr(bits), stride, st))
     off_mask = exclusive_scan(cnt_mask)
-    m1 = int(off_mask[n].item())
+    if also_read is None:
+        m1, extra = int(off_mask[n].item()), None
+    else:
+        m1, extra = torch.stack([off_mask[n], also_read.to(torch.int32)]).tolist()
     s_ray, s_step, s_sdf = _i32(m1, dev), _i32(m1, dev), _f32(m1, dev=dev)
     check(L.esr_march_fill_bits(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(sdf_grid),
                                 ptr(off_mask), ptr(s_ray), ptr(s_step), ptr(s_sdf), ptr(bits), stride, st))
-    return Streams(n, ray_order, n_steps, cnt_in, off_mask, m1, s_ray, s_step, s_sdf)
+    streams = Streams(n, ray_order, n_steps, cnt_in, off_mask, m1, s_ray, s_step, s_sdf)
+    return streams if also_read is None else (streams, extra)
 
 
 class AlphaScan(torch.autograd.Function):
@@ -198,16 +204,16 @@ class AlphaScan(torch.autograd.Function):
         n, st, scp = streams.n_rays, stream_ptr(), ctypes.byref(sc)
         cnt_shade = _i32(n, dev)
         last = _f32(n, dev=dev)
+        streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
         check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
-                                     ptr(cnt_shade), ptr(last), st))
+                                     ptr(cnt_shade), ptr(last), ptr(streams.s_alpha), ptr(streams.s_T), st))
         off_shade = exclusive_scan(cnt_shade) if n else torch.zeros(1, dtype=torch.int32, device=dev)
         if n_on is None:
             m3 = int(off_shade[n].item())
             m3_on = m3
         else:
-            m3, m3_on = torch.stack([off_shade[n], off_shade[n_on]]).tolist()
+            m3, m3_on = torch.stack([off_shade[n], off_shade[int(n_on)]]).tolist()   # n_on: host int (see march)
         streams.off_shade, streams.m3, streams.m3_on = off_shade, m3, m3_on
-        streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
         streams.h_ray, streams.h_step, streams.h_m1 = _i32(m3, dev), _i32(m3, dev), _i32(m3, dev)
         streams.h_sdf = _f32(m3, dev=dev)
         h_w = _f32(m3, dev=dev)
@@ -356,7 +362,9 @@ def _mlp_forward(desc, image, x, rb, re, m_total, train, save_begin=0):
     L = _lib.lib()
     d = _desc(desc)
     dev = x.device
-    y = torch.zeros(m_total, desc["n_out"], dtype=torch.float32, device=dev)
+    # rows outside [rb, re) are defined to be zero; a full-range call writes every row
+    y = (torch.empty if (rb == 0 and re == m_total) else torch.zeros)(m_total, desc["n_out"], dtype=torch.float32,
+                                                                      device=dev)
     # activations (tiled bf16) + ReLU bit masks, layout private to the library
     hidden = (torch.empty(L.esr_mlp_hidden_bytes(ctypes.byref(d), m_total), dtype=torch.uint8, device=dev)
               if train else None)
@@ -529,12 +537,12 @@ class CoarseAlpha(torch.autograd.Function):
         n, st, scp = streams.n_rays, stream_ptr(), ctypes.byref(sc)
         cnt_shade = _i32(n, dev)
         last = _f32(n, dev=dev)
+        streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
         check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
-                                     ptr(cnt_shade), ptr(last), st))
+                                     ptr(cnt_shade), ptr(last), ptr(streams.s_alpha), ptr(streams.s_T), st))
         off_shade = exclusive_scan(cnt_shade)
         m3 = int(off_shade[n].item())
         streams.off_shade, streams.m3, streams.m3_on = off_shade, m3, m3
-        streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
         streams.h_ray, streams.h_step, streams.h_m1 = _i32(m3, dev), _i32(m3, dev), _i32(m3, dev)
         streams.h_sdf = _f32(m3, dev=dev)
         h_w = _f32(m3, dev=dev)

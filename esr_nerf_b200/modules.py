@@ -225,6 +225,17 @@ class GradientConv(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # flat parameter images for the tensor-core MLP kernels
 # ------------------------------------------------------------------------------------------------
+_ZEROS = {}
+
+
+def _zeros(n: int, device) -> torch.Tensor:
+    """cached read-only f32 zeros (padding blocks of the flat parameter image)"""
+    key = (int(n), str(device))
+    if key not in _ZEROS:
+        _ZEROS[key] = torch.zeros(int(n), dtype=torch.float32, device=device)
+    return _ZEROS[key]
+
+
 class _FlatParams(torch.autograd.Function):
     """One autograd node per net: nn.Linear parameters -> flat f32 master copy (and the flat gradient back)."""
 
@@ -234,21 +245,17 @@ class _FlatParams(torch.autograd.Function):
         w_last, b_last = params[-2], params[-1]
         width = w_first.shape[0]
         total = width * k0 + width + sum(p.numel() for p in params[2:-2]) + 8 * width + 8
-        flat = torch.zeros(total, dtype=torch.float32, device=w_first.device)
         # layer 0: reference column order -> internal column order (idx[c] = reference column of internal column c,
-        # = in_features for a zero column)
-        w0 = torch.cat([w_first.detach(), w_first.new_zeros(width, 1)], 1)
-        flat[: width * k0].view(width, k0).copy_(w0.index_select(1, idx))
-        o = width * k0
-        flat[o:o + width].copy_(b_first.detach())
-        o += width
-        for p in params[2:-2]:
-            flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
-            o += p.numel()
+        # = in_features for a zero column).  Three launches per net (cat, gather, cat) — this runs on the host's
+        # critical path between two steps, a copy_ per parameter was 13.
+        dev = w_first.device
+        w0 = torch.cat([w_first.detach(), _zeros(width, dev).view(width, 1)], 1).index_select(1, idx)
         n_out = w_last.shape[0]
-        flat[o:o + n_out * width].copy_(w_last.detach().reshape(-1))
-        o += 8 * width
-        flat[o:o + n_out].copy_(b_last.detach())
+        parts = [w0.reshape(-1), b_first.detach()]
+        parts += [p.detach().reshape(-1) for p in params[2:-2]]
+        parts += [w_last.detach().reshape(-1), _zeros((8 - n_out) * width, dev), b_last.detach(), _zeros(8 - n_out, dev)]
+        flat = torch.cat(parts)
+        assert flat.numel() == total
         ctx.k0, ctx.shapes = k0, [p.shape for p in params]
         ctx.save_for_backward(inv)
         return flat
@@ -324,27 +331,73 @@ def pbr_in_cols(which: str, device) -> torch.Tensor:
     return torch.tensor(cols, dtype=torch.long, device=device)
 
 
+class _FlatParamsPadded(torch.autograd.Function):
+    """nn.Linear parameters of a NARROWER net -> flat f32 master copy zero-padded to the instantiated kernel shape,
+    and the flat gradient back as views of the padded blocks.  One fill + one strided copy per parameter; the
+    torch-op version (F.pad per tensor, differentiated by autograd) cost ~50 launches per net per step on a step
+    that is bound by the host's launch rate."""
+
+    @staticmethod
+    def forward(ctx, idx, inv, k0, width, *params):
+        dev = params[0].device
+        n_layers = len(params) // 2
+        total = width * k0 + width + (n_layers - 2) * (width * width + width) + 8 * width + 8
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        blocks = []          # (offset, rows, cols) of every parameter's padded block
+        o = 0
+        for i in range(n_layers):
+            w, b = params[2 * i], params[2 * i + 1]
+            rows = 8 if i + 1 == n_layers else width
+            cols = k0 if i == 0 else width
+            if i == 0:       # reference column order -> internal column order (zero column for unused inputs)
+                w = torch.cat([w, _zeros(w.shape[0], dev).view(-1, 1)], 1).index_select(1, idx)
+            flat[o:o + rows * cols].view(rows, cols)[: w.shape[0], : w.shape[1]].copy_(w)
+            blocks.append((o, rows, cols))
+            o += rows * cols
+            flat[o:o + b.shape[0]].copy_(b)
+            blocks.append((o, rows, 1))
+            o += rows
+        assert o == total
+        ctx.blocks, ctx.shapes = blocks, [p.shape for p in params]
+        ctx.save_for_backward(inv)
+        return flat
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (inv,) = ctx.saved_tensors
+        grads = []
+        for j, ((o, rows, cols), shp) in enumerate(zip(ctx.blocks, ctx.shapes)):
+            if len(shp) == 1:
+                grads.append(g[o:o + shp[0]])
+            elif j == 0:     # inv[r] = internal column of reference column r
+                grads.append(g[o:o + rows * cols].view(rows, cols)[: shp[0]].index_select(1, inv))
+            else:
+                grads.append(g[o:o + rows * cols].view(rows, cols)[: shp[0], : shp[1]])
+        return (None, None, None, None, *grads)
+
+
 def flat_mlp_params_padded(layers: Sequence[nn.Linear], kind: str, k0: int = 96, width: int = 192) -> torch.Tensor:
     """Flat f32 master copy (layout of flat_mlp_params) of a NARROWER net zero-padded to the instantiated kernel shape
     (emitnet / brdfnet 76->128x3->{3,5} run as 96->192x3): padded hidden units have zero weights and biases, so they
-    stay at relu(0) = 0 and contribute nothing forward or backward.  Built from differentiable torch ops: autograd
-    routes the flat gradient back to the nn.Linear parameters."""
-    cols = pbr_in_cols(kind, layers[0].weight.device)
-    n_ref = layers[0].in_features
-    idx = torch.where(cols < 0, torch.full_like(cols, n_ref), cols)
-    parts = []
-    for i, lin in enumerate(layers):
-        w, b = lin.weight, lin.bias
-        last = i + 1 == len(layers)
-        if i == 0:
-            w = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).index_select(1, idx)      # [out, k0] internal order
-        else:
-            w = F.pad(w, (0, width - w.shape[1]))
-        rows = 8 if last else width
-        w = F.pad(w, (0, 0, 0, rows - w.shape[0]))
-        b = F.pad(b, (0, rows - b.shape[0]))
-        parts += [w.reshape(-1), b]
-    return torch.cat(parts)
+    stay at relu(0) = 0 and contribute nothing forward or backward.  A single autograd node routes the flat gradient
+    back to the nn.Linear parameters."""
+    dev = layers[0].weight.device
+    key = ("pbr_" + kind, str(dev))
+    if key not in _COLS_CACHE:
+        cols = pbr_in_cols(kind, "cpu")
+        n_ref = layers[0].in_features
+        idx = torch.where(cols < 0, torch.full_like(cols, n_ref), cols)
+        inv = torch.empty(n_ref, dtype=torch.long)
+        for c_int, c_ref in enumerate(cols.tolist()):
+            if c_ref >= 0:
+                inv[c_ref] = c_int
+        _COLS_CACHE[key] = (idx.to(dev), inv.to(dev))
+    idx, inv = _COLS_CACHE[key]
+    params = []
+    for lin in layers:
+        params += [lin.weight, lin.bias]
+    return _FlatParamsPadded.apply(idx, inv, k0, width, *params)
 
 
 def radiance_in_cols(which: str, device) -> torch.Tensor:
@@ -514,6 +567,25 @@ def voxel_geometry(xyz_min: torch.Tensor, xyz_max: torch.Tensor, num_voxels: int
     voxel_size = ((xyz_max - xyz_min).prod() / num_voxels).pow(1 / 3)
     world_size = ((xyz_max - xyz_min) / voxel_size).long()
     return voxel_size, world_size
+
+
+def host_geometry(owner, stepsize: float) -> dict:
+    """Host copies of the small device tensors that parameterise a render call (the two AABBs, voxel size, step
+    length), cached on the model.  The reference keeps them on cfg.system.device (voxurff.py:36-41) and so does the
+    drop-in; reading them back with .tolist() / float() on every call is six device synchronisations at the top of
+    each step — the host could never queue the next step while the previous backward still runs.  The cache is keyed
+    on tensor identity + in-place version, so set_grid_resolution / scale_volume_grid / load_state_dict invalidate it;
+    the floats are produced by the same torch expressions as before (bit-identical)."""
+    ts = (owner.xyz_min, owner.xyz_max, owner.mask_xyz_min, owner.mask_xyz_max, owner.voxel_size)
+    ver = tuple(t._version if torch.is_tensor(t) else t for t in ts) + (float(stepsize),)
+    c = owner.__dict__.get("_host_geo")
+    if c is not None and c[1] == ver and all(a is b for a, b in zip(c[0], ts)):
+        return c[2]
+    vals = dict(xyz_min=owner.xyz_min.tolist(), xyz_max=owner.xyz_max.tolist(),
+                mask_xyz_min=owner.mask_xyz_min.tolist(), mask_xyz_max=owner.mask_xyz_max.tolist(),
+                stepdist=float(stepsize * owner.voxel_size), voxel_size=float(owner.voxel_size))
+    owner.__dict__["_host_geo"] = (ts, ver, vals)
+    return vals
 
 
 def n_candidate_steps(world_size, stepsize: float) -> int:

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import fused
-from .modules import DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, _mlp_stack, cfg_get, voxel_geometry
+from .modules import DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, _mlp_stack, cfg_get, host_geometry, voxel_geometry
 from .render_utils import Alphas2Weights
 
 
@@ -113,9 +113,9 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
     def _scene(self, s_val: float):
         g = self.sdf.grid.shape
         md = self.mask_cache.density.shape
-        return fused.make_scene(self.xyz_min.tolist(), self.xyz_max.tolist(), g[2:], self.mask_xyz_min.tolist(),
-                                self.mask_xyz_max.tolist(), md[2:], self.near, 1e9,
-                                float(self.stepsize * self.voxel_size), float(self.voxel_size),
+        h = host_geometry(self, self.stepsize)
+        return fused.make_scene(h["xyz_min"], h["xyz_max"], g[2:], h["mask_xyz_min"], h["mask_xyz_max"], md[2:],
+                                self.near, 1e9, h["stepdist"], h["voxel_size"],
                                 self.mask_cache.act_shift, self.maskcache_thres, self.fastcolor_thres, s_val,
                                 alpha_thres=-1.0)     # the coarse stage has no alpha filter before the scan
 
@@ -182,7 +182,7 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
             emo = torch.sigmoid(self.emo_rgbnet(torch.cat([x[:, 12:24], feat], -1)))
             normal = ((x[:, 66:69] @ pos_rt) * torch.tensor([1.0, -1.0, -1.0], device=dev) + 1.0) / 2.0
             dvec = torch.ones(s.m3, 3, device=dev)
-            dvec[:, 0] = s.h_step.float() * float(self.stepsize * self.voxel_size)
+            dvec[:, 0] = s.h_step.float() * host_geometry(self, self.stepsize)["stepdist"]
             off_m, emo_m = fused.composite_infer(weights, off, emo, s)
             on_m, nrm_m = fused.composite_infer(weights, off + emo, normal, s)
             dw, _ = fused.composite_infer(weights, dvec, dvec, s)                      # (depth, sum w, sum w)

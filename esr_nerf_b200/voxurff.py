@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import fused
-from .modules import (DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, RadianceNet, TonemapNet, cfg_get, flat_mlp_params,
+from .modules import (host_geometry, DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, RadianceNet, TonemapNet, cfg_get, flat_mlp_params,
                       radiance_in_cols, tonemap_in_cols, voxel_geometry)
 
 
@@ -135,9 +135,9 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
     def _scene(self, s_val: float, near=None):
         g = self.sdf.grid.shape
         md = self.mask_cache.density.shape
-        return fused.make_scene(self.xyz_min.tolist(), self.xyz_max.tolist(), g[2:], self.mask_xyz_min.tolist(),
-                                self.mask_xyz_max.tolist(), md[2:], self.near if near is None else near, 1e9,
-                                float(self.stepsize * self.voxel_size), float(self.voxel_size),
+        h = host_geometry(self, self.stepsize)
+        return fused.make_scene(h["xyz_min"], h["xyz_max"], g[2:], h["mask_xyz_min"], h["mask_xyz_max"], md[2:],
+                                self.near if near is None else near, 1e9, h["stepdist"], h["voxel_size"],
                                 self.mask_cache.act_shift, self.maskcache_thres, self.fastcolor_thres, s_val)
 
     def _flat(self, which: str):
@@ -152,11 +152,13 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
         if self.on_first_order and em_modes is not None and em_modes.dim() == 1:
             on = em_modes == 1
             order = torch.argsort((~on).to(torch.uint8), stable=True).to(torch.int32)
-            n_on = on.sum()
+            n_on = on.sum(dtype=torch.int32)
         for g in (self.sdf, self.off_color, self.emo_color):
             g.ensure_layout()
-        streams = fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach())
-        return streams, n_on
+        if n_on is None:
+            return fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach()), None
+        # the emission-on ray count reaches the host on the read that sizes the M1 stream (no extra synchronisation)
+        return fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach(), also_read=n_on)
 
     def forward_training(self, **kwargs) -> Dict[str, torch.Tensor]:
         """voxurff.py:177-278"""
@@ -247,7 +249,7 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
             off_rgb, on_rgb, emo_rgb = srgb[: s.m3], srgb[s.m3: 2 * s.m3], srgb[2 * s.m3:]
             grad = fused.sdf_fd_gradient(sc, rays_o, rays_d, sdf_g, s)
             normal = (F.normalize(grad, dim=-1) @ pos_rt * self.normal_flipper.to(dev) + 1.0) / 2.0
-            dist = float(self.stepsize * self.voxel_size)
+            dist = host_geometry(self, self.stepsize)["stepdist"]
             dvec = torch.zeros(s.m3, 3, device=dev)
             dvec[:, 0] = s.h_step.float() * dist
             off_m, lin_off_m = fused.composite_infer(h_w, off_rgb, lin_off, s)

@@ -158,17 +158,18 @@ int esr_march_fill_bits(const esr_scene_t *sc, const float *rays_o, const float 
 /*
  * Stage C/D — NeuS 'interp' alpha (functions.py:72-105), alpha>thr filter (voxurff.py:201),
  * transmittance scan with the reference's sequential float/double recurrence and early stop
- * (kernel.cu:591-603), weight>thr filter (voxurff.py:209).  Warp per ray slot over its M1 segment.
- *   count: cnt_shade[slot]; alphainv_last[ray]
- *   fill : h_ray/h_step/h_m1[M3] (int32), h_w/h_sdf[M3]; s_alpha[M1], s_T[M1]
+ * (kernel.cu:591-603), weight>thr filter (voxurff.py:209).
+ *   count: s_alpha[M1] (warp per ray slot, lanes over its M1 segment), then s_T[M1], cnt_shade[slot] and
+ *          alphainv_last[ray] (thread per ray slot: 32 rays' dependent chains advance per warp instruction)
  *          (s_T = T of the sample, or -1 when the sample is not part of the scan)
+ *   fill : reads s_alpha / s_T, writes h_ray/h_step/h_m1[M3] (int32), h_w/h_sdf[M3] (warp per ray slot)
  */
 int esr_alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
                          const int32_t *off_mask, const float *s_sdf, int32_t *cnt_shade,
-                         float *alphainv_last, esr_stream_t stream);
+                         float *alphainv_last, float *s_alpha, float *s_T, esr_stream_t stream);
 int esr_alpha_scan_fill(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
                         const int32_t *off_mask, const int32_t *s_step, const float *s_sdf,
-                        const int32_t *off_shade, float *s_alpha, float *s_T, int32_t *h_ray,
+                        const int32_t *off_shade, const float *s_alpha, const float *s_T, int32_t *h_ray,
                         int32_t *h_step, int32_t *h_m1, float *h_w, float *h_sdf,
                         esr_stream_t stream);
 

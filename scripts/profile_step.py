@@ -50,3 +50,21 @@ span = ev[-1].time_range.end - ev[0].time_range.start
 print(f"GPU busy {busy/3e3:.3f} ms/step, span {span/3e3:.3f} ms/step, idle {(span-busy)/3e3:.3f} ms/step")
 gaps = sorted(((ev[i+1].time_range.start - ev[i].time_range.end, ev[i].name[:50], ev[i+1].name[:50]) for i in range(len(ev)-1)), reverse=True)[:12]
 for g in gaps: print(f"gap {g[0]:8.1f} us after {g[1]} before {g[2]}")
+
+# full GPU timeline of the middle step (start us, duration us, idle gap before, name): where the device waits for the host
+import json as _json
+marks = [i for i, e in enumerate(ev) if "k_march<false>" in e.name or "k_march<0>" in e.name]
+if len(marks) >= 3:
+    lo, hi = marks[1], marks[2]
+    t0 = ev[lo].time_range.start
+    rows = []
+    for i in range(lo, hi):
+        e = ev[i]
+        rows.append((e.time_range.start - t0, e.time_range.end - e.time_range.start,
+                     e.time_range.start - ev[i - 1].time_range.end, e.name[:70]))
+    out = os.path.join(ROOT, "gpurun_out", f"timeline_{stage}.txt")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "w") as f:
+        for r in rows:
+            f.write(f"{r[0]:9.1f} {r[1]:8.1f} {r[2]:7.1f}  {r[3]}\n")
+    print(f"timeline: {len(rows)} GPU events, idle {sum(max(r[2], 0) for r in rows) / 1e3:.3f} ms -> {out}")
