@@ -132,7 +132,9 @@ PROTOTYPES = {
     "esr_exclusive_scan_i32": (I32, [P, P, I64, P, P]),
     "esr_march_count": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P]),
     "esr_march_fill": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P]),
-    "esr_march_count_bits": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, I32, P]),
+    "esr_march_count_bits": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, I32, P, P]),
+    "esr_mask_class_bytes": (I64, [SCENE_P]),
+    "esr_mask_classify": (I32, [SCENE_P, P, P, P]),
     "esr_march_fill_bits": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, I32, P]),
     "esr_alpha_scan_count": (I32, [SCENE_P, P, I64, P, P, P, P, P, P, P]),
     "esr_alpha_scan_fill": (I32, [SCENE_P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]),

@@ -14,6 +14,89 @@ static inline unsigned ray_blocks(int64_t n_rays) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// MaskCache cell classes.  MaskCache.forward (module.py:104-114) is trilinear(density) -> softplus -> 1 - exp(-.) >= thres,
+// i.e. sigmoid(d + shift) >= thres: monotone in the interpolated density d, and d is a convex combination of the 8
+// corners of the cell.  A cell whose corners (and those of its 26 neighbours, so that the cheap cell lookup below may
+// be off by one cell) all lie above the decision density by a margin keeps every point in it; all below drops every
+// point.  The march test then costs one byte load for those cells and the exact 8-tap evaluation only near the
+// occupancy boundary — the boolean results are identical by construction (the margin is ~150x the float rounding
+// of the exact chain near the threshold; non-finite densities and out-of-grid neighbours force the exact path).
+// cls[(i * (my-1) + j) * (mz-1) + k]: 0 = evaluate exactly, 1 = keep, 2 = drop.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_mask_classify(const __grid_constant__ esr_scene_t sc, const float *__restrict__ dens, float d_star,
+                    uint8_t *__restrict__ cls) {
+  const int cx = sc.mx - 1, cy = sc.my - 1, cz = sc.mz - 1;
+  const int64_t total = (int64_t)cx * cy * cz;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(c % cz), j = (int)((c / cz) % cy), i = (int)(c / ((int64_t)cz * cy));
+    float lo = 3.0e38f, hi = -3.0e38f;
+    bool finite = true;
+    for (int a = i - 1; a <= i + 2; ++a)
+      for (int b = j - 1; b <= j + 2; ++b)
+        for (int d = k - 1; d <= k + 2; ++d) {
+          // zeros padding of grid_sample outside the grid
+          const float v = in_grid(a, b, d, sc.mx, sc.my, sc.mz) ? __ldg(dens + ((int64_t)a * sc.my + b) * sc.mz + d) : 0.f;
+          finite = finite && (fabsf(v) <= 1.0e30f);
+          lo = fminf(lo, v);
+          hi = fmaxf(hi, v);
+        }
+    const float margin = 0.01f + 1e-5f * fmaxf(fabsf(lo), fabsf(hi));
+    uint8_t r = 0;
+    if (finite && lo > d_star + margin) r = 1;
+    else if (finite && hi < d_star - margin) r = 2;
+    cls[c] = r;
+  }
+}
+
+extern "C" int64_t esr_mask_class_bytes(const esr_scene_t *sc) {
+  if (!sc || sc->mx < 2 || sc->my < 2 || sc->mz < 2) return 0;
+  return (int64_t)(sc->mx - 1) * (sc->my - 1) * (sc->mz - 1);
+}
+
+extern "C" int esr_mask_classify(const esr_scene_t *sc, const float *mask_density, uint8_t *cls, esr_stream_t stream) {
+  ESR_CHECK_ARG(sc && mask_density && cls && sc->mx >= 2 && sc->my >= 2 && sc->mz >= 2);
+  ESR_CHECK_ARG(sc->mask_thres > 0.f && sc->mask_thres < 1.f);
+  // sigmoid(d + shift) >= thres  <=>  d >= logit(thres) - shift
+  const double t = (double)sc->mask_thres;
+  const float d_star = (float)(log(t / (1.0 - t)) - (double)sc->act_shift);
+  const int64_t total = esr_mask_class_bytes(sc);
+  ESR_STAGE("k_mask_classify", (cudaStream_t)stream);
+  k_mask_classify<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(*sc, mask_density, d_star, cls);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+// cheap cell lookup: index = (p - min) * (size - 1) / (max - min) with one multiply per axis (scale precomputed per
+// thread); it may differ from world_to_index's separately rounded expression by a fraction of a cell — covered by the
+// neighbour dilation of the class table.  Points outside the mask grid's cells take the exact path.
+struct MaskCls {
+  const uint8_t *cls;
+  float sx, sy, sz;
+};
+ESR_D MaskCls mask_cls_setup(const esr_scene_t &sc, const uint8_t *cls) {
+  MaskCls m;
+  m.cls = cls;
+  m.sx = (float)(sc.mx - 1) / (sc.mask_xyz_max[0] - sc.mask_xyz_min[0]);
+  m.sy = (float)(sc.my - 1) / (sc.mask_xyz_max[1] - sc.mask_xyz_min[1]);
+  m.sz = (float)(sc.mz - 1) / (sc.mask_xyz_max[2] - sc.mask_xyz_min[2]);
+  return m;
+}
+ESR_D bool mask_keep_cls(const esr_scene_t &sc, const MaskCls &m, const float *__restrict__ mask_density, float px,
+                         float py, float pz) {
+  if (m.cls) {
+    const float fx = (px - sc.mask_xyz_min[0]) * m.sx, fy = (py - sc.mask_xyz_min[1]) * m.sy,
+                fz = (pz - sc.mask_xyz_min[2]) * m.sz;
+    const int i = (int)floorf(fx), j = (int)floorf(fy), k = (int)floorf(fz);
+    if ((unsigned)i < (unsigned)(sc.mx - 1) && (unsigned)j < (unsigned)(sc.my - 1) && (unsigned)k < (unsigned)(sc.mz - 1)) {
+      const uint8_t c = __ldg(m.cls + ((int64_t)i * (sc.my - 1) + j) * (sc.mz - 1) + k);
+      if (c) return c == 1;
+    }
+  }
+  return mask_keep(sc, mask_density, px, py, pz);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage A/B: march
 // ---------------------------------------------------------------------------------------------
 // keep_bits (nullable): [n_rays][bits_stride] uint32, one ballot word per 32 candidate steps of a ray slot.  The count
@@ -26,11 +109,13 @@ __global__ void __launch_bounds__(256)
             const float *__restrict__ mask_density, const float *__restrict__ sdf_grid,
             int32_t *__restrict__ n_steps, int32_t *__restrict__ cnt_inbox, int32_t *__restrict__ cnt_mask,
             const int32_t *__restrict__ off_mask, int32_t *__restrict__ s_ray, int32_t *__restrict__ s_step,
-            float *__restrict__ s_sdf, uint32_t *__restrict__ keep_bits, int bits_stride) {
+            float *__restrict__ s_sdf, uint32_t *__restrict__ keep_bits, int bits_stride,
+            const uint8_t *__restrict__ mask_cls) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned lane = lane_id();
   const unsigned lt = lanemask_lt();
+  const MaskCls mc = mask_cls_setup(sc, mask_cls);
   for (int64_t slot = warp; slot < n_rays; slot += nwarps) {
     const int r = ray_order ? ray_order[slot] : (int)slot;
     const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
@@ -47,7 +132,7 @@ __global__ void __launch_bounds__(256)
         bal = bits[chunk];                              // warp-uniform load
       } else {
         const bool inb = (k < s.n) && !out_bbox(sc.xyz_min, sc.xyz_max, px, py, pz);
-        const bool keep = inb && mask_keep(sc, mask_density, px, py, pz);
+        const bool keep = inb && mask_keep_cls(sc, mc, mask_density, px, py, pz);
         bal = __ballot_sync(FULL, keep);
         if (!FILL) {
           c_in += __popc(__ballot_sync(FULL, inb));
@@ -81,7 +166,8 @@ static int check_scene(const esr_scene_t *sc) {
 
 static int march_count_impl(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
                             int64_t n_rays, const float *mask_density, int32_t *n_steps, int32_t *cnt_inbox,
-                            int32_t *cnt_mask, uint32_t *keep_bits, int bits_stride, esr_stream_t stream) {
+                            int32_t *cnt_mask, uint32_t *keep_bits, int bits_stride, const uint8_t *mask_cls,
+                            esr_stream_t stream) {
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
@@ -90,7 +176,7 @@ static int march_count_impl(const esr_scene_t *sc, const float *rays_o, const fl
   k_march<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
                                                                        mask_density, nullptr, n_steps, cnt_inbox,
                                                                        cnt_mask, nullptr, nullptr, nullptr, nullptr,
-                                                                       keep_bits, bits_stride);
+                                                                       keep_bits, bits_stride, mask_cls);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -99,16 +185,16 @@ extern "C" int esr_march_count(const esr_scene_t *sc, const float *rays_o, const
                                const int32_t *ray_order, int64_t n_rays, const float *mask_density, int32_t *n_steps,
                                int32_t *cnt_inbox, int32_t *cnt_mask, esr_stream_t stream) {
   return march_count_impl(sc, rays_o, rays_d, ray_order, n_rays, mask_density, n_steps, cnt_inbox, cnt_mask, nullptr, 0,
-                          stream);
+                          nullptr, stream);
 }
 
 extern "C" int esr_march_count_bits(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
                                     const int32_t *ray_order, int64_t n_rays, const float *mask_density,
                                     int32_t *n_steps, int32_t *cnt_inbox, int32_t *cnt_mask, uint32_t *keep_bits,
-                                    int bits_stride, esr_stream_t stream) {
+                                    int bits_stride, const uint8_t *mask_cls, esr_stream_t stream) {
   ESR_CHECK_ARG(!keep_bits || bits_stride > 0);
   return march_count_impl(sc, rays_o, rays_d, ray_order, n_rays, mask_density, n_steps, cnt_inbox, cnt_mask, keep_bits,
-                          bits_stride, stream);
+                          bits_stride, mask_cls, stream);
 }
 
 static int march_fill_impl(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
@@ -124,7 +210,8 @@ static int march_fill_impl(const esr_scene_t *sc, const float *rays_o, const flo
   k_march<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, ray_order, n_rays,
                                                                       mask_density, sdf_grid, nullptr, nullptr,
                                                                       nullptr, off_mask, s_ray, s_step, s_sdf,
-                                                                      const_cast<uint32_t *>(keep_bits), bits_stride);
+                                                                      const_cast<uint32_t *>(keep_bits), bits_stride,
+                                                                      nullptr);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

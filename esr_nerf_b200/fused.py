@@ -161,6 +161,26 @@ def march_count(sc: Scene, rays_o, rays_d, mask_density):
     return n_steps, cnt_in, cnt_mask
 
 
+MASK_CLASSES = True   # tests switch the class table off to compare against the exact 8-tap test on every candidate
+_MASK_CLS = {}   # id(density) -> (density, version, scene key, class table)
+
+
+def mask_class_table(sc: Scene, mask_density: torch.Tensor) -> torch.Tensor:
+    """per-cell keep / drop / undecided classes of the MaskCache grid (esr_mask_classify), rebuilt only when the
+    density tensor (identity + in-place version) or the scene constants it depends on change"""
+    key = (tuple(sc.mask_xyz_min), tuple(sc.mask_xyz_max), sc.mx, sc.my, sc.mz, sc.act_shift, sc.mask_thres)
+    hit = _MASK_CLS.get(id(mask_density))
+    if hit is not None and hit[0] is mask_density and hit[1] == mask_density._version and hit[2] == key:
+        return hit[3]
+    L = _lib.lib()
+    cls = torch.empty(int(L.esr_mask_class_bytes(ctypes.byref(sc))), dtype=torch.uint8, device=mask_density.device)
+    check(L.esr_mask_classify(ctypes.byref(sc), ptr(mask_density), ptr(cls), stream_ptr()))
+    if len(_MASK_CLS) > 16:
+        _MASK_CLS.clear()
+    _MASK_CLS[id(mask_density)] = (mask_density, mask_density._version, key, cls)
+    return cls
+
+
 def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_read=None):
     """Stages A/B.  One host read (M1) sizes the stream buffers — the reference syncs at the same
     point (render_utils_kernel.cu:212) and four more times before shading.  `also_read` (optional 0-dim integer device
@@ -180,8 +200,9 @@ def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_rea
     diag = sum((sc.xyz_max[i] - sc.xyz_min[i]) ** 2 for i in range(3)) ** 0.5
     stride = int(diag / sc.stepdist) // 32 + 2
     bits = _i32(n * stride, dev)
+    cls = mask_class_table(sc, mask_density) if MASK_CLASSES else None
     check(L.esr_march_count_bits(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(n_steps),
-                                 ptr(cnt_in), ptr(cnt_mask), ptr(bits), stride, st))
+                                 ptr(cnt_in), ptr(cnt_mask), ptr(bits), stride, ptr(cls), st))
     off_mask = exclusive_scan(cnt_mask)
     if also_read is None:
         m1, extra = int(off_mask[n].item()), None

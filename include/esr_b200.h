@@ -146,10 +146,19 @@ int esr_march_fill(const esr_scene_t *sc, const float *rays_o, const float *rays
  * Same two calls with a keep-bit cache: the count pass stores one ballot word per 32 candidate steps of each ray slot
  * (keep_bits [n_rays][bits_stride] uint32, bits_stride >= ceil(max steps per ray / 32)), the fill pass reads the words
  * instead of repeating the AABB test and the 8-tap MaskCache lookup of every candidate.  Results are identical.
+ *
+ * mask_cls (nullable): per-cell classes of the MaskCache density grid made by esr_mask_classify ([mx-1][my-1][mz-1]
+ * bytes, esr_mask_class_bytes): 1 = every point of the cell passes MaskCache.forward (module.py:104-114), 2 = none
+ * does, 0 = evaluate exactly.  The test is monotone in the interpolated density, so a cell whose corners (and its
+ * neighbours') lie on one side of the decision density by a margin is decided by one byte load; results are identical.
+ * The table must be rebuilt when the density grid, its bbox, act_shift or mask_thres change.
  */
+int64_t esr_mask_class_bytes(const esr_scene_t *sc);
+int esr_mask_classify(const esr_scene_t *sc, const float *mask_density, uint8_t *cls, esr_stream_t stream);
 int esr_march_count_bits(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
                          int64_t n_rays, const float *mask_density, int32_t *n_steps, int32_t *cnt_inbox,
-                         int32_t *cnt_mask, uint32_t *keep_bits, int bits_stride, esr_stream_t stream);
+                         int32_t *cnt_mask, uint32_t *keep_bits, int bits_stride, const uint8_t *mask_cls,
+                         esr_stream_t stream);
 int esr_march_fill_bits(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
                         int64_t n_rays, const float *mask_density, const float *sdf_grid, const int32_t *off_mask,
                         int32_t *s_ray, int32_t *s_step, float *s_sdf, const uint32_t *keep_bits, int bits_stride,

@@ -158,3 +158,52 @@ def test_exclusive_scan_large():
         ref = torch.cat([torch.zeros(1, dtype=torch.int64), c.long().cumsum(0)])
         assert torch.equal(out.long(), ref), n
     _ = np
+
+
+@pytest.mark.parametrize("kind", ["near_threshold", "shell", "offset_bbox", "nonfinite"])
+def test_mask_class_table_leaves_march_streams_identical(kind):
+    """esr_mask_classify: the per-cell keep / drop classes shortcut MaskCache.forward (module.py:104-114) in the march
+    kernel.  The packed streams with the table must equal those of the exact 8-tap test on every candidate — on a
+    smooth density that hovers around the decision value (most cells undecided or one step from it), on the sparse
+    shell, with a mask bbox that differs from the scene bbox (candidates outside the mask grid), and with non-finite
+    densities."""
+    from esr_nerf_b200 import fused
+
+    res, n = 48, 4096
+    g = torch.Generator().manual_seed(5)
+    act_shift = float(np.log(1 / (1 - S.MASK_ALPHA_INIT) - 1))
+    d_star = float(np.log(1e-3 / (1 - 1e-3)) - act_shift)
+    if kind == "shell":
+        dens = S.mask_density(res, True)
+    else:
+        coarse = torch.randn(1, 1, 7, 7, 7, generator=g)
+        smooth = torch.nn.functional.interpolate(coarse, size=(res, res, res), mode="trilinear", align_corners=True)
+        dens = d_star + 0.5 * smooth + 0.02 * torch.randn(1, 1, res, res, res, generator=g)
+        if kind == "nonfinite":
+            dens[0, 0, 10, 11, 12] = float("inf")
+            dens[0, 0, 30, 5, 7] = float("nan")
+            dens[0, 0, 20:24, 20:24, 20:24] = 50.0
+    dens = dens.to(DEV).contiguous()
+    mmin, mmax = (S.BBOX_MIN, S.BBOX_MAX) if kind != "offset_bbox" else (S.BBOX_MIN * 0.7 + 0.05, S.BBOX_MAX * 0.8)
+    sc = fused.make_scene(S.BBOX_MIN.tolist(), S.BBOX_MAX.tolist(), (64, 64, 64), mmin.tolist(), mmax.tolist(),
+                          (res, res, res), S.NEAR, 1e9, 0.5 * 2.1 / 64, 2.1 / 64, act_shift, 1e-3, 1e-4, 20.0)
+    rays = S.make_rays(n, 77)
+    o, d = rays["rays_o"].to(DEV), rays["rays_d"].to(DEV)
+    sdf = S.sphere_sdf((64, 64, 64)).to(DEV).contiguous()
+    cls = fused.mask_class_table(sc, dens)
+    counts = torch.bincount(cls.long(), minlength=3).tolist()
+    if kind in ("near_threshold", "shell"):
+        assert counts[0] > 0 and counts[1] > 0 and counts[2] > 0, counts
+    got = []
+    for on in (True, False):
+        fused.MASK_CLASSES = on
+        try:
+            s = fused.march(sc, o, d, None, dens, sdf)
+        finally:
+            fused.MASK_CLASSES = True
+        got.append(s)
+    a, b = got
+    assert a.m1 == b.m1 and a.m1 > 0
+    for f in ("n_steps", "cnt_inbox", "off_mask", "s_ray", "s_step"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    assert torch.equal(a.s_sdf.view(torch.int32), b.s_sdf.view(torch.int32))   # bit-identical, NaN-safe
