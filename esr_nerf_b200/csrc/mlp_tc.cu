@@ -16,6 +16,8 @@
 // K-halves of one MMA (K = 16) R*16 bytes apart (descriptor LBO), consecutive 8-row groups 128 bytes apart
 // (descriptor SBO).  The global weight image built by tc_pack has exactly this byte order, so staging is a
 // straight copy, and an epilogue thread (= one row) writing one 16-byte chunk per k-chunk is conflict-free.
+#include <stdlib.h>
+
 #include "mlp_layout.cuh"
 
 using namespace esr;
@@ -451,6 +453,167 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       tc_fence_before();   // the next tile's first MMA overwrites D0 / the region read above
     }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_issuer) tmem_dealloc(tmem, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tone-map forward, two tiles in flight
+// ------------------------------------------------------------------------------------------------
+// The tone-map net (33 -> 192 -> 3) is too small for the generic chain: one 128-row tile is a string of latencies
+// (encode -> MMA -> commit -> epilogue -> MMA -> commit -> epilogue, ~2.4 us) during which the 16 epilogue warps work
+// for ~0.9 us.  This kernel keeps TWO tiles in flight per CTA, in two slots s = tile & 1:
+//   TMEM  D_s [192 s, 192 s + 192): layer-0 accumulator; once every epilogue warp has read it (named barrier) the bf16
+//         A operand of the output layer is written over its first 96 columns (the accumulator is dead by then), so two
+//         slots fit 512 columns;  O_s [384 + 16 s, +16): output-layer accumulator
+//   smem  x_s: the encoded 128 x 48 tile (the CTA computes the positional encoding itself, as the generic XSRC path)
+//   mbarriers per slot: x ready (12 encoding warps) -> MMA0 done (commit) -> A ready (16 warps) -> out MMA done (commit)
+// The issuer alternates [out MMA of tile i] [MMA0 of tile i + 2]; the epilogue warps alternate [layer-0 epilogue of tile
+// i] [output epilogue of tile i - 1], so each side always has the other slot's work to do while a commit is in flight.
+struct Tm2Sm {
+  using F = FwdSm<48, 1>;
+  static constexpr int x0 = (F::weights_bytes + 127) / 128 * 128;
+  static constexpr int x_bytes = TC_TM * 48 * 2;
+  static constexpr int bar = x0 + 2 * x_bytes;      // bar_x[2], bar_mma0[2], bar_a[2], bar_out[2] (8 B each), TMEM slot
+  static constexpr int bytes = bar + 8 * 8 + 16;
+};
+
+template <int NO>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_tonemap_fwd2(const uint8_t *__restrict__ image, const float *__restrict__ lin, int64_t m, float *__restrict__ y,
+                   int n_out, int act) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = Tm2Sm;
+  using F = FwdSm<48, 1>;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
+  const uint32_t sbase = smem_addr(smem);
+  const uint32_t bar_x = sbase + S::bar, bar_mma0 = bar_x + 16, bar_a = bar_x + 32, bar_out = bar_x + 48;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 64);
+
+  stage_bytes(smem, image, F::weights_bytes);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_x + 8 * s, 12);               // the 12 warps of column groups 0..2 encode one channel each
+      mbar_init(bar_mma0 + 8 * s, 1);
+      mbar_init(bar_a + 8 * s, TC_EPI_WARPS);
+      mbar_init(bar_out + 8 * s, 1);
+    }
+    fence_mbar_init();
+  }
+  if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float *sbias = reinterpret_cast<const float *>(smem + F::bias);
+
+  const int64_t n_tiles = (m + TC_TM - 1) / TC_TM;
+  const int n_my = blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;   // tiles of this CTA
+  const EpiThread et(warp, lane);
+  const int t = et.row_in_tile;
+
+  if (is_issuer) {
+    if (lane == 0) {
+      auto mma0 = [&](int s) {   // layer 0 of the tile waiting in slot s: A = x_s (shared), B = W0
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          mma_ss(tmem + 192 * s, make_desc(sbase + S::x0 + s * S::x_bytes + 2 * k * (TC_TM * 16), TC_TM * 16, 128),
+                 make_desc(sbase + F::w0 + 2 * k * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), k > 0);
+        mma_commit(bar_mma0 + 8 * s);
+      };
+      for (int i = 0; i < 2 && i < n_my; ++i) {
+        mbar_wait(bar_x + 8 * i, 0);
+        tc_fence_after();
+        mma0(i);
+      }
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i & 1;
+        mbar_wait(bar_a + 8 * s, (i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < TC_W / 16; ++k)      // output layer: A = bf16 activations in TMEM (over D_s), B = Wo
+          mma_ts(tmem + 384 + 16 * s, tmem + 192 * s + 8 * k,
+                 make_desc(sbase + F::wo + 2 * k * (TC_NOUT_PAD * 16), TC_NOUT_PAD * 16, 128), make_idesc(TC_NOUT_PAD), k > 0);
+        mma_commit(bar_out + 8 * s);
+        if (i + 2 < n_my) {                       // in order behind the out MMA: D_s / A_s are free when it starts
+          mbar_wait(bar_x + 8 * s, ((i + 2) >> 1) & 1);
+          tc_fence_after();
+          mma0(s);
+        }
+      }
+    }
+  } else if (is_epi) {
+    auto load_x = [&](int i) {   // column group g < 3 encodes channel g of its row into chunks 2 g, 2 g + 1 of slot i & 1
+      if (et.grp < 3) {
+        const int64_t row = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC_TM + t;
+        const bool ok = row < m;
+        const float v = ok ? __ldg(lin + 3 * row + et.grp) : 0.f;
+        uint4 lo, hi;
+        float sn[5], cs[5];
+        tonemap_pe_channel(v, lo, hi, sn, cs);
+        if (!ok) lo = hi = make_uint4(0u, 0u, 0u, 0u);
+        uint8_t *xs = smem + S::x0 + (i & 1) * S::x_bytes;
+        *reinterpret_cast<uint4 *>(xs + (2 * et.grp) * (TC_TM * 16) + t * 16) = lo;
+        *reinterpret_cast<uint4 *>(xs + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hi;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_x + 8 * (i & 1));
+      }
+    };
+    auto out_epilogue = [&](int i) {
+      const int s = i & 1;
+      mbar_wait(bar_out + 8 * s, (i >> 1) & 1);
+      tc_fence_after();
+      if (et.grp == 0) {
+        uint32_t r[16];
+        tmem_ld16(tmem + et.lane_base + 384 + 16 * s, r);
+        tmem_ld_wait();
+        const int64_t row = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC_TM + t;
+        if (row < m) {
+          const float *bo = sbias + TC_W;
+#pragma unroll
+          for (int c = 0; c < NO; ++c)
+            if (c < n_out) y[row * n_out + c] = act_fwd(__uint_as_float(r[c]) + bo[c], act);
+        }
+      }
+      tc_fence_before();
+    };
+    for (int i = 0; i < 2 && i < n_my; ++i) load_x(i);
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i & 1;
+      mbar_wait(bar_mma0 + 8 * s, (i >> 1) & 1);
+      tc_fence_after();
+      if (i + 2 < n_my) load_x(i + 2);            // x_s is free: encode the tile after next
+      uint32_t r[3][16];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + 192 * s + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");   // every warp has read D_s: A may overwrite it
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int col0 = TC_GCOLS * et.grp + 16 * cc;
+        uint32_t p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
+          p[j] = pack2(fmaxf(__uint_as_float(r[cc][2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(r[cc][2 * j + 1]) + bb.y, 0.f));
+        }
+        tmem_st8(tmem + et.lane_base + 192 * s + col0 / 2, p);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a + 8 * s);
+      if (i >= 1) out_epilogue(i - 1);
+    }
+    if (n_my >= 1) out_epilogue(n_my - 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -1214,7 +1377,14 @@ int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t
 }
 
 int tc_tonemap_fwd(const esr_mlp_desc_t *d, const void *tc_image, const float *lin, int64_t m, float *y, cudaStream_t st) {
-  return launch_fwd<48, 1, 3, 1>(d, tc_image, lin, 0, m, m, y, nullptr, 0, st);
+  if (getenv("ESR_TONEMAP_FWD_GENERIC"))   // the one-tile-at-a-time generic chain (kept for A/B measurements)
+    return launch_fwd<48, 1, 3, 1>(d, tc_image, lin, 0, m, m, y, nullptr, 0, st);
+  auto kern = k_tonemap_fwd2<3>;
+  if (int e = set_smem_tc(kern, Tm2Sm::bytes)) return e;
+  ESR_STAGE("k_tonemap_fwd_fused", st);
+  kern<<<tc_grid(m), TC_THREADS, Tm2Sm::bytes, st>>>((const uint8_t *)tc_image, lin, m, y, d->n_out, d->act);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
 }
 
 int tc_tonemap_bwd(const esr_mlp_desc_t *d, const void *tc_image, const float *lin, const float *y, const float *d_y,

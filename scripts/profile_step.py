@@ -43,6 +43,8 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60))
+print("==== host side (3 steps) ====")
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45, max_name_column_width=60))
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.start)
 busy = sum(e.time_range.end - e.time_range.start for e in ev)
