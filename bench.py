@@ -27,6 +27,10 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# stdout carries exactly one JSON line: NCCL's version / debug banner (printed on stdout when the box sets NCCL_DEBUG)
+# goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 
 METRIC = "train rays/sec (fwd+bwd)"
