@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off captures "
+                         "exactly the timed region; numbers printed under a profiler are not bench values)")
     ap.add_argument("--with-optimizer", action="store_true",
                     help="also run the fused Adam step (esr_nerf_b200.optimizer, SURVEY.md §8f row 3) inside the timed "
                          "step; NOT part of the metric BASELINE.json names (render step only), off by default")
@@ -421,11 +424,15 @@ def run_b200(a, rank, world, local_rank):
     launches0 = L.esr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    if a.profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(a.steps):
         step(batch)
     e1.record()
     sync_all()
+    if a.profiler_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = L.esr_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
@@ -448,11 +455,23 @@ def run_b200(a, rank, world, local_rank):
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         d2h = 0
 
+        pinned_out = {}
+
+        def to_host(name, t):
+            """device -> pinned host buffer on the current stream (buffers are reused; one synchronisation per step)"""
+            t = t.detach()
+            buf = pinned_out.get(name)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = pinned_out[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            return buf
+
         def e2e_step():
             b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             out, loss = step(b)
             keys = sorted(out) if a.stage == "eval" else ["srgb/rgb", "lin/rgb", "etc/alphainv_cum"]
-            res = [out[k].detach().cpu() for k in keys] + [loss.detach().cpu()]
+            res = [to_host(k, out[k]) for k in keys] + [to_host("loss", loss)]
+            torch.cuda.current_stream().synchronize()          # the step's results are on the host from here on
             return sum(r.numel() * r.element_size() for r in res)
 
         for _ in range(2):   # untimed: first use of the H2D / D2H staging buffers

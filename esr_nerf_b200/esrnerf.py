@@ -184,7 +184,12 @@ class ESRNeRF(VoxurfF):
             for g in (self.sdf, self.off_color, self.emo_color, self.brdf):
                 g.ensure_layout()
             sc = self._pbr_scene(self.near, True)
-            s = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, self.sdf.grid.detach())
+            # the uncertain-ray count rides along on the host read that sizes the M1 stream: the two boolean-mask
+            # outputs below then need no synchronisation of their own
+            um = uncert_masks.bool()
+            s, n_uncert = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, self.sdf.grid.detach(),
+                                      also_read=um.sum(dtype=torch.int32))
+            um_order = torch.argsort((~um).to(torch.uint8), stable=True)     # uncertain rays first, original order kept
             h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, s, None)
             m3 = s.m3
             pts = fused.sample_points(sc, rays_o, rays_d, s.h_ray, s.h_step)
@@ -220,8 +225,8 @@ class ESRNeRF(VoxurfF):
             "lin/pbr/off_hat": lts["off_hat"],
             "lin/pbr/emo": lts["emo"],
             "lin/pbr/emo_hat": lts["emo_hat"],
-            "etc/emit_uncert": emit_m[uncert_masks],
-            "etc/emit_cert": emit_m[~uncert_masks],
+            "etc/emit_uncert": emit_m[um_order[:n_uncert]],        # == emit_m[uncert_masks]  (esrnerf.py:840)
+            "etc/emit_cert": emit_m[um_order[n_uncert:]],          # == emit_m[~uncert_masks] (esrnerf.py:841)
             "etc/normal": exp_grad,
             "etc/normal_eps": exp_grad_eps,
             "etc/emit": emit,
