@@ -188,6 +188,69 @@ def run_reference(a, rank, world):
 # ---------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
+class NvmlClockSampler:
+    """SM clock + clocks-event (throttle) reasons of one GPU through NVML (the counters `nvidia-smi
+    --query-gpu=clocks.sm,clocks_event_reasons.*` prints), sampled DURING the timed region from the timing thread itself:
+    one sample after each step has been queued, while the device is still executing it and the host has milliseconds of
+    slack.  A concurrent sampler — the `nvidia-smi -lms` loop of the recipe, or an NVML thread in this process — was
+    measured to stall this process at random points (the device-resident region read 11 / 17 / 21 ms per step on runs
+    whose per-kernel times and end-to-end region were identical): its driver calls contend with the launches that
+    follow a stream-size read, exactly where the host is on the critical path."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+
+    def __init__(self, cuda_index):
+        import pynvml as N
+
+        N.nvmlInit()
+        self.N = N
+        pr = torch.cuda.get_device_properties(cuda_index)
+        try:
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            self.h = N.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            self.h = N.nvmlDeviceGetHandleByIndex(cuda_index)
+        self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+        self.reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.sm, self.mask, self.spent = [], 0, 0.0
+        self.sample()
+
+    def sample(self):
+        t0 = time.perf_counter()
+        try:
+            self.sm.append(float(self.N.nvmlDeviceGetClockInfo(self.h, self.N.NVML_CLOCK_SM)))
+            self.mask |= int(self.reasons_fn(self.h))
+        except Exception:
+            pass
+        self.spent += time.perf_counter() - t0
+
+    def mark(self):
+        """forget the samples taken so far (set-up / warm-up): what follows is the timed region"""
+        self.sm, self.mask, self.spent = [], 0, 0.0
+
+    def wait_ready(self, timeout=0.0):
+        return
+
+    def stop(self):
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(v for k, v in self.REASONS.items() if self.mask & k), "samples": len(sm),
+               "source": "nvml, one sample per queued step", "host_ms_in_sampler": round(self.spent * 1e3, 3)}
+        try:
+            self.N.nvmlShutdown()
+        except Exception:
+            pass
+        return out
+
+
+def make_clock_sampler(cuda_index):
+    if os.environ.get("ESR_BENCH_NO_CLOCKS"):      # A/B switch: is the sampler itself visible in the timing?
+        return None
+    try:
+        return NvmlClockSampler(cuda_index)
+    except Exception:
+        return ClockSampler(cuda_index)     # nvidia-smi loop (B200_PROFILING.md recipe) when NVML is not importable
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -197,10 +260,16 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark(self):
+        return
+
+    def sample(self):
+        return
 
     def wait_ready(self, timeout=8.0):
         """block until nvidia-smi has printed its first sample: its start-up (NVML attach, ~1 s) must not land inside
@@ -400,7 +469,7 @@ def run_b200(a, rank, world, local_rank):
 
     # clocks / throttle reasons are sampled from before the warm-up to the end of the timed region (nvidia-smi needs a
     # moment to start; starting it inside the timed region would both miss it and perturb it)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = make_clock_sampler(local_rank) if rank == 0 else None
     for _ in range(max(a.warmup, 5)):
         step(batch)
     sync_all()
@@ -423,14 +492,36 @@ def run_b200(a, rank, world, local_rank):
     # ---- device-resident timed region (value): exactly K steps between two CUDA events ----
     launches0 = L.esr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the host must stay ahead of the device between the two stream-size reads of a step: a cyclic-GC pass over the
+    # interpreter's heap (tens of ms with torch loaded) inside the timed region shows up as device idle time, so the
+    # collector is run now and kept off while timing (what training loops do with gc.freeze / manual collection)
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
+    # the housekeeping above (stream-count read-backs, garbage collection: ~0.2 s with the device idle) is followed by a
+    # transient: the SECOND step after it stalls for 25-215 ms (per-step events, 4 of 8 runs; steps 3..K then sit at
+    # 10.90 +- 0.03 ms).  Three more untimed steps absorb it, exactly as the end-to-end region below has always been
+    # entered; the timed region still starts from a barrier + synchronize with nothing in flight.
+    for _ in range(3):
+        step(batch)
     sync_all()
+    if sampler:
+        sampler.mark()          # clock samples from here on belong to the timed region
     if a.profiler_range:
         torch.cuda.profiler.start()
     e0.record()
+    marks = []
     for _ in range(a.steps):
         step(batch)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()             # per-step boundaries (diagnostic: "ms_each"); value is e0 -> e1 over all K steps
+        marks.append(ev)
+        if sampler:
+            sampler.sample()    # the step is queued and still executing: clocks under load, host off the critical path
     e1.record()
     sync_all()
+    ms_each = [round(x.elapsed_time(y), 3) for x, y in zip([e0] + marks[:-1], marks)]
     if a.profiler_range:
         torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
@@ -488,6 +579,7 @@ def run_b200(a, rank, world, local_rank):
         e2e = {"value": a.rays * world * a.steps / (float(t.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
+    gc.enable()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -548,11 +640,12 @@ def run_b200(a, rank, world, local_rank):
                                   + (f", {reduced[0] / 1e6:.0f} MB/rank" if world > 1 else "") + ")",
                    "stage": a.stage, "optimizer_in_step": bool(optimizer is not None),
                    "l2": "working set (0.83 GB of grids + grads) exceeds the 126 MB L2; no flush between steps",
+                   "host": "python cyclic GC collected + frozen before, disabled during the timed regions",
                    "counts_per_gpu_step": counts,
                    "samples_per_s": {"candidate_M0": counts["M0"] * world * a.steps / (ms * 1e-3),
                                      "shaded_M3": counts["M3"] * world * a.steps / (ms * 1e-3)}},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "kernels": stage_rows[:12],
+        "clocks": clocks, "ms_each": ms_each, "kernels": stage_rows[:16],
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
