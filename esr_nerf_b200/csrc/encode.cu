@@ -2,6 +2,8 @@
 // trilinear gathers + scatter-add), tone-map encode fwd/bwd, and the per-ray compositing fwd/bwd that
 // replaces torch_scatter.segment_coo.
 #include "common.cuh"
+#include <type_traits>
+
 #include "mlp_layout.cuh"
 
 using namespace esr;
@@ -176,10 +178,10 @@ struct RowWriter<float> {
   float *row;
   ESR_D RowWriter(float *b, int64_t r) : row(b + r * ESR_FEAT_DIM) {}
   ESR_D void finish() {}
-  template <int N>
-  ESR_D void put(int col0, const float (&v)[N]) {
+  template <int COL0, int N>
+  ESR_D void put(const float (&v)[N]) {
 #pragma unroll
-    for (int i = 0; i < N; i += 2) *reinterpret_cast<float2 *>(row + col0 + i) = make_float2(v[i], v[i + 1]);
+    for (int i = 0; i < N; i += 2) *reinterpret_cast<float2 *>(row + COL0 + i) = make_float2(v[i], v[i + 1]);
   }
   // second copy of the finished row with colour slot 0 replaced
   ESR_D void second(float *b, int64_t r, const float (&col)[6]) {
@@ -196,12 +198,12 @@ struct RowWriter<float> {
 template <int WIDTH>
 struct TiledRowWriter {
   uint32_t w[WIDTH / 2];
-  template <int N>
-  ESR_D void put(int col0, const float (&v)[N]) {
+  template <int COL0, int N>
+  ESR_D void put(const float (&v)[N]) {
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
       __nv_bfloat162 p = __floats2bfloat162_rn(v[i], v[i + 1]);
-      w[(col0 + i) >> 1] = *reinterpret_cast<uint32_t *>(&p);
+      w[(COL0 + i) >> 1] = *reinterpret_cast<uint32_t *>(&p);
     }
   }
   ESR_D void flush(__nv_bfloat16 *base, int64_t row) {
@@ -219,9 +221,45 @@ struct RowWriter<__nv_bfloat16> : TiledRowWriter<ESR_FEAT_DIM> {
   ESR_D RowWriter(__nv_bfloat16 *b, int64_t r) : base(b), row(r) {}
   ESR_D void finish() { flush(base, row); }
   ESR_D void second(__nv_bfloat16 *b, int64_t r, const float (&col)[6]) {
-    put(0, col);
+    put<0>(col);
     flush(b, r);
   }
+};
+// Same tiled bf16 row, written chunk by chunk as the columns arrive (puts come in increasing column order): only the
+// words of the chunk in progress stay in registers instead of the whole 48-word row — the register budget that lets
+// the fine-stage instantiation of k_encode_fwd run 10 blocks per SM instead of 8.
+template <bool SECOND>
+struct StreamRowWriter {
+  uint4 *b4, *b4b;       // b4b: the second copy of the row whose colour slot 0 (columns 0..5) holds `alt` (BRDF grid taps)
+  int64_t row;
+  uint32_t cur[4], alt[3];
+  ESR_D StreamRowWriter(__nv_bfloat16 *b, int64_t r) : b4(reinterpret_cast<uint4 *>(b)), b4b(nullptr), row(r) {}
+  ESR_D void set_second(__nv_bfloat16 *b, const float (&col)[6]) {
+    b4b = reinterpret_cast<uint4 *>(b);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(col[2 * i], col[2 * i + 1]);
+      alt[i] = *reinterpret_cast<uint32_t *>(&p);
+    }
+  }
+  template <int COL0, int N>
+  ESR_D void put(const float (&v)[N]) {
+    static_assert((COL0 & 1) == 0 && (N & 1) == 0, "column pairs");
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      const int wi = (COL0 + i) >> 1;
+      __nv_bfloat162 p = __floats2bfloat162_rn(v[i], v[i + 1]);
+      cur[wi & 3] = *reinterpret_cast<uint32_t *>(&p);
+      if ((wi & 3) == 3) {
+        const int64_t at = tiled_chunk_index(row, wi >> 2, ESR_FEAT_DIM / 8);
+        __stcs(b4 + at, make_uint4(cur[0], cur[1], cur[2], cur[3]));
+        if constexpr (SECOND)
+          __stcs(b4b + at, wi == 3 ? make_uint4(alt[0], alt[1], alt[2], cur[3]) : make_uint4(cur[0], cur[1], cur[2], cur[3]));
+      }
+    }
+  }
+  ESR_D void finish() {}
+  ESR_D void second(__nv_bfloat16 *, int64_t, const float (&)[6]) {}
 };
 
 // world position + ray index of stream sample j: recomputed from (ray, step) exactly as the march kernel does, or
@@ -242,7 +280,9 @@ ESR_D int sample_pos(const esr_scene_t &sc, const float *__restrict__ rays_o, co
 
 constexpr int COL_SDF = 12, COL_FEAT = 13, COL_NRM = 37, COL_XYZ = 49, COL_SIN = 52, COL_COS = 67, COL_VIEW = 82;
 
-template <typename OutT>
+// 8 blocks of 128 per SM (64 registers): measured 1.31 ms at config 2 against 1.37 / 1.47 ms for 10 / 12 blocks (48 / 40
+// registers spill 104 / 164 bytes); the whole-row writer at 8 blocks was 1.48 ms
+template <typename OutT, bool THIRD>
 __global__ void __launch_bounds__(ENC_THREADS, 8)
     k_encode_fwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
                  const float *__restrict__ rays_d, const float *__restrict__ viewdirs,
@@ -260,14 +300,20 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
   g.ix = world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx);
   g.iy = world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy);
   g.iz = world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz);
-  RowWriter<OutT> wr(feat, j);
+  constexpr bool STREAM = sizeof(OutT) == 2;   // bf16 rows leave chunk by chunk; f32 rows (strict path) row-major
+  typename std::conditional<STREAM, StreamRowWriter<THIRD>, RowWriter<OutT>>::type wr(feat, j);
 
   {  // colour grids (module.py:24-35), channels-last
     const Cell c = make_cell(g.ix, g.iy, g.iz);
+    if constexpr (THIRD && STREAM) {  // the BRDF copy of the row leaves together with the first one
+      float col3[6];
+      tapC<6>(third_grid, sc.gx, sc.gy, sc.gz, c, col3);
+      wr.set_second(reinterpret_cast<__nv_bfloat16 *>(feat2), col3);
+    }
     float col[12];
     tapC<6>(off_grid, sc.gx, sc.gy, sc.gz, c, col);
     tapC<6>(emo_grid, sc.gx, sc.gy, sc.gz, c, col + 6);
-    wr.put(0, col);
+    wr.template put<0>(col);
   }
   {  // sdf, 24 taps, 12 normal components, normalised xyz (voxurff.py:219-225)
     float v[40];
@@ -303,7 +349,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
     v[37] = __fdiv_rn(__fsub_rn(px, sc.xyz_min[0]), __fsub_rn(sc.xyz_max[0], sc.xyz_min[0]));
     v[38] = __fdiv_rn(__fsub_rn(py, sc.xyz_min[1]), __fsub_rn(sc.xyz_max[1], sc.xyz_min[1]));
     v[39] = __fdiv_rn(__fsub_rn(pz, sc.xyz_min[2]), __fsub_rn(sc.xyz_max[2], sc.xyz_min[2]));
-    wr.put(COL_SDF, v);
+    wr.template put<COL_SDF>(v);
     float sc30[30];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -313,7 +359,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
         sc30[c * 5 + f] = sinf(x);
         sc30[15 + c * 5 + f] = cosf(x);
       }
-    wr.put(COL_SIN, sc30);
+    wr.template put<COL_SIN>(sc30);
   }
   {  // view direction encoding (viewbase_pe = 1) + zero padding
     float v[14];
@@ -326,10 +372,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
     }
 #pragma unroll
     for (int c = 9; c < 14; ++c) v[c] = 0.f;
-    wr.put(COL_VIEW, v);
+    wr.template put<COL_VIEW>(v);
   }
   wr.finish();
-  if (third_grid) {  // same row with colour slot 0 taken from a third grid (BRDF grid, esrnerf.py:761-763)
+  if constexpr (THIRD && !STREAM) {  // same row with colour slot 0 taken from a third grid (BRDF grid, esrnerf.py:761-763)
     const Cell c = make_cell(g.ix, g.iy, g.iz);
     float col[6];
     tapC<6>(third_grid, sc.gx, sc.gy, sc.gz, c, col);
@@ -675,7 +721,7 @@ __global__ void __launch_bounds__(256)
   }
   if constexpr (sizeof(OutT) == 2) {
     TiledRowWriter<ESR_TFEAT_DIM> wr;
-    wr.put(0, v);
+    wr.put<0>(v);
     wr.flush(tfeat, j);
   } else {
 #pragma unroll
@@ -786,15 +832,18 @@ static int encode_fwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
   ESR_CHECK_ARG(!third_grid == !feat2);
   cudaStream_t st = (cudaStream_t)stream;
   ESR_STAGE("k_encode_fwd", st);
-  if (out_is_bf16)
-    k_encode_fwd<__nv_bfloat16><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,
-                                                               emo_color_grid, h_ray, h_step, h_sdf, m3,
-                                                               (__nv_bfloat16 *)feat, pts, third_grid,
-                                                               (__nv_bfloat16 *)feat2, save_fd);
-  else
-    k_encode_fwd<float><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,
-                                                       emo_color_grid, h_ray, h_step, h_sdf, m3, (float *)feat, pts,
-                                                       third_grid, (float *)feat2, save_fd);
+#define ESR_ENC_FWD(T, THIRD)                                                                                          \
+  k_encode_fwd<T, THIRD><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,       \
+                                                        emo_color_grid, h_ray, h_step, h_sdf, m3, (T *)feat, pts,      \
+                                                        third_grid, (T *)feat2, save_fd)
+  if (out_is_bf16) {
+    if (third_grid) ESR_ENC_FWD(__nv_bfloat16, true);
+    else ESR_ENC_FWD(__nv_bfloat16, false);
+  } else {
+    if (third_grid) ESR_ENC_FWD(float, true);
+    else ESR_ENC_FWD(float, false);
+  }
+#undef ESR_ENC_FWD
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
