@@ -27,9 +27,13 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-# stdout carries exactly one JSON line: NCCL's version / debug banner (printed on stdout when the box sets NCCL_DEBUG)
-# goes to stderr
+# stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there): keep a private handle on the real stdout for the JSON line and point fd 1 at stderr for
+# everything else in this process and its children.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import torch  # noqa: E402
 
@@ -182,7 +186,7 @@ def run_reference(a, rank, world):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -647,7 +651,7 @@ def run_b200(a, rank, world, local_rank):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "ms_each": ms_each, "kernels": stage_rows[:16],
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
