@@ -82,18 +82,20 @@ ESR_D MaskCls mask_cls_setup(const esr_scene_t &sc, const uint8_t *cls) {
   m.sz = (float)(sc.mz - 1) / (sc.mask_xyz_max[2] - sc.mask_xyz_min[2]);
   return m;
 }
+// class of the cell a point falls in: 1 keep, 2 drop, 0 = evaluate MaskCache.forward exactly
+ESR_D int mask_cls_lookup(const esr_scene_t &sc, const MaskCls &m, float px, float py, float pz) {
+  if (!m.cls) return 0;
+  const float fx = (px - sc.mask_xyz_min[0]) * m.sx, fy = (py - sc.mask_xyz_min[1]) * m.sy,
+              fz = (pz - sc.mask_xyz_min[2]) * m.sz;
+  const int i = (int)floorf(fx), j = (int)floorf(fy), k = (int)floorf(fz);
+  if ((unsigned)i < (unsigned)(sc.mx - 1) && (unsigned)j < (unsigned)(sc.my - 1) && (unsigned)k < (unsigned)(sc.mz - 1))
+    return __ldg(m.cls + ((int64_t)i * (sc.my - 1) + j) * (sc.mz - 1) + k);
+  return 0;
+}
 ESR_D bool mask_keep_cls(const esr_scene_t &sc, const MaskCls &m, const float *__restrict__ mask_density, float px,
                          float py, float pz) {
-  if (m.cls) {
-    const float fx = (px - sc.mask_xyz_min[0]) * m.sx, fy = (py - sc.mask_xyz_min[1]) * m.sy,
-                fz = (pz - sc.mask_xyz_min[2]) * m.sz;
-    const int i = (int)floorf(fx), j = (int)floorf(fy), k = (int)floorf(fz);
-    if ((unsigned)i < (unsigned)(sc.mx - 1) && (unsigned)j < (unsigned)(sc.my - 1) && (unsigned)k < (unsigned)(sc.mz - 1)) {
-      const uint8_t c = __ldg(m.cls + ((int64_t)i * (sc.my - 1) + j) * (sc.mz - 1) + k);
-      if (c) return c == 1;
-    }
-  }
-  return mask_keep(sc, mask_density, px, py, pz);
+  const int c = mask_cls_lookup(sc, m, px, py, pz);
+  return c ? c == 1 : mask_keep(sc, mask_density, px, py, pz);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -122,7 +124,31 @@ __global__ void __launch_bounds__(256)
     const int base = FILL ? off_mask[slot] : 0;
     uint32_t *bits = keep_bits ? keep_bits + slot * (int64_t)bits_stride : nullptr;
     int c_in = 0, c_mask = 0;
-    for (int k0 = 0; k0 < s.n; k0 += 32) {
+    if (!FILL) {
+      // count pass: two 32-candidate chunks per iteration, both class-table bytes requested before either is used
+      // (the loop is a chain of dependent L1/L2 loads; one chunk at a time left the issue slots idle)
+      for (int k0 = 0; k0 < s.n; k0 += 64) {
+        const int ka = k0 + (int)lane, kb = ka + 32;
+        float ax, ay, az, bx, by, bz;
+        ray_point(s, sc.stepdist, ka, ax, ay, az);
+        ray_point(s, sc.stepdist, kb, bx, by, bz);
+        const bool in_a = (ka < s.n) && !out_bbox(sc.xyz_min, sc.xyz_max, ax, ay, az);
+        const bool in_b = (kb < s.n) && !out_bbox(sc.xyz_min, sc.xyz_max, bx, by, bz);
+        const int ca = in_a ? mask_cls_lookup(sc, mc, ax, ay, az) : 2;
+        const int cb = in_b ? mask_cls_lookup(sc, mc, bx, by, bz) : 2;
+        const bool keep_a = ca ? ca == 1 : mask_keep(sc, mask_density, ax, ay, az);
+        const bool keep_b = cb ? cb == 1 : mask_keep(sc, mask_density, bx, by, bz);
+        const unsigned bal_a = __ballot_sync(FULL, keep_a), bal_b = __ballot_sync(FULL, keep_b);
+        c_in += __popc(__ballot_sync(FULL, in_a)) + __popc(__ballot_sync(FULL, in_b));
+        c_mask += __popc(bal_a) + __popc(bal_b);
+        const int chunk = k0 >> 5;
+        if (bits && lane == 0) {
+          if (chunk < bits_stride) bits[chunk] = bal_a;
+          if (chunk + 1 < bits_stride) bits[chunk + 1] = bal_b;
+        }
+      }
+    }
+    for (int k0 = 0; FILL && k0 < s.n; k0 += 32) {
       const int k = k0 + (int)lane;
       const int chunk = k0 >> 5;
       float px, py, pz;

@@ -232,8 +232,14 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
                         "srgb/on_rgb": z3, "lin/on_rgb": z3, "srgb/emo_rgb": z3, "lin/emo_rgb": z3, "srgb/rgb": z3,
                         "lin/rgb": z3}
             sdf_g, off_g, emo_g = self.sdf.grid.detach(), self.off_color.grid.detach(), self.emo_color.grid.detach()
+            grad = None
             if self.mlp_mode == "bf16":
-                x = fused.encode_features(sc, rays_o, rays_d, viewdirs, sdf_g, off_g, emo_g, s, bf16=True)
+                # the encode kernel already forms the finite-difference SDF gradients of all four displacements; the
+                # displacement-1.0 one IS sample_sdf_grad (voxurff.py:670-676), bit for bit (same taps, same divisions,
+                # fd_eps = 0), stored (z, y, x): no second 6-tap pass over the SDF grid for the normal map
+                x, fd = fused.encode_features(sc, rays_o, rays_d, viewdirs, sdf_g, off_g, emo_g, s, bf16=True, save_fd=True)
+                if sc.fd_eps == 0.0:
+                    grad = fd[:, [6, 5, 4]]
                 lin_off = fused.mlp_infer(fused.RADIANCE_DESC, self._flat("off").detach(), x, 0, s.m3, s.m3)
                 lin_emo = fused.mlp_infer(fused.RADIANCE_DESC, self._flat("emo").detach(), x, 0, s.m3, s.m3)
                 lin_on = lin_off + lin_emo
@@ -247,7 +253,8 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
             else:
                 raise ValueError(f"unknown mlp_mode {self.mlp_mode!r}")
             off_rgb, on_rgb, emo_rgb = srgb[: s.m3], srgb[s.m3: 2 * s.m3], srgb[2 * s.m3:]
-            grad = fused.sdf_fd_gradient(sc, rays_o, rays_d, sdf_g, s)
+            if grad is None:
+                grad = fused.sdf_fd_gradient(sc, rays_o, rays_d, sdf_g, s)
             normal = (F.normalize(grad, dim=-1) @ pos_rt * self.normal_flipper.to(dev) + 1.0) / 2.0
             dist = host_geometry(self, self.stepsize)["stepdist"]
             dvec = torch.zeros(s.m3, 3, device=dev)

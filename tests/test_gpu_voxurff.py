@@ -251,6 +251,16 @@ def test_forward_evaluate_vs_oracle_port(mode, em):
     for k in ref:
         assert out[k].shape == ref[k].shape, k
         assert C.rel_err(out[k], ref[k]) < tol, (k, C.rel_err(out[k], ref[k]))
+    if mode == "bf16":
+        # the normal map reuses the displacement-1.0 finite-difference gradient the encode kernel forms anyway: it must
+        # be sample_sdf_grad (voxurff.py:670-676) bit for bit
+        from esr_nerf_b200 import fused
+
+        sc = m._scene(float(fx["s_val"]))
+        ro, rd, vd = (rays[k].to(DEV) for k in ("rays_o", "rays_d", "viewdirs"))
+        grids = (m.sdf.grid.detach(), m.off_color.grid.detach(), m.emo_color.grid.detach())
+        _, fd = fused.encode_features(sc, ro, rd, vd, *grids, st, bf16=True, save_fd=True)
+        assert torch.equal(fd[:, [6, 5, 4]], fused.sdf_fd_gradient(sc, ro, rd, grids[0], st))
     m.train()
     assert m.forward == m.forward_training
 
