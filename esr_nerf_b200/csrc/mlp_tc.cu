@@ -304,14 +304,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
-  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
+  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8, bar_x = bar + 40;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
+  // the next tile's layer-0 MMA is issued behind this tile's output-layer MMA and runs under the output epilogue; it
+  // writes D0, which must then be the accumulator of the LAST hidden layer (read before bar_x), not of the output layer
+  static_assert(NH & 1, "odd number of hidden layers: the output accumulator lives in D1");
 
   stage_bytes(smem, image, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
+    mbar_init(bar_x, TC_EPI_WARPS);
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -322,6 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem = *tmem_slot;
   const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
   uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
+  uint32_t xphase = 0;   // parity of bar_x (issuer)
 
   const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
   const EpiThread et(warp, lane);
@@ -356,19 +361,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const bool valid = is_epi && row < row_end;
     const bool save = valid && hidden && row >= save_begin;  // rows the backward pass will visit
     // ---- layer 0: A = x tile (shared), B = W0 ----
-    if (is_epi) {
-      cp_async_wait_all();
-      fence_proxy_async();
+    const bool first = tile == (int64_t)blockIdx.x, more = tile + gridDim.x < n_tiles;
+    if (first) {   // later tiles: layer 0 was issued behind the previous tile's output layer (below)
+      if (is_epi) {
+        cp_async_wait_all();
+        fence_proxy_async();
+      }
+      tc_fence_before();
+      __syncthreads();
     }
-    tc_fence_before();
-    __syncthreads();
-    if (is_issuer && lane == 0) {
-      tc_fence_after();
+    auto issue_layer0 = [&]() {
 #pragma unroll
       for (int s = 0; s < K0 / 16; ++s)
         mma_ss(tmem + tm_d(0), make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
                make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
       mma_commit(bar);
+    };
+    if (is_issuer && lane == 0) {
+      if (first) {
+        tc_fence_after();
+        issue_layer0();
+      }
       // the rest of the chain: layer l + 1 (or the output layer) is fed chunk by chunk as the epilogue of layer l
       // produces its A operand; its accumulator is the D region layer l does not use
 #pragma unroll 1
@@ -390,6 +403,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         mma_commit(bar);
         cphase ^= 1;
+      }
+      if (more) {   // the next x tile has landed and every warp is done with D0: layer 0 of the next tile, now
+        mbar_wait(bar_x, xphase);
+        xphase ^= 1;
+        tc_fence_after();
+        issue_layer0();
       }
     }
     if (is_epi) {
@@ -435,6 +454,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
           mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
         }
+      }
+      if (more) {   // hidden layers done: the prefetched x tile is complete, D0 has been read -> release layer 0 of the next tile
+        cp_async_wait_all();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_x);
       }
       // ---- output layer epilogue (column group 0 threads) ----
       mbar_wait(bar, phase);
