@@ -184,7 +184,6 @@ class ESRNeRF(VoxurfF):
             for g in (self.sdf, self.off_color, self.emo_color, self.brdf):
                 g.ensure_layout()
             sc = self._pbr_scene(self.near, True)
-            fused.GRAD_SINK.prefetch((self.sdf.grid, self.off_color.grid, self.emo_color.grid, self.brdf.grid))
             # the uncertain-ray count rides along on the host read that sizes the M1 stream: the two boolean-mask
             # outputs below then need no synchronisation of their own
             um = uncert_masks.bool()

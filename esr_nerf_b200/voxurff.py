@@ -173,8 +173,6 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
             if self.mlp_mode == "bf16":
                 # weight prep is queued before the two stream-size host reads below so the GPU never waits for it
                 flat_off, flat_emo, flat_tone = self._flat("off"), self._flat("emo"), self._flat("tone")
-            # the dense grid-gradient buffers of the coming backward are zero-filled on a side stream meanwhile
-            fused.GRAD_SINK.prefetch((self.sdf.grid, self.off_color.grid, self.emo_color.grid))
             streams, n_on = self._streams(sc, rays_o, rays_d, em_modes)
             h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, streams, n_on)
             s = streams
