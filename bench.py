@@ -31,9 +31,15 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 # version banner there): keep a private handle on the real stdout for the JSON line and point fd 1 at stderr for
 # everything else in this process and its children.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-sys.stdout.flush()
-JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+JSON_OUT = sys.stdout
+
+
+def _claim_stdout():
+    """(bench.py run as a program only — scripts that import this module keep their stdout)"""
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 import torch  # noqa: E402
 
@@ -657,6 +663,7 @@ def run_b200(a, rank, world, local_rank):
 
 
 def main():
+    _claim_stdout()
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
