@@ -434,6 +434,8 @@ def run_b200(a, rank, world, local_rank):
     model.keep_streams = True
     params = [p for p in model.parameters() if p.requires_grad]
     compactor = GridGradCompactor(model) if (world > 1 and not a.dense_allreduce and a.stage == "fine") else None
+    if compactor is not None and not os.environ.get("ESR_NO_ALLREDUCE_OVERLAP"):
+        compactor.overlap_color_allreduce(True)
     reduced = [0]
     optimizer = None
     if a.with_optimizer and a.stage != "eval":

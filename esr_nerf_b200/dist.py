@@ -73,6 +73,30 @@ class GridGradCompactor:
         self.shape = tuple(model.sdf.grid.shape[2:])
         self.grids = [model.sdf.grid, model.off_color.grid, model.emo_color.grid]
         self._idx32 = None
+        self._early = None      # (work handle, packed buffer, gradient buffers) of a colour all-reduce already in flight
+        self.group = None
+
+    def overlap_color_allreduce(self, enable: bool = True, group=None):
+        """Start the colour-grid part of the exchange (12 of the 13 floats per voxel) from inside the backward pass, as
+        soon as the encode backward has produced it (fused.COLOR_GRADS_READY_HOOK), so that it overlaps the alpha-path
+        backward; allreduce() then only has the SDF grid and the MLP bucket left before it waits for it."""
+        from . import fused
+
+        self.group = group
+        fused.COLOR_GRADS_READY_HOOK = self._on_color_grads if enable else None
+
+    def _on_color_grads(self, bufs):
+        import torch.distributed as dist
+
+        params = self.grids[1:]
+        if self._early is not None or any(p.grad is not None for p in params) or any(p not in bufs for p in params):
+            return          # gradient accumulation across calls (or an unexpected graph): the exchange happens at the end
+        if not all(bufs[p].is_cuda for p in params):
+            return
+        rows = [self._rows(bufs[p]) for p in params]
+        buf = self.pack(rows)
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._early = (work, buf, [bufs[p] for p in params])
 
     @property
     def fraction(self) -> float:
@@ -149,6 +173,19 @@ class GridGradCompactor:
         grid_ids = {id(p) for p in self.grids}
         others = [p for p in self.model.parameters() if id(p) not in grid_ids]
         nbytes = allreduce_gradients(others, group)      # the small MLP bucket first: it is ready and tiny
+        early, self._early = self._early, None
+        if early is not None and all(p.grad is not None and p.grad.data_ptr() == b.data_ptr()
+                                     for p, b in zip(self.grids[1:], early[2])):
+            # the colour volumes are already on their way (started inside the backward pass): SDF grid now, then join
+            work, cbuf, _ = early
+            sbuf = self.pack(rows[:1])
+            dist.all_reduce(sbuf, op=dist.ReduceOp.SUM, group=group)
+            self.unpack(rows[:1], sbuf)
+            work.wait()
+            self.unpack(rows[1:], cbuf)
+            return nbytes + (sbuf.numel() + cbuf.numel()) * 4
+        if early is not None:
+            early[0].wait()     # the buffers it reduced are not the final gradients (accumulation): redo the exchange
         buf = self.pack(rows)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         self.unpack(rows, buf)

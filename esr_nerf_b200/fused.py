@@ -99,6 +99,11 @@ class _GradSink:
 
 GRAD_SINK = _GradSink()
 
+# Multi-GPU: called by Shade.backward as soon as the colour-grid gradients of the step are final (its encode backward
+# is the only kernel that writes them), with {parameter: gradient buffer}.  dist.GridGradCompactor uses it to start their
+# all-reduce while the alpha-path backward (k_alpha_scan_bwd, k_sdf_scatter) still runs.  None = no hook.
+COLOR_GRADS_READY_HOOK = None
+
 
 def _grad_target(param: Optional[torch.Tensor], like: torch.Tensor):
     """(buffer to scatter into, value to return to autograd) for a grid input of a backward"""
@@ -451,6 +456,9 @@ class Shade(torch.autograd.Function):
         ctx.hidden = None
         g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x,
                                                 ctx.grid_params, fd)
+        if COLOR_GRADS_READY_HOOK is not None and g_offc is None and g_emoc is None:   # both went to the gradient sink
+            p_off, p_emo = ctx.grid_params[1], ctx.grid_params[2]
+            COLOR_GRADS_READY_HOOK({p_off: GRAD_SINK.get(p_off), p_emo: GRAD_SINK.get(p_emo)})
         return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None
 
 
