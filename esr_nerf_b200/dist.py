@@ -94,7 +94,7 @@ class GridGradCompactor:
         if not all(bufs[p].is_cuda for p in params):
             return
         rows = [self._rows(bufs[p]) for p in params]
-        buf = self.pack(rows)
+        buf = self.pack(rows, "_cbuf")
         work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._early = (work, buf, [bufs[p] for p in params])
 
@@ -121,7 +121,16 @@ class GridGradCompactor:
             rows.append(self._rows(p.grad))
         return rows
 
-    def pack(self, rows) -> torch.Tensor:
+    def _persistent(self, name: str, n: int, device) -> torch.Tensor:
+        """exchange buffers are allocated once: a buffer handed to an asynchronous NCCL call is tied to NCCL's stream by
+        the caching allocator, and re-allocating it every step can miss the cache (a cudaMalloc inside the step)"""
+        buf = self.__dict__.get(name)
+        if buf is None or buf.numel() != n or buf.device != device:
+            buf = torch.empty(n, dtype=torch.float32, device=device)
+            self.__dict__[name] = buf
+        return buf
+
+    def pack(self, rows, out_name: str = None) -> torch.Tensor:
         """dense gradient volumes -> one packed buffer (CUDA: one launch of esr_grad_pack, planar blocks [K][C_j];
         host tensors of the gloo tests: the same layout with torch indexing)"""
         chans = [r.shape[1] for r in rows]
@@ -138,7 +147,8 @@ class GridGradCompactor:
             c_arr = (ctypes.c_int32 * len(rows))(*chans)
             v_arr = (ctypes.c_void_p * len(rows))(*[r.data_ptr() for r in rows])
             n = int(L.esr_grad_pack_floats(c_arr, len(rows), k))
-            buf = torch.empty(n, dtype=torch.float32, device=rows[0].device)
+            buf = (self._persistent(out_name, n, rows[0].device) if out_name
+                   else torch.empty(n, dtype=torch.float32, device=rows[0].device))
             check(L.esr_grad_pack(v_arr, c_arr, len(rows), ptr(self._idx32), k, ptr(buf), stream_ptr()))
             return buf
         blocks = []
@@ -178,7 +188,7 @@ class GridGradCompactor:
                                      for p, b in zip(self.grids[1:], early[2])):
             # the colour volumes are already on their way (started inside the backward pass): SDF grid now, then join
             work, cbuf, _ = early
-            sbuf = self.pack(rows[:1])
+            sbuf = self.pack(rows[:1], "_sbuf")
             dist.all_reduce(sbuf, op=dist.ReduceOp.SUM, group=group)
             self.unpack(rows[:1], sbuf)
             work.wait()
@@ -186,7 +196,7 @@ class GridGradCompactor:
             return nbytes + (sbuf.numel() + cbuf.numel()) * 4
         if early is not None:
             early[0].wait()     # the buffers it reduced are not the final gradients (accumulation): redo the exchange
-        buf = self.pack(rows)
+        buf = self.pack(rows, "_abuf")
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         self.unpack(rows, buf)
         return nbytes + buf.numel() * buf.element_size()

@@ -39,7 +39,8 @@ def _worker(rank, world, port, out):
     model = C.build_product_model(fx, weights, str(dev))
     n = 4096
     batch = {k: v.to(dev) for k, v in D.shard_batch(S.make_rays(n, 21), rank, world).items()}
-    cot = {k: v.to(dev) for k, v in D.shard_batch(C.cotangents(n), rank, world).items()}
+    sl = D.shard_slice(n, rank, world)
+    cot = {k: v[sl].to(dev) for k, v in C.cotangents(n).items()}
     params = [p for p in model.parameters() if p.requires_grad]
 
     def local_backward():
@@ -48,22 +49,38 @@ def _worker(rank, world, port, out):
         o = model(s_val=float(fx["s_val"]), **batch)
         sum((o[k] * cot[k]).sum() for k in cot).backward()
 
-    # reference: dense all-reduce of every gradient
+    # local gradients once (the kernels accumulate with float REDs: a second backward differs in the last bits)
     fused.COLOR_GRADS_READY_HOOK = None
     local_backward()
+    local = [p.grad.clone() for p in params]
+    # reference: dense all-reduce of every gradient
     D.allreduce_gradients(params)
     ref = [p.grad.clone() for p in params]
+    comp = D.GridGradCompactor(model)
+    color = comp.grids[1:]
     worst = 0.0
-    for overlap in (False, True):
-        comp = D.GridGradCompactor(model)
-        comp.overlap_color_allreduce(overlap)
-        local_backward()
-        assert (comp._early is not None) == overlap
-        comp.allreduce(verify=not overlap)
+    for overlap in (False, True):   # same local gradients through the compacted exchange: bit-exact
+        for p, g in zip(params, local):
+            p.grad = None if (overlap and any(p is c for c in color)) else g.clone()
+        if overlap:                 # what Shade.backward does when the colour gradients are final
+            bufs = {p: g.clone() for p, g in zip(params, local) if any(p is c for c in color)}
+            comp._on_color_grads(bufs)
+            assert comp._early is not None
+            for p in color:
+                p.grad = bufs[p]
+        comp.allreduce(verify=True)
         assert comp._early is None
         for p, r in zip(params, ref):
             assert torch.equal(p.grad, r), (overlap, tuple(p.shape))
-            worst = max(worst, float((p.grad - r).abs().max()))
+    # and inside autograd: the hook fires from the backward pass, the result matches within the REDs' reordering
+    comp.overlap_color_allreduce(True)
+    local_backward()
+    assert comp._early is not None
+    comp.allreduce()
+    for p, r in zip(params, ref):
+        err = float((p.grad - r).abs().max()) / (float(r.abs().max()) + 1e-30)
+        assert err < 1e-3, (tuple(p.shape), err)      # bf16-MLP gradients: RED order + tensor-core split-K order
+        worst = max(worst, err)
     fused.COLOR_GRADS_READY_HOOK = None
     if rank == 0:
         out.put(worst)
@@ -82,4 +99,4 @@ def test_compacted_and_overlapped_allreduce_equal_dense_allreduce():
     for p in procs:
         p.join(300)
         assert p.exitcode == 0
-    assert out.get(timeout=5) == 0.0
+    assert out.get(timeout=5) < 1e-3
