@@ -1,0 +1,84 @@
+"""CPU tests of the host-side logic around the C ABI (no compute calls): cached scene geometry, flat parameter
+assembly of the tensor-core MLPs (layout + gradient routing)."""
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from esr_nerf_b200 import modules as M
+
+
+def test_host_geometry_cache_follows_tensor_identity_and_version():
+    o = types.SimpleNamespace(xyz_min=torch.tensor([-1.0, -1.0, -1.0]), xyz_max=torch.tensor([1.0, 1.0, 1.0]),
+                              mask_xyz_min=torch.tensor([-1.0, -1.0, -1.0]), mask_xyz_max=torch.tensor([1.0, 1.0, 1.0]),
+                              voxel_size=torch.tensor(0.02))
+    a = M.host_geometry(o, 0.5)
+    assert a["xyz_min"] == [-1.0, -1.0, -1.0] and a["stepdist"] == float(0.5 * o.voxel_size)
+    assert M.host_geometry(o, 0.5) is a                      # cached: no read-back per call
+    o.voxel_size = torch.tensor(0.01)                        # set_grid_resolution: a new tensor
+    b = M.host_geometry(o, 0.5)
+    assert b is not a and b["voxel_size"] == float(torch.tensor(0.01))
+    o.xyz_max.mul_(2.0)                                      # in-place edit (load_state_dict): version bump
+    c = M.host_geometry(o, 0.5)
+    assert c["xyz_max"] == [2.0, 2.0, 2.0]
+    assert M.host_geometry(o, 0.25)["stepdist"] == float(0.25 * o.voxel_size)
+
+
+def _reference_flat(layers, cols, k0):
+    """the flat image spelt out with differentiable torch ops: per layer W then b, layer-0 columns permuted (zero
+    column for unused inputs), output layer padded to 8 rows"""
+    n_ref = layers[0].in_features
+    idx = torch.where(cols < 0, torch.full_like(cols, n_ref), cols)
+    parts = []
+    for i, lin in enumerate(layers):
+        w, b = lin.weight, lin.bias
+        if i == 0:
+            w = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).index_select(1, idx)
+        if i + 1 == len(layers):
+            w, b = F.pad(w, (0, 0, 0, 8 - w.shape[0])), F.pad(b, (0, 8 - b.shape[0]))
+        parts += [w.reshape(-1), b]
+    return torch.cat(parts)
+
+
+def test_flat_params_layout_and_gradient_routing():
+    torch.manual_seed(0)
+    for kind, k0, dims in (("off", 96, (85, 192, 192, 192, 3)), ("emo", 96, (85, 192, 192, 192, 3)), ("tone", 48, (33, 192, 3))):
+        layers = [nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])]
+        cols = M.tonemap_in_cols("cpu") if kind == "tone" else M.radiance_in_cols(kind, "cpu")
+        ref = _reference_flat(layers, cols, k0)
+        g = torch.randn_like(ref)
+        (ref * g).sum().backward()
+        want = [p.grad.clone() for l in layers for p in (l.weight, l.bias)]
+        for l in layers:
+            l.zero_grad()
+        got = M.flat_mlp_params(layers, kind, k0)
+        assert torch.equal(got, ref.detach())
+        (got * g).sum().backward()
+        for p, w in zip([p for l in layers for p in (l.weight, l.bias)], want):
+            assert torch.equal(p.grad, w)
+
+
+def test_padded_flat_params_match_zero_padding():
+    torch.manual_seed(1)
+    for kind, n_out in (("emit", 3), ("brdf", 5)):
+        layers = [nn.Linear(76, 128), nn.Linear(128, 128), nn.Linear(128, 128), nn.Linear(128, n_out)]
+        cols = M.pbr_in_cols(kind, "cpu")
+        idx = torch.where(cols < 0, torch.full_like(cols, 76), cols)
+        parts = []
+        for i, lin in enumerate(layers):
+            w, b = lin.weight, lin.bias
+            w = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).index_select(1, idx) if i == 0 else F.pad(w, (0, 192 - w.shape[1]))
+            rows = 8 if i == 3 else 192
+            parts += [F.pad(w, (0, 0, 0, rows - w.shape[0])).reshape(-1), F.pad(b, (0, rows - b.shape[0]))]
+        ref = torch.cat(parts)
+        g = torch.randn_like(ref)
+        (ref * g).sum().backward()
+        want = [p.grad.clone() for l in layers for p in (l.weight, l.bias)]
+        for l in layers:
+            l.zero_grad()
+        got = M.flat_mlp_params_padded(layers, kind)
+        assert torch.equal(got, ref.detach())
+        (got * g).sum().backward()
+        for p, w in zip([p for l in layers for p in (l.weight, l.bias)], want):
+            assert torch.equal(p.grad, w)
