@@ -671,15 +671,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
-  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
+  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8, bar_x = bar + 40;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
   uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
+  uint32_t xphase = 0;   // parity of bar_x (issuer)
+  // as in the forward chain: the next tile's first MMA (dZ_out W_o -> D0) is issued behind this tile's last MMA and
+  // runs under the d_x epilogue; D0 must then be the accumulator of the last chain step, not of d_x
+  static_assert(NH & 1, "odd number of hidden layers: the d_x accumulator lives in D1");
 
   stage_bytes(smem, image_bwd, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
+    mbar_init(bar_x, TC_EPI_WARPS);
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -716,6 +721,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int l = 0; l < NH; ++l)
       pf_mask[l] = ok ? __ldg(mask_base + act_mask_index(l, act_rows_padded(m_total), row, et.grp)) : make_uint2(0, 0);
   };
+  // dZ_out = d_y * act'(y) of tile `tl` from the prefetched (y, d_y): A tile of the chain's first MMA (column group 0)
+  auto make_dz = [&](int64_t tl) {
+    const int64_t row = row_begin + tl * TC_TM + t;
+    const bool valid = row < row_end;
+    float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < NO; ++c)
+        if (c < n_out) {
+          const float yy = pf_y[c];
+          dz[c] = pf_dy[c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
+        }
+      if (d_z_out) {
+        *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+        *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
+      }
+    }
+    const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
+    if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
+      uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
+      zo[tiled_chunk_index(row, 0, 2)] = dz16;
+      zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
+    fence_proxy_async();
+  };
   prefetch(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -735,38 +766,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column group 0 threads) ----
-    if (is_epi && et.grp == 0) {
-      float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < NO; ++c)
-          if (c < n_out) {
-            const float yy = pf_y[c];
-            dz[c] = pf_dy[c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
-          }
-        if (d_z_out) {
-          *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], dz[3]);
-          *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
-        }
-      }
-      const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
-      if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
-        uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
-        zo[tiled_chunk_index(row, 0, 2)] = dz16;
-        zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
-      fence_proxy_async();
-    }
+    // ---- dZ_out tile of the first MMA: made here for the CTA's first tile, under the previous tile's chain otherwise ----
+    const bool first = tile == (int64_t)blockIdx.x, more = tile + gridDim.x < n_tiles;
+    if (first && is_epi && et.grp == 0) make_dz(tile);
     prefetch(tile + gridDim.x);
-    tc_fence_before();
-    __syncthreads();
-    if (is_issuer && lane == 0) {
-      tc_fence_after();
+    if (first) {
+      tc_fence_before();
+      __syncthreads();
+    }
+    auto issue_first = [&]() {
       mma_ss(tmem + tm_d(0), make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
              make_idesc(TC_W), 0);
       mma_commit(bar);
+    };
+    if (is_issuer && lane == 0) {
+      if (first) {
+        tc_fence_after();
+        issue_first();
+      }
       // chain step i handles layer l = NH - 1 - i: its accumulator is D region i & 1, the MMA it feeds (W_l^T, or
       // W_0^T -> d_x for l == 0) accumulates in the other region, chunk by chunk (see chunk_ready)
 #pragma unroll 1
@@ -788,6 +805,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         mma_commit(bar);
         cphase ^= 1;
+      }
+      if (more) {   // next tile's dZ_out is in shared memory and every warp is done with D0
+        mbar_wait(bar_x, xphase);
+        xphase ^= 1;
+        tc_fence_after();
+        issue_first();
       }
     }
     if (is_epi) {
@@ -824,6 +847,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           chunk_ready(bar_chunk + 8 * cc, lane);
         }
+      }
+      if (more) {   // chain epilogues done (D0 read): hand the next tile's dZ_out (prefetched y, d_y) to the issuer
+        if (et.grp == 0) make_dz(tile + gridDim.x);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_x);
       }
       // ---- d_x epilogue: one 16-column group per epilogue column group ----
       mbar_wait(bar, phase);
