@@ -153,6 +153,7 @@ class Streams:
     h_step: Optional[torch.Tensor] = None
     h_m1: Optional[torch.Tensor] = None
     h_sdf: Optional[torch.Tensor] = None
+    aux: object = None          # result of march(between=...)
 
 
 def march_count(sc: Scene, rays_o, rays_d, mask_density):
@@ -186,16 +187,20 @@ def mask_class_table(sc: Scene, mask_density: torch.Tensor) -> torch.Tensor:
     return cls
 
 
-def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_read=None):
+def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_read=None, between=None):
     """Stages A/B.  One host read (M1) sizes the stream buffers — the reference syncs at the same
     point (render_utils_kernel.cu:212) and four more times before shading.  `also_read` (optional 0-dim integer device
-    tensor, e.g. the emission-on ray count) rides along on that read: returns (streams, int(also_read))."""
+    tensor, e.g. the emission-on ray count) rides along on that read: returns (streams, int(also_read)).  `between`
+    (optional callable) runs on the host after the count pass has been queued and before the read blocks — work that
+    only queues small kernels (weight prep) goes there, so that after a step-end synchronisation the device starts
+    marching at once instead of waiting for that host code; its result is stored in streams.aux."""
     L = _lib.lib()
     dev = rays_o.device
     n = rays_o.shape[0]
     if n == 0:  # no rays (e.g. an LTS segment without points): empty streams, no launch
         z = torch.zeros(1, dtype=torch.int32, device=dev)
         empty = Streams(0, ray_order, _i32(0, dev), _i32(0, dev), z, 0, _i32(0, dev), _i32(0, dev), _f32(0, dev=dev))
+        empty.aux = between() if between is not None else None
         return empty if also_read is None else (empty, int(also_read))
     n_steps, cnt_in, cnt_mask = _i32(n, dev), _i32(n, dev), _i32(n, dev)
     st = stream_ptr()
@@ -209,6 +214,7 @@ def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_rea
     check(L.esr_march_count_bits(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(n_steps),
                                  ptr(cnt_in), ptr(cnt_mask), ptr(bits), stride, ptr(cls), st))
     off_mask = exclusive_scan(cnt_mask)
+    aux = between() if between is not None else None
     if also_read is None:
         m1, extra = int(off_mask[n].item()), None
     else:
@@ -217,6 +223,7 @@ def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_rea
     check(L.esr_march_fill_bits(scp, ptr(rays_o), ptr(rays_d), ptr(ray_order), n, ptr(mask_density), ptr(sdf_grid),
                                 ptr(off_mask), ptr(s_ray), ptr(s_step), ptr(s_sdf), ptr(bits), stride, st))
     streams = Streams(n, ray_order, n_steps, cnt_in, off_mask, m1, s_ray, s_step, s_sdf)
+    streams.aux = aux
     return streams if also_read is None else (streams, extra)
 
 

@@ -146,7 +146,7 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
         net = self.off_rgbnet if which == "off" else self.emo_rgbnet
         return flat_mlp_params(net.layers(), which, 96)
 
-    def _streams(self, sc, rays_o, rays_d, em_modes):
+    def _streams(self, sc, rays_o, rays_d, em_modes, between=None):
         n = rays_o.shape[0]
         order, n_on = None, None
         if self.on_first_order and em_modes is not None and em_modes.dim() == 1:
@@ -156,9 +156,11 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
         for g in (self.sdf, self.off_color, self.emo_color):
             g.ensure_layout()
         if n_on is None:
-            return fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach()), None
+            return fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach(),
+                               between=between), None
         # the emission-on ray count reaches the host on the read that sizes the M1 stream (no extra synchronisation)
-        return fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach(), also_read=n_on)
+        return fused.march(sc, rays_o, rays_d, order, self.mask_cache.density, self.sdf.grid.detach(), also_read=n_on,
+                           between=between)
 
     def forward_training(self, **kwargs) -> Dict[str, torch.Tensor]:
         """voxurff.py:177-278"""
@@ -170,10 +172,12 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
         N = rays_o.shape[0]
         with torch.cuda.device(rays_o.device):
             sc = self._scene(float(self.s_val))
-            if self.mlp_mode == "bf16":
-                # weight prep is queued before the two stream-size host reads below so the GPU never waits for it
-                flat_off, flat_emo, flat_tone = self._flat("off"), self._flat("emo"), self._flat("tone")
-            streams, n_on = self._streams(sc, rays_o, rays_d, em_modes)
+            # weight prep is queued after the march count pass and before the stream-size host read that follows it:
+            # the GPU never waits for it, and after a step-end synchronisation it starts marching at once
+            prep = (lambda: (self._flat("off"), self._flat("emo"), self._flat("tone"))) if self.mlp_mode == "bf16" else None
+            streams, n_on = self._streams(sc, rays_o, rays_d, em_modes, between=prep)
+            if prep is not None:
+                flat_off, flat_emo, flat_tone = streams.aux
             h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, streams, n_on)
             s = streams
             if self.mlp_mode == "bf16":
