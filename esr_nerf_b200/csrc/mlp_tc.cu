@@ -144,6 +144,13 @@ ESR_D uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
 }
+// relu(lo), relu(hi) -> packed bf16 pair in ONE conversion instruction (cvt.rn.relu: negative inputs and -0 give +0,
+// so clamping before or after the rounding is the same value); the epilogues issue it 24 times per thread per layer
+ESR_D uint32_t pack2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 ESR_D float lo16(uint32_t v) { return __uint_as_float(v << 16); }
 ESR_D float hi16(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           for (int j = 0; j < 8; ++j) {
             const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
             const float z0 = __uint_as_float(r[cc][2 * j]) + bb.x, z1 = __uint_as_float(r[cc][2 * j + 1]) + bb.y;
-            p[j] = pack2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+            p[j] = pack2_relu(z0, z1);
             // mask of the STORED activation (test the rounded word so forward and backward agree), 3 integer ops per
             // pair: a non-zero non-negative bf16 half plus 0x7fff carries into its top bit (halves are <= 0x7f80, so
             // the low half never carries into the high one); the two top bits land on mask bits (s, 16 + s),
@@ -629,7 +636,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
-          p[j] = pack2(fmaxf(__uint_as_float(r[cc][2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(r[cc][2 * j + 1]) + bb.y, 0.f));
+          p[j] = pack2_relu(__uint_as_float(r[cc][2 * j]) + bb.x, __uint_as_float(r[cc][2 * j + 1]) + bb.y);
         }
         tmem_st8(tmem + et.lane_base + 192 * s + col0 / 2, p);
       }
@@ -1204,7 +1211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
-          p[j] = pack2(fmaxf(__uint_as_float(r[cc][2 * j]) + bb.x, 0.f), fmaxf(__uint_as_float(r[cc][2 * j + 1]) + bb.y, 0.f));
+          p[j] = pack2_relu(__uint_as_float(r[cc][2 * j]) + bb.x, __uint_as_float(r[cc][2 * j + 1]) + bb.y);
           const uint32_t tt = p[j] + 0x7fff7fffu;
           mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (0x00010001u << (8 * (cc & 1) + j));
         }
