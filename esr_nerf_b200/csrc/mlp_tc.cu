@@ -151,6 +151,13 @@ ESR_D uint32_t pack2_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// (a0, a1) += (b.x, b.y) as one packed FADD2 (add.rn.f32x2, sm_100): the bias add of a column pair
+ESR_D void add2(float &a0, float &a1, float2 b) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b.x), "f"(b.y));
+}
 ESR_D float lo16(uint32_t v) { return __uint_as_float(v << 16); }
 ESR_D float hi16(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
@@ -440,7 +447,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
-            const float z0 = __uint_as_float(r[cc][2 * j]) + bb.x, z1 = __uint_as_float(r[cc][2 * j + 1]) + bb.y;
+            float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
+            add2(z0, z1, bb);
             p[j] = pack2_relu(z0, z1);
             // mask of the STORED activation (test the rounded word so forward and backward agree), 3 integer ops per
             // pair: a non-zero non-negative bf16 half plus 0x7fff carries into its top bit (halves are <= 0x7f80, so
@@ -636,7 +644,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
-          p[j] = pack2_relu(__uint_as_float(r[cc][2 * j]) + bb.x, __uint_as_float(r[cc][2 * j + 1]) + bb.y);
+          float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
+          add2(z0, z1, bb);
+          p[j] = pack2_relu(z0, z1);
         }
         tmem_st8(tmem + et.lane_base + 192 * s + col0 / 2, p);
       }
@@ -1211,7 +1221,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
-          p[j] = pack2_relu(__uint_as_float(r[cc][2 * j]) + bb.x, __uint_as_float(r[cc][2 * j + 1]) + bb.y);
+          float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
+          add2(z0, z1, bb);
+          p[j] = pack2_relu(z0, z1);
           const uint32_t tt = p[j] + 0x7fff7fffu;
           mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (0x00010001u << (8 * (cc & 1) + j));
         }
