@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool valid = is_epi && row < row_end;
     const bool save = valid && hidden && row >= save_begin;  // rows the backward pass will visit
+    const bool save_w = __any_sync(FULL, save);               // warp-uniform (the issuer warp: false)
     // ---- layer 0: A = x tile (shared), B = W0 ----
     const bool first = tile == (int64_t)blockIdx.x, more = tile + gridDim.x < n_tiles;
     if (first) {   // later tiles: layer 0 was issued behind the previous tile's output layer (below)
@@ -453,10 +454,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // mask of the STORED activation (test the rounded word so forward and backward agree), 3 integer ops per
             // pair: a non-zero non-negative bf16 half plus 0x7fff carries into its top bit (halves are <= 0x7f80, so
             // the low half never carries into the high one); the two top bits land on mask bits (s, 16 + s),
-            // s = 8 (cc & 1) + j  (mlp_layout.cuh)
-            const uint32_t t = p[j] + 0x7fff7fffu;
-            constexpr uint32_t one2 = 0x00010001u;
-            mask[cc >> 1] |= (t >> (15 - 8 * (cc & 1) - j)) & (one2 << (8 * (cc & 1) + j));
+            // s = 8 (cc & 1) + j  (mlp_layout.cuh).  A third of the epilogue's instructions: skipped by warps none of
+            // whose rows is saved (inference; the off net's emission-on rows)
+            if (save_w) {
+              const uint32_t t = p[j] + 0x7fff7fffu;
+              constexpr uint32_t one2 = 0x00010001u;
+              mask[cc >> 1] |= (t >> (15 - 8 * (cc & 1) - j)) & (one2 << (8 * (cc & 1) + j));
+            }
           }
           tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (save) {  // the warp's 32 rows write 512 contiguous bytes per chunk (issued under the TMEM store latency)
