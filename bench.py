@@ -502,7 +502,6 @@ def run_b200(a, rank, world, local_rank):
                       encode_bwd_rows=fused.STATS["encode_rows"])
 
     # ---- device-resident timed region (value): exactly K steps between two CUDA events ----
-    launches0 = L.esr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # the host must stay ahead of the device between the two stream-size reads of a step: a cyclic-GC pass over the
     # interpreter's heap (tens of ms with torch loaded) inside the timed region shows up as device idle time, so the
@@ -518,6 +517,7 @@ def run_b200(a, rank, world, local_rank):
     for _ in range(3):
         step(batch)
     sync_all()
+    launches0 = L.esr_launch_count()
     if sampler:
         sampler.mark()          # clock samples from here on belong to the timed region
     if a.profiler_range:
