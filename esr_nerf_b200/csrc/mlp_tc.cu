@@ -158,6 +158,14 @@ ESR_D void add2(float &a0, float &a1, float2 b) {
       : "+f"(a0), "+f"(a1)
       : "f"(b.x), "f"(b.y));
 }
+// 0xffff per half of a packed bf16 pair whose ReLU-mask bit is set: bits (j, 16 + j) of `mk` are moved onto the sign
+// positions of bytes 0 and 2 (shift), then PRMT replicates those signs over bytes (0,1) and (2,3) — two instructions
+// instead of shift + and + multiply
+ESR_D uint32_t pair_mask(uint32_t mk, int j) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(d) : "r"(mk << (7 - j)));
+  return d;
+}
 ESR_D float lo16(uint32_t v) { return __uint_as_float(v << 16); }
 ESR_D float hi16(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
@@ -860,7 +868,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           uint32_t p[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)   // 0xffff per live half: AND on the packed pair instead of two selects
-            p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & (((mk >> j) & 0x00010001u) * 0xffffu);
+            p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & pair_mask(mk, j);
           tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (valid) {
             zl[act_chunk_index(row, col0 / 8)] = make_uint4(p[0], p[1], p[2], p[3]);
@@ -1267,7 +1275,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         uint32_t p[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & (((mk >> j) & 0x00010001u) * 0xffffu);
+          p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & pair_mask(mk, j);
         tmem_st8(tmem + et.lane_base + TMB_A + col0 / 2, p);
         *reinterpret_cast<uint4 *>(smem + S::zs + (col0 / 8) * (TC_TM * 16) + t * 16) = make_uint4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<uint4 *>(smem + S::zs + (col0 / 8 + 1) * (TC_TM * 16) + t * 16) = make_uint4(p[4], p[5], p[6], p[7]);
