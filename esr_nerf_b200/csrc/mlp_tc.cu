@@ -326,18 +326,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
-  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8, bar_x = bar + 40;
+  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
-  // the next tile's layer-0 MMA is issued behind this tile's output-layer MMA and runs under the output epilogue; it
-  // writes D0, which must then be the accumulator of the LAST hidden layer (read before bar_x), not of the output layer
-  static_assert(NH & 1, "odd number of hidden layers: the output accumulator lives in D1");
 
   stage_bytes(smem, image, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
-    mbar_init(bar_x, TC_EPI_WARPS);
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -348,7 +344,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem = *tmem_slot;
   const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
   uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
-  uint32_t xphase = 0;   // parity of bar_x (issuer)
 
   const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
   const EpiThread et(warp, lane);
@@ -384,27 +379,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const bool save = valid && hidden && row >= save_begin;  // rows the backward pass will visit
     const bool save_w = __any_sync(FULL, save);               // warp-uniform (the issuer warp: false)
     // ---- layer 0: A = x tile (shared), B = W0 ----
-    const bool first = tile == (int64_t)blockIdx.x, more = tile + gridDim.x < n_tiles;
-    if (first) {   // later tiles: layer 0 was issued behind the previous tile's output layer (below)
-      if (is_epi) {
-        cp_async_wait_all();
-        fence_proxy_async();
-      }
-      tc_fence_before();
-      __syncthreads();
+    if (is_epi) {
+      cp_async_wait_all();
+      fence_proxy_async();
     }
-    auto issue_layer0 = [&]() {
+    tc_fence_before();
+    __syncthreads();
+    if (is_issuer && lane == 0) {
+      tc_fence_after();
 #pragma unroll
       for (int s = 0; s < K0 / 16; ++s)
         mma_ss(tmem + tm_d(0), make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
                make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
       mma_commit(bar);
-    };
-    if (is_issuer && lane == 0) {
-      if (first) {
-        tc_fence_after();
-        issue_layer0();
-      }
       // the rest of the chain: layer l + 1 (or the output layer) is fed chunk by chunk as the epilogue of layer l
       // produces its A operand; its accumulator is the D region layer l does not use
 #pragma unroll 1
@@ -426,12 +413,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         mma_commit(bar);
         cphase ^= 1;
-      }
-      if (more) {   // the next x tile has landed and every warp is done with D0: layer 0 of the next tile, now
-        mbar_wait(bar_x, xphase);
-        xphase ^= 1;
-        tc_fence_after();
-        issue_layer0();
       }
     }
     if (is_epi) {
@@ -481,13 +462,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
           mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
         }
-      }
-      if (more) {   // hidden layers done: the prefetched x tile is complete, D0 has been read -> release layer 0 of the next tile
-        cp_async_wait_all();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_x);
       }
       // ---- output layer epilogue (column group 0 threads) ----
       mbar_wait(bar, phase);
@@ -700,20 +674,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
-  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8, bar_x = bar + 40;
+  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
   uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
-  uint32_t xphase = 0;   // parity of bar_x (issuer)
-  // as in the forward chain: the next tile's first MMA (dZ_out W_o -> D0) is issued behind this tile's last MMA and
-  // runs under the d_x epilogue; D0 must then be the accumulator of the last chain step, not of d_x
-  static_assert(NH & 1, "odd number of hidden layers: the d_x accumulator lives in D1");
 
   stage_bytes(smem, image_bwd, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
-    mbar_init(bar_x, TC_EPI_WARPS);
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -750,32 +719,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int l = 0; l < NH; ++l)
       pf_mask[l] = ok ? __ldg(mask_base + act_mask_index(l, act_rows_padded(m_total), row, et.grp)) : make_uint2(0, 0);
   };
-  // dZ_out = d_y * act'(y) of tile `tl` from the prefetched (y, d_y): A tile of the chain's first MMA (column group 0)
-  auto make_dz = [&](int64_t tl) {
-    const int64_t row = row_begin + tl * TC_TM + t;
-    const bool valid = row < row_end;
-    float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < NO; ++c)
-        if (c < n_out) {
-          const float yy = pf_y[c];
-          dz[c] = pf_dy[c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
-        }
-      if (d_z_out) {
-        *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], dz[3]);
-        *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
-      }
-    }
-    const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
-    if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
-      uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
-      zo[tiled_chunk_index(row, 0, 2)] = dz16;
-      zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
-    fence_proxy_async();
-  };
   prefetch(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -795,24 +738,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    // ---- dZ_out tile of the first MMA: made here for the CTA's first tile, under the previous tile's chain otherwise ----
-    const bool first = tile == (int64_t)blockIdx.x, more = tile + gridDim.x < n_tiles;
-    if (first && is_epi && et.grp == 0) make_dz(tile);
-    prefetch(tile + gridDim.x);
-    if (first) {
-      tc_fence_before();
-      __syncthreads();
+    // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column group 0 threads) ----
+    if (is_epi && et.grp == 0) {
+      float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < NO; ++c)
+          if (c < n_out) {
+            const float yy = pf_y[c];
+            dz[c] = pf_dy[c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
+          }
+        if (d_z_out) {
+          *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+          *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
+        }
+      }
+      const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
+      if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
+        uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
+        zo[tiled_chunk_index(row, 0, 2)] = dz16;
+        zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
+      fence_proxy_async();
     }
-    auto issue_first = [&]() {
+    prefetch(tile + gridDim.x);
+    tc_fence_before();
+    __syncthreads();
+    if (is_issuer && lane == 0) {
+      tc_fence_after();
       mma_ss(tmem + tm_d(0), make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
              make_idesc(TC_W), 0);
       mma_commit(bar);
-    };
-    if (is_issuer && lane == 0) {
-      if (first) {
-        tc_fence_after();
-        issue_first();
-      }
       // chain step i handles layer l = NH - 1 - i: its accumulator is D region i & 1, the MMA it feeds (W_l^T, or
       // W_0^T -> d_x for l == 0) accumulates in the other region, chunk by chunk (see chunk_ready)
 #pragma unroll 1
@@ -834,12 +791,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         mma_commit(bar);
         cphase ^= 1;
-      }
-      if (more) {   // next tile's dZ_out is in shared memory and every warp is done with D0
-        mbar_wait(bar_x, xphase);
-        xphase ^= 1;
-        tc_fence_after();
-        issue_first();
       }
     }
     if (is_epi) {
@@ -876,12 +827,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
           chunk_ready(bar_chunk + 8 * cc, lane);
         }
-      }
-      if (more) {   // chain epilogues done (D0 read): hand the next tile's dZ_out (prefetched y, d_y) to the issuer
-        if (et.grp == 0) make_dz(tile + gridDim.x);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_x);
       }
       // ---- d_x epilogue: one 16-column group per epilogue column group ----
       mbar_wait(bar, phase);
