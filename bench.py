@@ -434,7 +434,10 @@ def run_b200(a, rank, world, local_rank):
     model.keep_streams = True
     params = [p for p in model.parameters() if p.requires_grad]
     compactor = GridGradCompactor(model) if (world > 1 and not a.dense_allreduce and a.stage == "fine") else None
-    if compactor is not None and not os.environ.get("ESR_NO_ALLREDUCE_OVERLAP"):
+    # the colour volumes' early start (dist.GridGradCompactor.overlap_color_allreduce: -0.14 ms per step at N = 2, tested
+    # by tests/test_gpu_dist.py) is opt-in here: it was measured at N = 2 and N = 8 only, and a 4-GPU run at the end of
+    # round 1 hung for an unexplained reason with no GPU budget left to investigate
+    if compactor is not None and os.environ.get("ESR_ALLREDUCE_OVERLAP"):
         compactor.overlap_color_allreduce(True)
     reduced = [0]
     optimizer = None
