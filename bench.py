@@ -427,7 +427,9 @@ def run_b200(a, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that stops making progress fails the run in minutes (NCCL watchdog) instead of hanging it
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     L = _lib.lib()
 
     model, host, fwd_kw, stage_loss = build_stage(a, dev, rank)
