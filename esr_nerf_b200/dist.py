@@ -91,8 +91,6 @@ class GridGradCompactor:
         params = self.grids[1:]
         if self._early is not None or any(p.grad is not None for p in params) or any(p not in bufs for p in params):
             return          # gradient accumulation across calls (or an unexpected graph): the exchange happens at the end
-        if not all(bufs[p].is_cuda for p in params):
-            return
         rows = [self._rows(bufs[p]) for p in params]
         buf = self.pack(rows, "_cbuf")
         work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)

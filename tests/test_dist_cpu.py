@@ -117,6 +117,24 @@ def _compactor_worker(rank, world, port, out):
         if p.dim() == 5:
             other = other * comp.mask
         err = max(err, (p.grad - (mine + other)).abs().max().item())
+    # the same exchange with the colour volumes started early (what Shade.backward's hook does on the GPU): the packed
+    # colour block is all-reduced asynchronously while the caller still finishes the SDF gradient
+    color = comp.grids[1:]
+    for p, mine in zip(model.parameters(), grads):
+        p.grad = None if any(p is c for c in color) else mine.clone()
+    bufs = {p: mine.clone() for p, mine in zip(model.parameters(), grads) if any(p is c for c in color)}
+    comp._on_color_grads(bufs)
+    assert comp._early is not None
+    for p in color:
+        p.grad = bufs[p]
+    comp.allreduce()
+    assert comp._early is None
+    g3 = torch.Generator().manual_seed(10 + (1 - rank))
+    for p, mine in zip(model.parameters(), grads):
+        other = torch.randn(p.shape, generator=g3)
+        if p.dim() == 5:
+            other = other * comp.mask
+        err = max(err, (p.grad - (mine + other)).abs().max().item())
     out.put(err)
     dist.barrier()
     dist.destroy_process_group()
