@@ -692,6 +692,10 @@ def run_b200(a, rank, world, local_rank):
 def main():
     _claim_stdout()
     a = parse()
+    # a wedged device or collective must end the process, not the box's time limit: after ESR_BENCH_WATCHDOG_S seconds
+    # (default 20 min; a default run takes ~2) every thread's stack goes to stderr and the process exits non-zero
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("ESR_BENCH_WATCHDOG_S", "1200")), exit=True, file=sys.stderr)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

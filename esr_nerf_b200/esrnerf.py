@@ -51,9 +51,16 @@ class ESRNeRF(VoxurfF):
         self.num_2ndrays = cfg_get(cfg, m + "num_2ndrays")
         self.num_ltspts = cfg_get(cfg, m + "num_ltspts")
         self.lts_near = cfg_get(cfg, m + "lts_near")
-        if not (self.brdfnet_width <= 192 and self.brdfnet_depth == 4 and str(self.ray_sampling).lower() in ("random", "rand")):
+        if not (self.brdfnet_width <= 192 and self.brdfnet_depth == 4):
             raise NotImplementedError("libesr_b200 instantiates the shipped LTS shape (cfg/app/lts.yaml:25-43): brdfnet "
-                                      "<=192 x 4, ray_sampling random")
+                                      "<=192 x 4")
+        # esrnerf.py:188-192 (the reference's `match` has no default arm: an unknown name fails at the first use)
+        if str(self.ray_sampling).lower() in ("random", "rand"):
+            self.fib_sampling = False
+        elif str(self.ray_sampling).lower() in ("fib", "fibo", "fibonacci"):
+            self.fib_sampling = True
+        else:
+            raise ValueError(f"ray_sampling {self.ray_sampling!r}: expected random | fib (esrnerf.py:188-192)")
         # esrnerf.py:174-195
         self.brdf = DenseGrid(self.color_dim, self.world_size, self.xyz_min, self.xyz_max)
         dim0 = (3 + 3 * self.posbase_pe * 2) + self.color_dim + len(self.grad_feat) * 9 + 1
@@ -113,6 +120,13 @@ class ESRNeRF(VoxurfF):
             return self.draws.randn(*shape).to(dev)
         return torch.randn(*shape, device=dev)
 
+    def _scatter(self, normal, number) -> torch.Tensor:
+        """self.scattering(normal, number) of esrnerf.py:188-192: `number` directions in the hemisphere of each normal —
+        normalised Gaussian draws (pbr/functions.py:10-18) or the fixed Fibonacci spiral (pbr/functions.py:21-32)"""
+        if self.fib_sampling:
+            return pbr.diffuse_scattering_fib(normal, number)
+        return pbr.diffuse_scattering(normal, self._randn(normal.shape[0], number, 3, dev=normal.device))
+
     def _shade(self, sc, pos, use, flats, emo_grid=None, sdf_grid=None):
         grids = (self.sdf.grid if sdf_grid is None else sdf_grid, self.off_color.grid,
                  self.emo_color.grid if emo_grid is None else emo_grid, self.brdf.grid if use[3] else None)
@@ -139,7 +153,7 @@ class ESRNeRF(VoxurfF):
         """esrnerf.py:487-679"""
         dev = pts.device
         n2, P = self.num_2ndrays, pts.shape[0]
-        dirs = pbr.diffuse_scattering(normal, self._randn(P, n2 + 1, 3, dev=dev))
+        dirs = self._scatter(normal, n2 + 1)
         v_rand = -dirs[:, -1]
         dirs = dirs[:, :-1]
         sc_pts = self._pbr_scene(self.near, False)
@@ -257,7 +271,7 @@ class ESRNeRF(VoxurfF):
             sc_pts = self._pbr_scene(self.near, False)
             sdf, exp_grad = fused.sdf_expgrad_points(sc_pts, self.sdf.grid.detach(), pts)
             normal = F.normalize(exp_grad, dim=-1)
-            dirs = pbr.diffuse_scattering(normal, self._randn(P, n2 + 1, 3, dev=dev))
+            dirs = self._scatter(normal, n2 + 1)
             v_rand = -dirs[:, -1]
             dirs = dirs[:, :-1]
             flats_ng = [f.detach() for f in self._flats()]
@@ -339,7 +353,7 @@ class ESRNeRF(VoxurfF):
         and indirect parts by Monte-Carlo integration over `num_2ndrays` hemisphere directions per sample."""
         dev = pts.device
         n2, P = self.num_2ndrays, pts.shape[0]
-        dirs = pbr.diffuse_scattering(normal, self._randn(P, n2, 3, dev=dev))
+        dirs = self._scatter(normal, n2)
 
         def ex(t, c):
             return t.view(-1, 1, c).expand(P, n2, c).flatten(0, 1)

@@ -178,27 +178,40 @@ class BRDFNet(nn.Module):
 
 
 class SphericalGaussian(nn.Module):
-    """pbr/module.py:86-143: 48-lobe spherical-Gaussian environment map, softplus activation (cfg/app/lts.yaml:29-30).
-    The initial energy normalisation follows pbr/module.py:104-127."""
+    """pbr/module.py:86-143: spherical-Gaussian environment map (48 lobes, softplus: cfg/app/lts.yaml:29-30).  The
+    activation is looked up by name in `torch`, then `torch.nn.functional`, as the reference does (relu, abs, exp,
+    sigmoid, softplus, ...); the initial energy normalisation follows pbr/module.py:104-127, which re-parametrises
+    `mus` for abs / relu / softplus / exp and leaves the raw draw in place for any other activation."""
 
     def __init__(self, num_sg: int = 48, activation: str = "softplus"):
         super().__init__()
-        if activation != "softplus":
-            raise NotImplementedError("only the shipped env_activation 'softplus' is provided (cfg/app/lts.yaml:30)")
+        if hasattr(torch, activation):
+            self.activation = getattr(torch, activation)
+        elif hasattr(F, activation):
+            self.activation = getattr(F, activation)
+        else:
+            raise AttributeError("'{}' not found in torch or torch.nn.functional".format(activation))
+        act = self.activation
         mus = torch.randn(num_sg, 3)
         lambdas = 10.0 + torch.abs(torch.randn(num_sg, 1) * 20.0)
         lobes = torch.randn(num_sg, 3)
         lam = torch.abs(lambdas)
-        energy = F.softplus(mus) * 2.0 * torch.pi / lam * (1.0 - torch.exp(-2.0 * lam))
-        normalized_mu = F.softplus(mus) / torch.sum(energy, dim=0, keepdim=True) * 2.0 * torch.pi * 0.8
-        self.mus = nn.Parameter(torch.log(torch.exp(normalized_mu) - 1.0))
+        energy = act(mus) * 2.0 * torch.pi / lam * (1.0 - torch.exp(-2.0 * lam))
+        normalized_mu = act(mus) / torch.sum(energy, dim=0, keepdim=True) * 2.0 * torch.pi * 0.8
+        if act in (torch.abs, torch.relu):
+            mus = normalized_mu
+        elif act is F.softplus:
+            mus = torch.log(torch.exp(normalized_mu) - 1.0)
+        elif act is torch.exp:
+            mus = torch.log(normalized_mu)
+        self.mus = nn.Parameter(mus)
         self.lambdas = nn.Parameter(lambdas)
         self.lobes = nn.Parameter(lobes)
 
     def forward(self, dirs):
         lobes = F.normalize(self.lobes, dim=-1)
         lambdas = torch.abs(self.lambdas)
-        return F.softplus((self.mus * torch.exp(lambdas * ((dirs.unsqueeze(-2) * lobes).sum(-1, keepdim=True) - 1.0))).sum(-2))
+        return self.activation((self.mus * torch.exp(lambdas * ((dirs.unsqueeze(-2) * lobes).sum(-1, keepdim=True) - 1.0))).sum(-2))
 
 
 class GradientConv(nn.Module):

@@ -18,6 +18,26 @@ def diffuse_scattering(normal: torch.Tensor, noise: torch.Tensor) -> torch.Tenso
     return torch.where(below, -ret, ret)
 
 
+def fibonacci_hemisphere(number: int) -> torch.Tensor:
+    """pbr/functions.py:176-194 (`random=False, up=True`): the upper half of a 2n-point Fibonacci spiral, [n, 3] fp32
+    on the host — golden-angle azimuths, cos(theta) equally spaced in (0, 1)."""
+    n = 2 * number
+    rn = torch.arange(number, n)
+    phi = (math.pi * (3.0 - math.sqrt(5.0))) * ((rn + 1.0) % n)
+    cos_theta = ((rn + 0.5) * (1.0 / number)) - 1.0
+    sin_theta = torch.sqrt(1.0 - cos_theta * cos_theta)
+    return torch.stack([torch.cos(phi) * sin_theta, torch.sin(phi) * sin_theta, cos_theta], dim=-1)
+
+
+@torch.no_grad()
+def diffuse_scattering_fib(normal: torch.Tensor, number: int) -> torch.Tensor:
+    """pbr/functions.py:21-32 (`ray_sampling: fib`): the same deterministic spiral for every point, each direction
+    mirrored into the hemisphere of that point's `normal` [..., 3] -> [..., number, 3].  No random draw."""
+    ret = fibonacci_hemisphere(number).to(normal.device).expand(*normal.shape[:-1], number, 3)
+    below = (ret * normal.unsqueeze(-2)).sum(-1, keepdim=True) < 0
+    return torch.where(below, -ret, ret)
+
+
 def disney_reflection(albedo, roughness, metallic, normal, win, wout):
     """pbr/functions.py:108-173: (diffuse + D F V) * cos(theta_i) * 2 pi with the spherical-Gaussian NDF, Schlick
     Fresnel and Schlick-GGX visibility."""

@@ -104,3 +104,93 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_fibonacci_scattering_properties_and_reference():
+    """`ray_sampling: fib` (pbr/functions.py:21-32, 176-194): unit directions, deterministic, mirrored into each point's
+    hemisphere; against a float64 restatement of the published spiral and — where /root/reference exists — the
+    reference's own function, bit for bit"""
+    import math
+
+    import numpy as np
+
+    from esr_nerf_b200 import pbr
+
+    n = 37
+    d = pbr.fibonacci_hemisphere(n)
+    assert d.shape == (n, 3) and d.dtype == torch.float32
+    rn = np.arange(n, 2 * n, dtype=np.float64)
+    phi = math.pi * (3.0 - math.sqrt(5.0)) * ((rn + 1.0) % (2 * n))
+    ct = (rn + 0.5) / n - 1.0
+    st = np.sqrt(1.0 - ct * ct)
+    want = np.stack([np.cos(phi) * st, np.sin(phi) * st, ct], -1)
+    assert np.abs(d.numpy() - want).max() < 2e-5            # fp32 phase of up to ~180 rad
+    assert (d[:, 2] > 0).all() and torch.allclose(d.norm(dim=-1), torch.ones(n), atol=1e-6)
+
+    torch.manual_seed(3)
+    normal = F.normalize(torch.randn(11, 3), dim=-1)
+    dirs = pbr.diffuse_scattering_fib(normal, n)
+    assert dirs.shape == (11, n, 3)
+    assert ((dirs * normal[:, None]).sum(-1) >= 0).all()
+    assert torch.equal(dirs.abs(), d.abs().expand(11, n, 3))        # the same spiral for every point, up to the mirror
+    assert torch.equal(dirs, pbr.diffuse_scattering_fib(normal, n))
+
+    from oracle import ref_harness as H
+    if H.reference_available():
+        H.install_stubs()
+        import importlib
+        ref = importlib.import_module("app.utils.pbr.functions")
+        assert torch.equal(d, ref.fibonacci_spiral_samples_on_unit_hemisphere(n))
+        assert torch.equal(dirs, ref.diffuse_scattering_fib(normal, n))
+
+
+def test_spherical_gaussian_activations_match_reference():
+    """`env_activation` (pbr/module.py:86-143): every activation the reference documents, same seeded initialisation
+    (incl. which ones re-parametrise `mus`), same forward"""
+    import pytest
+
+    with pytest.raises(AttributeError):
+        M.SphericalGaussian(8, "no_such_activation")
+    dirs = F.normalize(torch.randn(5, 7, 3), dim=-1)
+    torch.manual_seed(7)
+    sp = M.SphericalGaussian(48, "softplus")
+    assert sp.activation is F.softplus and sp(dirs).shape == (5, 7, 3) and (sp(dirs) > 0).all()
+
+    from oracle import ref_harness as H
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    H.install_stubs()
+    import importlib
+    ref_mod = importlib.import_module("app.utils.pbr.module")
+    for act in ("relu", "abs", "exp", "sigmoid", "softplus"):
+        torch.manual_seed(11)
+        mine = M.SphericalGaussian(16, act)
+        torch.manual_seed(11)
+        ref = ref_mod.SphericalGaussian(16, act)
+        for k, v in ref.state_dict().items():
+            assert torch.equal(mine.state_dict()[k], v), (act, k)
+        assert torch.equal(mine(dirs), ref(dirs)), act
+
+
+def test_esrnerf_scatter_dispatch():
+    """ESRNeRF._scatter: `ray_sampling` random draws through the model's (replaceable) normal source, fib draws nothing
+    (esrnerf.py:188-192, 302, 534, 874); unknown names are rejected at construction"""
+    import pytest
+
+    from esr_nerf_b200 import pbr
+    from esr_nerf_b200.esrnerf import ESRNeRF
+
+    normal = F.normalize(torch.randn(6, 3), dim=-1)
+    noise = torch.randn(6, 9, 3)
+    calls = []
+
+    def randn(*shape, dev):
+        calls.append(shape)
+        return noise
+
+    o = types.SimpleNamespace(fib_sampling=False, _randn=randn)
+    got = ESRNeRF._scatter(o, normal, 9)
+    assert calls == [(6, 9, 3)] and torch.equal(got, pbr.diffuse_scattering(normal, noise))
+    o.fib_sampling = True
+    got = ESRNeRF._scatter(o, normal, 9)
+    assert len(calls) == 1 and torch.equal(got, pbr.diffuse_scattering_fib(normal, 9))
