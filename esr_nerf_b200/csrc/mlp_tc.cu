@@ -288,8 +288,8 @@ struct FwdSm {
   static constexpr int bias = wo + TC_NOUT_PAD * TC_W * 2;
   static constexpr int weights_bytes = bias + (NH * TC_W + TC_NOUT_PAD) * 4;   // == TcLayout::f_bytes()
   static constexpr int x = (weights_bytes + 127) / 128 * 128;
-  static constexpr int bar = x + TC_TM * K0 * 2;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot
-  static constexpr int bytes = bar + 48;
+  static constexpr int bar = x + TC_TM * K0 * 2;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot, (OVL) bar_x, bar_first
+  static constexpr int bytes = bar + 64;
 };
 
 // Epilogue thread geometry (16 warps): TMEM lane quadrant = warp % 4 (hardware rule for tcgen05.ld/st), column
@@ -316,7 +316,13 @@ ESR_D void tonemap_pe_channel(float x, uint4 &lo, uint4 &hi, float (&sn)[5], flo
 // NO = compile-time bound on the real output columns (3: radiance / tone-map / emission nets, 8: the 5-output BRDF net)
 // XSRC = 0: x rows come tiled from global memory; 1 (K0 = 48 only): `x` is the f32 [m,3] linear radiance and the CTA
 // computes the tone-map encoding of its tile itself (no feature rows in HBM at all)
-template <int K0, int NH, int NO, int XSRC = 0>
+// OVL = tile overlap (opt-in, ESR_MLP_TILE_OVERLAP=1): the next tile's layer-0 MMA is issued behind this tile's
+// output-layer MMA and runs under the output epilogue (an x-ready mbarrier replaces the per-tile __syncthreads).  Its
+// commit goes to its OWN mbarrier (bar_first), so that no mbarrier ever completes two phases without every waiting warp
+// having observed the first: bar (layers 1.. + output) completes again only after all 16 warps have arrived on a chunk
+// barrier of the next tile, which each does after its own wait on the output phase; bar_first completes again only
+// after all 16 warps have arrived on bar_x, which each does after its own wait on bar_first.
+template <int K0, int NH, int NO, int XSRC = 0, bool OVL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_fwd_tc(const uint8_t *__restrict__ image, const __nv_bfloat16 *__restrict__ x, int64_t row_begin,
                  int64_t row_end, int64_t m_total, float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden,
@@ -327,13 +333,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
   const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
+  [[maybe_unused]] const uint32_t bar_x = bar + 40, bar_first = bar + 48;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
+  // OVL: layer 0 of the next tile writes D0 while the output epilogue still reads its accumulator, which must
+  // therefore be D1 — and D0 the accumulator of the LAST hidden layer, read before the arrival on bar_x
+  static_assert(!OVL || (NH & 1), "tile overlap: odd number of hidden layers (the output accumulator lives in D1)");
 
   stage_bytes(smem, image, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
+    if constexpr (OVL) {
+      mbar_init(bar_x, TC_EPI_WARPS);
+      mbar_init(bar_first, 1);
+    }
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -344,6 +358,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem = *tmem_slot;
   const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
   uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
+  [[maybe_unused]] uint32_t xphase = 0;   // OVL: parity of bar_x (issuer)
+  [[maybe_unused]] uint32_t fphase = 0;   // OVL: parity of bar_first (epilogue warps)
 
   const int64_t n_tiles = (row_end - row_begin + TC_TM - 1) / TC_TM;
   const EpiThread et(warp, lane);
@@ -379,19 +395,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const bool save = valid && hidden && row >= save_begin;  // rows the backward pass will visit
     const bool save_w = __any_sync(FULL, save);               // warp-uniform (the issuer warp: false)
     // ---- layer 0: A = x tile (shared), B = W0 ----
-    if (is_epi) {
-      cp_async_wait_all();
-      fence_proxy_async();
+    [[maybe_unused]] const bool first = tile == (int64_t)blockIdx.x, more = tile + gridDim.x < n_tiles;
+    if (!OVL || first) {   // OVL, later tiles: layer 0 was issued behind the previous tile's output layer (below)
+      if (is_epi) {
+        cp_async_wait_all();
+        fence_proxy_async();
+      }
+      tc_fence_before();
+      __syncthreads();
     }
-    tc_fence_before();
-    __syncthreads();
-    if (is_issuer && lane == 0) {
-      tc_fence_after();
+    auto issue_layer0 = [&]() {
 #pragma unroll
       for (int s = 0; s < K0 / 16; ++s)
         mma_ss(tmem + tm_d(0), make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
                make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
-      mma_commit(bar);
+      mma_commit(OVL ? bar_first : bar);
+    };
+    if (is_issuer && lane == 0) {
+      if (!OVL || first) {
+        tc_fence_after();
+        issue_layer0();
+      }
       // the rest of the chain: layer l + 1 (or the output layer) is fed chunk by chunk as the epilogue of layer l
       // produces its A operand; its accumulator is the D region layer l does not use
 #pragma unroll 1
@@ -414,12 +438,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mma_commit(bar);
         cphase ^= 1;
       }
+      if constexpr (OVL) {
+        if (more) {   // the next x tile has landed and every warp is done with D0: layer 0 of the next tile, now
+          mbar_wait(bar_x, xphase);
+          xphase ^= 1;
+          tc_fence_after();
+          issue_layer0();
+        }
+      }
     }
     if (is_epi) {
 #pragma unroll 1
       for (int l = 0; l < NH; ++l) {
-        mbar_wait(bar, phase);
-        phase ^= 1;
+        if (OVL && l == 0) {
+          mbar_wait(bar_first, fphase);
+          fphase ^= 1;
+        } else {
+          mbar_wait(bar, phase);
+          phase ^= 1;
+        }
         tc_fence_after();
         if (l == 0 && tile + gridDim.x < n_tiles) load_x(tile + gridDim.x);  // x tile is free: prefetch the next one
         // bias + ReLU -> bf16 -> TMEM A operand (+ global copy, tiled layout, for the backward pass)
@@ -461,6 +498,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (save) {
           uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
           mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
+        }
+      }
+      if constexpr (OVL) {
+        if (more) {   // hidden layers done: the prefetched x tile is complete, D0 has been read -> release layer 0 of the next tile
+          cp_async_wait_all();
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x);
         }
       }
       // ---- output layer epilogue (column group 0 threads) ----
@@ -659,11 +705,14 @@ struct BwdSm {
   static constexpr int w0 = wh + (NH - 1) * TC_W * TC_W * 2;          // W0T [DXN x W]
   static constexpr int weights_bytes = w0 + DXN * TC_W * 2;           // == TcLayout::b_bytes()
   static constexpr int dz = (weights_bytes + 127) / 128 * 128;        // dZ_out tile [128 x 16] bf16
-  static constexpr int bar = dz + TC_TM * TC_NOUT_PAD * 2;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot
-  static constexpr int bytes = bar + 48;
+  static constexpr int bar = dz + TC_TM * TC_NOUT_PAD * 2;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot, (OVL) bar_x, bar_first
+  static constexpr int bytes = bar + 64;
 };
 
-template <int K0, int NH, int DXN, int NO, bool ACC>
+// OVL = tile overlap (opt-in, see k_mlp_fwd_tc): the next tile's dZ_out tile is made under this tile's chain and its
+// first MMA (dZ_out W_o -> D0) is issued behind this tile's last MMA, so that it runs under the d_x epilogue; the first
+// MMA's commit has its own mbarrier (bar_first).
+template <int K0, int NH, int DXN, int NO, bool ACC, bool OVL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_dgrad_tc(const uint8_t *__restrict__ image_bwd, const float *__restrict__ y, const float *__restrict__ d_y,
                    int64_t row_begin, int64_t row_end, int64_t m_total, const __nv_bfloat16 *__restrict__ hidden,
@@ -675,14 +724,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
   const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
+  [[maybe_unused]] const uint32_t bar_x = bar + 40, bar_first = bar + 48;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
   uint32_t cphase = 0;   // parity of the chunk barriers (issuer)
+  [[maybe_unused]] uint32_t xphase = 0;   // OVL: parity of bar_x (issuer)
+  [[maybe_unused]] uint32_t fphase = 0;   // OVL: parity of bar_first (epilogue warps)
+  // OVL: the next tile's first MMA writes D0 under the d_x epilogue: D0 must be the accumulator of the last chain
+  // step (read before the arrival on bar_x), not of d_x
+  static_assert(!OVL || (NH & 1), "tile overlap: odd number of hidden layers (the d_x accumulator lives in D1)");
 
   stage_bytes(smem, image_bwd, S::weights_bytes);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, TC_EPI_WARPS);
+    if constexpr (OVL) {
+      mbar_init(bar_x, TC_EPI_WARPS);
+      mbar_init(bar_first, 1);
+    }
     fence_mbar_init();
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
@@ -719,6 +778,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int l = 0; l < NH; ++l)
       pf_mask[l] = ok ? __ldg(mask_base + act_mask_index(l, act_rows_padded(m_total), row, et.grp)) : make_uint2(0, 0);
   };
+  // OVL: dZ_out = d_y * act'(y) of tile `tl` from the prefetched (y, d_y): A tile of the chain's first MMA (column group 0)
+  [[maybe_unused]] auto make_dz = [&](int64_t tl) {
+    if constexpr (OVL) {   // (an empty body otherwise: the non-overlapped instantiation captures nothing)
+      const int64_t row = row_begin + tl * TC_TM + t;
+      const bool valid = row < row_end;
+      float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < NO; ++c)
+          if (c < n_out) {
+            const float yy = pf_y[c];
+            dz[c] = pf_dy[c] * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
+          }
+        if (d_z_out) {
+          *reinterpret_cast<float4 *>(d_z_out + row * 8) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+          *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
+        }
+      }
+      const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
+      if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
+        uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
+        zo[tiled_chunk_index(row, 0, 2)] = dz16;
+        zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
+      fence_proxy_async();
+    }
+  };
   prefetch(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -738,6 +825,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    [[maybe_unused]] const bool first = tile == (int64_t)blockIdx.x, more = tile + gridDim.x < n_tiles;
+    [[maybe_unused]] auto issue_first = [&]() {   // OVL
+      mma_ss(tmem + tm_d(0), make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
+             make_idesc(TC_W), 0);
+      mma_commit(bar_first);
+    };
+    if constexpr (OVL) {
+      // ---- dZ_out tile of the first MMA: made here for the CTA's first tile, under the previous tile's chain otherwise ----
+      if (first && is_epi && et.grp == 0) make_dz(tile);
+      prefetch(tile + gridDim.x);
+      if (first) {
+        tc_fence_before();
+        __syncthreads();
+      }
+    } else {
     // ---- dZ_out = d_y * act'(y): A tile of the first MMA (column group 0 threads) ----
     if (is_epi && et.grp == 0) {
       float dz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -765,11 +867,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     prefetch(tile + gridDim.x);
     tc_fence_before();
     __syncthreads();
+    }
     if (is_issuer && lane == 0) {
-      tc_fence_after();
-      mma_ss(tmem + tm_d(0), make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
-             make_idesc(TC_W), 0);
-      mma_commit(bar);
+      if constexpr (!OVL) {
+        tc_fence_after();
+        mma_ss(tmem + tm_d(0), make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
+               make_idesc(TC_W), 0);
+        mma_commit(bar);
+      } else if (first) {
+        tc_fence_after();
+        issue_first();
+      }
       // chain step i handles layer l = NH - 1 - i: its accumulator is D region i & 1, the MMA it feeds (W_l^T, or
       // W_0^T -> d_x for l == 0) accumulates in the other region, chunk by chunk (see chunk_ready)
 #pragma unroll 1
@@ -792,6 +900,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mma_commit(bar);
         cphase ^= 1;
       }
+      if constexpr (OVL) {
+        if (more) {   // next tile's dZ_out is in shared memory and every warp is done with D0
+          mbar_wait(bar_x, xphase);
+          xphase ^= 1;
+          tc_fence_after();
+          issue_first();
+        }
+      }
     }
     if (is_epi) {
 #pragma unroll 1
@@ -804,8 +920,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int q = 1; q < NH; ++q)
           if (q == l) mk2 = cur_mask[q];
         const uint32_t mask[2] = {mk2.x, mk2.y};
-        mbar_wait(bar, phase);
-        phase ^= 1;
+        if (OVL && i == 0) {
+          mbar_wait(bar_first, fphase);
+          fphase ^= 1;
+        } else {
+          mbar_wait(bar, phase);
+          phase ^= 1;
+        }
         tc_fence_after();
         // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy (tiled) for the weight-gradient GEMM
         uint32_t r[3][16];
@@ -826,6 +947,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             zl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(p[4], p[5], p[6], p[7]);
           }
           chunk_ready(bar_chunk + 8 * cc, lane);
+        }
+      }
+      if constexpr (OVL) {
+        if (more) {   // chain epilogues done (D0 read): hand the next tile's dZ_out (prefetched y, d_y) to the issuer
+          if (et.grp == 0) make_dz(tile + gridDim.x);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x);
         }
       }
       // ---- d_x epilogue: one 16-column group per epilogue column group ----
@@ -1331,10 +1460,24 @@ static unsigned tc_grid(int64_t rows) {
   return (unsigned)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
 }
 
-template <int K0, int NH, int NO, int XSRC = 0>
+// ESR_MLP_TILE_OVERLAP=1 (read once): the radiance-net chains run their tile-overlap instantiation (k_mlp_fwd_tc /
+// k_mlp_dgrad_tc, OVL).  Off by default: that variant has not run on a GPU in its present form (its predecessor, which
+// shared one mbarrier between the layer-0 and the output commits, measured -0.07 / -0.05 ms per launch and was
+// withdrawn for the double-completion hazard the separate mbarrier removes) — DESIGN.md §4.
+static bool tile_overlap() {
+  static const bool on = [] {
+    const char *e = getenv("ESR_MLP_TILE_OVERLAP");
+    return e && e[0] && e[0] != '0';
+  }();
+  return on;
+}
+
+template <int K0, int NH, int NO, int XSRC = 0, bool OVL = false>
 static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x, int64_t rb, int64_t re, int64_t mt,
                       float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
-  auto kern = k_mlp_fwd_tc<K0, NH, NO, XSRC>;
+  if constexpr (!OVL && K0 == 96 && XSRC == 0)
+    if (tile_overlap()) return launch_fwd<K0, NH, NO, XSRC, true>(d, image, x, rb, re, mt, y, hidden, save_begin, st);
+  auto kern = k_mlp_fwd_tc<K0, NH, NO, XSRC, OVL>;
   constexpr int bytes = FwdSm<K0, NH>::bytes;
   if (int e = set_smem_tc(kern, bytes)) return e;
   ESR_STAGE(K0 == 96 ? "k_mlp_fwd_tc_radiance" : (XSRC ? "k_tonemap_fwd_fused" : "k_mlp_fwd_tc_tonemap"), st);
@@ -1344,11 +1487,15 @@ static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x,
   return ESR_OK;
 }
 
-template <int K0, int NH, int DXN, int NO, bool ACC>
+template <int K0, int NH, int DXN, int NO, bool ACC, bool OVL = false>
 static int launch_dgrad_acc(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const float *y, const float *d_y,
                         int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z, float *d_z_out, float *d_x,
                         int dx_cols, int accumulate, cudaStream_t st) {
-  auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC>;
+  if constexpr (!OVL && K0 == 96)
+    if (tile_overlap())
+      return launch_dgrad_acc<K0, NH, DXN, NO, ACC, true>(d, T, image, y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x, dx_cols,
+                                                          accumulate, st);
+  auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC, OVL>;
   constexpr int bytes = BwdSm<K0, NH, DXN>::bytes;
   if (int e = set_smem_tc(kern, bytes)) return e;
   ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_tc_radiance" : "k_mlp_dgrad_tc_tonemap", st);
