@@ -341,7 +341,7 @@ def algorithmic_work(stage, c):
     taps_fwd = (768 + 192) * M3 + 192 * M3on            # 24 SDF taps + off colour (+ emo colour on its rows)
     t = {
         "k_march_count": ("hbm", 24 * N + 32 * M0 + 12 * N),
-        "k_march_fill": ("hbm", 24 * N + 32 * M0 + 32 * M1 + 12 * M1),
+        "k_march_fill": ("hbm", 24 * N + 32 * M1 + 12 * M1),    # the mask tap (32 M0) is counted once, in the count pass
         "k_neus_alpha": ("hbm", 4 * M1 + 8 * M1),                # read sdf, write alpha + T preset
         "k_transmittance": ("hbm", 4 * M1 + 4 * M1 + 16 * N),     # read alpha, write T; per-ray offsets / count / last
         "k_shade_compact": ("hbm", 8 * M1 + 8 * M3 + 20 * M3),    # read alpha + T (+ step, sdf of survivors), write M3 stream
@@ -359,6 +359,10 @@ def algorithmic_work(stage, c):
         "k_mlp_wgrad_tc_out": ("tensor", 2 * 192 * 3 * 2 * M3),
         "k_mlp_fwd_tc_tonemap": ("tensor", FLOP_TONEMAP * M3),
         "k_mlp_dgrad_tc_tonemap": ("tensor", FLOP_TONEMAP * M3),
+        # the fused tone-map net: forward; backward = data gradient + weight gradients (its recomputed forward is not
+        # algorithmic work)
+        "k_tonemap_fwd_fused": ("tensor", FLOP_TONEMAP * M3),
+        "k_tonemap_bwd_fused": ("tensor", 2 * FLOP_TONEMAP * M3),
     }
     _ = Mcand
     if "encode_rows" in c:   # lts stage: rows summed over primary / LTS-point / secondary / eps passes (fused.STATS)
@@ -371,6 +375,23 @@ def algorithmic_work(stage, c):
             "k_mlp_wgrad_tc": ("tensor", FLOP_RADIANCE * Rb + 2 * 33 * 192 * M3),
         })
     return t.get(stage)
+
+
+def step_roofline(stage_rows, pk):
+    """The step's kernels in aggregate, per bound: algorithmic work of all HBM-bound (tensor-bound) launches of one step
+    over the time they took together, against the same peaks as `roofline`.  `other_ms_per_step`: library kernels with
+    no algorithmic figure (fills, casts, packing)."""
+    out = {}
+    for bound, unit, peak, scale in (("hbm", "GB/s", pk["hbm_gbs"], 1e9), ("tensor", "TFLOP/s", pk["bf16_tflops_sustained"], 1e12)):
+        rows = [r for r in stage_rows if r.get("bound") == bound and r["ms_per_step"] > 0]
+        ms = sum(r["ms_per_step"] for r in rows)
+        work = sum(r["work_per_step"] for r in rows)
+        ach = work / (ms * 1e-3) / scale if ms > 0 else 0.0
+        out[bound] = {"kernels": len(rows), "ms_per_step": ms, "algorithmic_work_per_step": work / scale,
+                      "work_unit": "GB" if bound == "hbm" else "TFLOP", "achieved": ach, "peak": peak, "unit": unit,
+                      "frac": ach / peak if peak else None}
+    out["other_ms_per_step"] = sum(r["ms_per_step"] for r in stage_rows if "bound" not in r)
+    return out
 
 
 def lts_loss_fn(out, rgbs):
@@ -629,6 +650,7 @@ def run_b200(a, rank, world, local_rank):
         row = {"kernel": name, "launches_per_step": cnt / a.steps, "ms_per_step": tot / a.steps}
         if w is not None:
             bound, work = w
+            row["work_per_step"] = work
             per_s = work / (tot / a.steps * 1e-3) if tot > 0 else 0.0
             if bound == "hbm":
                 row.update(bound="hbm", achieved=per_s / 1e9, unit="GB/s", frac=per_s / 1e9 / pk["hbm_gbs"])
@@ -649,6 +671,11 @@ def run_b200(a, rank, world, local_rank):
                     "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "peak_source": pk_src,
                     "avg_launch_ms": top["ms_per_step"] / max(top["launches_per_step"], 1e-9),
                     "share_of_kernel_time": top["ms_per_step"] / max(sum(r["ms_per_step"] for r in stage_rows), 1e-9)}
+
+    try:
+        step_rf = step_roofline(stage_rows, pk)
+    except Exception as e:   # a reporting extra must never cost the bench line
+        step_rf = {"error": repr(e)}
 
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline and a.stage == "fine":
@@ -681,7 +708,7 @@ def run_b200(a, rank, world, local_rank):
                    "counts_per_gpu_step": counts,
                    "samples_per_s": {"candidate_M0": counts["M0"] * world * a.steps / (ms * 1e-3),
                                      "shaded_M3": counts["M3"] * world * a.steps / (ms * 1e-3)}},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "step_roofline": step_rf, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "ms_each": ms_each, "kernels": stage_rows[:16],
     }
     print(json.dumps(line), file=JSON_OUT, flush=True)

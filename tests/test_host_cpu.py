@@ -194,3 +194,30 @@ def test_esrnerf_scatter_dispatch():
     o.fib_sampling = True
     got = ESRNeRF._scatter(o, normal, 9)
     assert len(calls) == 1 and torch.equal(got, pbr.diffuse_scattering_fib(normal, 9))
+
+
+def test_bench_step_roofline_aggregates_measured_rows():
+    """bench.step_roofline on the per-kernel rows of a bench line measured on the B200 (profiles/r01_bench_lines): the
+    aggregate of the HBM-bound kernels is their summed algorithmic bytes over their summed time"""
+    import json
+    import os
+
+    import bench
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, "profiles", "r01_bench_lines", "fine_n1.json")).read().strip().splitlines()[-1])
+    rows = []
+    for r in line["kernels"]:
+        r = dict(r)
+        if "bound" in r:   # lines older than the work_per_step key: rebuild it from rate x time
+            r["work_per_step"] = r["achieved"] * (1e9 if r["bound"] == "hbm" else 1e12) * r["ms_per_step"] * 1e-3
+        rows.append(r)
+    pk = {"hbm_gbs": 6448.4, "bf16_tflops_sustained": 1386.5}
+    agg = bench.step_roofline(rows, pk)
+    hbm = [r for r in rows if r.get("bound") == "hbm"]
+    assert agg["hbm"]["kernels"] == len(hbm) and agg["tensor"]["kernels"] == sum(r.get("bound") == "tensor" for r in rows)
+    want = sum(r["work_per_step"] for r in hbm) / sum(r["ms_per_step"] for r in hbm) / 1e-3 / 1e9
+    assert abs(agg["hbm"]["achieved"] - want) < 1e-6 * want
+    assert 0.3 < agg["hbm"]["frac"] < 1.0 and 0.1 < agg["tensor"]["frac"] < 1.0
+    assert agg["other_ms_per_step"] == sum(r["ms_per_step"] for r in rows if "bound" not in r)
+    assert bench.step_roofline([], pk)["hbm"]["frac"] == 0.0       # no rows: zeros, no division
