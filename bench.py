@@ -85,6 +85,10 @@ def parse():
                          "step; NOT part of the metric BASELINE.json names (render step only), off by default")
     ap.add_argument("--dense-allreduce", action="store_true",
                     help="N>1: all-reduce the dense grid gradients instead of the occupancy-compacted voxel set")
+    ap.add_argument("--block-exchange", action="store_true",
+                    help="N>1: exact two-level exchange of the grid gradients (dist.TouchedBlockCompactor: OR-reduced map of "
+                         "touched 8^3 blocks, then pack / all-reduce / unpack of their voxels) instead of the static "
+                         "occupancy set (fine) or the dense all-reduce (lts); checked on gloo, not yet measured on NCCL")
     a = ap.parse_args()
     if a.rays is None:
         a.rays = {"fine": 1 << 16, "lts": 1 << 15, "eval": 1600 * 1200 // max(a.gpus, 1)}[a.stage]
@@ -438,7 +442,7 @@ def build_stage(a, dev, rank):
 
 def run_b200(a, rank, world, local_rank):
     from esr_nerf_b200 import _lib, fused
-    from esr_nerf_b200.dist import GridGradCompactor, allreduce_gradients
+    from esr_nerf_b200.dist import GridGradCompactor, TouchedBlockCompactor, allreduce_gradients
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 render path has no CPU fallback")
@@ -457,10 +461,12 @@ def run_b200(a, rank, world, local_rank):
     model.keep_streams = True
     params = [p for p in model.parameters() if p.requires_grad]
     compactor = GridGradCompactor(model) if (world > 1 and not a.dense_allreduce and a.stage == "fine") else None
+    if world > 1 and a.block_exchange and a.stage != "eval":
+        compactor = TouchedBlockCompactor(model)
     # the colour volumes' early start (dist.GridGradCompactor.overlap_color_allreduce: -0.14 ms per step at N = 2, tested
     # by tests/test_gpu_dist.py) is opt-in here: it was measured at N = 2 and N = 8 only, and a 4-GPU run at the end of
     # round 1 hung for an unexplained reason with no GPU budget left to investigate
-    if compactor is not None and os.environ.get("ESR_ALLREDUCE_OVERLAP"):
+    if compactor is not None and not a.block_exchange and os.environ.get("ESR_ALLREDUCE_OVERLAP"):
         compactor.overlap_color_allreduce(True)
     reduced = [0]
     optimizer = None

@@ -198,3 +198,104 @@ class GridGradCompactor:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         self.unpack(rows, buf)
         return nbytes + buf.numel() * buf.element_size()
+
+
+class TouchedBlockCompactor(GridGradCompactor):
+    """Exact compacted exchange without a static voxel set (the LTS / PDRA stage): the eps-jittered samples
+    and the secondary rays of `ESRNeRF.forward_training` (esrnerf.py:576-652, 807-830) touch voxels that no occupancy
+    mask bounds, so the set is found per step, in two levels:
+
+      1. every rank marks the blocks (8^3 voxels; per axis the largest divisor of the grid size <= 8) in which ANY of
+         its grid-gradient volumes holds a non-zero (one `count_nonzero` pass over each volume, in memory order);
+      2. the ranks OR the flag maps (one 128 KB all-reduce(max) at 256^3) — every rank now holds the same union;
+      3. the voxels of the union's blocks are packed / all-reduced / unpacked exactly like the static set
+         (`esr_grad_pack` / `esr_grad_unpack`): a voxel outside the union is zero on every rank, so the result equals
+         the dense all-reduce by construction, bit for bit on two ranks.
+
+    One host read per step (the number of touched blocks, identical on every rank after step 2).  Exchange buffers grow
+    monotonically and are re-used (no allocation inside a steady-state step)."""
+
+    def __init__(self, model, grids=None, block: int = 8):
+        self.model = model
+        if grids is None:
+            grids = [g.grid for g in (getattr(model, n, None) for n in ("sdf", "off_color", "emo_color", "brdf"))
+                     if g is not None]
+        self.grids = list(grids)
+        self.shape = tuple(self.grids[0].shape[2:])
+        assert all(tuple(g.shape[2:]) == self.shape for g in self.grids), "grids of one scene share their resolution"
+        assert self.shape[0] * self.shape[1] * self.shape[2] < (1 << 31)
+        self.edge = tuple(max(e for e in range(1, block + 1) if n % e == 0) for n in self.shape)
+        self.blocks = tuple(n // e for n, e in zip(self.shape, self.edge))
+        self.mask = None
+        self.idx = torch.zeros(0, dtype=torch.int64)
+        self._idx32 = None
+        self._early = None
+        self.group = None
+        self._tables = {}
+        self.last_fraction = 0.0
+
+    def overlap_color_allreduce(self, enable: bool = True, group=None):
+        raise NotImplementedError("the touched set is only known once every gradient of the step is final")
+
+    @property
+    def fraction(self) -> float:
+        return self.last_fraction
+
+    def outside_is_zero(self) -> bool:
+        keep = torch.zeros(self.shape[0] * self.shape[1] * self.shape[2], dtype=torch.bool, device=self.idx.device)
+        keep[self.idx] = True
+        return all(not bool((self._rows(p.grad)[~keep] != 0).any()) for p in self.grids if p.grad is not None)
+
+    def _persistent(self, name: str, n: int, device) -> torch.Tensor:
+        buf = self.__dict__.get(name)
+        if buf is None or buf.numel() < n or buf.device != device:
+            buf = torch.empty(max(n, 1) * 5 // 4, dtype=torch.float32, device=device)     # head-room: K drifts step to step
+            self.__dict__[name] = buf
+        return buf[:n]
+
+    def block_flags(self, rows) -> torch.Tensor:
+        """int32 [Bx*By*Bz]: 1 where a block holds a non-zero in any of `rows` ([XYZ, C_j] views in memory order)"""
+        (bx, by, bz), (ex, ey, ez) = self.blocks, self.edge
+        cnt = None
+        for r in rows:
+            c = torch.count_nonzero(r.view(bx, ex, by, ey, bz, ez * r.shape[1]), dim=(1, 3, 5))
+            cnt = c if cnt is None else cnt + c
+        return (cnt > 0).to(torch.int32).reshape(-1)
+
+    def _block_tables(self, device):
+        t = self._tables.get(device)
+        if t is None:
+            (X, Y, Z), (bx, by, bz), (ex, ey, ez) = self.shape, self.blocks, self.edge
+            ar = lambda n: torch.arange(n, device=device, dtype=torch.int64)
+            base = ((ar(bx) * ex)[:, None, None] * Y + (ar(by) * ey)[None, :, None]) * Z + (ar(bz) * ez)[None, None, :]
+            within = (ar(ex)[:, None, None] * Y + ar(ey)[None, :, None]) * Z + ar(ez)[None, None, :]
+            t = self._tables[device] = (base.reshape(-1), within.reshape(-1))
+        return t
+
+    def select(self, flags: torch.Tensor) -> int:
+        """voxel list (self.idx) of the flagged blocks; returns the number of blocks"""
+        base, within = self._block_tables(flags.device)
+        blocks = torch.nonzero(flags).reshape(-1)              # the step's one host read
+        self.idx = (base[blocks][:, None] + within[None, :]).reshape(-1)
+        self._idx32 = self.idx.to(torch.int32) if self.idx.is_cuda else None
+        self.last_fraction = blocks.numel() / max(flags.numel(), 1)
+        return int(blocks.numel())
+
+    def allreduce(self, group=None, verify: bool = False) -> int:
+        import torch.distributed as dist
+
+        rows = self._grids_rows()
+        flags = self.block_flags(rows)
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+        self.select(flags)
+        if verify:
+            assert self.outside_is_zero(), "non-zero gradient outside the union of touched blocks"
+        grid_ids = {id(p) for p in self.grids}
+        others = [p for p in self.model.parameters() if id(p) not in grid_ids]
+        nbytes = allreduce_gradients(others, group) + flags.numel() * 4
+        if self.idx.numel() == 0:
+            return nbytes
+        buf = self.pack(rows, "_abuf")
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        self.unpack(rows, buf)
+        return nbytes + buf.numel() * buf.element_size()

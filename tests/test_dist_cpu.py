@@ -151,3 +151,77 @@ def test_two_rank_compacted_grid_allreduce_equals_dense_sum():
         p.join(120)
         assert p.exitcode == 0
     assert max(out.get(timeout=5), out.get(timeout=5)) == 0.0
+
+
+class _LtsGrids(torch.nn.Module):
+    """the four grid-gradient volumes of the LTS stage (sdf + off / emo / brdf colour grids, parameters' memory layout);
+    20 is not a multiple of 8: that axis falls back to 5-voxel blocks"""
+
+    def __init__(self, shape=(32, 32, 20)):
+        super().__init__()
+        mk = lambda c: torch.nn.Parameter(torch.zeros(1, c, *shape).contiguous(
+            memory_format=torch.channels_last_3d if c > 1 else torch.contiguous_format))
+        self.sdf, self.off_color, self.emo_color, self.brdf = (torch.nn.Module() for _ in range(4))
+        self.sdf.grid, self.off_color.grid, self.emo_color.grid, self.brdf.grid = mk(1), mk(6), mk(6), mk(6)
+        self.head = torch.nn.Linear(4, 2)
+
+
+def _sparse_grads(model, seed):
+    """random gradients confined to a few random voxels per volume (different voxels per rank and per volume)"""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for p in model.parameters():
+        v = torch.randn(p.shape, generator=g)
+        if p.dim() == 5:
+            keep = torch.zeros(p.shape[2:], dtype=torch.bool)
+            n = keep.numel()
+            keep.view(-1)[torch.randint(0, n, (2,), generator=g)] = True
+            v = (v * keep).contiguous(memory_format=torch.channels_last_3d if p.shape[1] > 1 else torch.contiguous_format)
+        out.append(v)
+    return out
+
+
+def _block_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from esr_nerf_b200.dist import TouchedBlockCompactor
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = _LtsGrids()
+    comp = TouchedBlockCompactor(model)
+    assert comp.edge == (8, 8, 5) and comp.blocks == (4, 4, 4) and len(comp.grids) == 4
+    err, sizes = 0.0, []
+    for step in range(3):                                     # the touched set changes every step; step 2: nothing touched
+        mine = _sparse_grads(model, 100 * step + rank)
+        other = _sparse_grads(model, 100 * step + (1 - rank))
+        if step == 2:
+            mine = [v * 0 if v.dim() == 5 else v for v in mine]
+            other = [v * 0 if v.dim() == 5 else v for v in other]
+        for p, v in zip(model.parameters(), mine):
+            p.grad = v.clone()
+        nbytes = comp.allreduce(verify=True)
+        sizes.append((comp.idx.numel(), nbytes))
+        for p, a, b in zip(model.parameters(), mine, other):
+            err = max(err, (p.grad - (a + b)).abs().max().item())     # two-term sums: exact
+        if step < 2:
+            assert 0 < comp.fraction < 1 and comp.idx.numel() % (8 * 8 * 5) == 0
+            assert nbytes < 4 * sum(p.numel() for p in model.parameters())      # less than the dense exchange
+    assert sizes[2][0] == 0 and comp.fraction == 0.0
+    out.put(err)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_touched_block_allreduce_equals_dense_sum():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_block_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert max(out.get(timeout=5), out.get(timeout=5)) == 0.0
