@@ -108,25 +108,7 @@ ESR_D void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
-ESR_D void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
-      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
 ESR_D void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-ESR_D void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 ESR_D void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -166,9 +148,6 @@ ESR_D uint32_t pair_mask(uint32_t mk, int j) {
   asm("prmt.b32 %0, %1, %1, 0xAA88;" : "=r"(d) : "r"(mk << (7 - j)));
   return d;
 }
-ESR_D float lo16(uint32_t v) { return __uint_as_float(v << 16); }
-ESR_D float hi16(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
-
 // ------------------------------------------------------------------------------------------------
 // image layout (bytes).  Every matrix is bf16 chunk-major [K/8][R][8].
 // ------------------------------------------------------------------------------------------------
@@ -1058,9 +1037,11 @@ __global__ void __launch_bounds__(160, 1)
     if (r < TC_TM) v.x = 0x00003f80u;  // bf16 1.0 in element 0
     *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_bytes + (KIN / 8) * (TC_TM * 16) + r * 16) = v;
   }
-  for (int i = threadIdx.x; i < 2 * (S::a_chunks - ACH) * TC_TM; i += blockDim.x) {
-    const int st = i / ((S::a_chunks - ACH) * TC_TM), r = i % ((S::a_chunks - ACH) * TC_TM);
-    *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_load + r * 16) = make_uint4(0, 0, 0, 0);
+  if constexpr (S::a_chunks > ACH) {
+    for (int i = threadIdx.x; i < 2 * (S::a_chunks - ACH) * TC_TM; i += blockDim.x) {
+      const int st = i / ((S::a_chunks - ACH) * TC_TM), r = i % ((S::a_chunks - ACH) * TC_TM);
+      *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_load + r * 16) = make_uint4(0, 0, 0, 0);
+    }
   }
   if (threadIdx.x == 0) {
     mbar_init(bar_full, 1), mbar_init(bar_full + 8, 1), mbar_init(bar_empty, 1), mbar_init(bar_empty + 8, 1);
