@@ -726,9 +726,11 @@ def main():
     _claim_stdout()
     a = parse()
     # a wedged device or collective must end the process, not the box's time limit: after ESR_BENCH_WATCHDOG_S seconds
-    # (default 20 min; a default run takes ~2) every thread's stack goes to stderr and the process exits non-zero
+    # (default 20 min + 1 s per step; a default run takes ~2 min) every thread's stack goes to stderr and the process exits non-zero
     import faulthandler
-    faulthandler.dump_traceback_later(float(os.environ.get("ESR_BENCH_WATCHDOG_S", "1200")), exit=True, file=sys.stderr)
+    if a.impl != "reference":    # (the CPU arm cannot wedge, and its run time is whatever --steps asks for)
+        faulthandler.dump_traceback_later(float(os.environ.get("ESR_BENCH_WATCHDOG_S", 1200 + a.steps)), exit=True,
+                                          file=sys.stderr)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
