@@ -165,6 +165,7 @@ PROTOTYPES = {
     "esr_grad_pack_floats": (I64, [P, I32, I64]),
     "esr_grad_pack": (I32, [P, P, I32, P, I64, P, P]),
     "esr_grad_unpack": (I32, [P, P, I32, P, I64, P, P]),
+    "esr_grad_block_flags": (I32, [P, P, I32, I32, I32, I32, I32, I32, I32, P, P]),
     "esr_mlp_param_count": (I64, [DESC_P]),
     "esr_mlp_image_bytes": (I64, [DESC_P]),
     "esr_mlp_act_rows": (I64, [I64]),

@@ -82,7 +82,68 @@ int launch(bool pack, void *const *volumes, const int32_t *channels, int n_volum
   return ESR_OK;
 }
 
+// Touched-block map of the exact two-level exchange (dist.TouchedBlockCompactor): block b = (bx, by, bz) of edge
+// (ex, ey, ez) voxels is ex * ey runs of ez * c contiguous floats in a channels-last volume.  One warp per
+// (volume, block): lanes stride over the block's floats run by run (coalesced within a run), one vote, lane 0 sets the
+// flag (every writer stores 1: no atomics).  Reads each volume once — HBM-stream bound.
+struct BlockGeo {
+  int32_t Y, Z;            // grid extent along y, z (x follows from the block count)
+  int32_t ex, ey, ez;      // block edge per axis (divides the grid extent)
+  int32_t by, bz;          // blocks along y, z
+  int64_t n_blocks;
+};
+
+__global__ void __launch_bounds__(256)
+    k_grad_block_flags(const __grid_constant__ RowSets rs, const __grid_constant__ BlockGeo g, int32_t *__restrict__ flags) {
+  const unsigned lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = g.n_blocks * rs.n;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+    const int j = (int)(w / g.n_blocks);
+    const int64_t b = w - (int64_t)j * g.n_blocks;
+    const int64_t bz = b % g.bz, by = (b / g.bz) % g.by, bx = b / ((int64_t)g.bz * g.by);
+    const int c = rs.chan[j];
+    const int run = g.ez * c;                      // contiguous floats of one z-run
+    const int per_block = g.ex * g.ey * run;
+    const float *vol = rs.vol[j];
+    bool nz = false;
+    for (int e = (int)lane; e < per_block; e += 32) {
+      const int r = e / run, t = e - r * run;      // run r = (i, jj) of the block's ex x ey footprint
+      const int i = r / g.ey, jj = r - i * g.ey;
+      const int64_t voxel = ((bx * g.ex + i) * g.Y + (by * g.ey + jj)) * g.Z + bz * g.ez;
+      nz |= __ldg(vol + voxel * c + t) != 0.f;
+    }
+    if (__any_sync(FULL, nz) && lane == 0) flags[b] = 1;
+  }
+}
+
 }  // namespace
+
+extern "C" int esr_grad_block_flags(void *const *volumes, const int32_t *channels, int n_volumes, int32_t gx, int32_t gy,
+                                    int32_t gz, int32_t ex, int32_t ey, int32_t ez, int32_t *flags, esr_stream_t stream) {
+  ESR_CHECK_ARG(volumes && channels && flags && n_volumes >= 1 && n_volumes <= ESR_MAX_GRAD_VOLUMES);
+  ESR_CHECK_ARG(gx > 0 && gy > 0 && gz > 0 && ex > 0 && ey > 0 && ez > 0 && gx % ex == 0 && gy % ey == 0 && gz % ez == 0);
+  RowSets rs;
+  for (int j = 0; j < ESR_MAX_GRAD_VOLUMES; ++j) {
+    const bool live = j < n_volumes;
+    ESR_CHECK_ARG(!live || (volumes[j] && channels[j] >= 1));
+    rs.vol[j] = live ? (float *)volumes[j] : nullptr;
+    rs.chan[j] = live ? channels[j] : 1;
+    rs.unit_end[j] = 0;
+    rs.buf_off[j] = 0;
+  }
+  rs.n = n_volumes;
+  BlockGeo g;
+  g.Y = gy, g.Z = gz, g.ex = ex, g.ey = ey, g.ez = ez;
+  g.by = gy / ey, g.bz = gz / ez;
+  g.n_blocks = (int64_t)(gx / ex) * g.by * g.bz;
+  ESR_CHECK_CUDA(cudaMemsetAsync(flags, 0, (size_t)g.n_blocks * sizeof(int32_t), (cudaStream_t)stream));
+  const int64_t want = (g.n_blocks * n_volumes + 7) / 8, cap = (int64_t)num_sms() * 32;   // 8 warps per CTA
+  ESR_STAGE("k_grad_block_flags", stream);
+  k_grad_block_flags<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(rs, g, flags);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
 
 extern "C" int64_t esr_grad_pack_floats(const int32_t *channels, int n_volumes, int64_t k) {
   if (!channels || n_volumes < 1 || n_volumes > ESR_MAX_GRAD_VOLUMES || k < 0) return -1;

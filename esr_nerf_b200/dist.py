@@ -4,6 +4,7 @@ step per training step (`torch.distributed` all_reduce: NCCL over NVLink on the 
 No other collective is on the path.  The reference has no distributed code at all (cfg/__init__.yaml:24)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, Iterable
 
 import torch
@@ -206,7 +207,7 @@ class TouchedBlockCompactor(GridGradCompactor):
     mask bounds, so the set is found per step, in two levels:
 
       1. every rank marks the blocks (8^3 voxels; per axis the largest divisor of the grid size <= 8) in which ANY of
-         its grid-gradient volumes holds a non-zero (one `count_nonzero` pass over each volume, in memory order);
+         its grid-gradient volumes holds a non-zero (`esr_grad_block_flags`: one launch, each volume read once);
       2. the ranks OR the flag maps (one 128 KB all-reduce(max) at 256^3) — every rank now holds the same union;
       3. the voxels of the union's blocks are packed / all-reduced / unpacked exactly like the static set
          (`esr_grad_pack` / `esr_grad_unpack`): a voxel outside the union is zero on every rank, so the result equals
@@ -256,7 +257,19 @@ class TouchedBlockCompactor(GridGradCompactor):
     def block_flags(self, rows) -> torch.Tensor:
         """int32 [Bx*By*Bz]: 1 where a block holds a non-zero in any of `rows` ([XYZ, C_j] views in memory order)"""
         (bx, by, bz), (ex, ey, ez) = self.blocks, self.edge
-        cnt = None
+        if rows[0].is_cuda and not os.environ.get("ESR_BLOCK_FLAGS_TORCH"):     # one launch of esr_grad_block_flags
+            import ctypes
+
+            from ._lib import check, lib, ptr, stream_ptr
+
+            c_arr = (ctypes.c_int32 * len(rows))(*[r.shape[1] for r in rows])
+            v_arr = (ctypes.c_void_p * len(rows))(*[r.data_ptr() for r in rows])
+            flags = self.__dict__.get("_flags")
+            if flags is None or flags.device != rows[0].device:
+                flags = self._flags = torch.empty(bx * by * bz, dtype=torch.int32, device=rows[0].device)
+            check(lib().esr_grad_block_flags(v_arr, c_arr, len(rows), *self.shape, ex, ey, ez, ptr(flags), stream_ptr()))
+            return flags
+        cnt = None      # host tensors of the gloo tests (and the A/B switch): the same map with torch reductions
         for r in rows:
             c = torch.count_nonzero(r.view(bx, ex, by, ey, bz, ez * r.shape[1]), dim=(1, 3, 5))
             cnt = c if cnt is None else cnt + c

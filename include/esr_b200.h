@@ -435,6 +435,15 @@ int esr_grad_pack(void *const *volumes, const int32_t *channels, int n_volumes, 
                   float *buf, esr_stream_t stream);
 int esr_grad_unpack(void *const *volumes, const int32_t *channels, int n_volumes, const int32_t *idx, int64_t k,
                     const float *buf, esr_stream_t stream);
+/*
+ * Touched-block map for gradients without a static support set (LTS / PDRA stage: eps-jittered samples and secondary
+ * rays, esrnerf.py:576-652, 807-830): flags[b] (int32 [gx/ex * gy/ey * gz/ez], block index ((bx * By) + by) * Bz + bz)
+ * is set to 1 where any of the volumes holds a non-zero float inside block b of (ex, ey, ez) voxels, else 0.  The edges
+ * must divide the grid extents.  The ranks OR-reduce the maps and exchange the voxels of the union with
+ * esr_grad_pack / esr_grad_unpack (esr_nerf_b200/dist.py:TouchedBlockCompactor).
+ */
+int esr_grad_block_flags(void *const *volumes, const int32_t *channels, int n_volumes, int32_t gx, int32_t gy, int32_t gz,
+                         int32_t ex, int32_t ey, int32_t ez, int32_t *flags, esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 3. Alphamask stage (DVGO, app/coarse/model/dvgo.py:140-288): dense [N x S] sampling, density / colour grids only

@@ -7,7 +7,8 @@
 #  1. default build: pytest -m gpu + the bench line (the committed MLP chains never ran on a GPU in their present form:
 #     a mechanical revert of the tile overlap on top of GPU-verified epilogue trims)
 #  2. ESR_MLP_TILE_OVERLAP=1 (the safe tile overlap, own mbarrier for the layer-0 commit): MLP / fine / LTS parity, bench
-#  3. N = 2: fine bench; LTS bench dense vs --block-exchange (dist.TouchedBlockCompactor, gloo-checked only)
+#  3. esr_grad_block_flags against its torch restatement; N = 2: fine bench; LTS bench dense vs --block-exchange
+#     (dist.TouchedBlockCompactor, gloo-checked only)
 #  4. N = 4: the hang of round 1's last call — three runs each without / with ESR_ALLREDUCE_OVERLAP=1
 # Every step runs under its own `timeout`, so a wedged kernel costs minutes, not the call; results land in gpurun_out/.
 cd "$(dirname "$0")/.." || exit 1
@@ -23,6 +24,7 @@ run() {  # run <name> <timeout_s> <command...>: stdout -> $O/name.json|log, stde
 
 run pytest_default 900 python -m pytest tests -m gpu -x -q
 run bench_default 400 python bench.py --steps 20
+ESR_TEST_UNVERIFIED=1 run pytest_block_flags 300 python -m pytest tests/test_gpu_native_ops.py -m gpu -x -q -k block_flags
 ESR_MLP_TILE_OVERLAP=1 run pytest_tile_overlap 900 python -m pytest tests/test_gpu_mlp.py tests/test_gpu_voxurff.py tests/test_gpu_esrnerf.py -m gpu -x -q
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap 400 python bench.py --steps 20 --no-cpu-baseline
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap_eval 400 python bench.py --stage eval --steps 5

@@ -225,3 +225,33 @@ def test_two_rank_touched_block_allreduce_equals_dense_sum():
         p.join(120)
         assert p.exitcode == 0
     assert max(out.get(timeout=5), out.get(timeout=5)) == 0.0
+
+
+def test_block_flag_kernel_index_math_restated():
+    """csrc/grad_exchange.cu:k_grad_block_flags walks block b of volume j as ex * ey runs of ez * c floats at
+    voxel ((bx ex + i) Y + by ey + jj) Z + bz ez.  The same arithmetic, restated with Python integers over a
+    channels-last volume, must give the block map the torch reduction of TouchedBlockCompactor.block_flags gives."""
+    from esr_nerf_b200.dist import TouchedBlockCompactor
+
+    model = _LtsGrids((16, 12, 10))
+    comp = TouchedBlockCompactor(model)
+    (X, Y, Z), (ex, ey, ez), (Bx, By, Bz) = comp.shape, comp.edge, comp.blocks
+    assert (ex, ey, ez) == (8, 6, 5)
+    for p, v in zip(model.parameters(), _sparse_grads(model, 5)):
+        p.grad = v.clone()
+    rows = comp._grids_rows()
+    want = comp.block_flags(rows)
+    got = torch.zeros(Bx * By * Bz, dtype=torch.int32)
+    for r in rows:
+        flat, c = r.reshape(-1), r.shape[1]
+        run = ez * c
+        for b in range(Bx * By * Bz):
+            bz, by, bx = b % Bz, (b // Bz) % By, b // (Bz * By)
+            for e in range(ex * ey * run):
+                rr, t = divmod(e, run)
+                i, jj = divmod(rr, ey)
+                voxel = ((bx * ex + i) * Y + (by * ey + jj)) * Z + bz * ez
+                if flat[voxel * c + t] != 0:
+                    got[b] = 1
+                    break
+    assert torch.equal(got, want) and 0 < int(want.sum()) < want.numel()
