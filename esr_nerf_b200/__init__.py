@@ -10,6 +10,8 @@ Public surface (mirrors the reference names):
     render_utils.total_variation_cuda.*   <- app/utils/base/cuda/total_variation.cpp
     render_utils.segment_coo              <- torch_scatter.segment_coo(reduce="sum")
     render_utils.Alphas2Weights           <- app/utils/base/module.py:117-143
+    samplers.BatchSampler / RayGroupManager <- utils2/utils.py:41-312 (index-only shuffles, rank slices)
+    optimizer.*                           <- app/utils/optimizer.py (fused Adam step)
 """
 from . import _lib  # noqa: F401
 from ._lib import EsrError, build  # noqa: F401
@@ -28,7 +30,7 @@ def __getattr__(name):  # lazy: importing the package must work on a box without
     if name == "VoxurfC":
         from .voxurfc import VoxurfC
         return VoxurfC
-    if name in ("render_utils", "fused", "modules", "synthetic", "voxurff", "voxurfc", "dvgo", "dist", "esrnerf", "pbr"):
+    if name in ("render_utils", "fused", "modules", "synthetic", "voxurff", "voxurfc", "dvgo", "dist", "esrnerf", "pbr", "samplers", "optimizer"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

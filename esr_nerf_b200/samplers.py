@@ -1,0 +1,226 @@
+"""The ray feed of the render step: drop-ins for the reference's `BatchSampler` and
+`RayGroupManager` (utils2/utils.py:41-312) with the same constructor arguments, the same `shuffle / filter / sample`
+behaviour, the same checkpointed state (`batch_st`, `data_idxs`, ...) and the same random draws (`torch.randperm` on the
+same device), so a run can resume a reference checkpoint and vice versa (fine.py:221-228, 484-485).
+
+What changes is what moves.  The reference keeps every key PHYSICALLY in sampling order: each `shuffle()` and `filter()`
+re-materialises the whole ray set (`data[k] = data[k][b_ids].contiguous()`, ~100 B per ray for six keys, 10^7-10^8 rays:
+gigabytes per epoch wrap, and a transient second copy of the set).  With the set resident in HBM (`data_preload: gpu`)
+this module never moves a ray: it keeps the data where it was loaded and permutes only the int64 index (`data_idxs` —
+the very tensor the reference checkpoints; the invariant `data[k] == loaded[k][data_idxs]` holds in the reference after
+every operation), and `sample()` gathers the batch's rows through it: batch_size random rows per key per step (~6 MB at
+2^16 rays), nothing per shuffle.  `data` / `uncert_data` / `cert_data` remain readable as mappings (pdra.py:888-889):
+a key is gathered when it is asked for.
+
+`rank / world` (no counterpart in the reference, which is single-process: cfg/__init__.yaml:24): every rank holds the
+same set and — seeded alike — draws the same permutations; `sample()` returns only the rank's contiguous slice of the
+global batch (`dist.shard_slice`, last global ray on the last rank), so no rank gathers rows it will not render.
+
+`data_preload: cpu` keeps the reference's pinned-host behaviour (the permuted copy is what makes its per-step slice a
+contiguous pinned block that can be copied asynchronously)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .dist import shard_slice
+from .modules import cfg_get
+
+
+def _check_preload(mode: str) -> bool:
+    assert "cpu" == mode or "gpu" in mode or "cuda" in mode      # utils2/utils.py:54-58
+    return mode == "cpu"
+
+
+class _Gathered:
+    """read-only mapping view `loaded[k][idx]` (what the reference holds as a physical copy)"""
+
+    def __init__(self, loaded: Dict[str, torch.Tensor], keys: List[str], idx_of):
+        self._loaded, self._keys, self._idx_of = loaded, keys, idx_of
+
+    def __getitem__(self, k):
+        return self._loaded[k][self._idx_of()]
+
+    def keys(self):
+        return list(self._keys)
+
+    def __iter__(self):
+        return iter(self._keys)
+
+    def __len__(self):
+        return len(self._keys)
+
+    def __contains__(self, k):
+        return k in self._keys
+
+
+def _pin(t: torch.Tensor) -> torch.Tensor:
+    return torch._pin_memory(t.contiguous()) if torch.cuda.is_available() else t.contiguous()
+
+
+class BatchSampler:
+    """utils2/utils.py:41-119"""
+
+    def __init__(self, cfg, data: Dict[str, torch.Tensor], keys: List[str], batch_size: int, batch_st: int = 0,
+                 data_idxs: Optional[torch.Tensor] = None, rank: int = 0, world: int = 1):
+        self.cfg = cfg
+        self.device = cfg_get(cfg, "system.device")
+        self.data_preload_to_cpu = _check_preload(cfg_get(cfg, "system.data_preload"))
+        self.keys = keys
+        self.batch_size = batch_size
+        self.batch_st = batch_st
+        self.rank, self.world = rank, world
+        self.data_idxs = torch.arange(len(data[keys[0]])) if data_idxs is None else data_idxs
+        if self.data_preload_to_cpu:
+            self.data_idxs = _pin(self.data_idxs.cpu())
+            self.data = data
+            for k in keys:
+                data[k] = _pin(data[k][self.data_idxs])
+        else:
+            self.data_idxs = self.data_idxs.to(self.device).contiguous()
+            self._loaded = {k: data[k].to(self.device) for k in keys}          # stays in load order for good
+            self.data = _Gathered(self._loaded, keys, lambda: self.data_idxs)
+
+    @property
+    def data_num(self) -> int:
+        return len(self.data_idxs)
+
+    def shuffle(self):
+        if self.data_preload_to_cpu:
+            b_ids = torch.randperm(self.data_num, pin_memory=torch.cuda.is_available())
+            self.data_idxs = _pin(self.data_idxs[b_ids])
+            for k in self.keys:
+                self.data[k] = _pin(self.data[k][b_ids])
+        else:
+            b_ids = torch.randperm(self.data_num, device=self.device)
+            self.data_idxs = self.data_idxs[b_ids].contiguous()
+        self.batch_st = 0
+
+    def filter(self, mask: torch.Tensor):
+        if self.data_preload_to_cpu:
+            mask = mask.cpu().contiguous()
+            for k in self.keys:
+                self.data[k] = _pin(self.data[k][mask])
+            self.data_idxs = _pin(self.data_idxs[mask])
+        else:
+            self.data_idxs = self.data_idxs[mask.to(self.device)].contiguous()
+
+    def sample(self) -> Dict[str, torch.Tensor]:
+        b_en = self.batch_st + self.batch_size
+        if b_en > self.data_num:
+            self.shuffle()
+            b_en = self.batch_size
+        b_st = self.batch_st
+        self.batch_st = b_en
+        sl = shard_slice(b_en - b_st, self.rank, self.world)
+        lo, hi = b_st + sl.start, b_st + sl.stop
+        if self.data_preload_to_cpu:
+            return {k: self.data[k][lo:hi].to(self.device, non_blocking=True) for k in self.keys}
+        rows = self.data_idxs[lo:hi]
+        return {k: self._loaded[k][rows] for k in self.keys}
+
+
+class RayGroupManager:
+    """utils2/utils.py:122-312: the uncertain / certain ray groups of the LTS / PDRA stages.  `filter(mask)` moves the
+    uncertain rays with mask False to the END of the certain group, in their current order."""
+
+    def __init__(self, cfg, data: Dict[str, torch.Tensor], keys: List[str], uncert_batch_size: int, cert_batch_size: int,
+                 uncert_batch_st: int = 0, cert_batch_st: int = 0, uncert_data_idxs: Optional[torch.Tensor] = None,
+                 cert_data_idxs: Optional[torch.Tensor] = None, rank: int = 0, world: int = 1):
+        self.cfg = cfg
+        self.device = cfg_get(cfg, "system.device")
+        self.data_preload_to_cpu = _check_preload(cfg_get(cfg, "system.data_preload"))
+        self.keys = keys
+        self.uncert_batch_size, self.cert_batch_size = uncert_batch_size, cert_batch_size
+        self.uncert_batch_st, self.cert_batch_st = uncert_batch_st, cert_batch_st
+        self.rank, self.world = rank, world
+        self.uncert_data_idxs = torch.arange(len(data[keys[0]])) if uncert_data_idxs is None else uncert_data_idxs
+        self.cert_data_idxs = torch.arange(0) if cert_data_idxs is None else cert_data_idxs
+        if self.data_preload_to_cpu:
+            self.uncert_data_idxs = _pin(self.uncert_data_idxs.cpu())
+            self.cert_data_idxs = _pin(self.cert_data_idxs.cpu())
+            self.uncert_data = {k: _pin(data[k][self.uncert_data_idxs]) for k in keys}
+            self.cert_data = {k: _pin(data[k][self.cert_data_idxs]) for k in keys}
+        else:
+            self.uncert_data_idxs = self.uncert_data_idxs.to(self.device).contiguous()
+            self.cert_data_idxs = self.cert_data_idxs.to(self.device).contiguous()
+            self._loaded = {k: data[k].to(self.device) for k in keys}
+            self.uncert_data = _Gathered(self._loaded, keys, lambda: self.uncert_data_idxs)
+            self.cert_data = _Gathered(self._loaded, keys, lambda: self.cert_data_idxs)
+
+    @property
+    def uncert_data_num(self) -> int:
+        return len(self.uncert_data_idxs)
+
+    @property
+    def cert_data_num(self) -> int:
+        return len(self.cert_data_idxs)
+
+    def shuffle(self):
+        self.shuffle_uncert()
+        self.shuffle_cert()
+
+    def _shuffle(self, which: str):
+        n = len(getattr(self, which + "_data_idxs"))
+        if self.data_preload_to_cpu:
+            b_ids = torch.randperm(n, pin_memory=torch.cuda.is_available())
+            setattr(self, which + "_data_idxs", _pin(getattr(self, which + "_data_idxs")[b_ids]))
+            d = getattr(self, which + "_data")
+            for k in self.keys:
+                d[k] = _pin(d[k][b_ids])
+        else:
+            b_ids = torch.randperm(n, device=self.device)
+            setattr(self, which + "_data_idxs", getattr(self, which + "_data_idxs")[b_ids].contiguous())
+        setattr(self, which + "_batch_st", 0)
+
+    def shuffle_uncert(self):
+        self._shuffle("uncert")
+
+    def shuffle_cert(self):
+        self._shuffle("cert")
+
+    def filter(self, mask: torch.Tensor):
+        if self.data_preload_to_cpu:
+            mask = mask.cpu().contiguous()
+            for k in self.keys:
+                self.cert_data[k] = _pin(torch.concat([self.cert_data[k], self.uncert_data[k][~mask]], dim=0))
+                self.uncert_data[k] = _pin(self.uncert_data[k][mask])
+            self.cert_data_idxs = _pin(torch.concat([self.cert_data_idxs, self.uncert_data_idxs[~mask]], dim=0))
+            self.uncert_data_idxs = _pin(self.uncert_data_idxs[mask])
+        else:
+            mask = mask.to(self.device).contiguous()
+            self.cert_data_idxs = torch.concat([self.cert_data_idxs, self.uncert_data_idxs[~mask]], dim=0).contiguous()
+            self.uncert_data_idxs = self.uncert_data_idxs[mask].contiguous()
+
+    def sample(self) -> Dict[str, torch.Tensor]:
+        uncert_b_en = self.uncert_batch_st + self.uncert_batch_size
+        cert_b_en = self.cert_batch_st + self.cert_batch_size
+        if uncert_b_en > self.uncert_data_num:
+            self.shuffle_uncert()
+            uncert_b_en = min(len(self.uncert_data_idxs), self.uncert_batch_size)
+        if cert_b_en > self.cert_data_num:
+            self.shuffle_cert()
+            cert_b_en = min(len(self.cert_data_idxs), self.cert_batch_size)
+        uncert_b_st, cert_b_st = self.uncert_batch_st, self.cert_batch_st
+        self.uncert_batch_st, self.cert_batch_st = uncert_b_en, cert_b_en
+        uncert_bs, cert_bs = uncert_b_en - uncert_b_st, cert_b_en - cert_b_st
+        if self.data_preload_to_cpu:
+            batch = {k: torch.concat([self.uncert_data[k][uncert_b_st:uncert_b_en],
+                                      self.cert_data[k][cert_b_st:cert_b_en]], dim=0) for k in self.keys}
+        else:
+            rows = torch.concat([self.uncert_data_idxs[uncert_b_st:uncert_b_en], self.cert_data_idxs[cert_b_st:cert_b_en]])
+            batch = None
+        masks = torch.ones(uncert_bs + cert_bs, dtype=torch.bool, device=self.device)
+        masks[-cert_bs:] = False      # utils2/utils.py:302 as written: with no certain ray ([-0:]) EVERY mask is False
+        sl = shard_slice(uncert_bs + cert_bs, self.rank, self.world)
+        if batch is None:
+            batch = {k: self._loaded[k][rows[sl]] for k in self.keys}
+        else:
+            batch = {k: v[sl].to(self.device, non_blocking=True) for k, v in batch.items()}
+        batch["uncert_masks"] = masks[sl]
+        return batch
+
+    def print_stats(self):
+        nuncert, ncert = self.uncert_data_num, self.cert_data_num
+        print(f"uncertain: {nuncert}\t certain: {ncert}\t uncertain/all: {nuncert / (nuncert + ncert) * 100}")

@@ -1,0 +1,151 @@
+"""CPU tests of the ray feed: esr_nerf_b200.samplers against the reference's own BatchSampler /
+RayGroupManager (utils2/utils.py:41-312, imported from /root/reference where it exists) under the same seeds — same
+batches, same checkpointed state — and, without the reference, against the invariants its code implies."""
+import importlib.util
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from esr_nerf_b200 import samplers as SM
+from esr_nerf_b200.dist import shard_slice
+
+KEYS = ["rays_o", "rgbs", "em_modes"]
+
+
+def _cfg(preload="cuda"):
+    return types.SimpleNamespace(system=types.SimpleNamespace(device="cpu", data_preload=preload))
+
+
+def _data(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return {"rays_o": torch.randn(n, 3, generator=g), "rgbs": torch.rand(n, 3, generator=g),
+            "em_modes": torch.randint(0, 2, (n,), generator=g), "unused": torch.zeros(n)}
+
+
+def _reference_module():
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        return None
+    H.install_stubs()                                    # omegaconf / wandb stand-ins (rich and tqdm are installed)
+    spec = importlib.util.spec_from_file_location("_ref_utils2_utils", os.path.join(H.REF_ROOT, "utils2", "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _same_batch(a, b):
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_batch_sampler_matches_reference_sequence():
+    ref_mod = _reference_module()
+    if ref_mod is None:
+        pytest.skip("/root/reference not present")
+    n, bs = 1000, 96
+    g = torch.Generator().manual_seed(3)
+    mask = torch.rand(n, generator=g) < 0.7
+    torch.manual_seed(11)
+    ref = ref_mod.BatchSampler(_cfg(), _data(n), KEYS, bs)
+    ref.filter(mask)
+    ref.shuffle()
+    ref_batches = [ref.sample() for _ in range(20)]      # wraps (re-shuffles) twice
+    torch.manual_seed(11)
+    mine = SM.BatchSampler(_cfg(), _data(n), KEYS, bs)
+    mine.filter(mask)
+    mine.shuffle()
+    for rb in ref_batches:
+        _same_batch(mine.sample(), rb)
+    assert mine.batch_st == ref.batch_st and torch.equal(mine.data_idxs, ref.data_idxs) and mine.data_num == ref.data_num
+    for k in KEYS:                                       # the physical copy the reference holds == the gathered view
+        assert torch.equal(mine.data[k], ref.data[k])
+    # resume from the checkpointed state (fine.py:221-228): same continuation
+    torch.manual_seed(5)
+    ref2 = ref_mod.BatchSampler(_cfg(), _data(n), KEYS, bs, ref.batch_st, ref.data_idxs.clone())
+    tail = [ref2.sample() for _ in range(12)]
+    torch.manual_seed(5)
+    mine2 = SM.BatchSampler(_cfg(), _data(n), KEYS, bs, mine.batch_st, mine.data_idxs.clone())
+    for rb in tail:
+        _same_batch(mine2.sample(), rb)
+
+
+def test_ray_group_manager_matches_reference_sequence():
+    ref_mod = _reference_module()
+    if ref_mod is None:
+        pytest.skip("/root/reference not present")
+    n = 700
+
+    def drive(cls):
+        torch.manual_seed(21)
+        m = cls(_cfg(), _data(n), KEYS, 64, 32)
+        m.shuffle()
+        out = [m.sample() for _ in range(3)]             # no certain rays yet: every uncert_mask is False (:302 quirk)
+        g = torch.Generator().manual_seed(8)
+        m.filter(torch.rand(m.uncert_data_num, generator=g) < 0.6)
+        out += [m.sample() for _ in range(15)]           # both groups wrap
+        m.filter(torch.rand(m.uncert_data_num, generator=g) < 0.05)     # uncertain group smaller than its batch size
+        out += [m.sample() for _ in range(4)]
+        return m, out
+
+    ref, ref_out = drive(ref_mod.RayGroupManager)
+    mine, my_out = drive(SM.RayGroupManager)
+    assert not ref_out[0]["uncert_masks"].any()
+    for a, b in zip(my_out, ref_out):
+        _same_batch(a, b)
+    for name in ("uncert_batch_st", "cert_batch_st", "uncert_data_num", "cert_data_num"):
+        assert getattr(mine, name) == getattr(ref, name), name
+    assert torch.equal(mine.uncert_data_idxs, ref.uncert_data_idxs) and torch.equal(mine.cert_data_idxs, ref.cert_data_idxs)
+    assert torch.equal(mine.uncert_data["rays_o"], ref.uncert_data["rays_o"])       # pdra.py:888
+    assert torch.equal(mine.cert_data["rgbs"], ref.cert_data["rgbs"])
+
+
+@pytest.mark.parametrize("preload", ["cuda", "cpu"])
+def test_sampler_invariants_and_rank_slices(preload):
+    """without the reference: every epoch visits each surviving ray once; the host-preload mode (physical copies) and the
+    index-only mode agree; the ranks' slices concatenate to the single-process batch, last ray on the last rank"""
+    n, bs = 500, 64
+    data = _data(n, 4)
+    mask = torch.arange(n) % 5 != 0
+    steps = 2 * (400 // bs)
+
+    def drive(mode, rank=0, world=1):        # (the re-shuffles at the epoch wraps draw from the global generator)
+        torch.manual_seed(1)
+        s = SM.BatchSampler(_cfg(mode), dict(data), KEYS, bs, rank=rank, world=world)
+        s.filter(mask)
+        s.shuffle()
+        out, seen = [], []
+        for step in range(steps):
+            out.append(s.sample())
+            if step < 400 // bs:
+                seen.append(s.data_idxs[s.batch_st - bs:s.batch_st].clone())
+        return s, out, torch.cat(seen)
+
+    one, batches, seen = drive(preload)
+    _, other_batches, _ = drive("cuda" if preload == "cpu" else "cpu")
+    parts = [drive(preload, r, 3)[1] for r in range(3)]
+    for i, b in enumerate(batches):
+        _same_batch(b, other_batches[i])
+        for k in KEYS:
+            assert torch.equal(torch.cat([p[i][k] for p in parts]), b[k])
+        assert parts[-1][i]["rays_o"].shape[0] == shard_slice(bs, 2, 3).stop - shard_slice(bs, 2, 3).start
+        assert torch.equal(parts[-1][i]["rays_o"][-1], b["rays_o"][-1])
+    assert seen.unique().numel() == seen.numel() and mask[seen].all()
+    for k in KEYS:
+        assert torch.equal(one.data[k], data[k][one.data_idxs])
+
+    def drive_groups(rank=0, world=1):
+        torch.manual_seed(2)
+        m = SM.RayGroupManager(_cfg(preload), dict(data), KEYS, 40, 24, rank=rank, world=world)
+        m.filter(torch.arange(n) % 2 == 0)
+        return [m.sample() for _ in range(12)]
+
+    full, halves = drive_groups(), [drive_groups(r, 2) for r in range(2)]
+    for i, b in enumerate(full):
+        for k in KEYS + ["uncert_masks"]:
+            assert torch.equal(torch.cat([h[i][k] for h in halves]), b[k])
+        assert int(b["uncert_masks"].sum()) == 40 and b["uncert_masks"].numel() == 64
