@@ -224,3 +224,41 @@ class RayGroupManager:
     def print_stats(self):
         nuncert, ncert = self.uncert_data_num, self.cert_data_num
         print(f"uncertain: {nuncert}\t certain: {ncert}\t uncertain/all: {nuncert / (nuncert + ncert) * 100}")
+
+
+@torch.no_grad()
+def update_ray_groups(renderer, sampler: RayGroupManager, k_val: float, eval_uncert_bs: int, rank: int = 0, world: int = 1,
+                      group=None) -> torch.Tensor:
+    """pdra.py:882-932: the emission sweep over ALL uncertain training rays that re-partitions the
+    ray groups every `update_step` steps — `renderer.eval_emit` on chunks of `eval_uncert_bs` rays, a ray stays
+    uncertain while max_c emission > k_val, the rest join the certain group (`sampler.filter`).
+
+    The inference path at data-set scale (10^7-10^8 rays per sweep), so it is sharded like the render step: each rank
+    sweeps a contiguous slice of the uncertain set (rows gathered chunk by chunk through the sampler's index — the set
+    itself is never copied), writes its per-ray maxima into a zero vector, and ONE all-reduce(sum) of that vector (4 B
+    per ray) gives every rank the same mask, hence the same groups.  Rays are independent in every kernel of the path,
+    so the result does not depend on where the chunk or rank boundaries fall.  Returns the mask it applied."""
+    device = sampler.device
+    rows_all = sampler.uncert_data_idxs
+    n = len(rows_all)
+    peak = torch.zeros(n, dtype=torch.float32, device=device)
+    was_training = getattr(renderer, "training", False)
+    renderer.eval()
+    sl = shard_slice(n, rank, world)
+    for lo in range(sl.start, sl.stop, eval_uncert_bs):
+        hi = min(lo + eval_uncert_bs, sl.stop)
+        if sampler.data_preload_to_cpu:
+            batch = {k: sampler.uncert_data[k][lo:hi].to(device) for k in ("rays_o", "rays_d", "viewdirs")}
+        else:
+            rows = rows_all[lo:hi]
+            batch = {k: sampler._loaded[k][rows] for k in ("rays_o", "rays_d", "viewdirs")}
+        peak[lo:hi] = torch.max(renderer.eval_emit(**batch), dim=-1)[0]
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(peak, op=dist.ReduceOp.SUM, group=group)      # slices are disjoint: the sum is a concatenation
+    mask = peak > k_val
+    sampler.filter(mask)
+    if was_training:
+        renderer.train()
+    return mask

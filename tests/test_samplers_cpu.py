@@ -149,3 +149,100 @@ def test_sampler_invariants_and_rank_slices(preload):
         for k in KEYS + ["uncert_masks"]:
             assert torch.equal(torch.cat([h[i][k] for h in halves]), b[k])
         assert int(b["uncert_masks"].sum()) == 40 and b["uncert_masks"].numel() == 64
+
+
+class _FakeRenderer:
+    """eval_emit as a per-ray function (what the render path is: rays are independent), recording its chunk sizes"""
+
+    def __init__(self):
+        self.training, self.chunks = True, []
+
+    def eval(self):
+        self.training = False
+
+    def train(self):
+        self.training = True
+
+    def eval_emit(self, rays_o, rays_d, viewdirs):
+        self.chunks.append(rays_o.shape[0])
+        return (rays_o * viewdirs).abs() + rays_d[:, :1] ** 2
+
+
+def _sweep_data(n):
+    g = torch.Generator().manual_seed(9)
+    return {k: torch.randn(n, 3, generator=g) for k in ("rays_o", "rays_d", "viewdirs")}
+
+
+def _reference_update(renderer, sampler, k_val, bs):
+    """pdra.py:882-932 restated on the sampler's public state: full gather, chunk loop, max over channels, filter"""
+    ro, rd, vd = (sampler.uncert_data[k] for k in ("rays_o", "rays_d", "viewdirs"))
+    emission = torch.zeros_like(ro)
+    for idx in torch.arange(len(emission)).split(bs):
+        emission[idx] = renderer.eval_emit(rays_o=ro[idx], rays_d=rd[idx], viewdirs=vd[idx])
+    mask = torch.max(emission, dim=-1)[0] > k_val
+    sampler.filter(mask)
+    return mask
+
+
+@pytest.mark.parametrize("preload", ["cuda", "cpu"])
+def test_update_ray_groups_matches_restated_sweep(preload):
+    n, keys = 1000, ["rays_o", "rays_d", "viewdirs"]
+    torch.manual_seed(4)
+    a = SM.RayGroupManager(_cfg(preload), dict(_sweep_data(n)), keys, 64, 32)
+    a.shuffle()
+    torch.manual_seed(4)
+    b = SM.RayGroupManager(_cfg(preload), dict(_sweep_data(n)), keys, 64, 32)
+    b.shuffle()
+    r = _FakeRenderer()
+    for k_val in (0.3, 0.8):                              # two successive sweeps: the second over the survivors
+        want = _reference_update(_FakeRenderer(), b, k_val, 96)
+        r.chunks.clear()
+        got = SM.update_ray_groups(r, a, k_val, 96)
+        assert torch.equal(got, want) and 0 < int(got.sum()) < got.numel()
+        assert torch.equal(a.uncert_data_idxs, b.uncert_data_idxs) and torch.equal(a.cert_data_idxs, b.cert_data_idxs)
+        assert r.training and max(r.chunks) <= 96 and sum(r.chunks) == got.numel()
+
+
+def _sweep_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    keys = ["rays_o", "rays_d", "viewdirs"]
+    torch.manual_seed(4)
+    m = SM.RayGroupManager(_cfg(), dict(_sweep_data(1001)), keys, 64, 32, rank=rank, world=world)
+    m.shuffle()
+    r = _FakeRenderer()
+    mask = SM.update_ray_groups(r, m, 0.3, 96, rank=rank, world=world)
+    out.put((rank, sum(r.chunks), mask, m.uncert_data_idxs, m.cert_data_idxs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_update_ray_groups_two_ranks_agree_with_one():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([out.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    keys = ["rays_o", "rays_d", "viewdirs"]
+    torch.manual_seed(4)
+    single = SM.RayGroupManager(_cfg(), dict(_sweep_data(1001)), keys, 64, 32)
+    single.shuffle()
+    want = _reference_update(_FakeRenderer(), single, 0.3, 96)
+    assert res[0][1] + res[1][1] == 1001 and abs(res[0][1] - res[1][1]) <= 1        # each rank swept its half
+    for _, _, mask, unc, cert in res:
+        assert torch.equal(mask, want)
+        assert torch.equal(unc, single.uncert_data_idxs) and torch.equal(cert, single.cert_data_idxs)
