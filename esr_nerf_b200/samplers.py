@@ -36,11 +36,27 @@ def _check_preload(mode: str) -> bool:
 class _Gathered:
     """read-only mapping view `loaded[k][idx]` (what the reference holds as a physical copy)"""
 
-    def __init__(self, loaded: Dict[str, torch.Tensor], keys: List[str], idx_of):
+    def __init__(self, loaded: Dict[str, torch.Tensor], keys: List[str], idx_of, owned: Optional[set] = None):
         self._loaded, self._keys, self._idx_of = loaded, keys, idx_of
+        self._owned = set() if owned is None else owned      # keys whose load-order tensor this sampler allocated
+        self._n = len(loaded[keys[0]])
 
     def __getitem__(self, k):
         return self._loaded[k][self._idx_of()]
+
+    def __setitem__(self, k, v):
+        """`group_data[k] = v` with v in the group's current order (pdra.py:1023-1036 attaches per-ray edit attributes
+        to both groups this way): scattered into the load-order tensor of key k, created on first use"""
+        idx = self._idx_of()
+        v = v.to(idx.device)
+        full = self._loaded.get(k)
+        if full is None or full.dtype != v.dtype or full.shape[1:] != v.shape[1:]:
+            full = torch.zeros((self._n,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        elif k not in self._owned:
+            full = full.clone()                      # the loaded tensor may be the caller's own
+        self._owned.add(k)
+        full[idx] = v
+        self._loaded[k] = full
 
     def keys(self):
         return list(self._keys)
@@ -146,8 +162,9 @@ class RayGroupManager:
             self.uncert_data_idxs = self.uncert_data_idxs.to(self.device).contiguous()
             self.cert_data_idxs = self.cert_data_idxs.to(self.device).contiguous()
             self._loaded = {k: data[k].to(self.device) for k in keys}
-            self.uncert_data = _Gathered(self._loaded, keys, lambda: self.uncert_data_idxs)
-            self.cert_data = _Gathered(self._loaded, keys, lambda: self.cert_data_idxs)
+            owned = set()
+            self.uncert_data = _Gathered(self._loaded, keys, lambda: self.uncert_data_idxs, owned)
+            self.cert_data = _Gathered(self._loaded, keys, lambda: self.cert_data_idxs, owned)
 
     @property
     def uncert_data_num(self) -> int:

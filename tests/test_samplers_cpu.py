@@ -246,3 +246,40 @@ def test_update_ray_groups_two_ranks_agree_with_one():
     for _, _, mask, unc, cert in res:
         assert torch.equal(mask, want)
         assert torch.equal(unc, single.uncert_data_idxs) and torch.equal(cert, single.cert_data_idxs)
+
+
+def test_group_attributes_attached_like_filter_edit_rays():
+    """pdra.py:1023-1037: per-ray edit attributes are ASSIGNED to both groups' data mappings (in group order), two keys
+    are appended to sampler.keys, then the uncertain group is filtered; the batches that follow carry the new keys"""
+    ref_mod = _reference_module()
+    if ref_mod is None:
+        pytest.skip("/root/reference not present")
+    n = 400
+
+    def drive(cls):
+        torch.manual_seed(31)
+        data = _data(n, 6)
+        keep = data["em_modes"].clone()
+        m = cls(_cfg(), data, list(KEYS), 48, 16)
+        m.shuffle()
+        g = torch.Generator().manual_seed(2)
+        m.filter(torch.rand(n, generator=g) < 0.5)
+        nu, nc = m.uncert_data_num, m.cert_data_num
+        m.uncert_data["em_modes"] = torch.randint(0, 5, (nu,), generator=g)
+        m.uncert_data["em_colors"] = torch.rand(nu, 2, generator=g)
+        m.uncert_data["em_intensities"] = torch.rand(nu, generator=g)
+        m.cert_data["em_modes"] = torch.zeros(nc, dtype=torch.long)
+        m.cert_data["em_colors"] = torch.zeros(nc, 2)
+        m.cert_data["em_intensities"] = torch.zeros(nc)
+        m.keys.extend(["em_colors", "em_intensities"])
+        m.filter(torch.rand(nu, generator=g) < 0.7)
+        return m, [m.sample() for _ in range(10)], keep, data
+
+    ref, ref_out, _, _ = drive(ref_mod.RayGroupManager)
+    mine, my_out, keep, data = drive(SM.RayGroupManager)
+    assert set(my_out[0]) == set(KEYS) | {"em_colors", "em_intensities", "uncert_masks"}
+    for a, b in zip(my_out, ref_out):
+        _same_batch(a, b)
+    for k in mine.keys:
+        assert torch.equal(mine.uncert_data[k], ref.uncert_data[k]) and torch.equal(mine.cert_data[k], ref.cert_data[k])
+    assert torch.equal(data["em_modes"], keep)           # the caller's tensor was not written through
