@@ -279,3 +279,93 @@ def update_ray_groups(renderer, sampler: RayGroupManager, k_val: float, eval_unc
     if was_training:
         renderer.train()
     return mask
+
+
+def dilate_masks(em_masks: torch.Tensor, ks: int) -> torch.Tensor:
+    """cv2.dilate(masks, np.ones((ks, ks)), iterations=1) of pdra.py:946-961 on [n, h, w] masks, on the device: a
+    ks x ks maximum whose anchor is the kernel centre (ks // 2, ks // 2) — for the shipped even size (10,
+    cfg/app/pdra.yaml:132) the window reaches ks // 2 pixels towards smaller and ks - 1 - ks // 2 towards larger
+    indices — and pixels outside the image do not take part."""
+    import torch.nn.functional as F
+
+    a = ks // 2
+    x = F.pad(em_masks.float()[:, None], (a, ks - 1 - a, a, ks - 1 - a), value=float("-inf"))
+    return F.max_pool2d(x, kernel_size=ks, stride=1)[:, 0]
+
+
+@torch.no_grad()
+def filter_edit_rays(renderer, sampler: RayGroupManager, test_data: Dict[str, torch.Tensor], image_size, focal_length: float,
+                     mask_dilation_ks: int, eval_bs: int, rank: int = 0, world: int = 1, group=None) -> RayGroupManager:
+    """pdra.py:934-1038: before the finetune stage every uncertain training ray is traced to its
+    emissive surface point (`renderer.eval_esp`), the point is projected into the edit view, and rays that land inside
+    a (dilated) edit mask receive that mask's edit (`em_modes / em_colors / em_intensities`, LightDict of
+    utils2/utils.py:32-38); the others leave the uncertain group.  Same arithmetic as the reference, including its
+    bounds test (both image coordinates against both h - 1 and w - 1, :995) and "later masks overwrite earlier ones".
+
+    Sharded like `update_ray_groups`: each rank sweeps a contiguous slice of the uncertain set, one all-reduce(sum) of
+    the per-ray results [n, 5] (hit, mode - 1, colour x 2, intensity; zero outside the rank's slice) makes the groups
+    identical on every rank."""
+    import torch.nn.functional as F
+
+    device = sampler.device
+    w, h = image_size
+    f = focal_length
+    w2c = torch.inverse(test_data["poses"]).to(device)
+    K = torch.tensor([[-f, 0.0, w / 2.0 - 0.5], [0.0, f, h / 2.0 - 0.5], [0.0, 0.0, 1.0]]).to(device, dtype=torch.float32)
+    em_masks = dilate_masks(test_data["em_masks"].view(-1, h, w).to(device), mask_dilation_ks).view(-1, 1, h, w)
+    n_cond = len(em_masks)
+
+    rows_all = sampler.uncert_data_idxs
+    n = len(rows_all)
+    res = torch.zeros(n, 5, dtype=torch.float32, device=device)      # hit, mode - 1, colour (2), intensity
+    was_training = getattr(renderer, "training", False)
+    renderer.eval()
+    sl = shard_slice(n, rank, world)
+    for lo in range(sl.start, sl.stop, eval_bs):
+        hi = min(lo + eval_bs, sl.stop)
+        if sampler.data_preload_to_cpu:
+            batch = {k: sampler.uncert_data[k][lo:hi].to(device) for k in ("rays_o", "rays_d", "viewdirs")}
+        else:
+            rows = rows_all[lo:hi]
+            batch = {k: sampler._loaded[k][rows] for k in ("rays_o", "rays_d", "viewdirs")}
+        esp = renderer.eval_esp(**batch)
+        esp = torch.concat([esp, torch.ones_like(esp[..., :1])], dim=-1).T
+        xyz = w2c @ esp
+        cam_coord = xyz[:3] / xyz[-1:]
+        xyz = K @ cam_coord
+        img_coord = (xyz[:2] / xyz[-1:]).T
+        out_bound = (img_coord < 0) | (img_coord > (h - 1)) | (img_coord > (w - 1))
+        in_bound = (out_bound[..., 0] | out_bound[..., 1]).bitwise_not()
+        img_coord = img_coord[in_bound]
+        img_coord[..., 0] = img_coord[..., 0] / (w - 1) * 2 - 1
+        img_coord[..., 1] = img_coord[..., 1] / (h - 1) * 2 - 1
+        img_coord = img_coord.view(1, 1, -1, 2).repeat(n_cond, 1, 1, 1)
+        m = (F.grid_sample(em_masks, img_coord, align_corners=True, mode="bilinear") > 0).view(n_cond, -1)
+        where = torch.arange(lo, hi, device=device)[in_bound]
+        res[where, 0] = (torch.sum(m, dim=0) > 0).float()
+        for i in range(n_cond):
+            hit = where[m[i]]
+            mode = int(test_data["em_modes"][i])
+            res[hit, 1] = float(mode - 1)
+            if mode == 0:                                   # LightDict["off"]
+                res[hit, 4] = 0.0
+            if mode in (2, 4):                              # i_change, ic_change
+                res[hit, 4] = test_data["em_intensities"][i].to(device, dtype=torch.float32)
+            if mode in (3, 4):                              # c_change, ic_change
+                res[hit, 2:4] = test_data["em_colors"][i][:2].to(device, dtype=torch.float32)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(res, op=dist.ReduceOp.SUM, group=group)
+    nc = sampler.cert_data_num
+    sampler.uncert_data["em_modes"] = res[:, 1].round().long() + 1
+    sampler.uncert_data["em_colors"] = res[:, 2:4].contiguous()
+    sampler.uncert_data["em_intensities"] = res[:, 4].contiguous()
+    sampler.cert_data["em_modes"] = torch.zeros(nc, dtype=torch.long, device=device)
+    sampler.cert_data["em_colors"] = torch.zeros(nc, 2, dtype=torch.float32, device=device)
+    sampler.cert_data["em_intensities"] = torch.zeros(nc, dtype=torch.float32, device=device)
+    sampler.keys.extend(["em_colors", "em_intensities"])
+    sampler.filter(res[:, 0] > 0)
+    if was_training:
+        renderer.train()
+    return sampler

@@ -283,3 +283,140 @@ def test_group_attributes_attached_like_filter_edit_rays():
     for k in mine.keys:
         assert torch.equal(mine.uncert_data[k], ref.uncert_data[k]) and torch.equal(mine.cert_data[k], ref.cert_data[k])
     assert torch.equal(data["em_modes"], keep)           # the caller's tensor was not written through
+
+
+def _reference_pdra_class():
+    """the reference's PDRA trainer class (app/fine/pdra.py), imported only for its `filter_edit_rays` method: the
+    trainer's other dependencies (data sets, metrics, config managers) are given empty stand-ins"""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        return None
+    H.install_stubs()
+    ref_utils = _reference_module()
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("app", AppClass=object)
+    mod("app.fine.model", ESRNeRF=object)
+    mod("data", DataClass=object)
+    mod("utils2.image", apply_gamma_curve=None)
+    mod("utils2.manager", save_cfg=None)
+    mod("utils2.metric", IoU=None, loss2psnr=None, rgb_lpips=None, rgb_ssim=None)
+    mod("utils2.utils", LightDict=ref_utils.LightDict, RayGroupManager=ref_utils.RayGroupManager,
+        import_class=ref_utils.import_class, tqdm_safe=lambda it, **kw: it)
+    spec = importlib.util.spec_from_file_location("_ref_app_fine_pdra", os.path.join(H.REF_ROOT, "app", "fine", "pdra.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.PDRA, ref_utils
+
+
+class _FakeEsp(_FakeRenderer):
+    """eval_esp: a point on each ray (per-ray function)"""
+
+    def eval_esp(self, rays_o, rays_d, viewdirs):
+        self.chunks.append(rays_o.shape[0])
+        return rays_o + 2.5 * viewdirs
+
+
+def _edit_case(n=1500, w=48, h=40):
+    g = torch.Generator().manual_seed(12)
+    o = torch.randn(n, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, -3.0])
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * 0.25 + torch.tensor([0.0, 0.0, 1.0]), dim=-1)
+    data = {"rays_o": o, "rays_d": d * 1.1, "viewdirs": d, "em_modes": torch.ones(n, dtype=torch.long)}
+    pose = torch.eye(4)
+    pose[:3, :3] = torch.tensor([[-1.0, 0, 0], [0, 1.0, 0], [0, 0, -1.0]])       # camera looking down +z from z = -3
+    pose[:3, 3] = torch.tensor([0.0, 0.0, -3.0])
+    masks = torch.zeros(4, h, w)
+    masks[0, 5:12, 6:20] = 1
+    masks[1, 18:30, 25:40] = 1
+    masks[2, 8:25, 15:30] = 1            # overlaps 0 and 1: later masks overwrite
+    masks[3, 30:38, 2:10] = 1
+    test = {"poses": pose, "em_masks": masks.reshape(4, -1), "em_modes": torch.tensor([0, 2, 4, 3]),
+            "em_intensities": torch.tensor([0.0, 2.5, 0.3, 1.0]), "em_colors": torch.rand(4, 3, generator=g)}
+    return data, test, (w, h), 30.0
+
+
+def test_filter_edit_rays_matches_reference_method():
+    got = _reference_pdra_class()
+    if got is None:
+        pytest.skip("/root/reference not present")
+    PDRA, ref_utils = got
+    keys = ["rays_o", "rays_d", "viewdirs", "em_modes"]
+    data, test, (w, h), focal = _edit_case()
+    torch.manual_seed(3)
+    ref_s = ref_utils.RayGroupManager(_cfg(), dict(data), list(keys), 64, 32)
+    ref_s.shuffle()
+    ref_s.filter(torch.arange(ref_s.uncert_data_num) % 7 != 0)           # a non-empty certain group
+    me = types.SimpleNamespace(train_dataset=types.SimpleNamespace(image_size=(w, h), focal_length=focal), device="cpu",
+                               mask_dilation_ks=10, eval_bs=256, renderer=_FakeEsp())
+    PDRA.filter_edit_rays(me, ref_s, test)
+    torch.manual_seed(3)
+    mine = SM.RayGroupManager(_cfg(), dict(data), list(keys), 64, 32)
+    mine.shuffle()
+    mine.filter(torch.arange(mine.uncert_data_num) % 7 != 0)
+    r = _FakeEsp()
+    SM.filter_edit_rays(r, mine, test, (w, h), focal, 10, 256)
+    assert 0 < mine.uncert_data_num < 1500 and r.training
+    assert mine.keys == ref_s.keys
+    assert torch.equal(mine.uncert_data_idxs, ref_s.uncert_data_idxs) and torch.equal(mine.cert_data_idxs, ref_s.cert_data_idxs)
+    for k in mine.keys:
+        assert torch.equal(mine.uncert_data[k], ref_s.uncert_data[k]), k
+        assert torch.equal(mine.cert_data[k], ref_s.cert_data[k]), k
+    assert len(set(mine.uncert_data["em_modes"].tolist())) >= 3          # several edits present among the kept rays
+    torch.manual_seed(9)
+    a = [mine.sample() for _ in range(6)]
+    torch.manual_seed(9)
+    b = [ref_s.sample() for _ in range(6)]
+    for x, y in zip(a, b):
+        _same_batch(x, y)
+
+
+def _edit_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data, test, size, focal = _edit_case()
+    torch.manual_seed(3)
+    m = SM.RayGroupManager(_cfg(), dict(data), ["rays_o", "rays_d", "viewdirs", "em_modes"], 64, 32, rank=rank, world=world)
+    m.shuffle()
+    r = _FakeEsp()
+    SM.filter_edit_rays(r, m, test, size, focal, 10, 256, rank=rank, world=world)
+    out.put((rank, sum(r.chunks), m.uncert_data_idxs, m.cert_data_idxs, {k: m.uncert_data[k] for k in m.keys}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_filter_edit_rays_two_ranks_agree_with_one():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_edit_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([out.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    data, test, size, focal = _edit_case()
+    torch.manual_seed(3)
+    single = SM.RayGroupManager(_cfg(), dict(data), ["rays_o", "rays_d", "viewdirs", "em_modes"], 64, 32)
+    single.shuffle()
+    SM.filter_edit_rays(_FakeEsp(), single, test, size, focal, 10, 256)
+    assert res[0][1] + res[1][1] == 1500 and res[0][1] == res[1][1]
+    for _, _, unc, cert, vals in res:
+        assert torch.equal(unc, single.uncert_data_idxs) and torch.equal(cert, single.cert_data_idxs)
+        for k in single.keys:
+            assert torch.equal(vals[k], single.uncert_data[k]), k
