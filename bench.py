@@ -85,6 +85,9 @@ def parse():
                          "step; NOT part of the metric BASELINE.json names (render step only), off by default")
     ap.add_argument("--dense-allreduce", action="store_true",
                     help="N>1: all-reduce the dense grid gradients instead of the occupancy-compacted voxel set")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="eval, N>1: leave every rank's slice of the maps where it is (default: gathered on rank 0 inside the "
+                         "timed step, dist.gather_maps — gloo-checked, not yet measured on NCCL)")
     ap.add_argument("--block-exchange", action="store_true",
                     help="N>1: exact two-level exchange of the grid gradients (dist.TouchedBlockCompactor: OR-reduced map of "
                          "touched 8^3 blocks, then pack / all-reduce / unpack of their voxels) instead of the static "
@@ -442,7 +445,7 @@ def build_stage(a, dev, rank):
 
 def run_b200(a, rank, world, local_rank):
     from esr_nerf_b200 import _lib, fused
-    from esr_nerf_b200.dist import GridGradCompactor, TouchedBlockCompactor, allreduce_gradients
+    from esr_nerf_b200.dist import GridGradCompactor, TouchedBlockCompactor, allreduce_gradients, gather_maps
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 render path has no CPU fallback")
@@ -502,6 +505,9 @@ def run_b200(a, rank, world, local_rank):
             outs.append(model(rays_o=b["rays_o"][sl], rays_d=b["rays_d"][sl], viewdirs=b["viewdirs"][sl],
                               em_modes=torch.tensor(0), **fwd_kw))
         out = {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+        if dist is not None and not a.no_gather:     # configs[3]: the image's maps end up on rank 0 (one gather per image)
+            full = gather_maps(out, n * world, rank, world)
+            out = full if full is not None else out
         return out, out["etc/depth"].mean()
 
     step = eval_step if a.stage == "eval" else train_step

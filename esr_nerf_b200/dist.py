@@ -312,3 +312,53 @@ class TouchedBlockCompactor(GridGradCompactor):
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         self.unpack(rows, buf)
         return nbytes + buf.numel() * buf.element_size()
+
+
+def gather_maps(maps: Dict[str, torch.Tensor], n_total: int, rank: int, world: int, group=None, dst: int = 0):
+    """Per-ray output maps of a ray-sharded render (each rank holds the rows of `shard_slice(n_total, rank, world)`)
+    -> the full [n_total, ...] maps on rank `dst` (None elsewhere): SURVEY.md §8e, BASELINE.json configs[3] (1600x1200
+    full-image inference, 12 maps).  The maps are packed side by side into ONE [rows, sum C] float buffer, padded to the
+    common slice length (only the last rank's slice can be shorter), and gathered with one collective."""
+    import torch.distributed as dist
+
+    keys = sorted(maps)
+    per = (n_total + world - 1) // world
+    widths = [int(torch.Size(maps[k].shape[1:]).numel()) for k in keys]      # (explicit: an empty slice has no rows to infer from)
+    cols = [maps[k].reshape(maps[k].shape[0], wd) for k, wd in zip(keys, widths)]
+    assert all(c.dtype == torch.float32 for c in cols), "render maps are fp32"
+    packed = torch.zeros(per, sum(widths), dtype=torch.float32, device=cols[0].device)
+    packed[:cols[0].shape[0]] = torch.cat(cols, dim=1)
+    if world == 1:
+        full = packed
+    else:
+        out = [torch.empty_like(packed) for _ in range(world)] if rank == dst else None
+        dist.gather(packed, out, dst=dst, group=group)
+        if rank != dst:
+            return None
+        full = torch.cat(out, dim=0)
+    full = full[:n_total]
+    res, off = {}, 0
+    for k, wd in zip(keys, widths):
+        res[k] = full[:, off:off + wd].reshape(n_total, *maps[k].shape[1:])
+        off += wd
+    return res
+
+
+@torch.no_grad()
+def render_image_sharded(model, rays: Dict[str, torch.Tensor], rank: int, world: int, chunk: int = 1 << 18, group=None,
+                         **forward_kwargs):
+    """One full image through `model.forward_evaluate` on `world` GPUs: contiguous pixel ranges per rank, `chunk` rays
+    per call, all maps gathered on rank 0 (None on the other ranks).  `rays`: the image's [n, 3] rays_o / rays_d /
+    viewdirs (every rank holds them, or at least its own slice's rows at the right positions)."""
+    n = rays["rays_o"].shape[0]
+    sl = shard_slice(n, rank, world)
+    outs = []
+    for lo in range(sl.start, sl.stop, chunk):
+        hi = min(lo + chunk, sl.stop)
+        outs.append(model(rays_o=rays["rays_o"][lo:hi], rays_d=rays["rays_d"][lo:hi], viewdirs=rays["viewdirs"][lo:hi],
+                          **forward_kwargs))
+    if not outs:        # more ranks than rays: an empty slice still takes part in the collective
+        proto = model(rays_o=rays["rays_o"][:0], rays_d=rays["rays_d"][:0], viewdirs=rays["viewdirs"][:0], **forward_kwargs)
+        outs = [proto]
+    local = {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+    return gather_maps(local, n, rank, world, group)

@@ -3,6 +3,7 @@ reproduce the single-process gradient of a sum-over-rays loss."""
 import os
 import socket
 
+import pytest
 import torch
 import torch.multiprocessing as mp
 
@@ -255,3 +256,51 @@ def test_block_flag_kernel_index_math_restated():
                     got[b] = 1
                     break
     assert torch.equal(got, want) and 0 < int(want.sum()) < want.numel()
+
+
+class _FakeImageModel:
+    """forward_evaluate stand-in: per-ray maps of different widths (rays are independent on the render path)"""
+
+    def __call__(self, rays_o, rays_d, viewdirs, em_modes=None, scale=1.0):
+        # (elementwise, exactly rounded ops only: a vectorised transcendental may round differently at chunk tails)
+        return {"srgb/rgb": rays_o * scale + 1.0, "etc/depth": rays_o[:, 0] * rays_d[:, 1],
+                "etc/normal": viewdirs * 0.5 + 0.5, "etc/white_bg": rays_d[:, :1].abs()}
+
+
+def _image_rays(n):
+    g = torch.Generator().manual_seed(77)
+    return {k: torch.randn(n, 3, generator=g) for k in ("rays_o", "rays_d", "viewdirs")}
+
+
+def _image_worker(rank, world, port, out, n):
+    import torch.distributed as dist
+
+    from esr_nerf_b200.dist import render_image_sharded
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = render_image_sharded(_FakeImageModel(), _image_rays(n), rank, world, chunk=50, em_modes=torch.tensor(0), scale=2.0)
+    out.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [301, 2])        # 301: the last rank's slice is shorter; 2 rays on 3 ranks: an empty slice
+def test_sharded_image_render_gathers_every_map_on_rank0(n):
+    from esr_nerf_b200.dist import render_image_sharded
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_image_worker, args=(r, 3, port, out, n)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = render_image_sharded(_FakeImageModel(), _image_rays(n), 0, 1, chunk=64, em_modes=torch.tensor(0), scale=2.0)
+    assert res[1] is None and res[2] is None
+    assert set(res[0]) == set(want)
+    for k in want:
+        assert res[0][k].shape == want[k].shape and torch.equal(res[0][k], want[k]), k
