@@ -35,6 +35,8 @@ if [ "$NGPU" -ge 2 ]; then
   run bench_lts_n2_dense 500 $TR --nproc-per-node 2 --master-port 29512 bench.py --gpus 2 --stage lts
   run bench_lts_n2_blocks 500 $TR --nproc-per-node 2 --master-port 29513 bench.py --gpus 2 --stage lts --block-exchange
   run bench_fine_n2_blocks 400 $TR --nproc-per-node 2 --master-port 29514 bench.py --gpus 2 --block-exchange
+  run bench_eval_n2_gather 400 $TR --nproc-per-node 2 --master-port 29515 bench.py --gpus 2 --stage eval --steps 5
+  run bench_eval_n2_nogather 400 $TR --nproc-per-node 2 --master-port 29516 bench.py --gpus 2 --stage eval --steps 5 --no-gather
 fi
 if [ "$NGPU" -ge 4 ]; then
   for i in 1 2 3; do
