@@ -1,0 +1,214 @@
+"""Explicit-state model check (CPU) of the mbarrier protocols of the tcgen05 MLP forward chain
+(esr_nerf_b200/csrc/mlp_tc.cu:k_mlp_fwd_tc; the data-gradient chain k_mlp_dgrad_tc has the same structure with the
+d_x accumulator in place of the output layer).
+
+Three protocols are explored over EVERY interleaving of the MMA issuer thread, the epilogue warps and the (in-order,
+asynchronous) tensor-core engine, for a CTA that processes several tiles:
+
+  * "per_tile"  — the default build: every tile starts behind a __syncthreads, one mbarrier `bar` takes every commit;
+  * "ovl_own"   — the opt-in tile overlap (template parameter OVL, ESR_MLP_TILE_OVERLAP=1): the next tile's layer-0 MMA
+                  is issued behind this tile's output-layer MMA once all warps have arrived on `bar_x`, and commits to
+                  its OWN mbarrier `bar_first`;
+  * "ovl_shared" — the variant withdrawn at the end of round 1: the same overlap with the layer-0 commit on `bar`.
+
+Model: an mbarrier is (completed phases, pending arrivals); `try_wait.parity P` succeeds iff the parity of the phase in
+progress differs from P — so a waiter that sleeps through TWO completions sees its own parity again and never wakes.
+Every TMEM / shared-memory region carries the (tile, layer) tag of its last writer; a reader asserts the tag it expects,
+which catches an accumulator overwritten before a slow warp has read it and an operand consumed before it is complete.
+The checker must prove the first two protocols free of deadlock and tag violations, and must FIND the hang of the third
+(the diagnosis behind DESIGN.md §4 "Tile overlap (withdrawn)")."""
+from collections import deque
+
+import pytest
+
+W = 2            # epilogue warps in the model (16 in the kernel: the protocol is symmetric in them)
+
+
+def build_programs(proto: str, n_tiles: int, nh: int):
+    """op lists of the issuer (thread 0) and the W epilogue warps (threads 1..W), with the parities each thread's
+    toggling phase variables take at every wait (static: the control flow does not depend on data)"""
+    ovl = proto != "per_tile"
+    first_bar = "bar_first" if proto == "ovl_own" else "bar"
+    d = lambda i: f"D{i & 1}"
+
+    issuer, cphase, xphase, n_sync = [], 0, 0, 0
+    mma_id = 0
+
+    def layer0(tile):
+        nonlocal mma_id
+        issuer.append(("issue", mma_id, ("x", tile), d(0), (tile, 0), first_bar))
+        mma_id += 1
+
+    for t in range(n_tiles):
+        more = t + 1 < n_tiles
+        if not ovl or t == 0:
+            issuer.append(("sync", n_sync))
+            n_sync += 1
+            layer0(t)
+        for l in range(nh):                       # layer l + 1 (l + 1 == nh: the output layer) behind the chunk barrier
+            issuer.append(("wait", "chunk", cphase))
+            issuer.append(("issue", mma_id, ("A", (t, l)), d(l + 1), (t, l + 1), "bar"))
+            mma_id += 1
+            cphase ^= 1
+        if ovl and more:
+            issuer.append(("wait", "bar_x", xphase))
+            xphase ^= 1
+            layer0(t + 1)
+
+    warps = []
+    for w in range(W):
+        ops, phase, fphase, n_sync = [("loadx", w, 0)], 0, 0, 0
+        for t in range(n_tiles):
+            more = t + 1 < n_tiles
+            if not ovl or t == 0:
+                ops.append(("sync", n_sync))
+                n_sync += 1
+            for l in range(nh):
+                if l == 0 and proto == "ovl_own":
+                    ops.append(("wait", "bar_first", fphase))
+                    fphase ^= 1
+                else:
+                    ops.append(("wait", "bar", phase))
+                    phase ^= 1
+                if l == 0 and more:
+                    ops.append(("loadx", w, t + 1))          # the x tile is free: prefetch the next one
+                ops.append(("read", d(l), (t, l)))
+                ops.append(("writeA", w, (t, l)))
+                ops.append(("arrive", "chunk"))
+            if ovl and more:
+                ops.append(("arrive", "bar_x"))
+            ops.append(("wait", "bar", phase))
+            phase ^= 1
+            ops.append(("read", d(nh), (t, nh)))
+        warps.append(ops)
+    return [issuer] + warps
+
+
+BARS = {"bar": 1, "bar_first": 1, "bar_x": W, "chunk": W}
+BAR_NAMES = sorted(BARS)
+
+
+def explore(proto: str, n_tiles: int, nh: int, limit: int = 4_000_000):
+    """BFS over all interleavings -> (states, deadlocks, violations)"""
+    progs = build_programs(proto, n_tiles, nh)
+    mmas = [op for op in progs[0] if op[0] == "issue"]
+    issued_before = []                                       # number of MMAs issued once the issuer's pc has passed op i
+    n = 0
+    for op in progs[0]:
+        issued_before.append(n)
+        n += op[0] == "issue"
+    issued_before.append(n)
+    n_threads = len(progs)
+    n_syncs = max((op[1] for p in progs for op in p if op[0] == "sync"), default=-1) + 1
+
+    # state: pcs, bars ((done, pending) per name), tags (D0, D1, x[w]..., A[w]...), engine position, sync arrivals
+    tags0 = (None, None) + tuple([None] * W) + tuple([None] * W)
+    init = (tuple([0] * n_threads), tuple((0, BARS[b]) for b in BAR_NAMES), tags0, 0, tuple([0] * n_syncs))
+    seen, todo = {init}, deque([init])
+    deadlocks, violations = [], []
+
+    def arrive(bars, name):
+        i = BAR_NAMES.index(name)
+        done, pend = bars[i]
+        pend -= 1
+        if pend == 0:
+            done, pend = done + 1, BARS[name]
+        return bars[:i] + ((done, pend),) + bars[i + 1:]
+
+    while todo:
+        st = todo.popleft()
+        pcs, bars, tags, eng, syncs = st
+        succ = []
+        # the tensor-core engine retires the next issued MMA (in order, at any time after its issue)
+        if eng < issued_before[pcs[0]]:
+            _, _, src, dst, tag, commit = mmas[eng]
+            if src[0] == "x":
+                ok = all(tags[2 + w] == src[1] for w in range(W))
+            else:
+                ok = all(tags[2 + W + w] == src[1] for w in range(W))
+            if not ok:
+                violations.append(("operand", mmas[eng], tags))
+            t2 = list(tags)
+            t2[0 if dst == "D0" else 1] = tag
+            succ.append((pcs, arrive(bars, commit), tuple(t2), eng + 1, syncs))
+        for th in range(n_threads):
+            if pcs[th] >= len(progs[th]):
+                continue
+            op = progs[th][pcs[th]]
+            nxt = pcs[:th] + (pcs[th] + 1,) + pcs[th + 1:]
+            if op[0] == "wait":
+                done, _ = bars[BAR_NAMES.index(op[1])]
+                if (done & 1) != op[2]:
+                    succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "sync":                  # __syncthreads: register the arrival (bit th), pass when all have
+                k, full = op[1], (1 << n_threads) - 1
+                if not (syncs[k] >> th) & 1:
+                    succ.append((pcs, bars, tags, eng, syncs[:k] + (syncs[k] | (1 << th),) + syncs[k + 1:]))
+                elif syncs[k] == full:
+                    succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "arrive":
+                succ.append((nxt, arrive(bars, op[1]), tags, eng, syncs))
+            elif op[0] == "issue":
+                succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "read":
+                if tags[0 if op[1] == "D0" else 1] != op[2]:
+                    violations.append(("accumulator", th, op, tags))
+                succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "writeA":
+                t2 = list(tags)
+                t2[2 + W + op[1]] = op[2]
+                succ.append((nxt, bars, tuple(t2), eng, syncs))
+            elif op[0] == "loadx":
+                t2 = list(tags)
+                t2[2 + op[1]] = op[2]
+                succ.append((nxt, bars, tuple(t2), eng, syncs))
+        finished = all(pcs[t] >= len(progs[t]) for t in range(n_threads)) and eng == len(mmas)
+        if not succ and not finished:
+            deadlocks.append(st)
+        for s in succ:
+            if s not in seen:
+                seen.add(s)
+                todo.append(s)
+        assert len(seen) < limit, "state space larger than expected"
+    return len(seen), deadlocks, violations
+
+
+@pytest.mark.parametrize("nh", [1, 3])
+@pytest.mark.parametrize("proto", ["per_tile", "ovl_own"])
+def test_protocol_is_free_of_deadlock_and_hazards(proto, nh):
+    states, deadlocks, violations = explore(proto, n_tiles=3, nh=nh)
+    assert states > 100
+    assert not deadlocks, f"{proto}: {len(deadlocks)} deadlocked states, e.g. {deadlocks[0]}"
+    assert not violations, f"{proto}: {violations[0]}"
+
+
+@pytest.mark.parametrize("nh", [1, 3])
+def test_shared_barrier_overlap_can_hang(nh):
+    """the withdrawn variant: the output-layer commit and the next tile's layer-0 commit both land on `bar` while a
+    slow warp still sits in front of its wait for the first of them -> it sees its own parity again and never wakes"""
+    _, deadlocks, _ = explore("ovl_shared", n_tiles=3, nh=nh)
+    assert deadlocks, "the model did not reproduce the double phase completion"
+    pcs, bars, _, _, _ = deadlocks[0]
+    progs = build_programs("ovl_shared", 3, nh)
+    stuck = [progs[t][pcs[t]] for t in range(len(progs)) if pcs[t] < len(progs[t])]
+    assert any(op[0] == "wait" and op[1] == "bar" for op in stuck)
+
+
+def test_even_hidden_layer_count_is_rejected_for_a_reason():
+    """the kernels' static_assert(!OVL || (NH & 1)): with an even number of hidden layers the output accumulator is D0,
+    which the next tile's layer-0 MMA overwrites while a slow warp still reads it — the model finds exactly that"""
+    _, deadlocks, violations = explore("ovl_own", n_tiles=3, nh=2)
+    assert not deadlocks and violations and all(v[0] == "accumulator" for v in violations)
+    assert not explore("per_tile", n_tiles=3, nh=2)[2]          # the per-tile barrier has no such restriction
+
+
+def test_three_warps_four_tiles(monkeypatch):
+    """a larger instance of the same model (3 epilogue warps, 4 tiles): same verdicts"""
+    import test_mbarrier_protocol_cpu as M
+
+    monkeypatch.setattr(M, "W", 3)
+    monkeypatch.setattr(M, "BARS", {"bar": 1, "bar_first": 1, "bar_x": 3, "chunk": 3})
+    for proto in ("per_tile", "ovl_own"):
+        states, deadlocks, violations = M.explore(proto, n_tiles=4, nh=3)
+        assert states > 1000 and not deadlocks and not violations, proto
+    assert M.explore("ovl_shared", n_tiles=4, nh=3)[1]
