@@ -212,3 +212,158 @@ def test_three_warps_four_tiles(monkeypatch):
         states, deadlocks, violations = M.explore(proto, n_tiles=4, nh=3)
         assert states > 1000 and not deadlocks and not violations, proto
     assert M.explore("ovl_shared", n_tiles=4, nh=3)[1]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generic checker (named regions, multi-region MMAs, named barriers) + the two-slot tone-map forward (k_tonemap_fwd2)
+# ------------------------------------------------------------------------------------------------------------------
+def explore_generic(progs, bar_counts, limit=4_000_000):
+    """progs[0] = issuer.  Ops:
+         ("wait", bar, parity) ("arrive", bar)
+         ("sync", key, n_participants)                         named / CTA barrier instance `key`
+         ("read", region, expected_tag) ("write", ((region, tag), ...))
+         ("issue", reads ((region, expected), ...), writes ((region, tag), ...), commit_bar)   issuer only
+    Returns (states, deadlocks, violations)."""
+    bar_names = sorted(bar_counts)
+    regions = sorted({r for p in progs for op in p for r in (
+        [op[1]] if op[0] == "read" else [x[0] for x in op[1]] if op[0] == "write" else
+        [x[0] for x in op[1]] + [x[0] for x in op[2]] if op[0] == "issue" else [])})
+    sync_keys = sorted({op[1] for p in progs for op in p if op[0] == "sync"})
+    mmas = [op for op in progs[0] if op[0] == "issue"]
+    issued_before, n = [], 0
+    for op in progs[0]:
+        issued_before.append(n)
+        n += op[0] == "issue"
+    issued_before.append(n)
+    init = (tuple([0] * len(progs)), tuple((0, bar_counts[b]) for b in bar_names), tuple([None] * len(regions)), 0,
+            tuple([0] * len(sync_keys)))
+    seen, todo, deadlocks, violations = {init}, deque([init]), [], []
+
+    def arrive(bars, name):
+        i = bar_names.index(name)
+        done, pend = bars[i]
+        pend -= 1
+        if pend == 0:
+            done, pend = done + 1, bar_counts[name]
+        return bars[:i] + ((done, pend),) + bars[i + 1:]
+
+    def put(tags, writes):
+        t2 = list(tags)
+        for r, tag in writes:
+            t2[regions.index(r)] = tag
+        return tuple(t2)
+
+    while todo:
+        st = todo.popleft()
+        pcs, bars, tags, eng, syncs = st
+        succ = []
+        if eng < issued_before[pcs[0]]:
+            _, reads, writes, commit = mmas[eng]
+            for r, exp in reads:
+                if tags[regions.index(r)] != exp:
+                    violations.append(("operand", eng, r, exp, tags[regions.index(r)]))
+            succ.append((pcs, arrive(bars, commit), put(tags, writes), eng + 1, syncs))
+        for th in range(len(progs)):
+            if pcs[th] >= len(progs[th]):
+                continue
+            op = progs[th][pcs[th]]
+            nxt = pcs[:th] + (pcs[th] + 1,) + pcs[th + 1:]
+            if op[0] == "wait":
+                if (bars[bar_names.index(op[1])][0] & 1) != op[2]:
+                    succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "sync":
+                k = sync_keys.index(op[1])
+                if not (syncs[k] >> th) & 1:
+                    succ.append((pcs, bars, tags, eng, syncs[:k] + (syncs[k] | (1 << th),) + syncs[k + 1:]))
+                elif bin(syncs[k]).count("1") == op[2]:
+                    succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "arrive":
+                succ.append((nxt, arrive(bars, op[1]), tags, eng, syncs))
+            elif op[0] == "issue":
+                succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "read":
+                if tags[regions.index(op[1])] != op[2]:
+                    violations.append(("read", th, op, tags[regions.index(op[1])]))
+                succ.append((nxt, bars, tags, eng, syncs))
+            elif op[0] == "write":
+                succ.append((nxt, bars, put(tags, op[1]), eng, syncs))
+        done = all(pcs[t] >= len(progs[t]) for t in range(len(progs))) and eng == len(mmas)
+        if not succ and not done:
+            deadlocks.append(st)
+        for s in succ:
+            if s not in seen:
+                seen.add(s)
+                todo.append(s)
+        assert len(seen) < limit, "state space larger than expected"
+    return len(seen), deadlocks, violations
+
+
+def tonemap_fwd2_programs(n_my: int, n_warps: int, named_barrier: bool = True):
+    """k_tonemap_fwd2 (mlp_tc.cu): two tiles in flight in slots s = i & 1.  Regions per slot: x_s[w] (encoded tile, one
+    part per warp), D_s (layer-0 accumulator; the bf16 A operand is written OVER it, part A_s[w] per warp — the first
+    A write destroys D_s for every warp, hence the named barrier between the D_s reads and the A_s writes), O_s."""
+    issuer = []
+
+    def mma0(i):
+        s = i & 1
+        issuer.append(("issue", tuple((f"x{s}_{w}", i) for w in range(n_warps)),
+                       ((f"D{s}", (i, "d")),) + tuple((f"A{s}_{w}", None) for w in range(n_warps)), f"mma0_{s}"))
+
+    for i in range(min(2, n_my)):
+        issuer.append(("wait", f"x_{i}", 0))
+        mma0(i)
+    for i in range(n_my):
+        s = i & 1
+        issuer.append(("wait", f"a_{s}", (i >> 1) & 1))
+        issuer.append(("issue", tuple((f"A{s}_{w}", (i, "a")) for w in range(n_warps)), ((f"O{s}", (i, "o")),), f"out_{s}"))
+        if i + 2 < n_my:
+            issuer.append(("wait", f"x_{s}", ((i + 2) >> 1) & 1))
+            mma0(i + 2)
+    warps = []
+    for w in range(n_warps):
+        ops = []
+
+        def load_x(i):
+            ops.append(("write", ((f"x{i & 1}_{w}", i),)))
+            ops.append(("arrive", f"x_{i & 1}"))
+
+        def out_epilogue(i):
+            ops.append(("wait", f"out_{i & 1}", (i >> 1) & 1))
+            ops.append(("read", f"O{i & 1}", (i, "o")))
+
+        for i in range(min(2, n_my)):
+            load_x(i)
+        for i in range(n_my):
+            s = i & 1
+            ops.append(("wait", f"mma0_{s}", (i >> 1) & 1))
+            if i + 2 < n_my:
+                load_x(i + 2)
+            ops.append(("read", f"D{s}", (i, "d")))
+            if named_barrier:
+                ops.append(("sync", ("named", i), n_warps))
+            ops.append(("write", ((f"A{s}_{w}", (i, "a")), (f"D{s}", ("overwritten by A", i)))))
+            ops.append(("arrive", f"a_{s}"))
+            if i >= 1:
+                out_epilogue(i - 1)
+        if n_my >= 1:
+            out_epilogue(n_my - 1)
+        warps.append(ops)
+    bars = {}
+    for s in range(2):
+        bars.update({f"x_{s}": n_warps, f"mma0_{s}": 1, f"a_{s}": n_warps, f"out_{s}": 1})
+    return [issuer] + warps, bars
+
+
+@pytest.mark.parametrize("n_my", [1, 2, 3, 5])
+def test_tonemap_two_slot_forward_protocol(n_my):
+    progs, bars = tonemap_fwd2_programs(n_my, n_warps=2)
+    states, deadlocks, violations = explore_generic(progs, bars)
+    assert states > 20 and not deadlocks and not violations, (deadlocks[:1], violations[:1])
+
+
+def test_tonemap_two_slot_forward_needs_its_named_barrier():
+    """without `bar.sync 1` between the D_s reads and the A_s writes a fast warp's A operand lands on accumulator
+    columns a slow warp has not read yet: the model must see it (sensitivity check of the checker itself)"""
+    progs, bars = tonemap_fwd2_programs(3, n_warps=2, named_barrier=False)
+    _, deadlocks, violations = explore_generic(progs, bars)
+    assert not deadlocks and any(v[0] == "read" for v in violations)
