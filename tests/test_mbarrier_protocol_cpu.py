@@ -222,30 +222,45 @@ def explore_generic(progs, bar_counts, limit=4_000_000):
          ("wait", bar, parity) ("arrive", bar)
          ("sync", key, n_participants)                         named / CTA barrier instance `key`
          ("read", region, expected_tag) ("write", ((region, tag), ...))
-         ("issue", reads ((region, expected), ...), writes ((region, tag), ...), commit_bar)   issuer only
+         ("issue", reads ((region, expected), ...), writes ((region, tag), ...), commit_bar)   issuer only: tcgen05.mma
+                                                               + commit, retired IN ORDER by the tensor-core engine
+         ("tma", bar, ((copy_id, writes), ...))                mbarrier.arrive.expect_tx on `bar` + one cp.async.bulk per
+                                                               copy; copies complete in ANY order (complete_tx)
+    An mbarrier is (completed phases, pending arrivals, pending transactions): the phase completes when both reach 0.
     Returns (states, deadlocks, violations)."""
     bar_names = sorted(bar_counts)
-    regions = sorted({r for p in progs for op in p for r in (
-        [op[1]] if op[0] == "read" else [x[0] for x in op[1]] if op[0] == "write" else
-        [x[0] for x in op[1]] + [x[0] for x in op[2]] if op[0] == "issue" else [])})
-    sync_keys = sorted({op[1] for p in progs for op in p if op[0] == "sync"})
+
+    def op_regions(op):
+        if op[0] == "read":
+            return [op[1]]
+        if op[0] == "write":
+            return [x[0] for x in op[1]]
+        if op[0] == "issue":
+            return [x[0] for x in op[1]] + [x[0] for x in op[2]]
+        if op[0] == "tma":
+            return [x[0] for c in op[2] for x in c[1]]
+        return []
+
+    regions = sorted({r for p in progs for op in p for r in op_regions(op)})
+    sync_keys = sorted({op[1] for p in progs for op in p if op[0] == "sync"}, key=repr)
     mmas = [op for op in progs[0] if op[0] == "issue"]
+    copies = {c[0]: (op[1], c[1]) for p in progs for op in p if op[0] == "tma" for c in op[2]}
     issued_before, n = [], 0
     for op in progs[0]:
         issued_before.append(n)
         n += op[0] == "issue"
     issued_before.append(n)
-    init = (tuple([0] * len(progs)), tuple((0, bar_counts[b]) for b in bar_names), tuple([None] * len(regions)), 0,
-            tuple([0] * len(sync_keys)))
+    init = (tuple([0] * len(progs)), tuple((0, bar_counts[b], 0) for b in bar_names), tuple([None] * len(regions)), 0,
+            tuple([0] * len(sync_keys)), frozenset())
     seen, todo, deadlocks, violations = {init}, deque([init]), [], []
 
-    def arrive(bars, name):
+    def update(bars, name, arrivals=0, tx=0):
         i = bar_names.index(name)
-        done, pend = bars[i]
-        pend -= 1
-        if pend == 0:
+        done, pend, ptx = bars[i]
+        pend, ptx = pend - arrivals, ptx + tx
+        if pend == 0 and ptx == 0:
             done, pend = done + 1, bar_counts[name]
-        return bars[:i] + ((done, pend),) + bars[i + 1:]
+        return bars[:i] + ((done, pend, ptx),) + bars[i + 1:]
 
     def put(tags, writes):
         t2 = list(tags)
@@ -255,14 +270,18 @@ def explore_generic(progs, bar_counts, limit=4_000_000):
 
     while todo:
         st = todo.popleft()
-        pcs, bars, tags, eng, syncs = st
+        pcs, bars, tags, eng, syncs, flying = st
         succ = []
         if eng < issued_before[pcs[0]]:
             _, reads, writes, commit = mmas[eng]
             for r, exp in reads:
                 if tags[regions.index(r)] != exp:
                     violations.append(("operand", eng, r, exp, tags[regions.index(r)]))
-            succ.append((pcs, arrive(bars, commit), put(tags, writes), eng + 1, syncs))
+            b2 = update(bars, commit, arrivals=1) if commit is not None else bars      # (None: covered by a later commit)
+            succ.append((pcs, b2, put(tags, writes), eng + 1, syncs, flying))
+        for cid in flying:                                   # any copy in flight may land next
+            bar, writes = copies[cid]
+            succ.append((pcs, update(bars, bar, tx=-1), put(tags, writes), eng, syncs, flying - {cid}))
         for th in range(len(progs)):
             if pcs[th] >= len(progs[th]):
                 continue
@@ -270,30 +289,33 @@ def explore_generic(progs, bar_counts, limit=4_000_000):
             nxt = pcs[:th] + (pcs[th] + 1,) + pcs[th + 1:]
             if op[0] == "wait":
                 if (bars[bar_names.index(op[1])][0] & 1) != op[2]:
-                    succ.append((nxt, bars, tags, eng, syncs))
+                    succ.append((nxt, bars, tags, eng, syncs, flying))
             elif op[0] == "sync":
                 k = sync_keys.index(op[1])
                 if not (syncs[k] >> th) & 1:
-                    succ.append((pcs, bars, tags, eng, syncs[:k] + (syncs[k] | (1 << th),) + syncs[k + 1:]))
+                    succ.append((pcs, bars, tags, eng, syncs[:k] + (syncs[k] | (1 << th),) + syncs[k + 1:], flying))
                 elif bin(syncs[k]).count("1") == op[2]:
-                    succ.append((nxt, bars, tags, eng, syncs))
+                    succ.append((nxt, bars, tags, eng, syncs, flying))
             elif op[0] == "arrive":
-                succ.append((nxt, arrive(bars, op[1]), tags, eng, syncs))
+                succ.append((nxt, update(bars, op[1], arrivals=1), tags, eng, syncs, flying))
             elif op[0] == "issue":
-                succ.append((nxt, bars, tags, eng, syncs))
+                succ.append((nxt, bars, tags, eng, syncs, flying))
+            elif op[0] == "tma":
+                b2 = update(update(bars, op[1], tx=len(op[2])), op[1], arrivals=1)
+                succ.append((nxt, b2, tags, eng, syncs, flying | {c[0] for c in op[2]}))
             elif op[0] == "read":
                 if tags[regions.index(op[1])] != op[2]:
                     violations.append(("read", th, op, tags[regions.index(op[1])]))
-                succ.append((nxt, bars, tags, eng, syncs))
+                succ.append((nxt, bars, tags, eng, syncs, flying))
             elif op[0] == "write":
-                succ.append((nxt, bars, put(tags, op[1]), eng, syncs))
-        done = all(pcs[t] >= len(progs[t]) for t in range(len(progs))) and eng == len(mmas)
+                succ.append((nxt, bars, put(tags, op[1]), eng, syncs, flying))
+        done = all(pcs[t] >= len(progs[t]) for t in range(len(progs))) and eng == len(mmas) and not flying
         if not succ and not done:
             deadlocks.append(st)
-        for s in succ:
-            if s not in seen:
-                seen.add(s)
-                todo.append(s)
+        for s2 in succ:
+            if s2 not in seen:
+                seen.add(s2)
+                todo.append(s2)
         assert len(seen) < limit, "state space larger than expected"
     return len(seen), deadlocks, violations
 
@@ -367,3 +389,110 @@ def test_tonemap_two_slot_forward_needs_its_named_barrier():
     progs, bars = tonemap_fwd2_programs(3, n_warps=2, named_barrier=False)
     _, deadlocks, violations = explore_generic(progs, bars)
     assert not deadlocks and any(v[0] == "read" for v in violations)
+
+
+def wgrad_programs(n: int, boundary=(), wait_empty: bool = True):
+    """k_mlp_wgrad_tc (mlp_tc.cu): split-K weight-gradient GEMM, two shared-memory stages filled by cp.async.bulk
+    (operand tiles A_st, B_st; completion on full[st] via expect_tx) and drained by tcgen05.mma (commit on empty[st]).
+    Thread 0 = the driver (producer + MMA issuer), thread 1 = the other threads of the CTA.  `boundary`: tiles whose
+    out-of-range rows are zeroed in shared memory by all threads before the MMAs and whose "ones" rows are restored after
+    them.  `wait_empty=False` drops the driver's wait for the MMAs of tile it - 1 before it refills their stage."""
+    driver, other = [], []
+
+    def load(tile, st):
+        driver.append(("tma", f"full{st}", ((("A", tile), ((f"A{st}", tile),)), (("B", tile), ((f"B{st}", tile),)))))
+
+    load(0, 0)
+    for it in range(n):
+        st, par = it & 1, (it >> 1) & 1
+        if it + 1 < n:
+            if it >= 1 and wait_empty:
+                driver.append(("wait", f"empty{st ^ 1}", ((it - 1) >> 1) & 1))
+            load(it + 1, st ^ 1)
+        if it in boundary:
+            for t in (driver, other):
+                t.append(("wait", f"full{st}", par))
+                t.append(("read", f"A{st}", it))                 # the rows being zeroed are this tile's
+                t.append(("sync", ("zeroed", it), 2))
+        driver.append(("wait", f"full{st}", par))
+        driver.append(("issue", ((f"A{st}", it), (f"B{st}", it)), (("acc", it),), f"empty{st}"))
+        for t in (driver, other):
+            t.append(("sync", ("iter", it), 2))
+        if it in boundary:
+            for t in (driver, other):
+                t.append(("wait", f"empty{st}", par))
+                t.append(("read", f"B{st}", it))                 # restoring the "ones" rows: the stage is still this tile's
+                t.append(("sync", ("restored", it), 2))
+    for t in (driver, other):
+        t.append(("wait", f"empty{(n - 1) & 1}", ((n - 1) >> 1) & 1))
+        t.append(("read", "acc", n - 1))
+    return [driver, other], {"full0": 1, "full1": 1, "empty0": 1, "empty1": 1}
+
+
+@pytest.mark.parametrize("n,boundary", [(1, ()), (2, ()), (5, ()), (4, (0, 3)), (1, (0,)), (5, (0, 1, 2, 3, 4))])
+def test_weight_gradient_pipeline_protocol(n, boundary):
+    progs, bars = wgrad_programs(n, boundary)
+    states, deadlocks, violations = explore_generic(progs, bars)
+    assert states > 10 and not deadlocks and not violations, (deadlocks[:1], violations[:1])
+
+
+def test_weight_gradient_pipeline_needs_the_empty_wait():
+    """sensitivity: refilling a stage without waiting for the MMAs that still read it is seen by the model"""
+    progs, bars = wgrad_programs(5, (), wait_empty=False)
+    _, _, violations = explore_generic(progs, bars)
+    assert any(v[0] == "operand" for v in violations)
+
+
+def tonemap_bwd_programs(n_tiles: int, n_warps: int, wait_bar_w: bool = True):
+    """k_tonemap_bwd_fused (mlp_tc.cu): per tile T0 (encode X, dZ_out) | MMA X W0 -> D | E1 (H -> Hs) | MMA dZ_out Wo^T -> D,
+    dWo^T += Hs^T dZ_out | E2 (dZ0 -> A, Zs) | MMA A W0 -> S, dW0 += Zs^T [X|1] (commit bar_w) | E3; a __syncthreads
+    after T0, E1, E2; the weight-gradient MMAs of tile t still read X / Hs / Zs / dZ_out while tile t + 1 begins, so T0
+    of the next tile first waits for bar_w."""
+    nthreads = n_warps + 1
+    issuer, warps = [], [[] for _ in range(n_warps)]
+    every = lambda name, t: tuple((f"{name}_{w}", t) for w in range(n_warps))
+    for t in range(n_tiles):
+        for w, ops in enumerate(warps):
+            if t > 0 and wait_bar_w:
+                ops.append(("wait", "bar_w", (t - 1) & 1))
+            ops.append(("write", ((f"X_{w}", t), (f"DZO_{w}", t))))
+            ops.append(("sync", ("T0", t), nthreads))
+        issuer.append(("sync", ("T0", t), nthreads))
+        issuer.append(("issue", every("X", t), (("D", (t, "z0")),), "bar"))
+        for w, ops in enumerate(warps):
+            ops.append(("wait", "bar", (3 * t) & 1))
+            ops.append(("read", "D", (t, "z0")))
+            ops.append(("write", ((f"HS_{w}", t),)))
+            ops.append(("sync", ("E1", t), nthreads))
+        issuer.append(("sync", ("E1", t), nthreads))
+        issuer.append(("issue", every("DZO", t), (("D", (t, "dh")),), "bar"))
+        issuer.append(("issue", every("HS", t) + every("DZO", t), (("GO", t),), None))
+        for w, ops in enumerate(warps):
+            ops.append(("wait", "bar", (3 * t + 1) & 1))
+            ops.append(("read", "D", (t, "dh")))
+            ops.append(("write", ((f"A_{w}", t), (f"ZS_{w}", t))))
+            ops.append(("sync", ("E2", t), nthreads))
+        issuer.append(("sync", ("E2", t), nthreads))
+        issuer.append(("issue", every("A", t), (("S", t),), "bar"))
+        issuer.append(("issue", every("ZS", t) + every("X", t), (("G0", t),), "bar_w"))
+        for w, ops in enumerate(warps):
+            ops.append(("wait", "bar", (3 * t + 2) & 1))
+            ops.append(("read", "S", t))
+    for ops in warps:
+        ops.append(("wait", "bar_w", (n_tiles - 1) & 1))
+        ops.append(("read", "G0", n_tiles - 1))
+        ops.append(("read", "GO", n_tiles - 1))
+    return [issuer] + warps, {"bar": 1, "bar_w": 1}
+
+
+@pytest.mark.parametrize("n_tiles", [1, 2, 4])
+def test_fused_tonemap_backward_protocol(n_tiles):
+    progs, bars = tonemap_bwd_programs(n_tiles, n_warps=2)
+    states, deadlocks, violations = explore_generic(progs, bars)
+    assert states > 20 and not deadlocks and not violations, (deadlocks[:1], violations[:1])
+
+
+def test_fused_tonemap_backward_needs_the_bar_w_wait():
+    progs, bars = tonemap_bwd_programs(3, n_warps=2, wait_bar_w=False)
+    _, _, violations = explore_generic(progs, bars)
+    assert any(v[0] == "operand" for v in violations)
