@@ -496,3 +496,67 @@ def test_fused_tonemap_backward_needs_the_bar_w_wait():
     progs, bars = tonemap_bwd_programs(3, n_warps=2, wait_bar_w=False)
     _, _, violations = explore_generic(progs, bars)
     assert any(v[0] == "operand" for v in violations)
+
+
+def chain_programs_chunked(ovl: bool, n_tiles: int, nh: int, n_warps: int, chunks: int = 3):
+    """the forward chain again, with its chunk pipeline spelt out (mlp_tc.cu `chunk_ready`): the A operand is produced in
+    `chunks` column chunks per warp, each with its own mbarrier (count = warps, one shared parity); the issuer fires the
+    K-steps of chunk cc as soon as chunk cc is complete and commits once after the last chunk"""
+    d = lambda i: f"D{i & 1}"
+    issuer, cphase, xphase = [], 0, 0
+
+    def layer0(t):
+        issuer.append(("issue", tuple((f"x_{w}", t) for w in range(n_warps)), ((d(0), (t, 0)),), "bar_first" if ovl else "bar"))
+
+    for t in range(n_tiles):
+        more = t + 1 < n_tiles
+        if not ovl or t == 0:
+            issuer.append(("sync", ("tile", t), n_warps + 1))
+            layer0(t)
+        for l in range(nh):
+            for cc in range(chunks):
+                issuer.append(("wait", f"chunk{cc}", cphase))
+                last = cc == chunks - 1
+                issuer.append(("issue", tuple((f"A_{w}_{cc}", (t, l)) for w in range(n_warps)),
+                               ((d(l + 1), (t, l + 1) if last else (t, l + 1, "partial", cc)),), "bar" if last else None))
+            cphase ^= 1
+        if ovl and more:
+            issuer.append(("wait", "bar_x", xphase))
+            xphase ^= 1
+            layer0(t + 1)
+    warps = []
+    for w in range(n_warps):
+        ops, phase, fphase = [("write", ((f"x_{w}", 0),))], 0, 0
+        for t in range(n_tiles):
+            more = t + 1 < n_tiles
+            if not ovl or t == 0:
+                ops.append(("sync", ("tile", t), n_warps + 1))
+            for l in range(nh):
+                if l == 0 and ovl:
+                    ops.append(("wait", "bar_first", fphase))
+                    fphase ^= 1
+                else:
+                    ops.append(("wait", "bar", phase))
+                    phase ^= 1
+                if l == 0 and more:
+                    ops.append(("write", ((f"x_{w}", t + 1),)))
+                ops.append(("read", d(l), (t, l)))              # all three chunks are loaded from TMEM up front
+                for cc in range(chunks):
+                    ops.append(("write", ((f"A_{w}_{cc}", (t, l)),)))
+                    ops.append(("arrive", f"chunk{cc}"))
+            if ovl and more:
+                ops.append(("arrive", "bar_x"))
+            ops.append(("wait", "bar", phase))
+            phase ^= 1
+            ops.append(("read", d(nh), (t, nh)))
+        warps.append(ops)
+    bars = {"bar": 1, "bar_first": 1, "bar_x": n_warps}
+    bars.update({f"chunk{cc}": n_warps for cc in range(chunks)})
+    return [issuer] + warps, bars
+
+
+@pytest.mark.parametrize("ovl", [False, True])
+def test_chunk_pipelined_chain_protocol(ovl):
+    progs, bars = chain_programs_chunked(ovl, n_tiles=3, nh=3, n_warps=2)
+    states, deadlocks, violations = explore_generic(progs, bars)
+    assert states > 1000 and not deadlocks and not violations, (deadlocks[:1], violations[:1])
