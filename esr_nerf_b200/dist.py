@@ -75,6 +75,7 @@ class GridGradCompactor:
         self.grids = [model.sdf.grid, model.off_color.grid, model.emo_color.grid]
         self._idx32 = None
         self._early = None      # (work handle, packed buffer, gradient buffers) of a colour all-reduce already in flight
+        self._overlap = False
         self.group = None
 
     def overlap_color_allreduce(self, enable: bool = True, group=None):
@@ -84,18 +85,23 @@ class GridGradCompactor:
         from . import fused
 
         self.group = group
+        self._overlap = bool(enable)
         fused.COLOR_GRADS_READY_HOOK = self._on_color_grads if enable else None
 
     def _on_color_grads(self, bufs):
+        """Every rank must issue the same collectives in the same order, so whether the colour block leaves early may
+        depend only on what the CALLER does identically on every rank (gradient accumulation across calls), never on
+        this rank's data: a colour volume this rank's rays did not touch goes in as zeros, and a rank whose backward
+        pass never got here (no shaded sample at all) issues the same all-reduce from allreduce(), late."""
         import torch.distributed as dist
 
         params = self.grids[1:]
-        if self._early is not None or any(p.grad is not None for p in params) or any(p not in bufs for p in params):
-            return          # gradient accumulation across calls (or an unexpected graph): the exchange happens at the end
-        rows = [self._rows(bufs[p]) for p in params]
-        buf = self.pack(rows, "_cbuf")
+        if self._early is not None or any(p.grad is not None for p in params):
+            return          # gradient accumulation across calls: the exchange happens at the end, on every rank alike
+        grads = [bufs[p] if p in bufs else torch.zeros_like(p) for p in params]
+        buf = self.pack([self._rows(g) for g in grads], "_cbuf")
         work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._early = (work, buf, [bufs[p] for p in params])
+        self._early = (work, buf, grads)
 
     @property
     def fraction(self) -> float:
@@ -176,13 +182,20 @@ class GridGradCompactor:
     def allreduce(self, group=None, verify: bool = False) -> int:
         import torch.distributed as dist
 
+        color = self.grids[1:]
+        if self._early is None and self._overlap and all(p.grad is None for p in color):
+            self._on_color_grads({})     # this rank's backward never reached the hook: same collective, zeros, now
+        early, self._early = self._early, None
+        if early is not None:
+            for p, b in zip(color, early[2]):
+                if p.grad is None:       # a volume this rank did not touch: the zeros that went into the exchange
+                    p.grad = b
         rows = self._grids_rows()
         if verify:
             assert self.outside_is_zero(), "gradient outside the dilated occupancy set"
         grid_ids = {id(p) for p in self.grids}
         others = [p for p in self.model.parameters() if id(p) not in grid_ids]
         nbytes = allreduce_gradients(others, group)      # the small MLP bucket first: it is ready and tiny
-        early, self._early = self._early, None
         if early is not None and all(p.grad is not None and p.grad.data_ptr() == b.data_ptr()
                                      for p, b in zip(self.grids[1:], early[2])):
             # the colour volumes are already on their way (started inside the backward pass): SDF grid now, then join
@@ -231,6 +244,7 @@ class TouchedBlockCompactor(GridGradCompactor):
         self.idx = torch.zeros(0, dtype=torch.int64)
         self._idx32 = None
         self._early = None
+        self._overlap = False
         self.group = None
         self._tables = {}
         self.last_fraction = 0.0

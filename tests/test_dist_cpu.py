@@ -136,6 +136,34 @@ def _compactor_worker(rank, world, port, out):
         if p.dim() == 5:
             other = other * comp.mask
         err = max(err, (p.grad - (mine + other)).abs().max().item())
+    # rank-dependent data must not change the collective sequence: (A) rank 1's rays never touched the second colour
+    # volume (it is missing from the hook's buffers), (B) rank 1's backward never reached the hook at all — in both
+    # cases rank 1 contributes zeros through the SAME early all-reduce, and nothing hangs or mismatches
+    comp._overlap = True
+    for case in ("A", "B"):
+        mine_c = []
+        for p, mine in zip(model.parameters(), grads):
+            is_color = any(p is c for c in color)
+            absent = is_color and rank == 1 and (case == "B" or p is color[1])
+            p.grad = None if is_color else mine.clone()
+            mine_c.append(torch.zeros_like(mine) if absent else mine)
+        bufs = {p: m.clone() for p, m in zip(model.parameters(), mine_c)
+                if any(p is c for c in color) and not (rank == 1 and (case == "B" or p is color[1]))}
+        if not (rank == 1 and case == "B"):
+            comp._on_color_grads(bufs)
+            for p in color:
+                if p in bufs:
+                    p.grad = bufs[p]
+        comp.allreduce()
+        assert comp._early is None
+        g4 = torch.Generator().manual_seed(10 + (1 - rank))
+        for p, m in zip(model.parameters(), mine_c):
+            other = torch.randn(p.shape, generator=g4)
+            if p.dim() == 5:
+                other = other * comp.mask
+                if rank == 0 and (case == "B" or p is color[1]) and any(p is c for c in color):
+                    other = other * 0          # what rank 1 left out
+            err = max(err, (p.grad - (m + other)).abs().max().item())
     out.put(err)
     dist.barrier()
     dist.destroy_process_group()
