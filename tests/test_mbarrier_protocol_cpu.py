@@ -498,10 +498,13 @@ def test_fused_tonemap_backward_needs_the_bar_w_wait():
     assert any(v[0] == "operand" for v in violations)
 
 
-def chain_programs_chunked(ovl: bool, n_tiles: int, nh: int, n_warps: int, chunks: int = 3):
+def chain_programs_chunked(ovl: bool, n_tiles: int, nh: int, n_warps: int, chunks: int = 3, dgrad: bool = False):
     """the forward chain again, with its chunk pipeline spelt out (mlp_tc.cu `chunk_ready`): the A operand is produced in
     `chunks` column chunks per warp, each with its own mbarrier (count = warps, one shared parity); the issuer fires the
-    K-steps of chunk cc as soon as chunk cc is complete and commits once after the last chunk"""
+    K-steps of chunk cc as soon as chunk cc is complete and commits once after the last chunk.
+    `dgrad`: the data-gradient chain (k_mlp_dgrad_tc) — the first MMA's shared-memory operand is the dZ_out tile, which
+    each tile's warps write at the top of the tile (per-tile barrier) or, with the overlap, for the NEXT tile after
+    the chain epilogues and before the arrival on bar_x (`make_dz(tile + gridDim.x)`)"""
     d = lambda i: f"D{i & 1}"
     issuer, cphase, xphase = [], 0, 0
 
@@ -526,9 +529,11 @@ def chain_programs_chunked(ovl: bool, n_tiles: int, nh: int, n_warps: int, chunk
             layer0(t + 1)
     warps = []
     for w in range(n_warps):
-        ops, phase, fphase = [("write", ((f"x_{w}", 0),))], 0, 0
+        ops, phase, fphase = ([] if dgrad else [("write", ((f"x_{w}", 0),))]), 0, 0
         for t in range(n_tiles):
             more = t + 1 < n_tiles
+            if dgrad and (not ovl or t == 0):
+                ops.append(("write", ((f"x_{w}", t),)))          # dZ_out tile of this tile
             if not ovl or t == 0:
                 ops.append(("sync", ("tile", t), n_warps + 1))
             for l in range(nh):
@@ -538,13 +543,15 @@ def chain_programs_chunked(ovl: bool, n_tiles: int, nh: int, n_warps: int, chunk
                 else:
                     ops.append(("wait", "bar", phase))
                     phase ^= 1
-                if l == 0 and more:
+                if l == 0 and more and not dgrad:
                     ops.append(("write", ((f"x_{w}", t + 1),)))
                 ops.append(("read", d(l), (t, l)))              # all three chunks are loaded from TMEM up front
                 for cc in range(chunks):
                     ops.append(("write", ((f"A_{w}_{cc}", (t, l)),)))
                     ops.append(("arrive", f"chunk{cc}"))
             if ovl and more:
+                if dgrad:
+                    ops.append(("write", ((f"x_{w}", t + 1),)))
                 ops.append(("arrive", "bar_x"))
             ops.append(("wait", "bar", phase))
             phase ^= 1
@@ -555,8 +562,9 @@ def chain_programs_chunked(ovl: bool, n_tiles: int, nh: int, n_warps: int, chunk
     return [issuer] + warps, bars
 
 
+@pytest.mark.parametrize("dgrad", [False, True])
 @pytest.mark.parametrize("ovl", [False, True])
-def test_chunk_pipelined_chain_protocol(ovl):
-    progs, bars = chain_programs_chunked(ovl, n_tiles=3, nh=3, n_warps=2)
+def test_chunk_pipelined_chain_protocol(ovl, dgrad):
+    progs, bars = chain_programs_chunked(ovl, n_tiles=3, nh=3, n_warps=2, dgrad=dgrad)
     states, deadlocks, violations = explore_generic(progs, bars)
     assert states > 1000 and not deadlocks and not violations, (deadlocks[:1], violations[:1])
