@@ -2,7 +2,11 @@
 # scripts/gpu_followup.sh — ONE gpurun call that measures everything round 1 wrote after its GPU budget was spent
 # (DESIGN.md §7 "Next, ranked"):
 #
-#   /usr/local/graft/bin/gpurun --gpus 4 --timeout 1500 -- 'bash scripts/gpu_followup.sh'
+#   /usr/local/graft/bin/gpurun           --timeout 900  -- 'bash scripts/gpu_followup.sh single'   # ~10 GPU-minutes
+#   /usr/local/graft/bin/gpurun --gpus 2  --timeout 1200 -- 'bash scripts/gpu_followup.sh pair'     # ~15 min x 2 GPUs
+#   /usr/local/graft/bin/gpurun --gpus 4  --timeout 900  -- 'bash scripts/gpu_followup.sh quad'     # ~12 min x 4 GPUs
+#
+# (box time is charged per GPU: run the parts separately; with no argument every part the box has GPUs for runs.)
 #
 #  1. default build: pytest -m gpu + the bench line (the committed MLP chains never ran on a GPU in their present form:
 #     a mechanical revert of the tile overlap on top of GPU-verified epilogue trims)
@@ -22,14 +26,19 @@ run() {  # run <name> <timeout_s> <command...>: stdout -> $O/name.json|log, stde
   echo "$name rc=$?" | tee -a "$O/summary.txt"
 }
 
+PART=${1:-all}
+want() { [ "$PART" = all ] || [ "$PART" = "$1" ]; }
+
+if want single; then
 run pytest_default 900 python -m pytest tests -m gpu -x -q
 run bench_default 400 python bench.py --steps 20
 ESR_TEST_UNVERIFIED=1 run pytest_block_flags 300 python -m pytest tests/test_gpu_native_ops.py -m gpu -x -q -k block_flags
 ESR_MLP_TILE_OVERLAP=1 run pytest_tile_overlap 900 python -m pytest tests/test_gpu_mlp.py tests/test_gpu_voxurff.py tests/test_gpu_esrnerf.py -m gpu -x -q
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap 400 python bench.py --steps 20 --no-cpu-baseline
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap_eval 400 python bench.py --stage eval --steps 5
+fi
 
-if [ "$NGPU" -ge 2 ]; then
+if want pair && [ "$NGPU" -ge 2 ]; then
   run pytest_dist 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q
   run bench_n2 400 $TR --nproc-per-node 2 --master-port 29511 bench.py --gpus 2
   run bench_lts_n2_dense 500 $TR --nproc-per-node 2 --master-port 29512 bench.py --gpus 2 --stage lts
@@ -38,7 +47,7 @@ if [ "$NGPU" -ge 2 ]; then
   run bench_eval_n2_gather 400 $TR --nproc-per-node 2 --master-port 29515 bench.py --gpus 2 --stage eval --steps 5
   run bench_eval_n2_nogather 400 $TR --nproc-per-node 2 --master-port 29516 bench.py --gpus 2 --stage eval --steps 5 --no-gather
 fi
-if [ "$NGPU" -ge 4 ]; then
+if want quad && [ "$NGPU" -ge 4 ]; then
   for i in 1 2 3; do
     run bench_n4_$i 400 $TR --nproc-per-node 4 --master-port $((29520 + i)) bench.py --gpus 4
     ESR_ALLREDUCE_OVERLAP=1 run bench_n4_overlap_$i 400 $TR --nproc-per-node 4 --master-port $((29530 + i)) bench.py --gpus 4
