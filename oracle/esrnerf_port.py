@@ -113,6 +113,34 @@ def diffuse_scattering(normal: torch.Tensor, noise: torch.Tensor) -> torch.Tenso
     return torch.where(flip[..., None], ret * -1.0, ret)
 
 
+def _is_fib(scene) -> bool:
+    """esrnerf.py:188-192: cfg.app.model.ray_sampling (scene["ray_sampling"], default "random")"""
+    return str(scene.get("ray_sampling", "random")).lower() in ("fib", "fibo", "fibonacci")
+
+
+def scatter_noise(scene, draws, *shape):
+    """the Gaussian draw behind `self.scattering` — none at all with the Fibonacci sampler (pbr/functions.py:21-32)"""
+    return None if _is_fib(scene) else draws.randn(*shape)
+
+
+def scatter_dirs(scene, normal: torch.Tensor, number: int, noise) -> torch.Tensor:
+    """self.scattering(normal, number): diffuse_scattering (pbr/functions.py:10-18) or diffuse_scattering_fib (:21-32,
+    176-194: the upper half of a 2n-point Fibonacci spiral, the same for every point, mirrored by the normal)"""
+    if not _is_fib(scene):
+        return diffuse_scattering(normal, noise)
+    import math
+
+    n = 2 * number
+    rn = torch.arange(number, n)
+    phi = (math.pi * (3.0 - math.sqrt(5.0))) * ((rn + 1.0) % n)
+    cos_theta = ((rn + 0.5) * (1.0 / number)) - 1.0
+    sin_theta = torch.sqrt(1.0 - cos_theta * cos_theta)
+    ret = torch.stack([torch.cos(phi) * sin_theta, torch.sin(phi) * sin_theta, cos_theta], dim=-1)
+    ret = ret.expand(*normal.shape[:-1], number, 3).clone().to(normal.device)
+    ret[torch.sum(ret * normal.unsqueeze(-2), dim=-1) < 0] *= -1.0
+    return ret
+
+
 def disney_reflection(albedo, roughness, metallic, normal, win, wout):
     """pbr/functions.py:108-173"""
     eps = 1e-7
@@ -139,11 +167,13 @@ def disney_reflection(albedo, roughness, metallic, normal, win, wout):
     return (fd + D * Fr * V) * ion * torch.pi * 2
 
 
-def sg_envmap(params: Dict, dirs: torch.Tensor) -> torch.Tensor:
-    """pbr/module.py:133-143 (softplus activation, cfg/app/lts.yaml:30)"""
+def sg_envmap(params: Dict, dirs: torch.Tensor, activation: str = "softplus") -> torch.Tensor:
+    """pbr/module.py:133-143; the activation is looked up in torch, then torch.nn.functional (:94-101; softplus:
+    cfg/app/lts.yaml:30)"""
+    act = getattr(torch, activation) if hasattr(torch, activation) else getattr(F, activation)
     lobes = F.normalize(params["envmap.lobes"], dim=-1)
     lambdas = torch.abs(params["envmap.lambdas"])
-    return F.softplus((params["envmap.mus"] * torch.exp(
+    return act((params["envmap.mus"] * torch.exp(
         lambdas * ((dirs.unsqueeze(-2) * lobes).sum(-1, keepdim=True) - 1.0))).sum(-2))
 
 
@@ -205,7 +235,7 @@ def light_transport_segment(scene, params, pts, viewdirs, normal, sdf, base, rou
     """esrnerf.py:487-679"""
     n2 = scene["num_2ndrays"]
     Pn = pts.shape[0]
-    dirs = diffuse_scattering(normal, dir_noise)           # [P, n2+1, 3]
+    dirs = scatter_dirs(scene, normal, scene["num_2ndrays"] + 1, dir_noise)           # [P, n2+1, 3]
     v_rand = -dirs[:, -1]
     dirs = dirs[:, :-1]
     # radiance leaving the points towards the camera and towards one random direction
@@ -225,7 +255,7 @@ def light_transport_segment(scene, params, pts, viewdirs, normal, sdf, base, rou
     R = disney_reflection(ex(base, 3).repeat(2, 1), ex(rough, 1).repeat(2, 1), ex(metal, 1).repeat(2, 1),
                           ex(normal, 3).repeat(2, 1), d_flat.repeat(2, 1), wout)
     off_m, emo_m, last, inter = _secondary(scene, params, ex(pts, 3), d_flat, s_val)
-    env = sg_envmap(params, d_flat) * last.unsqueeze(-1)
+    env = sg_envmap(params, d_flat, scene.get("env_activation", "softplus")) * last.unsqueeze(-1)
     off_hat = ((off_m + env).repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
     reflect = (emo_m.repeat(2, 1) * R).view(-1, n2, 3).mean(-2)
     if pdra_mode:
@@ -282,7 +312,7 @@ def esrnerf_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     normal = F.normalize(exp_grad.detach(), dim=-1)
     m3 = ray_pts.shape[0]
     idx = draws.choice(m3, min(scene["num_ltspts"], m3))
-    dir_noise = draws.randn(idx.shape[0], scene["num_2ndrays"] + 1, 3)
+    dir_noise = scatter_noise(scene, draws, idx.shape[0], scene["num_2ndrays"] + 1, 3)
     lts, lts_inter = light_transport_segment(scene, params, ray_pts[idx], viewdirs[ray_id][idx], normal[idx], sdf[idx],
                                              base[idx], rough[idx], metal[idx], emit[idx], uncert_masks[ray_id][idx],
                                              s_val, pdra_mode, dir_noise)
@@ -351,7 +381,7 @@ def esrnerf_eval_emit(scene, params, rays_o, rays_d, viewdirs, s_val):
 def _lts_eval(scene, params, pts, viewdirs, normal, base, rough, metal, emit, s_val, dir_noise):
     """esrnerf.py:854-1001 (one chunk)"""
     n2, Pn = scene["num_2ndrays"], pts.shape[0]
-    dirs = diffuse_scattering(normal, dir_noise)
+    dirs = scatter_dirs(scene, normal, scene["num_2ndrays"], dir_noise)
 
     def ex(t, c):
         return t.view(-1, 1, c).expand(Pn, n2, c).flatten(0, 1)
@@ -359,7 +389,7 @@ def _lts_eval(scene, params, pts, viewdirs, normal, base, rough, metal, emit, s_
     d_flat = dirs.flatten(0, 1)
     R = disney_reflection(ex(base, 3), ex(rough, 1), ex(metal, 1), ex(normal, 3), d_flat, -ex(viewdirs, 3))
     off_m, emo_m, last, _ = _secondary(scene, params, ex(pts, 3), d_flat, s_val)
-    env = sg_envmap(params, d_flat) * last.unsqueeze(-1)
+    env = sg_envmap(params, d_flat, scene.get("env_activation", "softplus")) * last.unsqueeze(-1)
     out = {"lin/env_dir": (env * R).view(-1, n2, 3).mean(-2), "lin/env_indir": (off_m * R).view(-1, n2, 3).mean(-2)}
     out["lin/env_effects"] = out["lin/env_dir"] + out["lin/env_indir"]
     out["lin/emit_(in)dir"] = (emo_m * R).view(-1, n2, 3).mean(-2)
@@ -412,7 +442,7 @@ def esrnerf_forward_evaluate(scene, params, rays_o, rays_d, viewdirs, em_modes, 
         nrm = F.normalize(st["exp_grad"], dim=-1)
         parts = {}
         for idx in torch.arange(pts.shape[0]).split(chunk_sz):
-            noise = draws.randn(idx.shape[0], scene["num_2ndrays"], 3)
+            noise = scatter_noise(scene, draws, idx.shape[0], scene["num_2ndrays"], 3)
             ret = _lts_eval(scene, params, pts[idx], vdir[idx], nrm[idx], base[idx], rough[idx], metal[idx], emit[idx],
                             s_val, noise)
             for k, val in ret.items():
@@ -477,7 +507,7 @@ def esrnerf_forward_finetune(scene, params, rays_o, rays_d, viewdirs, em_modes, 
         Pn = pts.shape[0]
         sdf, exp_grad = sdf_expgrad(params["sdf"], pts, scene["xyz_min"], scene["xyz_max"], True)
         sdf, normal = sdf.detach(), F.normalize(exp_grad.detach(), dim=-1)
-        dirs = diffuse_scattering(normal, draws.randn(Pn, n2 + 1, 3))
+        dirs = scatter_dirs(scene, normal, n2 + 1, scatter_noise(scene, draws, Pn, n2 + 1, 3))
         v_rand = -dirs[:, -1]
         dirs = dirs[:, :-1]
         feat, _, fnormal = _taps(scene, params, pts)

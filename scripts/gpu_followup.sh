@@ -33,6 +33,7 @@ if want single; then
 run pytest_default 900 python -m pytest tests -m gpu -x -q
 run bench_default 400 python bench.py --steps 20
 ESR_TEST_UNVERIFIED=1 run pytest_block_flags 300 python -m pytest tests/test_gpu_native_ops.py -m gpu -x -q -k block_flags
+ESR_TEST_UNVERIFIED=1 run pytest_fib_envmaps 300 python -m pytest tests/test_gpu_esrnerf.py -m gpu -x -q -k other_samplers
 ESR_MLP_TILE_OVERLAP=1 run pytest_tile_overlap 900 python -m pytest tests/test_gpu_mlp.py tests/test_gpu_voxurff.py tests/test_gpu_esrnerf.py -m gpu -x -q
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap 400 python bench.py --steps 20 --no-cpu-baseline
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap_eval 400 python bench.py --stage eval --steps 5

@@ -205,6 +205,7 @@ def load_esrnerf_case(name):
 def esrnerf_oracle_scene(fx):
     scene = oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
     scene.update(num_2ndrays=int(fx["num_2ndrays"]), num_ltspts=int(fx["num_ltspts"]), lts_near=1e-5)
+    scene.update({k: str(fx[k]) for k in ("ray_sampling", "env_activation") if k in fx})     # defaults: random / softplus
     return scene
 
 
@@ -243,7 +244,8 @@ def run_esrnerf_port(fx, weights, draws=None):
 def build_product_esrnerf(fx, weights, device="cuda:0"):
     from esr_nerf_b200.esrnerf import ESRNeRF
 
-    cfg = S.lts_cfg(device=device, num_2ndrays=int(fx["num_2ndrays"]), num_ltspts=int(fx["num_ltspts"]))
+    cfg = S.lts_cfg(device=device, num_2ndrays=int(fx["num_2ndrays"]), num_ltspts=int(fx["num_ltspts"]),
+                    **{k: str(fx[k]) for k in ("ray_sampling", "env_activation") if k in fx})
     m = ESRNeRF(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
                 S.mask_density(int(fx["mask_res"]), bool(fx["sparse"])), float(fx["s_val"]), int(fx["num_voxels"]))
     m.load_state_dict({**m.state_dict(), **weights})

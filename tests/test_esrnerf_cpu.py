@@ -126,3 +126,45 @@ def test_esrnerf_finetune_port_matches_golden(case):
     for name in with_grad:
         err, s_err = C.digest_check(ft, name, leaves[name].grad, rtol=1e-4)
         assert err < 1.0 and s_err < 1e-4, (name, err, s_err)
+
+
+@pytest.mark.parametrize("ray_sampling,env_activation", [("fib", "softplus"), ("random", "relu"), ("fibonacci", "sigmoid")])
+def test_esrnerf_port_matches_reference_other_samplers_and_envmaps(ray_sampling, env_activation):
+    """the configurable pieces no shipped config uses (esrnerf.py:188-195): the Fibonacci hemisphere sampler (no random
+    draw for the directions) and the other environment-map activations — port vs the reference's own class on the CPU,
+    training step and finetune target"""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import esrnerf_port as E
+    from oracle.make_golden import build_reference_esrnerf
+
+    fx, weights = C.load_esrnerf_case("pdra_sparse_s60")
+    n, s_val = 64, 35.0
+    ref = build_reference_esrnerf(int(fx["num_voxels"]), int(fx["mask_res"]), True, s_val, weights, num_2ndrays=8,
+                                  num_ltspts=16, ray_sampling=ray_sampling, env_activation=env_activation)
+    ref.pdra_mode = True
+    rays = S.make_rays(n, 777)
+    um = S.uncert_masks(n)
+    np.random.seed(6)
+    torch.manual_seed(12)
+    ref_out = ref(s_val=s_val, rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+                  em_modes=rays["em_modes"], uncert_masks=um, normal_eps=0.01, emit_eps=0.03)
+    scene = C.esrnerf_oracle_scene(dict(fx, num_2ndrays=8, num_ltspts=16))
+    scene.update(ray_sampling=ray_sampling, env_activation=env_activation)
+    params, leaves = C.esrnerf_oracle_params(scene, weights)
+    np.random.seed(6)
+    torch.manual_seed(12)
+    out, _ = E.esrnerf_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                        rays["em_modes"], um, s_val, 0.01, 0.03, True, E.Draws())
+    cot = C.esrnerf_cotangents(out)
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    assert set(out) == set(ref_out)
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    for name, p in ref.named_parameters():
+        if p.grad is not None:
+            assert C.rel_err(leaves[name].grad, p.grad) < 1e-5, name
