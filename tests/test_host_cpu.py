@@ -221,3 +221,30 @@ def test_bench_step_roofline_aggregates_measured_rows():
     assert 0.3 < agg["hbm"]["frac"] < 1.0 and 0.1 < agg["tensor"]["frac"] < 1.0
     assert agg["other_ms_per_step"] == sum(r["ms_per_step"] for r in rows if "bound" not in r)
     assert bench.step_roofline([], pk)["hbm"]["frac"] == 0.0       # no rows: zeros, no division
+
+
+def test_cabi_gradient_exchange_argument_checks_without_a_device():
+    """the exchange entry points validate their arguments before any CUDA call (include/esr_b200.h §2e): status codes
+    and esr_last_error() can be checked on a box without a GPU"""
+    import ctypes
+
+    from esr_nerf_b200 import _lib
+
+    L = _lib.lib()
+    ch = (ctypes.c_int32 * 3)(1, 6, 6)
+    assert L.esr_grad_pack_floats(ch, 3, 5) == 5 + 1 + 30 + 30            # every block starts on an even float offset
+    assert L.esr_grad_pack_floats(ch, 3, 4) == 4 + 24 + 24
+    assert L.esr_grad_pack_floats(ch, 0, 4) == -1 and L.esr_grad_pack_floats(ch, 5, 4) == -1
+    assert L.esr_grad_pack_floats(None, 3, 4) == -1 and L.esr_grad_pack_floats(ch, 3, -1) == -1
+    bad = (ctypes.c_int32 * 1)(0)
+    assert L.esr_grad_pack_floats(bad, 1, 4) == -1
+    vols = (ctypes.c_void_p * 3)(None, None, None)
+    assert L.esr_grad_pack(vols, ch, 3, None, 0, None, None) == 0          # nothing to move: no pointer is touched
+    assert L.esr_grad_pack(vols, ch, 0, None, 4, None, None) != 0          # no volumes
+    assert L.esr_grad_unpack(vols, ch, 9, None, 4, None, None) != 0        # more than ESR_MAX_GRAD_VOLUMES
+    assert L.esr_grad_pack(vols, ch, 3, None, 4, None, None) != 0          # null index / buffer
+    assert L.esr_last_error()
+    # block map: the block edges must divide the grid extents, pointers must be there
+    assert L.esr_grad_block_flags(vols, ch, 3, 16, 16, 12, 8, 8, 8, None, None) != 0
+    assert L.esr_grad_block_flags(None, ch, 3, 16, 16, 16, 8, 8, 8, None, None) != 0
+    assert L.esr_grad_block_flags(vols, ch, 0, 16, 16, 16, 8, 8, 8, None, None) != 0
