@@ -518,3 +518,40 @@ def test_optimizer_port_matches_reference():
            [(pg["name"], pg["lr"], len(pg["params"])) for pg in o_mine.param_groups]
     assert {n: p.requires_grad for n, p in ref.named_parameters()} == {n: p.requires_grad for n, p in mine.named_parameters()}
     assert sorted(o_mine.name2pg) == sorted(o_ref.name2pg)
+
+
+def test_checkpoints_load_both_ways_for_every_stage_model():
+    """a reference checkpoint resumes on this library and vice versa — for each of the four render
+    models the state_dict keys, order and shapes are the reference's, and strict loading works in both directions
+    without changing a value (multi-channel grids are re-laid-out channels-last on the way in)"""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.dvgo import DVGO
+    from esr_nerf_b200.esrnerf import ESRNeRF
+    from esr_nerf_b200.voxurfc import VoxurfC
+    from esr_nerf_b200.voxurff import VoxurfF
+    from oracle import make_golden as G
+
+    geo = (S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT, S.mask_density(12, True))
+    pairs = {
+        "fine": (G.build_reference_model(24 ** 3, 12, True, 20.0), VoxurfF(S.fine_cfg("cpu"), *geo, 20.0, 24 ** 3)),
+        "lts": (G.build_reference_esrnerf(24 ** 3, 12, True, 20.0), ESRNeRF(S.lts_cfg("cpu"), *geo, 20.0, 24 ** 3)),
+        "coarse": (G.build_reference_coarse(24 ** 3, 12, True, 5.0),
+                   VoxurfC(S.coarse_cfg("cpu", num_voxels=24 ** 3), *geo, 5.0)),
+        "alphamask": (G.build_reference_dvgo(24 ** 3), DVGO(S.dvgo_cfg("cpu", 24 ** 3), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX)),
+    }
+    for stage, (ref, mine) in pairs.items():
+        rsd, msd = ref.state_dict(), mine.state_dict()
+        assert list(rsd) == list(msd), stage
+        assert [tuple(v.shape) for v in rsd.values()] == [tuple(v.shape) for v in msd.values()], stage
+        g = torch.Generator().manual_seed(1)
+        new = {k: (torch.randn(v.shape, generator=g) if v.is_floating_point() else v.clone()) for k, v in rsd.items()}
+        mine.load_state_dict(new, strict=True)
+        for k, v in mine.state_dict().items():
+            assert torch.equal(v, new[k]), (stage, k)
+        ref.load_state_dict(mine.state_dict(), strict=True)
+        for k, v in ref.state_dict().items():
+            assert torch.equal(v, new[k]), (stage, k)
