@@ -555,3 +555,34 @@ def test_checkpoints_load_both_ways_for_every_stage_model():
         ref.load_state_dict(mine.state_dict(), strict=True)
         for k, v in ref.state_dict().items():
             assert torch.equal(v, new[k]), (stage, k)
+
+
+def test_progressive_grid_rescale_matches_reference():
+    """scale_volume_grid (voxurff.py:547-566; DenseGrid.scale_volume_grid, module.py:37-46): the progressive rescale between training phases —
+    new resolution, voxel size, trilinear re-sampling of every grid, occupancy mask — equals the reference's on the same
+    state (CPU); and a second rescale on top of the first"""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.voxurff import VoxurfF
+    from oracle import make_golden as G
+
+    geo = (S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT, S.mask_density(12, True))
+    pairs = {
+        "fine": (G.build_reference_model(20 ** 3, 12, True, 20.0), VoxurfF(S.fine_cfg("cpu"), *geo, 20.0, 20 ** 3)),
+    }       # (only the fine stage rescales: the reference's VoxurfC and ESRNeRF have no scale_volume_grid)
+    for stage, (ref, mine) in pairs.items():
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        for num_voxels in (27 ** 3, 33 ** 3 + 100):
+            ref.scale_volume_grid(num_voxels)
+            mine.scale_volume_grid(num_voxels)
+            assert torch.equal(torch.as_tensor(mine.world_size).cpu(), torch.as_tensor(ref.world_size).cpu()), stage
+            assert torch.equal(torch.as_tensor(mine.voxel_size).cpu(), torch.as_tensor(ref.voxel_size).cpu()), stage
+            rsd, msd = ref.state_dict(), mine.state_dict()
+            assert list(rsd) == list(msd)
+            for k in rsd:
+                assert rsd[k].shape == msd[k].shape and torch.equal(rsd[k], msd[k]), (stage, num_voxels, k)
+            if hasattr(ref, "nonempty_mask"):
+                assert torch.equal(ref.nonempty_mask, mine.nonempty_mask), stage
