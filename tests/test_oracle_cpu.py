@@ -586,3 +586,45 @@ def test_progressive_grid_rescale_matches_reference():
                 assert rsd[k].shape == msd[k].shape and torch.equal(rsd[k], msd[k]), (stage, num_voxels, k)
             if hasattr(ref, "nonempty_mask"):
                 assert torch.equal(ref.nonempty_mask, mine.nonempty_mask), stage
+
+
+def test_optimizer_groups_of_every_stage_match_reference():
+    """create_optimizer_or_freeze_model (app/utils/optimizer.py:231-275) with each stage's shipped learning rates
+    (cfg/app/{alphamask,coarse,lts}.yaml `lrs`; pdra.yaml shares the LTS model): the drop-in builds the same parameter
+    groups (name, lr, tensor count, order) and freezes the same parameters on this library's models as the reference's
+    function does on the reference's, including the groups switched off with lr 0"""
+    import importlib
+
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present")
+    H.install_stubs()
+    R = importlib.import_module("app.utils.optimizer")
+    from esr_nerf_b200 import optimizer as O
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.dvgo import DVGO
+    from esr_nerf_b200.esrnerf import ESRNeRF
+    from esr_nerf_b200.voxurfc import VoxurfC
+    from oracle import make_golden as G
+
+    geo = (S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT, S.mask_density(8, True))
+    cases = {
+        "alphamask": (G.build_reference_dvgo(16 ** 3), DVGO(S.dvgo_cfg("cpu", 16 ** 3), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX),
+                      dict(density=0.1, off_color=0.1, emo_color=0.1)),
+        "coarse": (G.build_reference_coarse(16 ** 3, 8, True, 5.0), VoxurfC(S.coarse_cfg("cpu", num_voxels=16 ** 3), *geo, 5.0),
+                   dict(off_color=0.1, off_rgbnet=0.001, emo_color=0.1, emo_rgbnet=0.001, sdf=0.1)),
+        "lts": (G.build_reference_esrnerf(16 ** 3, 8, True, 20.0), ESRNeRF(S.lts_cfg("cpu"), *geo, 20.0, 16 ** 3),
+                dict(off_color=0.1, off_rgbnet=0.003, emo_color=0.1, emo_rgbnet=0.003, sdf=0.0005, tonemapper=0.003, brdf=0.1,
+                     brdfnet=0.001, emitnet=0.001, envmap=0.001)),
+        "lts, frozen geometry": (G.build_reference_esrnerf(16 ** 3, 8, True, 20.0), ESRNeRF(S.lts_cfg("cpu"), *geo, 20.0, 16 ** 3),
+                                 dict(off_color=0.0, off_rgbnet=0.0, emo_color=0.1, emo_rgbnet=0.003, sdf=0.0, tonemapper=0.0,
+                                      brdf=0.1, brdfnet=0.001, emitnet=0.001, envmap=0.0)),
+    }
+    for stage, (ref, mine, lrs) in cases.items():
+        o_ref, o_mine = R.create_optimizer_or_freeze_model(ref, **lrs), O.create_optimizer_or_freeze_model(mine, **lrs)
+        assert [(pg["name"], pg["lr"], len(pg["params"])) for pg in o_ref.param_groups] == \
+               [(pg["name"], pg["lr"], len(pg["params"])) for pg in o_mine.param_groups], stage
+        assert {n: p.requires_grad for n, p in ref.named_parameters()} == \
+               {n: p.requires_grad for n, p in mine.named_parameters()}, stage
+        assert sorted(o_mine.name2pg) == sorted(o_ref.name2pg), stage
