@@ -3,6 +3,7 @@
 # (DESIGN.md §7 "Next, ranked"):
 #
 #   /usr/local/graft/bin/gpurun           --timeout 900  -- 'bash scripts/gpu_followup.sh single'   # ~10 GPU-minutes
+#   /usr/local/graft/bin/gpurun           --timeout 1500 -- 'bash scripts/gpu_followup.sh ncu'      # ~6 GPU-minutes
 #   /usr/local/graft/bin/gpurun --gpus 2  --timeout 1200 -- 'bash scripts/gpu_followup.sh pair'     # ~15 min x 2 GPUs
 #   /usr/local/graft/bin/gpurun --gpus 4  --timeout 900  -- 'bash scripts/gpu_followup.sh quad'     # ~12 min x 4 GPUs
 #
@@ -27,7 +28,7 @@ run() {  # run <name> <timeout_s> <command...>: stdout -> $O/name.json|log, stde
 }
 
 PART=${1:-all}
-want() { [ "$PART" = all ] || [ "$PART" = "$1" ]; }
+want() { { [ "$PART" = all ] && [ "$1" != ncu ]; } || [ "$PART" = "$1" ]; }   # (ncu only when asked for)
 
 if want single; then
 run pytest_default 900 python -m pytest tests -m gpu -x -q
@@ -37,6 +38,14 @@ ESR_TEST_UNVERIFIED=1 run pytest_fib_envmaps 300 python -m pytest tests/test_gpu
 ESR_MLP_TILE_OVERLAP=1 run pytest_tile_overlap 900 python -m pytest tests/test_gpu_mlp.py tests/test_gpu_voxurff.py tests/test_gpu_esrnerf.py -m gpu -x -q
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap 400 python bench.py --steps 20 --no-cpu-baseline
 ESR_MLP_TILE_OVERLAP=1 run bench_tile_overlap_eval 400 python bench.py --stage eval --steps 5
+fi
+
+if want ncu; then   # ~6 GPU-minutes: launch list + full capture of exactly the timed steps (numbers printed here are not bench values)
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --profiler-range"
+run ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file "$O/r02_launches.csv" $B
+run ncu_full 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o "$O/r02_full" -f $B
+# then, here: python scripts/ncu_summary.py launches gpurun_out/followup/r02_launches.csv profiles/r02_launches_summary.csv "..."
+#             python scripts/ncu_summary.py full gpurun_out/followup/r02_full.ncu-rep profiles/r02_top_kernels_ncu_full.json "..."
 fi
 
 if want pair && [ "$NGPU" -ge 2 ]; then
