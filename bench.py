@@ -662,7 +662,7 @@ def run_b200(a, rank, world, local_rank):
         row = {"kernel": name, "launches_per_step": cnt / a.steps, "ms_per_step": tot / a.steps}
         if w is not None:
             bound, work = w
-            row["work_per_step"] = work
+            row["work_per_step"] = float(work)
             per_s = work / (tot / a.steps * 1e-3) if tot > 0 else 0.0
             if bound == "hbm":
                 row.update(bound="hbm", achieved=per_s / 1e9, unit="GB/s", frac=per_s / 1e9 / pk["hbm_gbs"])
