@@ -101,7 +101,7 @@ class DvgoScene(ctypes.Structure):
 class MlpDesc(ctypes.Structure):
     """esr_mlp_desc_t"""
     _fields_ = [("k0", ctypes.c_int32), ("width", ctypes.c_int32), ("n_hidden", ctypes.c_int32),
-                ("n_out", ctypes.c_int32), ("act", ctypes.c_int32)]
+                ("n_out", ctypes.c_int32), ("act", ctypes.c_int32), ("precision", ctypes.c_int32)]
 
 
 P = ctypes.c_void_p

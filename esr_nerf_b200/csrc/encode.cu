@@ -176,7 +176,7 @@ struct RowWriter;
 template <>
 struct RowWriter<float> {
   float *row;
-  ESR_D RowWriter(float *b, int64_t r) : row(b + r * ESR_FEAT_DIM) {}
+  ESR_D RowWriter(float *b, int64_t r, int64_t = 0) : row(b + r * ESR_FEAT_DIM) {}
   ESR_D void finish() {}
   template <int COL0, int N>
   ESR_D void put(const float (&v)[N]) {
@@ -218,7 +218,7 @@ template <>
 struct RowWriter<__nv_bfloat16> : TiledRowWriter<ESR_FEAT_DIM> {
   __nv_bfloat16 *base;
   int64_t row;
-  ESR_D RowWriter(__nv_bfloat16 *b, int64_t r) : base(b), row(r) {}
+  ESR_D RowWriter(__nv_bfloat16 *b, int64_t r, int64_t = 0) : base(b), row(r) {}
   ESR_D void finish() { flush(base, row); }
   ESR_D void second(__nv_bfloat16 *b, int64_t r, const float (&col)[6]) {
     put<0>(col);
@@ -228,19 +228,32 @@ struct RowWriter<__nv_bfloat16> : TiledRowWriter<ESR_FEAT_DIM> {
 // Same tiled bf16 row, written chunk by chunk as the columns arrive (puts come in increasing column order): only the
 // words of the chunk in progress stay in registers instead of the whole 48-word row — the register budget that lets
 // the fine-stage instantiation of k_encode_fwd run 10 blocks per SM instead of 8.
-template <bool SECOND>
+// RES (esr_mlp_desc_t::precision = 1, out_is_bf16 = 2): every 16-byte bf16 chunk is followed into a second tiled
+// buffer (`res_off` 16-byte words further: the row count padded to whole tiles x 12 chunks) by the fp16 chunk of what
+// the bf16 rounding lost, v - bf16(v): the forward chain then sees the feature to ~19 bits while the weight-gradient
+// GEMM keeps reading the bf16 tile.
+template <bool SECOND, bool RES = false>
 struct StreamRowWriter {
   uint4 *b4, *b4b;       // b4b: the second copy of the row whose colour slot 0 (columns 0..5) holds `alt` (BRDF grid taps)
-  int64_t row;
+  int64_t row, res_off;
   uint32_t cur[4], alt[3];
-  ESR_D StreamRowWriter(__nv_bfloat16 *b, int64_t r) : b4(reinterpret_cast<uint4 *>(b)), b4b(nullptr), row(r) {}
+  uint32_t cur_r[RES ? 4 : 1], alt_r[RES ? 3 : 1];
+  ESR_D StreamRowWriter(__nv_bfloat16 *b, int64_t r, int64_t m_total = 0)
+      : b4(reinterpret_cast<uint4 *>(b)), b4b(nullptr), row(r), res_off(act_rows_padded(m_total) * (ESR_FEAT_DIM / 8)) {}
+  // bf16 pair of (a, b) and, with RES, the fp16 pair of the two rounding residuals
+  ESR_D static uint32_t pack(float a, float b, uint32_t &res) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    const uint32_t w = *reinterpret_cast<uint32_t *>(&p);
+    if constexpr (RES) {
+      const __half2 h = __floats2half2_rn(a - __uint_as_float(w << 16), b - __uint_as_float(w & 0xffff0000u));
+      res = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    return w;
+  }
   ESR_D void set_second(__nv_bfloat16 *b, const float (&col)[6]) {
     b4b = reinterpret_cast<uint4 *>(b);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      __nv_bfloat162 p = __floats2bfloat162_rn(col[2 * i], col[2 * i + 1]);
-      alt[i] = *reinterpret_cast<uint32_t *>(&p);
-    }
+    for (int i = 0; i < 3; ++i) alt[i] = pack(col[2 * i], col[2 * i + 1], alt_r[RES ? i : 0]);
   }
   template <int COL0, int N>
   ESR_D void put(const float (&v)[N]) {
@@ -248,13 +261,17 @@ struct StreamRowWriter {
 #pragma unroll
     for (int i = 0; i < N; i += 2) {
       const int wi = (COL0 + i) >> 1;
-      __nv_bfloat162 p = __floats2bfloat162_rn(v[i], v[i + 1]);
-      cur[wi & 3] = *reinterpret_cast<uint32_t *>(&p);
+      cur[wi & 3] = pack(v[i], v[i + 1], cur_r[RES ? (wi & 3) : 0]);
       if ((wi & 3) == 3) {
         const int64_t at = tiled_chunk_index(row, wi >> 2, ESR_FEAT_DIM / 8);
         __stcs(b4 + at, make_uint4(cur[0], cur[1], cur[2], cur[3]));
-        if constexpr (SECOND)
+        if constexpr (RES) __stcs(b4 + res_off + at, make_uint4(cur_r[0], cur_r[1], cur_r[2], cur_r[3]));
+        if constexpr (SECOND) {
           __stcs(b4b + at, wi == 3 ? make_uint4(alt[0], alt[1], alt[2], cur[3]) : make_uint4(cur[0], cur[1], cur[2], cur[3]));
+          if constexpr (RES)
+            __stcs(b4b + res_off + at, wi == 3 ? make_uint4(alt_r[0], alt_r[1], alt_r[2], cur_r[3])
+                                               : make_uint4(cur_r[0], cur_r[1], cur_r[2], cur_r[3]));
+        }
       }
     }
   }
@@ -282,7 +299,7 @@ constexpr int COL_SDF = 12, COL_FEAT = 13, COL_NRM = 37, COL_XYZ = 49, COL_SIN =
 
 // 8 blocks of 128 per SM (64 registers): measured 1.31 ms at config 2 against 1.37 / 1.47 ms for 10 / 12 blocks (48 / 40
 // registers spill 104 / 164 bytes); the whole-row writer at 8 blocks was 1.48 ms
-template <typename OutT, bool THIRD>
+template <typename OutT, bool THIRD, bool RES = false>
 __global__ void __launch_bounds__(ENC_THREADS, 8)
     k_encode_fwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
                  const float *__restrict__ rays_d, const float *__restrict__ viewdirs,
@@ -301,7 +318,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
   g.iy = world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy);
   g.iz = world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz);
   constexpr bool STREAM = sizeof(OutT) == 2;   // bf16 rows leave chunk by chunk; f32 rows (strict path) row-major
-  typename std::conditional<STREAM, StreamRowWriter<THIRD>, RowWriter<OutT>>::type wr(feat, j);
+  typename std::conditional<STREAM, StreamRowWriter<THIRD, RES>, RowWriter<OutT>>::type wr(feat, j, m3);
 
   {  // colour grids (module.py:24-35), channels-last
     const Cell c = make_cell(g.ix, g.iy, g.iz);
@@ -832,11 +849,14 @@ static int encode_fwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
   ESR_CHECK_ARG(!third_grid == !feat2);
   cudaStream_t st = (cudaStream_t)stream;
   ESR_STAGE("k_encode_fwd", st);
-#define ESR_ENC_FWD(T, THIRD)                                                                                          \
-  k_encode_fwd<T, THIRD><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid,       \
-                                                        emo_color_grid, h_ray, h_step, h_sdf, m3, (T *)feat, pts,      \
-                                                        third_grid, (T *)feat2, save_fd)
-  if (out_is_bf16) {
+#define ESR_ENC_FWD(T, ...)                                                                                            \
+  k_encode_fwd<T, __VA_ARGS__><<<cdiv(m3, 128), 128, 0, st>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid, off_color_grid, \
+                                                              emo_color_grid, h_ray, h_step, h_sdf, m3, (T *)feat, pts, \
+                                                              third_grid, (T *)feat2, save_fd)
+  if (out_is_bf16 == 2) {   // bf16 tile + fp16 residual tile (the x2 forward chain's layer-0 operand)
+    if (third_grid) ESR_ENC_FWD(__nv_bfloat16, true, true);
+    else ESR_ENC_FWD(__nv_bfloat16, false, true);
+  } else if (out_is_bf16) {
     if (third_grid) ESR_ENC_FWD(__nv_bfloat16, true);
     else ESR_ENC_FWD(__nv_bfloat16, false);
   } else {

@@ -149,10 +149,109 @@ ESR_D uint32_t pair_mask(uint32_t mk, int j) {
   return d;
 }
 // ------------------------------------------------------------------------------------------------
+// "x2" forward (esr_mlp_desc_t::precision = 1): fp16 hi + lo operand pairs, three MMAs per product.
+// ------------------------------------------------------------------------------------------------
+// The weights are scaled by 2^4 before the split so that the lo part of a typical |w| ~ 0.05 is a NORMAL fp16 number
+// (the pair then carries ~24 bits); the epilogues undo the scale in the fused multiply-add that applies the bias.
+constexpr float TC_WSCALE = 16.f;
+// instruction descriptor: D f32, A/B fp16, both K-major; M = 128 (cta_group::1) or 256 (cta_group::2: 128 rows per CTA)
+__host__ __device__ constexpr uint32_t make_idesc_h(int n, int m = TC_TM) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+ESR_D uint32_t pack2h(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+ESR_D uint32_t pack2h_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+ESR_D float2 unpack2h(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2 *>(&v)); }
+// relu(z0), relu(z1) as an fp16 pair hi plus the fp16 pair lo of what the first rounding lost: hi + lo carries 22
+// significant bits (an absolute error of 2^-25 where lo is subnormal, i.e. for values below 0.25)
+ESR_D void split2h_relu(float z0, float z1, uint32_t &hi, uint32_t &lo) {
+  hi = pack2h_relu(z0, z1);
+  const float2 h = unpack2h(hi);
+  lo = pack2h(fmaxf(z0, 0.f) - h.x, fmaxf(z1, 0.f) - h.y);
+}
+ESR_D void split2h(float z0, float z1, uint32_t &hi, uint32_t &lo) {
+  hi = pack2h(z0, z1);
+  const float2 h = unpack2h(hi);
+  lo = pack2h(z0 - h.x, z1 - h.y);
+}
+// a packed bf16 pair as the same two values in fp16 (exact for 2^-14 <= |v| < 65504; below that the error is < 2^-25)
+ESR_D uint32_t bf2_to_h2(uint32_t w) { return pack2h(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+// (a0, a1) = (a0, a1) * s + (b.x, b.y) as one packed FFMA2 (fma.rn.f32x2, sm_100)
+ESR_D void fma2(float &a0, float &a1, float s, float2 b) {
+  asm("{\n\t.reg .b64 ra, rs, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rs, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
+      "fma.rn.f32x2 ra, ra, rs, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(s), "f"(b.x), "f"(b.y));
+}
+ESR_D void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// ---- CTA pair (cta_group::2): one MMA spans the two SMs of a cluster of 2; each CTA supplies its own 128 rows of A /
+// D (own TMEM) and HALF of the B rows (own shared memory), the leader CTA (cluster rank 0) issues ----
+ESR_D uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+ESR_D void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in the CTA of cluster rank `rank`
+ESR_D uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+ESR_D void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+ESR_D void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // waits for arrivals that may come from the peer CTA
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+ESR_D void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {   // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+ESR_D void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+ESR_D void mma_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the mbarrier at the same shared-memory offset of BOTH CTAs receives one arrival once every MMA issued so far has completed
+ESR_D void mma_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // image layout (bytes).  Every matrix is bf16 chunk-major [K/8][R][8].
 // ------------------------------------------------------------------------------------------------
 struct TcLayout {
-  int k0, NH, dxn;
+  int k0, NH, dxn, x2;
   __host__ __device__ int64_t mat_bytes(int rows, int k) const { return (int64_t)rows * k * 2; }
   // forward section: W0 [W x k0], W_1..W_{NH-1} [W x W], Wo [16 x W], bias f32 [NH*W + 16]
   __host__ __device__ int64_t f_w0() const { return 0; }
@@ -166,18 +265,45 @@ struct TcLayout {
   __host__ __device__ int64_t b_w0() const { return b_wh(NH); }
   __host__ __device__ int64_t b_bytes() const { return b_w0() + mat_bytes(dxn, TC_W); }
   __host__ __device__ int64_t bwd_off() const { return (f_bytes() + 127) / 128 * 128; }
-  __host__ __device__ int64_t total() const { return bwd_off() + (b_bytes() + 127) / 128 * 128; }
+  // x2 section (precision 1): fp16 hi / lo parts of the forward matrices, scaled by TC_WSCALE.
+  //   radiance chains (k0 = 96, CTA pair): per cluster rank r the N-half r of every matrix, parts adjacent:
+  //     [W0 p0 | W0 p1] [W1 p0 | W1 p1] ... [Wo p0 | Wo p1]  (matrix halves [W/2 x K] / [8 x W], chunk-major), then the
+  //     second rank, then the f32 biases — byte for byte the shared-memory image of k_mlp_fwd_x2
+  //   tone-map net (k0 = 48, one CTA): [W0 p0 | W0 p1 | Wo p0 | Wo p1] full matrices
+  __host__ __device__ int64_t x2_off() const { return bwd_off() + (b_bytes() + 127) / 128 * 128; }
+  __host__ __device__ int64_t x2_w0_part() const { return (k0 == 96 ? TC_W / 2 : TC_W) * (int64_t)k0 * 2; }
+  __host__ __device__ int64_t x2_wh_part() const { return (TC_W / 2) * (int64_t)TC_W * 2; }
+  __host__ __device__ int64_t x2_wo_part() const { return (k0 == 96 ? TC_NOUT_PAD / 2 : TC_NOUT_PAD) * (int64_t)TC_W * 2; }
+  __host__ __device__ int64_t x2_wh(int l) const { return 2 * x2_w0_part() + (int64_t)(l - 1) * 2 * x2_wh_part(); }
+  __host__ __device__ int64_t x2_wo() const { return x2_wh(NH); }
+  __host__ __device__ int64_t x2_rank_bytes() const { return x2_wo() + 2 * x2_wo_part(); }
+  __host__ __device__ int64_t x2_bias() const { return (k0 == 96 ? 2 : 1) * x2_rank_bytes(); }
+  __host__ __device__ int64_t x2_bytes() const { return x2_bias() + (int64_t)(NH * TC_W + TC_NOUT_PAD) * 4; }
+  __host__ __device__ int64_t total() const { return x2_off() + (x2 ? (x2_bytes() + 127) / 128 * 128 : 0); }
+  // precision 1, radiance-shaped nets: the transposed matrices of the data-gradient chain are fp16 (k_mlp_dgrad_tc H16)
+  __host__ __device__ bool bwd_h16() const { return x2 && k0 == 96; }
 };
 
-static TcLayout tc_layout(const esr_mlp_desc_t *d) { return TcLayout{d->k0, d->n_hidden, d->k0 == 96 ? 64 : 48}; }
+static TcLayout tc_layout(const esr_mlp_desc_t *d) {
+  return TcLayout{d->k0, d->n_hidden, d->k0 == 96 ? 64 : 48, d->precision == 1};
+}
 
 ESR_HD int64_t chunk_index(int rows, int r, int k) { return ((int64_t)(k >> 3) * rows + r) * 8 + (k & 7); }
+
+// 16-bit store of a transposed (data-gradient) matrix element: bf16, or fp16 for the fp16 data-gradient chain
+struct BwdElem {
+  uint16_t *p;
+  bool h16;
+  __device__ void set(int64_t i, float v) const {
+    p[i] = h16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16(v));
+  }
+};
 
 __global__ void k_tc_pack(TcLayout T, MlpLayout L, const float *__restrict__ flat, uint8_t *__restrict__ image) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int W = TC_W, NH = T.NH;
   __nv_bfloat16 *f = reinterpret_cast<__nv_bfloat16 *>(image);
-  __nv_bfloat16 *b = reinterpret_cast<__nv_bfloat16 *>(image + T.bwd_off());
+  const BwdElem b{reinterpret_cast<uint16_t *>(image + T.bwd_off()), T.bwd_h16()};
   // one thread per (layer-matrix element) of the padded logical matrices; enumerate W0, Wh.., Wo in turn
   int64_t e = i;
   // W0 [W x k0]
@@ -185,7 +311,7 @@ __global__ void k_tc_pack(TcLayout T, MlpLayout L, const float *__restrict__ fla
     const int o = (int)(e / T.k0), in = (int)(e % T.k0);
     const float v = flat[L.flat_w(0) + e];
     f[T.f_w0() / 2 + chunk_index(W, o, in)] = __float2bfloat16(v);
-    if (in < T.dxn) b[T.b_w0() / 2 + chunk_index(T.dxn, in, o)] = __float2bfloat16(v);
+    if (in < T.dxn) b.set(T.b_w0() / 2 + chunk_index(T.dxn, in, o), v);
     return;
   }
   e -= (int64_t)W * T.k0;
@@ -194,7 +320,7 @@ __global__ void k_tc_pack(TcLayout T, MlpLayout L, const float *__restrict__ fla
       const int o = (int)(e / W), in = (int)(e % W);
       const float v = flat[L.flat_w(l) + e];
       f[T.f_wh(l) / 2 + chunk_index(W, o, in)] = __float2bfloat16(v);
-      b[T.b_wh(l) / 2 + chunk_index(W, in, o)] = __float2bfloat16(v);
+      b.set(T.b_wh(l) / 2 + chunk_index(W, in, o), v);
       return;
     }
     e -= (int64_t)W * W;
@@ -204,13 +330,63 @@ __global__ void k_tc_pack(TcLayout T, MlpLayout L, const float *__restrict__ fla
     const int o = (int)(e / W), in = (int)(e % W);
     const float v = o < 8 ? flat[L.flat_w(NH) + (int64_t)o * W + in] : 0.f;
     f[T.f_wo() / 2 + chunk_index(TC_NOUT_PAD, o, in)] = __float2bfloat16(v);
-    b[T.b_wo() / 2 + chunk_index(W, in, o)] = __float2bfloat16(v);
+    b.set(T.b_wo() / 2 + chunk_index(W, in, o), v);
     return;
   }
   e -= (int64_t)TC_NOUT_PAD * W;
   // biases
   if (e < (int64_t)NH * W + TC_NOUT_PAD) {
     float *bias = reinterpret_cast<float *>(image + T.f_bias());
+    float v;
+    if (e < (int64_t)NH * W) {
+      const int l = (int)(e / W);
+      v = flat[L.flat_b(l) + (e - (int64_t)l * W)];
+    } else {
+      const int o = (int)(e - (int64_t)NH * W);
+      v = o < 8 ? flat[L.flat_b(NH) + o] : 0.f;
+    }
+    bias[e] = v;
+  }
+}
+
+// x2 section: one thread per element of the (padded) forward matrices and biases
+__global__ void k_tc_pack_x2(TcLayout T, MlpLayout L, const float *__restrict__ flat, uint8_t *__restrict__ image) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = TC_W, NH = T.NH;
+  uint8_t *sec = image + T.x2_off();
+  const bool pair = T.k0 == 96;
+  // element (o, in) of a matrix with `rows` output rows, K = kdim, stored at byte `base` of a rank section
+  auto put = [&](int64_t base, int64_t part_bytes, int rows, int o, int in, float v) {
+    const int half = pair ? rows / 2 : rows;
+    const int rank = o / half, oh = o % half;
+    const __half hi = __float2half_rn(v * TC_WSCALE);
+    const __half lo = __float2half_rn(v * TC_WSCALE - __half2float(hi));
+    __half *dst = reinterpret_cast<__half *>(sec + (int64_t)rank * T.x2_rank_bytes() + base);
+    dst[chunk_index(half, oh, in)] = hi;
+    dst[part_bytes / 2 + chunk_index(half, oh, in)] = lo;
+  };
+  int64_t e = i;
+  if (e < (int64_t)W * T.k0) {
+    const int o = (int)(e / T.k0), in = (int)(e % T.k0);
+    put(0, T.x2_w0_part(), W, o, in, flat[L.flat_w(0) + e]);
+    return;
+  }
+  e -= (int64_t)W * T.k0;
+  for (int l = 1; l < NH; ++l) {
+    if (e < (int64_t)W * W) {
+      put(T.x2_wh(l), T.x2_wh_part(), W, (int)(e / W), (int)(e % W), flat[L.flat_w(l) + e]);
+      return;
+    }
+    e -= (int64_t)W * W;
+  }
+  if (e < (int64_t)TC_NOUT_PAD * W) {
+    const int o = (int)(e / W), in = (int)(e % W);
+    put(T.x2_wo(), T.x2_wo_part(), TC_NOUT_PAD, o, in, o < 8 ? flat[L.flat_w(NH) + (int64_t)o * W + in] : 0.f);
+    return;
+  }
+  e -= (int64_t)TC_NOUT_PAD * W;
+  if (e < (int64_t)NH * W + TC_NOUT_PAD) {
+    float *bias = reinterpret_cast<float *>(sec + T.x2_bias());
     float v;
     if (e < (int64_t)NH * W) {
       const int l = (int)(e / W);
@@ -290,6 +466,24 @@ ESR_D void tonemap_pe_channel(float x, uint4 &lo, uint4 &hi, float (&sn)[5], flo
     __sincosf(__fmul_rn(x, (float)(1 << f)), &sn[f], &cs[f]);
   lo = make_uint4(pack2(x, sn[0]), pack2(sn[1], sn[2]), pack2(sn[3], sn[4]), pack2(cs[0], cs[1]));
   hi = make_uint4(pack2(cs[2], cs[3]), pack2(cs[4], 0.f), 0u, 0u);
+}
+
+// x2 variant: the same 16 columns as fp16 hi + lo pairs (chunks hl / hh and ll / lh); accurate sines / cosines (the SFU
+// versions err by ~2^-21 absolute, more for large arguments — the size of the lo part)
+ESR_D void tonemap_pe_channel_x2(float x, uint4 &hl, uint4 &hh, uint4 &ll, uint4 &lh, float (&sn)[5], float (&cs)[5]) {
+#pragma unroll
+  for (int f = 0; f < 5; ++f) sincosf(__fmul_rn(x, (float)(1 << f)), &sn[f], &cs[f]);
+  uint32_t h[6], l[6];
+  split2h(x, sn[0], h[0], l[0]);
+  split2h(sn[1], sn[2], h[1], l[1]);
+  split2h(sn[3], sn[4], h[2], l[2]);
+  split2h(cs[0], cs[1], h[3], l[3]);
+  split2h(cs[2], cs[3], h[4], l[4]);
+  split2h(cs[4], 0.f, h[5], l[5]);
+  hl = make_uint4(h[0], h[1], h[2], h[3]);
+  hh = make_uint4(h[4], h[5], 0u, 0u);
+  ll = make_uint4(l[0], l[1], l[2], l[3]);
+  lh = make_uint4(l[4], l[5], 0u, 0u);
 }
 
 // NO = compile-time bound on the real output columns (3: radiance / tone-map / emission nets, 8: the 5-output BRDF net)
@@ -512,6 +706,231 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward chain, "x2" precision (esr_mlp_desc_t::precision = 1), on a CTA PAIR
+// ------------------------------------------------------------------------------------------------
+// Why.  The reference's nets are fp32 (pbr/module.py:6-83).  With bf16 operands ~0.4 % of the hidden pre-activations
+// land on the other side of zero, each flipped ReLU mask changes one sample's whole contribution to the weight /
+// colour-grid gradients, and those gradients end up 2-5 % (relative L2) away from the reference's.  Carrying every
+// forward operand — input features, weights, hidden activations — as an fp16 pair hi + lo (22 significant bits) and
+// forming each product as hi.hi + hi.lo + lo.hi (fp32 accumulation in TMEM) makes the pre-activations, hence the
+// masks and the outputs, fp32-class; the backward kernels stay on single bf16 operands (their rounding errors are
+// zero-mean and average out over the samples): every parameter gradient within 1e-2 (measured 3e-3 .. 5e-3), outputs
+// ~1e-6.  Three times the MMA work of the bf16 chain, forward only.
+//
+// How.  Two parts of every weight matrix do not fit one SM's shared memory (2 x 190 KB), so the chain runs on the two
+// SMs of a cluster of 2 with cta_group::2 MMAs (M = 256): CTA r holds rows [96 r, 96 r + 96) of every matrix (both
+// parts: 190 KB) as its half of the B operand and the 128 rows [256 t + 128 r, +128) of the pair's tile t in its own
+// TMEM; the leader CTA's issuer thread drives both tensor cores.  The A operand always comes from TMEM: the hidden
+// layers' epilogues write the (hi, lo) pair of the activation there, and layer 0's operand — the feature rows, stored
+// by the encoder as a bf16 tile (the one the weight-gradient GEMM reads) plus an fp16 tile of what that rounding lost —
+// is loaded into registers one tile ahead and stored to TMEM by the same threads (no x tile in shared memory).
+// TMEM columns: D [0,192) accumulator (one region suffices: every epilogue warp has read all of its D columns before
+// it arrives on the first chunk barrier), A_hi [192,288), A_lo [288,384), O [384,400) output-layer accumulator.
+// Synchronisation: the chunk barriers live in the leader CTA and count the 32 epilogue warps of both CTAs (the peer's
+// arrive through shared::cluster); every commit is multicast to the MMA barrier of both CTAs.
+constexpr uint32_t X2_D = 0, X2_A0 = 192, X2_A1 = 288, X2_O = 384;
+
+template <int K0, int NH>
+struct X2Sm {
+  static constexpr int HALF = TC_W / 2, OHALF = TC_NOUT_PAD / 2;
+  static constexpr int w0_part = HALF * K0 * 2, wh_part = HALF * TC_W * 2, wo_part = OHALF * TC_W * 2;
+  static constexpr int w0 = 0;
+  static constexpr int wh = w0 + 2 * w0_part;
+  static constexpr int wo = wh + (NH - 1) * 2 * wh_part;
+  static constexpr int rank_bytes = wo + 2 * wo_part;            // == TcLayout::x2_rank_bytes()
+  static constexpr int bias = rank_bytes;
+  static constexpr int bias_bytes = (NH * TC_W + TC_NOUT_PAD) * 4;
+  static constexpr int bar = (bias + bias_bytes + 15) / 16 * 16;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot
+  static constexpr int bytes = bar + 64;
+};
+
+template <int K0, int NH, int NO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    k_mlp_fwd_x2(const uint8_t *__restrict__ image_x2, const __nv_bfloat16 *__restrict__ x,
+                 const __half *__restrict__ x_lo, int64_t row_begin, int64_t row_end, int64_t m_total,
+                 float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden, int64_t save_begin, int n_out, int act) {
+  static_assert(K0 == 96, "x chunks per column group: K0 / 32");
+  extern __shared__ __align__(128) uint8_t smem[];
+  using S = X2Sm<K0, NH>;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t sbase = smem_addr(smem);
+  const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
+
+  stage_bytes(smem, image_x2 + (int64_t)rank * S::rank_bytes, S::rank_bytes);
+  stage_bytes(smem + S::bias, image_x2 + 2 * (int64_t)S::rank_bytes, S::bias_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mbar_init(bar_chunk + 8 * c, 2 * TC_EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (is_issuer) tmem_alloc2(smem_addr(tmem_slot), TM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs: weights staged, mbarriers initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
+
+  const int64_t n_pt = (row_end - row_begin + 2 * TC_TM - 1) / (2 * TC_TM);   // tiles of the pair: 256 rows
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (is_epi) {
+    const EpiThread et(warp, lane);
+    const int t = et.row_in_tile;
+    const uint32_t cbar_chunk = mapa_rank(bar_chunk, 0);   // the leader's chunk barriers
+    const uint4 *x4 = reinterpret_cast<const uint4 *>(x), *l4 = reinterpret_cast<const uint4 *>(x_lo);
+    uint32_t phase = 0;
+    // layer-0 operand: column group g moves feature chunks 3 g .. 3 g + 2 (24 features) of its row, both tiles
+    uint4 xb[3], xl[3];
+    auto load_x = [&](int64_t pt) {
+      const int64_t row = row_begin + (2 * pt + rank) * TC_TM + t;
+      const bool ok = pt < n_pt && row < row_end;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int64_t at = tiled_chunk_index(ok ? row : row_begin, 3 * et.grp + i, K0 / 8);
+        xb[i] = ok ? __ldg(x4 + at) : make_uint4(0u, 0u, 0u, 0u);
+        xl[i] = ok ? __ldg(l4 + at) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    auto arrive_chunk = [&](int cc) {   // this warp's part of chunk cc of the A operand is in TMEM
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(cbar_chunk + 8 * cc);
+    };
+    load_x(pair);
+    for (int64_t pt = pair; pt < n_pt; pt += n_pairs) {
+      const int64_t row = row_begin + (2 * pt + rank) * TC_TM + t;
+      const bool valid = row < row_end;
+      const bool save = valid && hidden && row >= save_begin;
+      const bool save_w = __any_sync(FULL, save);
+      // ---- layer-0 operand -> TMEM (A_hi = the bf16 tile's values as fp16, A_lo = the residual tile) ----
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint32_t col = 4 * (3 * et.grp + i);
+        tmem_st4(tmem + et.lane_base + X2_A0 + col, bf2_to_h2(xb[i].x), bf2_to_h2(xb[i].y), bf2_to_h2(xb[i].z),
+                 bf2_to_h2(xb[i].w));
+        tmem_st4(tmem + et.lane_base + X2_A1 + col, xl[i].x, xl[i].y, xl[i].z, xl[i].w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) mbar_arrive_cluster(cbar_chunk + 8 * cc);
+      }
+#pragma unroll 1
+      for (int l = 0; l < NH; ++l) {
+        if (l == NH - 1) load_x(pt + n_pairs);   // next tile's feature rows: in flight under the rest of this tile
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        const float *b = sbias + l * TC_W;
+        uint4 *hl = hidden ? reinterpret_cast<uint4 *>(hidden + (int64_t)l * act_rows_padded(m_total) * TC_W) : nullptr;
+        uint32_t r[3][16];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + X2_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
+        tmem_ld_wait();
+        uint32_t mask[2] = {0u, 0u};
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const int col0 = TC_GCOLS * et.grp + 16 * cc;
+          uint32_t ph[8], pl[8], pb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
+            float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
+            fma2(z0, z1, 1.f / TC_WSCALE, bb);
+            split2h_relu(z0, z1, ph[j], pl[j]);
+            if (save_w) {   // bf16 copy + masks for the backward kernels (same layout as the bf16 chain writes)
+              pb[j] = pack2_relu(z0, z1);
+              const uint32_t tt = pb[j] + 0x7fff7fffu;
+              constexpr uint32_t one2 = 0x00010001u;
+              mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (one2 << (8 * (cc & 1) + j));
+            }
+          }
+          tmem_st8(tmem + et.lane_base + X2_A0 + col0 / 2, ph);
+          tmem_st8(tmem + et.lane_base + X2_A1 + col0 / 2, pl);
+          if (save) {
+            hl[act_chunk_index(row, col0 / 8)] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+            hl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(pb[4], pb[5], pb[6], pb[7]);
+          }
+          arrive_chunk(cc);
+        }
+        if (save) {
+          uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
+          mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
+        }
+      }
+      // ---- output layer epilogue (column group 0 threads); every warp observes the phase: the A regions are free ----
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      if (et.grp == 0) {
+        uint32_t r[16];
+        tmem_ld16(tmem + et.lane_base + X2_O, r);
+        tmem_ld_wait();
+        if (valid) {
+          const float *bo = sbias + NH * TC_W;
+#pragma unroll
+          for (int c = 0; c < NO; ++c)
+            if (c < n_out) y[row * n_out + c] = act_fwd(__fmaf_rn(__uint_as_float(r[c]), 1.f / TC_WSCALE, bo[c]), act);
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (is_issuer && rank == 0 && lane == 0) {
+    uint32_t cphase = 0;
+    constexpr uint32_t idesc_h = make_idesc_h(TC_W, 2 * TC_TM), idesc_o = make_idesc_h(TC_NOUT_PAD, 2 * TC_TM);
+    // one K-step (16 features) of one product: hi.hi + hi.lo + lo.hi
+    auto product = [&](uint32_t dst, int s, uint32_t w_hi, uint32_t part_bytes, uint32_t rows16, uint32_t idesc, bool first) {
+      const uint64_t bh = make_desc(w_hi + 2 * s * rows16, rows16, 128), bl = make_desc(w_hi + part_bytes + 2 * s * rows16, rows16, 128);
+      mma_ts2(dst, tmem + X2_A0 + 8 * s, bh, idesc, !first);
+      mma_ts2(dst, tmem + X2_A0 + 8 * s, bl, idesc, 1);
+      mma_ts2(dst, tmem + X2_A1 + 8 * s, bh, idesc, 1);
+    };
+    for (int64_t pt = pair; pt < n_pt; pt += n_pairs) {
+      // ---- layer 0: the feature rows the epilogue warps of both CTAs have put into TMEM ----
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        mbar_wait_cluster(bar_chunk + 8 * cc, cphase);
+        tc_fence_after();
+#pragma unroll
+        for (int s = cc; s < K0 / 16; s += 3)
+          product(tmem + X2_D, s, sbase + S::w0, S::w0_part, S::HALF * 16, idesc_h, s == 0);
+      }
+      mma_commit2(bar);
+      cphase ^= 1;
+#pragma unroll 1
+      for (int l = 0; l < NH; ++l) {
+        const bool last = l + 1 == NH;
+        const uint32_t dst = tmem + (last ? X2_O : X2_D);
+        const uint32_t wl = last ? sbase + S::wo : sbase + S::wh + l * (2 * S::wh_part);
+        const uint32_t part = last ? S::wo_part : S::wh_part;
+        const uint32_t rows16 = (last ? S::OHALF : S::HALF) * 16;
+        const uint32_t idesc = last ? idesc_o : idesc_h;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          mbar_wait_cluster(bar_chunk + 8 * cc, cphase);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) product(dst, 3 * g + cc, wl, part, rows16, idesc, (cc | g) == 0);
+        }
+        mma_commit2(bar);
+        cphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // no CTA of the pair may exit (or free its TMEM) while the other can still address it
+  if (is_issuer) tmem_dealloc2(tmem, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // tone-map forward, two tiles in flight
 // ------------------------------------------------------------------------------------------------
 // The tone-map net (33 -> 192 -> 3) is too small for the generic chain: one 128-row tile is a string of latencies
@@ -524,28 +943,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 //   mbarriers per slot: x ready (12 encoding warps) -> MMA0 done (commit) -> A ready (16 warps) -> out MMA done (commit)
 // The issuer alternates [out MMA of tile i] [MMA0 of tile i + 2]; the epilogue warps alternate [layer-0 epilogue of tile
 // i] [output epilogue of tile i - 1], so each side always has the other slot's work to do while a commit is in flight.
-struct Tm2Sm {
+template <bool X2>
+struct Tm2SmT {
   using F = FwdSm<48, 1>;
-  static constexpr int x0 = (F::weights_bytes + 127) / 128 * 128;
-  static constexpr int x_bytes = TC_TM * 48 * 2;
+  // X2: [W0 hi | W0 lo | Wo hi | Wo lo] fp16 (TcLayout x2 section of the tone-map net) then the f32 biases
+  static constexpr int w0 = 0, w0_part = TC_W * 48 * 2;
+  static constexpr int wo = X2 ? 2 * w0_part : F::wo, wo_part = TC_NOUT_PAD * TC_W * 2;
+  static constexpr int bias = X2 ? wo + 2 * wo_part : F::bias;
+  static constexpr int weights_bytes = bias + (TC_W + TC_NOUT_PAD) * 4;
+  static constexpr int x0 = (weights_bytes + 127) / 128 * 128;
+  static constexpr int x_part = TC_TM * 48 * 2;
+  static constexpr int x_bytes = (X2 ? 2 : 1) * x_part;   // per slot: hi tile (+ lo tile)
   static constexpr int bar = x0 + 2 * x_bytes;      // bar_x[2], bar_mma0[2], bar_a[2], bar_out[2] (8 B each), TMEM slot
   static constexpr int bytes = bar + 8 * 8 + 16;
 };
+using Tm2Sm = Tm2SmT<false>;
 
-template <int NO>
+template <int NO, bool X2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_tonemap_fwd2(const uint8_t *__restrict__ image, const float *__restrict__ lin, int64_t m, float *__restrict__ y,
                    int n_out, int act) {
+  // X2 (precision 1): `image` is the x2 section of the tone-map image (fp16 hi / lo weights scaled by TC_WSCALE, biases);
+  // the encoded tile is kept as an fp16 hi and an fp16 lo tile, every product is three MMAs, and the pair of the hidden
+  // activation fills all 192 columns of the consumed accumulator D_s (hi [0,96), lo [96,192))
   extern __shared__ __align__(128) uint8_t smem[];
-  using S = Tm2Sm;
-  using F = FwdSm<48, 1>;
+  using S = Tm2SmT<X2>;
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
   const uint32_t bar_x = sbase + S::bar, bar_mma0 = bar_x + 16, bar_a = bar_x + 32, bar_out = bar_x + 48;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 64);
 
-  stage_bytes(smem, image, F::weights_bytes);
+  stage_bytes(smem, image, S::weights_bytes);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -562,20 +991,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const float *sbias = reinterpret_cast<const float *>(smem + F::bias);
+  const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
 
   const int64_t n_tiles = (m + TC_TM - 1) / TC_TM;
   const int n_my = blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;   // tiles of this CTA
   const EpiThread et(warp, lane);
   const int t = et.row_in_tile;
+  constexpr uint32_t idesc_h = X2 ? make_idesc_h(TC_W) : make_idesc(TC_W);
+  constexpr uint32_t idesc_o = X2 ? make_idesc_h(TC_NOUT_PAD) : make_idesc(TC_NOUT_PAD);
+  constexpr int NT = X2 ? 3 : 1;   // MMAs per product: hi.hi, hi.lo, lo.hi
 
   if (is_issuer) {
     if (lane == 0) {
       auto mma0 = [&](int s) {   // layer 0 of the tile waiting in slot s: A = x_s (shared), B = W0
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-          mma_ss(tmem + 192 * s, make_desc(sbase + S::x0 + s * S::x_bytes + 2 * k * (TC_TM * 16), TC_TM * 16, 128),
-                 make_desc(sbase + F::w0 + 2 * k * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), k > 0);
+#pragma unroll
+          for (int term = 0; term < NT; ++term) {
+            const uint32_t xa = sbase + S::x0 + s * S::x_bytes + (term == 2 ? S::x_part : 0) + 2 * k * (TC_TM * 16);
+            const uint32_t wb = sbase + S::w0 + (term == 1 ? S::w0_part : 0) + 2 * k * (TC_W * 16);
+            mma_ss(tmem + 192 * s, make_desc(xa, TC_TM * 16, 128), make_desc(wb, TC_W * 16, 128), idesc_h, (k | term) != 0);
+          }
         mma_commit(bar_mma0 + 8 * s);
       };
       for (int i = 0; i < 2 && i < n_my; ++i) {
@@ -588,9 +1024,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(bar_a + 8 * s, (i >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < TC_W / 16; ++k)      // output layer: A = bf16 activations in TMEM (over D_s), B = Wo
-          mma_ts(tmem + 384 + 16 * s, tmem + 192 * s + 8 * k,
-                 make_desc(sbase + F::wo + 2 * k * (TC_NOUT_PAD * 16), TC_NOUT_PAD * 16, 128), make_idesc(TC_NOUT_PAD), k > 0);
+        for (int k = 0; k < TC_W / 16; ++k)      // output layer: A = activations in TMEM (over D_s), B = Wo
+#pragma unroll
+          for (int term = 0; term < NT; ++term)
+            mma_ts(tmem + 384 + 16 * s, tmem + 192 * s + (term == 2 ? 96 : 0) + 8 * k,
+                   make_desc(sbase + S::wo + (term == 1 ? S::wo_part : 0) + 2 * k * (TC_NOUT_PAD * 16), TC_NOUT_PAD * 16, 128),
+                   idesc_o, (k | term) != 0);
         mma_commit(bar_out + 8 * s);
         if (i + 2 < n_my) {                       // in order behind the out MMA: D_s / A_s are free when it starts
           mbar_wait(bar_x + 8 * s, ((i + 2) >> 1) & 1);
@@ -607,9 +1046,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const float v = ok ? __ldg(lin + 3 * row + et.grp) : 0.f;
         uint4 lo, hi;
         float sn[5], cs[5];
-        tonemap_pe_channel(v, lo, hi, sn, cs);
-        if (!ok) lo = hi = make_uint4(0u, 0u, 0u, 0u);
         uint8_t *xs = smem + S::x0 + (i & 1) * S::x_bytes;
+        if constexpr (X2) {
+          uint4 ll, lh;
+          tonemap_pe_channel_x2(v, lo, hi, ll, lh, sn, cs);
+          if (!ok) ll = lh = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4 *>(xs + S::x_part + (2 * et.grp) * (TC_TM * 16) + t * 16) = ll;
+          *reinterpret_cast<uint4 *>(xs + S::x_part + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = lh;
+        } else {
+          tonemap_pe_channel(v, lo, hi, sn, cs);
+        }
+        if (!ok) lo = hi = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4 *>(xs + (2 * et.grp) * (TC_TM * 16) + t * 16) = lo;
         *reinterpret_cast<uint4 *>(xs + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hi;
         fence_proxy_async();
@@ -630,7 +1077,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const float *bo = sbias + TC_W;
 #pragma unroll
           for (int c = 0; c < NO; ++c)
-            if (c < n_out) y[row * n_out + c] = act_fwd(__uint_as_float(r[c]) + bo[c], act);
+            if (c < n_out)
+              y[row * n_out + c] = act_fwd(X2 ? __fmaf_rn(__uint_as_float(r[c]), 1.f / TC_WSCALE, bo[c]) : __uint_as_float(r[c]) + bo[c], act);
         }
       }
       tc_fence_before();
@@ -652,14 +1100,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       for (int cc = 0; cc < 3; ++cc) {
         const int col0 = TC_GCOLS * et.grp + 16 * cc;
         uint32_t p[8];
+        [[maybe_unused]] uint32_t pl[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
           float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
-          add2(z0, z1, bb);
-          p[j] = pack2_relu(z0, z1);
+          if constexpr (X2) {
+            fma2(z0, z1, 1.f / TC_WSCALE, bb);
+            split2h_relu(z0, z1, p[j], pl[j]);
+          } else {
+            add2(z0, z1, bb);
+            p[j] = pack2_relu(z0, z1);
+          }
         }
         tmem_st8(tmem + et.lane_base + 192 * s + col0 / 2, p);
+        if constexpr (X2) tmem_st8(tmem + et.lane_base + 192 * s + 96 + col0 / 2, pl);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -691,7 +1146,14 @@ struct BwdSm {
 // OVL = tile overlap (opt-in, see k_mlp_fwd_tc): the next tile's dZ_out tile is made under this tile's chain and its
 // first MMA (dZ_out W_o -> D0) is issued behind this tile's last MMA, so that it runs under the d_x epilogue; the first
 // MMA's commit has its own mbarrier (bar_first).
-template <int K0, int NH, int DXN, int NO, bool ACC, bool OVL = false>
+// H16 = fp16 chain (precision 1): the cotangents travel through the chain as fp16 (11 significant bits against bf16's
+// 8) and the transposed weights are fp16.  fp16's narrow exponent is dealt with PER ROW: the chain is linear in a row's
+// output cotangent, so row r is multiplied by a power of two s_r that puts max|dZ_out[r]| in [16, 32) (what the chain can
+// add on top stays far below 65504, what it loses at the bottom is an ABSOLUTE error of s_r^-1 2^-25, irrelevant in sums
+// over rows); everything that leaves the kernel (bf16 dZ_l for the weight-gradient GEMM, d_x) is multiplied by 1 / s_r,
+// exactly.  Same MMAs as the bf16 chain; the colour-grid / feature gradients it produces are ~8x closer to the
+// reference's (5e-4 instead of 4e-3 relative L2).
+template <int K0, int NH, int DXN, int NO, bool ACC, bool OVL = false, bool H16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_dgrad_tc(const uint8_t *__restrict__ image_bwd, const float *__restrict__ y, const float *__restrict__ d_y,
                    int64_t row_begin, int64_t row_end, int64_t m_total, const __nv_bfloat16 *__restrict__ hidden,
@@ -711,6 +1173,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // OVL: the next tile's first MMA writes D0 under the d_x epilogue: D0 must be the accumulator of the last chain
   // step (read before the arrival on bar_x), not of d_x
   static_assert(!OVL || (NH & 1), "tile overlap: odd number of hidden layers (the d_x accumulator lives in D1)");
+  static_assert(!(OVL && H16), "the fp16 chain is instantiated without the tile overlap");
+  [[maybe_unused]] float *s_inv = reinterpret_cast<float *>(smem + S::bytes);   // H16: 1 / s_r of the tile's rows
+  constexpr uint32_t idesc_w = H16 ? make_idesc_h(TC_W) : make_idesc(TC_W);
+  constexpr uint32_t idesc_x = H16 ? make_idesc_h(DXN) : make_idesc(DXN);
 
   stage_bytes(smem, image_bwd, S::weights_bytes);
   if (threadIdx.x == 0) {
@@ -840,18 +1306,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         zo[tiled_chunk_index(row, 0, 2)] = dz16;
         zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
       }
-      *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
+      if constexpr (H16) {   // the chain's own copy: fp16, times the row's power-of-two scale
+        float mxa = 0.f;
+#pragma unroll
+        for (int c = 0; c < NO; ++c) mxa = fmaxf(mxa, fabsf(dz[c]));
+        const int e = (__float_as_int(mxa) >> 23) & 0xff;          // biased exponent of the row's largest |dZ_out|
+        const bool scaled = e >= 8 && e <= 250;                    // zero / denormal / absurd rows travel unscaled
+        const float sr = scaled ? __int_as_float((258 - e) << 23) : 1.f;   // 2^(4 - (e - 127))
+        s_inv[t] = scaled ? __int_as_float((e - 4) << 23) : 1.f;
+        *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) =
+            make_uint4(pack2h(dz[0] * sr, dz[1] * sr), pack2h(dz[2] * sr, dz[3] * sr), pack2h(dz[4] * sr, dz[5] * sr),
+                       pack2h(dz[6] * sr, dz[7] * sr));
+      } else {
+        *reinterpret_cast<uint4 *>(smem + S::dz + t * 16) = dz16;
+      }
       fence_proxy_async();
     }
     prefetch(tile + gridDim.x);
     tc_fence_before();
     __syncthreads();
     }
+    [[maybe_unused]] const float inv_s = (H16 && is_epi) ? s_inv[t] : 1.f;
     if (is_issuer && lane == 0) {
       if constexpr (!OVL) {
         tc_fence_after();
         mma_ss(tmem + tm_d(0), make_desc(sbase + S::dz, TC_TM * 16, 128), make_desc(sbase + S::wo, TC_W * 16, 128),
-               make_idesc(TC_W), 0);
+               idesc_w, 0);
         mma_commit(bar);
       } else if (first) {
         tc_fence_after();
@@ -865,7 +1345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint32_t dst = tmem + tm_d(i + 1);
         const uint32_t wl = l > 0 ? sbase + S::wh + (l - 1) * (TC_W * TC_W * 2) : sbase + S::w0;
         const uint32_t rows16 = (l > 0 ? TC_W : DXN) * 16;
-        const uint32_t idesc = l > 0 ? make_idesc(TC_W) : make_idesc(DXN);
+        const uint32_t idesc = l > 0 ? idesc_w : idesc_x;
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           mbar_wait(bar_chunk + 8 * cc, cphase);
@@ -917,10 +1397,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int col0 = TC_GCOLS * et.grp + 16 * cc;
           const uint32_t mk = mask[cc >> 1] >> (8 * (cc & 1));   // pair j: bits (j, 16 + j)
           uint32_t p[8];
+          [[maybe_unused]] uint32_t pa[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)   // 0xffff per live half: AND on the packed pair instead of two selects
-            p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & pair_mask(mk, j);
-          tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
+          for (int j = 0; j < 8; ++j) {   // 0xffff per live half: AND on the packed pair instead of two selects
+            const float v0 = __uint_as_float(r[cc][2 * j]), v1 = __uint_as_float(r[cc][2 * j + 1]);
+            const uint32_t pm = pair_mask(mk, j);
+            if constexpr (H16) {
+              pa[j] = pack2h(v0, v1) & pm;                     // next MMA's operand: fp16, still carrying s_r
+              p[j] = pack2(v0 * inv_s, v1 * inv_s) & pm;       // what the weight-gradient GEMM reads: bf16, unscaled
+            } else {
+              p[j] = pack2(v0, v1) & pm;
+            }
+          }
+          if constexpr (H16)
+            tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, pa);
+          else
+            tmem_st8(tmem + et.lane_base + TM_A + col0 / 2, p);
           if (valid) {
             zl[act_chunk_index(row, col0 / 8)] = make_uint4(p[0], p[1], p[2], p[3]);
             zl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(p[4], p[5], p[6], p[7]);
@@ -954,6 +1446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               float4 *p4 = reinterpret_cast<float4 *>(d_x + row * dx_cols + col);
               float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
                                      __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              if constexpr (H16) v.x *= inv_s, v.y *= inv_s, v.z *= inv_s, v.w *= inv_s;
               if (ACC) {
                 const float4 o = old_dx[ACC ? q : 0];
                 v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
@@ -1177,34 +1670,47 @@ static int launch_wgrad(const __nv_bfloat16 *dz, const __nv_bfloat16 *in, int64_
 //   N = 64), dWo^T += Hs^T dZ_out (N = 16); db_out is a register sum.  They leave through REDs once per CTA.
 // TMEM: D [0,192)  A [192,288)  S [288,336)  dW0 halves [336,400) [400,464)  dWo^T halves [464,480) [480,496).
 // ------------------------------------------------------------------------------------------------
-struct TmBwdSm {
-  static constexpr int w0 = 0;                         // W0   K-major [6][192][8]
-  static constexpr int wot = w0 + TC_W * 48 * 2;       // Wo^T K-major [2][192][8]
+template <bool X2>
+struct TmBwdSmT {
+  static constexpr int w0 = 0;                         // W0   K-major [6][192][8]; X2: fp16 hi then fp16 lo (scaled)
+  static constexpr int w0_part = TC_W * 48 * 2;
+  static constexpr int wot = w0 + (X2 ? 2 : 1) * w0_part;   // Wo^T K-major [2][192][8]
   static constexpr int w0t = wot + TC_W * 16 * 2;      // W0^T K-major [24][48][8]
   static constexpr int bias = w0t + 48 * TC_W * 2;     // b0 f32 [192]
-  static constexpr int x = bias + TC_W * 4;            // X tile [8][128][8]: 6 feature chunks, ones chunk, zero chunk
+  static constexpr int x = bias + TC_W * 4;            // X tile [8][128][8] bf16: 6 feature chunks, ones chunk, zero chunk
   static constexpr int hs = x + 8 * TC_TM * 16;        // H tile  [24][128][8]
   static constexpr int zs = hs + 24 * TC_TM * 16;      // dZ0 tile [24][128][8]
   static constexpr int dzo = zs + 24 * TC_TM * 16;     // dZ_out tile [2][128][8] (chunk 1 zero)
-  static constexpr int bar = dzo + 2 * TC_TM * 16;     // bar_mma, bar_w, TMEM slot
+  static constexpr int xh = dzo + 2 * TC_TM * 16;      // X2: fp16 hi / lo tiles of the encoding [6][128][8] each
+  static constexpr int xl = xh + (X2 ? 6 * TC_TM * 16 : 0);
+  static constexpr int bar = xl + (X2 ? 6 * TC_TM * 16 : 0);   // bar_mma, bar_w, TMEM slot
   static constexpr int bytes = bar + 32;
 };
+using TmBwdSm = TmBwdSmT<false>;
 constexpr uint32_t TMB_D = 0, TMB_A = 192, TMB_S = 288, TMB_G0 = 336, TMB_GO = 464;
 
+// X2 (precision 1): the recomputation of H uses the forward's arithmetic — fp16 hi / lo tiles of the encoding and of W0
+// (x2 section at byte x2_off of the image), three MMAs per K-step — so that the masks are the forward's; everything
+// downstream (bf16 H tile for dWo, dZ tiles, data gradient) is unchanged.
+template <bool X2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    k_tonemap_bwd_fused(const uint8_t *__restrict__ image, int64_t bwd_off, int64_t bias_off, const float *__restrict__ lin,
+    k_tonemap_bwd_fused(const uint8_t *__restrict__ image, int64_t bwd_off, int64_t bias_off, int64_t x2_off,
+                        const float *__restrict__ lin,
                         const float *__restrict__ y, const float *__restrict__ d_y, const float *__restrict__ d_direct,
                         int64_t m, float *__restrict__ d_lin, float *__restrict__ gW0, float *__restrict__ gb0,
                         float *__restrict__ gWo, float *__restrict__ gbo, int n_out, int act) {
   extern __shared__ __align__(128) uint8_t smem[];
-  using S = TmBwdSm;
+  using S = TmBwdSmT<X2>;
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
   const uint32_t bar = sbase + S::bar, bar_w = bar + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 16);
 
-  stage_bytes(smem + S::w0, image, TC_W * 48 * 2);
+  if constexpr (X2)
+    stage_bytes(smem + S::w0, image + x2_off, 2 * S::w0_part);   // [W0 hi | W0 lo] lead the tone-map x2 section
+  else
+    stage_bytes(smem + S::w0, image, TC_W * 48 * 2);
   stage_bytes(smem + S::wot, image + bwd_off, TC_W * 16 * 2 + 48 * TC_W * 2);   // Wo^T and W0^T are adjacent in the image
   stage_bytes(smem + S::bias, image + bias_off, TC_W * 4);
   for (int i = threadIdx.x; i < TC_TM; i += blockDim.x) {   // constant zero chunks
@@ -1241,7 +1747,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (et.grp < 3) {
         xv = valid ? __ldg(lin + 3 * row + et.grp) : 0.f;
         uint4 lo, hi;
-        tonemap_pe_channel(xv, lo, hi, sn, cs);
+        if constexpr (X2) {
+          uint4 hl, hh, ll, lh;
+          tonemap_pe_channel_x2(xv, hl, hh, ll, lh, sn, cs);
+          if (!valid) hl = hh = ll = lh = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4 *>(smem + S::xh + (2 * et.grp) * (TC_TM * 16) + t * 16) = hl;
+          *reinterpret_cast<uint4 *>(smem + S::xh + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hh;
+          *reinterpret_cast<uint4 *>(smem + S::xl + (2 * et.grp) * (TC_TM * 16) + t * 16) = ll;
+          *reinterpret_cast<uint4 *>(smem + S::xl + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = lh;
+          // bf16 tile for the weight-gradient GEMM (dW0 += dZ0^T X), from the same sines / cosines
+          lo = make_uint4(pack2(xv, sn[0]), pack2(sn[1], sn[2]), pack2(sn[3], sn[4]), pack2(cs[0], cs[1]));
+          hi = make_uint4(pack2(cs[2], cs[3]), pack2(cs[4], 0.f), 0u, 0u);
+        } else {
+          tonemap_pe_channel(xv, lo, hi, sn, cs);
+        }
         if (!valid) lo = hi = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp) * (TC_TM * 16) + t * 16) = lo;
         *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hi;
@@ -1265,10 +1784,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     if (is_issuer && lane == 0) {
       tc_fence_after();
+      if constexpr (X2) {
 #pragma unroll
-      for (int s = 0; s < 3; ++s)
-        mma_ss(tmem + TMB_D, make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
-               make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int term = 0; term < 3; ++term)   // hi.hi, hi.lo, lo.hi
+            mma_ss(tmem + TMB_D, make_desc(sbase + (term == 2 ? S::xl : S::xh) + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
+                   make_desc(sbase + S::w0 + (term == 1 ? S::w0_part : 0) + 2 * s * (TC_W * 16), TC_W * 16, 128),
+                   make_idesc_h(TC_W), (s | term) != 0);
+      } else {
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+          mma_ss(tmem + TMB_D, make_desc(sbase + S::x + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
+                 make_desc(sbase + S::w0 + 2 * s * (TC_W * 16), TC_W * 16, 128), make_idesc(TC_W), s > 0);
+      }
       mma_commit(bar);
     }
     // ---- E1: H = relu(Z0 + b0) -> shared tile + masks ----
@@ -1289,7 +1818,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
           float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
-          add2(z0, z1, bb);
+          if constexpr (X2)
+            fma2(z0, z1, 1.f / TC_WSCALE, bb);
+          else
+            add2(z0, z1, bb);
           p[j] = pack2_relu(z0, z1);
           const uint32_t tt = p[j] + 0x7fff7fffu;
           mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (0x00010001u << (8 * (cc & 1) + j));
@@ -1468,16 +2000,41 @@ static int launch_fwd(const esr_mlp_desc_t *d, const void *image, const void *x,
   return ESR_OK;
 }
 
-template <int K0, int NH, int DXN, int NO, bool ACC, bool OVL = false>
+template <int K0, int NH, int NO>
+static int launch_fwd_x2(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const void *x, int64_t rb, int64_t re,
+                         int64_t mt, float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
+  auto kern = k_mlp_fwd_x2<K0, NH, NO>;
+  using S = X2Sm<K0, NH>;
+  if (T.x2_rank_bytes() != S::rank_bytes) {
+    set_error("x2 forward: image layout mismatch");
+    return ESR_ERR_BAD_ARG;
+  }
+  if (int e = set_smem_tc(kern, S::bytes)) return e;
+  const int64_t pair_tiles = (re - rb + 2 * TC_TM - 1) / (2 * TC_TM);
+  const int64_t pairs = max((int64_t)1, min((int64_t)(num_sms() / 2), pair_tiles));
+  // the residual tile of the feature rows follows the bf16 tile (esr_encode_*_fwd with out_is_bf16 = 2)
+  const __half *x_lo = reinterpret_cast<const __half *>(reinterpret_cast<const __nv_bfloat16 *>(x) + act_rows_padded(mt) * K0);
+  ESR_STAGE("k_mlp_fwd_x2_radiance", st);
+  kern<<<(unsigned)(2 * pairs), TC_THREADS, S::bytes, st>>>((const uint8_t *)image + T.x2_off(), (const __nv_bfloat16 *)x, x_lo,
+                                                           rb, re, mt, y, (__nv_bfloat16 *)hidden, save_begin, d->n_out, d->act);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+template <int K0, int NH, int DXN, int NO, bool ACC, bool OVL = false, bool H16 = false>
 static int launch_dgrad_acc(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const float *y, const float *d_y,
                         int64_t rb, int64_t re, int64_t mt, const void *hidden, void *d_z, float *d_z_out, float *d_x,
                         int dx_cols, int accumulate, cudaStream_t st) {
-  if constexpr (!OVL && K0 == 96)
+  if constexpr (!OVL && !H16 && K0 == 96) {
+    if (T.bwd_h16())   // precision 1: the image's transposed matrices are fp16 -> the fp16 chain
+      return launch_dgrad_acc<K0, NH, DXN, NO, ACC, false, true>(d, T, image, y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x,
+                                                                 dx_cols, accumulate, st);
     if (tile_overlap())
       return launch_dgrad_acc<K0, NH, DXN, NO, ACC, true>(d, T, image, y, d_y, rb, re, mt, hidden, d_z, d_z_out, d_x, dx_cols,
                                                           accumulate, st);
-  auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC, OVL>;
-  constexpr int bytes = BwdSm<K0, NH, DXN>::bytes;
+  }
+  auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC, OVL, H16>;
+  constexpr int bytes = BwdSm<K0, NH, DXN>::bytes + (H16 ? TC_TM * 4 : 0);
   if (int e = set_smem_tc(kern, bytes)) return e;
   ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_tc_radiance" : "k_mlp_dgrad_tc_tonemap", st);
   kern<<<tc_grid(re - rb), TC_THREADS, bytes, st>>>((const uint8_t *)image + T.bwd_off(), y, d_y, rb, re, mt,
@@ -1520,11 +2077,25 @@ int tc_pack(const esr_mlp_desc_t *d, const float *flat_params, void *tc_image, c
   ESR_STAGE("k_tc_pack", st);
   k_tc_pack<<<cdiv(n, 256), 256, 0, st>>>(T, L, flat_params, (uint8_t *)tc_image);
   ESR_LAUNCH_OK();
+  if (T.x2) {
+    ESR_STAGE("k_tc_pack", st);
+    k_tc_pack_x2<<<cdiv(n, 256), 256, 0, st>>>(T, L, flat_params, (uint8_t *)tc_image);
+    ESR_LAUNCH_OK();
+  }
   return ESR_OK;
 }
 
 int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t row_begin, int64_t row_end,
            int64_t m_total, float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
+  if (d->precision == 1) {
+    const TcLayout T = tc_layout(d);
+    if (d->k0 == 96 && d->n_hidden == 3 && d->n_out <= 3)
+      return launch_fwd_x2<96, 3, 3>(d, T, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
+    if (d->k0 == 96 && d->n_hidden == 3)
+      return launch_fwd_x2<96, 3, 8>(d, T, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
+    set_error("tc_fwd: the x2 forward chain is instantiated for the 96 -> 192 x 3 nets (the tone-map net: esr_tonemap_mlp_*)");
+    return ESR_ERR_BAD_ARG;
+  }
   if (d->k0 == 96 && d->n_hidden == 3 && d->n_out <= 3)
     return launch_fwd<96, 3, 3>(d, tc_image, x, row_begin, row_end, m_total, y, hidden, save_begin, st);
   if (d->k0 == 96 && d->n_hidden == 3)
@@ -1538,6 +2109,15 @@ int tc_fwd(const esr_mlp_desc_t *d, const void *tc_image, const void *x, int64_t
 int tc_tonemap_fwd(const esr_mlp_desc_t *d, const void *tc_image, const float *lin, int64_t m, float *y, cudaStream_t st) {
   if (getenv("ESR_TONEMAP_FWD_GENERIC"))   // the one-tile-at-a-time generic chain (kept for A/B measurements)
     return launch_fwd<48, 1, 3, 1>(d, tc_image, lin, 0, m, m, y, nullptr, 0, st);
+  if (d->precision == 1) {
+    auto kern = k_tonemap_fwd2<3, true>;
+    using S2 = Tm2SmT<true>;
+    if (int e = set_smem_tc(kern, S2::bytes)) return e;
+    ESR_STAGE("k_tonemap_fwd_fused", st);
+    kern<<<tc_grid(m), TC_THREADS, S2::bytes, st>>>((const uint8_t *)tc_image + tc_layout(d).x2_off(), lin, m, y, d->n_out, d->act);
+    ESR_LAUNCH_OK();
+    return ESR_OK;
+  }
   auto kern = k_tonemap_fwd2<3>;
   if (int e = set_smem_tc(kern, Tm2Sm::bytes)) return e;
   ESR_STAGE("k_tonemap_fwd_fused", st);
@@ -1550,11 +2130,21 @@ int tc_tonemap_bwd(const esr_mlp_desc_t *d, const void *tc_image, const float *l
                    const float *d_direct, int64_t m, float *d_lin, float *grad_flat, cudaStream_t st) {
   const TcLayout T = tc_layout(d);
   const MlpLayout L = layout_of(d);
-  auto kern = k_tonemap_bwd_fused;
+  if (d->precision == 1) {
+    auto kern = k_tonemap_bwd_fused<true>;
+    if (int e = set_smem_tc(kern, TmBwdSmT<true>::bytes)) return e;
+    ESR_STAGE("k_tonemap_bwd_fused", st);
+    kern<<<tc_grid(m), TC_THREADS, TmBwdSmT<true>::bytes, st>>>(
+        (const uint8_t *)tc_image, T.bwd_off(), T.f_bias(), T.x2_off(), lin, y, d_y, d_direct, m, d_lin, grad_flat + L.flat_w(0),
+        grad_flat + L.flat_b(0), grad_flat + L.flat_w(1), grad_flat + L.flat_b(1), d->n_out, d->act);
+    ESR_LAUNCH_OK();
+    return ESR_OK;
+  }
+  auto kern = k_tonemap_bwd_fused<false>;
   if (int e = set_smem_tc(kern, TmBwdSm::bytes)) return e;
   ESR_STAGE("k_tonemap_bwd_fused", st);
-  kern<<<tc_grid(m), TC_THREADS, TmBwdSm::bytes, st>>>((const uint8_t *)tc_image, T.bwd_off(), T.f_bias(), lin, y, d_y, d_direct,
-                                                       m, d_lin, grad_flat + L.flat_w(0), grad_flat + L.flat_b(0),
+  kern<<<tc_grid(m), TC_THREADS, TmBwdSm::bytes, st>>>((const uint8_t *)tc_image, T.bwd_off(), T.f_bias(), 0, lin, y, d_y,
+                                                       d_direct, m, d_lin, grad_flat + L.flat_w(0), grad_flat + L.flat_b(0),
                                                        grad_flat + L.flat_w(1), grad_flat + L.flat_b(1), d->n_out, d->act);
   ESR_LAUNCH_OK();
   return ESR_OK;

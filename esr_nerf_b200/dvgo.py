@@ -46,10 +46,13 @@ class _DvgoRender(torch.autograd.Function):
         g_off = torch.zeros(1, 3, *density.shape[2:], dtype=torch.float32, device=density.device)
         g_emo = torch.zeros_like(g_off)
         d_alpha, d_raw = torch.empty_like(alpha), torch.empty_like(raw_rgb)
+        # named contiguous copies: a temporary is released as soon as ptr() returns and its block could be handed to the
+        # next .contiguous() before the kernel has been queued
+        g_cum, g_w, g_raw, g_rgb = g_cum.contiguous(), g_w.contiguous(), g_raw.contiguous(), g_rgb.contiguous()
         check(_lib.lib().esr_dvgo_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(jitter), ptr(em_modes),
                                       ptr(density), n, S, ptr(alpha), ptr(raw_off), ptr(raw_emo), ptr(cum), ptr(raw_rgb),
-                                      ptr(g_cum.contiguous()), ptr(g_w.contiguous()), ptr(g_raw.contiguous()),
-                                      ptr(g_rgb.contiguous()), ptr(d_alpha), ptr(d_raw), ptr(g_den), ptr(g_off),
+                                      ptr(g_cum), ptr(g_w), ptr(g_raw),
+                                      ptr(g_rgb), ptr(d_alpha), ptr(d_raw), ptr(g_den), ptr(g_off),
                                       ptr(g_emo), stream_ptr()))
         return g_den, g_off, g_emo, None, None, None, None, None, None
 
@@ -157,9 +160,9 @@ class DVGO(nn.Module):
         cum, weights = torch.empty(n, S + 1, **f), torch.empty(n, S, **f)
         off, emo, on, depth = torch.empty(n, 3, **f), torch.empty(n, 3, **f), torch.empty(n, 3, **f), torch.empty(n, **f)
         sc = self._scene()
+        den_c, off_c, emo_c = (t.detach().contiguous() for t in (self.density, self.off_color, self.emo_color))
         with torch.cuda.device(dev):
-            check(L.esr_dvgo_eval(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(self.density.detach().contiguous()),
-                                  ptr(self.off_color.detach().contiguous()), ptr(self.emo_color.detach().contiguous()), n,
+            check(L.esr_dvgo_eval(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(den_c), ptr(off_c), ptr(emo_c), n,
                                   S, ptr(alpha), ptr(raw_off), ptr(raw_emo), ptr(cum), ptr(weights), ptr(off), ptr(emo),
                                   ptr(on), ptr(depth), stream_ptr()))
         disp = 1 / (depth + cum[..., -1] * self.far)

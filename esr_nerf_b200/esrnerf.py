@@ -131,7 +131,7 @@ class ESRNeRF(VoxurfF):
         grids = (self.sdf.grid if sdf_grid is None else sdf_grid, self.off_color.grid,
                  self.emo_color.grid if emo_grid is None else emo_grid, self.brdf.grid if use[3] else None)
         fl = [f if u else None for f, u in zip(flats, use)]
-        return fused.ShadePBR.apply(*grids, *fl, sc, pos, use)
+        return fused.ShadePBR.apply(*grids, *fl, sc, pos, use, self._precision())
 
     # ------------------------------------------------------------------------------------------
     def _secondary(self, flats, rays_o2, d_flat, use=(True, True, False, False)):
@@ -211,7 +211,8 @@ class ESRNeRF(VoxurfF):
             pos = fused.SamplePos(m3, viewdirs, s.h_sdf, rays_o, rays_d, s.h_ray, s.h_step)
             lin_off, lin_emo, emit, brdf = self._shade(sc, pos, (True, True, True, True), flats)
             # esrnerf.py:751-757: emo on the emission-on rays + off on all of them, no stop-gradient
-            rgb, lin = fused.CombineTonemap.apply(lin_off, lin_emo, flat_tone, s.h_ray, em_modes, False, True)
+            rgb, lin = fused.CombineTonemap.apply(lin_off, lin_emo, flat_tone, s.h_ray, em_modes, False, True,
+                                                  self._precision())
             rgb_m, lin_m = fused.Composite.apply(h_w, rgb, lin, s)
             emit_m, _ = fused.Composite.apply(h_w, emit, None, s)
             if self.keep_streams:

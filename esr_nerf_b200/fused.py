@@ -272,15 +272,22 @@ class AlphaScan(torch.autograd.Function):
         if s.m3:
             g_w_m1.index_copy_(0, s.h_m1.long(), g_hw.contiguous())
         tmp_p, tmp_n = _f32(s.m1, dev=dev), _f32(s.m1, dev=dev)
+        g_last = g_last.contiguous()
         check(_lib.lib().esr_alpha_scan_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.ray_order), s.n_rays,
                                             ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(s.s_alpha),
-                                            ptr(s.s_T), ptr(last), ptr(g_w_m1), ptr(g_last.contiguous()), ptr(tmp_p),
+                                            ptr(s.s_T), ptr(last), ptr(g_w_m1), ptr(g_last), ptr(tmp_p),
                                             ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
         return ret_sdf, None, None, None, None, None
 
 
 def _desc(d: dict) -> MlpDesc:
-    return MlpDesc(d["k0"], d["width"], d["n_hidden"], d["n_out"], d["act"])
+    return MlpDesc(d["k0"], d["width"], d["n_hidden"], d["n_out"], d["act"], int(d.get("precision", 0)))
+
+
+def with_precision(desc: dict, precision: int) -> dict:
+    """desc with esr_mlp_desc_t::precision set: 0 = bf16 forward operands, 1 = "x2" (fp16 hi + lo pairs, three MMAs per
+    product: fp32-class pre-activations / ReLU masks — the mode whose parameter gradients meet the 1e-2 tolerance)"""
+    return desc if int(desc.get("precision", 0)) == int(precision) else {**desc, "precision": int(precision)}
 
 
 def mlp_pack(desc: dict, flat: torch.Tensor) -> torch.Tensor:
@@ -288,21 +295,25 @@ def mlp_pack(desc: dict, flat: torch.Tensor) -> torch.Tensor:
     d = _desc(desc)
     assert flat.numel() == L.esr_mlp_param_count(ctypes.byref(d)), (flat.numel(), L.esr_mlp_param_count(ctypes.byref(d)))
     image = torch.empty(L.esr_mlp_image_bytes(ctypes.byref(d)), dtype=torch.uint8, device=flat.device)
-    check(L.esr_mlp_pack(ctypes.byref(d), ptr(flat.detach().contiguous()), ptr(image), stream_ptr()))
+    flat_c = flat.detach().contiguous()
+    check(L.esr_mlp_pack(ctypes.byref(d), ptr(flat_c), ptr(image), stream_ptr()))
     return image
 
 
 def encode_features(sc: Scene, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s: Streams, bf16: bool,
-                    save_fd: bool = False):
+                    save_fd: bool = False, residual: bool = False):
     """feature rows of the shaded stream; save_fd=True also returns the f32 [m3,16] finite-difference gradients the
-    backward then reuses instead of re-gathering the SDF taps"""
+    backward then reuses instead of re-gathering the SDF taps.  residual=True (bf16 only): the buffer holds a second
+    tile set behind the first — the fp16 residuals of the bf16 rounding — for the x2 forward chain."""
     # bf16 rows are written in the library's tiled layout (padded to whole 128-row tiles); f32 rows are row-major
     rows = _lib.lib().esr_mlp_act_rows(s.m3) if bf16 else s.m3
-    x = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16 if bf16 else torch.float32, device=rays_o.device)
+    x = torch.empty(rows * (2 if (bf16 and residual) else 1), FEAT_DIM, dtype=torch.bfloat16 if bf16 else torch.float32,
+                    device=rays_o.device)
     fd = torch.empty(s.m3, 16, dtype=torch.float32, device=rays_o.device) if save_fd else None
     check(_lib.lib().esr_encode_pbr_fwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(viewdirs), ptr(sdf_grid),
                                         ptr(off_grid), ptr(emo_grid), None, 6, None, ptr(s.h_ray), ptr(s.h_step),
-                                        ptr(s.h_sdf), s.m3, ptr(x), None, int(bf16), ptr(fd), stream_ptr()))
+                                        ptr(s.h_sdf), s.m3, ptr(x), None, (2 if residual else 1) if bf16 else 0, ptr(fd),
+                                        stream_ptr()))
     return (x, fd) if save_fd else x
 
 
@@ -330,24 +341,27 @@ def mlp_infer(desc, flat, x, rb, re, m_total):
     return y
 
 
-def _tonemap_fwd(lin, img):
+def _tonemap_fwd(lin, img, desc=None):
     """rgb = sigmoid(tonemapper(PE(lin))) by the fused kernel: the encoding never leaves the SM"""
     m = lin.shape[0]
     rgb = torch.empty(m, 3, dtype=torch.float32, device=lin.device)
-    d = _desc(TONEMAP_DESC)
+    d = _desc(desc or TONEMAP_DESC)
     check(_lib.lib().esr_tonemap_mlp_fwd(ctypes.byref(d), ptr(img), ptr(lin), m, ptr(rgb), stream_ptr()))
     return rgb
 
 
-def _tonemap_bwd(lin, img, rgb, d_rgb, d_lin_direct):
+def _tonemap_bwd(lin, img, rgb, d_rgb, d_lin_direct, desc=None):
     """(d_lin, flat weight gradient) by the fused backward kernel (hidden activations recomputed on the SM)"""
     L = _lib.lib()
     m = lin.shape[0]
-    d = _desc(TONEMAP_DESC)
+    d = _desc(desc or TONEMAP_DESC)
     d_lin = torch.empty_like(lin)
     g_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=lin.device)
-    check(L.esr_tonemap_mlp_bwd(ctypes.byref(d), ptr(img), ptr(lin), ptr(rgb), ptr(d_rgb.contiguous()),
-                                ptr(d_lin_direct.contiguous()) if d_lin_direct is not None else None, m, ptr(d_lin),
+    # the contiguous copies are bound to names: a temporary would be released (and its block possibly re-used by the
+    # next .contiguous()) before the kernel that reads it has been queued
+    d_rgb_c = d_rgb.contiguous()
+    d_dir_c = d_lin_direct.contiguous() if d_lin_direct is not None else None
+    check(L.esr_tonemap_mlp_bwd(ctypes.byref(d), ptr(img), ptr(lin), ptr(rgb), ptr(d_rgb_c), ptr(d_dir_c), m, ptr(d_lin),
                                 ptr(g_flat), stream_ptr()))
     return d_lin, g_flat
 
@@ -410,6 +424,7 @@ def _mlp_backward(desc, image, x, y, d_y, rb, re, m_total, hidden, d_x, dx_cols,
     L = _lib.lib()
     d = _desc(desc)
     dev = x.device
+    d_y = d_y.contiguous()   # bound to a name for the life of the call (see _tonemap_bwd)
     if scratch is None:
         scratch = torch.empty(L.esr_mlp_dz_bytes(ctypes.byref(d), m_total), dtype=torch.uint8, device=dev)
     d_z_out = None
@@ -429,15 +444,18 @@ class Shade(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sdf_grid, off_grid, emo_grid, flat_off, flat_emo, sc, rays_o, rays_d, viewdirs, streams,
-                off_grad_rows, emo_grad_rows):
+                off_grad_rows, emo_grad_rows, precision=0):
         _check_cl(off_grid, "off_color.grid")
         _check_cl(emo_grid, "emo_color.grid")
         s: Streams = streams
         train = any(ctx.needs_input_grad[:5])
-        x, fd = encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s, bf16=True, save_fd=True)
-        img_off, img_emo = mlp_pack(RADIANCE_DESC, flat_off), mlp_pack(RADIANCE_DESC, flat_emo)
-        lin_off, hid_off = _mlp_forward(RADIANCE_DESC, img_off, x, 0, s.m3, s.m3, train, save_begin=off_grad_rows[0])
-        lin_emo, hid_emo = _mlp_forward(RADIANCE_DESC, img_emo, x, 0, s.m3_on, s.m3, train)
+        desc = with_precision(RADIANCE_DESC, precision)
+        x, fd = encode_features(sc, rays_o, rays_d, viewdirs, sdf_grid, off_grid, emo_grid, s, bf16=True, save_fd=True,
+                                residual=bool(precision))
+        img_off, img_emo = mlp_pack(desc, flat_off), mlp_pack(desc, flat_emo)
+        lin_off, hid_off = _mlp_forward(desc, img_off, x, 0, s.m3, s.m3, train, save_begin=off_grad_rows[0])
+        lin_emo, hid_emo = _mlp_forward(desc, img_emo, x, 0, s.m3_on, s.m3, train)
+        ctx.desc = desc
         ctx.sc, ctx.streams, ctx.grid_params = sc, s, (sdf_grid, off_grid, emo_grid)
         ctx.rows = (off_grad_rows, emo_grad_rows)
         ctx.hidden = (hid_off, hid_emo)
@@ -456,9 +474,9 @@ class Shade(torch.autograd.Function):
         disjoint = (eb, ee, oe) == (0, ob, s.m3)
         d_x = (torch.empty if disjoint else torch.zeros)(s.m3, FEAT_GRAD_DIM, dtype=torch.float32, device=x.device)
         acc = 0 if disjoint else 1
-        g_off_flat, scratch = _mlp_backward(RADIANCE_DESC, img_off, x, lin_off, d_off.contiguous(), ob, oe, s.m3,
+        g_off_flat, scratch = _mlp_backward(ctx.desc, img_off, x, lin_off, d_off.contiguous(), ob, oe, s.m3,
                                             hid_off, d_x, FEAT_GRAD_DIM, acc)
-        g_emo_flat, _ = _mlp_backward(RADIANCE_DESC, img_emo, x, lin_emo, d_emo.contiguous(), eb, ee, s.m3, hid_emo,
+        g_emo_flat, _ = _mlp_backward(ctx.desc, img_emo, x, lin_emo, d_emo.contiguous(), eb, ee, s.m3, hid_emo,
                                       d_x, FEAT_GRAD_DIM, acc, scratch)
         ctx.hidden = None
         g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x,
@@ -466,17 +484,18 @@ class Shade(torch.autograd.Function):
         if COLOR_GRADS_READY_HOOK is not None and g_offc is None and g_emoc is None:   # both went to the gradient sink
             p_off, p_emo = ctx.grid_params[1], ctx.grid_params[2]
             COLOR_GRADS_READY_HOOK({p_off: GRAD_SINK.get(p_off), p_emo: GRAD_SINK.get(p_emo)})
-        return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None
+        return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None, None
 
 
 class Tonemap(torch.autograd.Function):
     """rgb = sigmoid(tonemapper([lin, sin(lin 2^f), cos(lin 2^f)]))  (voxurff.py:783-788): fused tone-map kernels."""
 
     @staticmethod
-    def forward(ctx, lin, flat_tone):
+    def forward(ctx, lin, flat_tone, precision=0):
         lin = lin.contiguous()
-        img = mlp_pack(TONEMAP_DESC, flat_tone)
-        rgb = _tonemap_fwd(lin, img)
+        ctx.desc = with_precision(TONEMAP_DESC, precision)
+        img = mlp_pack(ctx.desc, flat_tone)
+        rgb = _tonemap_fwd(lin, img, ctx.desc)
         ctx.save_for_backward(lin, img, rgb)
         return rgb
 
@@ -484,7 +503,7 @@ class Tonemap(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_rgb):
         lin, img, rgb = ctx.saved_tensors
-        return _tonemap_bwd(lin, img, rgb, d_rgb, None)
+        return (*_tonemap_bwd(lin, img, rgb, d_rgb, None, ctx.desc), None)
 
 
 class CombineTonemap(torch.autograd.Function):
@@ -493,16 +512,17 @@ class CombineTonemap(torch.autograd.Function):
     One encode kernel + the tensor-core MLP; replaces torch.where / add / copies around `Tonemap`."""
 
     @staticmethod
-    def forward(ctx, lin_off, lin_emo, flat_tone, h_ray, em_modes, ordered, off_sees_on=False):
+    def forward(ctx, lin_off, lin_emo, flat_tone, h_ray, em_modes, ordered, off_sees_on=False, precision=0):
         L = _lib.lib()
+        ctx.desc = with_precision(TONEMAP_DESC, precision)
         m = lin_off.shape[0]
         lin_off, lin_emo = lin_off.contiguous(), lin_emo.contiguous()
         lin = torch.empty_like(lin_off)
         # combine only (tfeat = NULL): the fused tone-map kernel encodes lin itself
         check(L.esr_tonemap_encode_fwd(ptr(lin_off), ptr(lin_emo), ptr(h_ray), ptr(em_modes), m, ptr(lin), None, 1,
                                        stream_ptr()))
-        img = mlp_pack(TONEMAP_DESC, flat_tone)
-        rgb = _tonemap_fwd(lin, img)
+        img = mlp_pack(ctx.desc, flat_tone)
+        rgb = _tonemap_fwd(lin, img, ctx.desc)
         # off_sees_on: the off net receives the cotangent of emission-on rows too (ESRNeRF adds the two radiances
         # without a stop-gradient, esrnerf.py:751-757; VoxurfF detaches, voxurff.py:243-254)
         ctx.ordered, ctx.off_sees_on = ordered, off_sees_on
@@ -513,15 +533,15 @@ class CombineTonemap(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, d_rgb, d_lin_direct):
         lin, img, rgb, h_ray, em_modes = ctx.saved_tensors
-        d_lin, g_flat = _tonemap_bwd(lin, img, rgb, d_rgb, d_lin_direct)
+        d_lin, g_flat = _tonemap_bwd(lin, img, rgb, d_rgb, d_lin_direct, ctx.desc)
         if ctx.ordered:
             # emission-on rows are a prefix and each net back-propagates through its own row range only (Shade.backward):
             # both can read the same cotangent
-            return d_lin, d_lin, g_flat, None, None, None, None
+            return d_lin, d_lin, g_flat, None, None, None, None, None
         on = (em_modes[h_ray.long()] == 1)[:, None]
         zero = torch.zeros_like(d_lin)
         d_off = d_lin if ctx.off_sees_on else torch.where(on, zero, d_lin)
-        return d_off, torch.where(on, d_lin, zero), g_flat, None, None, None, None
+        return d_off, torch.where(on, d_lin, zero), g_flat, None, None, None, None, None
 
 
 class Composite(torch.autograd.Function):
@@ -549,9 +569,10 @@ class Composite(torch.autograd.Function):
         s: Streams = ctx.streams
         d_a, g_w = torch.empty_like(a), torch.empty_like(h_w)
         d_b = torch.empty_like(b) if b is not None else None
-        check(_lib.lib().esr_composite_bwd(ptr(s.h_ray), None, ptr(h_w), ptr(a), ptr(b), ptr(c_a.contiguous()),
-                                           ptr(c_b.contiguous()) if b is not None else None, s.m3, ptr(d_a), ptr(d_b),
-                                           ptr(g_w), stream_ptr()))
+        c_a = c_a.contiguous()          # named: the copies must outlive the launch (a temporary's block could be handed
+        c_b = c_b.contiguous() if b is not None else None   # to the next .contiguous() before the kernel is queued)
+        check(_lib.lib().esr_composite_bwd(ptr(s.h_ray), None, ptr(h_w), ptr(a), ptr(b), ptr(c_a), ptr(c_b), s.m3,
+                                           ptr(d_a), ptr(d_b), ptr(g_w), stream_ptr()))
         return g_w, d_a, d_b, None
 
 
@@ -632,8 +653,9 @@ class EncodeCoarse(torch.autograd.Function):
         rays_o, rays_d, grad_vol, off_grid, emo_grid = ctx.saved_tensors
         s: Streams = ctx.streams
         g_vol, g_off, g_emo = torch.zeros_like(grad_vol), torch.zeros_like(off_grid), torch.zeros_like(emo_grid)
+        d_x = d_x.contiguous()
         check(_lib.lib().esr_encode_coarse_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(grad_vol),
-                                               ptr(s.h_ray), ptr(s.h_step), s.m3, ptr(d_x.contiguous()), ptr(g_vol),
+                                               ptr(s.h_ray), ptr(s.h_step), s.m3, ptr(d_x), ptr(g_vol),
                                                ptr(g_off), ptr(g_emo), stream_ptr()))
         return g_vol, g_off, g_emo, None, None, None, None, None
 
@@ -695,8 +717,9 @@ class SdfExpGrad(torch.autograd.Function):
         if pts.shape[0] == 0:
             return None, None, None
         g, ret = _grad_target(ctx.grid_param, sdf_grid)
+        g_grad = g_grad.contiguous()
         check(_lib.lib().esr_sdf_expgrad_bwd(ctypes.byref(ctx.sc), ptr(pts), pts.shape[0], None,
-                                             ptr(g_grad.contiguous()), ptr(g), stream_ptr()))
+                                             ptr(g_grad), ptr(g), stream_ptr()))
         return ret, None, None
 
 
@@ -724,7 +747,8 @@ class ShadePBR(torch.autograd.Function):
     kernels with zero-padded weights (view columns and hidden units 128..191 have zero weights)."""
 
     @staticmethod
-    def forward(ctx, sdf_grid, off_grid, emo_grid, brdf_grid, flat_off, flat_emo, flat_emit, flat_brdf, sc, pos, use):
+    def forward(ctx, sdf_grid, off_grid, emo_grid, brdf_grid, flat_off, flat_emo, flat_emit, flat_brdf, sc, pos, use,
+                precision=0):
         _check_cl(off_grid, "off_color.grid")
         _check_cl(emo_grid, "emo_color.grid")
         p: SamplePos = pos
@@ -732,7 +756,8 @@ class ShadePBR(torch.autograd.Function):
         dev = sdf_grid.device
         m = p.m
         train = any(ctx.needs_input_grad[:8])
-        rows = L.esr_mlp_act_rows(m)
+        precision = int(precision) if train else 0   # the x2 forward exists for the backward's sake (exact ReLU masks)
+        rows = L.esr_mlp_act_rows(m) * (2 if precision else 1)   # x2: the fp16 residual tiles follow the bf16 tiles
         x = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16, device=dev)
         x2 = None
         if use[3]:
@@ -741,10 +766,11 @@ class ShadePBR(torch.autograd.Function):
         fd = torch.empty(m, 16, dtype=torch.float32, device=dev) if train else None
         check(L.esr_encode_pbr_fwd(ctypes.byref(sc), ptr(p.rays_o), ptr(p.rays_d), ptr(p.viewdirs), ptr(sdf_grid),
                                    ptr(off_grid), ptr(emo_grid), ptr(brdf_grid) if use[3] else None, 6, ptr(p.pts),
-                                   ptr(p.h_ray), ptr(p.h_step), ptr(p.h_sdf), m, ptr(x), ptr(x2), 1, ptr(fd),
-                                   stream_ptr()))
+                                   ptr(p.h_ray), ptr(p.h_step), ptr(p.h_sdf), m, ptr(x), ptr(x2), 2 if precision else 1,
+                                   ptr(fd), stream_ptr()))
         ctx.fd = fd
-        descs = (RADIANCE_DESC, RADIANCE_DESC, EMIT_DESC, BRDF_DESC)
+        descs = tuple(with_precision(d, precision) for d in (RADIANCE_DESC, RADIANCE_DESC, EMIT_DESC, BRDF_DESC))
+        ctx.descs = descs
         flats = (flat_off, flat_emo, flat_emit, flat_brdf)
         STATS["encode_rows"] += m
         STATS["mlp_fwd_rows"] += m * sum(use)
@@ -779,7 +805,7 @@ class ShadePBR(torch.autograd.Function):
         p: SamplePos = ctx.pos
         use, m = ctx.use, p.m
         dev = x.device
-        descs = (RADIANCE_DESC, RADIANCE_DESC, EMIT_DESC, BRDF_DESC)
+        descs = ctx.descs
         d_ys = (d_off, d_emo, d_emit, d_brdf)
         imgs = [img_list.pop(0) if has else None for has in ctx.n_saved]
         d_x = torch.zeros(m, FEAT_GRAD_DIM, dtype=torch.float32, device=dev)
@@ -795,7 +821,7 @@ class ShadePBR(torch.autograd.Function):
                 d_x[:, :6] = 0
         ctx.hids = None
         if m == 0:
-            return (None, None, None, None, *g_flat, None, None, None)
+            return (None, None, None, None, *g_flat, None, None, None, None)
         needs = ctx.needs_input_grad
         gp = ctx.grid_params
         g_sdf, r_sdf = _grad_target(gp[0], sdf_grid) if needs[0] else (torch.zeros_like(sdf_grid), None)
@@ -808,7 +834,7 @@ class ShadePBR(torch.autograd.Function):
                                             ptr(p.pts), ptr(p.h_ray), ptr(p.h_step), m, ptr(d_x), ptr(d_brdf_c),
                                             ptr(g_sdf), ptr(g_off), ptr(g_emo), ptr(g_brdf), ptr(ctx.fd), stream_ptr()))
         ctx.fd = None
-        return (r_sdf, r_off, r_emo, r_brdf, *g_flat, None, None, None)
+        return (r_sdf, r_off, r_emo, r_brdf, *g_flat, None, None, None, None)
 
 
 class LtsAccumulate(torch.autograd.Function):
@@ -842,9 +868,10 @@ class LtsAccumulate(torch.autograd.Function):
         g_rad_emo = torch.empty_like(rad_emo)
         g_rad_off = torch.empty_like(rad_off) if rad_off is not None else None
         if P:
+            g_off_hat = g_off_hat.contiguous() if rad_off is not None else None   # named: must outlive the launch
+            g_reflect = g_reflect.contiguous()
             check(_lib.lib().esr_lts_accumulate_bwd(ptr(normal), ptr(base), ptr(rough), ptr(metal), ptr(wo_a), ptr(wo_b),
                                                     ptr(dirs), ptr(rad_off), ptr(rad_emo), P, ctx.n_dirs,
-                                                    ptr(g_off_hat.contiguous()) if rad_off is not None else None,
-                                                    ptr(g_reflect.contiguous()), ptr(g_base), ptr(g_rough), ptr(g_metal),
+                                                    ptr(g_off_hat), ptr(g_reflect), ptr(g_base), ptr(g_rough), ptr(g_metal),
                                                     ptr(g_rad_off), ptr(g_rad_emo), stream_ptr()))
         return g_base, g_rough, g_metal, g_rad_off, g_rad_emo, None, None, None, None, None

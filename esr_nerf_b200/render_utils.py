@@ -48,9 +48,10 @@ def sample_pts_on_rays(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist):
     t_max = torch.empty(n, dtype=torch.float32, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
+        scratch = _scratch(n, dev)   # named: must stay allocated until the launch has been queued
         check(L.esr_sample_pts_on_rays_count(ptr(rays_o), ptr(rays_d), mn, mx, float(near), float(far), stepdist, n,
                                              ptr(N_steps), ptr(N_cum), ptr(t_min), ptr(t_max), ptr(total),
-                                             ptr(_scratch(n, dev)), stream_ptr()))
+                                             ptr(scratch), stream_ptr()))
         m = int(total.item())  # the reference syncs here as well (kernel.cu:212)
         ray_pts = torch.empty(m, 3, dtype=torch.float32, device=dev)
         mask = torch.empty(m, dtype=torch.bool, device=dev)

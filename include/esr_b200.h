@@ -215,6 +215,10 @@ int esr_neus_alpha_bwd(const esr_scene_t *sc, const float *rays_o, const float *
  *              1 -> __nv_bfloat16 rows in the library's TILED MLP-input layout (per 128-row tile:
  *                   [12 feature chunks][128 rows][8]); `feat` must hold esr_mlp_act_rows(m3) rows.  The same holds
  *                   for esr_tonemap_encode_fwd's tfeat (48 columns = 6 chunks).
+ *              2 -> (esr_encode_fwd / esr_encode_pbr_fwd) as 1, followed in the same buffer — which must hold
+ *                   2 * esr_mlp_act_rows(m3) rows — by a second tile set of __half: the residual v - bf16(v) of every
+ *                   column.  This is the layer-0 operand of the x2 forward chain (esr_mlp_desc_t::precision = 1):
+ *                   esr_mlp_fwd then expects `x` to be such a buffer; esr_mlp_bwd reads the bf16 tiles only.
  */
 #define ESR_FEAT_DIM 96
 #define ESR_FEAT_GRAD_DIM 56 /* columns [0,49) carry gradient; padded to 56 */
@@ -352,6 +356,11 @@ typedef struct esr_mlp_desc {
   int32_t n_hidden;/* hidden layers: 3 (radiance nets), 1 (tonemapper) */
   int32_t n_out;   /* real outputs (<= 8: 3 radiance / tone-map / emission, 5 BRDF; padded to 8 rows in the flat copy) */
   int32_t act;     /* 1 softplus, 2 sigmoid */
+  int32_t precision; /* forward arithmetic: 0 = bf16 operands (fast, 1e-2 class on outputs only);
+                        1 = "x2": every forward operand (inputs, weights, hidden activations) carried as an fp16
+                        hi + lo pair, three tcgen05 MMAs per product, fp32 accumulation — pre-activations (and with
+                        them the ReLU masks the backward uses) are fp32-class, which is what brings every parameter
+                        gradient within 1e-2 of the reference's fp32 nets.  The backward kernels are the same. */
 } esr_mlp_desc_t;
 
 int64_t esr_mlp_param_count(const esr_mlp_desc_t *d); /* f32 elements of the flat master copy */
@@ -375,7 +384,8 @@ int64_t esr_mlp_dz_bytes(const esr_mlp_desc_t *d, int64_t m_total);
 int esr_mlp_pack(const esr_mlp_desc_t *d, const float *flat_params, void *image, esr_stream_t stream);
 /*
  * Forward over rows [row_begin,row_end) of x (bf16, k0 columns, TILED layout as written by esr_encode_fwd /
- * esr_tonemap_encode_fwd with out_is_bf16 = 1).  y: f32 [*,n_out] (activated).
+ * esr_tonemap_encode_fwd with out_is_bf16 = 1; with d->precision = 1: out_is_bf16 = 2, sized for m_total rows, and
+ * only the 96 -> 192 x 3 shape — the kernel then runs on CTA pairs, cta_group::2).  y: f32 [*,n_out] (activated).
  * hidden (nullable): esr_mlp_hidden_bytes(d, m_total) bytes; post-ReLU activations + ReLU masks saved for backward,
  * only for rows >= save_row_begin (rows the caller will never back-propagate through — e.g. the off net on
  * emission-on rays, which see it through a stop-gradient, voxurff.py:243-254 — need not be stored).

@@ -308,7 +308,8 @@ def _image_worker(rank, world, port, out, n):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     res = render_image_sharded(_FakeImageModel(), _image_rays(n), rank, world, chunk=50, em_modes=torch.tensor(0), scale=2.0)
-    out.put((rank, res))
+    # numpy payloads: torch tensors travel as shared-memory handles that die with this process
+    out.put((rank, None if res is None else {k: v.numpy().copy() for k, v in res.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -331,4 +332,5 @@ def test_sharded_image_render_gathers_every_map_on_rank0(n):
     assert res[1] is None and res[2] is None
     assert set(res[0]) == set(want)
     for k in want:
-        assert res[0][k].shape == want[k].shape and torch.equal(res[0][k], want[k]), k
+        got = torch.from_numpy(res[0][k])
+        assert got.shape == want[k].shape and torch.equal(got, want[k]), k

@@ -4,9 +4,10 @@
  (2) the travelling oracle port (oracle/esrnerf_port.py) run beside it on the same inputs and random draws.
 
 Tolerances (BASELINE.json north_star): sample streams (primary and LTS secondary rays) bit-exact; fp32 stages
-(SDF value, analytic SDF gradient, transmittance) 1e-4; everything downstream of the bf16 tensor-core MLPs 1e-2
-on rendered / per-sample outputs.  Gradients: SDF-grid gradient 1e-2 (max-abs / max|ref|) and MLP / colour-grid
-gradients within the inherent bf16 bound (relative L2 < 0.1, tests/test_gpu_voxurff.py docstring)."""
+(SDF value, analytic SDF gradient, transmittance) 1e-4; everything downstream of the tensor-core MLPs 1e-2
+on rendered / per-sample outputs.  Gradients (default mlp_mode "x2": fp16 hi + lo forward operands, fp16 data-gradient
+chain): EVERY parameter gradient — five grids, five nets, the SG environment map — within 1e-2 of the reference's in
+max-abs / max|ref| AND in relative L2."""
 import os
 
 import numpy as np
@@ -78,16 +79,14 @@ def _port_grads(fx, weights, precision):
 @pytest.mark.parametrize("case", C.ESRNERF_CASES)
 def test_esrnerf_gradients_vs_golden(case):
     """Every parameter gradient of the stage (5 grids / nets x layers + the SG environment map) under random
-    cotangents on all 16 outputs: (a) against the bf16-rounding port = the kernels' numeric contract (tight),
-    (b) against the reference's own gradients (golden digests): fp32-only paths (sdf.grid through alpha / the
-    analytic normal, envmap) 1e-2, MLP / colour-grid gradients within the inherent bf16 bound (module docstring)."""
+    cotangents on all 16 outputs against the reference's own gradients (golden digests): 1e-2 in max-norm and in
+    relative L2, no tensor excepted."""
     fx, weights = C.load_esrnerf_case(case)
     m, out = _run_product(fx, weights)
     cot = C.esrnerf_cotangents(out)
     loss = sum((out[k] * cot[k].to(DEV)).sum() for k in cot)
     loss.backward()
-    assert abs(loss.item() - float(fx["loss"])) < 2e-2 * max(1.0, abs(float(fx["loss"])))
-    leaves16 = _port_grads(fx, weights, "bf16")
+    assert abs(loss.item() - float(fx["loss"])) < 1e-3 * max(1.0, abs(float(fx["loss"])))
     checked, bad = 0, {}
     for name, p in m.named_parameters():
         if f"grad/{name}/idx" not in fx:
@@ -100,13 +99,8 @@ def test_esrnerf_gradients_vs_golden(case):
         abs_sum = float(fx[f"grad/{name}/abs_sum"])
         s_err = abs(flat.double().abs().sum().item() - abs_sum) / max(abs_sum, 1e-12)
         mx, l2 = C.grad_err(flat[idx], refv)
-        mx16, l2_16 = C.grad_err(g, leaves16[name].grad)
-        if name == "sdf.grid" or name.startswith("envmap"):
-            ok = (mx < 1e-2 or l2 < 1e-2) and s_err < 1e-2
-        else:
-            ok = l2_16 < 3e-2 and l2 < 0.15 and s_err < 0.05
-        if not ok:
-            bad[name] = dict(vs_golden=(mx, l2, s_err), vs_bf16_port=(mx16, l2_16))
+        if not (mx < 1e-2 and l2 < 1e-2 and s_err < 1e-2):      # every tensor, both metrics
+            bad[name] = dict(vs_golden=(mx, l2, s_err))
         checked += 1
     assert not bad, bad
     assert checked >= 40
@@ -224,8 +218,8 @@ def test_esrnerf_finetune_vs_golden(case):
     for name in want:
         p = dict(m.named_parameters())[name]
         flat = p.grad.contiguous().reshape(-1).cpu()
-        _, l2 = C.grad_err(flat[torch.from_numpy(fx[f"ftgrad/{name}/idx"])], torch.from_numpy(fx[f"ftgrad/{name}/val"]))
-        assert l2 < 0.1, (name, l2)                      # bf16 tensor-core nets: inherent bound (module docstring)
+        mx, l2 = C.grad_err(flat[torch.from_numpy(fx[f"ftgrad/{name}/idx"])], torch.from_numpy(fx[f"ftgrad/{name}/val"]))
+        assert mx < 1e-2 and l2 < 1e-2, (name, mx, l2)
     m.train()
     assert "emit_color.grid" not in m.state_dict()
 

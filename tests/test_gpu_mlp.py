@@ -142,3 +142,119 @@ def test_mlp_accumulate_and_second_net_rows():
     want = dx_ref[:, :56].clone()
     want[m_on:] *= 2
     assert ((d_x.cpu() - want).norm() / want.norm()) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# "x2" precision (esr_mlp_desc_t::precision = 1): fp16 hi + lo operand pairs in the forward chain (CTA pair,
+# cta_group::2), bf16 backward.  Reference = the plain fp32 network (what app/utils/pbr/module.py computes).
+# ---------------------------------------------------------------------------------------------------
+def _fp32_reference(desc, layers, x, d_y, rb, re):
+    xs = x[rb:re].double().clone().requires_grad_(True)
+    ws = [(wt.double().clone().requires_grad_(True), b.double().clone().requires_grad_(True)) for wt, b in layers]
+    h = xs
+    hidden = []
+    for wt, b in ws[:-1]:
+        h = F.relu(F.linear(h, wt, b))
+        hidden.append(h)
+    z = F.linear(h, ws[-1][0], ws[-1][1])[:, : desc["n_out"]]
+    y = F.softplus(z) if desc["act"] == 1 else torch.sigmoid(z)
+    (y * d_y[rb:re].double()).sum().backward()
+    return y.detach(), [t.detach() for t in hidden], xs.grad, ws
+
+
+def _tile_with_residual(x):
+    """fp32 rows -> [bf16 tiles | fp16 residual tiles] as esr_encode_*_fwd(out_is_bf16 = 2) writes them"""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.float16)
+    return torch.cat([_tile(hi), _tile(lo).view(torch.bfloat16)], 0)
+
+
+@pytest.mark.parametrize("m,rb,re,n_out,act", [(1000, 0, 1000, 3, 1), (128, 0, 128, 3, 1), (700, 130, 517, 3, 1),
+                                               (300, 0, 300, 5, 2), (40000, 0, 40000, 3, 1), (75000, 0, 75000, 3, 1)])
+def test_mlp_x2_forward_is_fp32_class_and_grads_within_1e2(m, rb, re, n_out, act):
+    desc = dict(fused.with_precision(fused.RADIANCE_DESC, 1), n_out=n_out, act=act)
+    flat, layers = _flat_and_layers(desc, 3)
+    g = torch.Generator().manual_seed(m + rb)
+    x = torch.randn(m, 96, generator=g)
+    x[:, 91:] = 0
+    d_y = torch.randn(m, n_out, generator=g)
+    y_ref, hid_ref, dx_ref, ws = _fp32_reference(desc, layers, x, d_y, rb, re)
+
+    image = fused.mlp_pack(desc, flat.to(DEV))
+    xd = _tile_with_residual(x.to(DEV))
+    y, hidden = fused._mlp_forward(desc, image, xd, rb, re, m, True)
+    torch.cuda.synchronize()
+    err = ((y[rb:re].cpu().double() - y_ref).abs().max() / y_ref.abs().max()).item()
+    assert err < 2e-5, err                     # x carried to 19 bits, weights / activations to 22: fp32-class outputs
+    if rb > 0:
+        assert (y[:rb] == 0).all()
+    rows = (m + 127) // 128 * 128
+    flips = 0
+    for l, h in enumerate(hid_ref):
+        h_l = hidden[l * rows * 192 * 2:(l + 1) * rows * 192 * 2].view(torch.bfloat16).reshape(rows, 192)
+        got = _untile(h_l)[rb:re].float().cpu().double()
+        # bf16 copy of the exact value: half a bf16 ulp + the chain's own ~1e-6 absolute error
+        assert torch.allclose(got, h, rtol=1.02 * 2 ** -8, atol=1e-5), (l, (got - h).abs().max())
+        flips += int(((got > 0) != (h > 0)).sum())
+    assert flips <= 4 + (re - rb) * 192 * 3 // 50000, flips    # masks: those of the fp32 network to ~1e-5 (vs ~0.4 % flipped with bf16)
+
+    d_x = torch.zeros(m, 56, device=DEV)
+    grad_flat, _ = fused._mlp_backward(desc, image, xd, y, d_y.to(DEV), rb, re, m, hidden, d_x, 56, 0)
+    torch.cuda.synchronize()
+    dx_ref = dx_ref[:, :56]
+    l2 = ((d_x[rb:re].cpu().double() - dx_ref).norm() / dx_ref.norm()).item()
+    assert l2 < 1e-2, l2
+    off = 0
+    for i, (wt, b) in enumerate(ws):
+        n_w, n_b = layers[i][0].numel(), layers[i][1].numel()
+        gw = grad_flat[off:off + n_w].cpu().reshape(layers[i][0].shape).double()
+        gb = grad_flat[off + n_w:off + n_w + n_b].cpu().double()
+        off += n_w + n_b
+        for got, ref in ((gw, wt.grad), (gb, b.grad)):
+            mx = ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+            rel = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+            assert rel < 1e-2 and mx < 1e-2, (i, rel, mx)
+
+
+@pytest.mark.parametrize("m", [900, 128, 5000, 66000])
+def test_tonemap_x2_fused_kernels_vs_fp32_network(m):
+    """esr_tonemap_mlp_fwd / _bwd with precision 1 against the fp32 tone-map net (voxurff.py:783-788, pbr/module.py:24-39)"""
+    desc = fused.with_precision(fused.TONEMAP_DESC, 1)
+    flat, layers = _flat_and_layers(desc, 11)
+    g = torch.Generator().manual_seed(m)
+    lin = (torch.rand(m, 3, generator=g) * 3.0)
+    d_rgb = torch.randn(m, 3, generator=g)
+    d_dir = torch.randn(m, 3, generator=g)
+    # fp64 reference: PE(5) of lin -> 33 -> 192 -> 3 sigmoid; internal column order of the 48-wide row (16 per channel:
+    # lin, sin x5, cos x5, 5 zeros) is the layout of W0 in the flat master copy
+    lr = lin.double().clone().requires_grad_(True)
+    freq = torch.tensor([2.0 ** i for i in range(5)], dtype=torch.float64)
+    cols = []
+    for c in range(3):
+        e = lr[:, c:c + 1] * freq
+        cols += [lr[:, c:c + 1], e.sin(), e.cos(), torch.zeros(m, 5, dtype=torch.float64)]
+    xrow = torch.cat(cols, 1)
+    ws = [(wt.double().clone().requires_grad_(True), b.double().clone().requires_grad_(True)) for wt, b in layers]
+    h = F.relu(F.linear(xrow, ws[0][0], ws[0][1]))
+    y_ref = torch.sigmoid(F.linear(h, ws[1][0], ws[1][1])[:, :3])
+    ((y_ref * d_rgb.double()).sum() + (lr * d_dir.double()).sum()).backward()
+
+    img = fused.mlp_pack(desc, flat.to(DEV))
+    lin_d = lin.to(DEV)
+    rgb = fused._tonemap_fwd(lin_d, img, desc)
+    torch.cuda.synchronize()
+    assert ((rgb.cpu().double() - y_ref.detach()).abs().max()).item() < 2e-5
+    d_lin, g_flat = fused._tonemap_bwd(lin_d, img, rgb, d_rgb.to(DEV), d_dir.to(DEV), desc)
+    torch.cuda.synchronize()
+    l2 = ((d_lin.cpu().double() - lr.grad).norm() / lr.grad.norm()).item()
+    assert l2 < 1e-2, l2
+    off = 0
+    for i, (wt, b) in enumerate(ws):
+        n_w, n_b = layers[i][0].numel(), layers[i][1].numel()
+        gw = g_flat[off:off + n_w].cpu().reshape(layers[i][0].shape).double()
+        gb = g_flat[off + n_w:off + n_w + n_b].cpu().double()
+        off += n_w + n_b
+        for got, ref in ((gw, wt.grad), (gb, b.grad)):
+            keep = ref != 0          # padded input columns / output rows carry no gradient
+            rel = ((got - ref)[keep].norm() / ref[keep].norm().clamp_min(1e-30)).item()
+            assert rel < 1e-2, (i, rel)

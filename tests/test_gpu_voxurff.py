@@ -5,7 +5,11 @@
 
 Tolerances (BASELINE.json north_star): sample indices / masks bit-exact; rendered outputs and parameter
 gradients 1e-4 relative in fp32 (mlp_mode="torch_fp32": fp32 library GEMMs for the MLPs, all other stages the
-CUDA kernels), 1e-2 where bf16 tensor-core MLP math is used (mlp_mode="bf16").
+CUDA kernels), 1e-2 where 16-bit tensor-core MLP math is used.  The product's default, mlp_mode="x2" (fp16 hi + lo
+operand pairs in the forward chains, fp16 data-gradient chain with per-row scaling, bf16 weight-gradient GEMMs), is
+held to that on EVERY parameter gradient, in both metrics (max-abs error / max|ref| and relative L2) and with no
+exception for the MLP / colour-grid tensors; its rendered outputs are fp32-class (asserted at 1e-4).  The paragraph
+below documents why the single-bf16 forward (mlp_mode="bf16", the fast mode) cannot meet it, and how it is checked.
 
 Gradient metric.  "relative" = max-abs error / max|reference| per tensor.  MLP gradients are discontinuous
 at ReLU boundaries, so two correct fp32 evaluations with different summation orders flip a few masks per
@@ -26,7 +30,8 @@ from esr_nerf_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TOL = {"torch_fp32": 1e-4, "bf16": 1e-2}
+TOL = {"torch_fp32": 1e-4, "x2": 1e-2, "bf16": 1e-2}
+OUT_TOL = {"torch_fp32": 1e-4, "x2": 1e-4, "bf16": 1e-2}
 OUT_KEYS = ("etc/alphainv_cum", "etc/white_bg", "srgb/rgb", "lin/rgb")
 
 
@@ -75,14 +80,14 @@ def _is_mlp_or_color(name):
 
 
 @pytest.mark.parametrize("case", C.CASES)
-@pytest.mark.parametrize("mode", ["torch_fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["torch_fp32", "x2", "bf16"])
 def test_outputs_and_grads_vs_golden(case, mode):
     fx, weights = C.load_case(case)
     m, out = _run_product(fx, weights, mode, True)
     tol = TOL[mode]
     for k in OUT_KEYS:
         assert out[k].shape == fx["out/" + k].shape, k
-        assert C.rel_err(out[k], torch.from_numpy(fx["out/" + k])) < tol, k
+        assert C.rel_err(out[k], torch.from_numpy(fx["out/" + k])) < OUT_TOL[mode], k
     checked = 0
     for name, p in m.named_parameters():
         if f"grad/{name}/idx" not in fx:
@@ -94,7 +99,10 @@ def test_outputs_and_grads_vs_golden(case, mode):
         ref = torch.from_numpy(fx[f"grad/{name}/val"])
         abs_sum = float(fx[f"grad/{name}/abs_sum"])
         s_err = abs(flat.double().abs().sum().item() - abs_sum) / max(abs_sum, 1e-12)
-        if mode == "bf16" and _is_mlp_or_color(name):
+        if mode == "x2":                                       # every tensor, both metrics, no carve-out
+            mx, l2 = C.grad_err(flat[idx], ref)
+            assert mx < 1e-2 and l2 < 1e-2 and s_err < 1e-2, (name, mx, l2, s_err)
+        elif mode == "bf16" and _is_mlp_or_color(name):
             _, l2 = C.grad_err(flat[idx], ref)                 # inherent bf16 bound, see module docstring
             assert l2 < 0.1 and s_err < 0.05, (name, l2, s_err)
         else:
@@ -137,6 +145,27 @@ def test_fp32_vs_oracle_port_fresh_rays():
         if name in leaves and leaves[name].grad is not None:
             ok, msg = C.grad_close(p.grad.contiguous(), leaves[name].grad, 1e-4)
             assert ok, (name, msg)
+
+
+def test_x2_vs_oracle_port_fresh_rays():
+    """2048 unseen rays through the default mode (x2 forward chains): outputs at 1e-4 and EVERY parameter gradient
+    within 1e-2 of the fp32 oracle in max-norm and in relative L2."""
+    fx, weights = C.load_case("fine_sparse_s60_big")
+    rays = S.make_rays(2048, 31337)
+    m, out = _run_product(fx, weights, "x2", True, rays)
+    ref32, inter, leaves32 = _oracle_run(fx, weights, rays, "fp32")
+    ray, step, w, st = _stream_in_ray_order(m)
+    assert torch.equal(ray, inter["m3_ray"]) and torch.equal(step, inter["m3_step"])
+    for k in OUT_KEYS:
+        assert C.rel_err(out[k], ref32[k]) < 1e-4, k
+    checked = 0
+    for name, p in m.named_parameters():
+        if name not in leaves32 or leaves32[name].grad is None:
+            continue
+        mx, l2 = C.grad_err(p.grad.contiguous(), leaves32[name].grad)
+        assert mx < 1e-2 and l2 < 1e-2, (name, mx, l2)
+        checked += 1
+    assert checked >= 3 + 8 + 8 + 4
 
 
 def test_bf16_vs_oracle_port_fresh_rays():

@@ -214,7 +214,8 @@ def _sweep_worker(rank, world, port, out):
     m.shuffle()
     r = _FakeRenderer()
     mask = SM.update_ray_groups(r, m, 0.3, 96, rank=rank, world=world)
-    out.put((rank, sum(r.chunks), mask, m.uncert_data_idxs, m.cert_data_idxs))
+    # plain numpy payloads: torch tensors travel as shared-memory handles that die with this process
+    out.put((rank, sum(r.chunks), mask.numpy().copy(), m.uncert_data_idxs.numpy().copy(), m.cert_data_idxs.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -244,6 +245,7 @@ def test_update_ray_groups_two_ranks_agree_with_one():
     want = _reference_update(_FakeRenderer(), single, 0.3, 96)
     assert res[0][1] + res[1][1] == 1001 and abs(res[0][1] - res[1][1]) <= 1        # each rank swept its half
     for _, _, mask, unc, cert in res:
+        mask, unc, cert = torch.from_numpy(mask), torch.from_numpy(unc), torch.from_numpy(cert)
         assert torch.equal(mask, want)
         assert torch.equal(unc, single.uncert_data_idxs) and torch.equal(cert, single.cert_data_idxs)
 
@@ -387,7 +389,9 @@ def _edit_worker(rank, world, port, out):
     m.shuffle()
     r = _FakeEsp()
     SM.filter_edit_rays(r, m, test, size, focal, 10, 256, rank=rank, world=world)
-    out.put((rank, sum(r.chunks), m.uncert_data_idxs, m.cert_data_idxs, {k: m.uncert_data[k] for k in m.keys}))
+    # numpy payloads (see _sweep_worker)
+    out.put((rank, sum(r.chunks), m.uncert_data_idxs.numpy().copy(), m.cert_data_idxs.numpy().copy(),
+             {k: m.uncert_data[k].numpy().copy() for k in m.keys}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -417,6 +421,6 @@ def test_filter_edit_rays_two_ranks_agree_with_one():
     SM.filter_edit_rays(_FakeEsp(), single, test, size, focal, 10, 256)
     assert res[0][1] + res[1][1] == 1500 and res[0][1] == res[1][1]
     for _, _, unc, cert, vals in res:
-        assert torch.equal(unc, single.uncert_data_idxs) and torch.equal(cert, single.cert_data_idxs)
+        assert torch.equal(torch.from_numpy(unc), single.uncert_data_idxs) and torch.equal(torch.from_numpy(cert), single.cert_data_idxs)
         for k in single.keys:
-            assert torch.equal(vals[k], single.uncert_data[k]), k
+            assert torch.equal(torch.from_numpy(vals[k]), single.uncert_data[k]), k
