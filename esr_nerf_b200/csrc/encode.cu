@@ -228,10 +228,10 @@ struct RowWriter<__nv_bfloat16> : TiledRowWriter<ESR_FEAT_DIM> {
 // Same tiled bf16 row, written chunk by chunk as the columns arrive (puts come in increasing column order): only the
 // words of the chunk in progress stay in registers instead of the whole 48-word row — the register budget that lets
 // the fine-stage instantiation of k_encode_fwd run 10 blocks per SM instead of 8.
-// RES (esr_mlp_desc_t::precision = 1, out_is_bf16 = 2): every 16-byte bf16 chunk is followed into a second tiled
-// buffer (`res_off` 16-byte words further: the row count padded to whole tiles x 12 chunks) by the fp16 chunk of what
-// the bf16 rounding lost, v - bf16(v): the forward chain then sees the feature to ~19 bits while the weight-gradient
-// GEMM keeps reading the bf16 tile.
+// RES (esr_mlp_desc_t::precision = 1, out_is_bf16 = 2): the row is written as fp16 (not bf16) and every 16-byte chunk is
+// followed into a second tiled buffer (`res_off` 16-byte words further: the row count padded to whole tiles x 12
+// chunks) by the fp16 chunk of what that rounding lost, v - fp16(v): the forward chain sees the feature to ~22 bits,
+// the weight-gradient GEMM reads the first (fp16) tile.
 template <bool SECOND, bool RES = false>
 struct StreamRowWriter {
   uint4 *b4, *b4b;       // b4b: the second copy of the row whose colour slot 0 (columns 0..5) holds `alt` (BRDF grid taps)
@@ -240,15 +240,18 @@ struct StreamRowWriter {
   uint32_t cur_r[RES ? 4 : 1], alt_r[RES ? 3 : 1];
   ESR_D StreamRowWriter(__nv_bfloat16 *b, int64_t r, int64_t m_total = 0)
       : b4(reinterpret_cast<uint4 *>(b)), b4b(nullptr), row(r), res_off(act_rows_padded(m_total) * (ESR_FEAT_DIM / 8)) {}
-  // bf16 pair of (a, b) and, with RES, the fp16 pair of the two rounding residuals
+  // bf16 pair of (a, b); with RES the pair is fp16 and `res` the fp16 pair of the two rounding residuals
   ESR_D static uint32_t pack(float a, float b, uint32_t &res) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-    const uint32_t w = *reinterpret_cast<uint32_t *>(&p);
     if constexpr (RES) {
-      const __half2 h = __floats2half2_rn(a - __uint_as_float(w << 16), b - __uint_as_float(w & 0xffff0000u));
-      res = *reinterpret_cast<const uint32_t *>(&h);
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+      res = *reinterpret_cast<const uint32_t *>(&l);
+      return *reinterpret_cast<const uint32_t *>(&h);
+    } else {
+      __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+      return *reinterpret_cast<uint32_t *>(&p);
     }
-    return w;
   }
   ESR_D void set_second(__nv_bfloat16 *b, const float (&col)[6]) {
     b4b = reinterpret_cast<uint4 *>(b);

@@ -46,9 +46,20 @@ ESR_HD int64_t act_hidden_bytes(int n_hidden, int64_t m_total) {
   return (int64_t)n_hidden * act_rows_padded(m_total) * (ACT_W * 2 + 32);
 }
 // `d_z` scratch = [n_hidden][rows_padded][192] bf16 hidden-layer cotangents, then the output-layer cotangent as
-// [rows_padded][16] bf16 (tiled with 2 chunks per row)
-ESR_HD int64_t act_dz_bytes(int n_hidden, int64_t m_total) {
+// [rows_padded][16] bf16 (tiled with 2 chunks per row), then a 128-byte tail whose first word is max |d_y| (f32 bits)
+// of the launch: precision 1 stores the cotangents as fp16 times the power of two that puts that maximum in [64, 128)
+// (act_dz_scale), the weight-gradient GEMM divides its sums by it
+ESR_HD int64_t act_dz_tail_offset(int n_hidden, int64_t m_total) {
   return act_rows_padded(m_total) * ((int64_t)n_hidden * ACT_W * 2 + 32);
+}
+ESR_HD int64_t act_dz_bytes(int n_hidden, int64_t m_total) { return act_dz_tail_offset(n_hidden, m_total) + 128; }
+// (G, 1 / G) for the launch's max |d_y| given as f32 bits: G = 2^(133 - e) for a biased exponent e in [8, 250]
+// (zero / denormal / non-finite maxima: 1) — the stored cotangents then stay below 2^7 x (what the chain adds on top)
+ESR_D float act_dz_scale(uint32_t absmax_bits, float &inv) {
+  const int e = (int)((absmax_bits >> 23) & 0xff);
+  const bool ok = e >= 8 && e <= 250;
+  inv = ok ? __int_as_float((e - 6) << 23) : 1.f;
+  return ok ? __int_as_float((260 - e) << 23) : 1.f;
 }
 ESR_HD int64_t act_mask_base_bytes(int n_hidden, int64_t m_total) {
   return (int64_t)n_hidden * act_rows_padded(m_total) * ACT_W * 2;

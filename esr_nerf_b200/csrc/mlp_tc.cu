@@ -168,6 +168,12 @@ ESR_D uint32_t pack2h_relu(float lo, float hi) {
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// the same with overflow clamped to +-65504 instead of +-inf (stored cotangents: a runaway value must not poison a sum)
+ESR_D uint32_t pack2h_sat(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 ESR_D float2 unpack2h(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2 *>(&v)); }
 // relu(z0), relu(z1) as an fp16 pair hi plus the fp16 pair lo of what the first rounding lost: hi + lo carries 22
 // significant bits (an absolute error of 2^-25 where lo is subnormal, i.e. for values below 0.25)
@@ -280,8 +286,8 @@ struct TcLayout {
   __host__ __device__ int64_t x2_bias() const { return (k0 == 96 ? 2 : 1) * x2_rank_bytes(); }
   __host__ __device__ int64_t x2_bytes() const { return x2_bias() + (int64_t)(NH * TC_W + TC_NOUT_PAD) * 4; }
   __host__ __device__ int64_t total() const { return x2_off() + (x2 ? (x2_bytes() + 127) / 128 * 128 : 0); }
-  // precision 1, radiance-shaped nets: the transposed matrices of the data-gradient chain are fp16 (k_mlp_dgrad_tc H16)
-  __host__ __device__ bool bwd_h16() const { return x2 && k0 == 96; }
+  // precision 1: the transposed matrices of the data-gradient chain are fp16 (k_mlp_dgrad_tc H16, k_tonemap_bwd_fused X2)
+  __host__ __device__ bool bwd_h16() const { return x2; }
 };
 
 static TcLayout tc_layout(const esr_mlp_desc_t *d) {
@@ -808,12 +814,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const bool valid = row < row_end;
       const bool save = valid && hidden && row >= save_begin;
       const bool save_w = __any_sync(FULL, save);
-      // ---- layer-0 operand -> TMEM (A_hi = the bf16 tile's values as fp16, A_lo = the residual tile) ----
+      // ---- layer-0 operand -> TMEM (A_hi = the fp16 tile, A_lo = the residual tile) ----
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const uint32_t col = 4 * (3 * et.grp + i);
-        tmem_st4(tmem + et.lane_base + X2_A0 + col, bf2_to_h2(xb[i].x), bf2_to_h2(xb[i].y), bf2_to_h2(xb[i].z),
-                 bf2_to_h2(xb[i].w));
+        tmem_st4(tmem + et.lane_base + X2_A0 + col, xb[i].x, xb[i].y, xb[i].z, xb[i].w);
         tmem_st4(tmem + et.lane_base + X2_A1 + col, xl[i].x, xl[i].y, xl[i].z, xl[i].w);
       }
       tmem_st_wait();
@@ -839,25 +844,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           const int col0 = TC_GCOLS * et.grp + 16 * cc;
-          uint32_t ph[8], pl[8], pb[8];
+          uint32_t ph[8], pl[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
             float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
             fma2(z0, z1, 1.f / TC_WSCALE, bb);
             split2h_relu(z0, z1, ph[j], pl[j]);
-            if (save_w) {   // bf16 copy + masks for the backward kernels (same layout as the bf16 chain writes)
-              pb[j] = pack2_relu(z0, z1);
-              const uint32_t tt = pb[j] + 0x7fff7fffu;
+            if (save_w) {   // masks for the data-gradient chain (same layout and bit trick as the bf16 chain: a non-zero
+              // non-negative fp16 half is <= 0x7c00, plus 0x7fff carries into its top bit and never into the other half)
+              const uint32_t tt = ph[j] + 0x7fff7fffu;
               constexpr uint32_t one2 = 0x00010001u;
               mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (one2 << (8 * (cc & 1) + j));
             }
           }
           tmem_st8(tmem + et.lane_base + X2_A0 + col0 / 2, ph);
           tmem_st8(tmem + et.lane_base + X2_A1 + col0 / 2, pl);
-          if (save) {
-            hl[act_chunk_index(row, col0 / 8)] = make_uint4(pb[0], pb[1], pb[2], pb[3]);
-            hl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(pb[4], pb[5], pb[6], pb[7]);
+          if (save) {   // the weight-gradient GEMM's operand: the fp16 hi part (same tiled layout as the bf16 chain's copy)
+            hl[act_chunk_index(row, col0 / 8)] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            hl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
           }
           arrive_chunk(cc);
         }
@@ -1150,17 +1155,21 @@ struct BwdSm {
 // 8) and the transposed weights are fp16.  fp16's narrow exponent is dealt with PER ROW: the chain is linear in a row's
 // output cotangent, so row r is multiplied by a power of two s_r that puts max|dZ_out[r]| in [16, 32) (what the chain can
 // add on top stays far below 65504, what it loses at the bottom is an ABSOLUTE error of s_r^-1 2^-25, irrelevant in sums
-// over rows); everything that leaves the kernel (bf16 dZ_l for the weight-gradient GEMM, d_x) is multiplied by 1 / s_r,
-// exactly.  Same MMAs as the bf16 chain; the colour-grid / feature gradients it produces are ~8x closer to the
-// reference's (5e-4 instead of 4e-3 relative L2).
+// over rows); d_x leaves the kernel multiplied by 1 / s_r, exactly.  The copies for the weight-gradient GEMM (dZ_l,
+// dZ_out) are fp16 too, but a sum over rows needs ONE scale for the whole launch: G = the power of two that puts
+// max |d_y| (`absmax`, made by k_absmax just before) in [64, 128) — |act'| <= 1, so no |dZ_out| exceeds it; rows more
+// than 2^20 below the largest lose precision gradually, and weigh that little in the sums.  Same MMAs as the bf16
+// chain; the gradients it produces are ~8x closer to the reference's (5e-4 instead of 4e-3 relative L2).
 template <int K0, int NH, int DXN, int NO, bool ACC, bool OVL = false, bool H16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_mlp_dgrad_tc(const uint8_t *__restrict__ image_bwd, const float *__restrict__ y, const float *__restrict__ d_y,
                    int64_t row_begin, int64_t row_end, int64_t m_total, const __nv_bfloat16 *__restrict__ hidden,
                    __nv_bfloat16 *__restrict__ d_z, float *__restrict__ d_z_out, float *__restrict__ d_x, int dx_cols,
-                   int accumulate, int n_out, int act) {
+                   int accumulate, int n_out, int act, const uint32_t *__restrict__ absmax) {
   extern __shared__ __align__(128) uint8_t smem[];
   using S = BwdSm<K0, NH, DXN>;
+  [[maybe_unused]] float g_inv = 1.f;
+  [[maybe_unused]] const float g_scale = H16 ? act_dz_scale(__ldg(absmax), g_inv) : 1.f;
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t sbase = smem_addr(smem);
@@ -1300,8 +1309,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           *reinterpret_cast<float4 *>(d_z_out + row * 8 + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
         }
       }
-      const uint4 dz16 = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
-      if (valid) {  // bf16 copy for the output layer's weight-gradient GEMM: tiled, 2 chunks per row, after the dZ_l
+      // copy for the output layer's weight-gradient GEMM (bf16, or fp16 times G): tiled, 2 chunks per row, after the dZ_l
+      const uint4 dz16 = H16 ? make_uint4(pack2h_sat(dz[0] * g_scale, dz[1] * g_scale), pack2h_sat(dz[2] * g_scale, dz[3] * g_scale),
+                                          pack2h_sat(dz[4] * g_scale, dz[5] * g_scale), pack2h_sat(dz[6] * g_scale, dz[7] * g_scale))
+                             : make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], dz[3]), pack2(dz[4], dz[5]), pack2(dz[6], dz[7]));
+      if (valid) {
         uint4 *zo = reinterpret_cast<uint4 *>(d_z + (int64_t)NH * layer_stride);
         zo[tiled_chunk_index(row, 0, 2)] = dz16;
         zo[tiled_chunk_index(row, 1, 2)] = make_uint4(0u, 0u, 0u, 0u);
@@ -1327,6 +1339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncthreads();
     }
     [[maybe_unused]] const float inv_s = (H16 && is_epi) ? s_inv[t] : 1.f;
+    [[maybe_unused]] const float z_s = inv_s * g_scale;   // chain value -> stored cotangent (both powers of two: exact)
     if (is_issuer && lane == 0) {
       if constexpr (!OVL) {
         tc_fence_after();
@@ -1404,7 +1417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t pm = pair_mask(mk, j);
             if constexpr (H16) {
               pa[j] = pack2h(v0, v1) & pm;                     // next MMA's operand: fp16, still carrying s_r
-              p[j] = pack2(v0 * inv_s, v1 * inv_s) & pm;       // what the weight-gradient GEMM reads: bf16, unscaled
+              p[j] = pack2h_sat(v0 * z_s, v1 * z_s) & pm;      // what the weight-gradient GEMM reads: fp16, times G
             } else {
               p[j] = pack2(v0, v1) & pm;
             }
@@ -1486,6 +1499,7 @@ ESR_D void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 }
 // instruction descriptor: D f32, A/B bf16, both MN-major, M = 128
 __host__ __device__ constexpr uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
+__host__ __device__ constexpr uint32_t make_idesc_h_mn(int n) { return make_idesc_h(n) | (1u << 15) | (1u << 16); }
 
 // ACH = feature chunks (8 features each) of the A operand per row: 24 for a hidden layer's dZ_l (two accumulators,
 // see above), 2 for the output layer's dZ_out (16 columns, 3 real: one accumulator over a 128-feature A tile whose
@@ -1504,11 +1518,15 @@ struct WgSm {
   static constexpr int NB = KIN + 16;                             // UMMA N
 };
 
-template <int KIN, int ACH>
+// H16 (precision 1): both operands are fp16 — the layer input as the forward chain saved it, the cotangent times the
+// launch's power-of-two scale G (k_mlp_dgrad_tc) — and the sums are divided by G on their way out.
+template <int KIN, int ACH, bool H16 = false>
 __global__ void __launch_bounds__(160, 1)
     k_mlp_wgrad_tc(const __nv_bfloat16 *__restrict__ dz, const __nv_bfloat16 *__restrict__ in, int64_t row_begin,
                    int64_t row_end, int out_rows, float *__restrict__ gW /* [out_rows][KIN] */,
-                   float *__restrict__ gb /* [out_rows] */) {
+                   float *__restrict__ gb /* [out_rows] */, const uint32_t *__restrict__ absmax) {
+  constexpr uint32_t ONE = H16 ? 0x00003c00u : 0x00003f80u;   // 1.0 in element 0 of a chunk (fp16 / bf16)
+  constexpr uint32_t idesc = H16 ? make_idesc_h_mn(WgSm<KIN, ACH>::NB) : make_idesc_mn(WgSm<KIN, ACH>::NB);
   extern __shared__ __align__(128) uint8_t smem[];
   using S = WgSm<KIN, ACH>;
   const int64_t T0 = row_begin >> 7, T1 = (row_end + 127) >> 7;
@@ -1527,7 +1545,7 @@ __global__ void __launch_bounds__(160, 1)
   for (int i = threadIdx.x; i < 2 * 2 * TC_TM; i += blockDim.x) {
     const int st = i / (2 * TC_TM), r = i % (2 * TC_TM);  // r < 128: chunk KIN/8, else chunk KIN/8 + 1
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < TC_TM) v.x = 0x00003f80u;  // bf16 1.0 in element 0
+    if (r < TC_TM) v.x = ONE;
     *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_bytes + (KIN / 8) * (TC_TM * 16) + r * 16) = v;
   }
   if constexpr (S::a_chunks > ACH) {
@@ -1590,10 +1608,9 @@ __global__ void __launch_bounds__(160, 1)
 #pragma unroll
       for (int s = 0; s < TC_TM / 16; ++s) {
         const uint64_t bd = make_desc(b0 + s * 256, 128, TC_TM * 16);
-        mma_ss(tmem + 0, make_desc(a0 + s * 256, 128, TC_TM * 16), bd, make_idesc_mn(S::NB), (it | s) != 0);
+        mma_ss(tmem + 0, make_desc(a0 + s * 256, 128, TC_TM * 16), bd, idesc, (it | s) != 0);
         if (ACH == 24)
-          mma_ss(tmem + 256, make_desc(a0 + 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16), bd, make_idesc_mn(S::NB),
-                 (it | s) != 0);
+          mma_ss(tmem + 256, make_desc(a0 + 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16), bd, idesc, (it | s) != 0);
       }
       mma_commit(bar_empty + 8 * st);
     }
@@ -1603,12 +1620,14 @@ __global__ void __launch_bounds__(160, 1)
       mbar_wait(bar_empty + 8 * st, k_par);
       if (threadIdx.x < TC_TM)
         *reinterpret_cast<uint4 *>(smem + st * S::stage + S::a_bytes + (KIN / 8) * (TC_TM * 16) + threadIdx.x * 16) =
-            make_uint4(0x00003f80u, 0, 0, 0);
+            make_uint4(ONE, 0, 0, 0);
       fence_proxy_async();
       __syncthreads();
     }
   }
   // ---- epilogue: accumulators -> global gradient (RED) ----
+  float g_inv = 1.f;
+  if constexpr (H16) act_dz_scale(__ldg(absmax), g_inv);
   mbar_wait(bar_empty + 8 * (int)((n - 1) & 1), (uint32_t)(((n - 1) >> 1) & 1));
   tc_fence_after();
   if (warp < 4) {
@@ -1627,10 +1646,11 @@ __global__ void __launch_bounds__(160, 1)
           if (cc < KIN / 16) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              red_add4(gW + (int64_t)o * KIN + cc * 16 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              red_add4(gW + (int64_t)o * KIN + cc * 16 + 4 * q, __uint_as_float(r[4 * q]) * g_inv,
+                       __uint_as_float(r[4 * q + 1]) * g_inv, __uint_as_float(r[4 * q + 2]) * g_inv,
+                       __uint_as_float(r[4 * q + 3]) * g_inv);
           } else {
-            red_add(gb + o, __uint_as_float(r[0]));
+            red_add(gb + o, __uint_as_float(r[0]) * g_inv);
           }
         }
       }
@@ -1641,16 +1661,26 @@ __global__ void __launch_bounds__(160, 1)
   if (warp == 4) tmem_dealloc(tmem, TM_COLS);
 }
 
-template <int KIN, int ACH>
+// max |v| over a float range as f32 bits (non-negative floats order like their bit patterns; NaNs are skipped by fmaxf)
+__global__ void k_absmax(const float *__restrict__ v, int64_t n, uint32_t *__restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(v + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+template <int KIN, int ACH, bool H16 = false>
 static int launch_wgrad(const __nv_bfloat16 *dz, const __nv_bfloat16 *in, int64_t rb, int64_t re, int out_rows, float *gW,
-                        float *gb, cudaStream_t st) {
-  auto kern = k_mlp_wgrad_tc<KIN, ACH>;
+                        float *gb, const uint32_t *absmax, cudaStream_t st) {
+  auto kern = k_mlp_wgrad_tc<KIN, ACH, H16>;
   constexpr int bytes = WgSm<KIN, ACH>::bytes;
   ESR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   const int64_t tiles = ((re + 127) >> 7) - (rb >> 7);
   const unsigned grid = (unsigned)max((int64_t)1, min((int64_t)num_sms(), tiles));
   ESR_STAGE(ACH == 24 ? "k_mlp_wgrad_tc" : "k_mlp_wgrad_tc_out", st);
-  kern<<<grid, 160, bytes, st>>>(dz, in, rb, re, out_rows, gW, gb);
+  kern<<<grid, 160, bytes, st>>>(dz, in, rb, re, out_rows, gW, gb, absmax);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -1680,18 +1710,23 @@ struct TmBwdSmT {
   static constexpr int x = bias + TC_W * 4;            // X tile [8][128][8] bf16: 6 feature chunks, ones chunk, zero chunk
   static constexpr int hs = x + 8 * TC_TM * 16;        // H tile  [24][128][8]
   static constexpr int zs = hs + 24 * TC_TM * 16;      // dZ0 tile [24][128][8]
-  static constexpr int dzo = zs + 24 * TC_TM * 16;     // dZ_out tile [2][128][8] (chunk 1 zero)
-  static constexpr int xh = dzo + 2 * TC_TM * 16;      // X2: fp16 hi / lo tiles of the encoding [6][128][8] each
-  static constexpr int xl = xh + (X2 ? 6 * TC_TM * 16 : 0);
-  static constexpr int bar = xl + (X2 ? 6 * TC_TM * 16 : 0);   // bar_mma, bar_w, TMEM slot
+  static constexpr int dzo = zs + 24 * TC_TM * 16;     // dZ_out tile [2][128][8] (chunk 1 zero); X2: times the ROW's scale
+  static constexpr int xl = dzo + 2 * TC_TM * 16;      // X2: fp16 lo tile of the encoding [6][128][8] (the hi tile is `x`)
+  static constexpr int dzw = xl + (X2 ? 6 * TC_TM * 16 : 0);   // X2: dZ_out tile times the CTA's scale (weight gradient)
+  static constexpr int sinv = dzw + (X2 ? 2 * TC_TM * 16 : 0); // X2: 1 / (row scale) f32 [128], then the CTA's max |d_y| (u32)
+  static constexpr int bar = sinv + (X2 ? TC_TM * 4 + 16 : 0);   // bar_mma, bar_w, TMEM slot
   static constexpr int bytes = bar + 32;
 };
 using TmBwdSm = TmBwdSmT<false>;
 constexpr uint32_t TMB_D = 0, TMB_A = 192, TMB_S = 288, TMB_G0 = 336, TMB_GO = 464;
 
 // X2 (precision 1): the recomputation of H uses the forward's arithmetic — fp16 hi / lo tiles of the encoding and of W0
-// (x2 section at byte x2_off of the image), three MMAs per K-step — so that the masks are the forward's; everything
-// downstream (bf16 H tile for dWo, dZ tiles, data gradient) is unchanged.
+// (x2 section at byte x2_off of the image), three MMAs per K-step — so that the masks are the forward's, and everything
+// downstream runs on fp16 operands (11 significant bits against bf16's 8): the H / X tiles, the transposed weights, and
+// the cotangents, whose narrow exponent is handled as in k_mlp_dgrad_tc — per ROW in the data-gradient chain (power of
+// two s_r putting max |dZ_out[r]| in [16, 32), divided out of d_lin), per CTA in the tiles of the weight-gradient MMAs
+// (their sums run over all rows of the CTA's tiles: G = the power of two putting the CTA's max |d_y|, found by a first
+// pass over its rows' d_y, in [64, 128); divided out of the accumulators before the REDs).
 template <bool X2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_tonemap_bwd_fused(const uint8_t *__restrict__ image, int64_t bwd_off, int64_t bias_off, int64_t x2_off,
@@ -1716,11 +1751,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   for (int i = threadIdx.x; i < TC_TM; i += blockDim.x) {   // constant zero chunks
     *reinterpret_cast<uint4 *>(smem + S::x + 7 * (TC_TM * 16) + i * 16) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4 *>(smem + S::dzo + TC_TM * 16 + i * 16) = make_uint4(0, 0, 0, 0);
+    if constexpr (X2) *reinterpret_cast<uint4 *>(smem + S::dzw + TC_TM * 16 + i * 16) = make_uint4(0, 0, 0, 0);
   }
+  [[maybe_unused]] float *s_inv = reinterpret_cast<float *>(smem + S::sinv);
+  [[maybe_unused]] uint32_t *s_absmax = reinterpret_cast<uint32_t *>(smem + S::sinv + TC_TM * 4);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_init(bar_w, 1);
     fence_mbar_init();
+    if constexpr (X2) *s_absmax = 0u;
   }
   if (is_issuer) tmem_alloc(smem_addr(tmem_slot), TM_COLS);
   fence_proxy_async();
@@ -1736,28 +1775,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t phase = 0;
   float bo_acc[3] = {0.f, 0.f, 0.f};
   int it = 0;
+  [[maybe_unused]] float g_scale = 1.f, g_inv = 1.f;
+  if constexpr (X2) {   // first pass: max |d_y| over the rows of this CTA's tiles (|act'| <= 1: a bound on every |dZ_out|)
+    float mx = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t base = tile * TC_TM * n_out, end = min(base + (int64_t)TC_TM * n_out, m * n_out);
+      for (int64_t i = base + threadIdx.x; i < end; i += blockDim.x) mx = fmaxf(mx, fabsf(__ldg(d_y + i)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    if (lane == 0 && mx > 0.f) atomicMax(s_absmax, __float_as_uint(mx));
+    __syncthreads();
+    g_scale = act_dz_scale(*s_absmax, g_inv);
+  }
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t row = tile * TC_TM + t;
     const bool valid = is_epi && row < m;
     float xv = 0.f, sn[5], cs[5], dz[3] = {0.f, 0.f, 0.f};
+    [[maybe_unused]] float inv_s = 1.f;   // X2: 1 / (row scale), read in E2 (a barrier before the next tile's T0 rewrites it)
     // ---- T0: encoding + output cotangent tiles ----
     if (is_epi) {
       if (it > 0) mbar_wait(bar_w, (uint32_t)((it - 1) & 1));   // the weight-gradient MMAs that read the tiles have retired
       if (et.grp < 3) {
         xv = valid ? __ldg(lin + 3 * row + et.grp) : 0.f;
         uint4 lo, hi;
-        if constexpr (X2) {
-          uint4 hl, hh, ll, lh;
-          tonemap_pe_channel_x2(xv, hl, hh, ll, lh, sn, cs);
-          if (!valid) hl = hh = ll = lh = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4 *>(smem + S::xh + (2 * et.grp) * (TC_TM * 16) + t * 16) = hl;
-          *reinterpret_cast<uint4 *>(smem + S::xh + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hh;
+        if constexpr (X2) {   // the fp16 hi tile is also the weight-gradient GEMM's operand (dW0 += dZ0^T X)
+          uint4 ll, lh;
+          tonemap_pe_channel_x2(xv, lo, hi, ll, lh, sn, cs);
+          if (!valid) ll = lh = make_uint4(0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4 *>(smem + S::xl + (2 * et.grp) * (TC_TM * 16) + t * 16) = ll;
           *reinterpret_cast<uint4 *>(smem + S::xl + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = lh;
-          // bf16 tile for the weight-gradient GEMM (dW0 += dZ0^T X), from the same sines / cosines
-          lo = make_uint4(pack2(xv, sn[0]), pack2(sn[1], sn[2]), pack2(sn[3], sn[4]), pack2(cs[0], cs[1]));
-          hi = make_uint4(pack2(cs[2], cs[3]), pack2(cs[4], 0.f), 0u, 0u);
         } else {
           tonemap_pe_channel(xv, lo, hi, sn, cs);
         }
@@ -1765,7 +1813,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp) * (TC_TM * 16) + t * 16) = lo;
         *reinterpret_cast<uint4 *>(smem + S::x + (2 * et.grp + 1) * (TC_TM * 16) + t * 16) = hi;
       } else {   // the "ones" column (bias gradient); zero for rows past the end
-        *reinterpret_cast<uint4 *>(smem + S::x + 6 * (TC_TM * 16) + t * 16) = make_uint4(valid ? 0x00003f80u : 0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(smem + S::x + 6 * (TC_TM * 16) + t * 16) =
+            make_uint4(valid ? (X2 ? 0x00003c00u : 0x00003f80u) : 0u, 0u, 0u, 0u);
       }
       if (et.grp == 0) {
         if (valid) {
@@ -1776,7 +1825,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               dz[c] = __ldg(d_y + row * n_out + c) * (act == 1 ? (1.f - expf(-yy)) : (act == 2 ? yy * (1.f - yy) : 1.f));
             }
         }
-        *reinterpret_cast<uint4 *>(smem + S::dzo + t * 16) = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
+        if constexpr (X2) {
+          const float mxa = fmaxf(fmaxf(fabsf(dz[0]), fabsf(dz[1])), fabsf(dz[2]));
+          const int e = (__float_as_int(mxa) >> 23) & 0xff;          // biased exponent of the row's largest |dZ_out|
+          const bool scaled = e >= 8 && e <= 250;                    // zero / denormal / absurd rows travel unscaled
+          const float sr = scaled ? __int_as_float((258 - e) << 23) : 1.f;   // 2^(4 - (e - 127))
+          s_inv[t] = scaled ? __int_as_float((e - 4) << 23) : 1.f;
+          *reinterpret_cast<uint4 *>(smem + S::dzo + t * 16) = make_uint4(pack2h(dz[0] * sr, dz[1] * sr), pack2h(dz[2] * sr, 0.f), 0u, 0u);
+          *reinterpret_cast<uint4 *>(smem + S::dzw + t * 16) =
+              make_uint4(pack2h_sat(dz[0] * g_scale, dz[1] * g_scale), pack2h_sat(dz[2] * g_scale, 0.f), 0u, 0u);
+        } else {
+          *reinterpret_cast<uint4 *>(smem + S::dzo + t * 16) = make_uint4(pack2(dz[0], dz[1]), pack2(dz[2], 0.f), 0u, 0u);
+        }
       }
       fence_proxy_async();
     }
@@ -1789,7 +1849,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int s = 0; s < 3; ++s)
 #pragma unroll
           for (int term = 0; term < 3; ++term)   // hi.hi, hi.lo, lo.hi
-            mma_ss(tmem + TMB_D, make_desc(sbase + (term == 2 ? S::xl : S::xh) + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
+            mma_ss(tmem + TMB_D, make_desc(sbase + (term == 2 ? S::xl : S::x) + 2 * s * (TC_TM * 16), TC_TM * 16, 128),
                    make_desc(sbase + S::w0 + (term == 1 ? S::w0_part : 0) + 2 * s * (TC_W * 16), TC_W * 16, 128),
                    make_idesc_h(TC_W), (s | term) != 0);
       } else {
@@ -1818,11 +1878,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int j = 0; j < 8; ++j) {
           const float2 bb = *reinterpret_cast<const float2 *>(sbias + col0 + 2 * j);
           float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
-          if constexpr (X2)
+          if constexpr (X2) {
             fma2(z0, z1, 1.f / TC_WSCALE, bb);
-          else
+            p[j] = pack2h_relu(z0, z1);
+          } else {
             add2(z0, z1, bb);
-          p[j] = pack2_relu(z0, z1);
+            p[j] = pack2_relu(z0, z1);
+          }
           const uint32_t tt = p[j] + 0x7fff7fffu;
           mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (0x00010001u << (8 * (cc & 1) + j));
         }
@@ -1836,7 +1898,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (is_issuer && lane == 0) {
       tc_fence_after();
       mma_ss(tmem + TMB_D, make_desc(sbase + S::dzo, TC_TM * 16, 128), make_desc(sbase + S::wot, TC_W * 16, 128),
-             make_idesc(TC_W), 0);
+             X2 ? make_idesc_h(TC_W) : make_idesc(TC_W), 0);
       mma_commit(bar);
       // dWo^T += Hs^T dZ_out (rows are the K dimension: both tiles are MN-major operands as they lie)
 #pragma unroll
@@ -1844,7 +1906,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
           mma_ss(tmem + TMB_GO + 16 * h, make_desc(sbase + S::hs + h * 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16),
-                 make_desc(sbase + S::dzo + s * 256, 128, TC_TM * 16), make_idesc_mn(16), (it | s) != 0);
+                 make_desc(sbase + (X2 ? S::dzw : S::dzo) + s * 256, 128, TC_TM * 16),
+                 X2 ? make_idesc_h_mn(16) : make_idesc_mn(16), (it | s) != 0);
     }
     // ---- E2: dZ0 = dH * mask -> TMEM A operand + shared tile ----
     if (is_epi) {
@@ -1860,10 +1923,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int col0 = TC_GCOLS * et.grp + 16 * cc;
         const uint32_t mk = mask[cc >> 1] >> (8 * (cc & 1));
         uint32_t p[8];
+        if constexpr (X2) {   // chain operand: fp16 carrying the row's scale; shared tile: fp16 times the CTA's scale
+          inv_s = s_inv[t];
+          const float z_s = inv_s * g_scale;
+          uint32_t pa[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & pair_mask(mk, j);
-        tmem_st8(tmem + et.lane_base + TMB_A + col0 / 2, p);
+          for (int j = 0; j < 8; ++j) {
+            const float v0 = __uint_as_float(r[cc][2 * j]), v1 = __uint_as_float(r[cc][2 * j + 1]);
+            const uint32_t pm = pair_mask(mk, j);
+            pa[j] = pack2h(v0, v1) & pm;
+            p[j] = pack2h_sat(v0 * z_s, v1 * z_s) & pm;
+          }
+          tmem_st8(tmem + et.lane_base + TMB_A + col0 / 2, pa);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            p[j] = pack2(__uint_as_float(r[cc][2 * j]), __uint_as_float(r[cc][2 * j + 1])) & pair_mask(mk, j);
+          tmem_st8(tmem + et.lane_base + TMB_A + col0 / 2, p);
+        }
         *reinterpret_cast<uint4 *>(smem + S::zs + (col0 / 8) * (TC_TM * 16) + t * 16) = make_uint4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<uint4 *>(smem + S::zs + (col0 / 8 + 1) * (TC_TM * 16) + t * 16) = make_uint4(p[4], p[5], p[6], p[7]);
       }
@@ -1876,8 +1953,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
 #pragma unroll
       for (int s = 0; s < TC_W / 16; ++s)
-        mma_ts(tmem + TMB_S, tmem + TMB_A + 8 * s, make_desc(sbase + S::w0t + 2 * s * (48 * 16), 48 * 16, 128), make_idesc(48),
-               s > 0);
+        mma_ts(tmem + TMB_S, tmem + TMB_A + 8 * s, make_desc(sbase + S::w0t + 2 * s * (48 * 16), 48 * 16, 128),
+               X2 ? make_idesc_h(48) : make_idesc(48), s > 0);
       mma_commit(bar);
       // dW0 | db0 += Zs^T [X | 1]
 #pragma unroll
@@ -1885,7 +1962,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
           mma_ss(tmem + TMB_G0 + 64 * h, make_desc(sbase + S::zs + h * 8 * (TC_TM * 16) + s * 256, 128, TC_TM * 16),
-                 make_desc(sbase + S::x + s * 256, 128, TC_TM * 16), make_idesc_mn(64), (it | s) != 0);
+                 make_desc(sbase + S::x + s * 256, 128, TC_TM * 16), X2 ? make_idesc_h_mn(64) : make_idesc_mn(64), (it | s) != 0);
       mma_commit(bar_w);
     }
     // ---- E3: d_lin of (row, channel) from the 16 encoded-column cotangents of the channel ----
@@ -1898,11 +1975,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tmem_ld16(tmem + et.lane_base + TMB_S + 16 * et.grp, r);
         tmem_ld_wait();
         if (valid) {
-          float g = __uint_as_float(r[0]) + (d_direct ? __ldg(d_direct + 3 * row + et.grp) : 0.f);
+          float g = __uint_as_float(r[0]);
 #pragma unroll
           for (int f = 0; f < 5; ++f)
             g += (float)(1 << f) * (cs[f] * __uint_as_float(r[1 + f]) - sn[f] * __uint_as_float(r[6 + f]));
-          d_lin[3 * row + et.grp] = g;
+          if constexpr (X2) g *= inv_s;   // the chain carried the row's scale
+          d_lin[3 * row + et.grp] = g + (d_direct ? __ldg(d_direct + 3 * row + et.grp) : 0.f);
         }
       }
       if (et.grp == 0) {
@@ -1934,10 +2012,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           if (cc < 3) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              red_add4(gW0 + (int64_t)o * 48 + cc * 16 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              red_add4(gW0 + (int64_t)o * 48 + cc * 16 + 4 * q, __uint_as_float(r[4 * q]) * g_inv,
+                       __uint_as_float(r[4 * q + 1]) * g_inv, __uint_as_float(r[4 * q + 2]) * g_inv,
+                       __uint_as_float(r[4 * q + 3]) * g_inv);
           } else {
-            red_add(gb0 + o, __uint_as_float(r[0]));
+            red_add(gb0 + o, __uint_as_float(r[0]) * g_inv);
           }
         }
         uint32_t r[16];
@@ -1946,7 +2025,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (use) {
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            if (c < n_out) red_add(gWo + (int64_t)c * TC_W + o, __uint_as_float(r[c]));
+            if (c < n_out) red_add(gWo + (int64_t)c * TC_W + o, __uint_as_float(r[c]) * g_inv);
         }
       }
       if (lane == 0) {
@@ -2036,10 +2115,18 @@ static int launch_dgrad_acc(const esr_mlp_desc_t *d, const TcLayout &T, const vo
   auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC, OVL, H16>;
   constexpr int bytes = BwdSm<K0, NH, DXN>::bytes + (H16 ? TC_TM * 4 : 0);
   if (int e = set_smem_tc(kern, bytes)) return e;
+  uint32_t *absmax = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_z) + act_dz_tail_offset(NH, mt));
+  if constexpr (H16) {   // max |d_y| of the launch -> the scale of the stored cotangents
+    ESR_CHECK_CUDA(cudaMemsetAsync(absmax, 0, 4, st));
+    const int64_t n = (re - rb) * d->n_out;
+    ESR_STAGE("k_absmax", st);
+    k_absmax<<<(unsigned)min((int64_t)num_sms() * 8, (int64_t)cdiv(n, 256)), 256, 0, st>>>(d_y + rb * d->n_out, n, absmax);
+    ESR_LAUNCH_OK();
+  }
   ESR_STAGE(K0 == 96 ? "k_mlp_dgrad_tc_radiance" : "k_mlp_dgrad_tc_tonemap", st);
   kern<<<tc_grid(re - rb), TC_THREADS, bytes, st>>>((const uint8_t *)image + T.bwd_off(), y, d_y, rb, re, mt,
                                                     (const __nv_bfloat16 *)hidden, (__nv_bfloat16 *)d_z, d_z_out, d_x,
-                                                    dx_cols, accumulate, d->n_out, d->act);
+                                                    dx_cols, accumulate, d->n_out, d->act, absmax);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -2154,6 +2241,10 @@ int tc_dgrad(const esr_mlp_desc_t *d, const void *tc_image, const float *y, cons
              int64_t row_end, int64_t m_total, const void *hidden, void *d_z, float *d_z_out, float *d_x, int dx_cols,
              int accumulate, cudaStream_t st) {
   const TcLayout T = tc_layout(d);
+  if (d->precision == 1 && d->k0 != 96) {
+    set_error("tc_dgrad: with precision 1 the tone-map net runs through esr_tonemap_mlp_bwd (fused kernel)");
+    return ESR_ERR_BAD_ARG;
+  }
   if (d->k0 == 96 && d->n_hidden == 3 && d->n_out <= 3)
     return launch_dgrad<96, 3, 64, 3>(d, T, tc_image, y, d_y, row_begin, row_end, m_total, hidden, d_z, d_z_out, d_x,
                                       dx_cols, accumulate, st);
@@ -2173,21 +2264,33 @@ int tc_wgrad(const esr_mlp_desc_t *d, const void *x, int64_t row_begin, int64_t 
   const int64_t ls = act_rows_padded(m_total) * TC_W;
   const int NH = d->n_hidden;
   const __nv_bfloat16 *H = (const __nv_bfloat16 *)hidden, *Z = (const __nv_bfloat16 *)d_z;
+  const uint32_t *absmax = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(d_z) + act_dz_tail_offset(NH, m_total));
   int e;
+  if (tc_layout(d).bwd_h16()) {   // precision 1: x (first tile set), H_l and the G-scaled dZ_l are fp16
+    if ((e = launch_wgrad<96, 24, true>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, TC_W, grad_flat + L.flat_w(0),
+                                        grad_flat + L.flat_b(0), absmax, st)))
+      return e;
+    for (int l = 1; l < NH; ++l)
+      if ((e = launch_wgrad<192, 24, true>(Z + l * ls, H + (l - 1) * ls, row_begin, row_end, TC_W, grad_flat + L.flat_w(l),
+                                           grad_flat + L.flat_b(l), absmax, st)))
+        return e;
+    return launch_wgrad<192, 2, true>(Z + NH * ls, H + (NH - 1) * ls, row_begin, row_end, d->n_out, grad_flat + L.flat_w(NH),
+                                      grad_flat + L.flat_b(NH), absmax, st);
+  }
   if (d->k0 == 96)
     e = launch_wgrad<96, 24>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, TC_W, grad_flat + L.flat_w(0),
-                             grad_flat + L.flat_b(0), st);
+                             grad_flat + L.flat_b(0), absmax, st);
   else
     e = launch_wgrad<48, 24>(Z, (const __nv_bfloat16 *)x, row_begin, row_end, TC_W, grad_flat + L.flat_w(0),
-                             grad_flat + L.flat_b(0), st);
+                             grad_flat + L.flat_b(0), absmax, st);
   if (e) return e;
   for (int l = 1; l < NH; ++l)
     if ((e = launch_wgrad<192, 24>(Z + l * ls, H + (l - 1) * ls, row_begin, row_end, TC_W, grad_flat + L.flat_w(l),
-                                   grad_flat + L.flat_b(l), st)))
+                                   grad_flat + L.flat_b(l), absmax, st)))
       return e;
   // output layer: A = dZ_out (tiled, 2 chunks per row, stored after the hidden-layer dZ), In = H_{NH-1}
   return launch_wgrad<192, 2>(Z + NH * ls, H + (NH - 1) * ls, row_begin, row_end, d->n_out, grad_flat + L.flat_w(NH),
-                              grad_flat + L.flat_b(NH), st);
+                              grad_flat + L.flat_b(NH), absmax, st);
 }
 
 }  // namespace esr

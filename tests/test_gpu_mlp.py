@@ -163,21 +163,26 @@ def _fp32_reference(desc, layers, x, d_y, rb, re):
 
 
 def _tile_with_residual(x):
-    """fp32 rows -> [bf16 tiles | fp16 residual tiles] as esr_encode_*_fwd(out_is_bf16 = 2) writes them"""
-    hi = x.to(torch.bfloat16)
+    """fp32 rows -> [fp16 tiles | fp16 residual tiles] as esr_encode_*_fwd(out_is_bf16 = 2) writes them"""
+    hi = x.to(torch.float16)
     lo = (x - hi.float()).to(torch.float16)
-    return torch.cat([_tile(hi), _tile(lo).view(torch.bfloat16)], 0)
+    return torch.cat([_tile(hi).view(torch.bfloat16), _tile(lo).view(torch.bfloat16)], 0)
 
 
-@pytest.mark.parametrize("m,rb,re,n_out,act", [(1000, 0, 1000, 3, 1), (128, 0, 128, 3, 1), (700, 130, 517, 3, 1),
-                                               (300, 0, 300, 5, 2), (40000, 0, 40000, 3, 1), (75000, 0, 75000, 3, 1)])
-def test_mlp_x2_forward_is_fp32_class_and_grads_within_1e2(m, rb, re, n_out, act):
+@pytest.mark.parametrize("m,rb,re,n_out,act,dy_scale",
+                         [(1000, 0, 1000, 3, 1, 1.0), (128, 0, 128, 3, 1, 1.0), (700, 130, 517, 3, 1, 1.0),
+                          (300, 0, 300, 5, 2, 1.0), (40000, 0, 40000, 3, 1, 1.0), (75000, 0, 75000, 3, 1, 1.0),
+                          # cotangents of a mean loss over 2^16 rays: ~1e-9, rows spread over four decades; and huge ones
+                          (3000, 0, 3000, 3, 1, 1e-9), (3000, 100, 2900, 5, 2, 3e7)])
+def test_mlp_x2_forward_is_fp32_class_and_grads_within_1e2(m, rb, re, n_out, act, dy_scale):
     desc = dict(fused.with_precision(fused.RADIANCE_DESC, 1), n_out=n_out, act=act)
     flat, layers = _flat_and_layers(desc, 3)
     g = torch.Generator().manual_seed(m + rb)
     x = torch.randn(m, 96, generator=g)
     x[:, 91:] = 0
     d_y = torch.randn(m, n_out, generator=g)
+    if dy_scale != 1.0:
+        d_y = d_y * dy_scale * 10.0 ** (-4.0 * torch.rand(m, 1, generator=g))
     y_ref, hid_ref, dx_ref, ws = _fp32_reference(desc, layers, x, d_y, rb, re)
 
     image = fused.mlp_pack(desc, flat.to(DEV))
@@ -191,10 +196,10 @@ def test_mlp_x2_forward_is_fp32_class_and_grads_within_1e2(m, rb, re, n_out, act
     rows = (m + 127) // 128 * 128
     flips = 0
     for l, h in enumerate(hid_ref):
-        h_l = hidden[l * rows * 192 * 2:(l + 1) * rows * 192 * 2].view(torch.bfloat16).reshape(rows, 192)
+        h_l = hidden[l * rows * 192 * 2:(l + 1) * rows * 192 * 2].view(torch.float16).reshape(rows, 192)
         got = _untile(h_l)[rb:re].float().cpu().double()
-        # bf16 copy of the exact value: half a bf16 ulp + the chain's own ~1e-6 absolute error
-        assert torch.allclose(got, h, rtol=1.02 * 2 ** -8, atol=1e-5), (l, (got - h).abs().max())
+        # fp16 copy of the exact value: half an fp16 ulp + the chain's own ~1e-6 absolute error
+        assert torch.allclose(got, h, rtol=1.02 * 2 ** -11, atol=1e-5), (l, (got - h).abs().max())
         flips += int(((got > 0) != (h > 0)).sum())
     assert flips <= 4 + (re - rb) * 192 * 3 // 50000, flips    # masks: those of the fp32 network to ~1e-5 (vs ~0.4 % flipped with bf16)
 
@@ -203,7 +208,7 @@ def test_mlp_x2_forward_is_fp32_class_and_grads_within_1e2(m, rb, re, n_out, act
     torch.cuda.synchronize()
     dx_ref = dx_ref[:, :56]
     l2 = ((d_x[rb:re].cpu().double() - dx_ref).norm() / dx_ref.norm()).item()
-    assert l2 < 1e-2, l2
+    assert l2 < 2e-3, l2                        # fp16 chain, row-scaled (the bf16 chain: ~4e-3)
     off = 0
     for i, (wt, b) in enumerate(ws):
         n_w, n_b = layers[i][0].numel(), layers[i][1].numel()
@@ -213,18 +218,23 @@ def test_mlp_x2_forward_is_fp32_class_and_grads_within_1e2(m, rb, re, n_out, act
         for got, ref in ((gw, wt.grad), (gb, b.grad)):
             mx = ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
             rel = ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
-            assert rel < 1e-2 and mx < 1e-2, (i, rel, mx)
+            # fp16 operands, fp32 sums: ~5e-4.  One ReLU mask on the other side of zero (|z| ~ 1e-6: fp32 summation order)
+            # moves one bias-gradient element by 1 / sqrt(rows) of its size — the max-norm carries that, at 1e-2
+            assert rel < 3e-3 and mx < 1e-2, (i, rel, mx)
 
 
-@pytest.mark.parametrize("m", [900, 128, 5000, 66000])
-def test_tonemap_x2_fused_kernels_vs_fp32_network(m):
+@pytest.mark.parametrize("m,dy_scale", [(900, 1.0), (128, 1.0), (5000, 1.0), (66000, 1.0), (5000, 1e-9), (40000, 3e7)])
+def test_tonemap_x2_fused_kernels_vs_fp32_network(m, dy_scale):
     """esr_tonemap_mlp_fwd / _bwd with precision 1 against the fp32 tone-map net (voxurff.py:783-788, pbr/module.py:24-39)"""
     desc = fused.with_precision(fused.TONEMAP_DESC, 1)
     flat, layers = _flat_and_layers(desc, 11)
     g = torch.Generator().manual_seed(m)
     lin = (torch.rand(m, 3, generator=g) * 3.0)
     d_rgb = torch.randn(m, 3, generator=g)
-    d_dir = torch.randn(m, 3, generator=g)
+    d_dir = 0.1 * torch.randn(m, 3, generator=g)
+    if dy_scale != 1.0:   # rows spread over four decades below dy_scale
+        row = dy_scale * 10.0 ** (-4.0 * torch.rand(m, 1, generator=g))
+        d_rgb, d_dir = d_rgb * row, d_dir * row
     # fp64 reference: PE(5) of lin -> 33 -> 192 -> 3 sigmoid; internal column order of the 48-wide row (16 per channel:
     # lin, sin x5, cos x5, 5 zeros) is the layout of W0 in the flat master copy
     lr = lin.double().clone().requires_grad_(True)
@@ -247,7 +257,7 @@ def test_tonemap_x2_fused_kernels_vs_fp32_network(m):
     d_lin, g_flat = fused._tonemap_bwd(lin_d, img, rgb, d_rgb.to(DEV), d_dir.to(DEV), desc)
     torch.cuda.synchronize()
     l2 = ((d_lin.cpu().double() - lr.grad).norm() / lr.grad.norm()).item()
-    assert l2 < 1e-2, l2
+    assert l2 < 3e-3, l2
     off = 0
     for i, (wt, b) in enumerate(ws):
         n_w, n_b = layers[i][0].numel(), layers[i][1].numel()
@@ -257,4 +267,5 @@ def test_tonemap_x2_fused_kernels_vs_fp32_network(m):
         for got, ref in ((gw, wt.grad), (gb, b.grad)):
             keep = ref != 0          # padded input columns / output rows carry no gradient
             rel = ((got - ref)[keep].norm() / ref[keep].norm().clamp_min(1e-30)).item()
-            assert rel < 1e-2, (i, rel)
+            mx = ((got - ref)[keep].abs().max() / ref[keep].abs().max().clamp_min(1e-300)).item()
+            assert rel < 3e-3 and mx < 3e-3, (i, rel, mx)   # fp16 operands (tolerance of the path: 1e-2)
