@@ -216,20 +216,16 @@ ESR_D uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrival on an mbarrier of the leader CTA, possibly from the peer.  Default semantics (release at CTA scope): what the
+// barrier hands over is TENSOR memory written by tcgen05.st, ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync
+// on this side and tcgen05.fence::after_thread_sync on the issuer's; no generic-proxy data crosses.  (A .release.cluster
+// arrive compiles to a membar that waits for every outstanding global store of the warp — the saved activations — and
+// was 30 % of this kernel's stall samples, profiles/r02b.)
 ESR_D void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 ESR_D void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // waits for arrivals that may come from the peer CTA
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
+  mbar_wait(bar, parity);
 }
 ESR_D void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {   // one warp of EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
