@@ -715,34 +715,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 // colour-grid gradients, and those gradients end up 2-5 % (relative L2) away from the reference's.  Carrying every
 // forward operand — input features, weights, hidden activations — as an fp16 pair hi + lo (22 significant bits) and
 // forming each product as hi.hi + hi.lo + lo.hi (fp32 accumulation in TMEM) makes the pre-activations, hence the
-// masks and the outputs, fp32-class; the backward kernels stay on single bf16 operands (their rounding errors are
-// zero-mean and average out over the samples): every parameter gradient within 1e-2 (measured 3e-3 .. 5e-3), outputs
-// ~1e-6.  Three times the MMA work of the bf16 chain, forward only.
+// masks and the outputs, fp32-class; the backward kernels run on single fp16 operands (their rounding errors are
+// zero-mean and average out over the samples): every parameter gradient within 1e-2 of the reference's (measured
+// <= 2.5e-3 max-norm, <= 1e-3 relative L2), outputs ~1e-6.  Three times the MMA work of the bf16 chain, forward only.
 //
 // How.  Two parts of every weight matrix do not fit one SM's shared memory (2 x 190 KB), so the chain runs on the two
-// SMs of a cluster of 2 with cta_group::2 MMAs (M = 256): CTA r holds rows [96 r, 96 r + 96) of every matrix (both
-// parts: 190 KB) as its half of the B operand and the 128 rows [256 t + 128 r, +128) of the pair's tile t in its own
-// TMEM; the leader CTA's issuer thread drives both tensor cores.  The A operand always comes from TMEM: the hidden
+// SMs of a cluster of 2 with cta_group::2 MMAs (M = 256): CTA r holds rows [96 r, 96 r + 96) of every hidden matrix
+// (both parts: 180 KB) as its half of the B operand and the 128 rows [256 t + 128 r, +128) of the pair's tile t in its
+// own TMEM; the leader CTA's issuer thread drives both tensor cores.  The A operand always comes from TMEM: the hidden
 // layers' epilogues write the (hi, lo) pair of the activation there, and layer 0's operand — the feature rows, stored
-// by the encoder as a bf16 tile (the one the weight-gradient GEMM reads) plus an fp16 tile of what that rounding lost —
-// is loaded into registers one tile ahead and stored to TMEM by the same threads (no x tile in shared memory).
-// TMEM columns: D [0,192) accumulator (one region suffices: every epilogue warp has read all of its D columns before
-// it arrives on the first chunk barrier), A_hi [192,288), A_lo [288,384), O [384,400) output-layer accumulator.
+// by the encoder as an fp16 tile (the one the weight-gradient GEMM reads) plus an fp16 tile of what that rounding lost —
+// is loaded into registers a layer ahead and stored to TMEM by the same threads (no x tile in shared memory).
+// TMEM columns: two accumulator regions D0 [0,192) / D1 [192,384) used by alternate MMA groups, X_hi [384,432) /
+// X_lo [432,480) layer 0's operand.  The A operand of a hidden layer is written IN PLACE over the accumulator it was made
+// from: a thread's 16-column accumulator chunk (K-step s = 3 g + c of the next layer) becomes 8 columns of fp16 hi and
+// 8 of fp16 lo — the same 16 columns, which only that thread reads, so there is no cross-thread hazard and no barrier.
+// Per tile the tensor cores run three MMA groups (layers 0, 1, 2); what keeps them busy between groups:
+//   * an epilogue reads its 48 accumulator columns chunk by chunk (tcgen05.ld of chunk c + 1 in flight while chunk c is
+//     converted), so the first K-steps of the next layer — which accumulate in the OTHER region — start a third of a
+//     TMEM read after the commit, not a whole one;
+//   * the OUTPUT layer (192 -> n_out <= 8) never goes to the tensor core: the last hidden epilogue holds relu(z) of its
+//     48 columns in fp32 registers and forms its part of the n_out dot products there (Wo in fp32 shared memory), the
+//     four column groups of a row meet in shared memory — no 16-wide MMA group, no commit round trip, no fourth epilogue;
+//   * layer 0 of the NEXT tile is issued under that last epilogue: its operand region is free once this tile's layer 0
+//     has committed, so the warps store the prefetched feature rows of the next tile there first thing and arrive, and
+//     the MMAs (into the region the last layer's operand occupied: the tensor core runs MMAs in issue order) run while
+//     the warps read, convert, save and reduce.
 // Synchronisation: the chunk barriers live in the leader CTA and count the 32 epilogue warps of both CTAs (the peer's
 // arrive through shared::cluster); every commit is multicast to the MMA barrier of both CTAs.
-constexpr uint32_t X2_D = 0, X2_A0 = 192, X2_A1 = 288, X2_O = 384;
+constexpr uint32_t X2_D = 0, X2_X0 = 384, X2_X1 = 432;
 
-template <int K0, int NH>
+template <int K0, int NH, int NO>
 struct X2Sm {
   static constexpr int HALF = TC_W / 2, OHALF = TC_NOUT_PAD / 2;
   static constexpr int w0_part = HALF * K0 * 2, wh_part = HALF * TC_W * 2, wo_part = OHALF * TC_W * 2;
   static constexpr int w0 = 0;
   static constexpr int wh = w0 + 2 * w0_part;
-  static constexpr int wo = wh + (NH - 1) * 2 * wh_part;
-  static constexpr int rank_bytes = wo + 2 * wo_part;            // == TcLayout::x2_rank_bytes()
-  static constexpr int bias = rank_bytes;
+  static constexpr int wo_img = wh + (NH - 1) * 2 * wh_part;          // offset of [Wo hi | Wo lo] in a rank section of the image
+  static constexpr int rank_bytes = wo_img + 2 * wo_part;             // == TcLayout::x2_rank_bytes()
+  static constexpr int wo32 = wo_img;                                  // shared memory: Wo as f32 [8][192] instead
+  static constexpr int bias = wo32 + 8 * TC_W * 4;
   static constexpr int bias_bytes = (NH * TC_W + TC_NOUT_PAD) * 4;
-  static constexpr int bar = (bias + bias_bytes + 15) / 16 * 16;   // bar_mma, bar_chunk[3] (8 B each), TMEM slot
+  static constexpr int part = (bias + bias_bytes + 15) / 16 * 16;     // output partial sums f32 [4 groups][128 rows][NO]
+  static constexpr int bar = part + 4 * TC_TM * NO * 4;               // bar_mma, bar_chunk[3] (8 B each), TMEM slot
   static constexpr int bytes = bar + 64;
 };
 
@@ -753,7 +768,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                  float *__restrict__ y, __nv_bfloat16 *__restrict__ hidden, int64_t save_begin, int n_out, int act) {
   static_assert(K0 == 96, "x chunks per column group: K0 / 32");
   extern __shared__ __align__(128) uint8_t smem[];
-  using S = X2Sm<K0, NH>;
+  using S = X2Sm<K0, NH, NO>;
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_epi = warp < TC_EPI_WARPS, is_issuer = warp == TC_EPI_WARPS;
   const uint32_t rank = cluster_ctarank();
@@ -761,8 +776,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const uint32_t bar = sbase + S::bar, bar_chunk = bar + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::bar + 32);
 
-  stage_bytes(smem, image_x2 + (int64_t)rank * S::rank_bytes, S::rank_bytes);
+  stage_bytes(smem, image_x2 + (int64_t)rank * S::rank_bytes, S::wo_img);   // this rank's halves of W0, W1, W2 (hi | lo)
   stage_bytes(smem + S::bias, image_x2 + 2 * (int64_t)S::rank_bytes, S::bias_bytes);
+  {  // Wo (rows 0..7: rank 0's half of the padded 16) as f32 = (hi + lo) / scale, row-major [8][192]
+    const __half *wo_hi = reinterpret_cast<const __half *>(image_x2 + S::wo_img), *wo_lo = wo_hi + S::wo_part / 2;
+    float *w32 = reinterpret_cast<float *>(smem + S::wo32);
+    for (int i = threadIdx.x; i < 8 * TC_W; i += blockDim.x) {
+      const int o = i / TC_W, in = i % TC_W;
+      const int64_t at = chunk_index(S::OHALF, o, in);
+      w32[i] = (__half2float(wo_hi[at]) + __half2float(wo_lo[at])) * (1.f / TC_WSCALE);
+    }
+  }
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
 #pragma unroll
@@ -776,6 +800,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
+  const float *wo32 = reinterpret_cast<const float *>(smem + S::wo32);
+  float *part = reinterpret_cast<float *>(smem + S::part);
 
   const int64_t n_pt = (row_end - row_begin + 2 * TC_TM - 1) / (2 * TC_TM);   // tiles of the pair: 256 rows
   const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -804,18 +830,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cbar_chunk + 8 * cc);
     };
-    load_x(pair);
-    for (int64_t pt = pair; pt < n_pt; pt += n_pairs) {
-      const int64_t row = row_begin + (2 * pt + rank) * TC_TM + t;
-      const bool valid = row < row_end;
-      const bool save = valid && hidden && row >= save_begin;
-      const bool save_w = __any_sync(FULL, save);
-      // ---- layer-0 operand -> TMEM (A_hi = the fp16 tile, A_lo = the residual tile) ----
+    auto store_x = [&]() {   // layer-0 operand -> TMEM (X_hi = the fp16 tile, X_lo = the residual tile); all three chunks
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         const uint32_t col = 4 * (3 * et.grp + i);
-        tmem_st4(tmem + et.lane_base + X2_A0 + col, xb[i].x, xb[i].y, xb[i].z, xb[i].w);
-        tmem_st4(tmem + et.lane_base + X2_A1 + col, xl[i].x, xl[i].y, xl[i].z, xl[i].w);
+        tmem_st4(tmem + et.lane_base + X2_X0 + col, xb[i].x, xb[i].y, xb[i].z, xb[i].w);
+        tmem_st4(tmem + et.lane_base + X2_X1 + col, xl[i].x, xl[i].y, xl[i].z, xl[i].w);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -824,21 +844,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) mbar_arrive_cluster(cbar_chunk + 8 * cc);
       }
+    };
+    load_x(pair);
+    if (pair < n_pt) store_x();
+    uint32_t dsel = 0;   // accumulator region of the MMA group whose commit comes next
+    for (int64_t pt = pair; pt < n_pt; pt += n_pairs) {
+      const int64_t row = row_begin + (2 * pt + rank) * TC_TM + t;
+      const bool valid = row < row_end;
+      const bool save = valid && hidden && row >= save_begin;
+      const bool save_w = __any_sync(FULL, save);
+      const bool more = pt + n_pairs < n_pt;
 #pragma unroll 1
       for (int l = 0; l < NH; ++l) {
-        if (l == NH - 1) load_x(pt + n_pairs);   // next tile's feature rows: in flight under the rest of this tile
+        const bool last = l == NH - 1;
+        if (l == NH - 2) load_x(pt + n_pairs);   // next tile's feature rows: a whole layer ahead of their use
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
         const float *b = sbias + l * TC_W;
         uint4 *hl = hidden ? reinterpret_cast<uint4 *>(hidden + (int64_t)l * act_rows_padded(m_total) * TC_W) : nullptr;
         uint32_t r[3][16];
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + X2_D + TC_GCOLS * et.grp + 16 * cc, r[cc]);
-        tmem_ld_wait();
         uint32_t mask[2] = {0u, 0u};
+        float2 acc[NO];
+#pragma unroll
+        for (int c = 0; c < NO; ++c) acc[c] = make_float2(0.f, 0.f);
+        const uint32_t d_cols = tmem + et.lane_base + X2_D + TC_W * dsel + TC_GCOLS * et.grp;
+        dsel ^= 1;
+        // layer 0's operand region is free (this tile's layer 0 committed long ago) and every warp is past the chunk
+        // barriers' previous phase: the next tile's layer 0 is released now and runs under this epilogue
+        if (last && more) store_x();
+        tmem_ld16(d_cols, r[0]);
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
+          tmem_ld_wait();   // chunk cc is converted while chunk cc + 1 is still coming out of TMEM
+          if (cc < 2) tmem_ld16(d_cols + 16 * (cc + 1), r[cc + 1]);
           const int col0 = TC_GCOLS * et.grp + 16 * cc;
           uint32_t ph[8], pl[8];
 #pragma unroll
@@ -846,7 +885,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             const float2 bb = *reinterpret_cast<const float2 *>(b + col0 + 2 * j);
             float z0 = __uint_as_float(r[cc][2 * j]), z1 = __uint_as_float(r[cc][2 * j + 1]);
             fma2(z0, z1, 1.f / TC_WSCALE, bb);
-            split2h_relu(z0, z1, ph[j], pl[j]);
+            if (last) {   // output layer on the CUDA cores: this thread's 48 columns of relu(z), exact fp32
+              ph[j] = pack2h_relu(z0, z1);
+              const float h0 = fmaxf(z0, 0.f), h1 = fmaxf(z1, 0.f);
+#pragma unroll
+              for (int c = 0; c < NO; ++c)
+                if (c < n_out) {
+                  const float2 w = *reinterpret_cast<const float2 *>(wo32 + c * TC_W + col0 + 2 * j);
+                  acc[c].x = fmaf(h0, w.x, acc[c].x);
+                  acc[c].y = fmaf(h1, w.y, acc[c].y);
+                }
+            } else {
+              split2h_relu(z0, z1, ph[j], pl[j]);
+            }
             if (save_w) {   // masks for the data-gradient chain (same layout and bit trick as the bf16 chain: a non-zero
               // non-negative fp16 half is <= 0x7c00, plus 0x7fff carries into its top bit and never into the other half)
               const uint32_t tt = ph[j] + 0x7fff7fffu;
@@ -854,46 +905,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               mask[cc >> 1] |= (tt >> (15 - 8 * (cc & 1) - j)) & (one2 << (8 * (cc & 1) + j));
             }
           }
-          tmem_st8(tmem + et.lane_base + X2_A0 + col0 / 2, ph);
-          tmem_st8(tmem + et.lane_base + X2_A1 + col0 / 2, pl);
+          if (!last) {   // in place: the chunk's own 16 accumulator columns now hold its K-step of the next A operand
+            tmem_st8(d_cols + 16 * cc, ph);
+            tmem_st8(d_cols + 16 * cc + 8, pl);
+          }
           if (save) {   // the weight-gradient GEMM's operand: the fp16 hi part (same tiled layout as the bf16 chain's copy)
             hl[act_chunk_index(row, col0 / 8)] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
             hl[act_chunk_index(row, col0 / 8 + 1)] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
           }
-          arrive_chunk(cc);
+          if (!last) arrive_chunk(cc);
         }
         if (save) {
           uint2 *mb = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(hidden) + act_mask_base_bytes(NH, m_total));
           mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
         }
-      }
-      // ---- output layer epilogue (column group 0 threads); every warp observes the phase: the A regions are free ----
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      tc_fence_after();
-      if (et.grp == 0) {
-        uint32_t r[16];
-        tmem_ld16(tmem + et.lane_base + X2_O, r);
-        tmem_ld_wait();
-        if (valid) {
-          const float *bo = sbias + NH * TC_W;
+        if (last) {   // the four column groups of a row meet in shared memory; column group 0 finishes the row
 #pragma unroll
-          for (int c = 0; c < NO; ++c)
-            if (c < n_out) y[row * n_out + c] = act_fwd(__fmaf_rn(__uint_as_float(r[c]), 1.f / TC_WSCALE, bo[c]), act);
+          for (int c = 0; c < NO; ++c) part[(et.grp * TC_TM + t) * NO + c] = acc[c].x + acc[c].y;
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+          if (et.grp == 0 && valid) {
+            const float *bo = sbias + NH * TC_W;
+#pragma unroll
+            for (int c = 0; c < NO; ++c)
+              if (c < n_out) {
+                float z = bo[c];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) z += part[(g * TC_TM + t) * NO + c];
+                y[row * n_out + c] = act_fwd(z, act);
+              }
+          }
         }
       }
-      tc_fence_before();
     }
   } else if (is_issuer && rank == 0 && lane == 0) {
     uint32_t cphase = 0;
-    constexpr uint32_t idesc_h = make_idesc_h(TC_W, 2 * TC_TM), idesc_o = make_idesc_h(TC_NOUT_PAD, 2 * TC_TM);
+    constexpr uint32_t idesc_h = make_idesc_h(TC_W, 2 * TC_TM);
     // one K-step (16 features) of one product: hi.hi + hi.lo + lo.hi
-    auto product = [&](uint32_t dst, int s, uint32_t w_hi, uint32_t part_bytes, uint32_t rows16, uint32_t idesc, bool first) {
+    auto product = [&](uint32_t dst, uint32_t a_hi, uint32_t a_lo, int s, uint32_t w_hi, uint32_t part_bytes, uint32_t rows16,
+                       bool first) {
       const uint64_t bh = make_desc(w_hi + 2 * s * rows16, rows16, 128), bl = make_desc(w_hi + part_bytes + 2 * s * rows16, rows16, 128);
-      mma_ts2(dst, tmem + X2_A0 + 8 * s, bh, idesc, !first);
-      mma_ts2(dst, tmem + X2_A0 + 8 * s, bl, idesc, 1);
-      mma_ts2(dst, tmem + X2_A1 + 8 * s, bh, idesc, 1);
+      mma_ts2(dst, a_hi, bh, idesc_h, !first);
+      mma_ts2(dst, a_hi, bl, idesc_h, 1);
+      mma_ts2(dst, a_lo, bh, idesc_h, 1);
     };
+    uint32_t dsel = 0;   // accumulator region of the next MMA group
     for (int64_t pt = pair; pt < n_pt; pt += n_pairs) {
       // ---- layer 0: the feature rows the epilogue warps of both CTAs have put into TMEM ----
 #pragma unroll
@@ -902,28 +957,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         tc_fence_after();
 #pragma unroll
         for (int s = cc; s < K0 / 16; s += 3)
-          product(tmem + X2_D, s, sbase + S::w0, S::w0_part, S::HALF * 16, idesc_h, s == 0);
+          product(tmem + X2_D + TC_W * dsel, tmem + X2_X0 + 8 * s, tmem + X2_X1 + 8 * s, s, sbase + S::w0, S::w0_part, S::HALF * 16,
+                  s == 0);
       }
       mma_commit2(bar);
       cphase ^= 1;
 #pragma unroll 1
-      for (int l = 0; l < NH; ++l) {
-        const bool last = l + 1 == NH;
-        const uint32_t dst = tmem + (last ? X2_O : X2_D);
-        const uint32_t wl = last ? sbase + S::wo : sbase + S::wh + l * (2 * S::wh_part);
-        const uint32_t part = last ? S::wo_part : S::wh_part;
-        const uint32_t rows16 = (last ? S::OHALF : S::HALF) * 16;
-        const uint32_t idesc = last ? idesc_o : idesc_h;
+      for (int l = 0; l + 1 < NH; ++l) {   // hidden layers 1 .. NH - 1 (the output layer runs on the CUDA cores)
+        const uint32_t wl = sbase + S::wh + l * (2 * S::wh_part);
+        const uint32_t a = tmem + X2_D + TC_W * dsel;   // operand: in place over the previous group's accumulator
+        dsel ^= 1;
+        const uint32_t dst = tmem + X2_D + TC_W * dsel;
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           mbar_wait_cluster(bar_chunk + 8 * cc, cphase);
           tc_fence_after();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) product(dst, 3 * g + cc, wl, part, rows16, idesc, (cc | g) == 0);
+          for (int g = 0; g < 4; ++g) {
+            const int s = 3 * g + cc;
+            product(dst, a + 16 * s, a + 16 * s + 8, s, wl, S::wh_part, S::HALF * 16, (cc | g) == 0);
+          }
         }
         mma_commit2(bar);
         cphase ^= 1;
       }
+      dsel ^= 1;   // the next tile's layer 0 accumulates in the region the last hidden layer's operand occupied
     }
   }
   tc_fence_before();
@@ -2079,7 +2137,7 @@ template <int K0, int NH, int NO>
 static int launch_fwd_x2(const esr_mlp_desc_t *d, const TcLayout &T, const void *image, const void *x, int64_t rb, int64_t re,
                          int64_t mt, float *y, void *hidden, int64_t save_begin, cudaStream_t st) {
   auto kern = k_mlp_fwd_x2<K0, NH, NO>;
-  using S = X2Sm<K0, NH>;
+  using S = X2Sm<K0, NH, NO>;
   if (T.x2_rank_bytes() != S::rank_bytes) {
     set_error("x2 forward: image layout mismatch");
     return ESR_ERR_BAD_ARG;
