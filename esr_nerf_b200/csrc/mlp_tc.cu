@@ -756,8 +756,8 @@ struct X2Sm {
   static constexpr int wo32 = wo_img;                                  // shared memory: Wo as f32 [8][192] instead
   static constexpr int bias = wo32 + 8 * TC_W * 4;
   static constexpr int bias_bytes = (NH * TC_W + TC_NOUT_PAD) * 4;
-  static constexpr int part = (bias + bias_bytes + 15) / 16 * 16;     // output partial sums f32 [4 groups][128 rows][NO]
-  static constexpr int bar = part + 4 * TC_TM * NO * 4;               // bar_mma, bar_chunk[3] (8 B each), TMEM slot
+  static constexpr int part = (bias + bias_bytes + 15) / 16 * 16;     // output partial sums f32 [2 tiles][4 groups][128 rows][NO]
+  static constexpr int bar = part + 2 * 4 * TC_TM * NO * 4;           // bar_mma, bar_chunk[3] (8 B each), TMEM slot
   static constexpr int bytes = bar + 64;
 };
 
@@ -801,7 +801,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem = *tmem_slot;
   const float *sbias = reinterpret_cast<const float *>(smem + S::bias);
   const float *wo32 = reinterpret_cast<const float *>(smem + S::wo32);
-  float *part = reinterpret_cast<float *>(smem + S::part);
+  float *part_buf = reinterpret_cast<float *>(smem + S::part);
 
   const int64_t n_pt = (row_end - row_begin + 2 * TC_TM - 1) / (2 * TC_TM);   // tiles of the pair: 256 rows
   const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -854,6 +854,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const bool save = valid && hidden && row >= save_begin;
       const bool save_w = __any_sync(FULL, save);
       const bool more = pt + n_pairs < n_pt;
+      // partial sums of alternate tiles use alternate buffers (the next tile's writes are ordered behind this tile's reads
+      // through the chunk barriers and the MMAs already; the second buffer makes that visible to racecheck as well)
+      float *part = part_buf + (((pt - pair) / n_pairs) & 1) * (4 * TC_TM * NO);
 #pragma unroll 1
       for (int l = 0; l < NH; ++l) {
         const bool last = l == NH - 1;
@@ -1237,7 +1240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // step (read before the arrival on bar_x), not of d_x
   static_assert(!OVL || (NH & 1), "tile overlap: odd number of hidden layers (the d_x accumulator lives in D1)");
   static_assert(!(OVL && H16), "the fp16 chain is instantiated without the tile overlap");
-  [[maybe_unused]] float *s_inv = reinterpret_cast<float *>(smem + S::bytes);   // H16: 1 / s_r of the tile's rows
+  [[maybe_unused]] float *s_inv_buf = reinterpret_cast<float *>(smem + S::bytes);   // H16: 1 / s_r of the rows, [2 tiles][128]
   constexpr uint32_t idesc_w = H16 ? make_idesc_h(TC_W) : make_idesc(TC_W);
   constexpr uint32_t idesc_x = H16 ? make_idesc_h(DXN) : make_idesc(DXN);
 
@@ -1319,6 +1322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool valid = is_epi && row < row_end;
+    // alternate tiles use alternate halves (the next tile's write is ordered behind this tile's reads through the chunk
+    // barriers and the MMAs; the second half makes that visible to racecheck as well)
+    [[maybe_unused]] float *s_inv = s_inv_buf + (((tile - blockIdx.x) / gridDim.x) & 1) * TC_TM;
     uint2 cur_mask[NH];
 #pragma unroll
     for (int l = 0; l < NH; ++l) cur_mask[l] = pf_mask[l];
@@ -2167,7 +2173,7 @@ static int launch_dgrad_acc(const esr_mlp_desc_t *d, const TcLayout &T, const vo
                                                           accumulate, st);
   }
   auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC, OVL, H16>;
-  constexpr int bytes = BwdSm<K0, NH, DXN>::bytes + (H16 ? TC_TM * 4 : 0);
+  constexpr int bytes = BwdSm<K0, NH, DXN>::bytes + (H16 ? 2 * TC_TM * 4 : 0);
   if (int e = set_smem_tc(kern, bytes)) return e;
   uint32_t *absmax = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_z) + act_dz_tail_offset(NH, mt));
   if constexpr (H16) {   // max |d_y| of the launch -> the scale of the stored cotangents

@@ -121,9 +121,6 @@ def test_esrnerf_port_as_live_oracle_on_new_rays():
         assert C.rel_err(out[k], ref[k]) < (1e-4 if k in FP32_KEYS else 1e-2), k
 
 
-@pytest.mark.skipif(not os.environ.get("ESR_TEST_UNVERIFIED"),
-                    reason="written after round 1's GPU budget was spent: run with ESR_TEST_UNVERIFIED=1 "
-                           "(scripts/gpu_followup.sh) before it joins the default suite")
 @pytest.mark.parametrize("ray_sampling,env_activation", [("fib", "softplus"), ("random", "relu"), ("fib", "sigmoid")])
 def test_esrnerf_other_samplers_and_envmaps_vs_port(ray_sampling, env_activation):
     """`ray_sampling: fib` (no random draw for the directions) and the other environment-map activations

@@ -211,9 +211,6 @@ def test_mask_class_table_leaves_march_streams_identical(kind):
     assert torch.equal(a.s_sdf.view(torch.int32), b.s_sdf.view(torch.int32))   # bit-identical, NaN-safe
 
 
-@pytest.mark.skipif(not os.environ.get("ESR_TEST_UNVERIFIED"),
-                    reason="esr_grad_block_flags was written after round 1's GPU budget was spent: run with "
-                           "ESR_TEST_UNVERIFIED=1 (scripts/gpu_followup.sh) before it joins the default suite")
 @pytest.mark.parametrize("shape", [(16, 24, 20), (64, 64, 64), (7, 9, 11)])
 def test_grad_block_flags_kernel_vs_torch(shape, monkeypatch):
     """esr_grad_block_flags (one warp per volume x block) against the torch reduction of the same map, and the voxel
