@@ -10,6 +10,7 @@ import ctypes
 import os
 import shutil
 import subprocess
+import sys
 from typing import Optional
 
 import torch
@@ -43,9 +44,25 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into esr_nerf_b200/libesr_b200.so."""
+    """Compile every CUDA source for sm_100a into esr_nerf_b200/libesr_b200.so.  Safe under torchrun: the stale check and
+    the build run under an exclusive file lock, objects and the library are written to temporary names and renamed into
+    place, so a rank never links or loads a half-written file (the ranks that waited find the library fresh)."""
     if not force and not _stale():
         return LIB_PATH
+    import fcntl
+
+    os.makedirs(os.path.join(PKG_DIR, "build"), exist_ok=True)
+    with open(os.path.join(PKG_DIR, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another process built it while this one waited for the lock
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     if nvcc is None:
         if os.path.isfile(LIB_PATH):
@@ -56,7 +73,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(build_dir, s.replace(".cu", ".o"))
+        o = os.path.join(build_dir, s.replace(".cu", f".{os.getpid()}.o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             print(" ".join(cmd))
@@ -68,10 +85,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise EsrError(f"nvcc failed on {s}:\n{out}")
         if verbose and out.strip():
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp_lib = f"{LIB_PATH}.{os.getpid()}.tmp"
+    cmd = [nvcc, "-shared", "-o", tmp_lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    for o in objs:
+        if os.path.isfile(o):
+            os.remove(o)
     if r.returncode != 0:
         raise EsrError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, LIB_PATH)
+    print(f"[esr_nerf_b200] compiled {len(SOURCES)} CUDA sources for sm_100a -> {LIB_PATH}", file=sys.stderr)
     return LIB_PATH
 
 

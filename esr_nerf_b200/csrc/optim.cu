@@ -13,12 +13,15 @@ struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay;
   float step_size;       // lr / (1 - beta1^step)
   float inv_sqrt_bc2;    // 1 / sqrt(1 - beta2^step)
+  // 1 - beta formed in double on the host and rounded ONCE, as the Python floats the reference passes for alpha / value
+  // (optimizer.py:213-214); 1.f - beta1 in float differs in the last place (9e-7 relative for beta2 = 0.99)
+  float one_minus_beta1, one_minus_beta2;
 };
 
 ESR_D void adam_one(float &p, float g, float &m, float &v, float per_lr, const AdamArgs &a) {
   if (a.weight_decay != 0.f) g = __fmaf_rn(a.weight_decay, p, g);
-  m = __fmaf_rn(1.f - a.beta1, g, m * a.beta1);                 // exp_avg.mul_(beta1).add_(grad, alpha=1-beta1)
-  v = __fmaf_rn((1.f - a.beta2) * g, g, v * a.beta2);           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+  m = __fmaf_rn(a.one_minus_beta1, g, m * a.beta1);             // exp_avg.mul_(beta1).add_(grad, alpha=1-beta1)
+  v = __fmaf_rn(a.one_minus_beta2 * g, g, v * a.beta2);         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
   const float denom = sqrtf(v) * a.inv_sqrt_bc2 + a.eps;        // (exp_avg_sq.sqrt() / sqrt(bias_correction2)).add_(eps)
   p = __fmaf_rn(-a.step_size, __fdiv_rn(m * per_lr, denom), p);  // param.addcdiv_(exp_avg * per_lr, denom, value=-step_size)
 }
@@ -61,6 +64,8 @@ extern "C" int esr_adam_step(float *param, const float *grad, float *exp_avg, fl
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   a.step_size = (float)((double)lr / bc1);
   a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  a.one_minus_beta1 = (float)(1.0 - (double)beta1);
+  a.one_minus_beta2 = (float)(1.0 - (double)beta2);
   const int64_t want = (n / 4 + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 8;
   ESR_STAGE("k_adam_step", stream);

@@ -27,15 +27,25 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[s
 
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int:
     """Sum every parameter gradient over the ranks (losses are written as sums over rays / the global ray count, so
-    a plain sum reproduces the single-process gradient).  Parameters a rank did not touch contribute zeros.
+    a plain sum reproduces the single-process gradient).  A parameter some rank did not touch contributes zeros there;
+    a parameter NO rank touched (e.g. envmap / brdf in a step without LTS points) keeps `grad = None` on every rank, so
+    that the optimizer skips it exactly as the single-process run does (optimizer.py:74: no step count, no moment
+    decay) — found with one small all-reduce(max) of a has-gradient vector and one host read.
     Returns the number of bytes reduced."""
     import torch.distributed as dist
 
-    nbytes = 0
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return 0
+    dev = next((p.grad.device for p in params if p.grad is not None), params[0].device)
+    has = torch.tensor([p.grad is not None for p in params], dtype=torch.int32, device=dev)
+    dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
+    has = has.tolist()
+    nbytes = 4 * len(params)
     small = []  # the MLP weights / biases (~1 MB in ~20 tensors): one flat bucket, one collective
-    for p in params:
-        if not p.requires_grad:
-            continue
+    for p, any_rank in zip(params, has):
+        if not any_rank:
+            continue            # untouched everywhere: stays None
         if p.grad is None:
             p.grad = torch.zeros_like(p)
         nbytes += p.grad.numel() * p.grad.element_size()
@@ -75,6 +85,7 @@ class GridGradCompactor:
         self.grids = [model.sdf.grid, model.off_color.grid, model.emo_color.grid]
         self._idx32 = None
         self._early = None      # (work handle, packed buffer, gradient buffers) of a colour all-reduce already in flight
+        self._early_stale = False   # a later backward pass added to the colour gradients after the early exchange left
         self._overlap = False
         self.group = None
 
@@ -96,7 +107,14 @@ class GridGradCompactor:
         import torch.distributed as dist
 
         params = self.grids[1:]
-        if self._early is not None or any(p.grad is not None for p in params):
+        if self._early is not None:
+            # a second backward pass before allreduce() (gradient accumulation): the gradient sink adds to the buffers the
+            # early exchange packed IN PLACE (same data_ptr), so what is in flight is only the first micro-batch — marked
+            # here, redone in full by allreduce().  Every rank runs the same number of backward passes, so the collective
+            # sequence stays rank-independent.
+            self._early_stale = True
+            return
+        if any(p.grad is not None for p in params):
             return          # gradient accumulation across calls: the exchange happens at the end, on every rank alike
         grads = [bufs[p] if p in bufs else torch.zeros_like(p) for p in params]
         buf = self.pack([self._rows(g) for g in grads], "_cbuf")
@@ -186,6 +204,7 @@ class GridGradCompactor:
         if self._early is None and self._overlap and all(p.grad is None for p in color):
             self._on_color_grads({})     # this rank's backward never reached the hook: same collective, zeros, now
         early, self._early = self._early, None
+        stale, self._early_stale = self._early_stale, False
         if early is not None:
             for p, b in zip(color, early[2]):
                 if p.grad is None:       # a volume this rank did not touch: the zeros that went into the exchange
@@ -196,8 +215,8 @@ class GridGradCompactor:
         grid_ids = {id(p) for p in self.grids}
         others = [p for p in self.model.parameters() if id(p) not in grid_ids]
         nbytes = allreduce_gradients(others, group)      # the small MLP bucket first: it is ready and tiny
-        if early is not None and all(p.grad is not None and p.grad.data_ptr() == b.data_ptr()
-                                     for p, b in zip(self.grids[1:], early[2])):
+        if early is not None and not stale and all(p.grad is not None and p.grad.data_ptr() == b.data_ptr()
+                                                   for p, b in zip(self.grids[1:], early[2])):
             # the colour volumes are already on their way (started inside the backward pass): SDF grid now, then join
             work, cbuf, _ = early
             sbuf = self.pack(rows[:1], "_sbuf")

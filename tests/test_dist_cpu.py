@@ -35,8 +35,15 @@ def _worker(rank, world, port, out):
     pred = net(torch.cat([local["rays_o"], local["rays_d"]], -1))
     loss = ((pred - local["rgbs"]) ** 2).sum() / n           # sum over local rays / GLOBAL ray count
     loss.backward()
-    nbytes = D.allreduce_gradients(list(net.parameters()) + [frozen])
-    assert nbytes == sum(p.numel() * 4 for p in net.parameters())
+    # `unused` received no gradient on any rank, `half_used` only on rank 1: the first stays None (the optimizer must skip
+    # it as the single-process run does), the second is summed with zeros from rank 0
+    unused = torch.nn.Parameter(torch.ones(5))
+    half_used = torch.nn.Parameter(torch.ones(4))
+    if rank == 1:
+        half_used.grad = torch.full((4,), 3.0)
+    nbytes = D.allreduce_gradients(list(net.parameters()) + [frozen, unused, half_used])
+    assert nbytes == sum(p.numel() * 4 for p in net.parameters()) + 4 * 4 + 4 * (len(list(net.parameters())) + 2)
+    assert unused.grad is None and torch.equal(half_used.grad, torch.full((4,), 3.0))
     if rank == 0:
         ref = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
         ref.load_state_dict(net.state_dict())
@@ -110,7 +117,8 @@ def _compactor_worker(rank, world, port, out):
         p.grad = v.clone()
         grads.append(v)
     nbytes = comp.allreduce(verify=True)
-    assert nbytes == 4 * (sum(p.numel() for p in model.head.parameters()) + 2 * ((comp.idx.numel() * 13 + 2) // 2))
+    assert nbytes == 4 * (sum(p.numel() for p in model.head.parameters()) + 2 * ((comp.idx.numel() * 13 + 2) // 2)
+                          + len(list(model.head.parameters())))        # + the has-gradient vector
     g2 = torch.Generator().manual_seed(10 + (1 - rank))
     err = 0.0
     for p, mine in zip(model.parameters(), grads):
@@ -164,6 +172,28 @@ def _compactor_worker(rank, world, port, out):
                 if rank == 0 and (case == "B" or p is color[1]) and any(p is c for c in color):
                     other = other * 0          # what rank 1 left out
             err = max(err, (p.grad - (m + other)).abs().max().item())
+    # gradient accumulation with the early start on: the first backward's hook starts the exchange, the second backward
+    # adds to the SAME buffers in place (what fused._GradSink.flush does: p.grad.add_) and calls the hook again — what is
+    # in flight is stale, allreduce() must redo the exchange with the accumulated gradients
+    for p, mine in zip(model.parameters(), grads):
+        p.grad = None if any(p is c for c in color) else 2 * mine.clone()
+    bufs = {p: mine.clone() for p, mine in zip(model.parameters(), grads) if any(p is c for c in color)}
+    comp._on_color_grads(bufs)
+    for p in color:
+        p.grad = bufs[p]
+    assert comp._early is not None and not comp._early_stale
+    for p in color:
+        p.grad.add_(bufs[p].clone())                          # second micro-batch, accumulated in place
+    comp._on_color_grads({p: p.grad for p in color})
+    assert comp._early_stale
+    comp.allreduce()
+    assert comp._early is None and not comp._early_stale
+    g5 = torch.Generator().manual_seed(10 + (1 - rank))
+    for p, mine in zip(model.parameters(), grads):
+        other = torch.randn(p.shape, generator=g5)
+        if p.dim() == 5:
+            other = other * comp.mask
+        err = max(err, (p.grad - 2 * (mine + other)).abs().max().item())
     out.put(err)
     dist.barrier()
     dist.destroy_process_group()
