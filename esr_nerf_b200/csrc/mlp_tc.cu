@@ -470,11 +470,21 @@ ESR_D void tonemap_pe_channel(float x, uint4 &lo, uint4 &hi, float (&sn)[5], flo
   hi = make_uint4(pack2(cs[2], cs[3]), pack2(cs[4], 0.f), 0u, 0u);
 }
 
-// x2 variant: the same 16 columns as fp16 hi + lo pairs (chunks hl / hh and ll / lh); accurate sines / cosines (the SFU
-// versions err by ~2^-21 absolute, more for large arguments — the size of the lo part)
+// sin / cos of y to ~2^-21 ABSOLUTE at a fifth of sincosf's instructions: two-constant Cody-Waite reduction of y to
+// [-pi, pi] (exact to ~1e-7 for the |y| <= ~100 the encoding sees: lin in [0, ~3] times 2^f <= 16), then the SFU sine /
+// cosine, whose error on that interval is 2^-21.4.  The feature error (~4e-7) moves a pre-activation by as much relative
+// to its scale: a ReLU mask in ~3e-7 — below what fp32 summation order already does (tests/test_gpu_mlp.py).
+ESR_D void sincos_reduced(float y, float &s, float &c) {
+  const float k = rintf(y * 0.15915494309189535f);          // y / 2 pi
+  float r = fmaf(k, -6.28318548202514648f, y);                // 2 pi = hi + lo, hi = fp32(2 pi)
+  r = fmaf(k, 1.74845553e-7f, r);                             // hi - 2 pi = 1.74845553e-7
+  s = __sinf(r);
+  c = __cosf(r);
+}
+// x2 variant: the same 16 columns as fp16 hi + lo pairs (chunks hl / hh and ll / lh)
 ESR_D void tonemap_pe_channel_x2(float x, uint4 &hl, uint4 &hh, uint4 &ll, uint4 &lh, float (&sn)[5], float (&cs)[5]) {
 #pragma unroll
-  for (int f = 0; f < 5; ++f) sincosf(__fmul_rn(x, (float)(1 << f)), &sn[f], &cs[f]);
+  for (int f = 0; f < 5; ++f) sincos_reduced(__fmul_rn(x, (float)(1 << f)), sn[f], cs[f]);
   uint32_t h[6], l[6];
   split2h(x, sn[0], h[0], l[0]);
   split2h(sn[1], sn[2], h[1], l[1]);
@@ -854,13 +864,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const bool save = valid && hidden && row >= save_begin;
       const bool save_w = __any_sync(FULL, save);
       const bool more = pt + n_pairs < n_pt;
-      // partial sums of alternate tiles use alternate buffers (the next tile's writes are ordered behind this tile's reads
-      // through the chunk barriers and the MMAs already; the second buffer makes that visible to racecheck as well)
-      float *part = part_buf + (((pt - pair) / n_pairs) & 1) * (4 * TC_TM * NO);
 #pragma unroll 1
       for (int l = 0; l < NH; ++l) {
         const bool last = l == NH - 1;
-        if (l == NH - 2) load_x(pt + n_pairs);   // next tile's feature rows: a whole layer ahead of their use
+        // next tile's feature rows: a whole layer ahead of their use (requested only before the last layer's wait they
+        // cost 0.2 ms per step: the store to TMEM right after that wait then stalls on them)
+        if (l == NH - 2) load_x(pt + n_pairs);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
@@ -923,6 +932,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           mb[act_mask_index(l, act_rows_padded(m_total), row, et.grp)] = make_uint2(mask[0], mask[1]);
         }
         if (last) {   // the four column groups of a row meet in shared memory; column group 0 finishes the row
+          // Alternate tiles use alternate buffers — `dsel` flips once per tile at this point (NH is odd) — although the
+          // next tile's writes are ordered behind this tile's reads through the chunk barriers and the MMAs already: the
+          // second buffer makes that visible to racecheck as well, at no register cost.
+          static_assert(NH & 1, "tile parity from dsel");
+          float *part = part_buf + dsel * (4 * TC_TM * NO);
 #pragma unroll
           for (int c = 0; c < NO; ++c) part[(et.grp * TC_TM + t) * NO + c] = acc[c].x + acc[c].y;
           asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
@@ -1240,7 +1254,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // step (read before the arrival on bar_x), not of d_x
   static_assert(!OVL || (NH & 1), "tile overlap: odd number of hidden layers (the d_x accumulator lives in D1)");
   static_assert(!(OVL && H16), "the fp16 chain is instantiated without the tile overlap");
-  [[maybe_unused]] float *s_inv_buf = reinterpret_cast<float *>(smem + S::bytes);   // H16: 1 / s_r of the rows, [2 tiles][128]
+  // H16: 1 / s_r of the tile's rows.  Written by column group 0 at the top of a tile, read by every epilogue thread right
+  // after the tile's first __syncthreads; the next tile's write is ordered behind those reads through the chunk
+  // barriers -> tcgen05.mma -> commit -> the writer's own d_x epilogue wait (racecheck, which does not follow that
+  // chain, reports it as a hazard: profiles/r02_sanitizer).  A second buffer costs the kernel a register it does not have.
+  [[maybe_unused]] float *s_inv = reinterpret_cast<float *>(smem + S::bytes);
   constexpr uint32_t idesc_w = H16 ? make_idesc_h(TC_W) : make_idesc(TC_W);
   constexpr uint32_t idesc_x = H16 ? make_idesc_h(DXN) : make_idesc(DXN);
 
@@ -1322,9 +1340,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = row_begin + tile * TC_TM + t;
     const bool valid = is_epi && row < row_end;
-    // alternate tiles use alternate halves (the next tile's write is ordered behind this tile's reads through the chunk
-    // barriers and the MMAs; the second half makes that visible to racecheck as well)
-    [[maybe_unused]] float *s_inv = s_inv_buf + (((tile - blockIdx.x) / gridDim.x) & 1) * TC_TM;
     uint2 cur_mask[NH];
 #pragma unroll
     for (int l = 0; l < NH; ++l) cur_mask[l] = pf_mask[l];
@@ -1837,10 +1852,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   int it = 0;
   [[maybe_unused]] float g_scale = 1.f, g_inv = 1.f;
   if constexpr (X2) {   // first pass: max |d_y| over the rows of this CTA's tiles (|act'| <= 1: a bound on every |dZ_out|)
+    // (one 16-byte load per thread per tile — a tile's 128 x n_out floats start 16-byte aligned — and four tiles in flight:
+    // a scalar loop over one tile at a time spent 50 us here waiting on one load after another)
     float mx = 0.f;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t base = tile * TC_TM * n_out, end = min(base + (int64_t)TC_TM * n_out, m * n_out);
-      for (int64_t i = base + threadIdx.x; i < end; i += blockDim.x) mx = fmaxf(mx, fabsf(__ldg(d_y + i)));
+    const bool vec = (reinterpret_cast<uintptr_t>(d_y) & 15) == 0;   // (a row-sliced view can start 12 bytes into a word)
+    const int per_tile4 = TC_TM * n_out / 4;
+    const int64_t total4 = vec ? m * n_out / 4 : 0;
+    const float4 *dy4 = reinterpret_cast<const float4 *>(d_y);
+    if (!vec) {
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * TC_TM * n_out, end = min(base + (int64_t)TC_TM * n_out, m * n_out);
+        for (int64_t i = base + threadIdx.x; i < end; i += blockDim.x) mx = fmaxf(mx, fabsf(__ldg(d_y + i)));
+      }
+    }
+    for (int64_t tile = blockIdx.x; vec && tile < n_tiles; tile += 4 * (int64_t)gridDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t tl = tile + (int64_t)u * gridDim.x;
+        const int64_t i = tl * per_tile4 + threadIdx.x;
+        v[u] = (tl < n_tiles && (int)threadIdx.x < per_tile4 && i < total4) ? __ldg(dy4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+    }
+    if (vec) {   // the (< 4) floats behind the last whole 16 bytes (every CTA: whoever owns the last tile needs them)
+      for (int64_t i = total4 * 4 + threadIdx.x; i < m * n_out; i += blockDim.x) mx = fmaxf(mx, fabsf(__ldg(d_y + i)));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
@@ -2173,7 +2210,7 @@ static int launch_dgrad_acc(const esr_mlp_desc_t *d, const TcLayout &T, const vo
                                                           accumulate, st);
   }
   auto kern = k_mlp_dgrad_tc<K0, NH, DXN, NO, ACC, OVL, H16>;
-  constexpr int bytes = BwdSm<K0, NH, DXN>::bytes + (H16 ? 2 * TC_TM * 4 : 0);
+  constexpr int bytes = BwdSm<K0, NH, DXN>::bytes + (H16 ? TC_TM * 4 : 0);
   if (int e = set_smem_tc(kern, bytes)) return e;
   uint32_t *absmax = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_z) + act_dz_tail_offset(NH, mt));
   if constexpr (H16) {   // max |d_y| of the launch -> the scale of the stored cotangents

@@ -25,27 +25,29 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[s
     return {k: (v[sl] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == n else v) for k, v in batch.items()}
 
 
-def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int:
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, defer: bool = False):
     """Sum every parameter gradient over the ranks (losses are written as sums over rays / the global ray count, so
     a plain sum reproduces the single-process gradient).  A parameter some rank did not touch contributes zeros there;
-    a parameter NO rank touched (e.g. envmap / brdf in a step without LTS points) keeps `grad = None` on every rank, so
-    that the optimizer skips it exactly as the single-process run does (optimizer.py:74: no step count, no moment
-    decay) — found with one small all-reduce(max) of a has-gradient vector and one host read.
-    Returns the number of bytes reduced."""
+    a parameter NO rank touched (e.g. envmap / brdf in a step without LTS points) ends with `grad = None` on every rank,
+    so that the optimizer skips it exactly as the single-process run does (optimizer.py:74: no step count, no moment
+    decay).  The collective sequence must not depend on a rank's data, so every rank reduces zeros for its own missing
+    gradients and a has-gradient vector goes along (one small all-reduce(max)); the vector is read on the host AFTER
+    every collective has been queued (one read at the end of the step, not a bubble in front of the exchange) and the
+    gradients no rank had are reset to None.
+    Returns the number of bytes reduced; with defer=True, (bytes, finish) — the caller runs finish() once it has queued
+    its own collectives."""
     import torch.distributed as dist
 
     params = [p for p in params if p.requires_grad]
     if not params:
-        return 0
+        return (0, lambda: None) if defer else 0
+    was_none = [p.grad is None for p in params]
     dev = next((p.grad.device for p in params if p.grad is not None), params[0].device)
-    has = torch.tensor([p.grad is not None for p in params], dtype=torch.int32, device=dev)
+    has = torch.tensor([not n for n in was_none], dtype=torch.int32, device=dev)
     dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
-    has = has.tolist()
     nbytes = 4 * len(params)
     small = []  # the MLP weights / biases (~1 MB in ~20 tensors): one flat bucket, one collective
-    for p, any_rank in zip(params, has):
-        if not any_rank:
-            continue            # untouched everywhere: stays None
+    for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
         nbytes += p.grad.numel() * p.grad.element_size()
@@ -60,6 +62,16 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int
         for g in small:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
+
+    def finish():
+        if any(was_none):       # (identical on no rank in general — but a rank with nothing missing has nothing to reset)
+            for p, n, any_rank in zip(params, was_none, has.tolist()):
+                if n and not any_rank:
+                    p.grad = None
+
+    if defer:
+        return nbytes, finish
+    finish()
     return nbytes
 
 
@@ -214,7 +226,7 @@ class GridGradCompactor:
             assert self.outside_is_zero(), "gradient outside the dilated occupancy set"
         grid_ids = {id(p) for p in self.grids}
         others = [p for p in self.model.parameters() if id(p) not in grid_ids]
-        nbytes = allreduce_gradients(others, group)      # the small MLP bucket first: it is ready and tiny
+        nbytes, finish = allreduce_gradients(others, group, defer=True)      # the small MLP bucket first: it is ready and tiny
         if early is not None and not stale and all(p.grad is not None and p.grad.data_ptr() == b.data_ptr()
                                                    for p, b in zip(self.grids[1:], early[2])):
             # the colour volumes are already on their way (started inside the backward pass): SDF grid now, then join
@@ -224,12 +236,14 @@ class GridGradCompactor:
             self.unpack(rows[:1], sbuf)
             work.wait()
             self.unpack(rows[1:], cbuf)
+            finish()
             return nbytes + (sbuf.numel() + cbuf.numel()) * 4
         if early is not None:
             early[0].wait()     # the buffers it reduced are not the final gradients (accumulation): redo the exchange
         buf = self.pack(rows, "_abuf")
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         self.unpack(rows, buf)
+        finish()
         return nbytes + buf.numel() * buf.element_size()
 
 
@@ -338,12 +352,15 @@ class TouchedBlockCompactor(GridGradCompactor):
             assert self.outside_is_zero(), "non-zero gradient outside the union of touched blocks"
         grid_ids = {id(p) for p in self.grids}
         others = [p for p in self.model.parameters() if id(p) not in grid_ids]
-        nbytes = allreduce_gradients(others, group) + flags.numel() * 4
+        nbytes, finish = allreduce_gradients(others, group, defer=True)
+        nbytes += flags.numel() * 4
         if self.idx.numel() == 0:
+            finish()
             return nbytes
         buf = self.pack(rows, "_abuf")
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
         self.unpack(rows, buf)
+        finish()
         return nbytes + buf.numel() * buf.element_size()
 
 
