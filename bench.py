@@ -485,11 +485,14 @@ def run_b200(a, rank, world, local_rank):
     # touched 8^3 blocks by default (the dense alternative is a 1.28 GB all-reduce per step)
     if world > 1 and a.stage != "eval" and (a.block_exchange or (a.stage == "lts" and not a.dense_allreduce)):
         compactor = TouchedBlockCompactor(model)
-    # the colour volumes' early start (dist.GridGradCompactor.overlap_color_allreduce: -0.14 ms per step at N = 2, tested
-    # by tests/test_gpu_dist.py) is opt-in here: it was measured at N = 2 and N = 8 only, and a 4-GPU run at the end of
-    # round 1 hung for an unexplained reason with no GPU budget left to investigate
-    if isinstance(compactor, GridGradCompactor) and not isinstance(compactor, TouchedBlockCompactor) \
-            and os.environ.get("ESR_ALLREDUCE_OVERLAP"):
+    # (round 1 kept this opt-in after a 4-GPU run hung; the likely cause — the collective sequence depended on whether a
+    # rank's backward reached the hook — was removed in dist._on_color_grads, and round 2 ran N = 4 three times each with
+    # and without it, clean, with the exchange self-check below: gpurun_out/multi_n4 -> profiles/r02_bench_lines)
+    # the colour volumes' exchange starts inside the backward pass (dist.GridGradCompactor.overlap_color_allreduce) and
+    # runs under the weight-gradient GEMMs; ESR_ALLREDUCE_OVERLAP=0 keeps the whole exchange behind backward()
+    overlap = (isinstance(compactor, GridGradCompactor) and not isinstance(compactor, TouchedBlockCompactor)
+               and os.environ.get("ESR_ALLREDUCE_OVERLAP", "1") not in ("0", ""))
+    if overlap:
         compactor.overlap_color_allreduce(True)
     reduced = [0]
     optimizer = None

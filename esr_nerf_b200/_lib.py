@@ -197,6 +197,7 @@ PROTOTYPES = {
     "esr_mlp_pack": (I32, [DESC_P, P, P, P]),
     "esr_mlp_fwd": (I32, [DESC_P, P, P, I64, I64, I64, P, P, I64, P]),
     "esr_mlp_bwd": (I32, [DESC_P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, I32, P, P]),
+    "esr_mlp_bwd_weights": (I32, [DESC_P, P, I64, I64, I64, P, P, P, P]),
 }
 
 

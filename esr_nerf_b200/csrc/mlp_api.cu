@@ -100,6 +100,16 @@ extern "C" int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const voi
   return ESR_ERR_BAD_ARG;
 }
 
+extern "C" int esr_mlp_bwd_weights(const esr_mlp_desc_t *d, const void *x, int64_t row_begin, int64_t row_end,
+                                   int64_t m_total, const void *hidden, const void *d_z, float *grad_flat,
+                                   esr_stream_t stream) {
+  if (int e = check_desc(d)) return e;
+  ESR_CHECK_ARG(row_begin >= 0 && row_end >= row_begin && row_end <= m_total);
+  if (row_end == row_begin) return ESR_OK;
+  ESR_CHECK_ARG(x && hidden && d_z && grad_flat);
+  return tc_wgrad(d, x, row_begin, row_end, m_total, hidden, d_z, grad_flat, (cudaStream_t)stream);
+}
+
 // fused tone-map net (voxurff.py:783-788 + pbr/module.py:24-39): see mlp_tc.cu
 static int check_tonemap_desc(const esr_mlp_desc_t *d) {
   if (int e = check_desc(d)) return e;

@@ -165,11 +165,20 @@ class GridGradCompactor:
             self.__dict__[name] = buf
         return buf
 
-    def pack(self, rows, out_name: str = None) -> torch.Tensor:
+    def packed_floats(self, rows) -> int:
+        """floats of the packed buffer of `rows` (every volume's block padded to an even count)"""
+        k = self.idx.numel()
+        return sum((k * r.shape[1] + 1) // 2 * 2 for r in rows)
+
+    def pack(self, rows, out_name: str = None, out: torch.Tensor = None) -> torch.Tensor:
         """dense gradient volumes -> one packed buffer (CUDA: one launch of esr_grad_pack, planar blocks [K][C_j];
-        host tensors of the gloo tests: the same layout with torch indexing)"""
+        host tensors of the gloo tests: the same layout with torch indexing); `out`: write into this buffer (a slice of a
+        larger exchange bucket) instead of allocating"""
         chans = [r.shape[1] for r in rows]
         k = self.idx.numel()
+        if out is not None and not rows[0].is_cuda:
+            out.copy_(self.pack(rows))
+            return out
         if rows[0].is_cuda:
             import ctypes
 
@@ -182,8 +191,12 @@ class GridGradCompactor:
             c_arr = (ctypes.c_int32 * len(rows))(*chans)
             v_arr = (ctypes.c_void_p * len(rows))(*[r.data_ptr() for r in rows])
             n = int(L.esr_grad_pack_floats(c_arr, len(rows), k))
-            buf = (self._persistent(out_name, n, rows[0].device) if out_name
-                   else torch.empty(n, dtype=torch.float32, device=rows[0].device))
+            if out is not None:
+                assert out.numel() == n and out.is_contiguous() and out.data_ptr() % 8 == 0
+                buf = out
+            else:
+                buf = (self._persistent(out_name, n, rows[0].device) if out_name
+                       else torch.empty(n, dtype=torch.float32, device=rows[0].device))
             check(L.esr_grad_pack(v_arr, c_arr, len(rows), ptr(self._idx32), k, ptr(buf), stream_ptr()))
             return buf
         blocks = []
@@ -209,9 +222,51 @@ class GridGradCompactor:
             r.index_copy_(0, self.idx, buf[off:off + n].view(k, r.shape[1]))
             off += n + (n & 1)
 
-    def allreduce(self, group=None, verify: bool = False) -> int:
+    def _bucket_exchange(self, rows, group, name: str) -> int:
+        """ONE all-reduce for everything that is not already on its way: the packed voxels of `rows`, every non-grid
+        parameter gradient (the MLPs: ~1 MB in ~20 tensors) and the has-gradient flags of those parameters, side by side
+        in one persistent buffer.  Around the collective: one pack / one unpack launch for the volumes, one multi-tensor
+        copy in and out for the small gradients — the per-tensor version (a cat, ~20 copy-backs, three collectives) kept
+        the device idle for ~0.6 ms per step behind a launch-bound host (profiles/r02 timeline_exchange).
+        A parameter no rank holds a gradient for ends with grad = None (see allreduce_gradients)."""
         import torch.distributed as dist
 
+        grid_ids = {id(p) for p in self.grids}
+        others = [p for p in self.model.parameters() if id(p) not in grid_ids and p.requires_grad]
+        was_none = [p.grad is None for p in others]
+        for p in others:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        assert all(p.grad.dtype == torch.float32 for p in others), "parameter gradients are fp32"
+        n_rows = self.packed_floats(rows) if (rows and self.idx.numel()) else 0
+        sizes = [p.grad.numel() for p in others]
+        n = n_rows + sum(sizes) + len(others)
+        dev = rows[0].device if rows else others[0].grad.device
+        buf = self._persistent(name, n + (n & 1), dev)[:n]
+        if n_rows:
+            self.pack(rows, out=buf[:n_rows])
+        flat = list(torch.split(buf[n_rows:n_rows + sum(sizes)], sizes))
+        if others:
+            torch._foreach_copy_(flat, [p.grad.reshape(-1) for p in others])
+            buf[n - len(others):] = torch.tensor([0.0 if w else 1.0 for w in was_none], dtype=torch.float32).to(dev, non_blocking=True)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        if n_rows:
+            self.unpack(rows, buf[:n_rows])
+        if others:
+            torch._foreach_copy_([p.grad.reshape(-1) for p in others], flat)
+            self._pending_flags = (others, was_none, buf[n - len(others):]) if any(was_none) else None
+        return n * 4
+
+    def _finish_flags(self):
+        """gradients no rank had -> None again (one host read, after every collective of the step has been queued)"""
+        pend, self._pending_flags = getattr(self, "_pending_flags", None), None
+        if pend is not None:
+            others, was_none, flags = pend
+            for p, w, f in zip(others, was_none, flags.tolist()):
+                if w and f == 0.0:
+                    p.grad = None
+
+    def allreduce(self, group=None, verify: bool = False) -> int:
         color = self.grids[1:]
         if self._early is None and self._overlap and all(p.grad is None for p in color):
             self._on_color_grads({})     # this rank's backward never reached the hook: same collective, zeros, now
@@ -224,27 +279,20 @@ class GridGradCompactor:
         rows = self._grids_rows()
         if verify:
             assert self.outside_is_zero(), "gradient outside the dilated occupancy set"
-        grid_ids = {id(p) for p in self.grids}
-        others = [p for p in self.model.parameters() if id(p) not in grid_ids]
-        nbytes, finish = allreduce_gradients(others, group, defer=True)      # the small MLP bucket first: it is ready and tiny
         if early is not None and not stale and all(p.grad is not None and p.grad.data_ptr() == b.data_ptr()
                                                    for p, b in zip(self.grids[1:], early[2])):
-            # the colour volumes are already on their way (started inside the backward pass): SDF grid now, then join
+            # the colour volumes are already on their way (started inside the backward pass): SDF grid + MLPs now, then join
             work, cbuf, _ = early
-            sbuf = self.pack(rows[:1], "_sbuf")
-            dist.all_reduce(sbuf, op=dist.ReduceOp.SUM, group=group)
-            self.unpack(rows[:1], sbuf)
+            nbytes = self._bucket_exchange(rows[:1], group, "_sbuf")
             work.wait()
             self.unpack(rows[1:], cbuf)
-            finish()
-            return nbytes + (sbuf.numel() + cbuf.numel()) * 4
+            self._finish_flags()
+            return nbytes + cbuf.numel() * 4
         if early is not None:
             early[0].wait()     # the buffers it reduced are not the final gradients (accumulation): redo the exchange
-        buf = self.pack(rows, "_abuf")
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-        self.unpack(rows, buf)
-        finish()
-        return nbytes + buf.numel() * buf.element_size()
+        nbytes = self._bucket_exchange(rows, group, "_abuf")
+        self._finish_flags()
+        return nbytes
 
 
 class TouchedBlockCompactor(GridGradCompactor):
@@ -350,18 +398,9 @@ class TouchedBlockCompactor(GridGradCompactor):
         self.select(flags)
         if verify:
             assert self.outside_is_zero(), "non-zero gradient outside the union of touched blocks"
-        grid_ids = {id(p) for p in self.grids}
-        others = [p for p in self.model.parameters() if id(p) not in grid_ids]
-        nbytes, finish = allreduce_gradients(others, group, defer=True)
-        nbytes += flags.numel() * 4
-        if self.idx.numel() == 0:
-            finish()
-            return nbytes
-        buf = self.pack(rows, "_abuf")
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-        self.unpack(rows, buf)
-        finish()
-        return nbytes + buf.numel() * buf.element_size()
+        nbytes = self._bucket_exchange(rows, group, "_abuf") + flags.numel() * 4
+        self._finish_flags()
+        return nbytes
 
 
 def gather_maps(maps: Dict[str, torch.Tensor], n_total: int, rank: int, world: int, group=None, dst: int = 0):

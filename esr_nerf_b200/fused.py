@@ -420,7 +420,10 @@ def _mlp_forward(desc, image, x, rb, re, m_total, train, save_begin=0):
     return y, hidden
 
 
-def _mlp_backward(desc, image, x, y, d_y, rb, re, m_total, hidden, d_x, dx_cols, accumulate, scratch=None):
+def _mlp_backward(desc, image, x, y, d_y, rb, re, m_total, hidden, d_x, dx_cols, accumulate, scratch=None,
+                  weights=True):
+    """data gradient (+ weight gradients unless weights=False: then _mlp_backward_weights finishes the job later from the
+    same scratch, which must stay untouched until it has)"""
     L = _lib.lib()
     d = _desc(desc)
     dev = x.device
@@ -428,10 +431,19 @@ def _mlp_backward(desc, image, x, y, d_y, rb, re, m_total, hidden, d_x, dx_cols,
     if scratch is None:
         scratch = torch.empty(L.esr_mlp_dz_bytes(ctypes.byref(d), m_total), dtype=torch.uint8, device=dev)
     d_z_out = None
-    grad_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=dev)
+    grad_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=dev) if weights else None
     check(L.esr_mlp_bwd(ctypes.byref(d), ptr(image), ptr(x), ptr(y), ptr(d_y), rb, re, m_total, ptr(hidden),
                         ptr(scratch), ptr(d_z_out), ptr(d_x), dx_cols, int(accumulate), ptr(grad_flat), stream_ptr()))
     return grad_flat, scratch
+
+
+def _mlp_backward_weights(desc, x, rb, re, m_total, hidden, scratch):
+    L = _lib.lib()
+    d = _desc(desc)
+    grad_flat = torch.zeros(L.esr_mlp_param_count(ctypes.byref(d)), dtype=torch.float32, device=x.device)
+    check(L.esr_mlp_bwd_weights(ctypes.byref(d), ptr(x), rb, re, m_total, ptr(hidden), ptr(scratch), ptr(grad_flat),
+                                stream_ptr()))
+    return grad_flat
 
 
 class Shade(torch.autograd.Function):
@@ -474,16 +486,26 @@ class Shade(torch.autograd.Function):
         disjoint = (eb, ee, oe) == (0, ob, s.m3)
         d_x = (torch.empty if disjoint else torch.zeros)(s.m3, FEAT_GRAD_DIM, dtype=torch.float32, device=x.device)
         acc = 0 if disjoint else 1
+        # Multi-GPU with the early colour-grid exchange: data gradients of both nets first, then the encode backward and
+        # the hook that starts the all-reduce of the colour volumes (12 of every 13 exchanged floats), and only then the
+        # weight-gradient GEMMs of both nets — 1.6 ms of tensor-core work for the collective to hide under.  (Costs a
+        # second d_z scratch: both nets' cotangents are alive at once.)
+        early = COLOR_GRADS_READY_HOOK is not None
         g_off_flat, scratch = _mlp_backward(ctx.desc, img_off, x, lin_off, d_off.contiguous(), ob, oe, s.m3,
-                                            hid_off, d_x, FEAT_GRAD_DIM, acc)
-        g_emo_flat, _ = _mlp_backward(ctx.desc, img_emo, x, lin_emo, d_emo.contiguous(), eb, ee, s.m3, hid_emo,
-                                      d_x, FEAT_GRAD_DIM, acc, scratch)
-        ctx.hidden = None
+                                            hid_off, d_x, FEAT_GRAD_DIM, acc, weights=not early)
+        g_emo_flat, scratch_emo = _mlp_backward(ctx.desc, img_emo, x, lin_emo, d_emo.contiguous(), eb, ee, s.m3, hid_emo,
+                                                d_x, FEAT_GRAD_DIM, acc, None if early else scratch, weights=not early)
+        if not early:
+            ctx.hidden = None
         g_sdf, g_offc, g_emoc = encode_backward(ctx.sc, rays_o, rays_d, sdf_grid, off_grid, emo_grid, s, d_x,
                                                 ctx.grid_params, fd)
-        if COLOR_GRADS_READY_HOOK is not None and g_offc is None and g_emoc is None:   # both went to the gradient sink
+        if early and g_offc is None and g_emoc is None:   # both went to the gradient sink
             p_off, p_emo = ctx.grid_params[1], ctx.grid_params[2]
             COLOR_GRADS_READY_HOOK({p_off: GRAD_SINK.get(p_off), p_emo: GRAD_SINK.get(p_emo)})
+        if early:
+            g_off_flat = _mlp_backward_weights(ctx.desc, x, ob, oe, s.m3, hid_off, scratch)
+            g_emo_flat = _mlp_backward_weights(ctx.desc, x, eb, ee, s.m3, hid_emo, scratch_emo)
+            ctx.hidden = None
         return g_sdf, g_offc, g_emoc, g_off_flat, g_emo_flat, None, None, None, None, None, None, None, None
 
 

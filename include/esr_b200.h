@@ -405,6 +405,14 @@ int esr_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const void *x, const
                 const float *d_y, int64_t row_begin, int64_t row_end, int64_t m_total,
                 const void *hidden, void *d_z, float *d_z_out, float *d_x, int dx_cols,
                 int accumulate, float *grad_flat, esr_stream_t stream);
+/*
+ * The weight-gradient half of esr_mlp_bwd on its own: grad_flat += dW / db of every layer from (x, hidden) and the d_z
+ * scratch a preceding esr_mlp_bwd call with grad_flat = NULL (data gradient only) left behind for the same rows.
+ * Splitting the two lets a caller run what depends on d_x — the encode backward, and with it the start of the
+ * colour-grid gradient exchange of a multi-GPU step — before the weight-gradient GEMMs, which then overlap the collective.
+ */
+int esr_mlp_bwd_weights(const esr_mlp_desc_t *d, const void *x, int64_t row_begin, int64_t row_end, int64_t m_total,
+                        const void *hidden, const void *d_z, float *grad_flat, esr_stream_t stream);
 
 /*
  * Fused tone-map net (apply_tonemapper, voxurff.py:783-788: PE(5) of the linear radiance -> 33 -> 192 -> 3 sigmoid,

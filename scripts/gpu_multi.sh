@@ -1,7 +1,8 @@
 #!/bin/bash
 # scripts/gpu_multi.sh <N> [parts...] — multi-GPU measurements of round 2 on N GPUs of one box (run under gpurun --gpus N)
 #   tests : pytest tests/test_gpu_dist.py (the 2-GPU NCCL exchange test)
-#   fine  : bench.py --gpus N (default exchange) and with ESR_ALLREDUCE_OVERLAP=1, each REPS times (hang hunt at N = 4)
+#   fine  : bench.py --gpus N (default: colour-grid exchange started inside backward) and with ESR_ALLREDUCE_OVERLAP=0,
+#           each REPS times
 #   lts   : bench.py --stage lts --gpus N (touched-block exchange) and --dense-allreduce
 #   eval  : bench.py --stage eval --gpus N with and without the gather
 cd "$(dirname "$0")/.." || exit 1
@@ -23,7 +24,7 @@ for part in $PARTS; do
     tests) timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q > "$O/pytest_dist.log" 2>&1; echo "pytest_dist rc=$?" | tee -a "$O/summary.txt"; tail -3 "$O/pytest_dist.log" ;;
     fine) for i in $(seq 1 "$REPS"); do
             run fine_default_$i 400 $TR --master-port $((port + 1)) bench.py --gpus "$N" --steps 20 --no-cpu-baseline
-            ESR_ALLREDUCE_OVERLAP=1 run fine_overlap_$i 400 $TR --master-port $((port + 1)) bench.py --gpus "$N" --steps 20 --no-cpu-baseline
+            ESR_ALLREDUCE_OVERLAP=0 run fine_nooverlap_$i 400 $TR --master-port $((port + 1)) bench.py --gpus "$N" --steps 20 --no-cpu-baseline
           done ;;
     lts) run lts_blocks 500 $TR --master-port $((port + 1)) bench.py --gpus "$N" --stage lts --steps 10
          run lts_dense 500 $TR --master-port $((port + 1)) bench.py --gpus "$N" --stage lts --steps 10 --dense-allreduce ;;

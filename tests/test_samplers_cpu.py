@@ -151,6 +151,53 @@ def test_sampler_invariants_and_rank_slices(preload):
         assert int(b["uncert_masks"].sum()) == 40 and b["uncert_masks"].numel() == 64
 
 
+def _drive_batch(make):
+    n, bs = 1000, 96
+    g = torch.Generator().manual_seed(3)
+    mask = torch.rand(n, generator=g) < 0.7
+    torch.manual_seed(11)
+    s = make(_data(n), bs)
+    s.filter(mask)
+    s.shuffle()
+    return s, [s.sample() for _ in range(20)]
+
+
+def _drive_groups(make, n=700):
+    torch.manual_seed(21)
+    m = make(_data(n), 64, 32)
+    m.shuffle()
+    out = [m.sample() for _ in range(3)]
+    g = torch.Generator().manual_seed(8)
+    m.filter(torch.rand(m.uncert_data_num, generator=g) < 0.6)
+    out += [m.sample() for _ in range(15)]
+    m.filter(torch.rand(m.uncert_data_num, generator=g) < 0.05)
+    out += [m.sample() for _ in range(4)]
+    return m, out
+
+
+def test_port_matches_reference():
+    """oracle/samplers_port.py (what tests/test_gpu_feed.py compares the product with on the GPU) against the reference's
+    own classes: same batches, same state, both samplers"""
+    from oracle import samplers_port as SP
+
+    ref_mod = _reference_module()
+    if ref_mod is None:
+        pytest.skip("/root/reference not present")
+    ref, ref_b = _drive_batch(lambda d, bs: ref_mod.BatchSampler(_cfg(), d, KEYS, bs))
+    port, port_b = _drive_batch(lambda d, bs: SP.BatchSamplerPort("cpu", d, KEYS, bs))
+    for a, b in zip(port_b, ref_b):
+        _same_batch(a, b)
+    assert port.batch_st == ref.batch_st and torch.equal(port.data_idxs, ref.data_idxs)
+    refg, refg_b = _drive_groups(lambda d, a, b: ref_mod.RayGroupManager(_cfg(), d, KEYS, a, b))
+    portg, portg_b = _drive_groups(lambda d, a, b: SP.RayGroupManagerPort("cpu", d, KEYS, a, b))
+    for a, b in zip(portg_b, refg_b):
+        _same_batch(a, b)
+    for name in ("uncert_batch_st", "cert_batch_st", "uncert_data_num", "cert_data_num"):
+        assert getattr(portg, name) == getattr(refg, name), name
+    assert torch.equal(portg.uncert_data_idxs, refg.uncert_data_idxs) and torch.equal(portg.cert_data_idxs, refg.cert_data_idxs)
+    assert torch.equal(portg.cert_data["rgbs"], refg.cert_data["rgbs"])
+
+
 class _FakeRenderer:
     """eval_emit as a per-ray function (what the render path is: rays are independent), recording its chunk sizes"""
 
