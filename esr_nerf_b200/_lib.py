@@ -172,8 +172,11 @@ PROTOTYPES = {
     "esr_sample_points": (I32, [SCENE_P, P, P, P, P, I64, P, P]),
     "esr_sdf_expgrad_fwd": (I32, [SCENE_P, P, P, I64, I32, P, P, P]),
     "esr_sdf_expgrad_bwd": (I32, [SCENE_P, P, I64, P, P, P, P]),
-    "esr_lts_accumulate_fwd": (I32, [P, P, P, P, P, P, P, P, P, I64, I32, P, P, P]),
-    "esr_lts_accumulate_bwd": (I32, [P, P, P, P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P]),
+    "esr_lts_accumulate_fwd": (I32, [P, P, P, P, P, P, P, P, P, I64, I32, P, P, P, P, I32, P]),
+    "esr_lts_accumulate_bwd": (I32, [P, P, P, P, P, P, P, P, P, I64, I32, P, P, P, P, P, P, P, P, P, I32, P, P]),
+    "esr_lts_scatter_dirs": (I32, [P, P, P, I64, I32, P, P]),
+    "esr_sg_envmap_fwd": (I32, [P, P, P, P, I32, I32, P, P, I64, P, P]),
+    "esr_sg_envmap_bwd": (I32, [P, P, P, P, I32, I32, P, I64, P, P, P, P, P, P]),
     "esr_sdf_fd_gradient": (I32, [SCENE_P, P, P, P, P, P, I64, P, P]),
     "esr_tonemap_encode_fwd": (I32, [P, P, P, P, I64, P, P, I32, P]),
     "esr_tonemap_encode_bwd": (I32, [P, P, P, I64, P, P]),

@@ -174,10 +174,16 @@ __global__ void __launch_bounds__(256)
                      int64_t P, int n2, float *__restrict__ off_hat, float *__restrict__ reflect,
                      const float *__restrict__ g_off_hat, const float *__restrict__ g_reflect, float *__restrict__ g_base,
                      float *__restrict__ g_rough, float *__restrict__ g_metal, float *__restrict__ g_rad_off,
-                     float *__restrict__ g_rad_emo) {
+                     float *__restrict__ g_rad_emo, const float *__restrict__ emission, const uint8_t *__restrict__ umask,
+                     int pdra, float *__restrict__ g_emission) {
   const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = lane_id();
   if (p >= P) return;
+  // emo_hat (esrnerf.py:668-677): emission + reflect; in PDRA mode an UNCERTAIN ray's point gets emission + stop-gradient(
+  // reflect), a certain ray's point reflect alone.  With `emission` the `reflect` output is emo_hat and g_reflect its cotangent.
+  const bool mix = emission != nullptr;
+  const bool um = mix && pdra && umask && __ldg(umask + p) != 0;
+  const bool add_emission = mix && (!pdra || um), reflect_has_grad = !(mix && pdra && um);
   float n[3], a[3], wo[2][3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -195,8 +201,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         go[v][c] = g_off_hat ? __ldg(g_off_hat + 3 * (v * P + p) + c) * inv : 0.f;
-        ge[v][c] = __ldg(g_reflect + 3 * (v * P + p) + c) * inv;
+        ge[v][c] = reflect_has_grad ? __ldg(g_reflect + 3 * (v * P + p) + c) * inv : 0.f;
       }
+    if (g_emission && lane < 3)   // both outgoing directions repeat the point's emission (emission.repeat(2, 1))
+      g_emission[3 * p + lane] = add_emission ? __ldg(g_reflect + 3 * p + lane) + __ldg(g_reflect + 3 * (P + p) + lane) : 0.f;
   }
   for (int j = (int)lane; j < n2; j += 32) {
     const int64_t ray = p * n2 + j;
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(256)
         const float so = warp_sum(acc_off[v][c]), se = warp_sum(acc_emo[v][c]);
         if (lane == 0) {
           if (off_hat) off_hat[3 * (v * P + p) + c] = so * inv;
-          reflect[3 * (v * P + p) + c] = se * inv;
+          reflect[3 * (v * P + p) + c] = se * inv + (add_emission ? __ldg(emission + 3 * p + c) : 0.f);
         }
       }
   } else {
@@ -253,6 +261,129 @@ __global__ void __launch_bounds__(256)
     }
     gr = warp_sum(gr), gm = warp_sum(gm);
     if (lane == 0) g_rough[p] = gr, g_metal[p] = gm;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hemisphere directions of the light-transport segment (pbr/functions.py:10-32): per LTS point n directions — the
+// normalised Gaussian draw `noise` (diffuse_scattering) or the fixed Fibonacci spiral `table` (diffuse_scattering_fib) —
+// each mirrored into the hemisphere of the point's normal.  One thread per (point, direction).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_lts_scatter_dirs(const float *__restrict__ normal, const float *__restrict__ noise, const float *__restrict__ table,
+                       int64_t P, int n, float *__restrict__ dirs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * n) return;
+  const int64_t p = i / n;
+  float d[3];
+  if (noise) {
+    const float x = __ldg(noise + 3 * i), y = __ldg(noise + 3 * i + 1), z = __ldg(noise + 3 * i + 2);
+    const float inv = 1.f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);   // F.normalize: v / max(|v|, eps)
+    d[0] = x * inv, d[1] = y * inv, d[2] = z * inv;
+  } else {
+    const int j = (int)(i - p * n);
+    d[0] = __ldg(table + 3 * j), d[1] = __ldg(table + 3 * j + 1), d[2] = __ldg(table + 3 * j + 2);
+  }
+  const float dn = d[0] * __ldg(normal + 3 * p) + d[1] * __ldg(normal + 3 * p + 1) + d[2] * __ldg(normal + 3 * p + 2);
+  const float sgn = dn < 0.f ? -1.f : 1.f;
+  dirs[3 * i] = sgn * d[0], dirs[3 * i + 1] = sgn * d[1], dirs[3 * i + 2] = sgn * d[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Spherical-Gaussian environment map (pbr/module.py:133-143) on the secondary rays, with what the light-transport
+// segment does to it fused in (esrnerf.py:560-566): out = add + act(sum_k mu_k exp(lambda_k (d . l_k - 1))) * scale,
+// `scale` = the secondary ray's final transmittance, `add` = its marched off-radiance.  lobes are unit vectors and
+// lambdas non-negative (the caller's F.normalize / abs stay in torch: [K, 3] tensors).  act: 1 softplus, 2 relu, 3 abs,
+// 4 exp, 5 sigmoid.  Backward: recomputes the lobes' responses, warp- then block-reduces the parameter gradients.
+// ---------------------------------------------------------------------------------------------
+constexpr int SG_MAX = 64;
+
+ESR_D float sg_act(float x, int act) {
+  switch (act) {
+    case 1: return x > 20.f ? x : log1pf(expf(x));
+    case 2: return fmaxf(x, 0.f);
+    case 3: return fabsf(x);
+    case 4: return expf(x);
+    default: return 1.f / (1.f + expf(-x));
+  }
+}
+ESR_D float sg_act_grad(float x, float y, int act) {   // d act / d x given x and y = act(x)
+  switch (act) {
+    case 1: return x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
+    case 2: return x > 0.f ? 1.f : 0.f;
+    case 3: return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f);
+    case 4: return y;
+    default: return y * (1.f - y);
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+    k_sg_envmap(const float *__restrict__ dirs, const float *__restrict__ mus, const float *__restrict__ lam,
+                const float *__restrict__ lobes, int K, int act, const float *__restrict__ scale,
+                const float *__restrict__ add, int64_t M, float *__restrict__ out, const float *__restrict__ g_out,
+                float *__restrict__ g_mus, float *__restrict__ g_lam, float *__restrict__ g_lobes,
+                float *__restrict__ g_scale) {
+  __shared__ float s_par[SG_MAX * 7];                       // mu (3), lambda, lobe (3) per lobe
+  __shared__ float s_acc[BWD ? SG_MAX * 7 : 1];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s_par[7 * i + c] = mus[3 * i + c], s_par[7 * i + 4 + c] = lobes[3 * i + c];
+    s_par[7 * i + 3] = lam[i];
+  }
+  if (BWD)
+    for (int i = threadIdx.x; i < 7 * K; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = m < M;
+  float d[3] = {0.f, 0.f, 0.f}, pre[3] = {0.f, 0.f, 0.f};
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = __ldg(dirs + 3 * m + c);
+    for (int k = 0; k < K; ++k) {
+      const float *q = s_par + 7 * k;
+      const float e = expf(q[3] * (d[0] * q[4] + d[1] * q[5] + d[2] * q[6] - 1.f));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pre[c] = fmaf(q[c], e, pre[c]);
+    }
+  }
+  const float sc_m = (live && scale) ? __ldg(scale + m) : 1.f;
+  if (!BWD) {
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[3 * m + c] = (add ? __ldg(add + 3 * m + c) : 0.f) + sg_act(pre[c], act) * sc_m;
+    }
+    return;
+  }
+  float gp[3] = {0.f, 0.f, 0.f};
+  if (live) {
+    float gs = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float y = sg_act(pre[c], act), g = __ldg(g_out + 3 * m + c);
+      gs = fmaf(g, y, gs);
+      gp[c] = g * sc_m * sg_act_grad(pre[c], y, act);
+    }
+    if (g_scale) g_scale[m] = gs;
+  }
+  const unsigned lane = lane_id();
+  for (int k = 0; k < K; ++k) {                              // warp-uniform loop: dead lanes contribute zeros
+    const float *q = s_par + 7 * k;
+    const float dot = d[0] * q[4] + d[1] * q[5] + d[2] * q[6];
+    const float e = live ? expf(q[3] * (dot - 1.f)) : 0.f;
+    const float ge = (gp[0] * q[0] + gp[1] * q[1] + gp[2] * q[2]) * e;     // cotangent of the exponent, times e
+    float v[7] = {gp[0] * e, gp[1] * e, gp[2] * e, ge * (dot - 1.f), ge * q[3] * d[0], ge * q[3] * d[1], ge * q[3] * d[2]};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const float sum = warp_sum(v[i]);
+      if (lane == 0) atomicAdd(s_acc + 7 * k + i, sum);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 7 * K; i += blockDim.x) {
+    const int k = i / 7, f = i % 7;
+    float *dst = f < 3 ? g_mus + 3 * k + f : (f == 3 ? g_lam + k : g_lobes + 3 * k + (f - 4));
+    atomicAdd(dst, s_acc[i]);
   }
 }
 
@@ -309,14 +440,14 @@ extern "C" int esr_sdf_expgrad_bwd(const esr_scene_t *sc, const float *pts, int6
 extern "C" int esr_lts_accumulate_fwd(const float *normal, const float *base, const float *rough, const float *metal,
                                       const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
                                       const float *rad_emo, int64_t n_pts, int n_dirs, float *off_hat, float *reflect,
-                                      esr_stream_t stream) {
+                                      const float *emission, const uint8_t *umask, int pdra_mode, esr_stream_t stream) {
   ESR_CHECK_ARG(n_pts >= 0 && n_dirs > 0);
   if (n_pts == 0) return ESR_OK;
   ESR_CHECK_ARG(normal && base && rough && metal && wo_a && wo_b && dirs && rad_emo && reflect && (!rad_off == !off_hat));
   ESR_STAGE("k_lts_accumulate_fwd", stream);
   k_lts_accumulate<false><<<cdiv(n_pts * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       normal, base, rough, metal, wo_a, wo_b, dirs, rad_off, rad_emo, n_pts, n_dirs, off_hat, reflect, nullptr, nullptr,
-      nullptr, nullptr, nullptr, nullptr, nullptr);
+      nullptr, nullptr, nullptr, nullptr, nullptr, emission, umask, pdra_mode, nullptr);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -325,7 +456,8 @@ extern "C" int esr_lts_accumulate_bwd(const float *normal, const float *base, co
                                       const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
                                       const float *rad_emo, int64_t n_pts, int n_dirs, const float *g_off_hat,
                                       const float *g_reflect, float *g_base, float *g_rough, float *g_metal,
-                                      float *g_rad_off, float *g_rad_emo, esr_stream_t stream) {
+                                      float *g_rad_off, float *g_rad_emo, const float *emission, const uint8_t *umask,
+                                      int pdra_mode, float *g_emission, esr_stream_t stream) {
   ESR_CHECK_ARG(n_pts >= 0 && n_dirs > 0);
   if (n_pts == 0) return ESR_OK;
   ESR_CHECK_ARG(normal && base && rough && metal && wo_a && wo_b && dirs && rad_emo && g_reflect && g_base && g_rough &&
@@ -334,7 +466,43 @@ extern "C" int esr_lts_accumulate_bwd(const float *normal, const float *base, co
   ESR_STAGE("k_lts_accumulate_bwd", stream);
   k_lts_accumulate<true><<<cdiv(n_pts * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       normal, base, rough, metal, wo_a, wo_b, dirs, rad_off, rad_emo, n_pts, n_dirs, nullptr, nullptr, g_off_hat, g_reflect,
-      g_base, g_rough, g_metal, g_rad_off, g_rad_emo);
+      g_base, g_rough, g_metal, g_rad_off, g_rad_emo, emission, umask, pdra_mode, g_emission);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_lts_scatter_dirs(const float *normal, const float *noise, const float *table, int64_t n_pts, int n_dirs,
+                                    float *dirs, esr_stream_t stream) {
+  ESR_CHECK_ARG(n_pts >= 0 && n_dirs > 0);
+  if (n_pts == 0) return ESR_OK;
+  ESR_CHECK_ARG(normal && dirs && (!noise != !table));
+  ESR_STAGE("k_lts_scatter_dirs", stream);
+  k_lts_scatter_dirs<<<cdiv(n_pts * n_dirs, 256), 256, 0, (cudaStream_t)stream>>>(normal, noise, table, n_pts, n_dirs, dirs);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_sg_envmap_fwd(const float *dirs, const float *mus, const float *lambdas, const float *lobes, int n_sg,
+                                 int act, const float *scale, const float *add, int64_t m, float *out, esr_stream_t stream) {
+  ESR_CHECK_ARG(m >= 0 && n_sg > 0 && n_sg <= SG_MAX && act >= 1 && act <= 5);
+  if (m == 0) return ESR_OK;
+  ESR_CHECK_ARG(dirs && mus && lambdas && lobes && out);
+  ESR_STAGE("k_sg_envmap_fwd", stream);
+  k_sg_envmap<false><<<cdiv(m, 256), 256, 0, (cudaStream_t)stream>>>(dirs, mus, lambdas, lobes, n_sg, act, scale, add, m, out,
+                                                                     nullptr, nullptr, nullptr, nullptr, nullptr);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_sg_envmap_bwd(const float *dirs, const float *mus, const float *lambdas, const float *lobes, int n_sg,
+                                 int act, const float *scale, int64_t m, const float *g_out, float *g_mus, float *g_lambdas,
+                                 float *g_lobes, float *g_scale, esr_stream_t stream) {
+  ESR_CHECK_ARG(m >= 0 && n_sg > 0 && n_sg <= SG_MAX && act >= 1 && act <= 5);
+  if (m == 0) return ESR_OK;
+  ESR_CHECK_ARG(dirs && mus && lambdas && lobes && g_out && g_mus && g_lambdas && g_lobes && (!scale == !g_scale));
+  ESR_STAGE("k_sg_envmap_bwd", stream);
+  k_sg_envmap<true><<<cdiv(m, 256), 256, 0, (cudaStream_t)stream>>>(dirs, mus, lambdas, lobes, n_sg, act, scale, nullptr, m,
+                                                                    nullptr, g_out, g_mus, g_lambdas, g_lobes, g_scale);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

@@ -123,9 +123,25 @@ class ESRNeRF(VoxurfF):
     def _scatter(self, normal, number) -> torch.Tensor:
         """self.scattering(normal, number) of esrnerf.py:188-192: `number` directions in the hemisphere of each normal —
         normalised Gaussian draws (pbr/functions.py:10-18) or the fixed Fibonacci spiral (pbr/functions.py:21-32)"""
+        if not normal.is_cuda:     # (host tensors: the torch restatement, used by CPU-side unit tests of the glue only)
+            if self.fib_sampling:
+                return pbr.diffuse_scattering_fib(normal, number)
+            return pbr.diffuse_scattering(normal, self._randn(normal.shape[0], number, 3, dev=normal.device))
         if self.fib_sampling:
-            return pbr.diffuse_scattering_fib(normal, number)
-        return pbr.diffuse_scattering(normal, self._randn(normal.shape[0], number, 3, dev=normal.device))
+            return fused.lts_scatter_dirs(normal, number, table=pbr.fibonacci_hemisphere(number).to(normal.device))
+        return fused.lts_scatter_dirs(normal, number, noise=self._randn(normal.shape[0], number, 3, dev=normal.device))
+
+    def _env_radiance(self, dirs, last, add):
+        """add + envmap(dirs) * last[:, None] (esrnerf.py:560-566; SphericalGaussian.forward, pbr/module.py:133-143): the
+        fused kernel for the activations it implements, the module's own torch forward for any other name the reference's
+        getattr lookup accepts"""
+        env = self.envmap
+        act_id = fused.SG_ACT_IDS.get(getattr(env.activation, "__name__", ""))
+        if act_id is None or not dirs.is_cuda or env.mus.shape[0] > 64:
+            return add + env(dirs) * last.unsqueeze(-1)
+        lobes = F.normalize(env.lobes, dim=-1)
+        lambdas = torch.abs(env.lambdas).reshape(-1)
+        return fused.SgEnvmap.apply(dirs, env.mus, lambdas, lobes, act_id, last, add)
 
     def _shade(self, sc, pos, use, flats, emo_grid=None, sdf_grid=None):
         grids = (self.sdf.grid if sdf_grid is None else sdf_grid, self.off_color.grid,
@@ -168,16 +184,12 @@ class ESRNeRF(VoxurfF):
         d_flat = dirs.flatten(0, 1).contiguous()
         # incoming radiance: the secondary rays go through the whole render chain (esrnerf.py:576-652)
         off_m, emo_m, last2, st2, hw2 = self._secondary(flats, ex(pts, 3).contiguous(), d_flat)
-        env = self.envmap(d_flat) * last2.unsqueeze(-1)
-        # Disney reflectance x marched radiance, Monte-Carlo mean over the directions, both outgoing directions: one
-        # kernel (esr_lts_accumulate) instead of the reference's elementwise swarm (esrnerf.py:556-574, 654-666)
-        off_hat, reflect = fused.LtsAccumulate.apply(base, rough.reshape(-1), metal.reshape(-1), off_m + env, emo_m, normal,
-                                                     -viewdirs, -v_rand, d_flat, n2)
-        if self.pdra_mode:   # esrnerf.py:668-675
-            um = umask.repeat(2)[:, None]
-            emo_hat = torch.where(um, emission.repeat(2, 1) + reflect.detach(), reflect)
-        else:
-            emo_hat = emission.repeat(2, 1) + reflect
+        rad_off = self._env_radiance(d_flat, last2, off_m)       # off_m + envmap(d) * T_last  (esrnerf.py:560-566)
+        # Disney reflectance x marched radiance, Monte-Carlo mean over the directions, both outgoing directions, and the
+        # emission / PDRA mix of esrnerf.py:668-677: one kernel (esr_lts_accumulate) instead of the reference's
+        # elementwise swarm (esrnerf.py:556-574, 654-677)
+        off_hat, emo_hat = fused.LtsAccumulate.apply(base, rough.reshape(-1), metal.reshape(-1), rad_off, emo_m, normal,
+                                                     -viewdirs, -v_rand, d_flat, n2, emission, umask, self.pdra_mode)
         if self.keep_streams:
             self.last_streams["lts"] = dict(streams=st2, h_w=hw2.detach())
         return dict(off=off, emo=emo, off_hat=off_hat, emo_hat=emo_hat)

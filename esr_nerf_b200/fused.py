@@ -865,17 +865,23 @@ class LtsAccumulate(torch.autograd.Function):
     over the directions — one kernel forward, one backward (esr_lts_accumulate_*).  rad_off may be None (finetune)."""
 
     @staticmethod
-    def forward(ctx, base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs, n_dirs):
+    def forward(ctx, base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs, n_dirs, emission=None, umask=None,
+                pdra_mode=False):
+        """emission (optional, [P,3]): the second output is emo_hat of esrnerf.py:668-677 instead of reflect — emission +
+        reflect, or in pdra_mode emission + stop-gradient(reflect) on uncertain rays' points (umask) and reflect elsewhere"""
         P = base.shape[0]
         dev = base.device
-        t = [x.contiguous().float() if x is not None else None for x in (base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs)]
-        base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs = t
+        t = [x.contiguous().float() if x is not None else None
+             for x in (base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs, emission)]
+        base, rough, metal, rad_off, rad_emo, normal, wo_a, wo_b, dirs, emission = t
+        um8 = umask.to(torch.uint8).contiguous() if (umask is not None and emission is not None) else None
         off_hat = _f32(2 * P, 3, dev=dev) if rad_off is not None else None
         reflect = _f32(2 * P, 3, dev=dev)
         check(_lib.lib().esr_lts_accumulate_fwd(ptr(normal), ptr(base), ptr(rough), ptr(metal), ptr(wo_a), ptr(wo_b), ptr(dirs),
                                                 ptr(rad_off), ptr(rad_emo), P, int(n_dirs), ptr(off_hat), ptr(reflect),
-                                                stream_ptr()))
-        ctx.n_dirs, ctx.has_off = int(n_dirs), rad_off is not None
+                                                ptr(emission), ptr(um8), int(bool(pdra_mode)), stream_ptr()))
+        ctx.n_dirs, ctx.has_off, ctx.pdra = int(n_dirs), rad_off is not None, bool(pdra_mode)
+        ctx.emission, ctx.um8 = emission, um8
         ctx.save_for_backward(base, rough, metal, rad_emo, normal, wo_a, wo_b, dirs, *([rad_off] if rad_off is not None else []))
         return (off_hat if off_hat is not None else reflect.new_zeros(0, 3)), reflect
 
@@ -889,11 +895,60 @@ class LtsAccumulate(torch.autograd.Function):
         g_base, g_rough, g_metal = _f32(P, 3, dev=dev), torch.empty_like(rough), torch.empty_like(metal)
         g_rad_emo = torch.empty_like(rad_emo)
         g_rad_off = torch.empty_like(rad_off) if rad_off is not None else None
+        g_emission = _f32(P, 3, dev=dev) if ctx.emission is not None else None
         if P:
             g_off_hat = g_off_hat.contiguous() if rad_off is not None else None   # named: must outlive the launch
             g_reflect = g_reflect.contiguous()
             check(_lib.lib().esr_lts_accumulate_bwd(ptr(normal), ptr(base), ptr(rough), ptr(metal), ptr(wo_a), ptr(wo_b),
                                                     ptr(dirs), ptr(rad_off), ptr(rad_emo), P, ctx.n_dirs,
                                                     ptr(g_off_hat), ptr(g_reflect), ptr(g_base), ptr(g_rough), ptr(g_metal),
-                                                    ptr(g_rad_off), ptr(g_rad_emo), stream_ptr()))
-        return g_base, g_rough, g_metal, g_rad_off, g_rad_emo, None, None, None, None, None
+                                                    ptr(g_rad_off), ptr(g_rad_emo), ptr(ctx.emission), ptr(ctx.um8),
+                                                    int(ctx.pdra), ptr(g_emission), stream_ptr()))
+        return g_base, g_rough, g_metal, g_rad_off, g_rad_emo, None, None, None, None, None, g_emission, None, None
+
+
+SG_ACT_IDS = {"softplus": 1, "relu": 2, "abs": 3, "exp": 4, "sigmoid": 5}
+
+
+class SgEnvmap(torch.autograd.Function):
+    """add + act(sum_k mus_k exp(lambdas_k (d . lobes_k - 1))) * scale over the secondary rays (pbr/module.py:133-143 with
+    its use at esrnerf.py:560-566 fused in): one kernel forward, one backward.  `lambdas` non-negative [K], `lobes` unit
+    [K,3] — the caller's abs / F.normalize stay in torch, autograd carries their (tiny) backward."""
+
+    @staticmethod
+    def forward(ctx, dirs, mus, lambdas, lobes, act_id, scale, add):
+        dirs, mus, lambdas, lobes = (t.contiguous().float() for t in (dirs, mus, lambdas, lobes))
+        scale = scale.contiguous().float() if scale is not None else None
+        add = add.contiguous().float() if add is not None else None
+        m = dirs.shape[0]
+        out = _f32(m, 3, dev=dirs.device)
+        check(_lib.lib().esr_sg_envmap_fwd(ptr(dirs), ptr(mus), ptr(lambdas), ptr(lobes), mus.shape[0], int(act_id), ptr(scale),
+                                           ptr(add), m, ptr(out), stream_ptr()))
+        ctx.act_id, ctx.has_add, ctx.has_scale = int(act_id), add is not None, scale is not None
+        ctx.save_for_backward(dirs, mus, lambdas, lobes, *([scale] if scale is not None else []))
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_out):
+        dirs, mus, lambdas, lobes = ctx.saved_tensors[:4]
+        scale = ctx.saved_tensors[4] if ctx.has_scale else None
+        g_out = g_out.contiguous()
+        g_mus, g_lam, g_lobes = torch.zeros_like(mus), torch.zeros_like(lambdas), torch.zeros_like(lobes)
+        g_scale = torch.empty_like(scale) if scale is not None else None
+        check(_lib.lib().esr_sg_envmap_bwd(ptr(dirs), ptr(mus), ptr(lambdas), ptr(lobes), mus.shape[0], ctx.act_id, ptr(scale),
+                                           dirs.shape[0], ptr(g_out), ptr(g_mus), ptr(g_lam), ptr(g_lobes), ptr(g_scale),
+                                           stream_ptr()))
+        return None, g_mus, g_lam, g_lobes, None, g_scale, (g_out if ctx.has_add else None)
+
+
+@torch.no_grad()
+def lts_scatter_dirs(normal, number: int, noise=None, table=None):
+    """hemisphere directions [P, number, 3] of the LTS points (pbr/functions.py:10-32): one kernel (esr_lts_scatter_dirs)"""
+    P = normal.shape[0]
+    normal = normal.contiguous().float()
+    noise = noise.contiguous().float() if noise is not None else None
+    table = table.contiguous().float() if table is not None else None
+    dirs = _f32(P, number, 3, dev=normal.device)
+    check(_lib.lib().esr_lts_scatter_dirs(ptr(normal), ptr(noise), ptr(table), P, int(number), ptr(dirs), stream_ptr()))
+    return dirs

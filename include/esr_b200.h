@@ -281,16 +281,39 @@ int esr_sdf_expgrad_bwd(const esr_scene_t *sc, const float *pts, int64_t m, cons
  * (rows [0,n_pts): wo_a, rows [n_pts, 2 n_pts): wo_b) with the Disney-style reflectance R.  Backward: cotangents of the
  * two outputs -> g_base [n_pts,3], g_rough / g_metal [n_pts], g_rad_off / g_rad_emo [n_pts*n_dirs,3]; normals and
  * directions carry no gradient (esrnerf.py:790: detached normal; pbr/functions.py:9: no_grad sampling).
+ * emission (nullable, [n_pts,3]) switches the second output to emo_hat of esrnerf.py:668-677: emission + reflect, or with
+ * pdra_mode != 0: emission + stop-gradient(reflect) for a point on an UNCERTAIN ray (umask [n_pts] u8 != 0), reflect
+ * alone otherwise; the backward then takes emo_hat's cotangent as g_reflect and also returns g_emission [n_pts,3].
  */
 int esr_lts_accumulate_fwd(const float *normal, const float *base, const float *rough, const float *metal,
                            const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
                            const float *rad_emo, int64_t n_pts, int n_dirs, float *off_hat, float *reflect,
-                           esr_stream_t stream);
+                           const float *emission, const uint8_t *umask, int pdra_mode, esr_stream_t stream);
 int esr_lts_accumulate_bwd(const float *normal, const float *base, const float *rough, const float *metal,
                            const float *wo_a, const float *wo_b, const float *dirs, const float *rad_off,
                            const float *rad_emo, int64_t n_pts, int n_dirs, const float *g_off_hat,
                            const float *g_reflect, float *g_base, float *g_rough, float *g_metal, float *g_rad_off,
-                           float *g_rad_emo, esr_stream_t stream);
+                           float *g_rad_emo, const float *emission, const uint8_t *umask, int pdra_mode,
+                           float *g_emission, esr_stream_t stream);
+/*
+ * Hemisphere directions of the light-transport segment (app/utils/pbr/functions.py:10-32): n_dirs directions per point —
+ * the normalised Gaussian draw `noise` [n_pts*n_dirs,3] (diffuse_scattering) or, with noise = NULL, the fixed spiral
+ * `table` [n_dirs,3] (diffuse_scattering_fib) — mirrored into the hemisphere of the point's normal -> dirs [n_pts*n_dirs,3].
+ */
+int esr_lts_scatter_dirs(const float *normal, const float *noise, const float *table, int64_t n_pts, int n_dirs,
+                         float *dirs, esr_stream_t stream);
+/*
+ * Spherical-Gaussian environment map (app/utils/pbr/module.py:133-143) on m directions, with its use in the light-transport
+ * segment fused in (esrnerf.py:560-566): out [m,3] = add + act(sum_k mus_k exp(lambdas_k (d . lobes_k - 1))) * scale.
+ * mus [n_sg,3]; lambdas [n_sg] (already |.|); lobes [n_sg,3] (already unit); n_sg <= 64; act: 1 softplus, 2 relu,
+ * 3 abs, 4 exp, 5 sigmoid; scale [m] / add [m,3] nullable.  Backward: g_out -> g_mus / g_lambdas / g_lobes (ACCUMULATED,
+ * atomics) and g_scale [m] (iff scale); the cotangent of `add` is g_out itself; directions carry no gradient.
+ */
+int esr_sg_envmap_fwd(const float *dirs, const float *mus, const float *lambdas, const float *lobes, int n_sg, int act,
+                      const float *scale, const float *add, int64_t m, float *out, esr_stream_t stream);
+int esr_sg_envmap_bwd(const float *dirs, const float *mus, const float *lambdas, const float *lobes, int n_sg, int act,
+                      const float *scale, int64_t m, const float *g_out, float *g_mus, float *g_lambdas, float *g_lobes,
+                      float *g_scale, esr_stream_t stream);
 
 /*
  * Coarse-stage feature encode (voxurfc.py:205-249): trilinear tap of the dense central-difference gradient volume

@@ -313,3 +313,91 @@ def test_lts_accumulate_kernel_vs_torch_disney(with_off):
             assert y.grad is None
             continue
         assert C.rel_err(y.grad, x.grad) < 1e-4, i
+
+
+@pytest.mark.parametrize("pdra", [False, True])
+def test_lts_accumulate_emission_mix_vs_torch(pdra):
+    """the emo_hat mix fused into esr_lts_accumulate (esrnerf.py:668-677): emission + reflect, PDRA: emission +
+    stop-gradient(reflect) on uncertain rays' points / reflect alone on the others — values and gradients vs torch"""
+    import torch.nn.functional as F
+
+    from esr_nerf_b200 import fused, pbr
+
+    g = torch.Generator().manual_seed(1)
+    P, n2 = 53, 11
+    normal = F.normalize(torch.randn(P, 3, generator=g), dim=-1).to(DEV)
+    d_flat = pbr.diffuse_scattering(normal, torch.randn(P, n2, 3, generator=g).to(DEV)).flatten(0, 1)
+    wo_a, wo_b = (F.normalize(torch.randn(P, 3, generator=g), dim=-1).to(DEV) for _ in range(2))
+    umask = (torch.rand(P, generator=g) < 0.5).to(DEV)
+    leaves = [torch.rand(P, 3, generator=g), torch.rand(P, generator=g) * 0.9 + 0.05, torch.rand(P, generator=g),
+              torch.rand(P * n2, 3, generator=g), torch.rand(P, 3, generator=g)]
+    a = [t.to(DEV).requires_grad_(True) for t in leaves]
+    b = [t.to(DEV).requires_grad_(True) for t in leaves]
+    cot = torch.randn(2 * P, 3, generator=g).to(DEV)
+    base, rough, metal, le, emission = a
+    _, reflect = fused.LtsAccumulate.apply(base, rough, metal, None, le, normal, wo_a, wo_b, d_flat, n2)
+    if pdra:
+        want = torch.where(umask.repeat(2)[:, None], emission.repeat(2, 1) + reflect.detach(), reflect)
+    else:
+        want = emission.repeat(2, 1) + reflect
+    (want * cot).sum().backward()
+    base2, rough2, metal2, le2, emission2 = b
+    _, got = fused.LtsAccumulate.apply(base2, rough2, metal2, None, le2, normal, wo_a, wo_b, d_flat, n2, emission2, umask, pdra)
+    (got * cot).sum().backward()
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)      # (the kernel's mean-and-add is one fused multiply-add)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert torch.allclose(y.grad, x.grad, rtol=1e-5, atol=1e-7), i   # same kernel arithmetic; the mix only gates it
+
+
+@pytest.mark.parametrize("activation", ["softplus", "relu", "abs", "exp", "sigmoid"])
+def test_sg_envmap_kernel_vs_module(activation):
+    """esr_sg_envmap_fwd/bwd (environment map of the secondary rays with `* T_last` and `+ off_m` fused in,
+    esrnerf.py:560-566) against SphericalGaussian.forward (pbr/module.py:133-143, torch): values 1e-5, gradients of
+    mus / lambdas / lobes / T_last / off_m 1e-4"""
+    import torch.nn.functional as F
+
+    from esr_nerf_b200 import fused
+    from esr_nerf_b200.modules import SphericalGaussian
+
+    torch.manual_seed(3)
+    env_a, env_b = SphericalGaussian(48, activation).to(DEV), SphericalGaussian(48, activation).to(DEV)
+    env_b.load_state_dict(env_a.state_dict())
+    g = torch.Generator().manual_seed(4)
+    M = 5000
+    dirs = F.normalize(torch.randn(M, 3, generator=g), dim=-1).to(DEV)
+    last_a, add_a = torch.rand(M, generator=g).to(DEV).requires_grad_(True), torch.rand(M, 3, generator=g).to(DEV).requires_grad_(True)
+    last_b, add_b = last_a.detach().clone().requires_grad_(True), add_a.detach().clone().requires_grad_(True)
+    cot = torch.randn(M, 3, generator=g).to(DEV)
+    want = add_a + env_a(dirs) * last_a.unsqueeze(-1)
+    (want * cot).sum().backward()
+    lobes = F.normalize(env_b.lobes, dim=-1)
+    got = fused.SgEnvmap.apply(dirs, env_b.mus, torch.abs(env_b.lambdas).reshape(-1), lobes, fused.SG_ACT_IDS[activation],
+                               last_b, add_b)
+    (got * cot).sum().backward()
+    assert C.rel_err(got, want) < 1e-5
+    for name in ("mus", "lambdas", "lobes"):
+        assert C.rel_err(getattr(env_b, name).grad, getattr(env_a, name).grad) < 1e-4, name
+    assert C.rel_err(last_b.grad, last_a.grad) < 1e-4 and torch.equal(add_b.grad, add_a.grad)
+
+
+@pytest.mark.parametrize("fib", [False, True])
+def test_lts_scatter_dirs_kernel_vs_torch(fib):
+    """esr_lts_scatter_dirs against pbr.diffuse_scattering / diffuse_scattering_fib (pbr/functions.py:10-32)"""
+    import torch.nn.functional as F
+
+    from esr_nerf_b200 import fused, pbr
+
+    g = torch.Generator().manual_seed(6)
+    P, n = 301, 257
+    normal = F.normalize(torch.randn(P, 3, generator=g), dim=-1).to(DEV)
+    if fib:
+        want = pbr.diffuse_scattering_fib(normal, n)
+        got = fused.lts_scatter_dirs(normal, n, table=pbr.fibonacci_hemisphere(n).to(DEV))
+        assert torch.equal(got, want)
+    else:
+        noise = torch.randn(P, n, 3, generator=g).to(DEV)
+        want = pbr.diffuse_scattering(normal, noise)
+        got = fused.lts_scatter_dirs(normal, n, noise=noise)
+        # x / max(|x|, eps) vs x * (1 / max(|x|, eps)): one rounding apart
+        assert torch.allclose(got, want, rtol=0, atol=2e-7) and torch.equal(torch.sign(got), torch.sign(want))
+    assert ((got * normal[:, None]).sum(-1) >= 0).all()
