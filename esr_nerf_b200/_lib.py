@@ -18,7 +18,8 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
-SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu", "optim.cu", "grad_exchange.cu"]
+SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu", "optim.cu", "grad_exchange.cu",
+           "regularizers.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -201,6 +202,11 @@ PROTOTYPES = {
     "esr_mlp_fwd": (I32, [DESC_P, P, P, I64, I64, I64, P, P, I64, P]),
     "esr_mlp_bwd": (I32, [DESC_P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, I32, P, P]),
     "esr_mlp_bwd_weights": (I32, [DESC_P, P, I64, I64, I64, P, P, P, P]),
+    "esr_grid_tv_fwd": (I32, [P, P, I32, I64, I64, I64, I64, I64, I64, I64, P, P]),
+    "esr_grid_tv_bwd": (I32, [P, P, I32, I64, I64, I64, I64, I64, I64, I64, P, P, F32, P, P]),
+    "esr_sdf_central_gradient": (I32, [P, I64, I64, I64, F32, P, P]),
+    "esr_smooth_grad_tv_fwd": (I32, [P, P, I64, I64, I64, P, F32, P, P, P]),
+    "esr_smooth_grad_tv_bwd": (I32, [P, I64, I64, I64, F32, P, P, F32, P, P]),
 }
 
 

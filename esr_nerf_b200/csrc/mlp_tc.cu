@@ -753,6 +753,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 //     the warps read, convert, save and reduce.
 // Synchronisation: the chunk barriers live in the leader CTA and count the 32 epilogue warps of both CTAs (the peer's
 // arrive through shared::cluster); every commit is multicast to the MMA barrier of both CTAs.
+// Tried and withdrawn (round 2, measured at config 2 where this version takes 3.56 ms per step): issuing every layer as
+// two (N = 96) or three (N = 64) column blocks with their own commits, so that a block's epilogue runs under the MMAs of
+// the next — 3.97 ms and 4.37 ms.  The narrower MMAs do not run proportionally faster (a cta_group::2 MMA of N = 64 costs
+// about what N = 128 does), which more than eats the overlap; N = 192 per instruction it stays.
 constexpr uint32_t X2_D = 0, X2_X0 = 384, X2_X1 = 432;
 
 template <int K0, int NH, int NO>

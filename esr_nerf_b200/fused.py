@@ -952,3 +952,95 @@ def lts_scatter_dirs(normal, number: int, noise=None, table=None):
     dirs = _f32(P, number, 3, dev=normal.device)
     check(_lib.lib().esr_lts_scatter_dirs(ptr(normal), ptr(noise), ptr(table), P, int(number), ptr(dirs), stream_ptr()))
     return dirs
+
+
+# ---------------------------------------------------------------------------------------------------
+# dense-grid loss terms of the stage drivers: csrc/regularizers.cu
+# ---------------------------------------------------------------------------------------------------
+def _mask_u8(mask, shape):
+    if mask is None:
+        return None
+    m = mask.reshape(-1)[: shape[0] * shape[1] * shape[2]] if mask.numel() != shape[0] * shape[1] * shape[2] else mask
+    return m.reshape(shape).contiguous().view(torch.uint8) if m.dtype == torch.bool else m.reshape(shape).to(torch.uint8).contiguous()
+
+
+class GridTV(torch.autograd.Function):
+    """total_variation(v, mask) of app/utils/base/functions.py:34-42 on a [1,C,X,Y,Z] grid in whatever memory layout it has
+    (contiguous SDF grid, channels-last colour grid): mean |forward difference| per axis over the pairs with both voxels in
+    `mask` ([1,1,X,Y,Z] bool, shared by the channels), averaged over the axes.  One launch forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, v, mask):
+        C, X, Y, Z = v.shape[1:]
+        m8 = _mask_u8(mask, (X, Y, Z))
+        acc = torch.empty(6, dtype=torch.float64, device=v.device)
+        st = v.stride()[1:]
+        check(_lib.lib().esr_grid_tv_fwd(ptr(v), ptr(m8), C, X, Y, Z, *st, ptr(acc), stream_ptr()))
+        ctx.save_for_backward(v, acc, *([m8] if m8 is not None else []))
+        return ((acc[0] / acc[3] + acc[1] / acc[4] + acc[2] / acc[5]) / 3).float()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        v, acc = ctx.saved_tensors[:2]
+        m8 = ctx.saved_tensors[2] if len(ctx.saved_tensors) > 2 else None
+        C, X, Y, Z = v.shape[1:]
+        grad = torch.zeros_like(v)            # (preserves the grid's memory layout)
+        g = g.reshape(1).float().contiguous()
+        check(_lib.lib().esr_grid_tv_bwd(ptr(v), ptr(m8), C, X, Y, Z, *v.stride()[1:], ptr(acc), ptr(g), 1.0, ptr(grad),
+                                         stream_ptr()))
+        return grad, None
+
+
+class SmoothGradTV(torch.autograd.Function):
+    """mean over the masked voxels and the three components of (conv3(grad) - grad)^2, grad = neus_sdf_gradient()
+    (voxurff.py:610-616, 723-742; fixed 3x3x3 kernel of GradientConv, replicate padding, the smoothed volume detached)."""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, mask, w27, bias, voxel_size):
+        X, Y, Z = sdf_grid.shape[2:]
+        sdf = sdf_grid.contiguous()
+        m8 = _mask_u8(mask, (X, Y, Z))
+        L = _lib.lib()
+        gvol = torch.empty(3, X, Y, Z, dtype=torch.float32, device=sdf.device)
+        check(L.esr_sdf_central_gradient(ptr(sdf), X, Y, Z, float(voxel_size), ptr(gvol), stream_ptr()))
+        err = torch.empty_like(gvol)
+        acc = torch.empty(2, dtype=torch.float64, device=sdf.device)
+        w27 = w27.reshape(-1).float().contiguous()
+        check(L.esr_smooth_grad_tv_fwd(ptr(gvol), ptr(m8), X, Y, Z, ptr(w27), float(bias), ptr(acc), ptr(err), stream_ptr()))
+        ctx.voxel_size = float(voxel_size)
+        ctx.save_for_backward(err, acc)
+        ctx.shape = tuple(sdf_grid.shape)
+        return (acc[0] / acc[1]).float()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        err, acc = ctx.saved_tensors
+        X, Y, Z = ctx.shape[2:]
+        grad = torch.zeros(ctx.shape, dtype=torch.float32, device=err.device)
+        g = g.reshape(1).float().contiguous()
+        check(_lib.lib().esr_smooth_grad_tv_bwd(ptr(err), X, Y, Z, ctx.voxel_size, ptr(acc), ptr(g), 1.0, ptr(grad), stream_ptr()))
+        return grad, None, None, None, None
+
+
+class SdfCentralGradient(torch.autograd.Function):
+    """neus_sdf_gradient (voxurff.py:723-742): [1,3,X,Y,Z] central differences / 2 / voxel_size, zero on the boundary faces"""
+
+    @staticmethod
+    def forward(ctx, sdf_grid, voxel_size):
+        X, Y, Z = sdf_grid.shape[2:]
+        sdf = sdf_grid.contiguous()
+        out = torch.empty(1, 3, X, Y, Z, dtype=torch.float32, device=sdf.device)
+        check(_lib.lib().esr_sdf_central_gradient(ptr(sdf), X, Y, Z, float(voxel_size), ptr(out), stream_ptr()))
+        ctx.voxel_size, ctx.shape = float(voxel_size), tuple(sdf_grid.shape)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        X, Y, Z = ctx.shape[2:]
+        g = g.contiguous().float()
+        grad = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        check(_lib.lib().esr_smooth_grad_tv_bwd(ptr(g), X, Y, Z, ctx.voxel_size, None, None, 1.0, ptr(grad), stream_ptr()))
+        return grad, None

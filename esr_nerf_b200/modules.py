@@ -463,9 +463,18 @@ class GridRegularizers:
     not involved.  The reference refreshes `self.gradient` in every forward (Q16) although only these methods read
     it; here it is derived from the current SDF grid on demand — same values, same autograd graph."""
 
+    def _voxel_size_host(self) -> float:
+        vs = self.voxel_size
+        return float(vs) if not torch.is_tensor(vs) else float(host_geometry(self, getattr(self, "stepsize", 0.5))["voxel_size"])
+
     def neus_sdf_gradient(self) -> torch.Tensor:
-        """voxurff.py:723-742: dense central-difference gradient volume [1,3,X,Y,Z] (zero on the boundary faces)"""
+        """voxurff.py:723-742: dense central-difference gradient volume [1,3,X,Y,Z] (zero on the boundary faces); one kernel
+        each way on the GPU (fused.SdfCentralGradient), the reference's sliced assignments on host tensors"""
         g = self.sdf.grid
+        if g.is_cuda:
+            from . import fused
+
+            return fused.SdfCentralGradient.apply(g, self._voxel_size_host())
         out = torch.zeros([1, 3, *g.shape[-3:]], device=g.device)
         out[:, 0, 1:-1, :, :] = (g[:, 0, 2:, :, :] - g[:, 0, :-2, :, :]) / 2 / self.voxel_size
         out[:, 1, :, 1:-1, :] = (g[:, 0, :, 2:, :] - g[:, 0, :, :-2, :]) / 2 / self.voxel_size
@@ -473,8 +482,21 @@ class GridRegularizers:
         return out
 
     def density_total_variation(self, sdf_tv: float = 0, smooth_grad_tv: float = 0):
-        """voxurff.py:600-617"""
+        """voxurff.py:600-617.  GPU: one kernel forward + one backward per term (csrc/regularizers.cu) instead of the ~25 dense
+        torch ops and their autograd graph; host tensors: the reference's torch formulation (what the CPU parity test pins)."""
         tv = 0
+        if self.sdf.grid.is_cuda:
+            from . import fused
+
+            h = self._voxel_size_host()
+            if sdf_tv > 0:
+                tv = tv + fused.GridTV.apply(self.sdf.grid, self.nonempty_mask) / 2 / h * sdf_tv
+            if smooth_grad_tv > 0:
+                conv = self.tv_smooth_conv.m
+                tv = tv + fused.SmoothGradTV.apply(self.sdf.grid, self.nonempty_mask, conv.weight.detach(),
+                                                   float(conv.bias.detach().reshape(-1)[0]) if conv.bias is not None else 0.0,
+                                                   h) * smooth_grad_tv
+            return tv
         if sdf_tv > 0:
             tv = tv + total_variation(self.sdf.grid, self.nonempty_mask) / 2 / self.voxel_size * sdf_tv
         if smooth_grad_tv > 0:
@@ -487,6 +509,10 @@ class GridRegularizers:
     def color_total_variation(self):
         """voxurfc.py:542-548"""
         v1, v2 = self.off_color.grid, self.emo_color.grid
+        if v1.is_cuda:
+            from . import fused
+
+            return fused.GridTV.apply(v1, self.nonempty_mask) + fused.GridTV.apply(v2, self.nonempty_mask)
         return (total_variation(v1, self.nonempty_mask.repeat(1, v1.shape[1], 1, 1, 1)) +
                 total_variation(v2, self.nonempty_mask.repeat(1, v2.shape[1], 1, 1, 1)))
 

@@ -96,6 +96,37 @@ int esr_segment_sum_bwd(const float *grad_out, const int64_t *index, int64_t n_p
 int esr_tv_add_grad(const float *param, float *grad, float wx, float wy, float wz, int64_t sz_i,
                     int64_t sz_j, int64_t sz_k, int64_t n_total, int dense_mode, esr_stream_t stream);
 
+/*
+ * Dense-grid loss terms of the stage drivers, one launch forward and one backward each.
+ *
+ * total_variation(v, mask) (app/utils/base/functions.py:34-42; voxurff.py:603-609, voxurfc.py:523-548): v is a
+ * [channels][X][Y][Z] view given by element strides (contiguous SDF grid or channels-last colour grid), mask (nullable)
+ * u8 [X][Y][Z].  fwd: acc6 (device, f64) <- per-axis sums of |v[p + e_a] - v[p]| over pairs with both voxels in the mask
+ * (all channels) and the three pair counts; the loss is (acc[0] / acc[3] + acc[1] / acc[4] + acc[2] / acc[5]) / 3.
+ * bwd: grad (same strides as v) += *g_out * scale * d loss / d v; g_out is a DEVICE scalar (no host read).
+ */
+int esr_grid_tv_fwd(const float *v, const uint8_t *mask, int channels, int64_t X, int64_t Y, int64_t Z, int64_t stride_c,
+                    int64_t stride_x, int64_t stride_y, int64_t stride_z, double *acc6, esr_stream_t stream);
+int esr_grid_tv_bwd(const float *v, const uint8_t *mask, int channels, int64_t X, int64_t Y, int64_t Z, int64_t stride_c,
+                    int64_t stride_x, int64_t stride_y, int64_t stride_z, const double *acc6, const float *g_out,
+                    float scale, float *grad, esr_stream_t stream);
+/*
+ * neus_sdf_gradient (voxurff.py:723-742): out [3][X][Y][Z] = central differences of the SDF grid / 2 / voxel_size, zero on
+ * the two boundary faces of each axis.
+ * Smooth-gradient term (voxurff.py:610-616): err = conv3(grad_vol) + bias - grad_vol on masked voxels with the fixed
+ * 3x3x3 kernel w27 of GradientConv (module.py:180-211; replicate padding; the smoothed volume is detached);
+ * fwd: acc2 (device, f64) <- (sum err^2, 3 * masked voxels), err_vol [3][X][Y][Z] <- err (0 outside the mask); the loss is
+ * acc[0] / acc[1].  bwd: grad_sdf [X][Y][Z] += *g_out * scale * d loss / d sdf (through the central differences).
+ * With acc2 = g_out = NULL the backward is the plain transpose of the central differences: grad_sdf += scale *
+ * (cotangent err_vol of esr_sdf_central_gradient's output pulled back to the grid).
+ */
+int esr_sdf_central_gradient(const float *sdf, int64_t X, int64_t Y, int64_t Z, float voxel_size, float *out,
+                             esr_stream_t stream);
+int esr_smooth_grad_tv_fwd(const float *grad_vol, const uint8_t *mask, int64_t X, int64_t Y, int64_t Z, const float *w27,
+                           float bias, double *acc2, float *err_vol, esr_stream_t stream);
+int esr_smooth_grad_tv_bwd(const float *err_vol, int64_t X, int64_t Y, int64_t Z, float voxel_size, const double *acc2,
+                           const float *g_out, float scale, float *grad_sdf, esr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 2. Fused pipeline (int32 packed streams; one warp per ray for ray-ordered stages)
  * ---------------------------------------------------------------------------------------- */
