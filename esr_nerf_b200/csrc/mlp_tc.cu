@@ -647,13 +647,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // bias + ReLU -> bf16 -> TMEM A operand (+ global copy, tiled layout, for the backward pass)
         const float *b = sbias + l * TC_W;
         uint4 *hl = hidden ? reinterpret_cast<uint4 *>(hidden + (int64_t)l * act_rows_padded(m_total) * TC_W) : nullptr;
+        // chunk cc is converted while chunk cc + 1 is still coming out of TMEM (the next layer accumulates in the other D
+        // region, so nothing overwrites the columns not yet read): the first K-steps of the next layer start a third of
+        // an accumulator read after the commit instead of a whole one
         uint32_t r[3][16];
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + tm_d(l) + TC_GCOLS * et.grp + 16 * cc, r[cc]);
-        tmem_ld_wait();
+        const uint32_t d_cols = tmem + et.lane_base + tm_d(l) + TC_GCOLS * et.grp;
+        tmem_ld16(d_cols, r[0]);
         uint32_t mask[2] = {0u, 0u};
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
+          tmem_ld_wait();
+          if (cc < 2) tmem_ld16(d_cols + 16 * (cc + 1), r[cc + 1]);
           const int col0 = TC_GCOLS * et.grp + 16 * cc;
           uint32_t p[8];
 #pragma unroll
@@ -1480,12 +1484,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         tc_fence_after();
         // dZ_l = dH_l * [H_l > 0] -> bf16 -> TMEM A operand + global copy (tiled) for the weight-gradient GEMM
-        uint32_t r[3][16];
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) tmem_ld16(tmem + et.lane_base + tm_d(i) + TC_GCOLS * et.grp + 16 * cc, r[cc]);
-        tmem_ld_wait();
+        uint32_t r[3][16];   // (chunk cc + 1 comes out of TMEM while chunk cc is converted: see k_mlp_fwd_tc)
+        const uint32_t d_cols = tmem + et.lane_base + tm_d(i) + TC_GCOLS * et.grp;
+        tmem_ld16(d_cols, r[0]);
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
+          tmem_ld_wait();
+          if (cc < 2) tmem_ld16(d_cols + 16 * (cc + 1), r[cc + 1]);
           const int col0 = TC_GCOLS * et.grp + 16 * cc;
           const uint32_t mk = mask[cc >> 1] >> (8 * (cc & 1));   // pair j: bits (j, 16 + j)
           uint32_t p[8];
