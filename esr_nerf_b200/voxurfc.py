@@ -104,6 +104,8 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
     def neus_sdf_gradient(self) -> torch.Tensor:
         """voxurfc.py:597-616 — dense central differences of the RAW sdf grid, channels (d/dx, d/dy, d/dz)"""
         g = self.sdf.grid
+        if g.is_cuda:      # one kernel each way (csrc/regularizers.cu) instead of zeros + three sliced assignments
+            return fused.SdfCentralGradient.apply(g, host_geometry(self, self.stepsize)["voxel_size"])
         out = torch.zeros([1, 3, *g.shape[-3:]], device=g.device)
         out[:, 0, 1:-1, :, :] = (g[:, 0, 2:, :, :] - g[:, 0, :-2, :, :]) / 2 / self.voxel_size
         out[:, 1, :, 1:-1, :] = (g[:, 0, :, 2:, :] - g[:, 0, :, :-2, :]) / 2 / self.voxel_size
