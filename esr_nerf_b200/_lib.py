@@ -202,6 +202,7 @@ PROTOTYPES = {
     "esr_mlp_fwd": (I32, [DESC_P, P, P, I64, I64, I64, P, P, I64, P]),
     "esr_mlp_bwd": (I32, [DESC_P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, I32, P, P]),
     "esr_mlp_bwd_weights": (I32, [DESC_P, P, I64, I64, I64, P, P, P, P]),
+    "esr_rows_to_mlp_tiles": (I32, [P, I64, I32, P, I32, P, P]),
     "esr_grid_tv_fwd": (I32, [P, P, I32, I64, I64, I64, I64, I64, I64, I64, P, P]),
     "esr_grid_tv_bwd": (I32, [P, P, I32, I64, I64, I64, I64, I64, I64, I64, P, P, F32, P, P]),
     "esr_sdf_central_gradient": (I32, [P, I64, I64, I64, F32, P, P]),

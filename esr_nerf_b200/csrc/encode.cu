@@ -1024,3 +1024,56 @@ extern "C" int esr_composite_bwd(const int32_t *h_ray, const int32_t *h_m1, cons
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// f32 rows -> the tiled 16-bit MLP input layout (the coarse stage: its 72-column feature rows are made by
+// esr_encode_coarse_fwd in f32; its colour nets run on the 96 -> 192 tcgen05 chains).  Column c of the
+// 96-wide input row takes column colmap[c] of the source row (or 0 for colmap[c] < 0).  precision 0: bf16 tiles;
+// 1: fp16 tiles followed by the fp16 residual tiles (as esr_encode_fwd with out_is_bf16 = 2).  Thread per (row, 8-column chunk).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+    k_rows_to_tiles(const float *__restrict__ src, int64_t m, int ld, const int32_t *__restrict__ colmap, int precision,
+                    uint4 *__restrict__ tiles) {
+  constexpr int CH = ESR_FEAT_DIM / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * CH) return;
+  const int64_t row = i / CH;
+  const int c = (int)(i - row * CH);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int sc = __ldg(colmap + 8 * c + j);
+    v[j] = sc >= 0 ? __ldg(src + row * ld + sc) : 0.f;
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (precision) {
+      const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t *>(&h), lo[j] = *reinterpret_cast<const uint32_t *>(&l);
+    } else {
+      __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      hi[j] = *reinterpret_cast<uint32_t *>(&p);
+    }
+  }
+  const int64_t at = tiled_chunk_index(row, c, CH);
+  tiles[at] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (precision) tiles[act_rows_padded(m) * CH + at] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+}  // namespace
+
+extern "C" int esr_rows_to_mlp_tiles(const float *src, int64_t m, int ld, const int32_t *colmap, int precision, void *tiles,
+                                     esr_stream_t stream) {
+  ESR_CHECK_ARG(m >= 0 && ld > 0 && (precision == 0 || precision == 1));
+  if (m == 0) return ESR_OK;
+  ESR_CHECK_ARG(src && colmap && tiles);
+  ESR_STAGE("k_rows_to_tiles", stream);
+  k_rows_to_tiles<<<cdiv(m * (ESR_FEAT_DIM / 8), 256), 256, 0, (cudaStream_t)stream>>>(src, m, ld, colmap, precision,
+                                                                                     reinterpret_cast<uint4 *>(tiles));
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}

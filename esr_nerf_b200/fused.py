@@ -1044,3 +1044,62 @@ class SdfCentralGradient(torch.autograd.Function):
         grad = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
         check(_lib.lib().esr_smooth_grad_tv_bwd(ptr(g), X, Y, Z, ctx.voxel_size, None, None, 1.0, ptr(grad), stream_ptr()))
         return grad, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# coarse stage: the two 57 -> 128 -> 128 -> 3 sigmoid colour nets (voxurfc.py:137-169, 229-249) on the tcgen05 chains
+# ---------------------------------------------------------------------------------------------------
+COARSE_DESC = dict(k0=96, width=192, n_hidden=3, n_out=3, act=2)      # zero-padded + identity third hidden layer (modules)
+COARSE_GRAD_COLS = 16                                                 # colour taps (12) + normal (3), padded to 16
+
+
+def rows_to_tiles(x: torch.Tensor, colmap: torch.Tensor, precision: int) -> torch.Tensor:
+    """f32 rows [m, ld] -> tiled 16-bit MLP input rows (esr_rows_to_mlp_tiles)"""
+    L = _lib.lib()
+    m = x.shape[0]
+    rows = L.esr_mlp_act_rows(m) * (2 if precision else 1)
+    tiles = torch.empty(rows, FEAT_DIM, dtype=torch.bfloat16, device=x.device)
+    check(L.esr_rows_to_mlp_tiles(ptr(x), m, x.shape[1], ptr(colmap), int(precision), ptr(tiles), stream_ptr()))
+    return tiles
+
+
+class CoarseShade(torch.autograd.Function):
+    """(sigmoid(off_rgbnet([off colour | feat])), sigmoid(emo_rgbnet([emo colour | feat]))) of voxurfc.py:229-240 on the
+    tensor-core chains: x is the f32 [M3,72] row of EncodeCoarse; each net reads its own tiled copy of the row (its colour
+    slot first).  Backward: data gradient of the 15 gradient-carrying columns (colour taps, normal) back into x's layout,
+    weight gradients of both nets."""
+
+    @staticmethod
+    def forward(ctx, x, flat_off, flat_emo, map_off, map_emo, precision):
+        m = x.shape[0]
+        train = any(ctx.needs_input_grad[:3])
+        precision = int(precision) if train else 0
+        desc = with_precision(COARSE_DESC, precision)
+        x = x.contiguous()
+        xt_off, xt_emo = rows_to_tiles(x, map_off, precision), rows_to_tiles(x, map_emo, precision)
+        img_off, img_emo = mlp_pack(desc, flat_off), mlp_pack(desc, flat_emo)
+        rgb_off, hid_off = _mlp_forward(desc, img_off, xt_off, 0, m, m, train)
+        rgb_emo, hid_emo = _mlp_forward(desc, img_emo, xt_emo, 0, m, m, train)
+        ctx.desc, ctx.hidden, ctx.m, ctx.ld = desc, (hid_off, hid_emo), m, x.shape[1]
+        ctx.save_for_backward(xt_off, xt_emo, img_off, img_emo, rgb_off, rgb_emo)
+        return rgb_off, rgb_emo
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_off, d_emo):
+        xt_off, xt_emo, img_off, img_emo, rgb_off, rgb_emo = ctx.saved_tensors
+        m = ctx.m
+        dev = xt_off.device
+        hid_off, hid_emo = ctx.hidden
+        dx_off = torch.empty(m, COARSE_GRAD_COLS, dtype=torch.float32, device=dev)
+        dx_emo = torch.empty(m, COARSE_GRAD_COLS, dtype=torch.float32, device=dev)
+        g_off, scratch = _mlp_backward(ctx.desc, img_off, xt_off, rgb_off, d_off.contiguous(), 0, m, m, hid_off, dx_off,
+                                       COARSE_GRAD_COLS, 0)
+        g_emo, _ = _mlp_backward(ctx.desc, img_emo, xt_emo, rgb_emo, d_emo.contiguous(), 0, m, m, hid_emo, dx_emo,
+                                 COARSE_GRAD_COLS, 0, scratch)
+        ctx.hidden = None
+        g_x = torch.zeros(m, ctx.ld, dtype=torch.float32, device=dev)
+        g_x[:, 0:12] = dx_off[:, 0:12]
+        g_x[:, 12:24] = dx_emo[:, 0:12]
+        g_x[:, 66:69] = dx_off[:, 12:15] + dx_emo[:, 12:15]
+        return g_x, g_off, g_emo, None, None, None

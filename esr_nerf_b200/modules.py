@@ -344,6 +344,51 @@ def pbr_in_cols(which: str, device) -> torch.Tensor:
     return torch.tensor(cols, dtype=torch.long, device=device)
 
 
+def coarse_in_cols(device) -> torch.Tensor:
+    """Internal 96-column input row of the coarse colour nets on the tcgen05 chains -> reference 57-column input
+    [colour 0-11 | xyz 12-14 | sin 15-29 | cos 30-44 | view 45-47 | sin view 48-50 | cos view 51-53 | normal 54-56]
+    (voxurfc.py:229-240).  The columns that carry gradient (colour taps, normal) come first: the data-gradient chain
+    returns the leading columns only."""
+    cols = [-1] * 96
+    cols[0:12] = range(0, 12)
+    cols[12:15] = range(54, 57)
+    cols[15:57] = range(12, 54)
+    return torch.tensor(cols, dtype=torch.long, device=device)
+
+
+def coarse_src_cols(which: str, device) -> torch.Tensor:
+    """Internal 96-column input row -> column of the 72-wide coarse feature row of esr_encode_coarse_fwd
+    [off_color 12 | emo_color 12 | xyz 3 | sin 15 | cos 15 | view 3 | sin view 3 | cos view 3 | normal 3 | pad 3]"""
+    cols = [-1] * 96
+    cols[0:12] = range(0, 12) if which == "off" else range(12, 24)
+    cols[12:15] = range(66, 69)
+    cols[15:57] = range(24, 66)
+    return torch.tensor(cols, dtype=torch.int32, device=device)
+
+
+def flat_coarse_mlp_params(seq: nn.Sequential, width: int = 192) -> torch.Tensor:
+    """Flat f32 master copy (96 -> 192 x 3 -> 8 shape of the radiance chains) of a coarse colour net 57 -> 128 -> 128 -> 3
+    (voxurfc.py:137-169): zero-padded to the chain's width, with an IDENTITY third hidden layer — its input is a ReLU output
+    (>= 0), so relu(I h) = h exactly, forward and backward, in every arithmetic the chains use (1.0 is exact in bf16 / fp16)."""
+    lins = _linears(seq)
+    assert len(lins) == 3, "coarse colour nets have two hidden layers (cfg/app/coarse.yaml: rgbnet_depth 3)"
+    dev = lins[0].weight.device
+    key = ("coarse", str(dev))
+    if key not in _COLS_CACHE:
+        cols = coarse_in_cols("cpu")
+        n_ref = lins[0].in_features
+        idx = torch.where(cols < 0, torch.full_like(cols, n_ref), cols)
+        inv = torch.empty(n_ref, dtype=torch.long)
+        for c_int, c_ref in enumerate(cols.tolist()):
+            if c_ref >= 0:
+                inv[c_ref] = c_int
+        w = lins[1].out_features
+        _COLS_CACHE[key] = (idx.to(dev), inv.to(dev), torch.eye(w, device=dev), torch.zeros(w, device=dev))
+    idx, inv, eye, zero = _COLS_CACHE[key]
+    params = [lins[0].weight, lins[0].bias, lins[1].weight, lins[1].bias, eye, zero, lins[2].weight, lins[2].bias]
+    return _FlatParamsPadded.apply(idx, inv, 96, width, *params)
+
+
 class _FlatParamsPadded(torch.autograd.Function):
     """nn.Linear parameters of a NARROWER net -> flat f32 master copy zero-padded to the instantiated kernel shape,
     and the flat gradient back as views of the padded blocks.  One fill + one strided copy per parameter; the

@@ -9,9 +9,11 @@
 Stages on the library's kernels: march + MaskCache + SDF tap (on the Gaussian-smoothed grid), NeuS alpha, the first
 transmittance scan and its weight filter, the second Alphas2Weights pass (reference-shaped op), the feature encode
 (colour taps, PE, normal from the central-difference gradient volume) and its scatter backward, compositing.
-Library calls (like the reference): the dense 5^3 Gaussian smoothing of the SDF grid (cuDNN conv3d, voxurfc.py:202),
-the dense central differences (voxurfc.py:597-616) and — this round — the two 57->128->128->3 colour MLPs in fp32
-(cuBLAS; the tcgen05 chains are instantiated for the 192-wide fine-stage nets only)."""
+The two 57->128->128->3 colour MLPs (voxurfc.py:137-169) run on the 96->192x3 tcgen05 chains, zero-padded and with an
+identity third hidden layer (modules.flat_coarse_mlp_params; 3.8x the MMA work of a native-width kernel — DESIGN.md §7):
+``mlp_mode`` "x2" (default: outputs ~1e-6, every gradient within 1e-2 of the reference's fp32 nets), "bf16", or
+"torch_fp32" (library GEMMs, the 1e-4 class of the strict tests).  Library call (like the reference): the dense 5^3
+Gaussian smoothing of the SDF grid (cuDNN conv3d, voxurfc.py:202)."""
 from __future__ import annotations
 
 from typing import Dict
@@ -22,7 +24,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import fused
-from .modules import DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, _mlp_stack, cfg_get, host_geometry, voxel_geometry
+from .modules import (DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, _mlp_stack, cfg_get, coarse_src_cols,
+                      flat_coarse_mlp_params, host_geometry, voxel_geometry)
 from .render_utils import Alphas2Weights
 
 
@@ -86,11 +89,29 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
         self.set_nonempty_mask()
         self.keep_streams = False
         self.last_streams = None
+        self.mlp_mode = "x2"        # "x2" | "bf16" (tcgen05 chains) | "torch_fp32" (library GEMMs)
         self.train()
 
     def train(self, mode=True):
         self.forward = self.forward_training if mode else self.forward_evaluate
         return super().train(mode)
+
+    def _colour_nets(self, x: torch.Tensor):
+        """(sigmoid(off_rgbnet(.)), sigmoid(emo_rgbnet(.))) of voxurfc.py:229-240 on the [M3,72] feature rows"""
+        if self.mlp_mode == "torch_fp32":
+            feat = x[:, 24:69]
+            return (torch.sigmoid(self.off_rgbnet(torch.cat([x[:, 0:12], feat], -1))),
+                    torch.sigmoid(self.emo_rgbnet(torch.cat([x[:, 12:24], feat], -1))))
+        if self.mlp_mode not in ("x2", "bf16"):
+            raise ValueError(f"unknown mlp_mode {self.mlp_mode!r}")
+        if self.rgbnet_width != 128 or self.rgbnet_depth != 3:
+            raise NotImplementedError("tcgen05 colour nets: the shipped coarse shape (rgbnet_width 128, rgbnet_depth 3)")
+        dev = x.device
+        maps = self.__dict__.get("_src_maps")
+        if maps is None or maps[0].device != dev:
+            maps = self.__dict__["_src_maps"] = (coarse_src_cols("off", dev), coarse_src_cols("emo", dev))
+        return fused.CoarseShade.apply(x, flat_coarse_mlp_params(self.off_rgbnet), flat_coarse_mlp_params(self.emo_rgbnet),
+                                       maps[0], maps[1], 1 if self.mlp_mode == "x2" else 0)
 
     @torch.no_grad()
     def set_nonempty_mask(self):
@@ -143,9 +164,7 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
             x = fused.EncodeCoarse.apply(self.gradient, self.off_color.grid, self.emo_color.grid, sc, rays_o, rays_d,
                                          viewdirs, s)
             on = em_modes[ray_id] == 1
-            feat = x[:, 24:69]
-            rgb_off = torch.sigmoid(self.off_rgbnet(torch.cat([x[:, 0:12], feat], -1)))
-            rgb_emo = torch.sigmoid(self.emo_rgbnet(torch.cat([x[:, 12:24], feat], -1)))
+            rgb_off, rgb_emo = self._colour_nets(x)
             rgb = torch.where(on[:, None], rgb_emo, torch.zeros_like(rgb_emo)) + rgb_off  # voxurfc.py:241-249
             rgb_marched, wsum = fused.Composite.apply(weights, rgb, torch.ones_like(rgb), s)
         if self.keep_streams:
@@ -179,9 +198,7 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
             weights, _ = Alphas2Weights.apply(h_alpha, ray_id, N)
             x = fused.EncodeCoarse.apply(self.gradient, self.off_color.grid, self.emo_color.grid, sc, rays_o, rays_d,
                                          viewdirs, s)
-            feat = x[:, 24:69]
-            off = torch.sigmoid(self.off_rgbnet(torch.cat([x[:, 0:12], feat], -1)))
-            emo = torch.sigmoid(self.emo_rgbnet(torch.cat([x[:, 12:24], feat], -1)))
+            off, emo = self._colour_nets(x)
             normal = ((x[:, 66:69] @ pos_rt) * torch.tensor([1.0, -1.0, -1.0], device=dev) + 1.0) / 2.0
             dvec = torch.ones(s.m3, 3, device=dev)
             dvec[:, 0] = s.h_step.float() * host_geometry(self, self.stepsize)["stepdist"]

@@ -358,6 +358,14 @@ int esr_encode_coarse_fwd(const esr_scene_t *sc, const float *rays_o, const floa
                           const float *grad_vol, const float *off_color_grid, const float *emo_color_grid,
                           const int32_t *h_ray, const int32_t *h_step, int64_t m3, float *feat,
                           esr_stream_t stream);
+/*
+ * f32 rows [m][ld] -> the library's tiled 16-bit MLP input rows (96 columns): column c takes source column colmap[c]
+ * (device int32 [96]; < 0: zero).  precision 0: bf16 tiles (esr_mlp_act_rows(m) rows); 1: fp16 tiles followed by the
+ * fp16 residual tiles (2 * esr_mlp_act_rows(m) rows) — the input of esr_mlp_fwd with esr_mlp_desc_t::precision = 1.
+ * The coarse stage feeds its 72-column feature rows to the 96 -> 192 tcgen05 chains through this.
+ */
+int esr_rows_to_mlp_tiles(const float *src, int64_t m, int ld, const int32_t *colmap, int precision, void *tiles,
+                          esr_stream_t stream);
 int esr_encode_coarse_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *grad_vol,
                           const int32_t *h_ray, const int32_t *h_step, int64_t m3, const float *d_feat,
                           float *g_grad_vol, float *g_off_grid, float *g_emo_grid, esr_stream_t stream);

@@ -1,8 +1,9 @@
 """GPU parity (-m gpu) of the coarse-stage render path (esr_nerf_b200.VoxurfC, BASELINE config 1 shape) against the
 golden vectors produced by the reference's own VoxurfC (tests/golden/voxurfc_*.npz) and the oracle port
-(oracle/voxurfc_port.py, pinned against the reference in tests/test_oracle_cpu.py).  Everything on this path is
-fp32: 1e-4 relative on outputs and gradients (isolated ReLU-boundary flips tolerated as documented in
-esr_testlib.grad_close); sample streams bit-exact."""
+(oracle/voxurfc_port.py, pinned against the reference in tests/test_oracle_cpu.py).  Sample streams bit-exact.  The two
+colour MLPs run in the default `x2` mode on the tcgen05 chains (zero-padded, identity third hidden layer): outputs 1e-4
+(measured ~1e-6), every parameter gradient within 1e-2 max-norm and relative L2; `torch_fp32` (library GEMMs) keeps the
+1e-4 class on everything (isolated ReLU-boundary flips tolerated as documented in esr_testlib.grad_close)."""
 import pytest
 import torch
 
@@ -14,8 +15,9 @@ DEV = "cuda:0"
 OUT_KEYS = ("etc/alphainv_cum", "etc/white_bg", "srgb/rgb")
 
 
-def _run(fx, weights, rays=None):
+def _run(fx, weights, rays=None, mode="x2"):
     m = C.build_product_coarse(fx, weights, DEV)
+    m.mlp_mode = mode
     m.keep_streams = True
     if rays is None:
         rays = S.make_rays(int(fx["n_rays"]), int(fx["ray_seed"]))
@@ -26,10 +28,11 @@ def _run(fx, weights, rays=None):
     return m, out
 
 
+@pytest.mark.parametrize("mode", ["x2", "torch_fp32"])
 @pytest.mark.parametrize("case", C.COARSE_CASES)
-def test_coarse_vs_golden(case):
+def test_coarse_vs_golden(case, mode):
     fx, weights = C.load_coarse_case(case)
-    m, out = _run(fx, weights)
+    m, out = _run(fx, weights, mode=mode)
     assert set(out) == set(OUT_KEYS)
     for k in OUT_KEYS:
         assert out[k].shape == fx["out/" + k].shape, k
@@ -40,8 +43,15 @@ def test_coarse_vs_golden(case):
             continue
         assert p.grad is not None, name
         flat = p.grad.contiguous().reshape(-1).cpu()
-        ok, msg = C.grad_close(flat[torch.from_numpy(fx[f"grad/{name}/idx"])], torch.from_numpy(fx[f"grad/{name}/val"]), 1e-4)
-        assert ok, (name, msg)
+        got, ref = flat[torch.from_numpy(fx[f"grad/{name}/idx"])], torch.from_numpy(fx[f"grad/{name}/val"])
+        if mode == "x2":      # tensor-core colour nets: relative L2 < 1e-2 on every tensor; max-norm 1e-2 up to isolated
+            # ReLU-boundary flips (with ~10^4 samples ONE flipped mask — fp32 summation order does that to the reference's
+            # own two devices — moves a weight-gradient row by a per-cent of the tensor's maximum: esr_testlib.grad_close)
+            ok, msg = C.grad_close(got, ref, 1e-2, l2_factor=1.0)
+            assert ok, (name, msg)
+        else:
+            ok, msg = C.grad_close(got, ref, 1e-4)
+            assert ok, (name, msg)
         checked += 1
     assert checked == 3 + 6 + 6
 
@@ -60,7 +70,7 @@ def test_coarse_vs_oracle_port_config1_shape():
                                              rays["em_modes"], 5.0)
     cot = C.coarse_cotangents(n)
     sum((ref[k] * cot[k]).sum() for k in cot).backward()
-    m, out = _run(fx, weights, rays)
+    m, out = _run(fx, weights, rays, mode="torch_fp32")
     st = m.last_streams["streams"]
     assert torch.equal(st.h_ray.long().cpu(), inter["m3_ray"]) and torch.equal(st.h_step.long().cpu(), inter["m3_step"])
     assert C.rel_err(m.last_streams["h_w"], inter["m3_weights"]) < 1e-4
@@ -84,8 +94,9 @@ def test_coarse_all_rays_miss():
     assert (out["etc/alphainv_cum"] == 1).all() and (out["srgb/rgb"] == 0).all() and (out["etc/white_bg"] == 1).all()
 
 
+@pytest.mark.parametrize("mode", ["x2", "torch_fp32"])
 @pytest.mark.parametrize("em", [0, 1])
-def test_coarse_forward_evaluate_vs_oracle_port(em):
+def test_coarse_forward_evaluate_vs_oracle_port(em, mode):
     """voxurfc.py:273-424: 8 inference maps vs the oracle port (pinned against the reference on the CPU)."""
     from oracle import voxurfc_port as PC
 
@@ -98,6 +109,7 @@ def test_coarse_forward_evaluate_vs_oracle_port(em):
         ref, inter = PC.voxurfc_forward_evaluate(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
                                                  torch.tensor(em), pos_rt, float(fx["s_val"]))
     m = C.build_product_coarse(fx, weights, DEV)
+    m.mlp_mode = mode
     m.keep_streams = True
     m.eval()
     out = m(rays_o=rays["rays_o"].to(DEV), rays_d=rays["rays_d"].to(DEV), viewdirs=rays["viewdirs"].to(DEV),
@@ -107,4 +119,6 @@ def test_coarse_forward_evaluate_vs_oracle_port(em):
     assert torch.equal(st.h_ray.long().cpu(), inter["m3_ray"]) and torch.equal(st.h_step.long().cpu(), inter["m3_step"])
     for k in ref:
         assert out[k].shape == ref[k].shape, k
-        assert C.rel_err(out[k], ref[k]) < 1e-4, (k, C.rel_err(out[k], ref[k]))
+        # inference on the tensor-core path uses single bf16 operands (as VoxurfF's): 1e-2 on the colour maps
+        tol = 1e-2 if (mode != "torch_fp32" and k.startswith("srgb/")) else 1e-4
+        assert C.rel_err(out[k], ref[k]) < tol, (k, C.rel_err(out[k], ref[k]))
