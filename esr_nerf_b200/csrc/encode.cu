@@ -242,12 +242,12 @@ struct StreamRowWriter {
       : b4(reinterpret_cast<uint4 *>(b)), b4b(nullptr), row(r), res_off(act_rows_padded(m_total) * (ESR_FEAT_DIM / 8)) {}
   // bf16 pair of (a, b); with RES the pair is fp16 and `res` the fp16 pair of the two rounding residuals
   ESR_D static uint32_t pack(float a, float b, uint32_t &res) {
-    if constexpr (RES) {
-      const __half2 h = __floats2half2_rn(a, b);
-      const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-      res = *reinterpret_cast<const uint32_t *>(&l);
-      return *reinterpret_cast<const uint32_t *>(&h);
+    if constexpr (RES) {   // (saturating conversions: a feature beyond fp16's range is clamped to +-65504, never an infinity)
+      uint32_t h;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(res) : "f"(b - hf.y), "f"(a - hf.x));
+      return h;
     } else {
       __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
       return *reinterpret_cast<uint32_t *>(&p);
@@ -1051,10 +1051,9 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (precision) {
-      const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-      const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
-      hi[j] = *reinterpret_cast<const uint32_t *>(&h), lo[j] = *reinterpret_cast<const uint32_t *>(&l);
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi[j]));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[j]) : "f"(v[2 * j + 1] - hf.y), "f"(v[2 * j] - hf.x));
     } else {
       __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
       hi[j] = *reinterpret_cast<uint32_t *>(&p);

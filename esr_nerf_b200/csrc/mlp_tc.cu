@@ -163,9 +163,10 @@ ESR_D uint32_t pack2h(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// (saturating: an activation beyond fp16's 65504 is clamped, not turned into an infinity that would poison the row)
 ESR_D uint32_t pack2h_relu(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 // the same with overflow clamped to +-65504 instead of +-inf (stored cotangents: a runaway value must not poison a sum)

@@ -269,3 +269,27 @@ def test_tonemap_x2_fused_kernels_vs_fp32_network(m, dy_scale):
             rel = ((got - ref)[keep].norm() / ref[keep].norm().clamp_min(1e-30)).item()
             mx = ((got - ref)[keep].abs().max() / ref[keep].abs().max().clamp_min(1e-300)).item()
             assert rel < 3e-3 and mx < 3e-3, (i, rel, mx)   # fp16 operands (tolerance of the path: 1e-2)
+
+
+def test_mlp_x2_out_of_range_values_stay_finite():
+    """features / activations beyond fp16's 65504 are clamped by the saturating conversions of the x2 path, never turned into
+    infinities: outputs and gradients stay finite (the bf16 mode cannot overflow; the fp32 reference does not either)"""
+    desc = fused.with_precision(fused.RADIANCE_DESC, 1)
+    flat, _ = _flat_and_layers(desc, 3)
+    m = 300
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(m, 96, generator=g)
+    x[:, 91:] = 0
+    x[::7, 3] = 3e5            # beyond the fp16 range: saturates in the feature tile and, through layer 0, in the activations
+    x[::11, 20] = -2e6
+    image = fused.mlp_pack(desc, flat.to(DEV))
+    xd = _tile_with_residual(x.to(DEV).clamp(-65504, 65504))      # what esr_encode_*_fwd writes for such a feature
+    y, hidden = fused._mlp_forward(desc, image, xd, 0, m, m, True)
+    d_x = torch.zeros(m, 56, device=DEV)
+    grad_flat, _ = fused._mlp_backward(desc, image, xd, y, torch.randn(m, 3, generator=g).to(DEV), 0, m, m, hidden, d_x, 56, 0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all() and torch.isfinite(d_x).all() and torch.isfinite(grad_flat).all()
+    # and the tiling kernel clamps on its own
+    xw = torch.cat([x, x[:84]], 0).to(DEV).contiguous()          # 384 rows: whole tiles (rows past m are never written)
+    t = fused.rows_to_tiles(xw, torch.arange(96, dtype=torch.int32, device=DEV), 1)
+    assert torch.isfinite(t.view(torch.float16).float()).all()
