@@ -325,6 +325,35 @@ def flat_mlp_params(layers: Sequence[nn.Linear], kind: str, k0: int) -> torch.Te
     return _FlatParams.apply(idx, inv, k0, *params)
 
 
+def flat_mlp_params_any(layers: Sequence[nn.Linear], kind: str, k0: int, width: int = 192, n_hidden: int = 3) -> torch.Tensor:
+    """flat_mlp_params for ANY net the instantiated chain shape can hold: hidden width <= `width`, 1 .. n_hidden hidden
+    layers.  The shipped shape goes the direct way; a narrower / shallower net is zero-padded to the chain's width and
+    topped up with identity hidden layers behind its last real one (their input is a ReLU output, so relu(I h) = h exactly,
+    forward and backward) — cfg values of `rgbnet_width / rgbnet_depth / tonemap_width` other than the shipped ones run on
+    the same kernels, at the shipped shape's cost."""
+    layers = list(layers)
+    hid = len(layers) - 1
+    w = layers[0].out_features
+    if not (1 <= hid <= n_hidden and w <= width and all(l.out_features == w for l in layers[:-1])):
+        raise NotImplementedError(f"MLP {[(l.in_features, l.out_features) for l in layers]} does not fit the instantiated "
+                                  f"tensor-core chain ({k0} -> {width} x {n_hidden})")
+    if hid == n_hidden and w == width:
+        return flat_mlp_params(layers, kind, k0)
+    idx, inv = _col_maps(kind, layers[0].weight.device)
+    dev = layers[0].weight.device
+    key = ("eye", w, str(dev))
+    if key not in _COLS_CACHE:
+        _COLS_CACHE[key] = (torch.eye(w, device=dev), torch.zeros(w, device=dev))
+    eye, zero = _COLS_CACHE[key]
+    params = []
+    for lin in layers[:-1]:
+        params += [lin.weight, lin.bias]
+    for _ in range(n_hidden - hid):
+        params += [eye, zero]
+    params += [layers[-1].weight, layers[-1].bias]
+    return _FlatParamsPadded.apply(idx, inv, k0, width, *params)
+
+
 def pbr_in_cols(which: str, device) -> torch.Tensor:
     """Internal 96-column feature row -> reference 76-column input of the emission / BRDF nets
     [color 0-5 | xyz 6-8 | sin 9-23 | cos 24-38 | sdf 39 | feat 40-63 | normal 64-75] (esrnerf.py:761-765).
@@ -366,14 +395,18 @@ def coarse_src_cols(which: str, device) -> torch.Tensor:
     return torch.tensor(cols, dtype=torch.int32, device=device)
 
 
-def flat_coarse_mlp_params(seq: nn.Sequential, width: int = 192) -> torch.Tensor:
-    """Flat f32 master copy (96 -> 192 x 3 -> 8 shape of the radiance chains) of a coarse colour net 57 -> 128 -> 128 -> 3
-    (voxurfc.py:137-169): zero-padded to the chain's width, with an IDENTITY third hidden layer — its input is a ReLU output
-    (>= 0), so relu(I h) = h exactly, forward and backward, in every arithmetic the chains use (1.0 is exact in bf16 / fp16)."""
+def flat_coarse_mlp_params(seq: nn.Sequential, width: int = 192, n_hidden: int = 3) -> torch.Tensor:
+    """Flat f32 master copy (96 -> 192 x 3 -> 8 shape of the radiance chains) of a coarse colour net — 57 -> 128 -> 128 -> 3
+    as shipped (voxurfc.py:137-169; any width <= 192 and 1..3 hidden layers): zero-padded to the chain's width and topped up
+    with IDENTITY hidden layers — their input is a ReLU output (>= 0), so relu(I h) = h exactly, forward and backward, in
+    every arithmetic the chains use (1.0 is exact in bf16 / fp16)."""
     lins = _linears(seq)
-    assert len(lins) == 3, "coarse colour nets have two hidden layers (cfg/app/coarse.yaml: rgbnet_depth 3)"
+    hid, w = len(lins) - 1, lins[0].out_features
+    if not (1 <= hid <= n_hidden and w <= width and all(l.out_features == w for l in lins[:-1])):
+        raise NotImplementedError(f"coarse colour net {[(l.in_features, l.out_features) for l in lins]} does not fit the "
+                                  f"instantiated tensor-core chain (96 -> {width} x {n_hidden})")
     dev = lins[0].weight.device
-    key = ("coarse", str(dev))
+    key = ("coarse", w, str(dev))
     if key not in _COLS_CACHE:
         cols = coarse_in_cols("cpu")
         n_ref = lins[0].in_features
@@ -382,10 +415,14 @@ def flat_coarse_mlp_params(seq: nn.Sequential, width: int = 192) -> torch.Tensor
         for c_int, c_ref in enumerate(cols.tolist()):
             if c_ref >= 0:
                 inv[c_ref] = c_int
-        w = lins[1].out_features
         _COLS_CACHE[key] = (idx.to(dev), inv.to(dev), torch.eye(w, device=dev), torch.zeros(w, device=dev))
     idx, inv, eye, zero = _COLS_CACHE[key]
-    params = [lins[0].weight, lins[0].bias, lins[1].weight, lins[1].bias, eye, zero, lins[2].weight, lins[2].bias]
+    params = []
+    for lin in lins[:-1]:
+        params += [lin.weight, lin.bias]
+    for _ in range(n_hidden - hid):
+        params += [eye, zero]
+    params += [lins[-1].weight, lins[-1].bias]
     return _FlatParamsPadded.apply(idx, inv, 96, width, *params)
 
 

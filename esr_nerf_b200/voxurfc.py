@@ -104,8 +104,6 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
                     torch.sigmoid(self.emo_rgbnet(torch.cat([x[:, 12:24], feat], -1))))
         if self.mlp_mode not in ("x2", "bf16"):
             raise ValueError(f"unknown mlp_mode {self.mlp_mode!r}")
-        if self.rgbnet_width != 128 or self.rgbnet_depth != 3:
-            raise NotImplementedError("tcgen05 colour nets: the shipped coarse shape (rgbnet_width 128, rgbnet_depth 3)")
         dev = x.device
         maps = self.__dict__.get("_src_maps")
         if maps is None or maps[0].device != dev:

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import fused
-from .modules import (host_geometry, DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, RadianceNet, TonemapNet, cfg_get, flat_mlp_params,
+from .modules import (host_geometry, DenseGrid, GradientConv, GridRegularizers, MaskCache, RayUtilities, RadianceNet, TonemapNet, cfg_get, flat_mlp_params, flat_mlp_params_any,
                       radiance_in_cols, tonemap_in_cols, voxel_geometry)
 
 
@@ -95,14 +95,16 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _check_supported(self):
-        ok = (self.color_dim == 6 and self.rgbnet_width == 192 and self.rgbnet_depth == 4 and
-              self.tonemap_width == 192 and self.tonemap_depth == 2 and self.posbase_pe == 5 and
+        # the feature row (colour taps, encodings, the four-scale SDF feature) is what the encode kernels are built for; the
+        # nets behind it may be narrower / shallower than the shipped ones (modules.flat_mlp_params_any)
+        ok = (self.color_dim == 6 and 1 <= self.rgbnet_width <= 192 and 2 <= self.rgbnet_depth <= 4 and
+              1 <= self.tonemap_width <= 192 and self.tonemap_depth == 2 and self.posbase_pe == 5 and
               self.viewbase_pe == 1 and self.colorbase_pe == 5 and self.grad_feat == [0.5, 1.0, 1.5, 2.0] and
               self.neus_alpha == "interp")
         if not ok:
             raise NotImplementedError(
-                "libesr_b200 instantiates the shipped fine-stage shape only (cfg/app/fine.yaml:13-30): color_dim 6, "
-                "rgbnet 192x4, tonemap 192x2, PE 5/1/5, grad_feat [.5,1,1.5,2], neus_alpha interp")
+                "libesr_b200 instantiates the shipped fine-stage feature row (cfg/app/fine.yaml:13-30): color_dim 6, PE 5/1/5, "
+                "grad_feat [.5,1,1.5,2], neus_alpha interp; rgbnet width <= 192, depth 2..4; tonemap width <= 192, depth 2")
 
     def train(self, mode=True):
         self.forward = self.forward_training if mode else self.forward_evaluate
@@ -156,9 +158,9 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
 
     def _flat(self, which: str):
         if which == "tone":
-            return flat_mlp_params(self.tonemapper.layers(), "tone", 48)
+            return flat_mlp_params_any(self.tonemapper.layers(), "tone", 48, 192, 1)
         net = self.off_rgbnet if which == "off" else self.emo_rgbnet
-        return flat_mlp_params(net.layers(), which, 96)
+        return flat_mlp_params_any(net.layers(), which, 96, 192, 3)
 
     def _streams(self, sc, rays_o, rays_d, em_modes, between=None):
         n = rays_o.shape[0]

@@ -363,3 +363,40 @@ def test_filter_training_rays_packed_branch_vs_oracle():
     inb = ~out
     want[rid[inb][P.mask_cache(scene, pts[inb])]] = True
     assert torch.equal(got.cpu(), want) and 0 < int(want.sum()) < 3000
+
+
+@pytest.mark.parametrize("width,depth,tone_width", [(128, 3, 96), (64, 2, 192), (192, 3, 192)])
+def test_other_net_shapes_run_on_the_same_chains(width, depth, tone_width):
+    """cfg values of rgbnet_width / rgbnet_depth / tonemap_width other than the shipped ones (voxurff.py:61-77 reads them
+    from the config): the nets are zero-padded to the chains' 192 columns and topped up with identity hidden layers
+    (modules.flat_mlp_params_any) — tensor-core x2 mode against the same model's fp32 library-GEMM mode, i.e. the nn
+    modules evaluated as the reference evaluates them: outputs 1e-4, every gradient relative L2 < 1e-2."""
+    from esr_nerf_b200.voxurff import VoxurfF
+
+    def make():
+        torch.manual_seed(0)
+        geo = (S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT, S.mask_density(24, True))
+        m = VoxurfF(S.fine_cfg(DEV, rgbnet_width=width, rgbnet_depth=depth, tonemap_width=tone_width), *geo, 20.0, 48 ** 3)
+        S.fill_fine_model(m)
+        return m
+
+    a, b = make(), make()
+    b.load_state_dict(a.state_dict(), strict=True)
+    a.mlp_mode, b.mlp_mode = "x2", "torch_fp32"
+    rays = {k: v.to(DEV) for k, v in S.make_rays(3000, 21).items()}
+    outs = []
+    for m in (a, b):
+        out = m(s_val=20.0, **{k: v for k, v in rays.items() if k != "rgbs"})
+        (((out["srgb/rgb"] - rays["rgbs"]) ** 2).mean() + 0.1 * (out["lin/rgb"] ** 2).mean() + out["etc/alphainv_cum"].mean()).backward()
+        outs.append(out)
+    for k in outs[0]:
+        assert C.rel_err(outs[0][k], outs[1][k]) < 1e-4, k
+    checked = 0
+    for (name, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        if q.grad is None:
+            continue
+        assert p.grad is not None, name
+        ok, msg = C.grad_close(p.grad.contiguous(), q.grad.contiguous(), 1e-2, l2_factor=1.0)
+        assert ok, (name, msg)
+        checked += 1
+    assert checked >= 3 + 2 * 2 * depth + 4
