@@ -19,7 +19,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libesr_b200.so")
 SOURCES = ["native_ops.cu", "voxurf_stream.cu", "encode.cu", "mlp_api.cu", "mlp_tc.cu", "dvgo.cu", "esrnerf.cu", "optim.cu", "grad_exchange.cu",
-           "regularizers.cu"]
+           "regularizers.cu", "render_step.cu"]
 HEADERS = ["common.cuh", "scan.cuh", "mlp_layout.cuh", os.path.join("..", "..", "include", "esr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -128,6 +128,17 @@ class MlpDesc(ctypes.Structure):
                 ("n_out", ctypes.c_int32), ("act", ctypes.c_int32), ("precision", ctypes.c_int32)]
 
 
+class VoxurffStep(ctypes.Structure):
+    """esr_voxurff_step_t"""
+    _fields_ = [("scene", Scene), ("mask_density", ctypes.c_void_p), ("mask_cls", ctypes.c_void_p),
+                ("sdf_grid", ctypes.c_void_p), ("off_color_grid", ctypes.c_void_p), ("emo_color_grid", ctypes.c_void_p),
+                ("flat_off", ctypes.c_void_p), ("flat_emo", ctypes.c_void_p), ("flat_tone", ctypes.c_void_p),
+                ("precision", ctypes.c_int32), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+                ("n_rays", ctypes.c_int64), ("n_on", ctypes.c_int64), ("m1", ctypes.c_int64), ("m3", ctypes.c_int64),
+                ("m3_on", ctypes.c_int64), ("workspace_used", ctypes.c_int64), ("workspace_needed", ctypes.c_int64),
+                ("alphainv_last", ctypes.c_void_p), ("slot", ctypes.c_void_p * 32)]
+
+
 P = ctypes.c_void_p
 I64 = ctypes.c_int64
 I32 = ctypes.c_int
@@ -202,6 +213,9 @@ PROTOTYPES = {
     "esr_mlp_fwd": (I32, [DESC_P, P, P, I64, I64, I64, P, P, I64, P]),
     "esr_mlp_bwd": (I32, [DESC_P, P, P, P, P, I64, I64, I64, P, P, P, P, I32, I32, P, P]),
     "esr_mlp_bwd_weights": (I32, [DESC_P, P, I64, I64, I64, P, P, P, P]),
+    "esr_render_voxurff_workspace_bytes": (I64, [ctypes.POINTER(Scene), I64, I64, I64, I32]),
+    "esr_render_voxurff_fwd": (I32, [ctypes.POINTER(VoxurffStep), P, P, P, P, I64, P, P, P, P]),
+    "esr_render_voxurff_bwd": (I32, [ctypes.POINTER(VoxurffStep), P, P, P, P, P, P, P, P, P, P, P, P]),
     "esr_rows_to_mlp_tiles": (I32, [P, I64, I32, P, I32, P, P]),
     "esr_grid_tv_fwd": (I32, [P, P, I32, I64, I64, I64, I64, I64, I64, I64, P, P]),
     "esr_grid_tv_bwd": (I32, [P, P, I32, I64, I64, I64, I64, I64, I64, I64, P, P, F32, P, P]),

@@ -246,10 +246,11 @@ int esr_neus_alpha_bwd(const esr_scene_t *sc, const float *rays_o, const float *
  *              1 -> __nv_bfloat16 rows in the library's TILED MLP-input layout (per 128-row tile:
  *                   [12 feature chunks][128 rows][8]); `feat` must hold esr_mlp_act_rows(m3) rows.  The same holds
  *                   for esr_tonemap_encode_fwd's tfeat (48 columns = 6 chunks).
- *              2 -> (esr_encode_fwd / esr_encode_pbr_fwd) as 1, followed in the same buffer — which must hold
- *                   2 * esr_mlp_act_rows(m3) rows — by a second tile set of __half: the residual v - bf16(v) of every
- *                   column.  This is the layer-0 operand of the x2 forward chain (esr_mlp_desc_t::precision = 1):
- *                   esr_mlp_fwd then expects `x` to be such a buffer; esr_mlp_bwd reads the bf16 tiles only.
+ *              2 -> (esr_encode_fwd / esr_encode_pbr_fwd) the same tiled layout with __half rows (saturating conversion),
+ *                   followed in the same buffer — which must hold 2 * esr_mlp_act_rows(m3) rows — by a second tile set of
+ *                   __half: the residual v - fp16(v) of every column.  This is the layer-0 operand of the x2 forward
+ *                   chain (esr_mlp_desc_t::precision = 1): esr_mlp_fwd then expects `x` to be such a buffer;
+ *                   esr_mlp_bwd reads the first tile set only.
  */
 #define ESR_FEAT_DIM 96
 #define ESR_FEAT_GRAD_DIM 56 /* columns [0,49) carry gradient; padded to 56 */
@@ -489,6 +490,51 @@ int esr_tonemap_mlp_fwd(const esr_mlp_desc_t *d, const void *image, const float 
 int esr_tonemap_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const float *lin, const float *rgb,
                         const float *d_rgb, const float *d_lin_direct, int64_t m, float *d_lin, float *grad_flat,
                         esr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One call = one fine-stage render step: VoxurfF.forward_training (app/fine/model/voxurff.py:177-278)
+ * and its backward, run on the stage entry points above in the order esr_nerf_b200/fused.py runs them, for hosts that
+ * are not Python.  Caller-owned everything: fill the input fields of esr_voxurff_step_t (zero the rest), pass ONE
+ * workspace (esr_render_voxurff_workspace_bytes for given bounds on the two stream sizes; the forward fails with
+ * ESR_ERR_CAPACITY and sets workspace_needed when it is too small), then
+ *   esr_render_voxurff_fwd: rays_o / rays_d / viewdirs f32 [n,3], em_modes i64 [n] -> srgb/rgb [n,3], lin/rgb [n,3],
+ *                           etc/alphainv_cum [n] (the dict of voxurff.py:273-278; etc/white_bg is alphainv_cum[:, None]);
+ *                           synchronises the stream twice (the two data-dependent stream sizes, as the reference does);
+ *   esr_render_voxurff_bwd: cotangents of the three outputs -> gradients ACCUMULATED into the caller's dense grid
+ *                           gradient volumes (layouts of the grids) and flat MLP gradients (layout of esr_mlp_pack's
+ *                           flat_params; esr_mlp_param_count floats each).  The step object, the workspace, the rays and
+ *                           alphainv_last must be unchanged since the forward.
+ * flat_* = the f32 master copies esr_mlp_pack consumes (radiance nets: k0 96, width 192, 3 hidden, 3 outputs softplus;
+ * tone mapper: k0 48, width 192, 1 hidden, 3 outputs sigmoid).  precision: esr_mlp_desc_t::precision of the three nets.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct esr_voxurff_step {
+  /* inputs */
+  esr_scene_t scene;
+  const float *mask_density;    /* MaskCache (max-pooled) density [mx][my][mz] */
+  const uint8_t *mask_cls;      /* nullable: esr_mask_classify table */
+  const float *sdf_grid;        /* [gx][gy][gz] */
+  const float *off_color_grid;  /* channels-last [gx][gy][gz][6] */
+  const float *emo_color_grid;
+  const float *flat_off, *flat_emo, *flat_tone;
+  int32_t precision;            /* 0 bf16 operands, 1 x2 */
+  void *workspace;
+  int64_t workspace_bytes;
+  /* outputs of the forward */
+  int64_t n_rays, n_on, m1, m3, m3_on;      /* rays, emission-on rays, stream sizes */
+  int64_t workspace_used, workspace_needed; /* bytes carved by the forward / needed by forward + backward */
+  /* private to the library */
+  const float *alphainv_last;
+  void *slot[32];
+} esr_voxurff_step_t;
+int64_t esr_render_voxurff_workspace_bytes(const esr_scene_t *sc, int64_t n_rays, int64_t m1_max, int64_t m3_max,
+                                           int precision);
+int esr_render_voxurff_fwd(esr_voxurff_step_t *step, const float *rays_o, const float *rays_d, const float *viewdirs,
+                           const int64_t *em_modes, int64_t n_rays, float *rgb_marched, float *lin_marched,
+                           float *alphainv_last, esr_stream_t stream);
+int esr_render_voxurff_bwd(esr_voxurff_step_t *step, const float *rays_o, const float *rays_d,
+                           const float *d_rgb_marched, const float *d_lin_marched, const float *d_alphainv_last,
+                           float *grad_sdf_grid, float *grad_off_grid, float *grad_emo_grid, float *grad_flat_off,
+                           float *grad_flat_emo, float *grad_flat_tone, esr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer step: app/utils/optimizer.py:63-228 — dense Adam with an optional per-voxel learning
