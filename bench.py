@@ -191,6 +191,38 @@ def cpu_port_step(a, scene, params, leaves, rays):
     return inter
 
 
+def cpu_coarse_config1(steps: int = 3):
+    """BASELINE configs[0] / SURVEY.md §8d "Config 1": the COARSE stage (VoxurfC 64^3, 4096 rays, ~128 candidate samples per
+    ray, 57 -> 128 -> 128 -> 3 colour nets, s_val 5), one fwd+bwd on the host cores through the oracle port of the reference's
+    VoxurfC render path; 1 warm-up + `steps` timed steps -> rays/s (reported beside the fine-stage CPU number, which is the
+    one on the bench line's own workload)"""
+    import esr_testlib as C
+    from esr_nerf_b200 import synthetic as S
+    from oracle import voxurfc_port as PC
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = 4096
+    _, weights = C.load_coarse_case("coarse_sparse_s5")
+    scene = C.coarse_oracle_scene(64 ** 3, 32, True)
+    params, leaves = C.coarse_oracle_params(scene, weights)
+    rays = S.make_rays(n, 2718)
+    cot = C.coarse_cotangents(n)
+
+    def step():
+        for leaf in leaves.values():
+            leaf.grad = None
+        out, _ = PC.voxurfc_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"], rays["em_modes"], 5.0)
+        sum((out[k] * cot[k]).sum() for k in cot).backward()
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "cores": os.cpu_count() or 1, "kind": "port",
+            "workload": "BASELINE configs[0]: coarse stage, VoxurfC 64^3, 4096 rays x ~128 samples, fwd+bwd (oracle port, torch CPU fp32)"}
+
+
 def run_reference(a, rank, world):
     if rank != 0:
         return
@@ -213,6 +245,10 @@ def run_reference(a, rank, world):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    try:      # the reference's own CPU-runnable case beside it (an extra: it must never cost the line)
+        line["cpu_baseline"]["config1_coarse"] = cpu_coarse_config1()
+    except Exception as e:   # noqa: BLE001
+        line["cpu_baseline"]["config1_coarse"] = {"error": repr(e)}
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
