@@ -402,8 +402,10 @@ def algorithmic_work(stage, c):
         "k_neus_alpha": ("hbm", 4 * M1 + 8 * M1),                # read sdf, write alpha + T preset
         "k_transmittance": ("hbm", 4 * M1 + 4 * M1 + 16 * N),     # read alpha, write T; per-ray offsets / count / last
         "k_shade_compact": ("hbm", 8 * M1 + 8 * M3 + 20 * M3),    # read alpha + T (+ step, sdf of survivors), write M3 stream
-        "k_encode_fwd": ("hbm", 8 * M3 + taps_fwd + 192 * M3),
-        "k_encode_bwd": ("hbm", 8 * M3 + 2 * taps_fwd + 224 * M3),
+        # taps at face value + the stream reload; the feature rows / their cotangents (intermediates a fully
+        # fused implementation need not materialise) are NOT counted, although these kernels do move them
+        "k_encode_fwd": ("hbm", 8 * M3 + taps_fwd),
+        "k_encode_bwd": ("hbm", 8 * M3 + 2 * taps_fwd),
         "k_alpha_scan_bwd": ("hbm", 16 * M1 + 8 * M1),
         "k_sdf_scatter": ("hbm", 16 * M1 + 64 * M1),
         "k_composite_fwd": ("hbm", 28 * M3 + 24 * N),
@@ -426,8 +428,8 @@ def algorithmic_work(stage, c):
     if "encode_rows" in c:   # lts stage: rows summed over primary / LTS-point / secondary / eps passes (fused.STATS)
         E, Rf, Rb = c["encode_rows"], c["mlp_fwd_rows"], c["mlp_bwd_rows"]
         t.update({
-            "k_encode_fwd": ("hbm", (8 + 768 + 384 + 192) * E),
-            "k_encode_bwd": ("hbm", (8 + 2 * (768 + 384) + 224) * c["encode_bwd_rows"]),
+            "k_encode_fwd": ("hbm", (8 + 768 + 384) * E),
+            "k_encode_bwd": ("hbm", (8 + 2 * (768 + 384)) * c["encode_bwd_rows"]),
             "k_mlp_fwd_tc_radiance": ("tensor", FLOP_RADIANCE * Rf),
             "k_mlp_fwd_x2_radiance": ("tensor", FLOP_RADIANCE * Rf),
             "k_mlp_dgrad_tc_radiance": ("tensor", FLOP_RADIANCE * Rb),
