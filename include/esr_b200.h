@@ -494,7 +494,7 @@ int esr_tonemap_mlp_bwd(const esr_mlp_desc_t *d, const void *image, const float 
 /* ------------------------------------------------------------------------------------------
  * One call = one fine-stage render step: VoxurfF.forward_training (app/fine/model/voxurff.py:177-278)
  * and its backward, run on the stage entry points above in the order esr_nerf_b200/fused.py runs them, for hosts that
- * are not Python.  Caller-owned everything: fill the input fields of esr_voxurff_step_t (zero the rest), pass ONE
+ * are not Python.  Caller-owned everything: fill the input fields of the esr_voxurff_step_t struct and zero the rest, pass ONE
  * workspace (esr_render_voxurff_workspace_bytes for given bounds on the two stream sizes; the forward fails with
  * ESR_ERR_CAPACITY and sets workspace_needed when it is too small), then
  *   esr_render_voxurff_fwd: rays_o / rays_d / viewdirs f32 [n,3], em_modes i64 [n] -> srgb/rgb [n,3], lin/rgb [n,3],
