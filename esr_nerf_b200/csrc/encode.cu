@@ -2,6 +2,7 @@
 // trilinear gathers + scatter-add), tone-map encode fwd/bwd, and the per-ray compositing fwd/bwd that
 // replaces torch_scatter.segment_coo.
 #include "common.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 #include "mlp_layout.cuh"
@@ -52,6 +53,11 @@ struct SdfFrame {
   int size[3];       // (Z, Y, X)
 };
 
+// FAST (backward kernels only): without the renormalisation round trip, which moves a coordinate by an ulp or two (two
+// IEEE divisions per coordinate, a quarter of k_encode_bwd's instructions).  Interpolation is continuous in the
+// coordinate, so a cotangent routed with weights that differ by 1e-7 — or, within an ulp of a plane, through the
+// neighbouring cell with weight ~0 — differs from the exact routing by less than fp32 summation order does.
+template <bool FAST = false>
 ESR_D SdfFrame make_frame(const esr_scene_t &sc, float ix, float iy, float iz) {
   SdfFrame f;
   f.c[0] = iz, f.c[1] = iy, f.c[2] = ix;
@@ -59,7 +65,8 @@ ESR_D SdfFrame make_frame(const esr_scene_t &sc, float ix, float iy, float iz) {
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     f.fb[a] = (int)floorf(f.c[a]);
-    const float r = renorm_index(clampf(f.c[a], 0.f, (float)(f.size[a] - 1)), f.size[a]);
+    const float cl = clampf(f.c[a], 0.f, (float)(f.size[a] - 1));
+    const float r = FAST ? cl : renorm_index(cl, f.size[a]);
     const float fl = floorf(r);
     f.o0[a] = (int)fl;
     f.wl[a] = __fsub_rn((float)(f.o0[a] + 1), r);
@@ -107,10 +114,11 @@ struct TapRef {
   float coord;   // clamped displaced coordinate (finite-difference denominator, voxurff.py:711)
 };
 
+template <bool FAST = false>
 ESR_D TapRef tap_ref(const SdfFrame &f, int a, float off) {
   TapRef t;
   t.coord = clampf(__fadd_rn(f.c[a], off), 0.f, (float)(f.size[a] - 1));
-  const float p = renorm_index(t.coord, f.size[a]);
+  const float p = FAST ? t.coord : renorm_index(t.coord, f.size[a]);
   const float fl = floorf(p);
   int idx = (int)fl - (f.fb[a] - 2);
   t.wl = __fsub_rn(fl + 1.f, p);
@@ -403,6 +411,72 @@ __global__ void __launch_bounds__(ENC_THREADS, 8)
   }
 }
 
+// Cotangents of the 18 line values of one sample (per-thread shared-memory column s_dl) from the cotangents of its 24
+// taps and 12 normal components — the backward of the tap / finite-difference / normalisation chain of k_encode_fwd.
+// FAST: reciprocals through MUFU.RCP (2 ulp) instead of IEEE divisions, taps without the renormalisation round trip.
+template <bool FAST = false>
+ESR_D void line_cotangents(const esr_scene_t &sc, const SdfFrame &fr, const float (&dv)[52], const float *__restrict__ saved_fd,
+                           int64_t j, const float *__restrict__ sdf_grid, float *s_lines, float *s_dl) {
+  const float disp[4] = {0.5f, 1.0f, 1.5f, 2.0f};
+  // the finite-difference gradients either come from the forward pass (saved_fd: no grid reads in this kernel) or
+  // are recomputed from the 18 line values
+  if (!saved_fd) load_lines(fr, sdf_grid, s_lines);
+#pragma unroll
+  for (int i = 0; i < N_LINES; ++i) s_dl[i * ENC_THREADS + threadIdx.x] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    TapRef tr[6];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) tr[t] = tap_ref<FAST>(fr, t >> 1, (t & 1) ? disp[k] : -disp[k]);
+    float gr[3], scale[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float diff = tr[2 * a + 1].coord - tr[2 * a].coord + sc.fd_eps;
+      scale[a] = FAST ? __fdividef(1.f, diff * sc.voxel_size) : 1.f / diff / sc.voxel_size;
+    }
+    if (saved_fd) {
+      const float4 q = __ldg(reinterpret_cast<const float4 *>(saved_fd + j * 16 + 4 * k));
+      gr[0] = q.x, gr[1] = q.y, gr[2] = q.z;
+    } else {
+      float f[6];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        const float lo = s_lines[tr[t].slot * ENC_THREADS + threadIdx.x], hi = s_lines[(tr[t].slot + 1) * ENC_THREADS + threadIdx.x];
+        f[t] = __fmaf_rn(hi, tr[t].wh, __fmul_rn(lo, tr[t].wl));
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) gr[a] = (f[2 * a + 1] - f[2 * a]) * scale[a];
+    }
+    const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
+    const float den = fmaxf(nrm, 1e-12f);
+    float dn[3], dot = 0.f;
+    [[maybe_unused]] const float inv_den = FAST ? __fdividef(1.f, den) : 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      dn[a] = dv[COL_NRM + a * 4 + k];
+      dot += (FAST ? gr[a] * inv_den : gr[a] / den) * dn[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      // d(g/max(|g|,eps)): the |g| term only exists where the clamp is inactive
+      float dg;
+      if constexpr (FAST)
+        dg = (nrm > 1e-12f) ? (dn[a] - (gr[a] * inv_den) * dot) * inv_den : dn[a] * inv_den;
+      else
+        dg = (nrm > 1e-12f) ? (dn[a] - (gr[a] / den) * dot) / den : dn[a] / den;
+      const float dfd = dg * scale[a];
+      const float d_hi = dv[COL_FEAT + (2 * a + 1) * 4 + k] + dfd;
+      const float d_lo = dv[COL_FEAT + (2 * a) * 4 + k] - dfd;
+      // tap cotangent -> its two line values (per-thread column: plain read-modify-write)
+      const TapRef &th = tr[2 * a + 1], &tl = tr[2 * a];
+      s_dl[th.slot * ENC_THREADS + threadIdx.x] += d_hi * th.wl;
+      s_dl[(th.slot + 1) * ENC_THREADS + threadIdx.x] += d_hi * th.wh;
+      s_dl[tl.slot * ENC_THREADS + threadIdx.x] += d_lo * tl.wl;
+      s_dl[(tl.slot + 1) * ENC_THREADS + threadIdx.x] += d_lo * tl.wh;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ENC_THREADS, 5)
     k_encode_bwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
                  const float *__restrict__ rays_d, const float *__restrict__ sdf_grid,
@@ -445,60 +519,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
       scatterC<6>(g_third, sc.gx, sc.gy, sc.gz, c, d3);
     }
   }
-  const float disp[4] = {0.5f, 1.0f, 1.5f, 2.0f};
   const SdfFrame fr = make_frame(sc, g.ix, g.iy, g.iz);
-  // the finite-difference gradients either come from the forward pass (saved_fd: no grid reads in this kernel) or
-  // are recomputed from the 18 line values
-  if (!saved_fd) load_lines(fr, sdf_grid, s_lines);
-#pragma unroll
-  for (int i = 0; i < N_LINES; ++i) s_dl[i * ENC_THREADS + threadIdx.x] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    TapRef tr[6];
-#pragma unroll
-    for (int t = 0; t < 6; ++t) tr[t] = tap_ref(fr, t >> 1, (t & 1) ? disp[k] : -disp[k]);
-    float gr[3], scale[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float diff = tr[2 * a + 1].coord - tr[2 * a].coord + sc.fd_eps;
-      scale[a] = 1.f / diff / sc.voxel_size;
-    }
-    if (saved_fd) {
-      const float4 q = __ldg(reinterpret_cast<const float4 *>(saved_fd + j * 16 + 4 * k));
-      gr[0] = q.x, gr[1] = q.y, gr[2] = q.z;
-    } else {
-      float f[6];
-#pragma unroll
-      for (int t = 0; t < 6; ++t) {
-        const float lo = s_lines[tr[t].slot * ENC_THREADS + threadIdx.x], hi = s_lines[(tr[t].slot + 1) * ENC_THREADS + threadIdx.x];
-        f[t] = __fmaf_rn(hi, tr[t].wh, __fmul_rn(lo, tr[t].wl));
-      }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) gr[a] = (f[2 * a + 1] - f[2 * a]) * scale[a];
-    }
-    const float nrm = sqrtf(gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
-    const float den = fmaxf(nrm, 1e-12f);
-    float dn[3], dot = 0.f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      dn[a] = dv[COL_NRM + a * 4 + k];
-      dot += (gr[a] / den) * dn[a];
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      // d(g/max(|g|,eps)): the |g| term only exists where the clamp is inactive
-      const float dg = (nrm > 1e-12f) ? (dn[a] - (gr[a] / den) * dot) / den : dn[a] / den;
-      const float dfd = dg * scale[a];
-      const float d_hi = dv[COL_FEAT + (2 * a + 1) * 4 + k] + dfd;
-      const float d_lo = dv[COL_FEAT + (2 * a) * 4 + k] - dfd;
-      // tap cotangent -> its two line values (per-thread column: plain read-modify-write)
-      const TapRef &th = tr[2 * a + 1], &tl = tr[2 * a];
-      s_dl[th.slot * ENC_THREADS + threadIdx.x] += d_hi * th.wl;
-      s_dl[(th.slot + 1) * ENC_THREADS + threadIdx.x] += d_hi * th.wh;
-      s_dl[tl.slot * ENC_THREADS + threadIdx.x] += d_lo * tl.wl;
-      s_dl[(tl.slot + 1) * ENC_THREADS + threadIdx.x] += d_lo * tl.wh;
-    }
-  }
+  line_cotangents(sc, fr, dv, saved_fd, j, sdf_grid, s_lines, s_dl);
   {  // z-displaced lines: the six planes fb-2 .. fb+3 of one (y, x) corner are six consecutive floats -> 8-byte REDs
     // on the even-aligned pairs (3 or 4 requests per corner instead of 6)
     float dlz[6];
@@ -569,6 +591,202 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_encode_bwd with run-merged REDs.
+//
+// The scatter above is bound by the number of RED requests (~75 per sample; L2 atomic units 82 % busy, DRAM at 19 %).
+// Consecutive threads are consecutive samples of one ray, half a voxel apart, so a voxel that receives a contribution
+// from one sample receives one from the next 2-4 samples as well (colour corners: mean chord through the 2 x 2 x 2
+// footprint x 2 samples per voxel length = 2.7; line corners, 2 x 2 x 6 footprint: 3.4).  Those contributions are
+// summed in the warp before they leave it:
+//   * every scatter target is enumerated in CANONICAL rounds, keyed by the voxel's own coordinates — the parity of a
+//     corner, the plane index modulo 6, the aligned z-pair index modulo 2 / 4 — never by the corner's role in the lane's
+//     cell, so that two lanes that touch the same voxel do so in the same round whatever their cells are;
+//   * in a round every lane holds (key = voxel index or -1, values); runs of equal keys over consecutive lanes (cut at
+//     multiples of 8 lanes) are summed towards the run's first lane by a three-step segmented shuffle reduction, and
+//     only that lane issues the RED (skipped when the sum is exactly zero).
+// Requires an even Z (aligned pairs / static 16-byte alignment of the colour corners) and < 2^31 voxels; the plain
+// kernel above serves everything else (odd grids, explicit point lists whose rows are not ordered along rays).
+// ---------------------------------------------------------------------------------------------
+struct Runs {
+  uint32_t after;   // bit d - 1: lane + d starts a new run (or lies outside the warp)
+  bool head;        // first lane of a run with a valid key
+};
+ESR_D Runs make_runs(int key, unsigned lane) {
+  const int prev = __shfl_up_sync(FULL, key, 1);
+  const bool start = ((lane & 7) == 0) | (key != prev) | (key < 0);
+  const uint32_t sm = __ballot_sync(FULL, start);
+  Runs r;
+  r.after = (uint32_t)((((uint64_t)1 << 32) | sm) >> (lane + 1));
+  r.head = start & (key >= 0);
+  return r;
+}
+template <int N>
+ESR_D void run_sum(float (&v)[N], const Runs &r) {
+#pragma unroll
+  for (int d = 1; d <= 4; d <<= 1) {
+    const bool ok = (r.after & ((1u << d) - 1u)) == 0u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float o = __shfl_down_sync(FULL, v[i], d);
+      if (ok) v[i] += o;
+    }
+  }
+}
+ESR_D int pos_mod6(int v) {
+  const int m = v % 6;
+  return m < 0 ? m + 6 : m;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 6)
+    k_encode_bwd_merged(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                        const float *__restrict__ rays_d, const float *__restrict__ sdf_grid,
+                        const int32_t *__restrict__ h_ray, const int32_t *__restrict__ h_step, int64_t m3,
+                        const float *__restrict__ d_feat, float *__restrict__ g_sdf, float *__restrict__ g_off,
+                        float *__restrict__ g_emo, const float *__restrict__ d_third, float *__restrict__ g_third,
+                        const float *__restrict__ saved_fd) {
+  __shared__ float s_lines[N_LINES * ENC_THREADS], s_dl[N_LINES * ENC_THREADS];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31;
+  const bool active = j < m3;
+  const int64_t js = active ? j : m3 - 1;   // rows past the end replay the last row with zero cotangents and no keys
+  float px, py, pz;
+  sample_pos(sc, rays_o, rays_d, nullptr, h_ray, h_step, js, px, py, pz);
+  TapGeom g;
+  g.ix = world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx);
+  g.iy = world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy);
+  g.iz = world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz);
+  const float *d = d_feat + js * ESR_FEAT_GRAD_DIM;
+  float dv[52];
+#pragma unroll
+  for (int i = 0; i < 52; i += 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(d + i));
+    dv[i] = q.x, dv[i + 1] = q.y, dv[i + 2] = q.z, dv[i + 3] = q.w;
+  }
+  if (!active) {
+#pragma unroll
+    for (int i = 0; i < 52; ++i) dv[i] = 0.f;
+  }
+  const int X = sc.gx, Y = sc.gy, Z = sc.gz;
+  const SdfFrame fr = make_frame<true>(sc, g.ix, g.iy, g.iz);
+  line_cotangents<true>(sc, fr, dv, saved_fd, js, sdf_grid, s_lines, s_dl);
+
+  {  // ---- colour grids + the sdf feature: the 8 corners of the sample's cell, rounds keyed by corner parity ----
+    const int x0 = (int)floorf(g.ix), y0 = (int)floorf(g.iy), z0 = (int)floorf(g.iz);
+    const float z_lo = __fsub_rn((float)(z0 + 1), g.iz), z_hi = __fsub_rn(g.iz, (float)z0);
+    const float y_lo = __fsub_rn((float)(y0 + 1), g.iy), y_hi = __fsub_rn(g.iy, (float)y0);
+    const float x_lo = __fsub_rn((float)(x0 + 1), g.ix), x_hi = __fsub_rn(g.ix, (float)x0);
+    const bool any_off = (dv[0] != 0.f) | (dv[1] != 0.f) | (dv[2] != 0.f) | (dv[3] != 0.f) | (dv[4] != 0.f) | (dv[5] != 0.f);
+    const bool any_emo = (dv[6] != 0.f) | (dv[7] != 0.f) | (dv[8] != 0.f) | (dv[9] != 0.f) | (dv[10] != 0.f) | (dv[11] != 0.f);
+    const bool w_off = g_off && __any_sync(FULL, any_off), w_emo = g_emo && __any_sync(FULL, any_emo);
+    const bool w_sdf = __any_sync(FULL, dv[COL_SDF] != 0.f);
+    float d3[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (g_third && active) {
+#pragma unroll
+      for (int i = 0; i < 6; i += 2) {
+        const float2 q = __ldg(reinterpret_cast<const float2 *>(d_third + j * 6 + i));
+        d3[i] = q.x, d3[i + 1] = q.y;
+      }
+    }
+    auto colour = [&](float *__restrict__ grid, const float *dc, float w, int vox, const Runs &runs, bool odd) {
+      float e[6];
+#pragma unroll
+      for (int ch = 0; ch < 6; ++ch) e[ch] = dc[ch] * w;
+      run_sum<6>(e, runs);
+      if (runs.head && ((e[0] != 0.f) | (e[1] != 0.f) | (e[2] != 0.f) | (e[3] != 0.f) | (e[4] != 0.f) | (e[5] != 0.f))) {
+        float *p = grid + (int64_t)vox * 6;   // 24 bytes per voxel: 16-byte aligned for even voxels, 8 (mod 16) for odd ones
+        if (!odd) {
+          red_add4(p, e[0], e[1], e[2], e[3]);
+          red_add2(p + 4, e[4], e[5]);
+        } else {
+          red_add2(p, e[0], e[1]);
+          red_add4(p + 2, e[2], e[3], e[4], e[5]);
+        }
+      }
+    };
+#pragma unroll
+    for (int rho = 0; rho < 8; ++rho) {
+      const int dx = ((rho >> 2) ^ x0) & 1, dy = ((rho >> 1) ^ y0) & 1, dz = (rho ^ z0) & 1;
+      const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
+      const float w = __fmul_rn(__fmul_rn(dz ? z_hi : z_lo, dy ? y_hi : y_lo), dx ? x_hi : x_lo);
+      const int vox = (active && in_grid(x, y, z, X, Y, Z)) ? (x * Y + y) * Z + z : -1;
+      const Runs runs = make_runs(vox, lane);
+      if (w_off) colour(g_off, dv, w, vox, runs, rho & 1);        // Z is even: the voxel index has the parity of z
+      if (w_emo) colour(g_emo, dv + 6, w, vox, runs, rho & 1);
+      if (g_third) colour(g_third, d3, w, vox, runs, rho & 1);
+      if (w_sdf) {
+        float e[1] = {dv[COL_SDF] * w};
+        run_sum<1>(e, runs);
+        if (runs.head && e[0] != 0.f) red_add(g_sdf + vox, e[0]);
+      }
+    }
+  }
+
+  // ---- line cotangents -> grid.  One round = one aligned z-pair of voxels (8-byte RED) ----
+  auto pair_round = [&](int key, float a0, float a1) {
+    const Runs runs = make_runs(key, lane);
+    float e[2] = {a0, a1};
+    run_sum<2>(e, runs);
+    if (runs.head && ((e[0] != 0.f) | (e[1] != 0.f))) red_add2(g_sdf + key, e[0], e[1]);
+  };
+  {  // z-displaced lines: planes zb .. zb + 5 of the four (y, x) corners; rounds keyed by (pair index mod 4, y parity, x parity)
+    const int zb = fr.fb[0] - 2, pf = zb >> 1;
+#pragma unroll
+    for (int rho = 0; rho < 4; ++rho) {
+      const int pi = pf + ((rho - pf) & 3), zz = 2 * pi, jl0 = zz - zb;   // jl0 in {-1, 0, .., 6}
+      const float d0 = (unsigned)jl0 < 6u ? s_dl[jl0 * ENC_THREADS + threadIdx.x] : 0.f;
+      const float d1 = (unsigned)(jl0 + 1) < 6u ? s_dl[(jl0 + 1) * ENC_THREADS + threadIdx.x] : 0.f;
+      const bool z_ok = active && (unsigned)zz < (unsigned)Z && jl0 < 6;
+#pragma unroll
+      for (int py2 = 0; py2 < 2; ++py2)
+#pragma unroll
+        for (int px2 = 0; px2 < 2; ++px2) {
+          const int dy = (py2 ^ fr.o0[1]) & 1, dx = (px2 ^ fr.o0[2]) & 1;
+          const int qy = fr.o0[1] + dy, qx = fr.o0[2] + dx;
+          const float w = __fmul_rn(dy ? fr.wh[1] : fr.wl[1], dx ? fr.wh[2] : fr.wl[2]);
+          const bool ok = z_ok && (unsigned)qy < (unsigned)Y && (unsigned)qx < (unsigned)X;
+          pair_round(ok ? (qx * Y + qy) * Z + zz : -1, d0 * w, d1 * w);
+        }
+    }
+  }
+  // y- and x-displaced lines: plane p of the displaced axis, corner qc of the other non-z axis, z corner qz — one voxel
+  // per round, keyed by (p mod 6, parity of qc, parity of qz).  (Aligned z-pairs as above would halve the requests of
+  // the lanes whose z0 is even but leave half of the rounds of those lanes empty: the instruction count is what
+  // bounds this kernel once the REDs are merged.)
+  auto single_round = [&](int key, float v) {
+    const Runs runs = make_runs(key, lane);
+    float e[1] = {v};
+    run_sum<1>(e, runs);
+    if (runs.head && e[0] != 0.f) red_add(g_sdf + key, e[0]);
+  };
+#pragma unroll
+  for (int a = 1; a < 3; ++a) {
+    const int c = a == 2 ? 1 : 2;   // the other non-z axis
+    const int m_a = pos_mod6(fr.fb[a] - 2);
+#pragma unroll
+    for (int rho = 0; rho < 6; ++rho) {
+      int jl = rho - m_a;
+      jl += jl < 0 ? 6 : 0;
+      const int p = fr.fb[a] - 2 + jl;
+      const float dl = s_dl[(a * 6 + jl) * ENC_THREADS + threadIdx.x];
+      const bool p_ok = active && (unsigned)p < (unsigned)fr.size[a];
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) {
+        const int dc = (pc ^ fr.o0[c]) & 1, qc = fr.o0[c] + dc;
+        const float dlc = dl * (dc ? fr.wh[c] : fr.wl[c]);
+        const bool c_ok = p_ok && (unsigned)qc < (unsigned)fr.size[c];
+        const int qy = a == 1 ? p : qc, qx = a == 1 ? qc : p;
+        const int row = (qx * Y + qy) * Z;
+#pragma unroll
+        for (int pz2 = 0; pz2 < 2; ++pz2) {
+          const int dz = (pz2 ^ fr.o0[0]) & 1, qz = fr.o0[0] + dz;
+          single_round((c_ok && (unsigned)qz < (unsigned)Z) ? row + qz : -1, dlc * (dz ? fr.wh[0] : fr.wl[0]));
+        }
+      }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Coarse-stage feature encode (voxurfc.py:205-249), thread per shaded sample.
@@ -883,9 +1101,17 @@ static int encode_bwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
   ESR_CHECK_ARG(pts || (rays_o && rays_d && h_ray && h_step));
   ESR_CHECK_ARG(!d_third == !grad_third_grid);
   ESR_STAGE("k_encode_bwd", (cudaStream_t)stream);
-  k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
-                                                                d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
-                                                                pts, d_third, grad_third_grid, saved_fd);
+  // rows ordered along rays on an even-Z grid: REDs merged over runs of consecutive samples (ESR_ENCODE_BWD_PLAIN=1: A/B)
+  const char *env = getenv("ESR_ENCODE_BWD_PLAIN");   // (read per call: the A/B test flips it inside one process)
+  const bool plain = env && env[0] && env[0] != '0';
+  if (!pts && !plain && (sc->gz & 1) == 0 && (int64_t)sc->gx * sc->gy * sc->gz < ((int64_t)1 << 31))
+    k_encode_bwd_merged<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
+                                                                         d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
+                                                                         d_third, grad_third_grid, saved_fd);
+  else
+    k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
+                                                                  d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
+                                                                  pts, d_third, grad_third_grid, saved_fd);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

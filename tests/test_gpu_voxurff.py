@@ -400,3 +400,29 @@ def test_other_net_shapes_run_on_the_same_chains(width, depth, tone_width):
         assert ok, (name, msg)
         checked += 1
     assert checked >= 3 + 2 * 2 * depth + 4
+
+
+@pytest.mark.parametrize("size", ["golden", "config2"])
+def test_encode_backward_merged_reds_equal_plain_scatter(size, monkeypatch):
+    """k_encode_bwd_merged (RED requests summed over runs of consecutive samples before they leave the warp) against the
+    plain thread-per-sample scatter on the same cotangents: same grid gradients up to summation order, nothing written
+    where the plain kernel writes nothing."""
+    if size == "golden":
+        fx, weights = C.load_case("fine_sparse_s60_big")
+        n = 192
+    else:
+        _, weights = C.load_case("fine_sparse_s20")
+        fx = dict(mask_res=100, sparse=1, s_val=20.0, num_voxels=256 ** 3, ray_seed=77)
+        n = 8192
+    rays = S.make_rays(n, 77)
+    grads = {}
+    for plain in ("1", "0"):
+        monkeypatch.setenv("ESR_ENCODE_BWD_PLAIN", plain)
+        m, _ = _run_product(dict(fx, n_rays=n), weights, "torch_fp32", False, rays=rays)
+        grads[plain] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None and "grid" in k}
+    assert set(grads["0"]) == set(grads["1"]) and len(grads["0"]) == 3
+    for k, ref in grads["1"].items():
+        got = grads["0"][k]
+        assert float(ref.abs().max()) > 0, k
+        assert C.rel_err(got, ref) < 2e-5, (k, C.rel_err(got, ref))
+        assert not ((ref == 0) & (got != 0)).any(), k
