@@ -606,6 +606,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 5)
 //   * in a round every lane holds (key = voxel index or -1, values); runs of equal keys over consecutive lanes (cut at
 //     multiples of 8 lanes) are summed towards the run's first lane by a three-step segmented shuffle reduction, and
 //     only that lane issues the RED (skipped when the sum is exactly zero).
+// ncu at config 2 (profiles/r02_encode_bwd_merged.md): RED requests 19.0 M -> 11.7 M warp-level requests, L2 83 % -> 66 %
+// busy with the kernel 1.45x faster, issue slots 30 % -> 50 % busy; what bounds it now is the shuffle / shared-memory
+// traffic of the merge itself (L1TEX 77 % busy), not the atomics.
 // Requires an even Z (aligned pairs / static 16-byte alignment of the colour corners) and < 2^31 voxels; the plain
 // kernel above serves everything else (odd grids, explicit point lists whose rows are not ordered along rays).
 // ---------------------------------------------------------------------------------------------
@@ -613,19 +616,20 @@ struct Runs {
   uint32_t after;   // bit d - 1: lane + d starts a new run (or lies outside the warp)
   bool head;        // first lane of a run with a valid key
 };
+template <int STEPS>   // runs are cut at multiples of 2^STEPS lanes
 ESR_D Runs make_runs(int key, unsigned lane) {
   const int prev = __shfl_up_sync(FULL, key, 1);
-  const bool start = ((lane & 7) == 0) | (key != prev) | (key < 0);
+  const bool start = ((lane & ((1u << STEPS) - 1u)) == 0) | (key != prev) | (key < 0);
   const uint32_t sm = __ballot_sync(FULL, start);
   Runs r;
   r.after = (uint32_t)((((uint64_t)1 << 32) | sm) >> (lane + 1));
   r.head = start & (key >= 0);
   return r;
 }
-template <int N>
+template <int N, int STEPS>
 ESR_D void run_sum(float (&v)[N], const Runs &r) {
 #pragma unroll
-  for (int d = 1; d <= 4; d <<= 1) {
+  for (int d = 1; d < (1 << STEPS); d <<= 1) {
     const bool ok = (r.after & ((1u << d) - 1u)) == 0u;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -639,6 +643,7 @@ ESR_D int pos_mod6(int v) {
   return m < 0 ? m + 6 : m;
 }
 
+template <int STEPS>
 __global__ void __launch_bounds__(ENC_THREADS, 6)
     k_encode_bwd_merged(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
                         const float *__restrict__ rays_d, const float *__restrict__ sdf_grid,
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 6)
       float e[6];
 #pragma unroll
       for (int ch = 0; ch < 6; ++ch) e[ch] = dc[ch] * w;
-      run_sum<6>(e, runs);
+      run_sum<6, STEPS>(e, runs);
       if (runs.head && ((e[0] != 0.f) | (e[1] != 0.f) | (e[2] != 0.f) | (e[3] != 0.f) | (e[4] != 0.f) | (e[5] != 0.f))) {
         float *p = grid + (int64_t)vox * 6;   // 24 bytes per voxel: 16-byte aligned for even voxels, 8 (mod 16) for odd ones
         if (!odd) {
@@ -711,13 +716,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 6)
       const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
       const float w = __fmul_rn(__fmul_rn(dz ? z_hi : z_lo, dy ? y_hi : y_lo), dx ? x_hi : x_lo);
       const int vox = (active && in_grid(x, y, z, X, Y, Z)) ? (x * Y + y) * Z + z : -1;
-      const Runs runs = make_runs(vox, lane);
+      const Runs runs = make_runs<STEPS>(vox, lane);
       if (w_off) colour(g_off, dv, w, vox, runs, rho & 1);        // Z is even: the voxel index has the parity of z
       if (w_emo) colour(g_emo, dv + 6, w, vox, runs, rho & 1);
       if (g_third) colour(g_third, d3, w, vox, runs, rho & 1);
       if (w_sdf) {
         float e[1] = {dv[COL_SDF] * w};
-        run_sum<1>(e, runs);
+        run_sum<1, STEPS>(e, runs);
         if (runs.head && e[0] != 0.f) red_add(g_sdf + vox, e[0]);
       }
     }
@@ -725,9 +730,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 6)
 
   // ---- line cotangents -> grid.  One round = one aligned z-pair of voxels (8-byte RED) ----
   auto pair_round = [&](int key, float a0, float a1) {
-    const Runs runs = make_runs(key, lane);
+    const Runs runs = make_runs<STEPS>(key, lane);
     float e[2] = {a0, a1};
-    run_sum<2>(e, runs);
+    run_sum<2, STEPS>(e, runs);
     if (runs.head && ((e[0] != 0.f) | (e[1] != 0.f))) red_add2(g_sdf + key, e[0], e[1]);
   };
   {  // z-displaced lines: planes zb .. zb + 5 of the four (y, x) corners; rounds keyed by (pair index mod 4, y parity, x parity)
@@ -755,9 +760,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 6)
   // the lanes whose z0 is even but leave half of the rounds of those lanes empty: the instruction count is what
   // bounds this kernel once the REDs are merged.)
   auto single_round = [&](int key, float v) {
-    const Runs runs = make_runs(key, lane);
+    const Runs runs = make_runs<STEPS>(key, lane);
     float e[1] = {v};
-    run_sum<1>(e, runs);
+    run_sum<1, STEPS>(e, runs);
     if (runs.head && e[0] != 0.f) red_add(g_sdf + key, e[0]);
   };
 #pragma unroll
@@ -1105,9 +1110,10 @@ static int encode_bwd_impl(const esr_scene_t *sc, const float *rays_o, const flo
   const char *env = getenv("ESR_ENCODE_BWD_PLAIN");   // (read per call: the A/B test flips it inside one process)
   const bool plain = env && env[0] && env[0] != '0';
   if (!pts && !plain && (sc->gz & 1) == 0 && (int64_t)sc->gx * sc->gy * sc->gz < ((int64_t)1 << 31))
-    k_encode_bwd_merged<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
-                                                                         d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
-                                                                         d_third, grad_third_grid, saved_fd);
+    // (measured at config 2: runs cut at 4 / 8 / 16 lanes 1.21 / 1.14 / 1.18 ms; 5 / 6 / 7 blocks per SM 1.17 / 1.14 / 1.14 ms)
+    k_encode_bwd_merged<3><<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
+                                                                            d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
+                                                                            d_third, grad_third_grid, saved_fd);
   else
     k_encode_bwd<<<cdiv(m3, 128), 128, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray, h_step, m3,
                                                                   d_feat, grad_sdf_grid, grad_off_grid, grad_emo_grid,
