@@ -100,12 +100,16 @@ def parse():
                     help="N>1: all-reduce the dense grid gradients instead of the occupancy-compacted voxel set")
     ap.add_argument("--no-gather", action="store_true",
                     help="eval, N>1: leave every rank's slice of the maps where it is (default: gathered on rank 0 inside the "
-                         "timed step, dist.gather_maps — gloo-checked, not yet measured on NCCL)")
+                         "timed step, dist.gather_maps: profiles/r02_bench_lines/eval_*_n{2,8}.json)")
     ap.add_argument("--block-exchange", action="store_true",
                     help="N>1: exact two-level exchange of the grid gradients (dist.TouchedBlockCompactor: OR-reduced map of "
                          "touched 8^3 blocks, then pack / all-reduce / unpack of their voxels) instead of the static "
-                         "occupancy set (fine) or the dense all-reduce (lts); checked on gloo, not yet measured on NCCL")
+                         "occupancy set; the lts stage's default (profiles/r02_bench_lines/lts_blocks_n*.json)")
+    ap.add_argument("--global-rays", type=int, default=None,
+                    help="strong scaling: rays per step over ALL GPUs (rays per GPU = global / N; the line says scaling: strong)")
     a = ap.parse_args()
+    if a.global_rays is not None:
+        a.rays = a.global_rays // max(a.gpus, 1)
     if a.rays is None:
         a.rays = {"fine": 1 << 16, "lts": 1 << 15, "eval": 1600 * 1200 // max(a.gpus, 1)}[a.stage]
     if a.ltspts is None:
@@ -792,6 +796,10 @@ def run_b200(a, rank, world, local_rank):
                 if name == "k_mlp_fwd_x2_radiance":   # the fp32-class forward costs three fp16 MMAs per algorithmic product
                     ex = per_s * FLOP_X2_EXECUTED / FLOP_RADIANCE
                     row.update(executed_tflops=ex / 1e12, frac_executed=ex / 1e12 / pk["bf16_tflops_sustained"])
+        if name == "k_encode_bwd":   # (a fraction above 1 is this accounting, not bandwidth)
+            row["note"] = ("face-value tap bytes (SURVEY 8d: 4 B x channels x 8 corners per tap, twice); the kernel sums the "
+                           "contributions of consecutive samples to a voxel in the warp and issues one RED for the run, so "
+                           "fewer bytes than that reach the L2 (profiles/r02_encode_bwd_merged.md)")
         stage_rows.append(row)
     stage_rows.sort(key=lambda r: -r["ms_per_step"])
     top = next((r for r in stage_rows if "bound" in r), None)
@@ -834,7 +842,8 @@ def run_b200(a, rank, world, local_rank):
               "eval": "render rays/sec (inference, 12 maps)"}[a.stage]
     line = {
         "metric": metric, "value": total_rays / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": max(a.warmup, 5), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(a.warmup, 5), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "strong" if a.global_rays is not None else "weak",
         "vs_baseline": None,
         "dtype": {"bf16": "f32 (grids, scan, compositing) + bf16 tensor-core MLPs, f32 accumulate",
                   "x2": "f32 (grids, scan, compositing) + tensor-core MLPs on fp16 operands (forward: hi + lo pairs, three "
