@@ -426,3 +426,33 @@ def test_encode_backward_merged_reds_equal_plain_scatter(size, monkeypatch):
         assert float(ref.abs().max()) > 0, k
         assert C.rel_err(got, ref) < 2e-5, (k, C.rel_err(got, ref))
         assert not ((ref == 0) & (got != 0)).any(), k
+
+
+@pytest.mark.parametrize("mode", ["torch_fp32", "x2"])
+def test_odd_grid_vs_oracle_port_fresh_rays(mode):
+    """A 45^3 grid (odd Z: the encode backward falls back to the plain thread-per-sample scatter, the aligned-pair REDs of
+    every scatter kernel to their scalar forms) and a dense 24^3 mask, 6144 unseen rays (enough shaded samples that the
+    handful of ReLU masks two correct fp32 evaluations disagree on stays below the 1e-4 class): streams bit-exact, outputs
+    and every parameter gradient against the oracle port at the mode's tolerance."""
+    _, weights = C.load_case("fine_sparse_s20")
+    fx = dict(num_voxels=45 ** 3, mask_res=24, sparse=0, s_val=60.0)
+    rays = S.make_rays(6144, 4242)
+    ref, inter, leaves = _oracle_run(fx, weights, rays)
+    m, out = _run_product(fx, weights, mode, True, rays)
+    assert tuple(m.sdf.grid.shape[2:]) == (45, 45, 45)
+    ray, step, w, st = _stream_in_ray_order(m)
+    assert torch.equal(ray, inter["m3_ray"]) and torch.equal(step, inter["m3_step"])
+    for k in OUT_KEYS:
+        assert C.rel_err(out[k], ref[k]) < OUT_TOL[mode], k
+    checked = 0
+    for name, p in m.named_parameters():
+        if name not in leaves or leaves[name].grad is None:
+            continue
+        if mode == "x2":
+            mx, l2 = C.grad_err(p.grad.contiguous(), leaves[name].grad)
+            assert mx < 1e-2 and l2 < 1e-2, (name, mx, l2)
+        else:
+            ok, msg = C.grad_close(p.grad.contiguous(), leaves[name].grad, 1e-4)
+            assert ok, (name, msg)
+        checked += 1
+    assert checked >= 3 + 8 + 8 + 4
