@@ -106,12 +106,16 @@ def test_esrnerf_gradients_vs_golden(case):
     assert checked >= 40
 
 
-def test_esrnerf_port_as_live_oracle_on_new_rays():
-    """rays / draws the fixtures never saw: product vs the port run side by side"""
+@pytest.mark.parametrize("num_voxels", [None, 37 ** 3])
+def test_esrnerf_port_as_live_oracle_on_new_rays(num_voxels):
+    """rays / draws the fixtures never saw: product vs the port run side by side — on the fixture's grid and on an odd one
+    (37^3: the scalar forms of the paired REDs, the plain encode-backward scatter)"""
     from oracle import esrnerf_port as E
 
     fx, weights = C.load_esrnerf_case("lts_sparse_s220")
     fx = dict(fx, ray_seed=2025, draw_seed=99, n_rays=200, s_val=90.0, pdra_mode=1)
+    if num_voxels is not None:
+        fx["num_voxels"] = num_voxels
     m, out = _run_product(fx, weights)
     ref, inter, _, _ = C.run_esrnerf_port(fx, weights, E.FixedDraws(99))
     st = m.last_streams["streams"]
