@@ -628,3 +628,43 @@ def test_optimizer_groups_of_every_stage_match_reference():
         assert {n: p.requires_grad for n, p in ref.named_parameters()} == \
                {n: p.requires_grad for n, p in mine.named_parameters()}, stage
         assert sorted(o_mine.name2pg) == sorted(o_ref.name2pg), stage
+
+
+NON_CUBIC_BOX = ([-1.05, -0.9, -0.75], [1.05, 0.9, 0.75])     # -> 56 x 48 x 40 voxels at num_voxels = 56 * 48 * 40
+
+
+def test_port_matches_reference_on_a_non_cubic_box(monkeypatch):
+    """Every fixture lives in a cube: an X / Y / Z mix-up in strides or sizes would be invisible there.  The port against
+    the reference's own VoxurfF in a 56 x 48 x 40 box (what tests/test_gpu_voxurff.py::test_non_cubic_grid_* then holds the
+    CUDA path to)."""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import voxurf_port as P
+    from oracle.make_golden import build_reference_model
+
+    monkeypatch.setattr(S, "BBOX_MIN", torch.tensor(NON_CUBIC_BOX[0]))
+    monkeypatch.setattr(S, "BBOX_MAX", torch.tensor(NON_CUBIC_BOX[1]))
+    _, weights = C.load_case("fine_sparse_s20")
+    nv, mask_res, s_val, n = 56 * 48 * 40, 24, 60.0, 256
+    ref = build_reference_model(nv, mask_res, False, s_val, weights)
+    assert [int(w) for w in ref.world_size] == [56, 48, 40]
+    rays = S.make_rays(n, 777)
+    ref_out = ref(s_val=s_val, **rays)
+    scene = C.oracle_scene(nv, mask_res, False)
+    assert scene["world_size"] == [56, 48, 40]
+    params, leaves = C.oracle_params(scene, weights)
+    out, inter = P.voxurff_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                            rays["em_modes"], s_val)
+    assert len(inter["m3_ray"]) > 1000
+    cot = C.cotangents(n)
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    ref_grads = dict(ref.named_parameters())
+    for name, leaf in leaves.items():
+        if name in ref_grads and ref_grads[name].grad is not None:
+            assert C.rel_err(leaf.grad, ref_grads[name].grad) < 1e-5, name
