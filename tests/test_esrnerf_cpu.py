@@ -168,3 +168,48 @@ def test_esrnerf_port_matches_reference_other_samplers_and_envmaps(ray_sampling,
     for name, p in ref.named_parameters():
         if p.grad is not None:
             assert C.rel_err(leaves[name].grad, p.grad) < 1e-5, name
+
+
+def test_esrnerf_port_matches_reference_on_a_non_cubic_box(monkeypatch):
+    """The LTS / PDRA training step in a 46 x 40 x 33 box (every fixture is a cube): port vs the reference's own class,
+    same RNG calls — what tests/test_gpu_esrnerf.py::test_esrnerf_port_as_live_oracle_on_new_rays[non_cubic] then holds
+    the CUDA path to."""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import esrnerf_port as E
+    from oracle.make_golden import build_reference_esrnerf
+
+    monkeypatch.setattr(S, "BBOX_MIN", torch.tensor([-1.05, -0.9, -0.75]))
+    monkeypatch.setattr(S, "BBOX_MAX", torch.tensor([1.05, 0.9, 0.75]))
+    fx, weights = C.load_esrnerf_case("pdra_sparse_s60")
+    fx = dict(fx, num_voxels=46 * 40 * 33, mask_res=20, sparse=0)
+    n, s_val = 96, 35.0
+    ref = build_reference_esrnerf(int(fx["num_voxels"]), int(fx["mask_res"]), False, s_val, weights, num_2ndrays=8,
+                                  num_ltspts=16)
+    assert len({int(w) for w in ref.world_size}) == 3, ref.world_size
+    ref.pdra_mode = True
+    rays = S.make_rays(n, 4243)
+    um = S.uncert_masks(n)
+    np.random.seed(5)
+    torch.manual_seed(11)
+    ref_out = ref(s_val=s_val, rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+                  em_modes=rays["em_modes"], uncert_masks=um, normal_eps=0.01, emit_eps=0.03)
+    scene = C.esrnerf_oracle_scene(dict(fx, num_2ndrays=8, num_ltspts=16))
+    assert scene["world_size"] == [int(w) for w in ref.world_size]
+    params, leaves = C.esrnerf_oracle_params(scene, weights)
+    np.random.seed(5)
+    torch.manual_seed(11)
+    out, _ = E.esrnerf_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                        rays["em_modes"], um, s_val, 0.01, 0.03, True, E.Draws())
+    cot = C.esrnerf_cotangents(out)
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    assert set(out) == set(ref_out)
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    for name, p in ref.named_parameters():
+        if p.grad is not None:
+            assert C.rel_err(leaves[name].grad, p.grad) < 1e-5, name

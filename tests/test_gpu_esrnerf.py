@@ -106,19 +106,26 @@ def test_esrnerf_gradients_vs_golden(case):
     assert checked >= 40
 
 
-@pytest.mark.parametrize("num_voxels", [None, 37 ** 3])
-def test_esrnerf_port_as_live_oracle_on_new_rays(num_voxels):
-    """rays / draws the fixtures never saw: product vs the port run side by side — on the fixture's grid and on an odd one
-    (37^3: the scalar forms of the paired REDs, the plain encode-backward scatter)"""
+@pytest.mark.parametrize("grid", ["fixture", "odd", "non_cubic"])
+def test_esrnerf_port_as_live_oracle_on_new_rays(grid, monkeypatch):
+    """rays / draws the fixtures never saw: product vs the port run side by side — on the fixture's grid, on an odd one
+    (37^3: the scalar forms of the paired REDs, the plain encode-backward scatter) and in a non-cubic box (46 x 40 x 33
+    voxels: the port is pinned to the reference's class there by tests/test_esrnerf_cpu.py)"""
     from oracle import esrnerf_port as E
 
     fx, weights = C.load_esrnerf_case("lts_sparse_s220")
     fx = dict(fx, ray_seed=2025, draw_seed=99, n_rays=200, s_val=90.0, pdra_mode=1)
-    if num_voxels is not None:
-        fx["num_voxels"] = num_voxels
+    if grid == "odd":
+        fx["num_voxels"] = 37 ** 3
+    elif grid == "non_cubic":
+        monkeypatch.setattr(S, "BBOX_MIN", torch.tensor([-1.05, -0.9, -0.75]))
+        monkeypatch.setattr(S, "BBOX_MAX", torch.tensor([1.05, 0.9, 0.75]))
+        fx.update(num_voxels=46 * 40 * 33, mask_res=20, sparse=0)
     m, out = _run_product(fx, weights)
     ref, inter, _, _ = C.run_esrnerf_port(fx, weights, E.FixedDraws(99))
     st = m.last_streams["streams"]
+    if grid == "non_cubic":
+        assert len(set(m.sdf.grid.shape[2:])) == 3 and st.m3 > 200
     assert torch.equal(st.h_ray.long().cpu(), inter["m3_ray"]) and torch.equal(st.h_step.long().cpu(), inter["m3_step"])
     for k in sorted(out):
         assert tuple(out[k].shape) == tuple(ref[k].shape), k
