@@ -273,4 +273,16 @@ ESR_D float neus_alpha(float sd, float sd_prev, float sd_next, bool has_prev, bo
   return fminf(fmaxf(r, 0.f), 1.f);
 }
 
+// NeuS 'grad' alpha (functions.py:45-69): section-point SDFs estimated along the view direction,
+// sdf -+ iter_cos with iter_cos = (v . grad sdf) * dist * 0.5 (computed per sample by k_neus_cos_fwd)
+ESR_D float neus_alpha_grad(float sd, float iter_cos, float s_val, float &pc, float &nc) {
+  const float next_est = __fadd_rn(sd, iter_cos);
+  const float prev_est = __fsub_rn(sd, iter_cos);
+  pc = sigmoidf(__fmul_rn(prev_est, s_val));
+  nc = sigmoidf(__fmul_rn(next_est, s_val));
+  const float p = fmaxf(__fsub_rn(pc, nc), 0.f);
+  const float r = __fdiv_rn(__fadd_rn(p, 1e-5f), __fadd_rn(pc, 1e-5f));
+  return fminf(fmaxf(r, 0.f), 1.f);
+}
+
 }  // namespace esr

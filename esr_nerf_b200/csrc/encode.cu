@@ -929,6 +929,87 @@ __global__ void __launch_bounds__(ENC_THREADS)
 }
 
 // ---------------------------------------------------------------------------------------------
+// `neus_alpha: grad` (functions.py:45-69; voxurff.py:151-154, 193-198): the NeuS section-point estimate of every M1
+// sample, iter_cos = (viewdir . grad sdf) * dist * 0.5 with grad sdf = sample_sdf_grad's finite differences (the
+// six axis taps at 1 voxel, as k_sdf_fd_gradient) and dist = stepsize * voxel_size = sc.stepdist.  The alpha kernels of
+// voxurf_stream.cu read it (k_neus_alpha<true>); the backward scatters dL/diter_cos through the same six taps into
+// the dense SDF gradient volume (taps are linear in the grid; coordinates carry no gradient, as in the reference where
+// ray_pts is a constant).  view: [n_rays,3], row = the sample's ray.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_neus_cos_fwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                   const float *__restrict__ rays_d, const float *__restrict__ view, const float *__restrict__ sdf_grid,
+                   const int32_t *__restrict__ s_ray, const int32_t *__restrict__ s_step, int64_t m1,
+                   float *__restrict__ s_cos) {
+  __shared__ float s_lines[N_LINES * ENC_THREADS];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m1) return;
+  const int r = s_ray[j];
+  const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
+  float px, py, pz;
+  ray_point(s, sc.stepdist, s_step[j], px, py, pz);
+  const SdfFrame fr = make_frame(sc, world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx),
+                                 world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy),
+                                 world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz));
+  load_lines(fr, sdf_grid, s_lines);
+  float g[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // a = 0: z, 1: y, 2: x
+    const TapRef lo = tap_ref(fr, a, -1.f), hi = tap_ref(fr, a, 1.f);
+    const float fl = __fmaf_rn(s_lines[(lo.slot + 1) * ENC_THREADS + threadIdx.x], lo.wh,
+                               __fmul_rn(s_lines[lo.slot * ENC_THREADS + threadIdx.x], lo.wl));
+    const float fh = __fmaf_rn(s_lines[(hi.slot + 1) * ENC_THREADS + threadIdx.x], hi.wh,
+                               __fmul_rn(s_lines[hi.slot * ENC_THREADS + threadIdx.x], hi.wl));
+    const float diff = __fadd_rn(__fsub_rn(hi.coord, lo.coord), sc.fd_eps);
+    g[a] = __fdiv_rn(__fdiv_rn(__fsub_rn(fh, fl), diff), sc.voxel_size);
+  }
+  // (viewdirs[ray_id] * gradients).sum(-1) * dist * 0.5 with the gradient in (x, y, z) order
+  const float dot = __fadd_rn(__fadd_rn(__fmul_rn(view[3 * r], g[2]), __fmul_rn(view[3 * r + 1], g[1])),
+                              __fmul_rn(view[3 * r + 2], g[0]));
+  s_cos[j] = __fmul_rn(__fmul_rn(dot, sc.stepdist), 0.5f);
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_neus_cos_bwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                   const float *__restrict__ rays_d, const float *__restrict__ view, const int32_t *__restrict__ s_ray,
+                   const int32_t *__restrict__ s_step, const float *__restrict__ d_cos, int64_t m1,
+                   float *__restrict__ grad_sdf) {
+  __shared__ float s_dl[N_LINES * ENC_THREADS];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m1) return;
+  const float dc = d_cos[j];
+  if (dc == 0.f) return;
+  const int r = s_ray[j];
+  const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
+  float px, py, pz;
+  ray_point(s, sc.stepdist, s_step[j], px, py, pz);
+  const SdfFrame fr = make_frame(sc, world_to_index(px, sc.xyz_min[0], sc.xyz_max[0], sc.gx),
+                                 world_to_index(py, sc.xyz_min[1], sc.xyz_max[1], sc.gy),
+                                 world_to_index(pz, sc.xyz_min[2], sc.xyz_max[2], sc.gz));
+#pragma unroll
+  for (int l = 0; l < N_LINES; ++l) s_dl[l * ENC_THREADS + threadIdx.x] = 0.f;
+  const float d_dot = dc * 0.5f * sc.stepdist;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // a = 0: z, 1: y, 2: x  <->  view component 2 - a
+    const TapRef lo = tap_ref(fr, a, -1.f), hi = tap_ref(fr, a, 1.f);
+    const float diff = __fadd_rn(__fsub_rn(hi.coord, lo.coord), sc.fd_eps);
+    const float t = d_dot * view[3 * r + (2 - a)] / diff / sc.voxel_size;     // dL/d(fh - fl)
+    s_dl[hi.slot * ENC_THREADS + threadIdx.x] += t * hi.wl;
+    s_dl[(hi.slot + 1) * ENC_THREADS + threadIdx.x] += t * hi.wh;
+    s_dl[lo.slot * ENC_THREADS + threadIdx.x] -= t * lo.wl;
+    s_dl[(lo.slot + 1) * ENC_THREADS + threadIdx.x] -= t * lo.wh;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int jl = 0; jl < 6; ++jl) {
+      const float v = s_dl[(a * 6 + jl) * ENC_THREADS + threadIdx.x];
+      if (v == 0.f) continue;
+      for_line_corners(fr, a, fr.fb[a] - 2 + jl, [&](int64_t off, float w) { red_add(grad_sdf + off, v * w); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // tone-map encode (voxurff.py:243-256, 783-788)
 // ---------------------------------------------------------------------------------------------
 template <typename OutT>
@@ -1198,6 +1279,34 @@ extern "C" int esr_sdf_fd_gradient(const esr_scene_t *sc, const float *rays_o, c
   ESR_STAGE("k_sdf_fd_gradient", stream);
   k_sdf_fd_gradient<<<cdiv(m3, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, sdf_grid, h_ray,
                                                                                      h_step, m3, grad_out);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_neus_cos_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                               const float *sdf_grid, const int32_t *s_ray, const int32_t *s_step, int64_t m1,
+                               float *s_cos, esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(m1 >= 0);
+  if (m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && viewdirs && sdf_grid && s_ray && s_step && s_cos);
+  ESR_STAGE("k_neus_cos_fwd", stream);
+  k_neus_cos_fwd<<<cdiv(m1, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, viewdirs, sdf_grid,
+                                                                                  s_ray, s_step, m1, s_cos);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_neus_cos_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                               const int32_t *s_ray, const int32_t *s_step, const float *d_cos, int64_t m1,
+                               float *grad_sdf_grid, esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(m1 >= 0);
+  if (m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && viewdirs && s_ray && s_step && d_cos && grad_sdf_grid);
+  ESR_STAGE("k_neus_cos_bwd", stream);
+  k_neus_cos_bwd<<<cdiv(m1, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, viewdirs, s_ray,
+                                                                                  s_step, d_cos, m1, grad_sdf_grid);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

@@ -271,9 +271,13 @@ extern "C" int esr_march_fill_bits(const esr_scene_t *sc, const float *rays_o, c
 //                    addresses, so each 128-byte line it touches serves its next 32 samples out of L1.
 //   k_shade_compact  warp per ray slot: weights, weight filter, ballot/popc compaction into the M3 stream (coalesced)
 // ---------------------------------------------------------------------------------------------
+// GRAD: `neus_alpha: grad` (functions.py:45-69) — the section-point SDFs come from s_cos[M1] (k_neus_cos_fwd) instead of
+// the neighbouring samples; the <false> instantiation is the 'interp' kernel unchanged.
+template <bool GRAD>
 __global__ void __launch_bounds__(256)
     k_neus_alpha(const __grid_constant__ esr_scene_t sc, int64_t n_rays, const int32_t *__restrict__ off_mask,
-                 const float *__restrict__ s_sdf, float *__restrict__ s_alpha, float *__restrict__ s_T) {
+                 const float *__restrict__ s_sdf, const float *__restrict__ s_cos, float *__restrict__ s_alpha,
+                 float *__restrict__ s_T) {
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const unsigned lane = lane_id();
@@ -281,11 +285,15 @@ __global__ void __launch_bounds__(256)
     const int s = off_mask[slot], e = off_mask[slot + 1];
     for (int i = s + (int)lane; i < e; i += 32) {
       const float sd = __ldg(s_sdf + i);
-      const bool has_prev = i > s, has_next = i + 1 < e;
-      const float sp = has_prev ? __ldg(s_sdf + i - 1) : 0.f;
-      const float sn = has_next ? __ldg(s_sdf + i + 1) : 0.f;
       float pc, nc;
-      s_alpha[i] = neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+      if constexpr (GRAD) {
+        s_alpha[i] = neus_alpha_grad(sd, __ldg(s_cos + i), sc.s_val, pc, nc);
+      } else {
+        const bool has_prev = i > s, has_next = i + 1 < e;
+        const float sp = has_prev ? __ldg(s_sdf + i - 1) : 0.f;
+        const float sn = has_next ? __ldg(s_sdf + i + 1) : 0.f;
+        s_alpha[i] = neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+      }
       s_T[i] = -1.f;   // "not part of the scan" until k_transmittance visits the sample
     }
   }
@@ -351,22 +359,38 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-extern "C" int esr_alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
-                                    const int32_t *off_mask, const float *s_sdf, int32_t *cnt_shade,
-                                    float *alphainv_last, float *s_alpha, float *s_T, esr_stream_t stream) {
+static int alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays, const int32_t *off_mask,
+                            const float *s_sdf, const float *s_cos, int32_t *cnt_shade, float *alphainv_last,
+                            float *s_alpha, float *s_T, esr_stream_t stream) {
   if (int e = check_scene(sc)) return e;
   ESR_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 31));
   if (n_rays == 0) return ESR_OK;
   // s_sdf / s_alpha / s_T may be NULL only when the M1 stream is empty
   ESR_CHECK_ARG(off_mask && cnt_shade && alphainv_last);
   ESR_STAGE("k_neus_alpha", (cudaStream_t)stream);
-  k_neus_alpha<<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, n_rays, off_mask, s_sdf, s_alpha, s_T);
+  if (s_cos)
+    k_neus_alpha<true><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, n_rays, off_mask, s_sdf, s_cos, s_alpha, s_T);
+  else
+    k_neus_alpha<false><<<ray_blocks(n_rays), 256, 0, (cudaStream_t)stream>>>(*sc, n_rays, off_mask, s_sdf, nullptr, s_alpha, s_T);
   ESR_LAUNCH_OK();
   ESR_STAGE("k_transmittance", (cudaStream_t)stream);
   k_transmittance<<<cdiv(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(*sc, ray_order, n_rays, off_mask, s_alpha, s_T,
                                                                       cnt_shade, alphainv_last);
   ESR_LAUNCH_OK();
   return ESR_OK;
+}
+
+extern "C" int esr_alpha_scan_count(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
+                                    const int32_t *off_mask, const float *s_sdf, int32_t *cnt_shade,
+                                    float *alphainv_last, float *s_alpha, float *s_T, esr_stream_t stream) {
+  return alpha_scan_count(sc, ray_order, n_rays, off_mask, s_sdf, nullptr, cnt_shade, alphainv_last, s_alpha, s_T, stream);
+}
+
+extern "C" int esr_alpha_scan_count_g(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
+                                      const int32_t *off_mask, const float *s_sdf, const float *s_cos, int32_t *cnt_shade,
+                                      float *alphainv_last, float *s_alpha, float *s_T, esr_stream_t stream) {
+  ESR_CHECK_ARG(s_cos || !s_sdf);   // NULL only with an empty M1 stream
+  return alpha_scan_count(sc, ray_order, n_rays, off_mask, s_sdf, s_cos, cnt_shade, alphainv_last, s_alpha, s_T, stream);
 }
 
 extern "C" int esr_alpha_scan_fill(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays,
@@ -391,10 +415,13 @@ extern "C" int esr_alpha_scan_fill(const esr_scene_t *sc, const int32_t *ray_ord
 // then d(alpha)/d(prev_est, next_est); (2) per M1 sample: fold neighbour terms and scatter into the
 // dense SDF gradient volume with the forward trilinear weights.
 // ---------------------------------------------------------------------------------------------
+// GRAD ('grad' alpha): dprev receives dL/dsdf of the sample itself (= dL/dprev_est + dL/dnext_est) and dnext
+// dL/diter_cos (= dL/dnext_est - dL/dprev_est); the <false> instantiation is the 'interp' kernel unchanged.
+template <bool GRAD>
 __global__ void __launch_bounds__(256)
     k_alpha_scan_bwd(const __grid_constant__ esr_scene_t sc, const int32_t *__restrict__ ray_order, int64_t n_rays,
                      const int32_t *__restrict__ off_mask, const float *__restrict__ s_sdf,
-                     const float *__restrict__ s_alpha, const float *__restrict__ s_T,
+                     const float *__restrict__ s_cos, const float *__restrict__ s_alpha, const float *__restrict__ s_T,
                      const float *__restrict__ alphainv_last, const float *__restrict__ g_w_m1,
                      const float *__restrict__ g_last, const float *__restrict__ g_alpha,
                      float *__restrict__ dprev, float *__restrict__ dnext) {
@@ -431,11 +458,15 @@ __global__ void __launch_bounds__(256)
                                  : (float)((double)(gw * Ti) - (double)back_cum / ((double)(1.f - a) + 1e-10));
         if (ga != 0.f) {
           const float sd = s_sdf[i];
-          const bool has_prev = i > s, has_next = i + 1 < e;
-          const float sp = has_prev ? s_sdf[i - 1] : 0.f;
-          const float sn = has_next ? s_sdf[i + 1] : 0.f;
           float pc, nc;
-          neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+          if constexpr (GRAD) {
+            neus_alpha_grad(sd, s_cos[i], sc.s_val, pc, nc);
+          } else {
+            const bool has_prev = i > s, has_next = i + 1 < e;
+            const float sp = has_prev ? s_sdf[i - 1] : 0.f;
+            const float sn = has_next ? s_sdf[i + 1] : 0.f;
+            neus_alpha(sd, sp, sn, has_prev, has_next, sc.s_val, pc, nc);
+          }
           const float q = pc - nc;
           const float num = fmaxf(q, 0.f) + 1e-5f, den = pc + 1e-5f;
           const float rr = num / den;
@@ -449,12 +480,13 @@ __global__ void __launch_bounds__(256)
           }
         }
       }
-      dprev[i] = dp;
-      dnext[i] = dn;
+      dprev[i] = GRAD ? dp + dn : dp;
+      dnext[i] = GRAD ? dn - dp : dn;
     }
   }
 }
 
+template <bool GRAD>   // GRAD: dprev is dL/dsdf of the sample itself (no neighbour terms), dnext is not read
 __global__ void __launch_bounds__(256)
     k_sdf_scatter(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
                   const float *__restrict__ rays_d, const int32_t *__restrict__ s_ray,
@@ -463,11 +495,16 @@ __global__ void __launch_bounds__(256)
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m1) return;
   const int r = s_ray[i];
-  const bool has_prev = i > 0 && s_ray[i - 1] == r;
-  const bool has_next = i + 1 < m1 && s_ray[i + 1] == r;
-  float g = (has_prev ? 0.5f : 1.f) * dprev[i] + (has_next ? 0.5f : 1.f) * dnext[i];
-  if (has_prev) g += 0.5f * dnext[i - 1];
-  if (has_next) g += 0.5f * dprev[i + 1];
+  float g;
+  if constexpr (GRAD) {
+    g = dprev[i];
+  } else {
+    const bool has_prev = i > 0 && s_ray[i - 1] == r;
+    const bool has_next = i + 1 < m1 && s_ray[i + 1] == r;
+    g = (has_prev ? 0.5f : 1.f) * dprev[i] + (has_next ? 0.5f : 1.f) * dnext[i];
+    if (has_prev) g += 0.5f * dnext[i - 1];
+    if (has_next) g += 0.5f * dprev[i + 1];
+  }
   if (g == 0.f) return;
   const RaySetup s = ray_setup(rays_o, rays_d, r, sc.xyz_min, sc.xyz_max, sc.near, sc.far, sc.stepdist);
   float px, py, pz;
@@ -491,12 +528,37 @@ extern "C" int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, co
                 g_w_m1 && tmp_dprev && tmp_dnext && grad_sdf_grid);
   cudaStream_t st = (cudaStream_t)stream;
   ESR_STAGE("k_alpha_scan_bwd", st);
-  k_alpha_scan_bwd<<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, s_alpha, s_T,
-                                                       alphainv_last, g_w_m1, g_last, nullptr, tmp_dprev, tmp_dnext);
+  k_alpha_scan_bwd<false><<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, nullptr, s_alpha, s_T,
+                                                              alphainv_last, g_w_m1, g_last, nullptr, tmp_dprev, tmp_dnext);
   ESR_LAUNCH_OK();
   ESR_STAGE("k_sdf_scatter", st);
-  k_sdf_scatter<<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,
-                                               grad_sdf_grid);
+  k_sdf_scatter<false><<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,
+                                                      grad_sdf_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+// 'grad' alpha: the same backward through alpha = f(sdf - iter_cos, sdf + iter_cos).  dL/dsdf of every sample is
+// scattered into the SDF gradient volume here; dL/diter_cos is left in tmp_dcos[M1] for esr_neus_cos_bwd.
+extern "C" int esr_alpha_scan_bwd_g(const esr_scene_t *sc, const float *rays_o, const float *rays_d,
+                                    const int32_t *ray_order, int64_t n_rays, const int32_t *off_mask,
+                                    const int32_t *s_ray, const int32_t *s_step, const float *s_sdf, const float *s_cos,
+                                    const float *s_alpha, const float *s_T, const float *alphainv_last,
+                                    const float *g_w_m1, const float *g_last, float *tmp_dsdf, float *tmp_dcos,
+                                    int64_t m1, float *grad_sdf_grid, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && m1 >= 0 && m1 < (1ll << 31));
+  if (n_rays == 0 || m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && off_mask && s_ray && s_step && s_sdf && s_cos && s_alpha && s_T && alphainv_last &&
+                g_w_m1 && tmp_dsdf && tmp_dcos && grad_sdf_grid);
+  cudaStream_t st = (cudaStream_t)stream;
+  ESR_STAGE("k_alpha_scan_bwd", st);
+  k_alpha_scan_bwd<true><<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, s_cos, s_alpha, s_T,
+                                                             alphainv_last, g_w_m1, g_last, nullptr, tmp_dsdf, tmp_dcos);
+  ESR_LAUNCH_OK();
+  ESR_STAGE("k_sdf_scatter", st);
+  k_sdf_scatter<true><<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dsdf, tmp_dcos, m1,
+                                                     grad_sdf_grid);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
@@ -514,12 +576,13 @@ extern "C" int esr_neus_alpha_bwd(const esr_scene_t *sc, const float *rays_o, co
                 grad_sdf_grid);
   cudaStream_t st = (cudaStream_t)stream;
   ESR_STAGE("k_neus_alpha_bwd", st);
-  k_alpha_scan_bwd<<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, nullptr, nullptr, nullptr,
-                                                       nullptr, nullptr, g_alpha_m1, tmp_dprev, tmp_dnext);
+  k_alpha_scan_bwd<false><<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, nullptr, nullptr,
+                                                              nullptr, nullptr, nullptr, nullptr, g_alpha_m1, tmp_dprev,
+                                                              tmp_dnext);
   ESR_LAUNCH_OK();
   ESR_STAGE("k_sdf_scatter", st);
-  k_sdf_scatter<<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,
-                                               grad_sdf_grid);
+  k_sdf_scatter<false><<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dprev, tmp_dnext, m1,
+                                                      grad_sdf_grid);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

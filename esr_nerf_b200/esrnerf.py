@@ -156,6 +156,8 @@ class ESRNeRF(VoxurfF):
         sc2 = self._pbr_scene(self.lts_near, False)
         st2 = fused.march(sc2, rays_o2, d_flat, None, self.mask_cache.density, self.sdf.grid.detach())
         sdf_g = self.sdf.grid if torch.is_grad_enabled() else self.sdf.grid.detach()
+        if self.neus_alpha == "grad":      # esrnerf.py:346-361: the secondary rays' directions are their view directions
+            st2.viewdirs = d_flat
         hw2, last2 = fused.AlphaScan.apply(sdf_g, sc2, rays_o2, d_flat, st2, None)
         pos2 = fused.SamplePos(st2.m3, d_flat, st2.h_sdf, rays_o2, d_flat, st2.h_ray, st2.h_step)
         lo, le, _, _ = self._shade(sc2, pos2, use, flats)
@@ -216,6 +218,8 @@ class ESRNeRF(VoxurfF):
             s, n_uncert = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, self.sdf.grid.detach(),
                                       also_read=um.sum(dtype=torch.int32))
             um_order = torch.argsort((~um).to(torch.uint8), stable=True)     # uncertain rays first, original order kept
+            if self.neus_alpha == "grad":
+                s.viewdirs = viewdirs
             h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, s, None)
             m3 = s.m3
             pts = fused.sample_points(sc, rays_o, rays_d, s.h_ray, s.h_step)
@@ -272,7 +276,7 @@ class ESRNeRF(VoxurfF):
         dev = rays_o.device
         n2 = self.num_2ndrays
         with torch.cuda.device(dev):
-            sc, s, _, _, _ = self._eval_stream(rays_o, rays_d, False)
+            sc, s, _, _, _ = self._eval_stream(rays_o, rays_d, False, viewdirs)
             idx = self._choice(s.m3, min(self.num_ltspts, s.m3), dev)
             P = idx.shape[0]
             if P == 0:
@@ -320,7 +324,7 @@ class ESRNeRF(VoxurfF):
     # ------------------------------------------------------------------------------------------
     # inference entry points
     # ------------------------------------------------------------------------------------------
-    def _eval_stream(self, rays_o, rays_d, manual: bool):
+    def _eval_stream(self, rays_o, rays_d, manual: bool, viewdirs=None):
         """shared head of forward_evaluate / eval_emit / eval_esp: packed shaded stream without autograd state.
         Returns (scene, streams, h_w, last, degenerate) — `degenerate` flags the reference's `.squeeze()` quirk
         (SURVEY.md Q7): exactly one sample passing the alpha filter makes 0-dim tensors there and zero images."""
@@ -328,6 +332,8 @@ class ESRNeRF(VoxurfF):
         for g in (self.sdf, self.off_color, self.emo_color, self.brdf):
             g.ensure_layout()
         s = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, self.sdf.grid.detach())
+        if self.neus_alpha == "grad":
+            s.viewdirs = viewdirs
         h_w, last = fused.AlphaScan.apply(self.sdf.grid.detach(), sc, rays_o, rays_d, s, None)
         degenerate = s.m3 <= 1 and s.m1 > 0 and int((s.s_alpha > self.fastcolor_thres).sum()) == 1
         return sc, s, h_w, last, degenerate
@@ -340,9 +346,9 @@ class ESRNeRF(VoxurfF):
     @torch.no_grad()
     def eval_esp(self, **kwargs) -> torch.Tensor:
         """esrnerf.py:1360-1407: expected surface point sum_ray w * ray_pts -> [N,3]"""
-        rays_o, rays_d, _ = self._rays(kwargs)
+        rays_o, rays_d, viewdirs = self._rays(kwargs)
         with torch.cuda.device(rays_o.device):
-            sc, s, h_w, _, degenerate = self._eval_stream(rays_o, rays_d, False)
+            sc, s, h_w, _, degenerate = self._eval_stream(rays_o, rays_d, False, viewdirs)
             if degenerate:
                 return torch.zeros_like(rays_o)
             pts = fused.sample_points(sc, rays_o, rays_d, s.h_ray, s.h_step)
@@ -353,7 +359,7 @@ class ESRNeRF(VoxurfF):
         """esrnerf.py:1299-1358: composite of the emission net -> [N,3]"""
         rays_o, rays_d, viewdirs = self._rays(kwargs)
         with torch.cuda.device(rays_o.device):
-            sc, s, h_w, _, degenerate = self._eval_stream(rays_o, rays_d, False)
+            sc, s, h_w, _, degenerate = self._eval_stream(rays_o, rays_d, False, viewdirs)
             if degenerate:
                 return torch.zeros_like(rays_o)
             pos = fused.SamplePos(s.m3, viewdirs, s.h_sdf, rays_o, rays_d, s.h_ray, s.h_step)
@@ -394,7 +400,7 @@ class ESRNeRF(VoxurfF):
         pos_rt = kwargs["pos_rt"].to(dev).float()
         assert getattr(self, "emit_color", self.emo_color) is self.emo_color      # eval aliases it (esrnerf.py:236-238)
         with torch.cuda.device(dev):
-            sc, s, h_w, last, degenerate = self._eval_stream(rays_o, rays_d, True)
+            sc, s, h_w, last, degenerate = self._eval_stream(rays_o, rays_d, True, viewdirs)
             if degenerate:
                 z3 = torch.zeros_like(rays_o)
                 depth = z3[..., 0]

@@ -154,6 +154,10 @@ class Streams:
     h_m1: Optional[torch.Tensor] = None
     h_sdf: Optional[torch.Tensor] = None
     aux: object = None          # result of march(between=...)
+    # `neus_alpha: grad` (functions.py:45-69): set `viewdirs` ([N,3] f32, row = ray) before AlphaScan to select it;
+    # AlphaScan then fills s_cos[M1] = (viewdir . grad sdf) * dist * 0.5 and computes the alphas from (s_sdf, s_cos)
+    viewdirs: Optional[torch.Tensor] = None
+    s_cos: Optional[torch.Tensor] = None
 
 
 def march_count(sc: Scene, rays_o, rays_d, mask_density):
@@ -227,6 +231,15 @@ def march(sc: Scene, rays_o, rays_d, ray_order, mask_density, sdf_grid, also_rea
     return streams if also_read is None else (streams, extra)
 
 
+def neus_cos(sc: Scene, rays_o, rays_d, viewdirs, sdf_grid, s: Streams) -> torch.Tensor:
+    """iter_cos[M1] of `neus_alpha: grad` (functions.py:52-54): (viewdirs[ray_id] * sample_sdf_grad's gradient).sum(-1)
+    * dist * 0.5 on the M1 stream"""
+    out = _f32(s.m1, dev=rays_o.device)
+    check(_lib.lib().esr_neus_cos_fwd(ctypes.byref(sc), ptr(rays_o), ptr(rays_d), ptr(viewdirs), ptr(sdf_grid), ptr(s.s_ray),
+                                      ptr(s.s_step), s.m1, ptr(out), stream_ptr()))
+    return out
+
+
 class AlphaScan(torch.autograd.Function):
     """(h_w [M3], alphainv_last [N]) = f(sdf_grid); fills the M3 stream fields of `streams`."""
 
@@ -238,8 +251,15 @@ class AlphaScan(torch.autograd.Function):
         cnt_shade = _i32(n, dev)
         last = _f32(n, dev=dev)
         streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
-        check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
-                                     ptr(cnt_shade), ptr(last), ptr(streams.s_alpha), ptr(streams.s_T), st))
+        if streams.viewdirs is not None:      # neus_alpha == "grad"
+            streams.viewdirs = streams.viewdirs.contiguous()
+            streams.s_cos = neus_cos(sc, rays_o, rays_d, streams.viewdirs, sdf_grid, streams)
+            check(L.esr_alpha_scan_count_g(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
+                                           ptr(streams.s_cos), ptr(cnt_shade), ptr(last), ptr(streams.s_alpha),
+                                           ptr(streams.s_T), st))
+        else:
+            check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
+                                         ptr(cnt_shade), ptr(last), ptr(streams.s_alpha), ptr(streams.s_T), st))
         off_shade = exclusive_scan(cnt_shade) if n else torch.zeros(1, dtype=torch.int32, device=dev)
         if n_on is None:
             m3 = int(off_shade[n].item())
@@ -273,6 +293,15 @@ class AlphaScan(torch.autograd.Function):
             g_w_m1.index_copy_(0, s.h_m1.long(), g_hw.contiguous())
         tmp_p, tmp_n = _f32(s.m1, dev=dev), _f32(s.m1, dev=dev)
         g_last = g_last.contiguous()
+        if s.s_cos is not None:               # neus_alpha == "grad": tmp_p = dL/dsdf (scattered), tmp_n = dL/diter_cos
+            L = _lib.lib()
+            check(L.esr_alpha_scan_bwd_g(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.ray_order), s.n_rays,
+                                         ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(s.s_cos),
+                                         ptr(s.s_alpha), ptr(s.s_T), ptr(last), ptr(g_w_m1), ptr(g_last), ptr(tmp_p),
+                                         ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
+            check(L.esr_neus_cos_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.viewdirs), ptr(s.s_ray),
+                                     ptr(s.s_step), ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
+            return ret_sdf, None, None, None, None, None
         check(_lib.lib().esr_alpha_scan_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.ray_order), s.n_rays,
                                             ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(s.s_alpha),
                                             ptr(s.s_T), ptr(last), ptr(g_w_m1), ptr(g_last), ptr(tmp_p),

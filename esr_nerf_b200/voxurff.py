@@ -100,11 +100,11 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
         ok = (self.color_dim == 6 and 1 <= self.rgbnet_width <= 192 and 2 <= self.rgbnet_depth <= 4 and
               1 <= self.tonemap_width <= 192 and self.tonemap_depth == 2 and self.posbase_pe == 5 and
               self.viewbase_pe == 1 and self.colorbase_pe == 5 and self.grad_feat == [0.5, 1.0, 1.5, 2.0] and
-              self.neus_alpha == "interp")
+              self.neus_alpha in ("interp", "grad"))
         if not ok:
             raise NotImplementedError(
                 "libesr_b200 instantiates the shipped fine-stage feature row (cfg/app/fine.yaml:13-30): color_dim 6, PE 5/1/5, "
-                "grad_feat [.5,1,1.5,2], neus_alpha interp; rgbnet width <= 192, depth 2..4; tonemap width <= 192, depth 2")
+                "grad_feat [.5,1,1.5,2], neus_alpha interp | grad; rgbnet width <= 192, depth 2..4; tonemap width <= 192, depth 2")
 
     def train(self, mode=True):
         self.forward = self.forward_training if mode else self.forward_evaluate
@@ -194,6 +194,8 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
             streams, n_on = self._streams(sc, rays_o, rays_d, em_modes, between=prep)
             if prep is not None:
                 flat_off, flat_emo, flat_tone = streams.aux
+            if self.neus_alpha == "grad":      # voxurff.py:151-154: section-point SDFs from the view-projected SDF gradient
+                streams.viewdirs = viewdirs
             h_w, last = fused.AlphaScan.apply(self.sdf.grid, sc, rays_o, rays_d, streams, n_on)
             s = streams
             if self._tensor_core_mlps():
@@ -239,6 +241,8 @@ class VoxurfF(GridRegularizers, RayUtilities, nn.Module):
         with torch.cuda.device(dev):
             sc = self._scene(float(self.s_val))
             streams, _ = self._streams(sc, rays_o, rays_d, None)
+            if self.neus_alpha == "grad":
+                streams.viewdirs = viewdirs
             h_w, last = fused.AlphaScan.apply(self.sdf.grid.detach(), sc, rays_o, rays_d, streams, None)
             s = streams
             if s.m3 <= 1 and s.m1 and int((s.s_alpha > self.fastcolor_thres).sum()) == 1:

@@ -226,6 +226,31 @@ int esr_alpha_scan_bwd(const esr_scene_t *sc, const float *rays_o, const float *
                        const float *g_w_m1, const float *g_last, float *tmp_dprev, float *tmp_dnext,
                        int64_t m1, float *grad_sdf_grid, esr_stream_t stream);
 /*
+ * `neus_alpha: grad` (functions.py:45-69, selected by voxurff.py:151-154 / esrnerf.py:197-200; every shipped config uses
+ * 'interp'): the section-point SDFs of a sample are sdf -+ iter_cos, iter_cos = (viewdir . grad sdf) * dist * 0.5, with
+ * grad sdf = sample_sdf_grad's finite differences (voxurff.py:670-676) and dist = stepsize * voxel_size = sc->stepdist.
+ *   esr_neus_cos_fwd      : s_cos[M1] for the M1 stream (viewdirs: f32 [n_rays,3], row = the sample's ray)
+ *   esr_alpha_scan_count_g: esr_alpha_scan_count with the alphas computed from (s_sdf, s_cos); esr_alpha_scan_fill follows
+ *                           unchanged
+ *   esr_alpha_scan_bwd_g  : esr_alpha_scan_bwd for those alphas — scatters dL/dsdf of every sample into grad_sdf_grid and
+ *                           leaves dL/diter_cos in tmp_dcos[M1]
+ *   esr_neus_cos_bwd      : scatter-adds d_cos[M1] through the six finite-difference taps into grad_sdf_grid
+ */
+int esr_neus_cos_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                     const float *sdf_grid, const int32_t *s_ray, const int32_t *s_step, int64_t m1, float *s_cos,
+                     esr_stream_t stream);
+int esr_neus_cos_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                     const int32_t *s_ray, const int32_t *s_step, const float *d_cos, int64_t m1, float *grad_sdf_grid,
+                     esr_stream_t stream);
+int esr_alpha_scan_count_g(const esr_scene_t *sc, const int32_t *ray_order, int64_t n_rays, const int32_t *off_mask,
+                           const float *s_sdf, const float *s_cos, int32_t *cnt_shade, float *alphainv_last,
+                           float *s_alpha, float *s_T, esr_stream_t stream);
+int esr_alpha_scan_bwd_g(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                         int64_t n_rays, const int32_t *off_mask, const int32_t *s_ray, const int32_t *s_step,
+                         const float *s_sdf, const float *s_cos, const float *s_alpha, const float *s_T,
+                         const float *alphainv_last, const float *g_w_m1, const float *g_last, float *tmp_dsdf,
+                         float *tmp_dcos, int64_t m1, float *grad_sdf_grid, esr_stream_t stream);
+/*
  * Same backward with dL/dalpha given directly on the M1 stream (g_alpha_m1) instead of going through the
  * Alphas2Weights recurrence: the coarse stage recomputes the weights on the shaded samples with the reference-shaped
  * esr_alpha2weight_* ops (voxurfc.py:211-219), so only the NeuS alpha -> sdf part is needed here.

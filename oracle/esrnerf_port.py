@@ -201,6 +201,12 @@ def _sample(grid, scene, pts):
     return P.grid_sample_world(grid, pts, scene["xyz_min"], scene["xyz_max"])
 
 
+def _alpha(scene, params, viewdirs, ray_id, ray_pts, sdf, s_val):
+    """self.neus_alpha_from_sdf_scatter (esrnerf.py:197-200): 'interp' or 'grad' — the latter from sample_sdf_grad's
+    finite differences (esrnerf.py:1519-1525, denominator + 1e-12) along the ray's view direction"""
+    return P.neus_alpha(scene, params["sdf"], viewdirs, ray_id, ray_pts, sdf, s_val, fd_eps=1e-12)
+
+
 def _brdf_split(y):
     return y[:, 0:3], y[:, 3:4], y[:, 4:5]
 
@@ -212,7 +218,7 @@ def _secondary(scene, params, rays_o, dirs, s_val):
     keep = P.mask_cache(scene, ray_pts)
     ray_pts, ray_id, step_id = ray_pts[keep], ray_id[keep], step_id[keep]
     sdf = _sample(params["sdf"], scene, ray_pts)[:, 0]
-    alpha = P.neus_alpha_interp(ray_id, sdf, s_val)
+    alpha = _alpha(scene, params, dirs, ray_id, ray_pts, sdf, s_val)      # esrnerf.py:346-361: viewdirs = dirs
     k0 = alpha > scene["fast_thres"]
     alpha, ray_id, step_id, ray_pts, sdf = alpha[k0], ray_id[k0], step_id[k0], ray_pts[k0], sdf[k0]
     weights, last = P._A2W.apply(alpha, ray_id, N)
@@ -278,7 +284,7 @@ def esrnerf_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     ray_pts, ray_id, step_id = ray_pts[keep], ray_id[keep], step_id[keep]
     inter.update(m1_ray=ray_id, m1_step=step_id)
     sdf, exp_grad = sdf_expgrad(params["sdf"], ray_pts, scene["xyz_min"], scene["xyz_max"], True)
-    alpha = P.neus_alpha_interp(ray_id, sdf, s_val)
+    alpha = _alpha(scene, params, viewdirs, ray_id, ray_pts, sdf, s_val)
     inter.update(m1_sdf=sdf, m1_alpha=alpha)
     k0 = alpha > scene["fast_thres"]
     alpha, ray_id, step_id, ray_pts, exp_grad, sdf = (t[k0] for t in (alpha, ray_id, step_id, ray_pts, exp_grad, sdf))
@@ -337,7 +343,7 @@ def esrnerf_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     return out, inter
 
 
-def _primary_eval_stream(scene, params, rays_o, rays_d, s_val, manual: bool):
+def _primary_eval_stream(scene, params, rays_o, rays_d, s_val, manual: bool, viewdirs=None):
     """shared head of forward_evaluate / eval_emit / eval_esp (esrnerf.py:1012-1089, 1306-1339, 1367-1400)"""
     N = rays_o.shape[0]
     ray_pts, ray_id, step_id, _ = _march_near(scene, rays_o, rays_d, scene["near"])
@@ -348,7 +354,7 @@ def _primary_eval_stream(scene, params, rays_o, rays_d, s_val, manual: bool):
         sdf, exp_grad = sdf_expgrad(params["sdf"], ray_pts, scene["xyz_min"], scene["xyz_max"], False)
     else:
         sdf = _sample(params["sdf"], scene, ray_pts)[:, 0]
-    alpha = P.neus_alpha_interp(ray_id, sdf, s_val)
+    alpha = _alpha(scene, params, viewdirs, ray_id, ray_pts, sdf, s_val)
     k0 = alpha > scene["fast_thres"]
     weights, T, last, _, _ = P.H.alpha2weight(alpha[k0], ray_id[k0], N)
     k1 = weights > scene["fast_thres"]
@@ -363,14 +369,14 @@ def _primary_eval_stream(scene, params, rays_o, rays_d, s_val, manual: bool):
 @torch.no_grad()
 def esrnerf_eval_esp(scene, params, rays_o, rays_d, viewdirs, s_val):
     """esrnerf.py:1360-1407: expected surface point = sum_ray w * ray_pts"""
-    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False)
+    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False, viewdirs)
     return torch.zeros(st["N"], 3).index_add(0, st["ray"], st["w"][:, None] * st["pts"]), st
 
 
 @torch.no_grad()
 def esrnerf_eval_emit(scene, params, rays_o, rays_d, viewdirs, s_val):
     """esrnerf.py:1299-1358: composite of the emission net (emit_color aliases emo_color outside finetune, Q13)"""
-    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False)
+    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False, viewdirs)
     pts = st["pts"]
     feat, _, fnormal = _taps(scene, params, pts)
     brdf_feat = torch.cat([_pos_emb(scene, pts), st["sdf"][:, None], feat, fnormal], -1)
@@ -402,7 +408,7 @@ def esrnerf_forward_evaluate(scene, params, rays_o, rays_d, viewdirs, em_modes, 
                              chunk_sz: int, draws=None):
     """esrnerf.py:853-1297 (general branch; the degenerate `alpha.dim() != 1` branch is not restated)."""
     draws = draws or Draws()
-    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, True)
+    st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, True, viewdirs)
     N, pts, ray_id, step_id, sdf, weights, last = (st[k] for k in ("N", "pts", "ray", "step", "sdf", "w", "last"))
     _, g, _ = P.sdf_feature_taps(scene, params["sdf"], pts, [1.0], fd_eps=1e-12)      # esrnerf.py:1598-1605
     grad = torch.stack([g[:, 2], g[:, 1], g[:, 0]], -1)
@@ -499,7 +505,7 @@ def esrnerf_forward_finetune(scene, params, rays_o, rays_d, viewdirs, em_modes, 
     draws = draws or Draws()
     n2 = scene["num_2ndrays"]
     with torch.no_grad():
-        st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False)
+        st = _primary_eval_stream(scene, params, rays_o, rays_d, s_val, False, viewdirs)
         m3 = st["pts"].shape[0]
         idx = draws.choice(m3, min(scene["num_ltspts"], m3))
         pts, ray = st["pts"][idx], st["ray"][idx]

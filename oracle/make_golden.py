@@ -33,9 +33,9 @@ CASES = {
 GRAD_PROBES = 4096
 
 
-def build_reference_model(num_voxels, mask_res, sparse, s_val, weights=None):
+def build_reference_model(num_voxels, mask_res, sparse, s_val, weights=None, **model_overrides):
     _, _, VoxurfF, _ = H.reference_classes()
-    cfg = H.fine_cfg()
+    cfg = H.fine_cfg(**model_overrides)
     torch.manual_seed(0)
     m = VoxurfF(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
                 S.mask_density(mask_res, sparse), s_val, num_voxels)

@@ -60,6 +60,35 @@ def neus_alpha_interp(ray_id: torch.Tensor, sdf: torch.Tensor, s_val: float) -> 
     return ((F.relu(pc - nc) + 1e-5) / (pc + 1e-5)).clip(0.0, 1.0)
 
 
+def neus_alpha_grad(viewdirs: torch.Tensor, ray_id: torch.Tensor, dist, sdf: torch.Tensor, grad: torch.Tensor,
+                    s_val: float) -> torch.Tensor:
+    """functions.py:45-69 (`neus_alpha: grad`): section-point SDFs estimated from the SDF gradient along the view
+    direction, sdf -+ 0.5 * dist * (v . grad sdf), instead of from the neighbouring samples."""
+    if sdf.numel() == 0:
+        return sdf
+    iter_cos = (viewdirs[ray_id] * grad).sum(-1, keepdim=True) * torch.as_tensor(dist).reshape(-1, 1) * 0.5
+    s = sdf.unsqueeze(-1)
+    pc = torch.sigmoid((s - iter_cos) * s_val)
+    nc = torch.sigmoid((s + iter_cos) * s_val)
+    return ((F.relu(pc - nc) + 1e-5) / (pc + 1e-5)).clip(0.0, 1.0).squeeze(-1)
+
+
+def sdf_fd_gradient(scene: Dict, sdf_grid: torch.Tensor, xyz: torch.Tensor, fd_eps: float = 0.0) -> torch.Tensor:
+    """sample_sdf_grad's gradient (voxurff.py:670-676): the displace = 1 finite differences, (z,y,x) -> (x,y,z)"""
+    _, g, _ = sdf_feature_taps(scene, sdf_grid, xyz, [1.0], fd_eps)
+    return torch.stack([g[:, 2], g[:, 1], g[:, 0]], -1)
+
+
+def neus_alpha(scene: Dict, sdf_grid: torch.Tensor, viewdirs, ray_id, ray_pts, sdf, s_val: float, fd_eps: float = 0.0):
+    """the model's `neus_alpha_from_sdf_scatter` (voxurff.py:151-154): scene["neus_alpha"] = "interp" (default, every
+    shipped config) or "grad"."""
+    if scene.get("neus_alpha", "interp") == "grad":
+        grad = sdf_fd_gradient(scene, sdf_grid, ray_pts, fd_eps)
+        dist = torch.tensor(scene["stepdist"], dtype=torch.float32)      # stepsize * voxel_size (voxurff.py:195)
+        return neus_alpha_grad(viewdirs, ray_id, dist, sdf, grad, s_val)
+    return neus_alpha_interp(ray_id, sdf, s_val)
+
+
 class _A2W(torch.autograd.Function):
     """module.py:117-143 over the C restatement of kernel.cu:576-707."""
 
@@ -194,7 +223,7 @@ def voxurff_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     inter.update(m1_ray=ray_id, m1_step=step_id)
 
     sdf = grid_sample_world(params["sdf"], ray_pts, scene["xyz_min"], scene["xyz_max"])[:, 0]
-    alpha = neus_alpha_interp(ray_id, sdf, s_val)
+    alpha = neus_alpha(scene, params["sdf"], viewdirs, ray_id, ray_pts, sdf, s_val)
     inter.update(m1_sdf=sdf, m1_alpha=alpha)
 
     k0 = alpha > scene["fast_thres"]
@@ -233,9 +262,8 @@ def voxurff_forward_evaluate(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     keep = mask_cache(scene, ray_pts)
     ray_pts, ray_id, step_id = ray_pts[keep], ray_id[keep], step_id[keep]
     sdf = grid_sample_world(params["sdf"], ray_pts, scene["xyz_min"], scene["xyz_max"])[:, 0]
-    _, g, _ = sdf_feature_taps(scene, params["sdf"], ray_pts, [1.0])  # voxurff.py:670-676
-    grad = torch.stack([g[:, 2], g[:, 1], g[:, 0]], -1)
-    alpha = neus_alpha_interp(ray_id, sdf, s_val)
+    grad = sdf_fd_gradient(scene, params["sdf"], ray_pts)  # voxurff.py:670-676
+    alpha = neus_alpha(scene, params["sdf"], viewdirs, ray_id, ray_pts, sdf, s_val)
     k0 = alpha > scene["fast_thres"]
     alpha, ray_id, step_id, ray_pts, sdf, grad = (t[k0] for t in (alpha, ray_id, step_id, ray_pts, sdf, grad))
     weights, T, last, _, _ = H.alpha2weight(alpha, ray_id, N)

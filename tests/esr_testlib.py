@@ -51,10 +51,10 @@ def oracle_params(scene, weights, requires_grad=True):
     return P.params_from_state_dict(leaves), leaves
 
 
-def build_product_model(fx, weights, device="cuda:0"):
+def build_product_model(fx, weights, device="cuda:0", **cfg_over):
     from esr_nerf_b200.voxurff import VoxurfF
 
-    cfg = S.fine_cfg(device=device)
+    cfg = S.fine_cfg(device=device, **cfg_over)
     m = VoxurfF(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
                 S.mask_density(int(fx["mask_res"]), bool(fx["sparse"])), float(fx["s_val"]), int(fx["num_voxels"]))
     m.load_state_dict({**m.state_dict(), **weights})
@@ -205,7 +205,8 @@ def load_esrnerf_case(name):
 def esrnerf_oracle_scene(fx):
     scene = oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
     scene.update(num_2ndrays=int(fx["num_2ndrays"]), num_ltspts=int(fx["num_ltspts"]), lts_near=1e-5)
-    scene.update({k: str(fx[k]) for k in ("ray_sampling", "env_activation") if k in fx})     # defaults: random / softplus
+    # defaults: random / softplus / interp
+    scene.update({k: str(fx[k]) for k in ("ray_sampling", "env_activation", "neus_alpha") if k in fx})
     return scene
 
 
@@ -245,7 +246,7 @@ def build_product_esrnerf(fx, weights, device="cuda:0"):
     from esr_nerf_b200.esrnerf import ESRNeRF
 
     cfg = S.lts_cfg(device=device, num_2ndrays=int(fx["num_2ndrays"]), num_ltspts=int(fx["num_ltspts"]),
-                    **{k: str(fx[k]) for k in ("ray_sampling", "env_activation") if k in fx})
+                    **{k: str(fx[k]) for k in ("ray_sampling", "env_activation", "neus_alpha") if k in fx})
     m = ESRNeRF(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
                 S.mask_density(int(fx["mask_res"]), bool(fx["sparse"])), float(fx["s_val"]), int(fx["num_voxels"]))
     m.load_state_dict({**m.state_dict(), **weights})

@@ -42,3 +42,44 @@ def test_plain_c_host_links_and_sees_the_bindings_struct_layouts(tmp_path):
     # every field of the one-call step is covered (a new field must be added to the C host check as well)
     assert {f[0] for f in _lib.VoxurffStep._fields_} == set(out["VoxurffStep"])
     assert {f[0] for f in _lib.MlpDesc._fields_} == set(out["MlpDesc"])
+
+
+def test_ctypes_prototypes_agree_with_the_header_signatures():
+    """every entry point: same number of parameters in include/esr_b200.h and in the binding's argtypes, and the same
+    type class position by position (pointer / int64 / int32 / float) — a swapped or missing argument in a ctypes
+    prototype is silent until the kernel reads garbage"""
+    import re
+
+    from esr_nerf_b200 import _lib
+
+    hdr = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+
+    def c_class(decl: str) -> str:
+        if "*" in decl or "[" in decl or "esr_stream_t" in decl:
+            return "ptr"
+        for t, k in (("int64_t", "i64"), ("int32_t", "i32"), ("uint8_t", "u8"), ("float", "f32"), ("double", "f64"), ("int", "i32")):
+            if re.search(rf"\b{t}\b", decl):
+                return k
+        raise AssertionError(decl)
+
+    def py_class(t) -> str:
+        if t in (ctypes.c_int64,):
+            return "i64"
+        if t in (ctypes.c_int, ctypes.c_int32):
+            return "i32"
+        if t is ctypes.c_float:
+            return "f32"
+        if t is ctypes.c_double:
+            return "f64"
+        return "ptr"      # c_void_p, c_char_p, POINTER(...)
+
+    seen = 0
+    for m in re.finditer(r"\b(esr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        decls = [] if args in ("void", "") else [a.strip() for a in args.split(",")]
+        _, argtypes = _lib.PROTOTYPES[name]
+        assert len(decls) == len(argtypes), (name, len(decls), len(argtypes))
+        for i, (d, t) in enumerate(zip(decls, argtypes)):
+            assert c_class(d) == py_class(t), (name, i, d, t)
+        seen += 1
+    assert seen == len(_lib.PROTOTYPES)

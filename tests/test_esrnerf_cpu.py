@@ -69,6 +69,57 @@ def test_esrnerf_port_matches_reference():
             assert C.rel_err(leaves[name].grad, p.grad) < 1e-5, name
 
 
+def test_esrnerf_port_matches_reference_neus_alpha_grad():
+    """`neus_alpha: grad` (functions.py:45-69, esrnerf.py:197-200): the port against the reference's own ESRNeRF built with
+    that option — the LTS / PDRA training step (primary AND secondary rays take the view-projected SDF gradient), eval_emit
+    and eval_esp."""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import esrnerf_port as E
+    from oracle.make_golden import build_reference_esrnerf
+
+    fx, weights = C.load_esrnerf_case("pdra_sparse_s60")
+    n, s_val = 96, 35.0
+    ref = build_reference_esrnerf(int(fx["num_voxels"]), int(fx["mask_res"]), True, s_val, weights, num_2ndrays=8,
+                                  num_ltspts=16, neus_alpha="grad")
+    ref.pdra_mode = True
+    rays = S.make_rays(n, 4243)
+    um = S.uncert_masks(n)
+    np.random.seed(5)
+    torch.manual_seed(11)
+    ref_out = ref(s_val=s_val, rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"],
+                  em_modes=rays["em_modes"], uncert_masks=um, normal_eps=0.01, emit_eps=0.03)
+    scene = C.esrnerf_oracle_scene(dict(fx, num_2ndrays=8, num_ltspts=16))
+    scene["neus_alpha"] = "grad"
+    params, leaves = C.esrnerf_oracle_params(scene, weights)
+    np.random.seed(5)
+    torch.manual_seed(11)
+    out, inter = E.esrnerf_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                            rays["em_modes"], um, s_val, 0.01, 0.03, True, E.Draws())
+    a_interp = E.P.neus_alpha_interp(inter["m1_ray"], inter["m1_sdf"].detach(), s_val)
+    assert (a_interp - inter["m1_alpha"].detach()).abs().max() > 1e-3       # really the other function
+    cot = C.esrnerf_cotangents(out)
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    assert set(out) == set(ref_out)
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    for name, p in ref.named_parameters():
+        if p.grad is not None:
+            assert C.rel_err(leaves[name].grad, p.grad) < 1e-5, name
+    ref.eval()
+    params0, _ = C.esrnerf_oracle_params(scene, weights, requires_grad=False)
+    args = (scene, params0, rays["rays_o"], rays["rays_d"], rays["viewdirs"])
+    with torch.no_grad():
+        r_emit = ref.eval_emit(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"])
+        r_esp = ref.eval_esp(rays_o=rays["rays_o"], rays_d=rays["rays_d"], viewdirs=rays["viewdirs"])
+    assert C.rel_err(E.esrnerf_eval_emit(*args, s_val)[0], r_emit) < 1e-5
+    assert C.rel_err(E.esrnerf_eval_esp(*args, s_val)[0], r_esp) < 1e-5
+
+
 @pytest.mark.parametrize("case", C.ESRNERF_CASES)
 def test_esrnerf_eval_ports_match_golden(case):
     """forward_evaluate (with the PBR decomposition, several LTS chunks), eval_emit, eval_esp: port vs the outputs of

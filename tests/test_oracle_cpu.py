@@ -128,6 +128,54 @@ def test_port_matches_reference(case):
             assert C.rel_err(leaf.grad, ref_grads[name].grad) < 1e-5, name
 
 
+def test_port_matches_reference_neus_alpha_grad():
+    """`neus_alpha: grad` (functions.py:45-69; no shipped config selects it): the port against the reference's own VoxurfF
+    built with that option — training outputs + every gradient (the SDF grid now also receives gradient through the
+    finite-difference SDF gradient of every M1 sample), and the inference maps."""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import voxurf_port as P
+    from oracle.make_golden import build_reference_model
+
+    fx, weights = C.load_case("fine_sparse_s20")
+    s_val, n = float(fx["s_val"]), int(fx["n_rays"])
+    ref = build_reference_model(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]), s_val, weights,
+                                neus_alpha="grad")
+    rays = S.make_rays(n, 778)
+    ref_out = ref(s_val=s_val, **rays)
+    scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    scene["neus_alpha"] = "grad"
+    params, leaves = C.oracle_params(scene, weights)
+    out, inter = P.voxurff_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                            rays["em_modes"], s_val)
+    assert len(inter["m3_ray"]) > 500
+    # the mode is really a different function of the grid: the interp alphas of the same samples differ
+    a_interp = P.neus_alpha_interp(inter["m1_ray"], inter["m1_sdf"].detach(), s_val)
+    assert (a_interp - inter["m1_alpha"].detach()).abs().max() > 1e-3
+    cot = C.cotangents(n)
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    ref_grads = dict(ref.named_parameters())
+    for name, leaf in leaves.items():
+        if name in ref_grads and ref_grads[name].grad is not None:
+            assert C.rel_err(leaf.grad, ref_grads[name].grad) < 1e-5, name
+    ref.eval()
+    pos_rt = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(3)))[0]
+    ev = S.make_rays(64, 5)
+    with torch.no_grad():
+        r = ref(rays_o=ev["rays_o"], rays_d=ev["rays_d"], viewdirs=ev["viewdirs"], em_modes=torch.tensor(1), pos_rt=pos_rt)
+        params0, _ = C.oracle_params(scene, weights, requires_grad=False)
+        o, _ = P.voxurff_forward_evaluate(scene, params0, ev["rays_o"], ev["rays_d"], ev["viewdirs"], torch.tensor(1),
+                                          pos_rt, s_val)
+    for k in o:
+        assert C.rel_err(o[k], r[k]) < 1e-5, k
+
+
 def test_eval_port_matches_reference():
     from oracle import ref_harness as H
 
