@@ -64,17 +64,25 @@ def test_voxurff_grad_alpha_vs_oracle_port(mode):
     assert C.rel_err(m.last_streams["h_w"].cpu()[o3], inter["m3_weights"]) < 1e-4
     for k in OUT_KEYS:
         assert C.rel_err(out[k], ref[k]) < 1e-4, k
-    checked = 0
+    checked, bad = 0, {}
     for name, p in m.named_parameters():
         if name not in leaves or leaves[name].grad is None:
             continue
         if mode == "x2":
             mx, l2 = C.grad_err(p.grad.contiguous(), leaves[name].grad)
-            assert mx < 1e-2 and l2 < 1e-2, (name, mx, l2)
+            if not (mx < 1e-2 and l2 < 1e-2):
+                bad[name] = (mx, l2)
         else:
-            ok, msg = C.grad_close(p.grad.contiguous(), leaves[name].grad, 1e-4)
-            assert ok, (name, msg)
+            # grids at 1e-4; MLP tensors at 1e-3, as in the other fresh-ray fp32 comparisons (tests/test_gpu_voxurff.py::
+            # test_odd_grid_vs_oracle_port_fresh_rays): with ~3 x 10^4 rows per net ONE ReLU mask on which two correct fp32
+            # evaluations disagree (library GEMM here, the CPU port there) moves the entries of the layers below it by a few
+            # 1e-4 of the tensor's maximum (measured 5.4e-4 on off_rgbnet.linear.0.weight, 14 % of its entries)
+            mlp = "net" in name or "tonemapper" in name
+            ok, msg = C.grad_close(p.grad.contiguous(), leaves[name].grad, 1e-3 if mlp else 1e-4)
+            if not ok:
+                bad[name] = msg
         checked += 1
+    assert not bad, bad
     assert checked >= 3 + 8 + 8 + 4
 
 
