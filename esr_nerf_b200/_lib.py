@@ -179,6 +179,9 @@ PROTOTYPES = {
     "esr_alpha_scan_bwd_g": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, P]),
     "esr_neus_cos_fwd": (I32, [SCENE_P, P, P, P, P, P, P, I64, P, P]),
     "esr_neus_cos_bwd": (I32, [SCENE_P, P, P, P, P, P, P, I64, P, P]),
+    "esr_neus_cos_vol_fwd": (I32, [SCENE_P, P, P, P, P, P, P, I64, P, P]),
+    "esr_neus_cos_vol_bwd": (I32, [SCENE_P, P, P, P, P, P, P, I64, P, P]),
+    "esr_neus_alpha_bwd_g": (I32, [SCENE_P, P, P, P, I64, P, P, P, P, P, P, P, P, I64, P, P]),
     "esr_encode_coarse_fwd": (I32, [SCENE_P, P, P, P, P, P, P, P, P, I64, P, P]),
     "esr_encode_coarse_bwd": (I32, [SCENE_P, P, P, P, P, P, I64, P, P, P, P, P]),
     "esr_encode_fwd": (I32, [SCENE_P, P, P, P, P, P, P, I32, P, P, P, I64, P, I32, P]),

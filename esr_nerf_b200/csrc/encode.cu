@@ -894,6 +894,54 @@ __global__ void __launch_bounds__(ENC_THREADS)
 }
 
 // ---------------------------------------------------------------------------------------------
+// `neus_alpha: grad` in the coarse stage (voxurfc.py:171-174, 204-210): the SDF gradient of an M1 sample is the
+// trilinear tap of the dense central-difference volume ([3][X][Y][Z], channels d/dx, d/dy, d/dz) — iter_cos =
+// (viewdir . tap) * dist * 0.5 forward, the tap's cotangent scattered into the volume's gradient backward (the
+// volume is a function of the raw SDF grid: fused.SdfCentralGradient carries it on).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_neus_cos_vol_fwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                       const float *__restrict__ rays_d, const float *__restrict__ view,
+                       const float *__restrict__ grad_vol, const int32_t *__restrict__ s_ray,
+                       const int32_t *__restrict__ s_step, int64_t m1, float *__restrict__ s_cos) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m1) return;
+  const int r = s_ray[j];
+  float px, py, pz;
+  Cell c;
+  coarse_sample(sc, rays_o, rays_d, r, s_step[j], px, py, pz, c);
+  const int64_t vol = (int64_t)sc.gx * sc.gy * sc.gz;
+  float g[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) g[a] = tap1(grad_vol + a * vol, sc.gx, sc.gy, sc.gz, c);
+  const float dot = __fadd_rn(__fadd_rn(__fmul_rn(view[3 * r], g[0]), __fmul_rn(view[3 * r + 1], g[1])),
+                              __fmul_rn(view[3 * r + 2], g[2]));
+  s_cos[j] = __fmul_rn(__fmul_rn(dot, sc.stepdist), 0.5f);
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+    k_neus_cos_vol_bwd(const __grid_constant__ esr_scene_t sc, const float *__restrict__ rays_o,
+                       const float *__restrict__ rays_d, const float *__restrict__ view,
+                       const int32_t *__restrict__ s_ray, const int32_t *__restrict__ s_step,
+                       const float *__restrict__ d_cos, int64_t m1, float *__restrict__ g_vol) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m1) return;
+  const float dc = d_cos[j];
+  if (dc == 0.f) return;
+  const int r = s_ray[j];
+  float px, py, pz;
+  Cell c;
+  coarse_sample(sc, rays_o, rays_d, r, s_step[j], px, py, pz, c);
+  const int64_t vol = (int64_t)sc.gx * sc.gy * sc.gz;
+  const float d_dot = dc * 0.5f * sc.stepdist;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float dg = d_dot * view[3 * r + a];
+    if (dg != 0.f) scatter1(g_vol + a * vol, sc.gx, sc.gy, sc.gz, c, dg);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // sample_sdf_grad (voxurff.py:670-676): finite-difference SDF gradient from the 6 axis taps at 1 voxel, in
 // world units and (x, y, z) order — the inference path turns it into the normal map (voxurff.py:421-430).
 // ---------------------------------------------------------------------------------------------
@@ -1307,6 +1355,34 @@ extern "C" int esr_neus_cos_bwd(const esr_scene_t *sc, const float *rays_o, cons
   ESR_STAGE("k_neus_cos_bwd", stream);
   k_neus_cos_bwd<<<cdiv(m1, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, viewdirs, s_ray,
                                                                                   s_step, d_cos, m1, grad_sdf_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_neus_cos_vol_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                                   const float *grad_vol, const int32_t *s_ray, const int32_t *s_step, int64_t m1,
+                                   float *s_cos, esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(m1 >= 0);
+  if (m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && viewdirs && grad_vol && s_ray && s_step && s_cos);
+  ESR_STAGE("k_neus_cos_vol_fwd", stream);
+  k_neus_cos_vol_fwd<<<cdiv(m1, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, viewdirs,
+                                                                                      grad_vol, s_ray, s_step, m1, s_cos);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}
+
+extern "C" int esr_neus_cos_vol_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                                   const int32_t *s_ray, const int32_t *s_step, const float *d_cos, int64_t m1,
+                                   float *g_grad_vol, esr_stream_t stream) {
+  if (int e = check_scene2(sc)) return e;
+  ESR_CHECK_ARG(m1 >= 0);
+  if (m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && viewdirs && s_ray && s_step && d_cos && g_grad_vol);
+  ESR_STAGE("k_neus_cos_vol_bwd", stream);
+  k_neus_cos_vol_bwd<<<cdiv(m1, ENC_THREADS), ENC_THREADS, 0, (cudaStream_t)stream>>>(*sc, rays_o, rays_d, viewdirs, s_ray,
+                                                                                      s_step, d_cos, m1, g_grad_vol);
   ESR_LAUNCH_OK();
   return ESR_OK;
 }

@@ -586,3 +586,26 @@ extern "C" int esr_neus_alpha_bwd(const esr_scene_t *sc, const float *rays_o, co
   ESR_LAUNCH_OK();
   return ESR_OK;
 }
+
+// 'grad' alpha with dL/dalpha given directly on the M1 stream (the coarse stage, see esr_neus_alpha_bwd): dL/dsdf of
+// every sample is scattered into grad_sdf_grid, dL/diter_cos is left in tmp_dcos[M1] for esr_neus_cos_vol_bwd
+extern "C" int esr_neus_alpha_bwd_g(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                                    int64_t n_rays, const int32_t *off_mask, const int32_t *s_ray, const int32_t *s_step,
+                                    const float *s_sdf, const float *s_cos, const float *g_alpha_m1, float *tmp_dsdf,
+                                    float *tmp_dcos, int64_t m1, float *grad_sdf_grid, esr_stream_t stream) {
+  if (int e = check_scene(sc)) return e;
+  ESR_CHECK_ARG(n_rays >= 0 && m1 >= 0 && m1 < (1ll << 31));
+  if (n_rays == 0 || m1 == 0) return ESR_OK;
+  ESR_CHECK_ARG(rays_o && rays_d && off_mask && s_ray && s_step && s_sdf && s_cos && g_alpha_m1 && tmp_dsdf && tmp_dcos &&
+                grad_sdf_grid);
+  cudaStream_t st = (cudaStream_t)stream;
+  ESR_STAGE("k_neus_alpha_bwd", st);
+  k_alpha_scan_bwd<true><<<ray_blocks(n_rays), 256, 0, st>>>(*sc, ray_order, n_rays, off_mask, s_sdf, s_cos, nullptr, nullptr,
+                                                             nullptr, nullptr, nullptr, g_alpha_m1, tmp_dsdf, tmp_dcos);
+  ESR_LAUNCH_OK();
+  ESR_STAGE("k_sdf_scatter", st);
+  k_sdf_scatter<true><<<cdiv(m1, 256), 256, 0, st>>>(*sc, rays_o, rays_d, s_ray, s_step, tmp_dsdf, tmp_dcos, m1,
+                                                     grad_sdf_grid);
+  ESR_LAUNCH_OK();
+  return ESR_OK;
+}

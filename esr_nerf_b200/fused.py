@@ -639,15 +639,27 @@ class CoarseAlpha(torch.autograd.Function):
     the weights on the survivors (voxurfc.py:219) — done by the caller with the reference-shaped Alphas2Weights."""
 
     @staticmethod
-    def forward(ctx, sdf_grid, sc: Scene, rays_o, rays_d, streams: Streams):
+    def forward(ctx, sdf_grid, sc: Scene, rays_o, rays_d, streams: Streams, grad_vol=None, viewdirs=None):
+        """grad_vol + viewdirs given = `neus_alpha: grad` (voxurfc.py:171-174): the section-point SDFs from the view-projected
+        trilinear tap of the central-difference volume grad_vol [1,3,X,Y,Z] (voxurfc.py:204-210)"""
         L = _lib.lib()
         dev = rays_o.device
         n, st, scp = streams.n_rays, stream_ptr(), ctypes.byref(sc)
         cnt_shade = _i32(n, dev)
         last = _f32(n, dev=dev)
         streams.s_alpha, streams.s_T = _f32(streams.m1, dev=dev), _f32(streams.m1, dev=dev)
-        check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
-                                     ptr(cnt_shade), ptr(last), ptr(streams.s_alpha), ptr(streams.s_T), st))
+        if grad_vol is not None:
+            grad_vol, streams.viewdirs = grad_vol.contiguous(), viewdirs.contiguous()
+            streams.s_cos = _f32(streams.m1, dev=dev)
+            check(L.esr_neus_cos_vol_fwd(scp, ptr(rays_o), ptr(rays_d), ptr(streams.viewdirs), ptr(grad_vol),
+                                         ptr(streams.s_ray), ptr(streams.s_step), streams.m1, ptr(streams.s_cos), st))
+            check(L.esr_alpha_scan_count_g(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
+                                           ptr(streams.s_cos), ptr(cnt_shade), ptr(last), ptr(streams.s_alpha),
+                                           ptr(streams.s_T), st))
+        else:
+            check(L.esr_alpha_scan_count(scp, ptr(streams.ray_order), n, ptr(streams.off_mask), ptr(streams.s_sdf),
+                                         ptr(cnt_shade), ptr(last), ptr(streams.s_alpha), ptr(streams.s_T), st))
+        ctx.grad_mode = grad_vol is not None
         off_shade = exclusive_scan(cnt_shade)
         m3 = int(off_shade[n].item())
         streams.off_shade, streams.m3, streams.m3_on = off_shade, m3, m3
@@ -660,6 +672,7 @@ class CoarseAlpha(torch.autograd.Function):
                                     ptr(streams.h_sdf), st))
         h_alpha = streams.s_alpha[streams.h_m1.long()] if m3 else _f32(0, dev=dev)
         ctx.sc, ctx.streams = sc, streams
+        ctx.vol_shape = None if grad_vol is None else tuple(grad_vol.shape)
         ctx.save_for_backward(rays_o, rays_d, sdf_grid)
         return h_alpha
 
@@ -670,15 +683,24 @@ class CoarseAlpha(torch.autograd.Function):
         s: Streams = ctx.streams
         dev = rays_o.device
         grad_sdf = torch.zeros_like(sdf_grid)
+        g_vol = torch.zeros(ctx.vol_shape, dtype=torch.float32, device=dev) if ctx.grad_mode else None
         if s.m1 == 0 or s.m3 == 0:
-            return grad_sdf, None, None, None, None
+            return grad_sdf, None, None, None, None, g_vol, None
         g_m1 = torch.zeros(s.m1, dtype=torch.float32, device=dev)
         g_m1.index_copy_(0, s.h_m1.long(), g_alpha.contiguous())
         tmp_p, tmp_n = _f32(s.m1, dev=dev), _f32(s.m1, dev=dev)
+        if ctx.grad_mode:                     # tmp_p = dL/dsdf (scattered into grad_sdf), tmp_n = dL/diter_cos -> g_vol
+            L = _lib.lib()
+            check(L.esr_neus_alpha_bwd_g(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.ray_order), s.n_rays,
+                                         ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(s.s_cos), ptr(g_m1),
+                                         ptr(tmp_p), ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
+            check(L.esr_neus_cos_vol_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.viewdirs), ptr(s.s_ray),
+                                         ptr(s.s_step), ptr(tmp_n), s.m1, ptr(g_vol), stream_ptr()))
+            return grad_sdf, None, None, None, None, g_vol, None
         check(_lib.lib().esr_neus_alpha_bwd(ctypes.byref(ctx.sc), ptr(rays_o), ptr(rays_d), ptr(s.ray_order), s.n_rays,
                                             ptr(s.off_mask), ptr(s.s_ray), ptr(s.s_step), ptr(s.s_sdf), ptr(g_m1),
                                             ptr(tmp_p), ptr(tmp_n), s.m1, ptr(grad_sdf), stream_ptr()))
-        return grad_sdf, None, None, None, None
+        return grad_sdf, None, None, None, None, None, None
 
 
 class EncodeCoarse(torch.autograd.Function):

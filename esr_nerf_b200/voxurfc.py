@@ -65,9 +65,10 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
         for k in ("mask_ks", "maskcache_thres", "fastcolor_thres", "stepsize", "num_voxels", "color_dim", "rgbnet_width",
                   "rgbnet_depth", "posbase_pe", "viewbase_pe", "smooth_ksize", "smooth_sigma", "neus_alpha"):
             setattr(self, k, cfg_get(cfg, m + k))
-        if not (self.color_dim == 12 and self.posbase_pe == 5 and self.viewbase_pe == 1 and self.neus_alpha == "interp"):
+        if not (self.color_dim == 12 and self.posbase_pe == 5 and self.viewbase_pe == 1 and
+                self.neus_alpha in ("interp", "grad")):
             raise NotImplementedError("libesr_b200 instantiates the shipped coarse-stage shape only "
-                                      "(cfg/app/coarse.yaml:13-31): color_dim 12, PE 5/1, neus_alpha interp")
+                                      "(cfg/app/coarse.yaml:13-31): color_dim 12, PE 5/1, neus_alpha interp | grad")
         self.voxel_size, self.world_size = voxel_geometry(self.xyz_min, self.xyz_max, self.num_voxels)
         ws = self.world_size
         self.sdf = DenseGrid(1, ws, self.xyz_min, self.xyz_max)
@@ -156,7 +157,9 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
             sdf_grid = self.smooth_conv(self.sdf.grid).contiguous()                      # voxurfc.py:202
             self.gradient = self.neus_sdf_gradient()                                     # voxurfc.py:205
             s = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, sdf_grid.detach())
-            h_alpha = fused.CoarseAlpha.apply(sdf_grid, sc, rays_o, rays_d, s)           # voxurfc.py:208-218
+            grad_mode = self.neus_alpha == "grad"                                        # voxurfc.py:171-174
+            h_alpha = fused.CoarseAlpha.apply(sdf_grid, sc, rays_o, rays_d, s, self.gradient if grad_mode else None,
+                                              viewdirs if grad_mode else None)           # voxurfc.py:208-218
             ray_id = s.h_ray.long()
             weights, last = Alphas2Weights.apply(h_alpha, ray_id, N)                     # voxurfc.py:219
             x = fused.EncodeCoarse.apply(self.gradient, self.off_color.grid, self.emo_color.grid, sc, rays_o, rays_d,
@@ -186,7 +189,9 @@ class VoxurfC(GridRegularizers, RayUtilities, nn.Module):
             sdf_grid = self.smooth_conv(self.sdf.grid).contiguous()
             self.gradient = self.neus_sdf_gradient()
             s = fused.march(sc, rays_o, rays_d, None, self.mask_cache.density, sdf_grid)
-            h_alpha = fused.CoarseAlpha.apply(sdf_grid, sc, rays_o, rays_d, s)
+            grad_mode = self.neus_alpha == "grad"
+            h_alpha = fused.CoarseAlpha.apply(sdf_grid, sc, rays_o, rays_d, s, self.gradient if grad_mode else None,
+                                              viewdirs if grad_mode else None)
             if s.m3 <= 1:                                                              # voxurfc.py:322-335
                 z3 = torch.zeros_like(rays_o)
                 return {"etc/depth": z3[..., 0], "etc/disp": 1 / (z3[..., 0] + self.far), "etc/normal": z3,

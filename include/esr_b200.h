@@ -251,6 +251,23 @@ int esr_alpha_scan_bwd_g(const esr_scene_t *sc, const float *rays_o, const float
                          const float *alphainv_last, const float *g_w_m1, const float *g_last, float *tmp_dsdf,
                          float *tmp_dcos, int64_t m1, float *grad_sdf_grid, esr_stream_t stream);
 /*
+ * The same mode in the coarse stage (voxurfc.py:171-174, 204-210), where the SDF gradient of a sample is the trilinear
+ * tap of the dense central-difference volume grad_vol ([3][X][Y][Z] f32, channels d/dx, d/dy, d/dz — esr_sdf_central_gradient):
+ *   esr_neus_cos_vol_fwd: s_cos[M1] from grad_vol;  esr_neus_cos_vol_bwd: scatter-adds d_cos[M1] into g_grad_vol
+ *   esr_neus_alpha_bwd_g: esr_neus_alpha_bwd (dL/dalpha given on the M1 stream) for alphas computed from (s_sdf, s_cos):
+ *                         dL/dsdf scattered into grad_sdf_grid, dL/diter_cos left in tmp_dcos[M1]
+ */
+int esr_neus_cos_vol_fwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                         const float *grad_vol, const int32_t *s_ray, const int32_t *s_step, int64_t m1, float *s_cos,
+                         esr_stream_t stream);
+int esr_neus_cos_vol_bwd(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const float *viewdirs,
+                         const int32_t *s_ray, const int32_t *s_step, const float *d_cos, int64_t m1, float *g_grad_vol,
+                         esr_stream_t stream);
+int esr_neus_alpha_bwd_g(const esr_scene_t *sc, const float *rays_o, const float *rays_d, const int32_t *ray_order,
+                         int64_t n_rays, const int32_t *off_mask, const int32_t *s_ray, const int32_t *s_step,
+                         const float *s_sdf, const float *s_cos, const float *g_alpha_m1, float *tmp_dsdf,
+                         float *tmp_dcos, int64_t m1, float *grad_sdf_grid, esr_stream_t stream);
+/*
  * Same backward with dL/dalpha given directly on the M1 stream (g_alpha_m1) instead of going through the
  * Alphas2Weights recurrence: the coarse stage recomputes the weights on the shaded samples with the reference-shaped
  * esr_alpha2weight_* ops (voxurfc.py:211-219), so only the NeuS alpha -> sdf part is needed here.

@@ -111,14 +111,15 @@ COARSE_CASES = {
 }
 
 
-def coarse_cfg(num_voxels):
-    return H.DictConfig(dict(system=dict(device="cpu"), app=dict(model=dict(S.COARSE_MODEL_CFG, num_voxels=num_voxels))))
+def coarse_cfg(num_voxels, **over):
+    return H.DictConfig(dict(system=dict(device="cpu"),
+                             app=dict(model=dict(S.COARSE_MODEL_CFG, num_voxels=num_voxels, **over))))
 
 
-def build_reference_coarse(num_voxels, mask_res, sparse, s_val, weights=None):
+def build_reference_coarse(num_voxels, mask_res, sparse, s_val, weights=None, **cfg_over):
     _, VoxurfC, _, _ = H.reference_classes()
     torch.manual_seed(0)
-    m = VoxurfC(coarse_cfg(num_voxels), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
+    m = VoxurfC(coarse_cfg(num_voxels, **cfg_over), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
                 S.mask_density(mask_res, sparse), s_val)
     if weights is not None:
         m.load_state_dict({**m.state_dict(), **weights})

@@ -42,6 +42,14 @@ def neus_sdf_gradient(sdf_grid: torch.Tensor, voxel_size: float) -> torch.Tensor
     return g
 
 
+def _alpha(scene, viewdirs, ray_id, sdf, gradient, s_val):
+    """self.neus_alpha_from_sdf_scatter (voxurfc.py:171-174): 'interp', or 'grad' with the trilinear tap of the
+    central-difference volume as the SDF gradient (voxurfc.py:204-210) and dist = stepsize * voxel_size"""
+    if scene.get("neus_alpha", "interp") == "grad":
+        return P.neus_alpha_grad(viewdirs, ray_id, torch.tensor(scene["stepdist"], dtype=torch.float32), sdf, gradient, s_val)
+    return P.neus_alpha_interp(ray_id, sdf, s_val)
+
+
 def voxurfc_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs, em_modes, s_val: float):
     N = rays_o.shape[0]
     ray_pts, ray_id, step_id, aux = P._march(scene, rays_o, rays_d)
@@ -55,7 +63,7 @@ def voxurfc_forward_training(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     sdf = P.grid_sample_world(sdf_grid, ray_pts, scene["xyz_min"], scene["xyz_max"])[:, 0]
     grad_vol = neus_sdf_gradient(params["sdf"], scene["voxel_size"])                    # voxurfc.py:205
     gradient = P.grid_sample_world(grad_vol, ray_pts, scene["xyz_min"], scene["xyz_max"])
-    alpha = P.neus_alpha_interp(ray_id, sdf, s_val)
+    alpha = _alpha(scene, viewdirs, ray_id, sdf, gradient, s_val)
     inter.update(m1_sdf=sdf, m1_alpha=alpha)
     weights, _ = P._A2W.apply(alpha, ray_id, N)                                         # voxurfc.py:211
     k1 = weights > scene["fast_thres"]
@@ -98,7 +106,7 @@ def voxurfc_forward_evaluate(scene: Dict, params: Dict, rays_o, rays_d, viewdirs
     sdf = P.grid_sample_world(sdf_grid, ray_pts, scene["xyz_min"], scene["xyz_max"])[:, 0]
     gradient = P.grid_sample_world(neus_sdf_gradient(params["sdf"], scene["voxel_size"]), ray_pts, scene["xyz_min"],
                                    scene["xyz_max"])
-    alpha = P.neus_alpha_interp(ray_id, sdf, s_val)
+    alpha = _alpha(scene, viewdirs, ray_id, sdf, gradient, s_val)
     weights = H.alpha2weight(alpha, ray_id, N)[0]
     k1 = weights > scene["fast_thres"]
     ray_pts, ray_id, step_id, alpha, gradient = ray_pts[k1], ray_id[k1], step_id[k1], alpha[k1], gradient[k1]

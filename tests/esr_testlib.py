@@ -144,10 +144,10 @@ def coarse_oracle_params(scene, weights, requires_grad=True):
     return PC.params_from_state_dict(leaves), leaves
 
 
-def build_product_coarse(fx, weights, device="cuda:0"):
+def build_product_coarse(fx, weights, device="cuda:0", **cfg_over):
     from esr_nerf_b200.voxurfc import VoxurfC
 
-    cfg = S.coarse_cfg(device=device, num_voxels=int(fx["num_voxels"]))
+    cfg = S.coarse_cfg(device=device, num_voxels=int(fx["num_voxels"]), **cfg_over)
     m = VoxurfC(cfg, S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX, S.MASK_ALPHA_INIT,
                 S.mask_density(int(fx["mask_res"]), bool(fx["sparse"])), float(fx["s_val"]))
     m.load_state_dict({**m.state_dict(), **weights})

@@ -176,3 +176,98 @@ def test_esrnerf_grad_alpha_vs_oracle_port():
         checked += 1
     assert not bad, bad
     assert checked >= 40
+
+
+# ---------------------------------------------------------------------------------------------------
+# coarse stage: the SDF gradient is the trilinear tap of the central-difference volume (voxurfc.py:204-210)
+# ---------------------------------------------------------------------------------------------------
+COARSE_KEYS = ("etc/alphainv_cum", "etc/white_bg", "srgb/rgb")
+
+
+def _coarse_oracle(fx, weights, rays, only=None):
+    from oracle import voxurfc_port as PC
+
+    scene = C.coarse_oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    scene["neus_alpha"] = "grad"
+    params, leaves = C.coarse_oracle_params(scene, weights)
+    ref, inter = PC.voxurfc_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                             rays["em_modes"], float(fx["s_val"]))
+    cot = C.coarse_cotangents(rays["rays_o"].shape[0])
+    sum((ref[k] * cot[k]).sum() for k in cot if only is None or k == only).backward()
+    return ref, inter, leaves
+
+
+def _coarse_product(fx, weights, rays, mode, only=None):
+    m = C.build_product_coarse(fx, weights, DEV, neus_alpha="grad")
+    m.mlp_mode, m.keep_streams = mode, True
+    out = m(s_val=float(fx["s_val"]), **{k: v.to(DEV) for k, v in rays.items()})
+    cot = C.coarse_cotangents(rays["rays_o"].shape[0])
+    sum((out[k] * cot[k].to(DEV)).sum() for k in cot if only is None or k == only).backward()
+    return m, out
+
+
+@pytest.mark.parametrize("mode", ["torch_fp32", "x2"])
+def test_voxurfc_grad_alpha_vs_oracle_port(mode):
+    fx, weights = C.load_coarse_case("coarse_sparse_s5")
+    rays = S.make_rays(1024, 515)
+    ref, inter, leaves = _coarse_oracle(fx, weights, rays)
+    m, out = _coarse_product(fx, weights, rays, mode)
+    st = m.last_streams["streams"]
+    assert st.s_cos is not None and st.m3 > 2000
+    assert torch.equal(st.s_ray.long().cpu(), inter["m1_ray"]) and torch.equal(st.s_step.long().cpu(), inter["m1_step"])
+    assert C.rel_err(st.s_alpha, inter["m1_alpha"]) < 1e-5
+    assert torch.equal(st.h_ray.long().cpu(), inter["m3_ray"]) and torch.equal(st.h_step.long().cpu(), inter["m3_step"])
+    assert C.rel_err(m.last_streams["h_w"], inter["m3_weights"]) < 1e-4
+    for k in COARSE_KEYS:
+        assert C.rel_err(out[k], ref[k]) < 1e-4, k
+    bad, checked = {}, 0
+    for name, p in m.named_parameters():
+        if name not in leaves or leaves[name].grad is None:
+            continue
+        if mode == "x2":
+            ok, msg = C.grad_close(p.grad.contiguous(), leaves[name].grad, 1e-2, l2_factor=1.0)
+        else:       # grids 1e-4; fp32 library GEMMs vs the CPU port on ~10^4 rows: 1e-3 on the nets (see above)
+            ok, msg = C.grad_close(p.grad.contiguous(), leaves[name].grad, 1e-3 if "rgbnet" in name else 1e-4)
+        if not ok:
+            bad[name] = msg
+        checked += 1
+    assert not bad, bad
+    assert checked == 3 + 6 + 6
+
+
+def test_voxurfc_grad_alpha_sdf_gradient_alone():
+    """cotangent on alphainv_last only: all gradient reaches the raw SDF grid through the alpha path — dL/dsdf through the
+    smoothing convolution, dL/diter_cos through the central-difference volume"""
+    fx, weights = C.load_coarse_case("coarse_sparse_s5")
+    rays = S.make_rays(512, 516)
+    ref, _, leaves = _coarse_oracle(fx, weights, rays, only="etc/alphainv_cum")
+    m, out = _coarse_product(fx, weights, rays, "x2", only="etc/alphainv_cum")
+    assert C.rel_err(out["etc/alphainv_cum"], ref["etc/alphainv_cum"]) < 1e-4
+    r = leaves["sdf.grid"].grad
+    assert r.abs().max() > 0
+    mx, l2 = C.grad_err(m.sdf.grid.grad, r)
+    assert mx < 1e-4 and l2 < 1e-4, (mx, l2)
+
+
+def test_voxurfc_grad_alpha_inference_vs_oracle_port():
+    from oracle import voxurfc_port as PC
+
+    fx, weights = C.load_coarse_case("coarse_dense_s25")
+    rays = S.make_rays(400, 78)
+    pos_rt = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(3)))[0]
+    scene = C.coarse_oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    scene["neus_alpha"] = "grad"
+    params, _ = C.coarse_oracle_params(scene, weights, requires_grad=False)
+    with torch.no_grad():
+        ref, inter = PC.voxurfc_forward_evaluate(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                                 torch.tensor(1), pos_rt, float(fx["s_val"]))
+    m = C.build_product_coarse(fx, weights, DEV, neus_alpha="grad")
+    m.mlp_mode, m.keep_streams = "torch_fp32", True
+    m.eval()
+    out = m(rays_o=rays["rays_o"].to(DEV), rays_d=rays["rays_d"].to(DEV), viewdirs=rays["viewdirs"].to(DEV),
+            em_modes=torch.tensor(1), pos_rt=pos_rt.to(DEV))
+    assert set(out) == set(ref)
+    st = m.last_streams["streams"]
+    assert torch.equal(st.h_ray.long().cpu(), inter["m3_ray"]) and torch.equal(st.h_step.long().cpu(), inter["m3_step"])
+    for k in ref:
+        assert C.rel_err(out[k], ref[k]) < 1e-4, (k, C.rel_err(out[k], ref[k]))

@@ -261,6 +261,53 @@ def test_coarse_port_matches_reference():
             assert C.rel_err(leaf.grad, ref_grads[name].grad) < 1e-5, name
 
 
+def test_coarse_port_matches_reference_neus_alpha_grad():
+    """`neus_alpha: grad` in the coarse stage (voxurfc.py:171-174, 204-210): the SDF gradient is the trilinear tap of the
+    central-difference volume of the RAW sdf grid — the port against the reference's own VoxurfC built with the option,
+    training step (outputs + every gradient) and inference maps."""
+    from oracle import ref_harness as H
+
+    if not H.reference_available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from esr_nerf_b200 import synthetic as S
+    from oracle import voxurfc_port as PC
+    from oracle.make_golden import build_reference_coarse
+
+    fx, weights = C.load_coarse_case("coarse_sparse_s5")
+    s_val = 5.0
+    ref = build_reference_coarse(int(fx["num_voxels"]), int(fx["mask_res"]), True, s_val, weights, neus_alpha="grad")
+    rays = S.make_rays(200, 4243)
+    ref_out = ref(s_val=s_val, **rays)
+    scene = C.coarse_oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), True)
+    scene["neus_alpha"] = "grad"
+    params, leaves = C.coarse_oracle_params(scene, weights)
+    out, inter = PC.voxurfc_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                             rays["em_modes"], s_val)
+    a_interp = PC.P.neus_alpha_interp(inter["m1_ray"], inter["m1_sdf"].detach(), s_val)
+    assert (a_interp - inter["m1_alpha"].detach()).abs().max() > 1e-3
+    cot = C.coarse_cotangents(200)
+    sum((ref_out[k] * cot[k]).sum() for k in cot).backward()
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    assert set(out) == set(ref_out)
+    for k in ref_out:
+        assert C.rel_err(out[k], ref_out[k]) < 1e-6, k
+    ref_grads = dict(ref.named_parameters())
+    for name, leaf in leaves.items():
+        if name in ref_grads and ref_grads[name].grad is not None:
+            assert C.rel_err(leaf.grad, ref_grads[name].grad) < 1e-5, name
+    ref.eval()
+    ev = S.make_rays(64, 5)
+    pos_rt = torch.linalg.qr(torch.randn(3, 3, generator=torch.Generator().manual_seed(3)))[0]
+    params0, _ = C.coarse_oracle_params(scene, weights, requires_grad=False)
+    with torch.no_grad():
+        r = ref(rays_o=ev["rays_o"], rays_d=ev["rays_d"], viewdirs=ev["viewdirs"], em_modes=torch.tensor(1), pos_rt=pos_rt)
+        o, _ = PC.voxurfc_forward_evaluate(scene, params0, ev["rays_o"], ev["rays_d"], ev["viewdirs"], torch.tensor(1),
+                                           pos_rt, s_val)
+    assert set(o) == set(r)
+    for k in o:
+        assert C.rel_err(o[k], r[k]) < 1e-5, k
+
+
 def test_coarse_eval_port_matches_reference():
     from oracle import ref_harness as H
 
