@@ -83,3 +83,20 @@ def test_ctypes_prototypes_agree_with_the_header_signatures():
             assert c_class(d) == py_class(t), (name, i, d, t)
         seen += 1
     assert seen == len(_lib.PROTOTYPES)
+
+
+def test_training_step_example_compiles_and_links(tmp_path):
+    """tests/chost/train_step_example.c — INTEGRATION.md's non-Python training step (esr_render_voxurff_fwd / _bwd, the
+    capacity protocol, esr_adam_step) as a complete C99 translation unit: must compile warning-free and resolve every
+    symbol against the library (not run: no device here)"""
+    from esr_nerf_b200 import _lib
+
+    so = _lib.build()
+    obj, lib = str(tmp_path / "tse.o"), str(tmp_path / "libtse.so")
+    src = os.path.join(ROOT, "tests", "chost", "train_step_example.c")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                    "-c", src, "-o", obj], check=True)
+    subprocess.run(["gcc", "-shared", "-o", lib, obj, "-L", os.path.dirname(so), "-lesr_b200", "-Wl,--no-undefined",
+                    "-Wl,-rpath," + os.path.dirname(so)], check=True)
+    h = ctypes.CDLL(lib)
+    assert hasattr(h, "host_train_step") and hasattr(h, "host_workspace_bytes")
