@@ -100,3 +100,45 @@ def test_training_step_example_compiles_and_links(tmp_path):
                     "-Wl,-rpath," + os.path.dirname(so)], check=True)
     h = ctypes.CDLL(lib)
     assert hasattr(h, "host_train_step") and hasattr(h, "host_workspace_bytes")
+
+
+def test_shipped_library_is_current_and_blackwell_native():
+    """the in-tree libesr_b200.so (it travels to the GPU box as built here) is newer than every source it is built from,
+    is sm_100a code only, and its contraction kernels really are tcgen05 / TMEM / bulk-copy code: UTCHMMA (tcgen05.mma),
+    LDTM / STTM (tcgen05.ld / st), UTCBAR (tcgen05.commit), UBLKCP (cp.async.bulk) in the SASS of the MLP chain kernels —
+    no mma.sync (HMMA) anywhere (scripts/sass_summary.py writes the per-kernel table under profiles/)"""
+    import re
+    import shutil
+
+    import pytest
+
+    from esr_nerf_b200 import _lib
+
+    so = _lib.build()
+    newest = max(os.path.getmtime(os.path.join(_lib.CSRC, f)) for f in list(_lib.SOURCES) + list(_lib.HEADERS))
+    assert os.path.getmtime(so) >= newest
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    elf = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", elf))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = set()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            per_kernel[cur].add(m.group(1))
+    assert len(per_kernel) > 90
+    assert not any("HMMA" in ops and "UTCHMMA" not in ops for ops in per_kernel.values())      # no mma.sync kernels
+    assert not any(op in ("HMMA", "IMMA", "HGMMA") for ops in per_kernel.values() for op in ops)
+    chains = {k: ops for k, ops in per_kernel.items() if re.search(r"k_mlp_(fwd|dgrad|wgrad)|k_tonemap_(fwd2|bwd_fused)", k)}
+    assert len(chains) >= 30
+    for k, ops in chains.items():
+        assert {"UTCHMMA", "LDTM", "UTCBAR"} <= ops, (k, sorted(ops & {"UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP"}))
+    assert any("UBLKCP" in ops for k, ops in chains.items() if "wgrad" in k)
+    assert any("STTM" in ops for k, ops in chains.items() if "k_mlp_fwd" in k)
