@@ -30,6 +30,9 @@ CASES = {
     "fine_dense_s220": (40 ** 3, 20, False, 128, 220.0, 4321),
     "fine_sparse_s60_big": (64 ** 3, 32, True, 192, 60.0, 99),
 }
+# `neus_alpha: grad` (functions.py:45-69): the reference's VoxurfF built with that option, on the rays the GPU test of the
+# mode uses (tests/test_gpu_neus_grad.py); written by `python -m oracle.make_golden --neus-grad-only` (fine_weights.npz as is)
+GRAD_ALPHA_CASES = {"fine_grad_sparse_s60_big": (64 ** 3, 32, True, 1536, 60.0, 4711)}
 GRAD_PROBES = 4096
 
 
@@ -70,9 +73,9 @@ def grad_digest(name, g: torch.Tensor):
             f"grad/{name}/idx": idx.numpy().astype(np.int64), f"grad/{name}/val": flat[idx].float().numpy()}
 
 
-def run_case(name, spec, weights):
+def run_case(name, spec, weights, **model_overrides):
     num_voxels, mask_res, sparse, n, s_val, seed = spec
-    m = build_reference_model(num_voxels, mask_res, sparse, s_val, weights)
+    m = build_reference_model(num_voxels, mask_res, sparse, s_val, weights, **model_overrides)
     rays = S.make_rays(n, seed)
     # instrument the stream: re-run the same calls the reference forward makes (voxurff.py:186-213)
     with torch.no_grad():
@@ -80,8 +83,8 @@ def run_case(name, spec, weights):
         m0 = ray_pts.shape[0]
         keep = m.mask_cache(ray_pts)
         ray_pts, ray_id, step_id = ray_pts[keep], ray_id[keep], step_id[keep]
-        sdf, _ = m.sample_sdf_grad(ray_pts)
-        alpha = m.neus_alpha_from_sdf_scatter(rays["viewdirs"], ray_id, None, sdf, None, s_val)
+        sdf, grad = m.sample_sdf_grad(ray_pts)
+        alpha = m.neus_alpha_from_sdf_scatter(rays["viewdirs"], ray_id, m.stepsize * m.voxel_size, sdf, grad, s_val)
         k0 = alpha > m.fastcolor_thres
         w, T, last, _, _ = H.alpha2weight(alpha[k0], ray_id[k0], n)
         k1 = w > m.fastcolor_thres
@@ -342,6 +345,11 @@ def main():
         raise SystemExit("reference tree not available; golden vectors can only be generated in the build container")
     os.makedirs(GOLDEN, exist_ok=True)
     wpath = os.path.join(GOLDEN, "fine_weights.npz")
+    if "--neus-grad-only" in sys.argv:      # adds the grad-alpha fixtures next to the existing ones (same net weights)
+        weights = {k: torch.from_numpy(v) for k, v in np.load(wpath).items()}
+        for name, spec in GRAD_ALPHA_CASES.items():
+            run_case(name, spec, weights, neus_alpha="grad")
+        return
     m = build_reference_model(40 ** 3, 20, True, 20.0)
     sd = m.state_dict()
     weights = {k: sd[k].clone() for k in mlp_weight_keys(sd)}
@@ -353,6 +361,9 @@ def main():
     np.savez_compressed(wpath, **{k: v.numpy() for k, v in weights.items()})
     if "--dvgo-only" in sys.argv:
         return main_dvgo()
+    if "--coarse-only" not in sys.argv:
+        for name, spec in GRAD_ALPHA_CASES.items():
+            run_case(name, spec, weights, neus_alpha="grad")
     if "--coarse-only" not in sys.argv:
         for name, spec in CASES.items():
             run_case(name, spec, weights)

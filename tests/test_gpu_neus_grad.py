@@ -86,6 +86,27 @@ def test_voxurff_grad_alpha_vs_oracle_port(mode):
     assert checked >= 3 + 8 + 8 + 4
 
 
+def test_voxurff_grad_alpha_vs_golden():
+    """the same step against the fixture made by the reference's own VoxurfF built with `neus_alpha: grad`
+    (tests/golden/voxurff_fine_grad_sparse_s60_big.npz, oracle/make_golden.py --neus-grad-only): M1 / M3 streams bit-exact,
+    alphas, weights and rendered outputs; its gradient digests are held against the port on the CPU
+    (tests/test_oracle_cpu.py::test_port_matches_golden_neus_alpha_grad), the kernels against the port above"""
+    import numpy as np
+
+    fx, weights = C.load_case("fine_grad_sparse_s60_big")
+    rays = S.make_rays(int(fx["n_rays"]), int(fx["ray_seed"]))
+    m, out = _fine_product(fx, weights, "x2", rays)
+    st = m.last_streams["streams"]
+    o1 = torch.argsort(st.s_ray.long().cpu() * (1 << 20) + st.s_step.long().cpu(), stable=True)
+    assert np.array_equal(st.s_ray.cpu()[o1].numpy(), fx["m1_ray"]) and np.array_equal(st.s_step.cpu()[o1].numpy(), fx["m1_step"])
+    assert C.rel_err(st.s_alpha.cpu()[o1], torch.from_numpy(fx["m1_alpha"])) < 1e-5
+    o3 = torch.argsort(st.h_ray.long().cpu() * (1 << 20) + st.h_step.long().cpu(), stable=True)
+    assert np.array_equal(st.h_ray.cpu()[o3].numpy(), fx["m3_ray"]) and np.array_equal(st.h_step.cpu()[o3].numpy(), fx["m3_step"])
+    assert C.rel_err(m.last_streams["h_w"].cpu()[o3], torch.from_numpy(fx["m3_weights"])) < 1e-4
+    for k in OUT_KEYS:
+        assert C.rel_err(out[k], torch.from_numpy(fx["out/" + k])) < 1e-4, k
+
+
 def test_voxurff_grad_alpha_sdf_gradient_alone():
     """only alphainv_last carries a cotangent: every bit of gradient reaches the SDF grid through the alpha path — the
     dL/dsdf scatter plus the six-tap scatter of dL/diter_cos — with no shading term to hide an error in it"""

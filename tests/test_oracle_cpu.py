@@ -64,11 +64,12 @@ def test_c_oracle_alpha2weight_semantics():
 # ---------------------------------------------------------------------------------------------
 # torch port vs golden vectors (made by the reference's own code) and vs the reference itself
 # ---------------------------------------------------------------------------------------------
-def _run_port(fx, weights):
+def _run_port(fx, weights, **scene_over):
     from esr_nerf_b200 import synthetic as S
     from oracle import voxurf_port as P
 
     scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), bool(fx["sparse"]))
+    scene.update(scene_over)
     params, leaves = C.oracle_params(scene, weights)
     rays = S.make_rays(int(fx["n_rays"]), int(fx["ray_seed"]))
     out, inter = P.voxurff_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
@@ -93,6 +94,28 @@ def test_port_matches_golden(case):
         if f"grad/{name}/idx" in fx and leaf.grad is not None:
             err, s_err = C.digest_check(fx, name, leaf.grad, rtol=1e-4)
             assert err < 1.0 and s_err < 1e-4, (name, err, s_err)
+
+
+def test_port_matches_golden_neus_alpha_grad():
+    """the `neus_alpha: grad` fixture (reference VoxurfF built with the option, oracle/make_golden.py --neus-grad-only):
+    travels to the GPU box, where the reference itself cannot be imported"""
+    fx, weights = C.load_case("fine_grad_sparse_s60_big")
+    out, inter, leaves, loss = _run_port(fx, weights, neus_alpha="grad")
+    assert inter["m0"] == int(fx["m0"])
+    for k in ("m1_ray", "m1_step", "m3_ray", "m3_step"):
+        assert np.array_equal(inter[k].numpy().astype(np.int32), fx[k]), k
+    assert np.abs(inter["m1_alpha"].detach().numpy() - fx["m1_alpha"]).max() < 1e-6
+    assert np.abs(inter["m3_weights"].detach().numpy() - fx["m3_weights"]).max() < 1e-6
+    for k in ("etc/alphainv_cum", "etc/white_bg", "srgb/rgb", "lin/rgb"):
+        assert C.rel_err(out[k], torch.from_numpy(fx["out/" + k])) < 1e-5, k
+    assert abs(loss.item() - float(fx["loss"])) < 1e-4 * abs(float(fx["loss"]))
+    checked = 0
+    for name, leaf in leaves.items():
+        if f"grad/{name}/idx" in fx and leaf.grad is not None:
+            err, s_err = C.digest_check(fx, name, leaf.grad, rtol=1e-4)
+            assert err < 1.0 and s_err < 1e-4, (name, err, s_err)
+            checked += 1
+    assert checked >= 3 + 8 + 8 + 4
 
 
 @pytest.mark.parametrize("case", C.CASES[:1])
