@@ -365,3 +365,41 @@ def test_sharded_image_render_gathers_every_map_on_rank0(n):
     for k in want:
         got = torch.from_numpy(res[0][k])
         assert got.shape == want[k].shape and torch.equal(got, want[k]), k
+
+
+@pytest.mark.parametrize("neus_alpha", ["interp", "grad"])
+def test_static_exchange_set_covers_the_gradients_of_both_alpha_modes(neus_alpha):
+    """GridGradCompactor exchanges only the voxels of the 5-voxel-dilated occupancy set; that is exact only if no gradient
+    falls outside it.  The oracle port's gradients on a sparse-shell scene (sdf + both colour grids) must all lie inside —
+    also with `neus_alpha: grad`, where EVERY MaskCache-kept sample (not only the shaded ones near the surface) scatters
+    into the SDF grid through taps one voxel away.  (The GPU test test_grid_gradient_compaction_is_exact checks the kernels'
+    gradients the same way in the default mode; bench.py's exchange_check compares against a dense all-reduce.)  Measured on
+    this scene: a dilation of 3 voxels is the smallest that covers everything in either mode, the default of 5 leaves 2."""
+    import esr_testlib as C
+    from esr_nerf_b200 import synthetic as S
+    from esr_nerf_b200.dist import GridGradCompactor
+    from esr_nerf_b200.voxurff import VoxurfF
+    from oracle import voxurf_port as P
+
+    fx, weights = C.load_case("fine_sparse_s60_big")
+    m = VoxurfF(S.fine_cfg("cpu", neus_alpha=neus_alpha), S.NEAR, S.FAR, S.BBOX_MIN, S.BBOX_MAX, S.BBOX_MIN, S.BBOX_MAX,
+                S.MASK_ALPHA_INIT, S.mask_density(int(fx["mask_res"]), True), float(fx["s_val"]), int(fx["num_voxels"]))
+    comp = GridGradCompactor(m)
+    assert 0.05 < comp.fraction < 0.6
+    scene = C.oracle_scene(int(fx["num_voxels"]), int(fx["mask_res"]), True)
+    scene["neus_alpha"] = neus_alpha
+    assert scene["world_size"] == list(comp.shape)
+    params, leaves = C.oracle_params(scene, weights)
+    rays = S.make_rays(3000, 8080)
+    out, inter = P.voxurff_forward_training(scene, params, rays["rays_o"], rays["rays_d"], rays["viewdirs"],
+                                            rays["em_modes"], float(fx["s_val"]))
+    cot = C.cotangents(3000)
+    sum((out[k] * cot[k]).sum() for k in cot).backward()
+    inside = comp.mask[0, 0]
+    for name in ("sdf.grid", "off_color.grid", "emo_color.grid"):
+        g = leaves[name].grad[0]                                  # [C, X, Y, Z]
+        touched = (g != 0).any(0)
+        assert int(touched.sum()) > 1000, name
+        assert not bool((touched & ~inside).any()), (name, int((touched & ~inside).sum()))
+    # the alpha path alone reaches further out than the shading path: all M1 samples, not just the shaded ones
+    assert inter["m1_ray"].numel() > 2 * inter["m3_ray"].numel()
